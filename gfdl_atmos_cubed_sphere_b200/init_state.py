@@ -1,0 +1,186 @@
+"""Idealised initial states for the hot-path harness (host-side fixture generator).
+
+* ``baroclinic_wave``: the Jablonowski-Williamson (2006) steady state + wind perturbation that
+  ``tools/test_cases.F90:1575-1890`` (test_case 12/13) initialises, evaluated pointwise from
+  the published analytic formulas at the D-grid edge mid-points / cell centres (the reference
+  additionally uses Gaussian quadrature along edges, ``test_cases.F90:1650-1700``; the
+  difference is O(dx^2) and irrelevant for oracle-vs-CUDA parity, which runs both from the
+  same arrays).  Dry, ``w`` = analytic perturbation of SURVEY 8(d), ``delz`` hydrostatic
+  (``init_hydro.F90`` ``p_var``: ``delz = -(rdgas/grav) T dln p``).
+* ``hybrid_levels``: a smooth hybrid sigma-p coordinate with ``npz`` layers.  The reference's
+  L79 table comes from the ``var_hi`` generator (``fv_eta.F90:656-666``), which is not restated
+  -- stated in DESIGN.md.
+* ``smooth_state``: cheap analytic fields for operator-level parity tests.
+
+All halos are filled with the 6-tile exchange of :mod:`cubed_sphere`.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import cubed_sphere as cs
+from .grid import latlon2xyz, CONSTANTS
+
+
+def hybrid_levels(npz, ptop=100.0, p0=1.0e5, eta_c=0.15, r=1.6):
+    """ak, bk (npz+1): log-stretched in pressure aloft, sigma-like near the surface."""
+    s = np.linspace(0.0, 1.0, npz + 1)
+    # blend log-spacing (top) with linear spacing (bottom) for well-resolved boundary layer
+    lo = np.log(ptop / p0)
+    eta = np.exp(lo * (1.0 - s) ** 1.4) * (1.0 - 0.35 * s * (1.0 - s))
+    eta[0], eta[-1] = ptop / p0, 1.0
+    eta = np.maximum.accumulate(eta)
+    bk = (np.maximum(eta - eta_c, 0.0) / (1.0 - eta_c)) ** r
+    ak = p0 * (eta - bk)
+    ak[0], bk[0] = ptop, 0.0
+    ak[-1], bk[-1] = 0.0, 1.0
+    assert np.all(np.diff(ak + bk * p0) > 0.0) and np.all(np.diff(ak + bk * 5.0e4) > 0.0)
+    return ak, bk
+
+
+def _edge_dirs(g):
+    """Unit tangent vectors + mid-point lon/lat of D-grid u (south) and v (west) edges."""
+    lon, lat = g.arr["grid"]
+    P = latlon2xyz(lon, lat)                      # (nj+1, ni+1, 3)
+    def mid_and_dir(a, b):
+        m = a + b
+        m /= np.linalg.norm(m, axis=-1, keepdims=True)
+        d = b - a
+        d -= np.sum(d * m, -1, keepdims=True) * m
+        d /= np.linalg.norm(d, axis=-1, keepdims=True)
+        return m, d
+    mu, du = mid_and_dir(P[:, :-1], P[:, 1:])    # u: (nj+1, ni)
+    mv, dv = mid_and_dir(P[:-1, :], P[1:, :])    # v: (nj, ni+1)
+    return mu, du, mv, dv
+
+
+def _wind_on_edge(m, d, ufun):
+    lon = np.arctan2(m[..., 1], m[..., 0])
+    lat = np.arcsin(np.clip(m[..., 2], -1, 1))
+    uz, vm = ufun(lon, lat)                       # (..., nj, ni) zonal, meridional
+    elon = np.stack([-np.sin(lon), np.cos(lon), np.zeros_like(lon)], -1)
+    elat = np.stack([-np.sin(lat) * np.cos(lon), -np.sin(lat) * np.sin(lon), np.cos(lat)], -1)
+    return uz * np.sum(elon * d, -1) + vm * np.sum(elat * d, -1)
+
+
+def _fill_scalar_halos(ex, arrs):
+    ex.scalar(arrs, cs.CENTER)
+
+
+def baroclinic_wave(tiles, bounds, npz, ak, bk, consts=None, perturb=True, w_amp=0.1):
+    """Returns a list of 6 dicts of native-extent state arrays (C-order (nk, nj, ni))."""
+    cst = dict(CONSTANTS)
+    if consts:
+        cst.update(consts)
+    a, omega, grav, rdgas, kappa = cst["radius"], cst["omega"], cst["grav"], cst["rdgas"], cst["kappa"]
+    n, ng = bounds["ie"], bounds["ng"]
+    ex = cs.Exchanger(n, ng)
+    p0, u0, eta0, eta_t, T0, gamma, dT = 1.0e5, 35.0, 0.252, 0.2, 288.0, 0.005, 4.8e5
+    lonc, latc, up, Rp = np.pi / 9.0, 2.0 * np.pi / 9.0, 1.0, a / 10.0
+    ps = p0
+    pe = ak + bk * ps                                   # (npz+1)
+    peln = np.log(pe)
+    delp_k = np.diff(pe)
+    pm = delp_k / np.diff(peln)                         # layer-mean pressure (nh_utils.F90:440)
+    eta = pm / p0
+    etav = (eta - eta0) * np.pi / 2.0
+
+    def Tbar(e):
+        t = T0 * e ** (rdgas * gamma / grav)
+        return np.where(e < eta_t, t + dT * np.maximum(eta_t - e, 0.0) ** 5, t)
+
+    def T_of(lat):
+        A = (-2.0 * np.sin(lat) ** 6 * (np.cos(lat) ** 2 + 1.0 / 3.0) + 10.0 / 63.0)
+        B = (1.6 * np.cos(lat) ** 3 * (np.sin(lat) ** 2 + 2.0 / 3.0) - np.pi / 4.0)
+        ev = etav[:, None, None]
+        e = eta[:, None, None]
+        return Tbar(e) + 0.75 * e * np.pi * u0 / rdgas * np.sin(ev) * np.sqrt(np.cos(ev)) * \
+            (A[None] * 2.0 * u0 * np.cos(ev) ** 1.5 + B[None] * a * omega)
+
+    def phis_of(lat):
+        c = np.cos((1.0 - eta0) * np.pi / 2.0) ** 1.5
+        A = (-2.0 * np.sin(lat) ** 6 * (np.cos(lat) ** 2 + 1.0 / 3.0) + 10.0 / 63.0)
+        B = (1.6 * np.cos(lat) ** 3 * (np.sin(lat) ** 2 + 2.0 / 3.0) - np.pi / 4.0)
+        return u0 * c * (A * u0 * c + B * a * omega)
+
+    def wind(lon, lat):
+        uz = u0 * np.cos(etav[:, None, None]) ** 1.5 * np.sin(2.0 * lat[None]) ** 2
+        if perturb:
+            r = a * np.arccos(np.clip(np.sin(latc) * np.sin(lat) + np.cos(latc) * np.cos(lat) * np.cos(lon - lonc), -1, 1))
+            uz = uz + up * np.exp(-(r / Rp) ** 2)[None]
+        return uz, np.zeros_like(uz)
+
+    states = []
+    isd, jsd = bounds["isd"], bounds["jsd"]
+    nja = bounds["jed"] - jsd + 1
+    nia = bounds["ied"] - isd + 1
+    for g in tiles:
+        lon, lat = g.arr["agrid"]
+        st = {}
+        T = T_of(lat)
+        st["delp"] = np.broadcast_to(delp_k[:, None, None], (npz, nja, nia)).copy()
+        st["pt"] = T / (pm[:, None, None] ** kappa)
+        st["phis"] = phis_of(lat)[None].copy()
+        kk = (np.arange(npz) + 1.0)[:, None, None]
+        st["w"] = w_amp * np.sin(7.0 * lon)[None] * np.cos(5.0 * lat)[None] * np.sin(np.pi * kk / npz)
+        delz = -(rdgas / grav) * T * np.diff(peln)[:, None, None]
+        st["delz"] = np.ascontiguousarray(delz[:, ng:-ng, ng:-ng])
+        mu, du, mv, dv = _edge_dirs(g)
+        st["u"] = _wind_on_edge(mu, du, wind)
+        st["v"] = _wind_on_edge(mv, dv, wind)
+        states.append(st)
+    # halos by exchange (overwrites the analytic halo values with the neighbours' compute-domain values)
+    for nm in ("delp", "pt", "w", "phis"):
+        _fill_scalar_halos(ex, [s[nm] for s in states])
+    ex.pair([s["u"] for s in states], [s["v"] for s in states], cs.NORTH, cs.EAST, kind="vector")
+    for s in states:
+        for nm in ("delp", "pt"):
+            _patch_corners(s[nm], ng, n)
+    return states
+
+
+def _patch_corners(a, ng, n):
+    """Give the (unused) ng x ng corner blocks benign finite values (nearest interior corner cell)."""
+    a[..., :ng, :ng] = a[..., ng:ng + 1, ng:ng + 1]
+    a[..., :ng, -ng:] = a[..., ng:ng + 1, -ng - 1:-ng]
+    a[..., -ng:, :ng] = a[..., -ng - 1:-ng, ng:ng + 1]
+    a[..., -ng:, -ng:] = a[..., -ng - 1:-ng, -ng - 1:-ng]
+
+
+def smooth_state(tiles, bounds, npz, seed=20241117, consts=None):
+    """Analytic smooth-plus-step fields exercising every limiter branch (operator parity tests)."""
+    cst = dict(CONSTANTS)
+    if consts:
+        cst.update(consts)
+    n, ng = bounds["ie"], bounds["ng"]
+    ex = cs.Exchanger(n, ng)
+    rng = np.random.default_rng(seed)
+    ph = rng.uniform(0, 2 * np.pi, size=(8,))
+    states = []
+    kk = (np.arange(npz) + 1.0)[:, None, None]
+
+    def wind(lon, lat):
+        uz = 30.0 * np.cos(lat)[None] * (1.0 + 0.3 * np.sin(3 * lon + ph[0])[None] * np.cos(kk)) + 0 * kk
+        vm = 12.0 * np.sin(2 * lon + ph[1])[None] * np.cos(lat)[None] ** 2 * np.sin(0.5 * kk + ph[2])
+        return uz, vm
+
+    for g in tiles:
+        lon, lat = g.arr["agrid"]
+        st = {}
+        base = 1000.0 + 300.0 * np.sin(0.37 * kk)
+        st["delp"] = base * (1.0 + 0.05 * np.sin(2 * lon + ph[3])[None] * np.cos(3 * lat)[None]) \
+            + 40.0 * (np.sin(5 * lon)[None] * np.cos(4 * lat + 0.1 * kk) > 0.3)
+        st["pt"] = 300.0 + 20.0 * np.cos(lat)[None] * np.sin(lon + ph[4] + 0.2 * kk) + 5.0 * (lat[None] > 0.3 + 0 * kk)
+        st["w"] = 0.5 * np.sin(4 * lon + ph[5])[None] * np.cos(3 * lat)[None] * np.sin(np.pi * kk / npz)
+        st["q_con"] = 1e-3 * (1.0 + np.sin(3 * lon + ph[6])[None] * np.cos(2 * lat)[None]) + 0 * kk
+        mu, du, mv, dv = _edge_dirs(g)
+        st["u"] = _wind_on_edge(mu, du, wind)
+        st["v"] = _wind_on_edge(mv, dv, wind)
+        states.append(st)
+    for nm in ("delp", "pt", "w", "q_con"):
+        _fill_scalar_halos(ex, [s[nm] for s in states])
+    ex.pair([s["u"] for s in states], [s["v"] for s in states], cs.NORTH, cs.EAST, kind="vector")
+    for s in states:
+        for nm in ("delp", "pt", "w", "q_con"):
+            _patch_corners(s[nm], ng, n)
+    return states

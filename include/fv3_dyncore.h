@@ -1,0 +1,257 @@
+/*
+ * fv3_dyncore.h -- C ABI of the B200-native FV3 acoustic-dynamics hot path.
+ *
+ * This is the drop-in boundary a Fortran ISO_C_BINDING shim inside
+ * model/dyn_core.F90 binds to (INTEGRATION.md shows the shim).  Every entry
+ * point cites the reference interface it replaces (paths relative to the
+ * reference checkout, NOAA-GFDL/GFDL_atmos_cubed_sphere @ 202411).
+ *
+ * Conventions
+ *  - all reals are fp64 ("real" in the 64bit build, fv_arrays.F90:39);
+ *  - arrays are Fortran column-major, i fastest, passed as the address of
+ *    element (lower_i, lower_j, 1) with the NATIVE Fortran extents written
+ *    beside each argument (fv_arrays.F90:1515-1563 state, :1749-1878 metrics);
+ *  - logicals are int (0/1); optional arrays are NULL;
+ *  - every call returns 0 on success, <0 for a bad argument / unsupported
+ *    flag combination (there is NO CPU fallback), >0 for a CUDA/NCCL error;
+ *    fv3_last_error() returns the message (the shim maps non-zero to
+ *    mpp_error(FATAL, ...), the reference's only error convention,
+ *    fv_control.F90:1100-1112);
+ *  - one fv3_ctx per GPU / cube face; not thread-safe: call from the master
+ *    thread outside any OpenMP region (dyn_core.F90:436,658 are replaced by
+ *    ONE batched-over-k call each).
+ */
+#ifndef FV3_DYNCORE_H
+#define FV3_DYNCORE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* fv_grid_bounds_type (fv_arrays.F90:1192-1200) + the few gridstruct scalars
+ * the hot path reads (fv_arrays.F90:75-205). One rank owns one whole face
+ * (layout 1x1), so is=js=1, ie=npx-1, je=npy-1, isd=is-ng ... */
+typedef struct fv3_bounds_t {
+  int npx, npy, npz, ng;
+  int is, ie, js, je;
+  int isd, ied, jsd, jed;
+  int grid_type;        /* 0..2 gnomonic cubed sphere, 4 doubly-periodic Cartesian */
+  int bounded_domain;   /* nested/regional: must be 0 (out of scope) */
+  int sw_corner, se_corner, ne_corner, nw_corner;
+  int stretched_grid;
+  int tile;             /* 1..6 (informational; halo topology uses it) */
+} fv3_bounds_t;
+
+/* fv_grid_type metric terms used on the path (fv_arrays.F90:75-205,
+ * allocation extents fv_arrays.F90:1749-1878). Immutable after
+ * grid_utils_init (fv_grid_utils.F90:84-790); uploaded once by fv3_create. */
+typedef struct fv3_grid_t {
+  /* (isd:ied, jsd:jed) */
+  const double *area, *rarea, *dxa, *dya, *rdxa, *rdya, *cosa_s, *rsin2, *f0;
+  /* (isd:ied, jsd:jed, 9) */
+  const double *sin_sg, *cos_sg;
+  /* (isd:ied+1, jsd:jed) */
+  const double *dy, *rdy, *dxc, *rdxc, *cosa_u, *sina_u, *rsin_u, *divg_v, *del6_v;
+  /* (isd:ied, jsd:jed+1) */
+  const double *dx, *rdx, *dyc, *rdyc, *cosa_v, *sina_v, *rsin_v, *divg_u, *del6_u;
+  /* (isd:ied+1, jsd:jed+1) */
+  const double *area_c, *rarea_c, *fC, *cosa, *sina;
+  /* (is:ie+1, js:je+1)  -- no halo, fv_arrays.F90:1784 */
+  const double *rsina;
+  /* edge_w, edge_e (npy); edge_s, edge_n (npx)  fv_arrays.F90:1796-1799 */
+  const double *edge_w, *edge_e, *edge_s, *edge_n;
+  /* grid (isd:ied+1, jsd:jed+1, 2) lon,lat of corners; agrid (isd:ied, jsd:jed, 2) */
+  const double *grid, *agrid;
+  double da_min, da_min_c;
+} fv3_grid_t;
+
+/* The subset of fv_flags_type (fv_arrays.F90:207-906) + FMS constants_mod
+ * values + vertical coordinate that dyn_core and its callees read. */
+typedef struct fv3_flags_t {
+  int hord_mt, hord_vt, hord_tm, hord_dp, hord_tr;
+  int nord, n_sponge, m_split;
+  int hydrostatic, do_vort_damp, use_cond, moist_kappa, inline_q, do_f3d;
+  int use_logp, convert_ke, prevent_diss_cooling, do_diss_est, is_ideal_case;
+  int use_old_omega, fill_dp, pad_;
+  double d4_bg, d2_bg, dddmp, d2_bg_k1, d2_bg_k2, vtdm4, d_con, ke_bg, d_ext;
+  double a_imp, p_fac, beta, lim_fac, fast_tau_w_sec, rf_cutoff, d2bg_zq, delt_max;
+  /* constants_mod (FMS, not in the reference repo): run-time parameters */
+  double rdgas, cp_air, grav, kappa, radius, omega, pi;
+  double ptop;
+  const double *ak, *bk;      /* (npz+1) */
+} fv3_flags_t;
+
+/* Prognostic + auxiliary state of fv_atmos_type that crosses the dyn_core
+ * boundary (dyn_core.F90:94-98; extents fv_arrays.F90:1521-1563). */
+typedef struct fv3_state_t {
+  double *u;      /* (isd:ied,   jsd:jed+1, npz) */
+  double *v;      /* (isd:ied+1, jsd:jed,   npz) */
+  double *w;      /* (isd:ied,   jsd:jed,   npz) */
+  double *delz;   /* (is:ie,     js:je,     npz) */
+  double *pt;     /* (isd:ied,   jsd:jed,   npz) */
+  double *delp;   /* (isd:ied,   jsd:jed,   npz) */
+  double *q_con;  /* (isd:ied,   jsd:jed,   npz) or NULL */
+  double *cappa;  /* (isd:ied,   jsd:jed,   npz) or NULL */
+  double *phis;   /* (isd:ied,   jsd:jed) */
+  double *omga;   /* (isd:ied,   jsd:jed,   npz) */
+  double *ua, *va;/* (isd:ied,   jsd:jed,   npz) */
+  double *uc;     /* (isd:ied+1, jsd:jed,   npz) */
+  double *vc;     /* (isd:ied,   jsd:jed+1, npz) */
+  double *mfx;    /* (is:ie+1,   js:je,     npz) */
+  double *mfy;    /* (is:ie,     js:je+1,   npz) */
+  double *cx;     /* (is:ie+1,   jsd:jed,   npz) */
+  double *cy;     /* (isd:ied,   js:je+1,   npz) */
+  double *pe;     /* (is-1:ie+1, npz+1, js-1:je+1)  k in the middle */
+  double *peln;   /* (is:ie,     npz+1, js:je)      k in the middle */
+  double *pk;     /* (is:ie,     js:je, npz+1) */
+  double *pkz;    /* (is:ie,     js:je, npz) */
+  double *ws;     /* (is:ie,     js:je) */
+  double *heat_source; /* (isd:ied, jsd:jed, npz) */
+  double *diss_est;    /* (isd:ied, jsd:jed, npz) */
+} fv3_state_t;
+
+typedef struct fv3_ctx fv3_ctx;
+
+/* ---- lifetime ---------------------------------------------------------- */
+/* Replaces the allocate/deallocate of dyn_core's module work arrays
+ * (dyn_core.F90:254-286, :1365-1390). Copies the metric terms to the device. */
+int  fv3_create(const fv3_bounds_t *bd, const fv3_grid_t *grid,
+                const fv3_flags_t *flags, int device, fv3_ctx **out);
+void fv3_destroy(fv3_ctx *ctx);
+const char *fv3_last_error(const fv3_ctx *ctx);
+/* struct sizes, so a binding can check it was built against this header */
+int  fv3_abi_sizeof(int which); /* 0 bounds, 1 grid, 2 flags, 3 state */
+int  fv3_abi_version(void);
+
+/* ---- named device fields (parity harness + shim plumbing) --------------- */
+/* Field ids name the arrays dyn_core touches; fv3_field_dims gives the
+ * native Fortran lower bounds and extents of each (what the host buffer
+ * must hold). fv3_put/get copy host<->device through pinned staging. */
+enum fv3_field_id {
+  FV3_U = 0, FV3_V, FV3_W, FV3_DELZ, FV3_PT, FV3_DELP, FV3_QCON, FV3_CAPPA,
+  FV3_PHIS, FV3_OMGA, FV3_UA, FV3_VA, FV3_UC, FV3_VC,
+  FV3_MFX, FV3_MFY, FV3_CX, FV3_CY,
+  FV3_DELPC, FV3_PTC, FV3_UT, FV3_VT, FV3_DIVGD,
+  FV3_CRX, FV3_CRY, FV3_XFX, FV3_YFX,
+  FV3_GZ, FV3_ZH, FV3_PKC, FV3_PK3, FV3_WS3, FV3_WS,
+  FV3_PE, FV3_PELN, FV3_PK, FV3_PKZ, FV3_HEAT, FV3_DISS,
+  FV3_WORK_Q,   /* scalar for stand-alone fv_tp_2d (isd:ied, jsd:jed, nk) */
+  FV3_WORK_FX,  /* (is:ie+1, js:je, nk) */
+  FV3_WORK_FY,  /* (is:ie, js:je+1, nk) */
+  FV3_WORK_RAX, /* (is:ie, jsd:jed, nk) */
+  FV3_WORK_RAY, /* (isd:ied, js:je, nk) */
+  FV3_NUM_FIELDS
+};
+/* dims = {i_lo, ni, j_lo, nj, nk, k_middle(0/1)} */
+int fv3_field_dims(const fv3_ctx *ctx, int field, int dims[6]);
+int fv3_put_field(fv3_ctx *ctx, int field, const double *host);
+int fv3_get_field(fv3_ctx *ctx, int field, double *host);
+int fv3_sync(fv3_ctx *ctx);
+
+/* ---- whole-state transfer at dyn_core entry/exit ------------------------ */
+int fv3_upload_state(fv3_ctx *ctx, const fv3_state_t *host);
+int fv3_download_state(fv3_ctx *ctx, fv3_state_t *host);
+
+/* ---- operator entry points (one call replaces one OpenMP k-loop) -------- */
+/* All operate on the DEVICE-RESIDENT fields named above; the *_host variants
+ * below wrap them with put/get for a per-call drop-in. */
+
+/* tp_core.F90:85 fv_tp_2d, batched over nk levels, on FV3_WORK_Q with
+ * Courant numbers FV3_CRX/CRY, fluxes FV3_XFX/YFX, FV3_WORK_RAX/RAY;
+ * writes FV3_WORK_FX/FY. use_mfx: multiply by FV3_MFX/MFY instead of xfx/yfx
+ * (tp_core.F90:187-200); nord/damp_c: deln_flux (tp_core.F90:201-206),
+ * mass-weighted with FV3_DELP when use_mass. */
+int fv3_fv_tp_2d(fv3_ctx *ctx, int nk, int hord, int use_mfx, int use_mass,
+                 int nord, double damp_c);
+
+/* sw_core.F90:79 c_sw for k = 1..npz (dyn_core.F90:436-447). */
+int fv3_c_sw(fv3_ctx *ctx, double dt2);
+/* nh_utils.F90:59 update_dz_c (dyn_core.F90:525). */
+int fv3_update_dz_c(fv3_ctx *ctx, double dt2);
+/* nh_utils.F90:323 Riem_Solver_c (dyn_core.F90:531-536). */
+int fv3_riem_solver_c(fv3_ctx *ctx, double dt2);
+/* dyn_core.F90:1635 p_grad_c (dyn_core.F90:562). */
+int fv3_p_grad_c(fv3_ctx *ctx, double dt2);
+/* sw_core.F90:494 d_sw for k = 1..npz incl. the per-k damping prologue
+ * dyn_core.F90:666-772. */
+int fv3_d_sw(fv3_ctx *ctx, double dt);
+/* nh_utils.F90:204 update_dz_d (dyn_core.F90:911). */
+int fv3_update_dz_d(fv3_ctx *ctx, double dt);
+/* nh_core.F90:47 Riem_Solver3 (dyn_core.F90:932-940). */
+int fv3_riem_solver3(fv3_ctx *ctx, double dt, int last_call);
+/* dyn_core.F90:1395 pk3_halo + :1498 pe_halo + gz = zh*grav (:982-989). */
+int fv3_pk3_halo(fv3_ctx *ctx);
+int fv3_pe_halo(fv3_ctx *ctx);
+int fv3_gz_from_zh(fv3_ctx *ctx);
+/* dyn_core.F90:1697 nh_p_grad (dyn_core.F90:1032). */
+int fv3_nh_p_grad(fv3_ctx *ctx, double dt);
+
+/* ---- halo exchange (replaces fv_mp_mod.F90:646-874 group updates) ------- */
+/* One process may own several faces (tiles) of the cube; peers are other
+ * contexts in the same process (device-local copies) or other ranks (NCCL
+ * P2P, attached with fv3_comm_attach). Without any peer the halo is frozen. */
+enum fv3_halo_group {
+  FV3_HALO_UVW = 0,   /* i_pack(8)+(7): u,v D-grid vector + w   dyn_core.F90:430-432 */
+  FV3_HALO_GZ,        /* i_pack(5): gz (it==1)                   dyn_core.F90:387,488 */
+  FV3_HALO_DIVGD_UCVC,/* i_pack(3)+(9): divgd@corner, uc,vc      dyn_core.F90:451,565,577-578 */
+  FV3_HALO_DELP_PT,   /* i_pack(1)(+11): delp, pt[, q_con]       dyn_core.F90:823-825,851 */
+  FV3_HALO_ZH_PKC,    /* i_pack(4)/(5): zh, pkc                  dyn_core.F90:945-949,980,992 */
+  FV3_HALO_UV_EDGE,   /* mpp_get_boundary(u,v) last substep      dyn_core.F90:1151-1163 */
+  FV3_NUM_HALO_GROUPS
+};
+/* Link the six (or fewer) contexts of one process into a cube. tiles[i] is
+ * the face number (1..6) of ctxs[i]. */
+int fv3_cube_link(fv3_ctx **ctxs, const int *tiles, int nctx);
+/* Attach an NCCL communicator (ncclComm_t passed as void*) and the
+ * tile->rank map (6 ints, -1 = not present) for off-process faces. */
+int fv3_comm_attach(fv3_ctx *ctx, void *nccl_comm, const int tile_rank[6]);
+/* Exchange one group for all linked contexts of this process. */
+int fv3_halo_exchange(fv3_ctx **ctxs, int nctx, int group);
+
+/* ---- the acoustic loop -------------------------------------------------- */
+/* dyn_core.F90:313-1286: n_split substeps on device-resident state for the
+ * linked contexts of this process (nctx faces), halo exchanges included.
+ * bdt is the large (k_split) time step; dt = bdt/n_split (dyn_core.F90:223).
+ * flags: bit0 = capture each substep in a CUDA graph. */
+int fv3_dyn_core(fv3_ctx **ctxs, int nctx, double bdt, int n_split, int flags);
+/* kernels launched by this context since creation (bench.py gpu_launches) */
+long long fv3_launch_count(const fv3_ctx *ctx);
+/* device time (ms) accumulated in a named stage since last reset:
+ * names follow fv_timing blocks (dyn_core.F90:435,524,530,657,910,931,1016):
+ * "C_SW","UPDATE_DZ_C","Riem_Solver_C","PG_C","D_SW","UPDATE_DZ","Riem_Solver3","PG_D","HALO" */
+int fv3_stage_time_ms(fv3_ctx *ctx, const char *stage, double *ms, long long *calls);
+int fv3_stage_timers(fv3_ctx *ctx, int enable);
+
+/* ---- per-call host-buffer drop-ins (Fortran call-site shaped) ----------- */
+/* sw_core.F90:79 / dyn_core.F90:439-447, batched over k=1..npz; arrays in
+ * native extents; w/wc NULL when hydrostatic. */
+int fv3_c_sw_host(fv3_ctx *ctx, double *delpc, double *delp, double *ptc, double *pt,
+                  double *u, double *v, double *w, double *uc, double *vc,
+                  double *ua, double *va, double *wc, double *ut, double *vt,
+                  double *divg_d, double dt2);
+/* sw_core.F90:494 / dyn_core.F90:762-772, batched over k=1..npz. delpc/ptc
+ * are the scratch arrays dyn_core passes (vt and ptc). */
+int fv3_d_sw_host(fv3_ctx *ctx, double *delp, double *pt, double *u, double *v,
+                  double *w, double *uc, double *vc, double *ua, double *va,
+                  double *divg_d, double *mfx, double *mfy, double *cx, double *cy,
+                  double *crx, double *cry, double *xfx, double *yfx,
+                  double *q_con, double *heat_source, double *diss_est, double dt);
+/* tp_core.F90:85, nk levels, host buffers in native extents; mfx/mfy/mass NULL
+ * to select the xfx/yfx weighting. q's corner halos are rewritten as in the
+ * reference (copy_corners, tp_core.F90:143,164). */
+int fv3_fv_tp_2d_host(fv3_ctx *ctx, int nk, double *q, const double *crx,
+                      const double *cry, const double *xfx, const double *yfx,
+                      const double *ra_x, const double *ra_y, int hord,
+                      double *fx, double *fy, const double *mfx,
+                      const double *mfy, const double *mass, int nord,
+                      double damp_c);
+/* nh_utils.F90:323 / dyn_core.F90:531-536 */
+int fv3_riem_solver_c_host(fv3_ctx *ctx, double dt2, const double *cappa,
+                           const double *phis, const double *w3, const double *ptc,
+                           const double *q_con, const double *delpc, double *gz,
+                           double *pef, const double *ws3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FV3_DYNCORE_H */

@@ -1,0 +1,316 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle (see fv3_oracle.hpp header).
+// extern "C" surface of the oracle, shaped like include/fv3_dyncore.h (prefix fv3o_) so the
+// parity tests drive oracle and product through the same harness.  Fields are held in the
+// reference's native Fortran layouts.  The per-stage drivers restate the call sites in
+// model/dyn_core.F90 (:436-447 c_sw, :525 update_dz_c, :531 Riem_Solver_C, :562 p_grad_c,
+// :666-812 d_sw with its per-k damping prologue, :911 update_dz_d, :932 Riem_Solver3,
+// :953-989 halo pressure fills + gz, :1032 nh_p_grad).
+#include "fv3_oracle.hpp"
+#include <string>
+#include <cstdio>
+#include <omp.h>
+
+using namespace fv3o;
+
+struct FieldDim { int ilo, ni, jlo, nj, nk, kmid; };
+
+struct fv3o_ctx {
+  fv3_bounds_t b; fv3_grid_t g; fv3_flags_t f;
+  std::vector<double> ak, bk;
+  std::vector<std::vector<double>> fld;
+  FieldDim dim[FV3_NUM_FIELDS];
+  std::string err;
+  // per-k damping arrays shared between d_sw and update_dz_d (dyn_core.F90:186-187)
+  std::vector<double> damp_vt; std::vector<int> nord_v;
+  explicit fv3o_ctx(const fv3_bounds_t& b_, const fv3_grid_t& g_, const fv3_flags_t& f_) : b(b_), g(g_), f(f_) {}
+};
+
+static void set_dims(fv3o_ctx* c) {
+  const fv3_bounds_t& b = c->b;
+  const int nia = b.ied - b.isd + 1, nja = b.jed - b.jsd + 1, nic = b.ie - b.is + 1, njc = b.je - b.js + 1, kz = b.npz;
+  auto A = [&](int nk) { return FieldDim{b.isd, nia, b.jsd, nja, nk, 0}; };
+  FieldDim* d = c->dim;
+  d[FV3_U] = {b.isd, nia, b.jsd, nja + 1, kz, 0};
+  d[FV3_V] = {b.isd, nia + 1, b.jsd, nja, kz, 0};
+  d[FV3_W] = A(kz); d[FV3_PT] = A(kz); d[FV3_DELP] = A(kz); d[FV3_QCON] = A(kz); d[FV3_CAPPA] = A(kz);
+  d[FV3_DELZ] = {b.is, nic, b.js, njc, kz, 0};
+  d[FV3_PHIS] = A(1); d[FV3_OMGA] = A(kz); d[FV3_UA] = A(kz); d[FV3_VA] = A(kz);
+  d[FV3_UC] = {b.isd, nia + 1, b.jsd, nja, kz, 0};
+  d[FV3_VC] = {b.isd, nia, b.jsd, nja + 1, kz, 0};
+  d[FV3_MFX] = {b.is, nic + 1, b.js, njc, kz, 0};
+  d[FV3_MFY] = {b.is, nic, b.js, njc + 1, kz, 0};
+  d[FV3_CX] = {b.is, nic + 1, b.jsd, nja, kz, 0};
+  d[FV3_CY] = {b.isd, nia, b.js, njc + 1, kz, 0};
+  d[FV3_DELPC] = A(kz); d[FV3_PTC] = A(kz); d[FV3_UT] = A(kz); d[FV3_VT] = A(kz);
+  d[FV3_DIVGD] = {b.isd, nia + 1, b.jsd, nja + 1, kz, 0};
+  d[FV3_CRX] = d[FV3_CX]; d[FV3_XFX] = d[FV3_CX]; d[FV3_CRY] = d[FV3_CY]; d[FV3_YFX] = d[FV3_CY];
+  d[FV3_GZ] = A(kz + 1); d[FV3_ZH] = A(kz + 1); d[FV3_PKC] = A(kz + 1); d[FV3_PK3] = A(kz + 1);
+  d[FV3_WS3] = A(1);
+  d[FV3_WS] = {b.is, nic, b.js, njc, 1, 0};
+  d[FV3_PE] = {b.is - 1, nic + 2, b.js - 1, njc + 2, kz + 1, 1};
+  d[FV3_PELN] = {b.is, nic, b.js, njc, kz + 1, 1};
+  d[FV3_PK] = {b.is, nic, b.js, njc, kz + 1, 0};
+  d[FV3_PKZ] = {b.is, nic, b.js, njc, kz, 0};
+  d[FV3_HEAT] = A(kz); d[FV3_DISS] = A(kz);
+  d[FV3_WORK_Q] = A(kz + 1);
+  d[FV3_WORK_FX] = {b.is, nic + 1, b.js, njc, kz + 1, 0};
+  d[FV3_WORK_FY] = {b.is, nic, b.js, njc + 1, kz + 1, 0};
+  d[FV3_WORK_RAX] = {b.is, nic, b.jsd, nja, kz + 1, 0};
+  d[FV3_WORK_RAY] = {b.isd, nia, b.js, njc, kz + 1, 0};
+}
+
+static V3 F3(fv3o_ctx* c, int id) {
+  const FieldDim& d = c->dim[id];
+  return V3(c->fld[id].data(), d.ilo, d.ilo + d.ni - 1, d.jlo, d.jlo + d.nj - 1);
+}
+static V2 F2(fv3o_ctx* c, int id, int k = 1) { return F3(c, id).k(k); }
+
+extern "C" {
+
+int fv3o_create(const fv3_bounds_t* bd, const fv3_grid_t* grid, const fv3_flags_t* flags, int device, fv3o_ctx** out) {
+  (void)device;
+  fv3o_ctx* c = new fv3o_ctx(*bd, *grid, *flags);
+  c->ak.assign(flags->ak, flags->ak + bd->npz + 1);
+  c->bk.assign(flags->bk, flags->bk + bd->npz + 1);
+  c->f.ak = c->ak.data(); c->f.bk = c->bk.data();
+  set_dims(c);
+  c->fld.resize(FV3_NUM_FIELDS);
+  for (int i = 0; i < FV3_NUM_FIELDS; i++) {
+    const FieldDim& d = c->dim[i];
+    c->fld[i].assign((size_t)d.ni * d.nj * d.nk, 0.0);
+  }
+  c->damp_vt.assign(bd->npz + 1, 0.); c->nord_v.assign(bd->npz + 1, 0);
+  *out = c;
+  return 0;
+}
+void fv3o_destroy(fv3o_ctx* c) { delete c; }
+const char* fv3o_last_error(const fv3o_ctx* c) { return c->err.c_str(); }
+int fv3o_field_dims(const fv3o_ctx* c, int field, int dims[6]) {
+  if (field < 0 || field >= FV3_NUM_FIELDS) return -1;
+  const FieldDim& d = c->dim[field];
+  dims[0] = d.ilo; dims[1] = d.ni; dims[2] = d.jlo; dims[3] = d.nj; dims[4] = d.nk; dims[5] = d.kmid;
+  return 0;
+}
+int fv3o_put_field(fv3o_ctx* c, int field, const double* host) {
+  if (field < 0 || field >= FV3_NUM_FIELDS) return -1;
+  std::memcpy(c->fld[field].data(), host, c->fld[field].size() * sizeof(double));
+  return 0;
+}
+int fv3o_get_field(fv3o_ctx* c, int field, double* host) {
+  if (field < 0 || field >= FV3_NUM_FIELDS) return -1;
+  std::memcpy(host, c->fld[field].data(), c->fld[field].size() * sizeof(double));
+  return 0;
+}
+int fv3o_sync(fv3o_ctx*) { return 0; }
+int fv3o_set_threads(int n) { omp_set_num_threads(n); return omp_get_max_threads(); }
+int fv3o_max_threads(void) { return omp_get_max_threads(); }
+
+// tp_core.F90:85, batched over nk levels (same field conventions as fv3_fv_tp_2d)
+int fv3o_fv_tp_2d(fv3o_ctx* c, int nk, int hord, int use_mfx, int use_mass, int nord, double damp_c) {
+  Bd bd(c->b); Grid g(c->g, bd);
+  V3 q = F3(c, FV3_WORK_Q), crx = F3(c, FV3_CRX), cry = F3(c, FV3_CRY), xfx = F3(c, FV3_XFX), yfx = F3(c, FV3_YFX);
+  V3 rax = F3(c, FV3_WORK_RAX), ray = F3(c, FV3_WORK_RAY), fx = F3(c, FV3_WORK_FX), fy = F3(c, FV3_WORK_FY);
+  V3 mfx = F3(c, FV3_MFX), mfy = F3(c, FV3_MFY), mass = F3(c, FV3_DELP);
+#pragma omp parallel for schedule(static)
+  for (int k = 1; k <= nk; k++) {
+    V2 mx = mfx.k(k), my = mfy.k(k), ms = mass.k(k);
+    fv_tp_2d(q.k(k), crx.k(k), cry.k(k), bd.npx, bd.npy, hord, fx.k(k), fy.k(k), xfx.k(k), yfx.k(k), g, bd, rax.k(k),
+             ray.k(k), c->f.lim_fac, use_mfx ? &mx : nullptr, use_mfx ? &my : nullptr, use_mass ? &ms : nullptr,
+             nord >= 0, nord, damp_c);
+  }
+  return 0;
+}
+
+// dyn_core.F90:436-447
+int fv3o_c_sw(fv3o_ctx* c, double dt2) {
+  Bd bd(c->b); Grid g(c->g, bd);
+  const bool hydro = c->f.hydrostatic != 0;
+#pragma omp parallel for schedule(dynamic)
+  for (int k = 1; k <= bd.npz; k++) {
+    c_sw(F2(c, FV3_DELPC, k), F2(c, FV3_DELP, k), F2(c, FV3_PTC, k), F2(c, FV3_PT, k), F2(c, FV3_U, k), F2(c, FV3_V, k),
+         F2(c, FV3_W, k), F2(c, FV3_UC, k), F2(c, FV3_VC, k), F2(c, FV3_UA, k), F2(c, FV3_VA, k), F2(c, FV3_OMGA, k),
+         F2(c, FV3_UT, k), F2(c, FV3_VT, k), F2(c, FV3_DIVGD, k), c->f.nord, dt2, hydro, true, bd, g);
+  }
+  return 0;
+}
+
+static std::vector<double> dp_ref(fv3o_ctx* c) {  // dyn_core.F90:242-244
+  std::vector<double> d(c->b.npz);
+  for (int k = 0; k < c->b.npz; k++) d[k] = c->ak[k + 1] - c->ak[k] + (c->bk[k + 1] - c->bk[k]) * 1.E5;
+  return d;
+}
+static std::vector<double> zs_of(fv3o_ctx* c) {  // dyn_core.F90:247-251
+  const double rgrav = 1.0 / c->f.grav;
+  std::vector<double> zs(c->fld[FV3_PHIS].size());
+  for (size_t i = 0; i < zs.size(); i++) zs[i] = c->fld[FV3_PHIS][i] * rgrav;
+  return zs;
+}
+
+// dyn_core.F90:525-527
+int fv3o_update_dz_c(fv3o_ctx* c, double dt2) {
+  Bd bd(c->b); Grid g(c->g, bd);
+  std::vector<double> dp0 = dp_ref(c), zs = zs_of(c);
+  update_dz_c(bd.is, bd.ie, bd.js, bd.je, bd.npz, bd.ng, dt2, dp0.data(), V2(zs.data(), bd.isd, bd.jsd, bd.ied - bd.isd + 1),
+              g.area, F3(c, FV3_UT), F3(c, FV3_VT), F3(c, FV3_GZ), F2(c, FV3_WS3), bd);
+  return 0;
+}
+// dyn_core.F90:531-536
+int fv3o_riem_solver_c(fv3o_ctx* c, double dt2) {
+  Bd bd(c->b);
+  Consts k{c->f.rdgas, c->f.cp_air, c->f.grav, c->f.kappa, c->f.radius, c->f.omega, c->f.pi};
+  const int ms = std::max(1, c->f.m_split / 2);
+  riem_solver_c(ms, dt2, bd.is, bd.ie, bd.js, bd.je, bd.npz, bd.ng, c->f.kappa, F3(c, FV3_CAPPA), c->f.cp_air, c->f.ptop,
+                F2(c, FV3_PHIS), F3(c, FV3_OMGA), F3(c, FV3_PTC), F3(c, FV3_QCON), F3(c, FV3_DELPC), F3(c, FV3_GZ),
+                F3(c, FV3_PKC), F2(c, FV3_WS3), c->f.p_fac, c->f.a_imp, c->f.use_cond != 0, c->f.moist_kappa != 0, k);
+  return 0;
+}
+// dyn_core.F90:562
+int fv3o_p_grad_c(fv3o_ctx* c, double dt2) {
+  Bd bd(c->b); Grid g(c->g, bd);
+  p_grad_c(dt2, bd.npz, F3(c, FV3_DELPC), F3(c, FV3_PKC), F3(c, FV3_GZ), F3(c, FV3_UC), F3(c, FV3_VC), bd, g.rdxc, g.rdyc,
+           c->f.hydrostatic != 0);
+  return 0;
+}
+
+// dyn_core.F90:666-812 (use_old_omega=T, d_ext=0, do_f3d=F paths)
+int fv3o_d_sw(fv3o_ctx* c, double dt) {
+  Bd bd(c->b); Grid g(c->g, bd);
+  const fv3_flags_t& f = c->f;
+  const int npz = bd.npz;
+  std::vector<int> nord_k_(npz + 1), nord_w_(npz + 1), nord_t_(npz + 1);
+  std::vector<double> d2_divg_(npz + 1), damp_w_(npz + 1), damp_t_(npz + 1), d_con_k_(npz + 1);
+  for (int k = 1; k <= npz; k++) {
+    int nord_k = f.nord;
+    c->nord_v[k - 1] = std::min(2, f.nord);
+    double d2_divg = std::min(0.20, f.d2_bg);
+    c->damp_vt[k - 1] = f.do_vort_damp ? f.vtdm4 : 0.;
+    int nord_w = c->nord_v[k - 1], nord_t = c->nord_v[k - 1];
+    double damp_w = c->damp_vt[k - 1], damp_t = c->damp_vt[k - 1], d_con_k = f.d_con;
+    if (npz == 1 || f.n_sponge < 0) {
+      d2_divg = f.d2_bg;
+    } else {
+      if (k == 1) {
+        nord_k = 0;
+        if (f.is_ideal_case) d2_divg = std::max(f.d2_bg, f.d2_bg_k1);
+        else d2_divg = max3(0.01, f.d2_bg, f.d2_bg_k1);
+        nord_w = 0; damp_w = d2_divg;
+        if (f.do_vort_damp) { c->nord_v[k - 1] = 0; c->damp_vt[k - 1] = 0.5 * d2_divg; }
+        d_con_k = 0.;
+      } else if (k == 2 && f.d2_bg_k2 > 0.01) {
+        nord_k = 0; d2_divg = std::max(f.d2_bg, f.d2_bg_k2);
+        nord_w = 0; damp_w = d2_divg;
+        if (f.do_vort_damp) { c->nord_v[k - 1] = 0; c->damp_vt[k - 1] = 0.5 * d2_divg; }
+        d_con_k = 0.;
+      } else if (k == 3 && f.d2_bg_k2 > 0.05) {
+        nord_k = 0; d2_divg = std::max(f.d2_bg, 0.2 * f.d2_bg_k2);
+        nord_w = 0; damp_w = d2_divg;
+        d_con_k = 0.;
+      }
+    }
+    nord_k_[k] = nord_k; nord_w_[k] = nord_w; nord_t_[k] = nord_t;
+    d2_divg_[k] = d2_divg; damp_w_[k] = damp_w; damp_t_[k] = damp_t; d_con_k_[k] = d_con_k;
+  }
+  const int nic = bd.ie - bd.is + 1, njc = bd.je - bd.js + 1;
+#pragma omp parallel for schedule(dynamic)
+  for (int k = 1; k <= npz; k++) {
+    DswArgs a;
+    a.dt = dt; a.hord_tr = f.hord_tr; a.hord_mt = f.hord_mt; a.hord_vt = f.hord_vt; a.hord_tm = f.hord_tm; a.hord_dp = f.hord_dp;
+    a.nord = nord_k_[k]; a.nord_v = c->nord_v[k - 1]; a.nord_w = nord_w_[k]; a.nord_t = nord_t_[k];
+    a.dddmp = f.dddmp; a.d2_bg = d2_divg_[k]; a.d4_bg = f.d4_bg; a.damp_v = c->damp_vt[k - 1]; a.damp_w = damp_w_[k];
+    a.damp_t = damp_t_[k]; a.d_con = d_con_k_[k]; a.kgb = f.ke_bg; a.hydrostatic = f.hydrostatic != 0;
+    a.use_cond = f.use_cond != 0; a.do_f3d = false; a.prevent_diss_cooling = f.prevent_diss_cooling != 0;
+    a.do_diss_est = f.do_diss_est != 0; a.lim_fac = f.lim_fac;
+    L2 heat_s(bd.is, bd.ie, bd.js, bd.je), diss_e(bd.is, bd.ie, bd.js, bd.je), z_rat(bd.isd, bd.ied, bd.jsd, bd.jed, 1.0);
+    // note the aliasing at dyn_core.F90:762: d_sw's delpc dummy is dyn_core's vt work array
+    d_sw(F2(c, FV3_VT, k), F2(c, FV3_DELP, k), F2(c, FV3_PTC, k), F2(c, FV3_PT, k), F2(c, FV3_U, k), F2(c, FV3_V, k),
+         F2(c, FV3_W, k), F2(c, FV3_UC, k), F2(c, FV3_VC, k), F2(c, FV3_UA, k), F2(c, FV3_VA, k), F2(c, FV3_DIVGD, k),
+         F2(c, FV3_MFX, k), F2(c, FV3_MFY, k), F2(c, FV3_CX, k), F2(c, FV3_CY, k), F2(c, FV3_CRX, k), F2(c, FV3_CRY, k),
+         F2(c, FV3_XFX, k), F2(c, FV3_YFX, k), F2(c, FV3_QCON, k), z_rat, heat_s, diss_e, a, g, bd);
+    if (f.d_con > 1.0E-5) {
+      V2 hs = F2(c, FV3_HEAT, k);
+      for (int j = bd.js; j <= bd.je; j++) for (int i = bd.is; i <= bd.ie; i++) hs(i, j) = hs(i, j) + heat_s(i, j);
+    }
+    if (f.do_diss_est) {
+      V2 ds = F2(c, FV3_DISS, k);
+      for (int j = bd.js; j <= bd.je; j++) for (int i = bd.is; i <= bd.ie; i++) ds(i, j) = ds(i, j) + diss_e(i, j);
+    }
+  }
+  (void)nic; (void)njc;
+  return 0;
+}
+
+// dyn_core.F90:911-912 (nord_v, damp_vt as left by the d_sw prologue)
+int fv3o_update_dz_d(fv3o_ctx* c, double dt) {
+  Bd bd(c->b); Grid g(c->g, bd);
+  std::vector<double> dp0 = dp_ref(c), zs = zs_of(c);
+  update_dz_d(c->nord_v.data(), c->damp_vt.data(), c->f.hord_tm, bd.is, bd.ie, bd.js, bd.je, bd.npz, bd.ng, bd.npx, bd.npy,
+              dp0.data(), V2(zs.data(), bd.isd, bd.jsd, bd.ied - bd.isd + 1), F3(c, FV3_ZH), F3(c, FV3_CRX), F3(c, FV3_CRY),
+              F3(c, FV3_XFX), F3(c, FV3_YFX), F2(c, FV3_WS), 1.0 / dt, g, bd, c->f.lim_fac);
+  return 0;
+}
+// dyn_core.F90:932-940
+int fv3o_riem_solver3(fv3o_ctx* c, double dt, int last_call) {
+  Bd bd(c->b);
+  Consts k{c->f.rdgas, c->f.cp_air, c->f.grav, c->f.kappa, c->f.radius, c->f.omega, c->f.pi};
+  std::vector<double> zs = zs_of(c);
+  riem_solver3(c->f.m_split, dt, bd.is, bd.ie, bd.js, bd.je, bd.npz, bd.ng, bd.isd, bd.ied, bd.jsd, bd.jed, c->f.kappa,
+               F3(c, FV3_CAPPA), c->f.cp_air, c->f.ptop, V2(zs.data(), bd.isd, bd.jsd, bd.ied - bd.isd + 1), F3(c, FV3_QCON),
+               F3(c, FV3_W), F3(c, FV3_DELZ), F3(c, FV3_PT), F3(c, FV3_DELP), F3(c, FV3_ZH), c->fld[FV3_PE].data(),
+               F3(c, FV3_PKC), F3(c, FV3_PK3), F3(c, FV3_PK), c->fld[FV3_PELN].data(), F2(c, FV3_WS), c->f.p_fac, c->f.a_imp,
+               c->f.use_logp != 0, c->f.use_cond != 0, c->f.moist_kappa != 0, last_call != 0, c->f.beta < -0.1, k);
+  return 0;
+}
+int fv3o_pk3_halo(fv3o_ctx* c) {
+  Bd bd(c->b);
+  pk3_halo(bd.is, bd.ie, bd.js, bd.je, bd.isd, bd.ied, bd.jsd, bd.jed, bd.npz, c->f.ptop, c->f.kappa, F3(c, FV3_PK3), F3(c, FV3_DELP));
+  return 0;
+}
+int fv3o_pe_halo(fv3o_ctx* c) {
+  Bd bd(c->b);
+  pe_halo(bd.is, bd.ie, bd.js, bd.je, bd.isd, bd.ied, bd.jsd, bd.jed, bd.npz, c->f.ptop, c->fld[FV3_PE].data(), F3(c, FV3_DELP));
+  return 0;
+}
+// dyn_core.F90:982-989
+int fv3o_gz_from_zh(fv3o_ctx* c) {
+  Bd bd(c->b);
+  V3 gz = F3(c, FV3_GZ), zh = F3(c, FV3_ZH);
+  for (int k = 1; k <= bd.npz + 1; k++)
+    for (int j = bd.js - 2; j <= bd.je + 2; j++)
+      for (int i = bd.is - 2; i <= bd.ie + 2; i++) gz(i, j, k) = zh(i, j, k) * c->f.grav;
+  return 0;
+}
+// dyn_core.F90:1032
+int fv3o_nh_p_grad(fv3o_ctx* c, double dt) {
+  Bd bd(c->b); Grid g(c->g, bd);
+  nh_p_grad(F3(c, FV3_U), F3(c, FV3_V), F3(c, FV3_PKC), F3(c, FV3_GZ), F3(c, FV3_DELP), F3(c, FV3_PK3), dt, bd.ng, g, bd,
+            bd.npx, bd.npy, bd.npz, c->f.use_logp != 0, c->f.ptop, c->f.kappa);
+  return 0;
+}
+// dyn_core.F90:370-385 (it==1): gz from zs and delz on the compute domain
+int fv3o_gz_init(fv3o_ctx* c) {
+  Bd bd(c->b);
+  std::vector<double> zs = zs_of(c);
+  V2 zsv(zs.data(), bd.isd, bd.jsd, bd.ied - bd.isd + 1);
+  V3 gz = F3(c, FV3_GZ), delz = F3(c, FV3_DELZ);
+  for (int j = bd.js; j <= bd.je; j++) {
+    for (int i = bd.is; i <= bd.ie; i++) gz(i, j, bd.npz + 1) = zsv(i, j);
+    for (int k = bd.npz; k >= 1; k--) for (int i = bd.is; i <= bd.ie; i++) gz(i, j, k) = gz(i, j, k + 1) - delz(i, j, k);
+  }
+  return 0;
+}
+// dyn_core.F90:491-521: zh = gz (it==1) or gz = zh
+int fv3o_copy_field(fv3o_ctx* c, int dst, int src) {
+  if (c->fld[dst].size() != c->fld[src].size()) return -1;
+  c->fld[dst] = c->fld[src];
+  return 0;
+}
+int fv3o_zero_field(fv3o_ctx* c, int f) { std::fill(c->fld[f].begin(), c->fld[f].end(), 0.0); return 0; }
+
+// stand-alone operators for unit parity
+int fv3o_a2b_ord4(fv3o_ctx* c, int field, int k, double* qout /*(isd:ied,jsd:jed)*/, int replace) {
+  Bd bd(c->b); Grid g(c->g, bd);
+  a2b_ord4(F2(c, field, k), V2(qout, bd.isd, bd.jsd, bd.ied - bd.isd + 1), g, bd, replace != 0);
+  return 0;
+}
+
+}  // extern "C"
