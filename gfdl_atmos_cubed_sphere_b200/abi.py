@@ -1,9 +1,9 @@
 """ctypes mirror of include/fv3_dyncore.h and a thin engine wrapper.
 
-``Engine`` drives either the CUDA library (prefix ``fv3_``; the product) or -- from tests,
-``smoke()`` and ``bench.py``'s CPU-baseline legs only -- the CPU oracle (prefix ``fv3o_``)
-through the same field/stage vocabulary.  The product path fails loudly when the CUDA
-library is missing: there is no CPU fallback.
+``Engine`` drives a library that exports the field/stage vocabulary of the header under a
+symbol prefix.  The package only ever loads the CUDA library (prefix ``fv3_``); the test
+harness reuses the same class for its CPU checker.  The product path fails loudly when the
+CUDA library is missing: there is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -78,21 +78,15 @@ def _ptr(a):
     return a.ctypes.data_as(_dp)
 
 
-def load_library(kind="cuda"):
+def load_library():
+    """The CUDA product library.  Fails loudly when it is missing: no CPU fallback."""
     here = os.path.dirname(os.path.abspath(__file__))
-    if kind == "cuda":
-        path = os.path.join(here, "csrc", "libfv3_b200.so")
-        if not os.path.exists(path):
-            raise RuntimeError(
-                f"CUDA library {path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
-                "There is no CPU fallback for the product path.")
-        return C.CDLL(path), "fv3_"
-    root = os.path.dirname(here)
-    name = {"oracle": "libfv3_oracle.so", "oracle_fast": "libfv3_oracle_fast.so"}[kind]
-    path = os.path.join(root, "oracle", "_build", name)
+    path = os.path.join(here, "csrc", "libfv3_b200.so")
     if not os.path.exists(path):
-        raise RuntimeError(f"oracle library {path} is missing: run `make -C oracle`")
-    return C.CDLL(path), "fv3o_"
+        raise RuntimeError(
+            f"CUDA library {path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU fallback for the product path.")
+    return C.CDLL(path), "fv3_"
 
 
 class Engine:

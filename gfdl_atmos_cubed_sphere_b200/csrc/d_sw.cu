@@ -1,0 +1,751 @@
+// d_sw: full-step D-grid shallow-water sweep for all levels, batched over k.
+//
+// Reference semantics: model/sw_core.F90:494-1606 d_sw (non-SW_DYNAMICS, AM4 variant of the
+// pt damping :1014-1016, inline_q = F), :1608-1737 del6_vt_flux, :2154-2998 xtp_u / ytp_v;
+// per-level damping prologue and call site model/dyn_core.F90:666-812; fill_corners
+// tools/fv_mp_mod.F90:1031-1062 (B-grid) and :1249-1281 (D-grid vector).
+//
+// Design notes (B200-first, not a translation):
+//  * k is batched in gridDim.z; the per-level damping orders/coefficients that dyn_core
+//    computes inside its OpenMP k-loop are small device tables read by blockIdx.z.
+//  * contravariant winds incl. the 4 edge strips and the 4 2x2 corner systems are a
+//    closed-form per-point evaluation (no ordered passes over edges/corners).
+//  * every "fill corners then sweep" of the reference is a read-side index remap.
+//  * prognostics are ping-ponged (fld <-> alt) so no kernel reads what a neighbour thread
+//    writes; the writers copy the halo through so a frozen halo stays frozen.
+//  * uc, vc, divg_d are left intact (the reference trashes them as scratch, sw_core.F90:
+//    1392-1424; the next c_sw overwrites them anyway).
+#include "tp2d.cuh"
+#include "ppm.cuh"
+#include <cmath>
+
+using namespace ppm;
+
+#define TI 32
+#define TJ 8
+#define PLANE_IJK                                              \
+  const int i = L.isd - FV3_IOFF + blockIdx.x * TI + threadIdx.x; \
+  const int j = L.jsd + blockIdx.y * TJ + threadIdx.y;          \
+  const int k = blockIdx.z;                                     \
+  const long long ko = (long long)k * L.plane;
+#define AT(p, i, j) __ldg((p) + ko + LIDX(L, (i), (j)))
+#define G2(p, i, j) __ldg((G.p) + LIDX(L, (i), (j)))
+#define SG(n, i, j) __ldg(G.sin_sg + (long long)((n)-1) * L.plane + LIDX(L, (i), (j)))
+
+static inline dim3 plane_grid(const Lay& L, int nk) { return dim3((L.NI + TI - 1) / TI, (L.NJ + TJ - 1) / TJ, nk); }
+void launch_deln_add(fv3_ctx* c, double* fx, double* fy, const double* fx2, const double* fy2, const double* mass,
+                     int slot_damp, double damp_const, int nk);
+int launch_a2b_ord4(fv3_ctx* c, const double* qin, double* qout, int nk, int replace_into_qin);
+
+// ---------------------------------------------------------------------------------------------
+// contravariant winds, Courant numbers, area fluxes  (sw_core.F90:653-917)
+// ---------------------------------------------------------------------------------------------
+struct WindCtx {
+  const double *uc, *vc; Lay L; DevGrid G; long long ko; double dt;
+  __device__ __forceinline__ double UC(int i, int j) const { return __ldg(uc + ko + LIDX(L, i, j)); }
+  __device__ __forceinline__ double VC(int i, int j) const { return __ldg(vc + ko + LIDX(L, i, j)); }
+  __device__ __forceinline__ double CU(int i, int j) const { return __ldg(G.cosa_u + LIDX(L, i, j)); }
+  __device__ __forceinline__ double CV(int i, int j) const { return __ldg(G.cosa_v + LIDX(L, i, j)); }
+  __device__ __forceinline__ double S(int n, int i, int j) const { return __ldg(G.sin_sg + (long long)(n - 1) * L.plane + LIDX(L, i, j)); }
+  // generic interior formulas (:670-687)
+  __device__ __forceinline__ double UTg(int i, int j) const {
+    return (UC(i, j) - 0.25 * CU(i, j) * (VC(i - 1, j) + VC(i, j) + VC(i - 1, j + 1) + VC(i, j + 1))) * __ldg(G.rsin_u + LIDX(L, i, j));
+  }
+  __device__ __forceinline__ double VTg(int i, int j) const {
+    return (VC(i, j) - 0.25 * CV(i, j) * (UC(i, j - 1) + UC(i + 1, j - 1) + UC(i, j) + UC(i + 1, j))) * __ldg(G.rsin_v + LIDX(L, i, j));
+  }
+  // face-edge values (:692-699, :709-716, :727-735, :746-753)
+  __device__ __forceinline__ double UTe(int i, int j) const {
+    const double u = UC(i, j);
+    return (u * dt > 0.) ? u / S(3, i - 1, j) : u / S(1, i, j);
+  }
+  __device__ __forceinline__ double VTe(int i, int j) const {
+    const double v = VC(i, j);
+    return (v * dt > 0.) ? v / S(4, i, j - 1) : v / S(2, i, j);
+  }
+  __device__ __forceinline__ double UTb(int i, int j) const { return (i == 1 || i == L.npx) ? UTe(i, j) : UTg(i, j); }
+  __device__ __forceinline__ double VTb(int i, int j) const { return (j == 1 || j == L.npy) ? VTe(i, j) : VTg(i, j); }
+
+  __device__ double ut_final(int i, int j) const {
+    if (!L.cube) return UC(i, j);
+    const int npx = L.npx, npy = L.npy;
+    if (i == 1 || i == npx) return UTe(i, j);
+    const bool erow = (j == 0 || j == 1 || j == npy - 1 || j == npy);
+    if (!erow) return UTg(i, j);
+    if (i >= 3 && i <= npx - 2)  // :737-742, :754-759
+      return UC(i, j) - 0.25 * CU(i, j) * (VTb(i - 1, j) + VTb(i, j) + VTb(i - 1, j + 1) + VTb(i, j + 1));
+    // 2x2 corner systems (:772-844)
+    if (i == 2 && j == 0) {
+      const double damp = 1. / (1. - 0.0625 * CU(2, 0) * CV(1, 0));
+      return (UC(2, 0) - 0.25 * CU(2, 0) * (VTb(1, 1) + VTb(2, 1) + VTb(2, 0) + VC(1, 0) - 0.25 * CV(1, 0) * (UTb(1, 0) + UTb(1, -1) + UTb(2, -1)))) * damp;
+    }
+    if (i == 2 && j == 1) {
+      const double damp = 1. / (1. - 0.0625 * CU(2, 1) * CV(1, 2));
+      return (UC(2, 1) - 0.25 * CU(2, 1) * (VTb(1, 1) + VTb(2, 1) + VTb(2, 2) + VC(1, 2) - 0.25 * CV(1, 2) * (UTb(1, 1) + UTb(1, 2) + UTb(2, 2)))) * damp;
+    }
+    if (i == npx - 1 && j == 0) {
+      const double damp = 1. / (1. - 0.0625 * CU(npx - 1, 0) * CV(npx - 1, 0));
+      return (UC(npx - 1, 0) - 0.25 * CU(npx - 1, 0) * (VTb(npx - 1, 1) + VTb(npx - 2, 1) + VTb(npx - 2, 0) + VC(npx - 1, 0) -
+                                                        0.25 * CV(npx - 1, 0) * (UTb(npx, 0) + UTb(npx, -1) + UTb(npx - 1, -1)))) * damp;
+    }
+    if (i == npx - 1 && j == 1) {
+      const double damp = 1. / (1. - 0.0625 * CU(npx - 1, 1) * CV(npx - 1, 2));
+      return (UC(npx - 1, 1) - 0.25 * CU(npx - 1, 1) * (VTb(npx - 1, 1) + VTb(npx - 2, 1) + VTb(npx - 2, 2) + VC(npx - 1, 2) -
+                                                        0.25 * CV(npx - 1, 2) * (UTb(npx, 1) + UTb(npx, 2) + UTb(npx - 1, 2)))) * damp;
+    }
+    if (i == npx - 1 && j == npy) {
+      const double damp = 1. / (1. - 0.0625 * CU(npx - 1, npy) * CV(npx - 1, npy + 1));
+      return (UC(npx - 1, npy) - 0.25 * CU(npx - 1, npy) * (VTb(npx - 1, npy) + VTb(npx - 2, npy) + VTb(npx - 2, npy + 1) + VC(npx - 1, npy + 1) -
+                                                            0.25 * CV(npx - 1, npy + 1) * (UTb(npx, npy) + UTb(npx, npy + 1) + UTb(npx - 1, npy + 1)))) * damp;
+    }
+    if (i == npx - 1 && j == npy - 1) {
+      const double damp = 1. / (1. - 0.0625 * CU(npx - 1, npy - 1) * CV(npx - 1, npy - 1));
+      return (UC(npx - 1, npy - 1) - 0.25 * CU(npx - 1, npy - 1) * (VTb(npx - 1, npy) + VTb(npx - 2, npy) + VTb(npx - 2, npy - 1) + VC(npx - 1, npy - 1) -
+                                                                    0.25 * CV(npx - 1, npy - 1) * (UTb(npx, npy - 1) + UTb(npx, npy - 2) + UTb(npx - 1, npy - 2)))) * damp;
+    }
+    if (i == 2 && j == npy) {
+      const double damp = 1. / (1. - 0.0625 * CU(2, npy) * CV(1, npy + 1));
+      return (UC(2, npy) - 0.25 * CU(2, npy) * (VTb(1, npy) + VTb(2, npy) + VTb(2, npy + 1) + VC(1, npy + 1) -
+                                                0.25 * CV(1, npy + 1) * (UTb(1, npy) + UTb(1, npy + 1) + UTb(2, npy + 1)))) * damp;
+    }
+    if (i == 2 && j == npy - 1) {
+      const double damp = 1. / (1. - 0.0625 * CU(2, npy - 1) * CV(1, npy - 1));
+      return (UC(2, npy - 1) - 0.25 * CU(2, npy - 1) * (VTb(1, npy) + VTb(2, npy) + VTb(2, npy - 1) + VC(1, npy - 1) -
+                                                        0.25 * CV(1, npy - 1) * (UTb(1, npy - 1) + UTb(1, npy - 2) + UTb(2, npy - 2)))) * damp;
+    }
+    return UTg(i, j);  // never set by the reference at these rows (i = 0, npx+1)
+  }
+
+  __device__ double vt_final(int i, int j) const {
+    if (!L.cube) return VC(i, j);
+    const int npx = L.npx, npy = L.npy;
+    if (j == 1 || j == npy) return VTe(i, j);
+    const bool ecol = (i == 0 || i == 1 || i == npx - 1 || i == npx);
+    if (!ecol) return VTg(i, j);
+    if (j >= 3 && j <= npy - 2)  // :700-705, :718-723
+      return VC(i, j) - 0.25 * CV(i, j) * (UTb(i, j - 1) + UTb(i + 1, j - 1) + UTb(i, j) + UTb(i + 1, j));
+    if (i == 0 && j == 2) {
+      const double damp = 1. / (1. - 0.0625 * CU(0, 1) * CV(0, 2));
+      return (VC(0, 2) - 0.25 * CV(0, 2) * (UTb(1, 1) + UTb(1, 2) + UTb(0, 2) + UC(0, 1) - 0.25 * CU(0, 1) * (VTb(0, 1) + VTb(-1, 1) + VTb(-1, 2)))) * damp;
+    }
+    if (i == 1 && j == 2) {
+      const double damp = 1. / (1. - 0.0625 * CU(2, 1) * CV(1, 2));
+      return (VC(1, 2) - 0.25 * CV(1, 2) * (UTb(1, 1) + UTb(1, 2) + UTb(2, 2) + UC(2, 1) - 0.25 * CU(2, 1) * (VTb(1, 1) + VTb(2, 1) + VTb(2, 2)))) * damp;
+    }
+    if (i == npx && j == 2) {
+      const double damp = 1. / (1. - 0.0625 * CU(npx + 1, 1) * CV(npx, 2));
+      return (VC(npx, 2) - 0.25 * CV(npx, 2) * (UTb(npx, 1) + UTb(npx, 2) + UTb(npx + 1, 2) + UC(npx + 1, 1) -
+                                                0.25 * CU(npx + 1, 1) * (VTb(npx, 1) + VTb(npx + 1, 1) + VTb(npx + 1, 2)))) * damp;
+    }
+    if (i == npx - 1 && j == 2) {
+      const double damp = 1. / (1. - 0.0625 * CU(npx - 1, 1) * CV(npx - 1, 2));
+      return (VC(npx - 1, 2) - 0.25 * CV(npx - 1, 2) * (UTb(npx, 1) + UTb(npx, 2) + UTb(npx - 1, 2) + UC(npx - 1, 1) -
+                                                        0.25 * CU(npx - 1, 1) * (VTb(npx - 1, 1) + VTb(npx - 2, 1) + VTb(npx - 2, 2)))) * damp;
+    }
+    if (i == npx && j == npy - 1) {
+      const double damp = 1. / (1. - 0.0625 * CU(npx + 1, npy - 1) * CV(npx, npy - 1));
+      return (VC(npx, npy - 1) - 0.25 * CV(npx, npy - 1) * (UTb(npx, npy - 1) + UTb(npx, npy - 2) + UTb(npx + 1, npy - 2) + UC(npx + 1, npy - 1) -
+                                                            0.25 * CU(npx + 1, npy - 1) * (VTb(npx, npy) + VTb(npx + 1, npy) + VTb(npx + 1, npy - 1)))) * damp;
+    }
+    if (i == npx - 1 && j == npy - 1) {
+      const double damp = 1. / (1. - 0.0625 * CU(npx - 1, npy - 1) * CV(npx - 1, npy - 1));
+      return (VC(npx - 1, npy - 1) - 0.25 * CV(npx - 1, npy - 1) * (UTb(npx, npy - 1) + UTb(npx, npy - 2) + UTb(npx - 1, npy - 2) + UC(npx - 1, npy - 1) -
+                                                                    0.25 * CU(npx - 1, npy - 1) * (VTb(npx - 1, npy) + VTb(npx - 2, npy) + VTb(npx - 2, npy - 1)))) * damp;
+    }
+    if (i == 0 && j == npy - 1) {
+      const double damp = 1. / (1. - 0.0625 * CU(0, npy - 1) * CV(0, npy - 1));
+      return (VC(0, npy - 1) - 0.25 * CV(0, npy - 1) * (UTb(1, npy - 1) + UTb(1, npy - 2) + UTb(0, npy - 2) + UC(0, npy - 1) -
+                                                        0.25 * CU(0, npy - 1) * (VTb(0, npy) + VTb(-1, npy) + VTb(-1, npy - 1)))) * damp;
+    }
+    if (i == 1 && j == npy - 1) {
+      const double damp = 1. / (1. - 0.0625 * CU(2, npy - 1) * CV(1, npy - 1));
+      return (VC(1, npy - 1) - 0.25 * CV(1, npy - 1) * (UTb(1, npy - 1) + UTb(1, npy - 2) + UTb(2, npy - 2) + UC(2, npy - 1) -
+                                                        0.25 * CU(2, npy - 1) * (VTb(1, npy) + VTb(2, npy) + VTb(2, npy - 1)))) * damp;
+    }
+    return VTg(i, j);
+  }
+};
+
+__global__ void __launch_bounds__(TI* TJ) k_dsw_wind(Lay L, DevGrid G, const double* __restrict__ uc, const double* __restrict__ vc,
+                                                    double* __restrict__ uts, double* __restrict__ vts, double* __restrict__ crx,
+                                                    double* __restrict__ cry, double* __restrict__ xfx, double* __restrict__ yfx,
+                                                    double* __restrict__ cx, double* __restrict__ cy, double dt) {
+  PLANE_IJK
+  if (i < L.isd || i > L.ied + 1 || j > L.jed + 1) return;
+  WindCtx W{uc, vc, L, G, ko, dt};
+  const long long o = ko + LIDX(L, i, j);
+  // ut on (is-1:ie+2, jsd:jed)
+  if (j <= L.jed && i >= L.is - 1 && i <= L.ie + 2) {
+    const double ut = W.ut_final(i, j);
+    uts[o] = ut;
+    if (i >= L.is && i <= L.ie + 1) {  // :863-890, :923-927
+      double xf = dt * ut, cr;
+      if (xf > 0.) { cr = xf * G2(rdxa, i - 1, j); xf = G2(dy, i, j) * xf * SG(3, i - 1, j); }
+      else { cr = xf * G2(rdxa, i, j); xf = G2(dy, i, j) * xf * SG(1, i, j); }
+      crx[o] = cr; xfx[o] = xf; cx[o] = cx[o] + cr;
+    }
+  }
+  // vt on (isd:ied, js-1:je+2)
+  if (i <= L.ied && j >= L.js - 1 && j <= L.je + 2) {
+    const double vt = W.vt_final(i, j);
+    vts[o] = vt;
+    if (j >= L.js && j <= L.je + 1) {  // :869-902, :933-936
+      double yf = dt * vt, cr;
+      if (yf > 0.) { cr = yf * G2(rdya, i, j - 1); yf = G2(dx, i, j) * yf * SG(4, i, j - 1); }
+      else { cr = yf * G2(rdya, i, j); yf = G2(dx, i, j) * yf * SG(2, i, j); }
+      cry[o] = cr; yfx[o] = yf; cy[o] = cy[o] + cr;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalar updates
+// ---------------------------------------------------------------------------------------------
+// q_out = q*delp + div(g)*rarea on the compute domain, halo copied through (sw_core.F90:985-999)
+__global__ void __launch_bounds__(TI* TJ) k_dsw_qdp(Lay L, DevGrid G, const double* __restrict__ q, const double* __restrict__ delp,
+                                                   const double* __restrict__ gx, const double* __restrict__ gy, double* __restrict__ qout) {
+  PLANE_IJK
+  if (i < L.isd || i > L.ied || j > L.jed) return;
+  const long long o = ko + LIDX(L, i, j);
+  if (i >= L.is && i <= L.ie && j >= L.js && j <= L.je)
+    qout[o] = __ldg(delp + o) * __ldg(q + o) + (gx[o] - gx[o + 1] + gy[o] - gy[o + L.NI]) * G2(rarea, i, j);
+  else
+    qout[o] = __ldg(q + o);
+}
+// pt, delp update + flux capacitors (sw_core.F90:928-940, :1053-1066)
+__global__ void __launch_bounds__(TI* TJ) k_dsw_ptdp(Lay L, DevGrid G, const double* __restrict__ pt, const double* __restrict__ delp,
+                                                    const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ gx,
+                                                    const double* __restrict__ gy, double* __restrict__ pt_out, double* __restrict__ delp_out,
+                                                    double* __restrict__ mfx, double* __restrict__ mfy) {
+  PLANE_IJK
+  if (i < L.isd || i > L.ied + 1 || j > L.jed + 1) return;
+  const long long o = ko + LIDX(L, i, j);
+  if (i >= L.is && i <= L.ie + 1 && j >= L.js && j <= L.je) mfx[o] = mfx[o] + fx[o];
+  if (i >= L.is && i <= L.ie && j >= L.js && j <= L.je + 1) mfy[o] = mfy[o] + fy[o];
+  if (i > L.ied || j > L.jed) return;
+  if (i >= L.is && i <= L.ie && j >= L.js && j <= L.je) {
+    const double ra = G2(rarea, i, j), dp = __ldg(delp + o);
+    double p = __ldg(pt + o) * dp + (gx[o] - gx[o + 1] + gy[o] - gy[o + L.NI]) * ra;
+    const double dpn = dp + (fx[o] - fx[o + 1] + fy[o] - fy[o + L.NI]) * ra;
+    delp_out[o] = dpn;
+    pt_out[o] = p / dpn;
+  } else {
+    delp_out[o] = __ldg(delp + o);
+    pt_out[o] = __ldg(pt + o);
+  }
+}
+// w damping increment and heating (sw_core.F90:951-982); hs = heat_s work plane, ds = diss_e
+__global__ void __launch_bounds__(TI* TJ) k_dsw_dw(Lay L, DevGrid G, const double* __restrict__ w, const double* __restrict__ fx2,
+                                                  const double* __restrict__ fy2, double* __restrict__ dw, double* __restrict__ hs,
+                                                  double* __restrict__ ds, const double* kdbl, double kgb, double dt, int prevent, int do_diss) {
+  PLANE_IJK
+  if (i < L.is || i > L.ie || j < L.js || j > L.je) return;
+  const long long o = ko + LIDX(L, i, j);
+  const double coef = kdbl[KD_DAMP4_W * (L.npz + 1) + k];
+  if (coef == 0.) { dw[o] = 0.; hs[o] = 0.; ds[o] = 0.; return; }
+  const double dd8 = kgb * fabs(dt);
+  const double d = (fx2[o] - fx2[o + 1] + fy2[o] - fy2[o + L.NI]) * G2(rarea, i, j);
+  dw[o] = d;
+  const double wv = __ldg(w + o);
+  const double tmp = d * (wv + 0.5 * d);
+  if (prevent) { hs[o] = dd8 - fmin(0., tmp); ds[o] = do_diss ? dd8 - tmp : 0.; }
+  else { hs[o] = dd8 - tmp; ds[o] = do_diss ? dd8 - tmp : 0.; }
+}
+// w = w/delp (+dw), q_con = q_con/delp  (sw_core.F90:1262-1283); in place, pointwise
+__global__ void __launch_bounds__(TI* TJ) k_dsw_wfin(Lay L, double* __restrict__ w, const double* __restrict__ delp_new,
+                                                    const double* __restrict__ dw, const double* kdbl, int have_dw) {
+  PLANE_IJK
+  if (i < L.is || i > L.ie || j < L.js || j > L.je) return;
+  const long long o = ko + LIDX(L, i, j);
+  double v = w[o] / __ldg(delp_new + o);
+  if (have_dw && kdbl[KD_DAMP4_W * (L.npz + 1) + k] != 0.) v = v + dw[o];
+  w[o] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kinetic energy at cell corners (sw_core.F90:1078-1228)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TI* TJ) k_dsw_ke(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
+                                                  const double* __restrict__ uc, const double* __restrict__ vc, const double* __restrict__ uts,
+                                                  const double* __restrict__ vts, double* __restrict__ ke, double dt, int hord_mt) {
+  PLANE_IJK
+  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
+  const int npx = L.npx, npy = L.npy;
+  const bool cube = L.cube;
+  const double dt5 = 0.5 * dt, dt4 = 0.25 * dt;
+  auto UT = [&](int ii, int jj) { return AT(uts, ii, jj); };
+  auto VT = [&](int ii, int jj) { return AT(vts, ii, jj); };
+  double vb, ub;
+  if (!cube) {
+    vb = dt5 * (AT(vc, i - 1, j) + AT(vc, i, j));
+    ub = dt5 * (AT(uc, i, j - 1) + AT(uc, i, j));
+  } else {
+    if (j == 1 || j == npy) vb = dt5 * (VT(i - 1, j) + VT(i, j));
+    else if (i == 1 || i == npx) vb = dt4 * (-VT(i - 2, j) + 3. * (VT(i - 1, j) + VT(i, j)) - VT(i + 1, j));
+    else vb = dt5 * (AT(vc, i - 1, j) + AT(vc, i, j) - (AT(uc, i, j - 1) + AT(uc, i, j)) * G2(cosa, i, j)) * G2(rsina, i, j);
+    if (i == 1 || i == npx) ub = dt5 * (UT(i, j - 1) + UT(i, j));
+    else if (j == 1 || j == npy) ub = dt4 * (-UT(i, j - 2) + 3. * (UT(i, j - 1) + UT(i, j)) - UT(i, j + 1));
+    else ub = dt5 * (AT(uc, i, j - 1) + AT(uc, i, j) - (AT(vc, i - 1, j) + AT(vc, i, j)) * G2(cosa, i, j)) * G2(rsina, i, j);
+  }
+  // ytp_v: advect v along y with vb (:1134)
+  double k1;
+  {
+    Acc va{v + ko, LIDX(L, i, 0), L.NI};
+    Acc dya{G.dy, LIDX(L, i, 0), L.NI}, rdy{G.rdy, LIDX(L, i, 0), L.NI};
+    const double f = flux_wind(va, dya, rdy, j, vb, hord_mt, npy, cube, cube && (i == 1 || i == npx));
+    k1 = vb * f;
+  }
+  // xtp_u: advect u along x with ub (:1191)
+  double k2;
+  {
+    Acc ua{u + ko, LIDX(L, 0, j), 1};
+    Acc dxa{G.dx, LIDX(L, 0, j), 1}, rdx{G.rdx, LIDX(L, 0, j), 1};
+    const double f = flux_wind(ua, dxa, rdx, i, ub, hord_mt, npx, cube, cube && (j == 1 || j == npy));
+    k2 = ub * f;
+  }
+  double kev = 0.5 * (k1 + k2);
+  if (cube) {  // :1203-1228
+    const double dt6 = dt / 6.;
+    if (i == 1 && j == 1)
+      kev = dt6 * ((UT(1, 1) + UT(1, 0)) * AT(u, 1, 1) + (VT(1, 1) + VT(0, 1)) * AT(v, 1, 1) + (UT(1, 1) + VT(1, 1)) * AT(u, 0, 1));
+    else if (i == npx && j == 1)
+      kev = dt6 * ((UT(i, 1) + UT(i, 0)) * AT(u, i - 1, 1) + (VT(i, 1) + VT(i - 1, 1)) * AT(v, i, 1) + (UT(i, 1) - VT(i - 1, 1)) * AT(u, i, 1));
+    else if (i == npx && j == npy)
+      kev = dt6 * ((UT(i, j) + UT(i, j - 1)) * AT(u, i - 1, j) + (VT(i, j) + VT(i - 1, j)) * AT(v, i, j - 1) + (UT(i, j - 1) + VT(i - 1, j)) * AT(u, i, j));
+    else if (i == 1 && j == npy)
+      kev = dt6 * ((UT(1, j) + UT(1, j - 1)) * AT(u, 1, j) + (VT(1, j) + VT(0, j)) * AT(v, 1, j - 1) + (UT(1, j - 1) - VT(1, j)) * AT(u, 0, j));
+  }
+  ke[ko + LIDX(L, i, j)] = kev;
+}
+
+// relative vorticity wk and absolute vorticity wk + f0 on the data domain (:1231-1247, :1476-1496)
+__global__ void __launch_bounds__(TI* TJ) k_dsw_vort(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
+                                                    double* __restrict__ wk, double* __restrict__ vq) {
+  PLANE_IJK
+  if (i < L.isd || i > L.ied || j > L.jed) return;
+  const long long o = ko + LIDX(L, i, j);
+  const double vt0 = AT(u, i, j) * G2(dx, i, j), vt1 = AT(u, i, j + 1) * G2(dx, i, j + 1);
+  const double ut0 = AT(v, i, j) * G2(dy, i, j), ut1 = AT(v, i + 1, j) * G2(dy, i + 1, j);
+  const double w = G2(rarea, i, j) * (vt0 - vt1 - ut0 + ut1);
+  wk[o] = w;
+  vq[o] = w + G2(f0, i, j);
+}
+
+// ---------------------------------------------------------------------------------------------
+// divergence damping
+// ---------------------------------------------------------------------------------------------
+// B-grid scalar with fill_corners(BGRID) views (fv_mp_mod.F90:1031-1062)
+struct BFillX {
+  const double* q; Lay L; bool on;
+  __device__ __forceinline__ double operator()(int ii, int jj) const {
+    if (on) {
+      const int npx = L.npx, npy = L.npy;
+      if (ii < 1 && jj < 1) { const int a = jj, b = 2 - ii; ii = a; jj = b; }
+      else if (ii < 1 && jj > npy) { const int a = npy + 1 - jj, b = npy - 1 + ii; ii = a; jj = b; }
+      else if (ii > npx && jj < 1) { const int a = npx + 1 - jj, b = ii - npx + 1; ii = a; jj = b; }
+      else if (ii > npx && jj > npy) { const int a = npx + jj - npy, b = npy - ii + npx; ii = a; jj = b; }
+    }
+    return __ldg(q + LIDX(L, ii, jj));
+  }
+};
+struct BFillY {
+  const double* q; Lay L; bool on;
+  __device__ __forceinline__ double operator()(int ii, int jj) const {
+    if (on) {
+      const int npx = L.npx, npy = L.npy;
+      if (ii < 1 && jj < 1) { const int a = 2 - jj, b = ii; ii = a; jj = b; }
+      else if (ii < 1 && jj > npy) { const int a = jj - npy + 1, b = npy + 1 - ii; ii = a; jj = b; }
+      else if (ii > npx && jj < 1) { const int a = npx - 1 + jj, b = 1 - ii + npx; ii = a; jj = b; }
+      else if (ii > npx && jj > npy) { const int a = npx - jj + npy, b = npy + ii - npx; ii = a; jj = b; }
+    }
+    return __ldg(q + LIDX(L, ii, jj));
+  }
+};
+
+// n-th pass, part 1: vc = d/dx divg * divg_u, uc = d/dy divg * divg_v  (:1392-1403)
+__global__ void __launch_bounds__(TI* TJ) k_dsw_dd_uv(Lay L, DevGrid G, const double* __restrict__ dg, double* __restrict__ vcs,
+                                                     double* __restrict__ ucs, const int* kint, int n) {
+  PLANE_IJK
+  const int nord = kint[KI_NORD * (L.npz + 1) + k];
+  if (n > nord) return;
+  const int nt = nord - n;
+  const bool fill_c = (nt != 0) && L.cube;
+  if (i >= L.is - 1 - nt && i <= L.ie + 1 + nt && j >= L.js - nt && j <= L.je + 1 + nt) {
+    BFillX d{dg + ko, L, fill_c};
+    vcs[ko + LIDX(L, i, j)] = (d(i + 1, j) - d(i, j)) * G2(divg_u, i, j);
+  }
+  if (i >= L.is - nt && i <= L.ie + 1 + nt && j >= L.js - 1 - nt && j <= L.je + 1 + nt) {
+    BFillY d{dg + ko, L, fill_c};
+    ucs[ko + LIDX(L, i, j)] = (d(i, j + 1) - d(i, j)) * G2(divg_v, i, j);
+  }
+}
+// part 2: divg = div(uc, vc) * rarea_c with fill_corners(vc,uc,VECTOR,DGRID) views (:1405-1424)
+__global__ void __launch_bounds__(TI* TJ) k_dsw_dd_div(Lay L, DevGrid G, const double* __restrict__ vcs, const double* __restrict__ ucs,
+                                                      double* __restrict__ dg, const int* kint, int n, int stretched) {
+  PLANE_IJK
+  const int nord = kint[KI_NORD * (L.npz + 1) + k];
+  if (n > nord) return;
+  const int nt = nord - n;
+  if (i < L.is - nt || i > L.ie + 1 + nt || j < L.js - nt || j > L.je + 1 + nt) return;
+  const bool fill_c = (nt != 0) && L.cube;
+  const int npx = L.npx, npy = L.npy;
+  const double s = -1.0;
+  // x = vc (u-like), y = uc (v-like): fv_mp_mod.F90:1262-1277
+  auto VCv = [&](int ii, int jj) -> double {
+    if (fill_c) {
+      if (ii <= 0 && jj <= 0) return s * AT(ucs, jj, 1 - ii);
+      if (ii <= 0 && jj >= npy + 1) return AT(ucs, npy + 1 - jj, npy - 1 + ii);
+      if (ii >= npx && jj <= 0) return AT(ucs, npx + 1 - jj, ii - npx + 1);
+      if (ii >= npx && jj >= npy + 1) return s * AT(ucs, npx + jj - npy, npy - ii + npx - 1);
+    }
+    return AT(vcs, ii, jj);
+  };
+  auto UCv = [&](int ii, int jj) -> double {
+    if (fill_c) {
+      if (ii <= 0 && jj <= 0) return s * AT(vcs, 1 - jj, ii);
+      if (ii <= 0 && jj >= npy) return AT(vcs, jj - npy + 1, npy + 1 - ii);
+      if (ii >= npx + 1 && jj <= 0) return AT(vcs, npx - 1 + jj, 1 - ii + npx);
+      if (ii >= npx + 1 && jj >= npy) return s * AT(vcs, npx - jj + npy - 1, npy + ii - npx);
+    }
+    return AT(ucs, ii, jj);
+  };
+  double d = UCv(i, j - 1) - UCv(i, j) + VCv(i - 1, j) - VCv(i, j);
+  if (L.cube) {
+    if (i == 1 && j == 1) d = d - UCv(1, 0);
+    if (i == npx && j == 1) d = d - UCv(npx, 0);
+    if (i == npx && j == npy) d = d + UCv(npx, npy);
+    if (i == 1 && j == npy) d = d + UCv(1, npy);
+  }
+  if (!stretched) d = d * G2(rarea_c, i, j);
+  dg[ko + LIDX(L, i, j)] = d;
+}
+
+// final damping term (both branches) and ke += term.  dterm = the reference's B-grid "vort".
+// nord==0 levels: del-2 from u, v, ua, va (:1290-1371); nord>0: :1376-1458
+__global__ void __launch_bounds__(TI* TJ) k_dsw_damp(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
+                                                    const double* __restrict__ ua, const double* __restrict__ va, const double* __restrict__ uc,
+                                                    const double* __restrict__ vc, const double* __restrict__ divg_in,
+                                                    const double* __restrict__ dg, const double* __restrict__ vortb, double* __restrict__ ke,
+                                                    double* __restrict__ dterm, const int* kint, const double* kdbl, double dt, double dddmp,
+                                                    double d4_bg, int stretched) {
+  PLANE_IJK
+  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
+  const int npx = L.npx, npy = L.npy;
+  const bool cube = L.cube;
+  const int nord = kint[KI_NORD * (L.npz + 1) + k];
+  const double d2_bg = kdbl[KD_D2BG * (L.npz + 1) + k];
+  const long long o = ko + LIDX(L, i, j);
+  double term;
+  if (nord == 0) {
+    auto PTC = [&](int ii, int jj) -> double {
+      if (cube && (jj == 1 || jj == npy)) {
+        return (AT(vc, ii, jj) > 0) ? AT(u, ii, jj) * G2(dyc, ii, jj) * SG(4, ii, jj - 1) : AT(u, ii, jj) * G2(dyc, ii, jj) * SG(2, ii, jj);
+      }
+      return (AT(u, ii, jj) - 0.5 * (AT(va, ii, jj - 1) + AT(va, ii, jj)) * G2(cosa_v, ii, jj)) * G2(dyc, ii, jj) * G2(sina_v, ii, jj);
+    };
+    auto VRT = [&](int ii, int jj) -> double {
+      if (cube && (ii == 1 || ii == npx)) {
+        return (AT(uc, ii, jj) > 0) ? AT(v, ii, jj) * G2(dxc, ii, jj) * SG(3, ii - 1, jj) : AT(v, ii, jj) * G2(dxc, ii, jj) * SG(1, ii, jj);
+      }
+      return (AT(v, ii, jj) - 0.5 * (AT(ua, ii - 1, jj) + AT(ua, ii, jj)) * G2(cosa_u, ii, jj)) * G2(dxc, ii, jj) * G2(sina_u, ii, jj);
+    };
+    double dpc = VRT(i, j - 1) - VRT(i, j) + PTC(i - 1, j) - PTC(i, j);
+    if (cube) {
+      if (i == 1 && j == 1) dpc = dpc - VRT(1, 0);
+      if (i == npx && j == 1) dpc = dpc - VRT(npx, 0);
+      if (i == npx && j == npy) dpc = dpc + VRT(npx, npy);
+      if (i == 1 && j == npy) dpc = dpc + VRT(1, npy);
+    }
+    dpc = G2(rarea_c, i, j) * dpc;
+    const double damp = G.da_min_c * fmax(d2_bg, fmin(0.20, dddmp * fabs(dpc * dt)));
+    term = damp * dpc;
+  } else {
+    const double dpc = __ldg(divg_in + o);   // delpc = divg_d saved before the loop (:1376-1381)
+    double vo = 0.;
+    if (dddmp >= 1.E-5) {
+      const double vb = __ldg(vortb + o);
+      vo = fabs(dt) * sqrt(dpc * dpc + vb * vb);
+    }
+    const int n2 = nord + 1;
+    const double dd8 = stretched ? G.da_min * pow(d4_bg, (double)n2) : pow(G.da_min_c * d4_bg, (double)n2);
+    const double damp2 = G.da_min_c * fmax(d2_bg, fmin(0.20, dddmp * vo));
+    term = damp2 * dpc + dd8 * __ldg(dg + o);
+  }
+  dterm[o] = term;
+  ke[o] = ke[o] + term;
+}
+
+// ---------------------------------------------------------------------------------------------
+// momentum update  (sw_core.F90:1500-1509), halo copied through
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TI* TJ) k_dsw_uv(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
+                                                  const double* __restrict__ ke, const double* __restrict__ fx, const double* __restrict__ fy,
+                                                  double* __restrict__ uo, double* __restrict__ vo) {
+  PLANE_IJK
+  if (i < L.isd || i > L.ied + 1 || j > L.jed + 1) return;
+  const long long o = ko + LIDX(L, i, j);
+  if (i <= L.ied) {
+    if (i >= L.is && i <= L.ie && j >= L.js && j <= L.je + 1)
+      uo[o] = __ldg(u + o) * G2(dx, i, j) + ke[o] - ke[o + 1] + fy[o];
+    else
+      uo[o] = __ldg(u + o);
+  }
+  if (j <= L.jed) {
+    if (i >= L.is && i <= L.ie + 1 && j >= L.js && j <= L.je)
+      vo[o] = __ldg(v + o) * G2(dy, i, j) + ke[o] - ke[o + L.NI] - fx[o];
+    else
+      vo[o] = __ldg(v + o);
+  }
+}
+
+// dissipative heating / dissipation estimate (:1462-1473, :1523-1586) and the vorticity-damping
+// momentum increments (:1589-1600).  ut_d, vt_d = del6_vt_flux outputs (x-flux "ut", y-flux "vt").
+__global__ void __launch_bounds__(TI* TJ) k_dsw_heat(Lay L, DevGrid G, const double* __restrict__ un, const double* __restrict__ vn,
+                                                    const double* __restrict__ uold, const double* __restrict__ vold,
+                                                    const double* __restrict__ dterm, const double* __restrict__ ut_d, const double* __restrict__ vt_d,
+                                                    const double* __restrict__ delp_new, const double* __restrict__ hs, const double* __restrict__ ds,
+                                                    double* __restrict__ heat, double* __restrict__ diss, const double* kdbl, int prevent,
+                                                    int do_diss, double d_con_flag) {
+  PLANE_IJK
+  if (i < L.is || i > L.ie || j < L.js || j > L.je) return;
+  const double d_con = kdbl[KD_DCON * (L.npz + 1) + k];
+  const bool have_v = kdbl[KD_DAMP4_V * (L.npz + 1) + k] != 0.;
+  const long long o = ko + LIDX(L, i, j);
+  double hsv = __ldg(hs + o), dsv = __ldg(ds + o);
+  if (d_con > 1.e-5 || do_diss) {
+    auto UB = [&](int ii, int jj) {  // (ub + vt)*rdx on (is:ie, js:je+1)
+      const double ub = AT(dterm, ii, jj) - AT(dterm, ii + 1, jj);
+      // without vorticity damping and without do_diss_est the reference's vt still holds u*dx (sw_core.F90:1233,1516)
+      const double vt = have_v ? AT(vt_d, ii, jj) : (do_diss ? 0. : AT(uold, ii, jj) * G2(dx, ii, jj));
+      return (ub + vt) * G2(rdx, ii, jj);
+    };
+    auto VB = [&](int ii, int jj) {  // (vb - ut)*rdy on (is:ie+1, js:je)
+      const double vb = AT(dterm, ii, jj) - AT(dterm, ii, jj + 1);
+      const double ut = have_v ? AT(ut_d, ii, jj) : (do_diss ? 0. : AT(vold, ii, jj) * G2(dy, ii, jj));
+      return (vb - ut) * G2(rdy, ii, jj);
+    };
+    const double ub0 = UB(i, j), ub1 = UB(i, j + 1), vb0 = VB(i, j), vb1 = VB(i + 1, j);
+    const double fy0 = AT(un, i, j) * G2(rdx, i, j), fy1 = AT(un, i, j + 1) * G2(rdx, i, j + 1);
+    const double fx0 = AT(vn, i, j) * G2(rdy, i, j), fx1 = AT(vn, i + 1, j) * G2(rdy, i + 1, j);
+    const double gy0 = fy0 * ub0, gy1 = fy1 * ub1, gx0 = fx0 * vb0, gx1 = fx1 * vb1;
+    const double u2 = fy0 + fy1, du2 = ub0 + ub1, v2 = fx0 + fx1, dv2 = vb0 + vb1;
+    const double inner = ((ub0 * ub0 + ub1 * ub1 + vb0 * vb0 + vb1 * vb1) + 2. * (gy0 + gy1 + gx0 + gx1) -
+                          G2(cosa_s, i, j) * (u2 * dv2 + v2 * du2 + du2 * dv2));
+    const double damp = 0.25 * d_con;
+    if (prevent) {
+      const double tmp = G2(rsin2, i, j) * inner;
+      if (d_con > 1.e-5) hsv = __ldg(delp_new + o) * (hsv - damp * fmin(0., tmp));
+      if (do_diss) dsv = dsv - tmp;
+    } else {
+      hsv = __ldg(delp_new + o) * (hsv - damp * G2(rsin2, i, j) * inner);
+      if (do_diss) dsv = dsv - G2(rsin2, i, j) * inner;
+    }
+  }
+  // dyn_core.F90:798-811 accumulation into the 3-D arrays
+  if (d_con_flag > 1.0E-5) heat[o] = heat[o] + hsv;
+  if (do_diss) diss[o] = diss[o] + dsv;
+}
+__global__ void __launch_bounds__(TI* TJ) k_dsw_vdamp(Lay L, double* __restrict__ un, double* __restrict__ vn, const double* __restrict__ ut_d,
+                                                     const double* __restrict__ vt_d, const double* kdbl) {
+  PLANE_IJK
+  if (kdbl[KD_DAMP4_V * (L.npz + 1) + k] == 0.) return;
+  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
+  const long long o = ko + LIDX(L, i, j);
+  if (i <= L.ie) un[o] = un[o] + vt_d[o];
+  if (j <= L.je) vn[o] = vn[o] - ut_d[o];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------
+static void dsw_tables(fv3_ctx* c, std::vector<int>& ki, std::vector<double>& kd) {
+  // model/dyn_core.F90:666-733
+  const fv3_flags_t& f = c->f;
+  const int npz = c->L.npz, n1 = npz + 1;
+  ki.assign(FV3_KSLOTS * n1, 0); kd.assign(FV3_KSLOTS * n1, 0.);
+  for (int k = 1; k <= npz; k++) {
+    int nord_k = f.nord;
+    c->nord_v[k - 1] = std::min(2, f.nord);
+    double d2_divg = std::min(0.20, f.d2_bg);
+    c->damp_vt[k - 1] = f.do_vort_damp ? f.vtdm4 : 0.;
+    int nord_w = c->nord_v[k - 1], nord_t = c->nord_v[k - 1];
+    double damp_w = c->damp_vt[k - 1], damp_t = c->damp_vt[k - 1], d_con_k = f.d_con;
+    if (npz == 1 || f.n_sponge < 0) {
+      d2_divg = f.d2_bg;
+    } else {
+      if (k == 1) {
+        nord_k = 0;
+        d2_divg = f.is_ideal_case ? std::max(f.d2_bg, f.d2_bg_k1) : std::max(0.01, std::max(f.d2_bg, f.d2_bg_k1));
+        nord_w = 0; damp_w = d2_divg;
+        if (f.do_vort_damp) { c->nord_v[k - 1] = 0; c->damp_vt[k - 1] = 0.5 * d2_divg; }
+        d_con_k = 0.;
+      } else if (k == 2 && f.d2_bg_k2 > 0.01) {
+        nord_k = 0; d2_divg = std::max(f.d2_bg, f.d2_bg_k2);
+        nord_w = 0; damp_w = d2_divg;
+        if (f.do_vort_damp) { c->nord_v[k - 1] = 0; c->damp_vt[k - 1] = 0.5 * d2_divg; }
+        d_con_k = 0.;
+      } else if (k == 3 && f.d2_bg_k2 > 0.05) {
+        nord_k = 0; d2_divg = std::max(f.d2_bg, 0.2 * f.d2_bg_k2);
+        nord_w = 0; damp_w = d2_divg;
+        d_con_k = 0.;
+      }
+    }
+    const int kk = k - 1;
+    const int nord_v = c->nord_v[kk]; const double damp_v = c->damp_vt[kk];
+    ki[KI_NORD * n1 + kk] = nord_k; ki[KI_NORD_V * n1 + kk] = nord_v; ki[KI_NORD_W * n1 + kk] = nord_w; ki[KI_NORD_T * n1 + kk] = nord_t;
+    kd[KD_D2BG * n1 + kk] = d2_divg; kd[KD_DAMP_V * n1 + kk] = damp_v; kd[KD_DAMP_W * n1 + kk] = damp_w; kd[KD_DAMP_T * n1 + kk] = damp_t;
+    kd[KD_DCON * n1 + kk] = d_con_k;
+    kd[KD_DAMP4_W * n1 + kk] = (!f.hydrostatic && damp_w > 1.E-5) ? pow(damp_w * c->G.da_min_c, (double)(nord_w + 1)) : 0.;   // sw_core.F90:951-953
+    kd[KD_DAMP4_V * n1 + kk] = (damp_v > 1.E-5) ? pow(damp_v * c->G.da_min_c, (double)(nord_v + 1)) : 0.;   // :1513-1514
+    kd[KD_DELN * n1 + kk] = (damp_v > 1.e-4) ? pow(damp_v * c->G.da_min, (double)(nord_v + 1)) : 0.;       // tp_core.F90:202-203, delp (nord_v, damp_v)
+    kd[KD_DELN_T * n1 + kk] = (damp_t > 1.e-4) ? pow(damp_t * c->G.da_min, (double)(nord_t + 1)) : 0.;     // pt, q_con (nord_t, damp_t)
+  }
+}
+
+int stage_d_sw(fv3_ctx* c, double dt) {
+  StageScope ts(c, "D_SW");
+  const Lay& L = c->L;
+  const fv3_flags_t& f = c->f;
+  const int nk = L.npz;
+  if (!hord_supported(f.hord_dp) || !hord_supported(f.hord_tm) || !hord_supported(f.hord_vt) || !hord_wind_supported(f.hord_mt))
+    return fv3_fail(c, -2, "d_sw: unsupported hord (supported: 5, 6, -5, 8, 10; hord_mt: 5, 6, 8, 10)");
+  if (f.inline_q) return fv3_fail(c, -2, "d_sw: inline_q not supported");
+  if (f.do_f3d) return fv3_fail(c, -2, "d_sw: do_f3d not supported");
+  if (f.nord > 3) return fv3_fail(c, -2, "d_sw: nord > 3 not supported");
+  std::vector<int> ki; std::vector<double> kd;
+  dsw_tables(c, ki, kd);
+  FV3_CUDA(c, cudaMemcpyAsync(c->d_kint, ki.data(), ki.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  FV3_CUDA(c, cudaMemcpyAsync(c->d_kdbl, kd.data(), kd.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  // the tables are consumed asynchronously; ki/kd are pageable -> copy is staged by the driver before return
+  const int n1 = nk + 1;
+  bool any_w = false, any_v = false, any_deln = false, any_deln_t = false, any_n0 = false, any_nn = false;
+  int nord_max = 0;
+  for (int k = 0; k < nk; k++) {
+    any_w |= kd[KD_DAMP4_W * n1 + k] != 0.; any_v |= kd[KD_DAMP4_V * n1 + k] != 0.; any_deln |= kd[KD_DELN * n1 + k] != 0.; any_deln_t |= kd[KD_DELN_T * n1 + k] != 0.;
+    any_n0 |= ki[KI_NORD * n1 + k] == 0; any_nn |= ki[KI_NORD * n1 + k] > 0;
+    nord_max = std::max(nord_max, ki[KI_NORD * n1 + k]);
+  }
+  (void)any_n0; (void)any_nn;
+  dim3 blk(TI, TJ), grd = plane_grid(L, nk);
+  cudaStream_t st = c->stream;
+  double *uts = c->scr[0], *vts = c->scr[1], *fx = c->scr[2], *fy = c->scr[3];
+  double *fx2 = c->scr[4], *fy2 = c->scr[5], *q_i = c->scr[6], *q_j = c->scr[7];
+  double *gx = c->scr[8], *gy = c->scr[9], *dfx = c->scr[10], *dfy = c->scr[11], *d2 = c->scr[12];
+  double *dw = c->scr[13], *hs = c->scr[14], *ds = c->scr[15];
+  double *delp = c->fld[FV3_DELP], *pt = c->fld[FV3_PT], *w = c->fld[FV3_W], *u = c->fld[FV3_U], *v = c->fld[FV3_V];
+  double *uc = c->fld[FV3_UC], *vc = c->fld[FV3_VC];
+  double *crx = c->fld[FV3_CRX], *cry = c->fld[FV3_CRY], *xfx = c->fld[FV3_XFX], *yfx = c->fld[FV3_YFX];
+
+  k_dsw_wind<<<grd, blk, 0, st>>>(L, c->G, uc, vc, uts, vts, crx, cry, xfx, yfx, c->fld[FV3_CX], c->fld[FV3_CY], dt);
+  c->launches++;
+
+  Tp2d tp;
+  tp.crx = crx; tp.cry = cry; tp.xfx = xfx; tp.yfx = yfx; tp.ra_x = nullptr; tp.ra_y = nullptr;
+  tp.nk = nk; tp.fx2 = fx2; tp.fy2 = fy2; tp.q_i = q_i; tp.q_j = q_j;
+  // --- delp (:919-920)
+  tp.q = delp; tp.fx = fx; tp.fy = fy; tp.mfx = nullptr; tp.mfy = nullptr; tp.hord = f.hord_dp;
+  int rc = launch_tp2d(c, tp); if (rc) return rc;
+  Deln dl;
+  dl.fx2 = dfx; dl.fy2 = dfy; dl.d2 = d2; dl.nk = nk; dl.thresh = 0; dl.nord_const = 0; dl.damp_const = 0;
+  if (any_deln) {
+    dl.q = delp; dl.slot_nord = KI_NORD_V; dl.slot_damp = KD_DELN; dl.premul = 1;
+    launch_deln(c, dl);
+    launch_deln_add(c, fx, fy, dfx, dfy, nullptr, KD_DELN, 0., nk);
+  }
+  // --- w (:950-990)
+  const bool nonhydro = !f.hydrostatic;
+  if (nonhydro) {
+    if (any_w) {
+      dl.q = w; dl.slot_nord = KI_NORD_W; dl.slot_damp = KD_DAMP4_W; dl.premul = 1;
+      launch_deln(c, dl);
+    }
+    k_dsw_dw<<<grd, blk, 0, st>>>(L, c->G, w, dfx, dfy, dw, hs, ds, c->d_kdbl, f.ke_bg, dt, f.prevent_diss_cooling, f.do_diss_est);
+    c->launches++;
+    tp.q = w; tp.fx = gx; tp.fy = gy; tp.mfx = fx; tp.mfy = fy; tp.hord = f.hord_vt;
+    rc = launch_tp2d(c, tp); if (rc) return rc;
+    k_dsw_qdp<<<grd, blk, 0, st>>>(L, c->G, w, delp, gx, gy, c->alt_w);
+    c->launches++;
+  } else {
+    FV3_CUDA(c, cudaMemsetAsync(hs, 0, (size_t)L.plane * nk * sizeof(double), st));
+    FV3_CUDA(c, cudaMemsetAsync(ds, 0, (size_t)L.plane * nk * sizeof(double), st));
+  }
+  // --- q_con (:992-1000)
+  if (f.use_cond) {
+    tp.q = c->fld[FV3_QCON]; tp.fx = gx; tp.fy = gy; tp.mfx = fx; tp.mfy = fy; tp.hord = f.hord_dp;
+    rc = launch_tp2d(c, tp); if (rc) return rc;
+    if (any_deln_t) {
+      dl.q = c->fld[FV3_QCON]; dl.slot_nord = KI_NORD_T; dl.slot_damp = KD_DELN_T; dl.premul = 0;
+      launch_deln(c, dl);
+      launch_deln_add(c, gx, gy, dfx, dfy, delp, KD_DELN_T, 0., nk);
+    }
+    k_dsw_qdp<<<grd, blk, 0, st>>>(L, c->G, c->fld[FV3_QCON], delp, gx, gy, c->alt_qcon);
+    c->launches++;
+  }
+  // --- pt (:1014-1016) and the delp/pt update (:1053-1066)
+  tp.q = pt; tp.fx = gx; tp.fy = gy; tp.mfx = fx; tp.mfy = fy; tp.hord = f.hord_tm;
+  rc = launch_tp2d(c, tp); if (rc) return rc;
+  if (any_deln_t) {
+    dl.q = pt; dl.slot_nord = KI_NORD_T; dl.slot_damp = KD_DELN_T; dl.premul = 0;
+    launch_deln(c, dl);
+    launch_deln_add(c, gx, gy, dfx, dfy, delp, KD_DELN_T, 0., nk);
+  }
+  k_dsw_ptdp<<<grd, blk, 0, st>>>(L, c->G, pt, delp, fx, fy, gx, gy, c->alt_pt, c->alt_delp, c->fld[FV3_MFX], c->fld[FV3_MFY]);
+  c->launches++;
+  std::swap(c->fld[FV3_DELP], c->alt_delp); std::swap(c->fld[FV3_PT], c->alt_pt);
+  double* delp_new = c->fld[FV3_DELP];
+  if (nonhydro) {
+    k_dsw_wfin<<<grd, blk, 0, st>>>(L, c->alt_w, delp_new, dw, c->d_kdbl, any_w ? 1 : 0);
+    c->launches++;
+    std::swap(c->fld[FV3_W], c->alt_w);
+  }
+  if (f.use_cond) {
+    k_dsw_wfin<<<grd, blk, 0, st>>>(L, c->alt_qcon, delp_new, dw, c->d_kdbl, 0);
+    c->launches++;
+    std::swap(c->fld[FV3_QCON], c->alt_qcon);
+  }
+  // --- KE (:1078-1228); ke lives in fx2's plane from here (tp scratch is rewritten later, so use gx)
+  double* ke = gx;      // B-grid (is:ie+1, js:je+1)
+  k_dsw_ke<<<grd, blk, 0, st>>>(L, c->G, u, v, uc, vc, uts, vts, ke, dt, f.hord_mt);
+  double *wk = uts, *vq = vts;   // contravariant winds are dead after KE
+  k_dsw_vort<<<grd, blk, 0, st>>>(L, c->G, u, v, wk, vq);
+  c->launches += 2;
+  // --- divergence damping (:1290-1460)
+  double *dg = gy, *vcs = dfx, *ucs = dfy, *vortb = d2, *dterm = q_i;
+  if (nord_max > 0) {
+    FV3_CUDA(c, cudaMemcpyAsync(dg, c->fld[FV3_DIVGD], (size_t)L.plane * nk * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    for (int n = 1; n <= nord_max; n++) {
+      k_dsw_dd_uv<<<grd, blk, 0, st>>>(L, c->G, dg, vcs, ucs, c->d_kint, n);
+      k_dsw_dd_div<<<grd, blk, 0, st>>>(L, c->G, vcs, ucs, dg, c->d_kint, n, c->b.stretched_grid);
+      c->launches += 2;
+    }
+    if (f.dddmp >= 1.E-5) {
+      if (!L.cube) return fv3_fail(c, -2, "d_sw: smag_corner (dddmp>0 on a doubly-periodic grid) not supported");
+      rc = launch_a2b_ord4(c, wk, vortb, nk, 0); if (rc) return rc;
+    }
+  }
+  k_dsw_damp<<<grd, blk, 0, st>>>(L, c->G, u, v, c->fld[FV3_UA], c->fld[FV3_VA], uc, vc, c->fld[FV3_DIVGD], dg, vortb, ke, dterm,
+                                  c->d_kint, c->d_kdbl, dt, f.dddmp, f.d4_bg, c->b.stretched_grid);
+  c->launches++;
+  // --- vorticity transport and momentum update (:1476-1509)
+  tp.q = vq; tp.fx = fx; tp.fy = fy; tp.mfx = nullptr; tp.mfy = nullptr; tp.hord = f.hord_vt;
+  tp.q_i = gy; tp.q_j = q_j;   // q_i's plane holds dterm
+  rc = launch_tp2d(c, tp); if (rc) return rc;
+  k_dsw_uv<<<grd, blk, 0, st>>>(L, c->G, u, v, ke, fx, fy, c->alt_u, c->alt_v);
+  c->launches++;
+  // --- vorticity damping + dissipative heating (:1513-1600)
+  if (any_v) {
+    dl.q = wk; dl.slot_nord = KI_NORD_V; dl.slot_damp = KD_DAMP4_V; dl.premul = 1;
+    launch_deln(c, dl);   // dfx = "ut", dfy = "vt"
+  }
+  if (f.d_con > 1.e-5 || f.do_diss_est) {
+    k_dsw_heat<<<grd, blk, 0, st>>>(L, c->G, c->alt_u, c->alt_v, u, v, dterm, dfx, dfy, delp_new, hs, ds, c->fld[FV3_HEAT], c->fld[FV3_DISS],
+                                    c->d_kdbl, f.prevent_diss_cooling, f.do_diss_est, f.d_con);
+    c->launches++;
+  }
+  if (any_v) {
+    k_dsw_vdamp<<<grd, blk, 0, st>>>(L, c->alt_u, c->alt_v, dfx, dfy, c->d_kdbl);
+    c->launches++;
+  }
+  std::swap(c->fld[FV3_U], c->alt_u); std::swap(c->fld[FV3_V], c->alt_v);
+  return 0;
+}

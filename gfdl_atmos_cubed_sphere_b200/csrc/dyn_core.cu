@@ -1,0 +1,152 @@
+// The acoustic (n_split) loop of dyn_core on device-resident state.
+//
+// Reference semantics: model/dyn_core.F90:289-294 (flux-capacitor reset) and :313-1286, the
+// non-hydrostatic, non-nested, non-regional global cubed-sphere branch:
+//   halo(u,v,w[,delp,pt]) -> c_sw -> [it==1: gz from delz, halo(gz), zh=gz | gz=zh]
+//   -> update_dz_c -> Riem_Solver_C -> p_grad_c -> halo(divgd@corner, uc,vc) -> d_sw
+//   -> halo(delp,pt[,q_con]) -> update_dz_d -> Riem_Solver3 -> halo(zh,pkc)
+//   -> [pe_halo] pk3_halo -> gz = zh*grav -> nh_p_grad -> [last: shared-edge u,v de-dup]
+// One call replaces the whole it-loop; all faces owned by this process advance in lockstep
+// (each on its own stream), exchanges are fv3_halo_exchange (device-local gathers and/or NCCL).
+// Not included (documented in DESIGN.md): the post-loop d_con heating del2_cubed
+// (dyn_core.F90:1300-1358), omega diagnostics (:1182-1215), Rayleigh friction, fast physics.
+#include "fv3_ctx.hpp"
+
+extern "C" int fv3_halo_exchange(fv3_ctx** ctxs, int nctx, int group);
+
+#define FORALL(stmt)                                   \
+  for (int a_ = 0; a_ < nctx; a_++) {                  \
+    fv3_ctx* c = ctxs[a_];                             \
+    cudaSetDevice(c->device);                          \
+    int rc_ = (stmt);                                  \
+    if (rc_) return rc_;                               \
+  }
+
+extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, int flags) {
+  (void)flags;
+  if (!ctxs || nctx < 1 || n_split < 1) return -1;
+  for (int a = 0; a < nctx; a++) {
+    if (ctxs[a]->f.hydrostatic) return fv3_fail(ctxs[a], -2, "dyn_core: hydrostatic path (geopk/one_grad_p) not supported yet");
+    if (ctxs[a]->f.beta != 0.0) return fv3_fail(ctxs[a], -2, "dyn_core: beta != 0 (split_p_grad/one_grad_p) not supported");
+    if (ctxs[a]->f.d_ext > 0.0) return fv3_fail(ctxs[a], -2, "dyn_core: d_ext > 0 (external-mode damping) not supported");
+  }
+  const double dt = bdt / (double)n_split;   // dyn_core.F90:223
+  const double dt2 = 0.5 * dt;
+  const bool linked = ctxs[0]->halo != nullptr;
+  // dyn_core.F90:289-294
+  FORALL(stage_zero_field(c, FV3_MFX)) FORALL(stage_zero_field(c, FV3_MFY)) FORALL(stage_zero_field(c, FV3_CX))
+  FORALL(stage_zero_field(c, FV3_CY)) FORALL(stage_zero_field(c, FV3_HEAT))
+  int rc;
+  for (int it = 1; it <= n_split; it++) {
+    const bool last_step = (it == n_split);
+    if (linked) {
+      if (it == 1 && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;   // :402 (started in fv_dynamics.F90:467)
+      if ((rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_UVW))) return rc;                  // :430-432
+    }
+    if (it == 1) {
+      FORALL(stage_gz_init(c))                                                            // :370-385
+      if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_GZ))) return rc;         // :387, :488
+    }
+    FORALL(stage_c_sw(c, dt2))                                                            // :436-447
+    if (it == 1) { FORALL(stage_copy_field(c, FV3_ZH, FV3_GZ)) }                          // :491-499
+    else { FORALL(stage_copy_field(c, FV3_GZ, FV3_ZH)) }                                  // :514-521
+    FORALL(stage_update_dz_c(c, dt2))                                                     // :525
+    FORALL(stage_riem_solver_c(c, dt2))                                                   // :531
+    FORALL(stage_p_grad_c(c, dt2))                                                        // :562
+    if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DIVGD_UCVC))) return rc;   // :451,:565,:577-578
+    FORALL(stage_d_sw(c, dt))                                                             // :666-812
+    if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;      // :823-825,:851
+    FORALL(stage_update_dz_d(c, dt))                                                      // :911
+    FORALL(stage_riem_solver3(c, dt, last_step ? 1 : 0))                                  // :932
+    if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_ZH_PKC))) return rc;       // :945-949,:980,:992
+    if (last_step) { FORALL(stage_pe_halo(c)) }                                           // :952-953
+    FORALL(stage_pk3_halo(c))                                                             // :958
+    FORALL(stage_gz_from_zh(c))                                                           // :982-989
+    FORALL(stage_nh_p_grad(c, dt))                                                        // :1032
+    if (last_step && linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_UV_EDGE))) return rc;   // :1151-1163
+  }
+  for (int a = 0; a < nctx; a++) {
+    cudaSetDevice(ctxs[a]->device);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fv3_fail(ctxs[a], (int)e, std::string("dyn_core: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+// ---- whole-state transfer (dyn_core entry/exit) ---------------------------------------------
+extern "C" int fv3_upload_state(fv3_ctx* c, const fv3_state_t* s) {
+  if (!c || !s) return -1;
+  struct { int id; const double* p; } m[] = {{FV3_U, s->u}, {FV3_V, s->v}, {FV3_W, s->w}, {FV3_DELZ, s->delz}, {FV3_PT, s->pt},
+                                             {FV3_DELP, s->delp}, {FV3_QCON, s->q_con}, {FV3_CAPPA, s->cappa}, {FV3_PHIS, s->phis},
+                                             {FV3_OMGA, s->omga}, {FV3_UA, s->ua}, {FV3_VA, s->va}, {FV3_UC, s->uc}, {FV3_VC, s->vc},
+                                             {FV3_PE, s->pe}, {FV3_PELN, s->peln}, {FV3_PK, s->pk}, {FV3_PKZ, s->pkz},
+                                             {FV3_DISS, s->diss_est}};
+  for (auto& e : m)
+    if (e.p) { int rc = fv3_put_field(c, e.id, e.p); if (rc) return rc; }
+  return 0;
+}
+extern "C" int fv3_download_state(fv3_ctx* c, fv3_state_t* s) {
+  if (!c || !s) return -1;
+  struct { int id; double* p; } m[] = {{FV3_U, s->u}, {FV3_V, s->v}, {FV3_W, s->w}, {FV3_DELZ, s->delz}, {FV3_PT, s->pt},
+                                       {FV3_DELP, s->delp}, {FV3_QCON, s->q_con}, {FV3_OMGA, s->omga}, {FV3_UA, s->ua}, {FV3_VA, s->va},
+                                       {FV3_UC, s->uc}, {FV3_VC, s->vc}, {FV3_MFX, s->mfx}, {FV3_MFY, s->mfy}, {FV3_CX, s->cx},
+                                       {FV3_CY, s->cy}, {FV3_PE, s->pe}, {FV3_PELN, s->peln}, {FV3_PK, s->pk}, {FV3_PKZ, s->pkz},
+                                       {FV3_WS, s->ws}, {FV3_HEAT, s->heat_source}, {FV3_DISS, s->diss_est}};
+  for (auto& e : m)
+    if (e.p) { int rc = fv3_get_field(c, e.id, e.p); if (rc) return rc; }
+  return 0;
+}
+
+// ---- per-call host-buffer drop-ins ----------------------------------------------------------
+#define PUT(id, p) if ((p) && (rc = fv3_put_field(c, id, p))) return rc;
+#define GET(id, p) if ((p) && (rc = fv3_get_field(c, id, p))) return rc;
+extern "C" int fv3_c_sw_host(fv3_ctx* c, double* delpc, double* delp, double* ptc, double* pt, double* u, double* v, double* w,
+                             double* uc, double* vc, double* ua, double* va, double* wc, double* ut, double* vt, double* divg_d,
+                             double dt2) {
+  if (!c) return -1;
+  int rc;
+  PUT(FV3_DELP, delp) PUT(FV3_PT, pt) PUT(FV3_U, u) PUT(FV3_V, v) PUT(FV3_W, w)
+  if ((rc = fv3_c_sw(c, dt2))) return rc;
+  GET(FV3_DELPC, delpc) GET(FV3_PTC, ptc) GET(FV3_UC, uc) GET(FV3_VC, vc) GET(FV3_UA, ua) GET(FV3_VA, va) GET(FV3_OMGA, wc)
+  GET(FV3_UT, ut) GET(FV3_VT, vt) GET(FV3_DIVGD, divg_d)
+  return 0;
+}
+extern "C" int fv3_d_sw_host(fv3_ctx* c, double* delp, double* pt, double* u, double* v, double* w, double* uc, double* vc, double* ua,
+                             double* va, double* divg_d, double* mfx, double* mfy, double* cx, double* cy, double* crx, double* cry,
+                             double* xfx, double* yfx, double* q_con, double* heat_source, double* diss_est, double dt) {
+  if (!c) return -1;
+  int rc;
+  PUT(FV3_DELP, delp) PUT(FV3_PT, pt) PUT(FV3_U, u) PUT(FV3_V, v) PUT(FV3_W, w) PUT(FV3_UC, uc) PUT(FV3_VC, vc) PUT(FV3_UA, ua)
+  PUT(FV3_VA, va) PUT(FV3_DIVGD, divg_d) PUT(FV3_MFX, mfx) PUT(FV3_MFY, mfy) PUT(FV3_CX, cx) PUT(FV3_CY, cy) PUT(FV3_QCON, q_con)
+  PUT(FV3_HEAT, heat_source) PUT(FV3_DISS, diss_est)
+  if ((rc = fv3_d_sw(c, dt))) return rc;
+  GET(FV3_DELP, delp) GET(FV3_PT, pt) GET(FV3_U, u) GET(FV3_V, v) GET(FV3_W, w) GET(FV3_MFX, mfx) GET(FV3_MFY, mfy) GET(FV3_CX, cx)
+  GET(FV3_CY, cy) GET(FV3_CRX, crx) GET(FV3_CRY, cry) GET(FV3_XFX, xfx) GET(FV3_YFX, yfx) GET(FV3_QCON, q_con)
+  GET(FV3_HEAT, heat_source) GET(FV3_DISS, diss_est)
+  return 0;
+}
+extern "C" int fv3_fv_tp_2d_host(fv3_ctx* c, int nk, double* q, const double* crx, const double* cry, const double* xfx,
+                                 const double* yfx, const double* ra_x, const double* ra_y, int hord, double* fx, double* fy,
+                                 const double* mfx, const double* mfy, const double* mass, int nord, double damp_c) {
+  if (!c) return -1;
+  if (nk != c->L.npz) return fv3_fail(c, -1, "fv_tp_2d_host: nk must be npz (buffers are full 3-D arrays of npz levels)");
+  if (!q || !crx || !cry || !xfx || !yfx || !ra_x || !ra_y || !fx || !fy) return fv3_fail(c, -1, "fv_tp_2d_host: null argument");
+  if ((mfx == nullptr) != (mfy == nullptr)) return fv3_fail(c, -1, "fv_tp_2d_host: mfx and mfy must be given together");
+  int rc;
+  PUT(FV3_WORK_Q, q) PUT(FV3_CRX, crx) PUT(FV3_CRY, cry) PUT(FV3_XFX, xfx) PUT(FV3_YFX, yfx)
+  PUT(FV3_WORK_RAX, ra_x) PUT(FV3_WORK_RAY, ra_y) PUT(FV3_MFX, mfx) PUT(FV3_MFY, mfy) PUT(FV3_DELP, mass)
+  if ((rc = fv3_fv_tp_2d(c, nk, hord, mfx ? 1 : 0, mass ? 1 : 0, nord, damp_c))) return rc;
+  GET(FV3_WORK_FX, fx) GET(FV3_WORK_FY, fy)
+  return 0;
+}
+extern "C" int fv3_riem_solver_c_host(fv3_ctx* c, double dt2, const double* cappa, const double* phis, const double* w3,
+                                      const double* ptc, const double* q_con, const double* delpc, double* gz, double* pef,
+                                      const double* ws3) {
+  if (!c) return -1;
+  int rc;
+  PUT(FV3_CAPPA, cappa) PUT(FV3_PHIS, phis) PUT(FV3_OMGA, w3) PUT(FV3_PTC, ptc) PUT(FV3_QCON, q_con) PUT(FV3_DELPC, delpc)
+  PUT(FV3_GZ, gz) PUT(FV3_WS3, ws3)
+  if ((rc = fv3_riem_solver_c(c, dt2))) return rc;
+  GET(FV3_GZ, gz) GET(FV3_PKC, pef)
+  return 0;
+}

@@ -1,0 +1,115 @@
+// Device context of the B200 FV3 acoustic-dynamics library (internal header).
+//
+// HBM layout: every horizontal field, whatever its staggering, lives in the same
+// padded plane  [NJ][NI]  with
+//     idx(i,j) = (i - isd + IOFF) + (j - jsd) * NI,   IOFF = 5,  NI % 8 == 0
+// so that i = 1 (first compute cell) starts a 64-byte aligned segment of every row
+// and one index function serves A-, C-, D- and B-grid arrays (extents isd:ied+1,
+// jsd:jed+1).  3-D fields are [nk][NJ][NI] (k slowest) -- coalesced for the (i,j)
+// stencil kernels (threadIdx.x -> i) and for the column solvers (one thread per
+// column, consecutive threads on consecutive i, marching in k).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/fv3_dyncore.h"
+
+#define FV3_IOFF 5
+
+struct Lay {
+  int npx, npy, npz, ng;
+  int is, ie, js, je, isd, ied, jsd, jed;
+  int NI, NJ;
+  long long plane;   // NI*NJ rounded up to a multiple of 16 doubles
+  int cube;          // grid_type < 3 && !bounded_domain : cube-edge / corner logic on
+  int grid_type;
+};
+
+#ifdef __CUDACC__
+#define LIDX(L, i, j) ((long long)((i) - (L).isd + FV3_IOFF) + (long long)((j) - (L).jsd) * (L).NI)
+#endif
+
+// pointers to the 2-D metric planes on the device
+struct DevGrid {
+  const double *area, *rarea, *dxa, *dya, *rdxa, *rdya, *cosa_s, *rsin2, *f0;
+  const double *sin_sg, *cos_sg;   // 9 planes each
+  const double *dy, *rdy, *dxc, *rdxc, *cosa_u, *sina_u, *rsin_u, *divg_v, *del6_v;
+  const double *dx, *rdx, *dyc, *rdyc, *cosa_v, *sina_v, *rsin_v, *divg_u, *del6_u;
+  const double *area_c, *rarea_c, *fC, *cosa, *sina, *rsina;
+  const double *edge_w, *edge_e, *edge_s, *edge_n;  // 1-based: edge_w[j-1]
+  double a2b_w[4][3];   // a2b_ord4 corner extrapolation weights x1/(x2-x1) (a2b_edge.F90:106-130,452-462)
+  double da_min, da_min_c;
+};
+
+struct FieldDim { int ilo, ni, jlo, nj, nk, kmid; };
+
+struct StageTimer { cudaEvent_t e0, e1; double ms; long long calls; bool pending; };
+
+struct HaloPlan;  // halo.cu
+
+struct fv3_ctx {
+  fv3_bounds_t b;
+  fv3_flags_t f;
+  std::vector<double> ak, bk;
+  Lay L;
+  DevGrid G;
+  int device;
+  cudaStream_t stream;
+  std::string err;
+  // device fields (padded layout); fld[id] may alias (ping-pong targets swapped by stages)
+  double* fld[FV3_NUM_FIELDS];
+  FieldDim dim[FV3_NUM_FIELDS];
+  // ping-pong partners for the in-place updated prognostics (delp, pt, w, u, v, q_con)
+  double *alt_delp, *alt_pt, *alt_w, *alt_u, *alt_v, *alt_qcon;
+  // scratch 3-D planes (nk = npz+1)
+  static const int NSCR = 16;
+  double* scr[NSCR];
+  // metrics storage
+  std::vector<double*> metric_alloc;
+  // staging
+  double* h_stage; size_t h_stage_bytes;
+  double* d_stage; size_t d_stage_bytes;
+  // per-k damping parameters (dyn_core.F90:666-733) on host and device
+  std::vector<int> nord_v; std::vector<double> damp_vt;
+  int* d_kint; double* d_kdbl;     // device copies of per-k coefficient tables
+  double* d_dp_ref;                // dp_ref(npz)  dyn_core.F90:242-244
+  long long launches;
+  bool timers_on;
+  std::map<std::string, StageTimer> timers;
+  HaloPlan* halo;
+  int tile;
+};
+
+// error helpers
+int fv3_fail(fv3_ctx* c, int code, const std::string& msg);
+#define FV3_CUDA(c, call)                                                                  \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return fv3_fail((c), (int)e__, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+struct StageScope {
+  fv3_ctx* c; StageTimer* t;
+  StageScope(fv3_ctx* c_, const char* name);
+  ~StageScope();
+};
+
+// stage implementations (each enqueues kernels on c->stream)
+int stage_fv_tp_2d(fv3_ctx* c, int nk, int hord, int use_mfx, int use_mass, int nord, double damp_c);
+int stage_c_sw(fv3_ctx* c, double dt2);
+int stage_d_sw(fv3_ctx* c, double dt);
+int stage_update_dz_c(fv3_ctx* c, double dt2);
+int stage_riem_solver_c(fv3_ctx* c, double dt2);
+int stage_p_grad_c(fv3_ctx* c, double dt2);
+int stage_update_dz_d(fv3_ctx* c, double dt);
+int stage_riem_solver3(fv3_ctx* c, double dt, int last_call);
+int stage_pk3_halo(fv3_ctx* c);
+int stage_pe_halo(fv3_ctx* c);
+int stage_gz_from_zh(fv3_ctx* c);
+int stage_nh_p_grad(fv3_ctx* c, double dt);
+int stage_gz_init(fv3_ctx* c);
+int stage_copy_field(fv3_ctx* c, int dst, int src);
+int stage_zero_field(fv3_ctx* c, int f);
+void halo_destroy(fv3_ctx* c);

@@ -1,0 +1,235 @@
+// Pressure-gradient stencils and the A->B (cell-corner) 4th-order interpolation (sm_100a).
+//
+// Reference semantics: model/a2b_edge.F90 a2b_ord4 (:47-327), extrap_corner (:452-462);
+// model/dyn_core.F90 p_grad_c (:1635-1694), nh_p_grad (:1697-1792).
+// Design: a2b_ord4 is two launches (1-D cubic sweeps qx/qy incl. the closed-form edge columns,
+// then the corner-point combination); the three-way corner extrapolation uses 12 weights
+// precomputed at fv3_create instead of calling great_circle_dist on every call.  nh_p_grad
+// keeps the interpolated (B-grid) pp, pk, gz, delp in scratch planes rather than writing
+// them back in place (the reference's replace=.true.), so the A-grid arrays stay readable by
+// neighbouring threads; nothing downstream reads the replaced arrays before they are rebuilt.
+#include "fv3_ctx.hpp"
+#include <cmath>
+
+#define TI 32
+#define TJ 8
+#define PLANE_IJK                                              \
+  const int i = L.isd - FV3_IOFF + blockIdx.x * TI + threadIdx.x; \
+  const int j = L.jsd + blockIdx.y * TJ + threadIdx.y;          \
+  const int k = blockIdx.z;                                     \
+  const long long ko = (long long)k * L.plane;
+#define AT(p, i, j) __ldg((p) + ko + LIDX(L, (i), (j)))
+#define G2(p, i, j) __ldg((G.p) + LIDX(L, (i), (j)))
+static inline dim3 plane_grid(const Lay& L, int nk) { return dim3((L.NI + TI - 1) / TI, (L.NJ + TJ - 1) / TJ, nk); }
+
+namespace {
+constexpr double r3 = 1. / 3.;
+constexpr double a1 = 0.5625, a2 = -0.0625;         // a2b_edge.F90:34-35
+constexpr double b1 = 7. / 12., b2 = -1. / 12.;     // :39-40
+constexpr double c1 = 2. / 3., c2 = -1. / 6.;       // :54-55
+}
+
+// pass 1: qx (is:ie+1, 1:npy-1) and qy (1:npx-1, js:je+1)   (a2b_edge.F90:132-233)
+__global__ void __launch_bounds__(TI* TJ) k_a2b_1(Lay L, DevGrid G, const double* __restrict__ qin, double* __restrict__ qx,
+                                                 double* __restrict__ qy) {
+  PLANE_IJK
+  const int npx = L.npx, npy = L.npy;
+  if (i < L.is - 2 || i > L.ie + 2 || j < L.js - 2 || j > L.je + 2) return;
+  const bool cube = L.cube;
+  auto Q = [&](int ii, int jj) { return AT(qin, ii, jj); };
+  if (i >= L.is && i <= L.ie + 1 && (!cube || (j >= 1 && j <= npy - 1))) {
+    double v;
+    auto gen = [&](int ii) { return b2 * (Q(ii - 2, j) + Q(ii + 1, j)) + b1 * (Q(ii - 1, j) + Q(ii, j)); };
+    if (!cube || (i >= 3 && i <= npx - 2)) v = gen(i);
+    else if (i <= 2) {
+      const double g_in = G2(dxa, 2, j) / G2(dxa, 1, j), g_ou = G2(dxa, -1, j) / G2(dxa, 0, j);
+      const double q1 = 0.5 * (((2. + g_in) * Q(1, j) - Q(2, j)) / (1. + g_in) + ((2. + g_ou) * Q(0, j) - Q(-1, j)) / (1. + g_ou));
+      v = (i == 1) ? q1 : (3. * (g_in * Q(1, j) + Q(2, j)) - (g_in * q1 + gen(3))) / (2. + 2. * g_in);
+    } else {
+      const double g_in = G2(dxa, npx - 2, j) / G2(dxa, npx - 1, j), g_ou = G2(dxa, npx + 1, j) / G2(dxa, npx, j);
+      const double qn = 0.5 * (((2. + g_in) * Q(npx - 1, j) - Q(npx - 2, j)) / (1. + g_in) + ((2. + g_ou) * Q(npx, j) - Q(npx + 1, j)) / (1. + g_ou));
+      v = (i == npx) ? qn : (3. * (Q(npx - 2, j) + g_in * Q(npx - 1, j)) - (g_in * qn + gen(npx - 2))) / (2. + 2. * g_in);
+    }
+    qx[ko + LIDX(L, i, j)] = v;
+  }
+  if (j >= L.js && j <= L.je + 1 && (!cube || (i >= 1 && i <= npx - 1))) {
+    double v;
+    auto gen = [&](int jj) { return b2 * (Q(i, jj - 2) + Q(i, jj + 1)) + b1 * (Q(i, jj - 1) + Q(i, jj)); };
+    if (!cube || (j >= 3 && j <= npy - 2)) v = gen(j);
+    else if (j <= 2) {
+      const double g_in = G2(dya, i, 2) / G2(dya, i, 1), g_ou = G2(dya, i, -1) / G2(dya, i, 0);
+      const double q1 = 0.5 * (((2. + g_in) * Q(i, 1) - Q(i, 2)) / (1. + g_in) + ((2. + g_ou) * Q(i, 0) - Q(i, -1)) / (1. + g_ou));
+      v = (j == 1) ? q1 : (3. * (g_in * Q(i, 1) + Q(i, 2)) - (g_in * q1 + gen(3))) / (2. + 2. * g_in);
+    } else {
+      const double g_in = G2(dya, i, npy - 2) / G2(dya, i, npy - 1), g_ou = G2(dya, i, npy + 1) / G2(dya, i, npy);
+      const double qn = 0.5 * (((2. + g_in) * Q(i, npy - 1) - Q(i, npy - 2)) / (1. + g_in) + ((2. + g_ou) * Q(i, npy) - Q(i, npy + 1)) / (1. + g_ou));
+      v = (j == npy) ? qn : (3. * (Q(i, npy - 2) + g_in * Q(i, npy - 1)) - (g_in * qn + gen(npy - 2))) / (2. + 2. * g_in);
+    }
+    qy[ko + LIDX(L, i, j)] = v;
+  }
+}
+
+// pass 2: qout on (is:ie+1, js:je+1)   (a2b_edge.F90:104-130, :141-166, :199-224, :258-288)
+__global__ void __launch_bounds__(TI* TJ) k_a2b_2(Lay L, DevGrid G, const double* __restrict__ qin, const double* __restrict__ qx,
+                                                 const double* __restrict__ qy, double* __restrict__ qout) {
+  PLANE_IJK
+  const int npx = L.npx, npy = L.npy;
+  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
+  auto Q = [&](int ii, int jj) { return AT(qin, ii, jj); };
+  auto QX = [&](int ii, int jj) { return AT(qx, ii, jj); };
+  auto QY = [&](int ii, int jj) { return AT(qy, ii, jj); };
+  double out;
+  if (!L.cube) {
+    out = 0.5 * (a1 * (QX(i, j - 1) + QX(i, j) + QY(i - 1, j) + QY(i, j)) + a2 * (QX(i, j - 2) + QX(i, j + 1) + QY(i - 2, j) + QY(i + 1, j)));
+    qout[ko + LIDX(L, i, j)] = out;
+    return;
+  }
+  auto ex = [&](int c, int m, double q1, double q2) { return q1 + G.a2b_w[c][m] * (q1 - q2); };
+  // edge values (closed form, also needed by the first interior row/column)
+  auto west = [&](int jj) {
+    auto q2 = [&](int j2) { return (Q(0, j2) * G2(dxa, 1, j2) + Q(1, j2) * G2(dxa, 0, j2)) / (G2(dxa, 0, j2) + G2(dxa, 1, j2)); };
+    const double ew = __ldg(G.edge_w + jj - 1);
+    return ew * q2(jj - 1) + (1. - ew) * q2(jj);
+  };
+  auto east = [&](int jj) {
+    auto q2 = [&](int j2) { return (Q(npx - 1, j2) * G2(dxa, npx, j2) + Q(npx, j2) * G2(dxa, npx - 1, j2)) / (G2(dxa, npx - 1, j2) + G2(dxa, npx, j2)); };
+    const double ee = __ldg(G.edge_e + jj - 1);
+    return ee * q2(jj - 1) + (1. - ee) * q2(jj);
+  };
+  auto south = [&](int ii) {
+    auto q1 = [&](int i2) { return (Q(i2, 0) * G2(dya, i2, 1) + Q(i2, 1) * G2(dya, i2, 0)) / (G2(dya, i2, 0) + G2(dya, i2, 1)); };
+    const double es = __ldg(G.edge_s + ii - 1);
+    return es * q1(ii - 1) + (1. - es) * q1(ii);
+  };
+  auto north = [&](int ii) {
+    auto q1 = [&](int i2) { return (Q(i2, npy - 1) * G2(dya, i2, npy) + Q(i2, npy) * G2(dya, i2, npy - 1)) / (G2(dya, i2, npy - 1) + G2(dya, i2, npy)); };
+    const double en = __ldg(G.edge_n + ii - 1);
+    return en * q1(ii - 1) + (1. - en) * q1(ii);
+  };
+  const bool ic = (i == 1 || i == npx), jc = (j == 1 || j == npy);
+  if (ic && jc) {
+    if (i == 1 && j == 1)
+      out = (ex(0, 0, Q(1, 1), Q(2, 2)) + ex(0, 1, Q(0, 1), Q(-1, 2)) + ex(0, 2, Q(1, 0), Q(2, -1))) * r3;
+    else if (i == npx && j == 1)
+      out = (ex(1, 0, Q(npx - 1, 1), Q(npx - 2, 2)) + ex(1, 1, Q(npx - 1, 0), Q(npx - 2, -1)) + ex(1, 2, Q(npx, 1), Q(npx + 1, 2))) * r3;
+    else if (i == npx && j == npy)
+      out = (ex(2, 0, Q(npx - 1, npy - 1), Q(npx - 2, npy - 2)) + ex(2, 1, Q(npx, npy - 1), Q(npx + 1, npy - 2)) +
+             ex(2, 2, Q(npx - 1, npy), Q(npx - 2, npy + 1))) * r3;
+    else
+      out = (ex(3, 0, Q(1, npy - 1), Q(2, npy - 2)) + ex(3, 1, Q(0, npy - 1), Q(-1, npy - 2)) + ex(3, 2, Q(1, npy), Q(2, npy + 1))) * r3;
+  } else if (i == 1) out = west(j);
+  else if (i == npx) out = east(j);
+  else if (j == 1) out = south(i);
+  else if (j == npy) out = north(i);
+  else {
+    auto qxx_gen = [&](int jj) { return a2 * (QX(i, jj - 2) + QX(i, jj + 1)) + a1 * (QX(i, jj - 1) + QX(i, jj)); };
+    auto qyy_gen = [&](int ii) { return a2 * (QY(ii - 2, j) + QY(ii + 1, j)) + a1 * (QY(ii - 1, j) + QY(ii, j)); };
+    double qxx, qyy;
+    if (j == 2) qxx = c1 * (QX(i, 1) + QX(i, 2)) + c2 * (south(i) + qxx_gen(3));
+    else if (j == npy - 1) qxx = c1 * (QX(i, npy - 2) + QX(i, npy - 1)) + c2 * (north(i) + qxx_gen(npy - 2));
+    else qxx = qxx_gen(j);
+    if (i == 2) qyy = c1 * (QY(1, j) + QY(2, j)) + c2 * (west(j) + qyy_gen(3));
+    else if (i == npx - 1) qyy = c1 * (QY(npx - 2, j) + QY(npx - 1, j)) + c2 * (east(j) + qyy_gen(npx - 2));
+    else qyy = qyy_gen(i);
+    out = 0.5 * (qxx + qyy);
+  }
+  qout[ko + LIDX(L, i, j)] = out;
+}
+
+// qx, qy scratch = c->scr[4], c->scr[5] (free in both callers: d_sw between transports, nh_p_grad)
+int launch_a2b_ord4(fv3_ctx* c, const double* qin, double* qout, int nk, int /*replace_into_qin*/) {
+  const Lay& L = c->L;
+  dim3 blk(TI, TJ), grd = plane_grid(L, nk);
+  k_a2b_1<<<grd, blk, 0, c->stream>>>(L, c->G, qin, c->scr[4], c->scr[5]);
+  k_a2b_2<<<grd, blk, 0, c->stream>>>(L, c->G, qin, c->scr[4], c->scr[5], qout);
+  c->launches += 2;
+  return 0;
+}
+
+// ---- p_grad_c (dyn_core.F90:1635-1694), in place on uc, vc ---------------------------------
+__global__ void __launch_bounds__(TI* TJ) k_pgrad_c(Lay L, DevGrid G, const double* __restrict__ delpc, const double* __restrict__ pkc,
+                                                   const double* __restrict__ gz, double* __restrict__ uc, double* __restrict__ vc,
+                                                   double dt2, int hydrostatic) {
+  PLANE_IJK
+  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
+  const long long P = L.plane;
+  const long long o = ko + LIDX(L, i, j);
+  auto WK = [&](long long oo) { return hydrostatic ? (__ldg(pkc + oo + P) - __ldg(pkc + oo)) : __ldg(delpc + oo); };
+  auto GZ = [&](long long oo) { return __ldg(gz + oo); };
+  auto PK = [&](long long oo) { return __ldg(pkc + oo); };
+  if (j <= L.je) {
+    const long long w = o - 1;
+    uc[o] = uc[o] + dt2 * G2(rdxc, i, j) / (WK(w) + WK(o)) *
+                        ((GZ(w + P) - GZ(o)) * (PK(o + P) - PK(w)) + (GZ(w) - GZ(o + P)) * (PK(w + P) - PK(o)));
+  }
+  if (i <= L.ie) {
+    const long long s = o - L.NI;
+    vc[o] = vc[o] + dt2 * G2(rdyc, i, j) / (WK(s) + WK(o)) *
+                        ((GZ(s + P) - GZ(o)) * (PK(o + P) - PK(s)) + (GZ(s) - GZ(o + P)) * (PK(s + P) - PK(o)));
+  }
+}
+int stage_p_grad_c(fv3_ctx* c, double dt2) {
+  StageScope ts(c, "PG_C");
+  const Lay& L = c->L;
+  dim3 blk(TI, TJ), grd = plane_grid(L, L.npz);
+  k_pgrad_c<<<grd, blk, 0, c->stream>>>(L, c->G, c->fld[FV3_DELPC], c->fld[FV3_PKC], c->fld[FV3_GZ], c->fld[FV3_UC], c->fld[FV3_VC], dt2,
+                                        c->f.hydrostatic);
+  c->launches++;
+  return 0;
+}
+
+// ---- nh_p_grad (dyn_core.F90:1697-1792) -----------------------------------------------------
+__global__ void __launch_bounds__(TI* TJ) k_nh_top(Lay L, double* __restrict__ ppb, double* __restrict__ pkb, double top_value) {
+  const int i = L.isd - FV3_IOFF + blockIdx.x * TI + threadIdx.x;
+  const int j = L.jsd + blockIdx.y * TJ + threadIdx.y;
+  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
+  ppb[LIDX(L, i, j)] = 0.;
+  pkb[LIDX(L, i, j)] = top_value;
+}
+__global__ void __launch_bounds__(TI* TJ) k_nh_pgrad(Lay L, DevGrid G, const double* __restrict__ pp, const double* __restrict__ pk,
+                                                    const double* __restrict__ gz, const double* __restrict__ dpb, double* __restrict__ u,
+                                                    double* __restrict__ v, double dt) {
+  PLANE_IJK
+  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
+  const long long P = L.plane;
+  const long long o = ko + LIDX(L, i, j);
+  auto WKo = [&](long long oo) { return __ldg(pk + oo + P) - __ldg(pk + oo); };
+  if (i <= L.ie) {
+    const long long e = o + 1;
+    const double du1 = dt / (WKo(o) + WKo(e)) *
+                       ((__ldg(gz + o + P) - __ldg(gz + e)) * (__ldg(pk + e + P) - __ldg(pk + o)) +
+                        (__ldg(gz + o) - __ldg(gz + e + P)) * (__ldg(pk + o + P) - __ldg(pk + e)));
+    u[o] = (u[o] + du1 + dt / (__ldg(dpb + o) + __ldg(dpb + e)) *
+                             ((__ldg(gz + o + P) - __ldg(gz + e)) * (__ldg(pp + e + P) - __ldg(pp + o)) +
+                              (__ldg(gz + o) - __ldg(gz + e + P)) * (__ldg(pp + o + P) - __ldg(pp + e)))) * G2(rdx, i, j);
+  }
+  if (j <= L.je) {
+    const long long n = o + L.NI;
+    const double dv1 = dt / (WKo(o) + WKo(n)) *
+                       ((__ldg(gz + o + P) - __ldg(gz + n)) * (__ldg(pk + n + P) - __ldg(pk + o)) +
+                        (__ldg(gz + o) - __ldg(gz + n + P)) * (__ldg(pk + o + P) - __ldg(pk + n)));
+    v[o] = (v[o] + dv1 + dt / (__ldg(dpb + o) + __ldg(dpb + n)) *
+                             ((__ldg(gz + o + P) - __ldg(gz + n)) * (__ldg(pp + n + P) - __ldg(pp + o)) +
+                              (__ldg(gz + o) - __ldg(gz + n + P)) * (__ldg(pp + o + P) - __ldg(pp + n)))) * G2(rdy, i, j);
+  }
+}
+
+int stage_nh_p_grad(fv3_ctx* c, double dt) {
+  StageScope ts(c, "PG_D");
+  const Lay& L = c->L;
+  const int km = L.npz;
+  double *ppb = c->scr[0], *pkb = c->scr[1], *gzb = c->scr[2], *dpb = c->scr[3];
+  const long long P = L.plane;
+  const double top_value = c->f.use_logp ? log(c->f.ptop) : pow(c->f.ptop, c->f.kappa);   // peln1 / ptk, dyn_core.F90:220-222
+  dim3 blk(TI, TJ), g1 = plane_grid(L, 1);
+  k_nh_top<<<g1, blk, 0, c->stream>>>(L, ppb, pkb, top_value);
+  c->launches++;
+  int rc;
+  if ((rc = launch_a2b_ord4(c, c->fld[FV3_PKC] + P, ppb + P, km, 1))) return rc;   // pp, k = 2..km+1
+  if ((rc = launch_a2b_ord4(c, c->fld[FV3_PK3] + P, pkb + P, km, 1))) return rc;   // pk, k = 2..km+1
+  if ((rc = launch_a2b_ord4(c, c->fld[FV3_GZ], gzb, km + 1, 1))) return rc;        // gz, k = 1..km+1
+  if ((rc = launch_a2b_ord4(c, c->fld[FV3_DELP], dpb, km, 0))) return rc;          // delp -> wk1
+  k_nh_pgrad<<<plane_grid(L, km), blk, 0, c->stream>>>(L, c->G, ppb, pkb, gzb, dpb, c->fld[FV3_U], c->fld[FV3_V], dt);
+  c->launches++;
+  return 0;
+}

@@ -1,0 +1,341 @@
+// 1-D PPM reconstruction + upwind flux device functions (sm_100a).
+//
+// What they compute: model/tp_core.F90 xppm (:324-712) / yppm (:715-1152) and
+// model/sw_core.F90 xtp_u (:2154-2521) / ytp_v (:2524-2998) of the reference.
+// How: the reference sweeps whole rows building al/bl/br arrays; here every thread owns ONE
+// flux interface, picks the UPWIND cell from the sign of the Courant number first and
+// reconstructs only that cell's (bl, br) from a 5-7 point register window -- no row
+// temporaries, no redundant reconstruction for the monotone family.  The x and y operators
+// share one implementation through a strided accessor.  Cube-edge one-sided formulas
+// (tp_core.F90:643-681, sw_core.F90:2446-2490) are taken only by the threads whose upwind
+// cell is one of {0,1,2,n-2,n-1,n}.
+//
+// Supported schemes: 5, 6, -5 (unlimited family) and 8, 10 (monotone family); the host
+// rejects the others (no silent fallback).
+#pragma once
+#include "fv3_ctx.hpp"
+
+namespace ppm {
+
+__device__ __forceinline__ double fsign(double a, double b) { return copysign(fabs(a), b); }
+__device__ __forceinline__ double min3(double a, double b, double c) { return fmin(fmin(a, b), c); }
+__device__ __forceinline__ double max3(double a, double b, double c) { return fmax(fmax(a, b), c); }
+
+// tp_core.F90:35-70
+constexpr double r3 = 1. / 3.;
+constexpr double r12 = 1. / 12.;
+constexpr double s11 = 11. / 14., s14 = 4. / 7., s15 = 3. / 14.;
+constexpr double c1 = -2. / 14., c2 = 11. / 14., c3 = 5. / 14.;
+constexpr double p1 = 7. / 12., p2 = -1. / 12.;
+constexpr double near_zero_tp = 1.E-25;   // tp_core.F90:37
+constexpr double near_zero_sw = 1.E-9;    // sw_core.F90:39
+
+// strided 1-D view: value at sweep index s is p[base + s*stride]
+struct Acc {
+  const double* p; long long base; long long stride;
+  __device__ __forceinline__ double operator()(int s) const { return __ldg(p + base + (long long)s * stride); }
+};
+
+// scalar field with the copy_corners(dir=1) view, x sweep along row j (tp_core.F90:257-286)
+struct QAccX {
+  const double* q; Lay L; int j;
+  __device__ __forceinline__ double operator()(int i) const {
+    int ii = i, jj = j;
+    if (L.cube) {
+      if (j <= 0) {
+        if (i <= 0) { ii = j; jj = 1 - i; }
+        else if (i >= L.npx) { ii = L.npy - j; jj = i - L.npx + 1; }
+      } else if (j >= L.npy) {
+        if (i >= L.npx) { ii = j; jj = 2 * L.npx - 1 - i; }
+        else if (i <= 0) { ii = L.npy - j; jj = i - 1 + L.npx; }
+      }
+    }
+    return __ldg(q + LIDX(L, ii, jj));
+  }
+};
+// copy_corners(dir=2) view, y sweep along column i (tp_core.F90:288-318)
+struct QAccY {
+  const double* q; Lay L; int i;
+  __device__ __forceinline__ double operator()(int j) const {
+    int ii = i, jj = j;
+    if (L.cube) {
+      if (i <= 0) {
+        if (j <= 0) { ii = 1 - j; jj = i; }
+        else if (j >= L.npy) { ii = j + 1 - L.npx; jj = L.npy - i; }
+      } else if (i >= L.npx) {
+        if (j <= 0) { ii = L.npy + j - 1; jj = L.npx - i; }
+        else if (j >= L.npy) { ii = 2 * L.npy - 1 - j; jj = i; }
+      }
+    }
+    return __ldg(q + LIDX(L, ii, jj));
+  }
+};
+
+template <class Q>
+__device__ __forceinline__ double dm_at(const Q& q, int i) {  // tp_core.F90:570-574
+  const double qm = q(i - 1), q0 = q(i), qp = q(i + 1);
+  const double xt = 0.25 * (qp - qm);
+  return fsign(fmin(fmin(fabs(xt), max3(qm, q0, qp) - q0), q0 - min3(qm, q0, qp)), xt);
+}
+
+__device__ __forceinline__ void pert_std(double& al, double& ar) {  // pert_ppm iv/=0, tp_core.F90:1245-1261
+  if (al * ar < 0.) {
+    const double da1 = al - ar, da2 = da1 * da1, a6da = 3. * (al + ar) * da1;
+    if (a6da < -da2) ar = -2. * al;
+    else if (a6da > da2) al = -2. * ar;
+  } else { al = 0.; ar = 0.; }
+}
+
+// dxa-weighted two-sided edge value (tp_core.F90:376-377 / :647-648); e = first cell inside
+// the face on the high side of the edge (e = 1 for the west/south edge, e = n for east/north)
+template <class Q, class D>
+__device__ __forceinline__ double edge_avg(const Q& q, const D& d, int e) {
+  return 0.5 * (((2. * d(e - 1) + d(e - 2)) * q(e - 1) - d(e - 1) * q(e - 2)) / (d(e - 2) + d(e - 1)) +
+                ((2. * d(e) + d(e + 1)) * q(e) - d(e) * q(e + 1)) / (d(e) + d(e + 1)));
+}
+
+// ------------------------------------------------------------------ scalar transport (xppm/yppm)
+// monotone family: (bl, br) of cell i.  n = npx (or npy).  tp_core.F90:563-681
+template <class Q, class D>
+__device__ __forceinline__ void cell_mono(const Q& q, const D& dxa, int i, int iord, int n, bool cube, double& bl, double& br) {
+  if (!cube || (i >= 3 && i <= n - 3)) {
+    const double qm1 = q(i - 1), q0 = q(i), qp1 = q(i + 1);
+    const double dmm = dm_at(q, i - 1), dm0 = dm_at(q, i), dmp = dm_at(q, i + 1);
+    const double al0 = 0.5 * (qm1 + q0) + r3 * (dmm - dm0);
+    const double al1 = 0.5 * (q0 + qp1) + r3 * (dm0 - dmp);
+    if (iord == 8) {
+      const double xt = 2. * dm0;
+      bl = -fsign(fmin(fabs(xt), fabs(al0 - q0)), xt);
+      br = fsign(fmin(fabs(xt), fabs(al1 - q0)), xt);
+    } else {  // 10
+      bl = al0 - q0; br = al1 - q0;
+      if (fabs(dmm) + fabs(dm0) + fabs(dmp) < near_zero_tp) { bl = 0.; br = 0.; }
+      else if (fabs(3. * (bl + br)) > fabs(bl - br)) {
+        const double dqm2 = 2. * (qm1 - q(i - 2)), dqm1 = 2. * (q0 - qm1), dq0 = 2. * (qp1 - q0), dqp1 = 2. * (q(i + 2) - qp1);
+        const double pmp_2 = dqm1, lac_2 = pmp_2 - 0.75 * dqm2;
+        br = fmin(max3(0., pmp_2, lac_2), fmax(br, min3(0., pmp_2, lac_2)));
+        const double pmp_1 = -dq0, lac_1 = pmp_1 + 0.75 * dqp1;
+        bl = fmin(max3(0., pmp_1, lac_1), fmax(bl, min3(0., pmp_1, lac_1)));
+      }
+    }
+    return;
+  }
+  // cube-edge cells
+  if (i <= 1) {  // cells 0 and 1 share the clamped two-sided edge value
+    double xt = edge_avg(q, dxa, 1);
+    const double qa = q(-1), qb = q(0), qc = q(1), qd = q(2);
+    xt = fmax(xt, fmin(fmin(qa, qb), fmin(qc, qd)));
+    xt = fmin(xt, fmax(fmax(qa, qb), fmax(qc, qd)));
+    if (i == 0) { bl = s14 * dm_at(q, -1) + s11 * (qa - qb); br = xt - qb; }
+    else { bl = xt - qc; br = (s15 * qc + s11 * qd - s14 * dm_at(q, 2)) - qc; }
+  } else if (i == 2) {
+    const double q1 = q(1), q2 = q(2), q3 = q(3);
+    const double dm2 = dm_at(q, 2);
+    bl = (s15 * q1 + s11 * q2 - s14 * dm2) - q2;
+    br = (0.5 * (q2 + q3) + r3 * (dm2 - dm_at(q, 3))) - q2;
+  } else if (i == n - 2) {
+    const double qa = q(n - 3), qb = q(n - 2), qc = q(n - 1);
+    const double dmb = dm_at(q, n - 2);
+    bl = (0.5 * (qa + qb) + r3 * (dm_at(q, n - 3) - dmb)) - qb;
+    br = (s15 * qc + s11 * qb + s14 * dmb) - qb;
+  } else {  // n-1, n
+    double xt = edge_avg(q, dxa, n);
+    const double qa = q(n - 2), qb = q(n - 1), qc = q(n), qd = q(n + 1);
+    xt = fmax(xt, fmin(fmin(qa, qb), fmin(qc, qd)));
+    xt = fmin(xt, fmax(fmax(qa, qb), fmax(qc, qd)));
+    if (i == n - 1) { bl = (s15 * qb + s11 * qa + s14 * dm_at(q, n - 2)) - qb; br = xt - qb; }
+    else { bl = xt - qc; br = s11 * (qd - qc) - s14 * dm_at(q, n + 1); }
+  }
+  pert_std(bl, br);   // pert_ppm(3, ..., 1), tp_core.F90:660,679
+}
+
+// unlimited family: edge value al(i).  tp_core.F90:369-392
+template <class Q, class D>
+__device__ __forceinline__ double al_unlim(const Q& q, const D& dxa, int i, int iord, int n, bool cube) {
+  double al;
+  if (!cube || (i >= 3 && i <= n - 2)) al = p1 * (q(i - 1) + q(i)) + p2 * (q(i - 2) + q(i + 1));
+  else if (i == 0) al = c1 * q(-2) + c2 * q(-1) + c3 * q(0);
+  else if (i == 1) al = edge_avg(q, dxa, 1);
+  else if (i == 2) al = c3 * q(1) + c2 * q(2) + c1 * q(3);
+  else if (i == n - 1) al = c1 * q(n - 3) + c2 * q(n - 2) + c3 * q(n - 1);
+  else if (i == n) al = edge_avg(q, dxa, n);
+  else al = c3 * q(n) + c2 * q(n + 1) + c1 * q(n + 2);  // n+1
+  if (iord < 0) al = fmax(0., al);
+  return al;
+}
+
+struct CellU { double bl, br, b0; bool smt; };
+
+// unlimited family cell (5, 6, -5).  tp_core.F90:491-546
+template <class Q, class D>
+__device__ __forceinline__ CellU cell_unlim(const Q& q, const D& dxa, int i, int iord, int n, bool cube) {
+  CellU c;
+  const double q0 = q(i);
+  c.bl = al_unlim(q, dxa, i, iord, n, cube) - q0;
+  c.br = al_unlim(q, dxa, i + 1, iord, n, cube) - q0;
+  c.b0 = c.bl + c.br;
+  if (iord == 5) { c.smt = c.bl * c.br < 0.; return c; }
+  if (iord == -5) {
+    c.smt = c.bl * c.br < 0.;
+    const double da1 = c.br - c.bl, a4 = -3. * c.b0;
+    if (fabs(da1) < -a4) {
+      if (q0 + 0.25 / a4 * (da1 * da1) + a4 * r12 < 0.) {
+        if (!c.smt) { c.br = 0.; c.bl = 0.; c.b0 = 0.; }
+        else if (da1 > 0.) { c.br = -2. * c.bl; c.b0 = -c.bl; }
+        else { c.bl = -2. * c.br; c.b0 = -c.br; }
+      }
+    }
+  } else {
+    c.smt = 3. * fabs(c.b0) < fabs(c.bl - c.br);
+  }
+  if (cube && (i == 0 || i == 1 || i == n - 1 || i == n)) c.smt = c.bl * c.br < 0.;   // tp_core.F90:536-545
+  return c;
+}
+
+// flux through interface i for Courant number c.  tp_core.F90:549-558, :701-707
+template <class Q, class D>
+__device__ __forceinline__ double flux_scalar(const Q& q, const D& dxa, int i, double c, int iord, int n, bool cube) {
+  if (iord >= 8) {
+    const int iu = (c > 0.) ? i - 1 : i;
+    double bl, br;
+    cell_mono(q, dxa, iu, iord, n, cube, bl, br);
+    const double qu = q(iu);
+    return (c > 0.) ? qu + (1. - c) * (br - c * (bl + br)) : qu + (1. + c) * (bl + c * (bl + br));
+  }
+  const CellU a = cell_unlim(q, dxa, i - 1, iord, n, cube);
+  const CellU b = cell_unlim(q, dxa, i, iord, n, cube);
+  double fx1, fl;
+  if (c > 0.) { fx1 = (1. - c) * (a.br - c * a.b0); fl = q(i - 1); }
+  else { fx1 = (1. + c) * (b.bl + c * b.b0); fl = q(i); }
+  if (a.smt || b.smt) fl = fl + fx1;
+  return fl;
+}
+
+// ------------------------------------------------------------------ momentum (xtp_u / ytp_v)
+// zero = the row/column of this sweep is a face edge line (j==1||j==npy for xtp_u),
+// where bl=br=0 at the two cells touching the face corner (sw_core.F90:2206-2210,2451-2455)
+template <class Q, class D>
+__device__ __forceinline__ void cell_wind_mono(const Q& u, const D& dx, int i, int iord, int n, bool cube, bool zero,
+                                               double& bl, double& br) {
+  if (!cube) {   // "Other grids" branch, sw_core.F90:2494-2505
+    const double um1 = u(i - 1), u0 = u(i), up1 = u(i + 1);
+    const double dmm = dm_at(u, i - 1), dm0 = dm_at(u, i), dmp = dm_at(u, i + 1);
+    const double al0 = 0.5 * (um1 + u0) + r3 * (dmm - dm0), al1 = 0.5 * (u0 + up1) + r3 * (dm0 - dmp);
+    double pmp = -2. * (up1 - u0), lac = pmp + 1.5 * (u(i + 2) - up1);
+    bl = fmin(max3(0., pmp, lac), fmax(al0 - u0, min3(0., pmp, lac)));
+    pmp = 2. * (u0 - um1); lac = pmp - 1.5 * (um1 - u(i - 2));
+    br = fmin(max3(0., pmp, lac), fmax(al1 - u0, min3(0., pmp, lac)));
+    return;
+  }
+  if (i >= 3 && i <= n - 3) {
+    const double um1 = u(i - 1), u0 = u(i), up1 = u(i + 1);
+    const double dmm = dm_at(u, i - 1), dm0 = dm_at(u, i), dmp = dm_at(u, i + 1);
+    const double al0 = 0.5 * (um1 + u0) + r3 * (dmm - dm0), al1 = 0.5 * (u0 + up1) + r3 * (dm0 - dmp);
+    if (iord == 8) {
+      const double xt = 2. * dm0;
+      bl = -fsign(fmin(fabs(xt), fabs(al0 - u0)), xt);
+      br = fsign(fmin(fabs(xt), fabs(al1 - u0)), xt);
+    } else {  // 10, sw_core.F90:2414-2433
+      bl = al0 - u0; br = al1 - u0;
+      if (fabs(dm0) < near_zero_sw) {
+        if (fabs(dmm) + fabs(dmp) < near_zero_sw) { bl = 0.; br = 0.; }
+      } else if (fabs(3. * (bl + br)) > fabs(bl - br)) {
+        const double dq0 = up1 - u0, dqp1 = u(i + 2) - up1, dqm1 = u0 - um1, dqm2 = um1 - u(i - 2);
+        const double pmp_1 = -2. * dq0, lac_1 = pmp_1 + 1.5 * dqp1;
+        bl = fmin(max3(0., pmp_1, lac_1), fmax(bl, min3(0., pmp_1, lac_1)));
+        const double pmp_2 = 2. * dqm1, lac_2 = pmp_2 - 1.5 * dqm2;
+        br = fmin(max3(0., pmp_2, lac_2), fmax(br, min3(0., pmp_2, lac_2)));
+      }
+    }
+    return;
+  }
+  // edges, sw_core.F90:2446-2490
+  if (i == 2) {
+    const double u1 = u(1), u2 = u(2), u3 = u(3);
+    const double dm2 = dm_at(u, 2);
+    br = (0.5 * (u2 + u3) + r3 * (dm2 - dm_at(u, 3))) - u2;
+    bl = (s15 * u1 + s11 * u2 - s14 * dm2) - u2;
+    pert_std(bl, br);
+  } else if (i == n - 2) {
+    const double ua = u(n - 3), ub = u(n - 2), uc = u(n - 1);
+    const double dmb = dm_at(u, n - 2);
+    bl = (0.5 * (ua + ub) + r3 * (dm_at(u, n - 3) - dmb)) - ub;
+    br = (s15 * uc + s11 * ub + s14 * dmb) - ub;
+    pert_std(bl, br);
+  } else if (zero) {
+    bl = 0.; br = 0.;
+  } else if (i <= 1) {
+    const double x0L = 0.5 * ((2. * dx(0) + dx(-1)) * (u(0)) - dx(0) * (u(-1))) / (dx(0) + dx(-1));
+    const double x0R = 0.5 * ((2. * dx(1) + dx(2)) * (u(1)) - dx(1) * (u(2))) / (dx(1) + dx(2));
+    const double xt = x0L + x0R;
+    if (i == 0) { bl = s14 * dm_at(u, -1) - s11 * (u(0) - u(-1)); br = xt - u(0); }
+    else { bl = xt - u(1); br = (s15 * u(1) + s11 * u(2) - s14 * dm_at(u, 2)) - u(1); }
+  } else {  // n-1, n
+    const double x0L = 0.5 * ((2. * dx(n - 1) + dx(n - 2)) * (u(n - 1)) - dx(n - 1) * (u(n - 2))) / (dx(n - 1) + dx(n - 2));
+    const double x0R = 0.5 * ((2. * dx(n) + dx(n + 1)) * (u(n)) - dx(n) * (u(n + 1))) / (dx(n) + dx(n + 1));
+    const double xt = x0L + x0R;
+    if (i == n - 1) { bl = (s15 * u(n - 1) + s11 * u(n - 2) + s14 * dm_at(u, n - 2)) - u(n - 1); br = xt - u(n - 1); }
+    else { bl = xt - u(n); br = s11 * (u(n + 1) - u(n)) - s14 * dm_at(u, n + 1); }
+  }
+}
+
+// iord < 8 family (5, 6[,7]) for the winds.  sw_core.F90:2187-2377
+template <class Q, class D>
+__device__ __forceinline__ CellU cell_wind_unlim(const Q& u, const D& dx, int i, int iord, int n, bool cube, bool zero) {
+  CellU c;
+  auto alg = [&](int m) { return p1 * (u(m - 1) + u(m)) + p2 * (u(m - 2) + u(m + 1)); };
+  if (!cube || (i >= 3 && i <= n - 3)) {
+    c.bl = alg(i) - u(i); c.br = alg(i + 1) - u(i);
+  } else if (i == 2) {
+    c.bl = (c3 * u(1) + c2 * u(2) + c1 * u(3)) - u(2);
+    c.br = alg(3) - u(2);
+  } else if (i == n - 2) {
+    c.bl = alg(n - 2) - u(n - 2);
+    c.br = (c1 * u(n - 3) + c2 * u(n - 2) + c3 * u(n - 1)) - u(n - 2);
+  } else if (zero) {
+    c.bl = 0.; c.br = 0.;
+  } else if (i <= 1) {
+    const double xt = 0.5 * (((2. * dx(0) + dx(-1)) * (u(0)) - dx(0) * u(-1)) / (dx(0) + dx(-1)) +
+                             ((2. * dx(1) + dx(2)) * (u(1)) - dx(1) * u(2)) / (dx(1) + dx(2)));
+    if (i == 0) { c.bl = c1 * u(-2) + c2 * u(-1) + c3 * u(0) - u(0); c.br = xt - u(0); }
+    else { c.bl = xt - u(1); c.br = (c3 * u(1) + c2 * u(2) + c1 * u(3)) - u(1); }
+  } else {
+    const double xt = 0.5 * (((2. * dx(n - 1) + dx(n - 2)) * u(n - 1) - dx(n - 1) * u(n - 2)) / (dx(n - 1) + dx(n - 2)) +
+                             ((2. * dx(n) + dx(n + 1)) * u(n) - dx(n) * u(n + 1)) / (dx(n) + dx(n + 1)));
+    if (i == n - 1) { c.bl = (c1 * u(n - 3) + c2 * u(n - 2) + c3 * u(n - 1)) - u(n - 1); c.br = xt - u(n - 1); }
+    else { c.bl = xt - u(n); c.br = c3 * u(n) + c2 * u(n + 1) + c1 * u(n + 2) - u(n); }
+  }
+  c.b0 = c.bl + c.br;
+  if (iord == 5) c.smt = c.bl * c.br < 0.;
+  else {
+    c.smt = 3. * fabs(c.b0) < fabs(c.bl - c.br);
+    if (cube && (i == 0 || i == 1 || i == n - 1 || i == n)) c.smt = c.bl * c.br < 0.;
+  }
+  return c;
+}
+
+// flux of the wind itself through interface i; c is a DISTANCE, cfl = c * rdx(upwind)
+template <class Q, class D>
+__device__ __forceinline__ double flux_wind(const Q& u, const D& dx, const D& rdx, int i, double c, int iord, int n,
+                                            bool cube, bool zero) {
+  if (iord >= 8) {
+    const int iu = (c > 0.) ? i - 1 : i;
+    double bl, br;
+    cell_wind_mono(u, dx, iu, iord, n, cube, zero, bl, br);
+    const double cfl = c * rdx(iu);
+    const double uu = u(iu);
+    return (c > 0.) ? uu + (1. - cfl) * (br - cfl * (bl + br)) : uu + (1. + cfl) * (bl + cfl * (bl + br));
+  }
+  const CellU a = cell_wind_unlim(u, dx, i - 1, iord, n, cube, zero);
+  const CellU b = cell_wind_unlim(u, dx, i, iord, n, cube, zero);
+  double fx0, fl;
+  if (c > 0.) { const double cfl = c * rdx(i - 1); fx0 = (1. - cfl) * (a.br - cfl * a.b0); fl = u(i - 1); }
+  else { const double cfl = c * rdx(i); fx0 = (1. + cfl) * (b.bl + cfl * b.b0); fl = u(i); }
+  if (a.smt || b.smt) fl = fl + fx0;
+  return fl;
+}
+
+__host__ inline bool hord_supported(int h) { return h == 5 || h == 6 || h == -5 || h == 8 || h == 10; }
+__host__ inline bool hord_wind_supported(int h) { return h == 5 || h == 6 || h == 8 || h == 10; }
+
+}  // namespace ppm

@@ -1,0 +1,241 @@
+// fv_tp_2d (Lin-Rood 2-D flux-form transport with PPM operators) and the del-n damping
+// fluxes, as CUDA kernels for sm_100a.
+//
+// Reference semantics: model/tp_core.F90:85-241 fv_tp_2d, :245-322 copy_corners,
+// :1267-1447 deln_flux; model/sw_core.F90:1608-1737 del6_vt_flux.
+// Design (not a translation): three launches per transport, one thread per flux point,
+//   1. inner advective-form sweeps  fy2 = yppm(q), fx2 = xppm(q)   (ord_in)
+//   2. q_i, q_j  (the intermediate advected fields, one division each)
+//   3. outer sweeps on q_i / q_j (ord_ou), average with the inner fluxes, weight
+// The cube-corner "copy_corners" transposes are NOT written into q: the inner sweeps read
+// q through a remapping accessor (ppm::QAccX / QAccY), so q stays read-only and corner
+// tiles pay one predicated index swap.  Intermediates are [k][j][i] planes sized for L2
+// residency when the caller chunks k.
+#include "tp2d.cuh"
+#include "ppm.cuh"
+
+using namespace ppm;
+
+#define TI 32
+#define TJ 8
+
+static inline dim3 plane_grid(const Lay& L, int nk) { return dim3((L.NI + TI - 1) / TI, (L.NJ + TJ - 1) / TJ, nk); }
+
+#define PLANE_IJK                                              \
+  const int i = L.isd - FV3_IOFF + blockIdx.x * TI + threadIdx.x; \
+  const int j = L.jsd + blockIdx.y * TJ + threadIdx.y;          \
+  const int k = blockIdx.z;                                     \
+  const long long ko = (long long)k * L.plane;
+
+__global__ void __launch_bounds__(TI* TJ) k_tp_inner(Lay L, DevGrid G, const double* __restrict__ q,
+                                                    const double* __restrict__ crx, const double* __restrict__ cry,
+                                                    double* __restrict__ fx2, double* __restrict__ fy2, int ord_in) {
+  PLANE_IJK
+  if (i < L.isd || i > L.ied + 1 || j > L.jed + 1) return;
+  const bool cube = L.cube;
+  // fy2 (isd:ied, js:je+1): y sweep with the dir=2 corner view  (tp_core.F90:143-148)
+  if (i <= L.ied && j >= L.js && j <= L.je + 1) {
+    QAccY qa{q + ko, L, i};
+    Acc da{G.dya, LIDX(L, i, 0), L.NI};
+    fy2[ko + LIDX(L, i, j)] = flux_scalar(qa, da, j, __ldg(cry + ko + LIDX(L, i, j)), ord_in, L.npy, cube);
+  }
+  // fx2 (is:ie+1, jsd:jed): x sweep with the dir=1 corner view  (tp_core.F90:164-169)
+  if (i >= L.is && i <= L.ie + 1 && j <= L.jed) {
+    QAccX qa{q + ko, L, j};
+    Acc da{G.dxa, LIDX(L, 0, j), 1};
+    fx2[ko + LIDX(L, i, j)] = flux_scalar(qa, da, i, __ldg(crx + ko + LIDX(L, i, j)), ord_in, L.npx, cube);
+  }
+}
+
+__global__ void __launch_bounds__(TI* TJ) k_tp_qiqj(Lay L, DevGrid G, const double* __restrict__ q,
+                                                   const double* __restrict__ xfx, const double* __restrict__ yfx,
+                                                   const double* __restrict__ ra_x, const double* __restrict__ ra_y,
+                                                   const double* __restrict__ fx2, const double* __restrict__ fy2,
+                                                   double* __restrict__ q_i, double* __restrict__ q_j) {
+  PLANE_IJK
+  if (i < L.isd || i > L.ied || j > L.jed) return;
+  const long long o = ko + LIDX(L, i, j);
+  const double qq = __ldg(q + o), ar = __ldg(G.area + LIDX(L, i, j));
+  // q_i (isd:ied, js:je)  tp_core.F90:150-159
+  if (j >= L.js && j <= L.je) {
+    const double y0 = __ldg(yfx + o), y1 = __ldg(yfx + o + L.NI);
+    const double f0 = y0 * __ldg(fy2 + o), f1 = y1 * __ldg(fy2 + o + L.NI);
+    const double ray = ra_y ? __ldg(ra_y + o) : (ar + y0 - y1);
+    q_i[o] = (qq * ar + f0 - f1) / ray;
+  }
+  // q_j (is:ie, jsd:jed)  tp_core.F90:171-178
+  if (i >= L.is && i <= L.ie) {
+    const double x0 = __ldg(xfx + o), x1 = __ldg(xfx + o + 1);
+    const double f0 = x0 * __ldg(fx2 + o), f1 = x1 * __ldg(fx2 + o + 1);
+    const double rax = ra_x ? __ldg(ra_x + o) : (ar + x0 - x1);
+    q_j[o] = (qq * ar + f0 - f1) / rax;
+  }
+}
+
+__global__ void __launch_bounds__(TI* TJ) k_tp_outer(Lay L, DevGrid G, const double* __restrict__ q_i,
+                                                    const double* __restrict__ q_j, const double* __restrict__ crx,
+                                                    const double* __restrict__ cry, const double* __restrict__ fx2,
+                                                    const double* __restrict__ fy2, const double* __restrict__ wx,
+                                                    const double* __restrict__ wy, double* __restrict__ fx,
+                                                    double* __restrict__ fy, int ord_ou) {
+  PLANE_IJK
+  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
+  const bool cube = L.cube;
+  const long long o = ko + LIDX(L, i, j);
+  if (j <= L.je) {  // fx (is:ie+1, js:je)  tp_core.F90:161, :193/:219
+    Acc qa{q_i + ko, LIDX(L, 0, j), 1};
+    Acc da{G.dxa, LIDX(L, 0, j), 1};
+    const double f = flux_scalar(qa, da, i, __ldg(crx + o), ord_ou, L.npx, cube);
+    fx[o] = 0.5 * (f + __ldg(fx2 + o)) * __ldg(wx + o);
+  }
+  if (i <= L.ie) {  // fy (is:ie, js:je+1)  tp_core.F90:180, :198/:224
+    Acc qa{q_j + ko, LIDX(L, i, 0), L.NI};
+    Acc da{G.dya, LIDX(L, i, 0), L.NI};
+    const double f = flux_scalar(qa, da, j, __ldg(cry + o), ord_ou, L.npy, cube);
+    fy[o] = 0.5 * (f + __ldg(fy2 + o)) * __ldg(wy + o);
+  }
+}
+
+int launch_tp2d(fv3_ctx* c, const Tp2d& a) {
+  if (!hord_supported(a.hord)) return fv3_fail(c, -2, "fv_tp_2d: hord " + std::to_string(a.hord) + " not supported on the GPU path (supported: 5, 6, -5, 8, 10)");
+  const Lay& L = c->L;
+  const int ord_in = (a.hord == 10) ? 8 : a.hord;   // tp_core.F90:136-141
+  dim3 blk(TI, TJ), grd = plane_grid(L, a.nk);
+  k_tp_inner<<<grd, blk, 0, c->stream>>>(L, c->G, a.q, a.crx, a.cry, a.fx2, a.fy2, ord_in);
+  k_tp_qiqj<<<grd, blk, 0, c->stream>>>(L, c->G, a.q, a.xfx, a.yfx, a.ra_x, a.ra_y, a.fx2, a.fy2, a.q_i, a.q_j);
+  k_tp_outer<<<grd, blk, 0, c->stream>>>(L, c->G, a.q_i, a.q_j, a.crx, a.cry, a.fx2, a.fy2, a.mfx ? a.mfx : a.xfx,
+                                         a.mfy ? a.mfy : a.yfx, a.fx, a.fy, a.hord);
+  c->launches += 3;
+  return 0;
+}
+
+// ------------------------------------------------------------------ del-n fluxes
+__device__ __forceinline__ void kparams(const int* kint, const double* kdbl, int npz1, int slot_nord, int slot_damp, int k,
+                                        int nord_const, double damp_const, int& nord, double& coef) {
+  nord = slot_nord >= 0 ? kint[slot_nord * npz1 + k] : nord_const;
+  coef = slot_damp >= 0 ? kdbl[slot_damp * npz1 + k] : damp_const;
+}
+
+__global__ void __launch_bounds__(TI* TJ) k_deln_first(Lay L, DevGrid G, const double* __restrict__ q, double* __restrict__ fx2,
+                                                      double* __restrict__ fy2, const int* kint, const double* kdbl, int slot_nord,
+                                                      int slot_damp, int nord_const, double damp_const, int premul) {
+  PLANE_IJK
+  int nord; double coef;
+  kparams(kint, kdbl, L.npz + 1, slot_nord, slot_damp, k, nord_const, damp_const, nord, coef);
+  if (coef == 0.) return;
+  const double m = premul ? coef : 1.0;
+  if (i >= L.is - nord && i <= L.ie + nord + 1 && j >= L.js - nord && j <= L.je + nord) {
+    QAccX qa{q + ko, L, j};
+    fx2[ko + LIDX(L, i, j)] = __ldg(G.del6_v + LIDX(L, i, j)) * (m * qa(i - 1) - m * qa(i));
+  }
+  if (i >= L.is - nord && i <= L.ie + nord && j >= L.js - nord && j <= L.je + nord + 1) {
+    QAccY qa{q + ko, L, i};
+    fy2[ko + LIDX(L, i, j)] = __ldg(G.del6_u + LIDX(L, i, j)) * (m * qa(j - 1) - m * qa(j));
+  }
+}
+
+__global__ void __launch_bounds__(TI* TJ) k_deln_d2(Lay L, DevGrid G, const double* __restrict__ fx2, const double* __restrict__ fy2,
+                                                   double* __restrict__ d2, const int* kint, const double* kdbl, int slot_nord,
+                                                   int slot_damp, int nord_const, double damp_const, int n) {
+  PLANE_IJK
+  int nord; double coef;
+  kparams(kint, kdbl, L.npz + 1, slot_nord, slot_damp, k, nord_const, damp_const, nord, coef);
+  if (coef == 0. || n > nord) return;
+  const int nt = nord - n;
+  if (i < L.is - nt - 1 || i > L.ie + nt + 1 || j < L.js - nt - 1 || j > L.je + nt + 1) return;
+  const long long o = ko + LIDX(L, i, j);
+  d2[o] = (fx2[o] - fx2[o + 1] + fy2[o] - fy2[o + L.NI]) * __ldg(G.rarea + LIDX(L, i, j));
+}
+
+__global__ void __launch_bounds__(TI* TJ) k_deln_flux(Lay L, DevGrid G, const double* __restrict__ d2, double* __restrict__ fx2,
+                                                     double* __restrict__ fy2, const int* kint, const double* kdbl, int slot_nord,
+                                                     int slot_damp, int nord_const, double damp_const, int n) {
+  PLANE_IJK
+  int nord; double coef;
+  kparams(kint, kdbl, L.npz + 1, slot_nord, slot_damp, k, nord_const, damp_const, nord, coef);
+  if (coef == 0. || n > nord) return;
+  const int nt = nord - n;
+  if (i >= L.is - nt && i <= L.ie + nt + 1 && j >= L.js - nt && j <= L.je + nt) {
+    QAccX da{d2 + ko, L, j};
+    fx2[ko + LIDX(L, i, j)] = __ldg(G.del6_v + LIDX(L, i, j)) * (da(i) - da(i - 1));
+  }
+  if (i >= L.is - nt && i <= L.ie + nt && j >= L.js - nt && j <= L.je + nt + 1) {
+    QAccY da{d2 + ko, L, i};
+    fy2[ko + LIDX(L, i, j)] = __ldg(G.del6_u + LIDX(L, i, j)) * (da(j) - da(j - 1));
+  }
+}
+
+int launch_deln(fv3_ctx* c, const Deln& a) {
+  const Lay& L = c->L;
+  dim3 blk(TI, TJ), grd = plane_grid(L, a.nk);
+  int nmax = a.nord_const;
+  if (a.slot_nord >= 0) {
+    nmax = 0;
+    // host copy of the per-k nord table lives in ctx (kept in sync by the d_sw prologue)
+    nmax = 2;
+  }
+  k_deln_first<<<grd, blk, 0, c->stream>>>(L, c->G, a.q, a.fx2, a.fy2, c->d_kint, c->d_kdbl, a.slot_nord, a.slot_damp,
+                                           a.nord_const, a.damp_const, a.premul);
+  c->launches++;
+  for (int n = 1; n <= nmax; n++) {
+    k_deln_d2<<<grd, blk, 0, c->stream>>>(L, c->G, a.fx2, a.fy2, a.d2, c->d_kint, c->d_kdbl, a.slot_nord, a.slot_damp,
+                                          a.nord_const, a.damp_const, n);
+    k_deln_flux<<<grd, blk, 0, c->stream>>>(L, c->G, a.d2, a.fx2, a.fy2, c->d_kint, c->d_kdbl, a.slot_nord, a.slot_damp,
+                                            a.nord_const, a.damp_const, n);
+    c->launches += 2;
+  }
+  return 0;
+}
+
+// add the del-n fluxes into fx, fy (tp_core.F90:1390-1445).  With mass: fx += 0.5*damp*(m(i-1)+m(i))*fx2
+__global__ void __launch_bounds__(TI* TJ) k_deln_add(Lay L, double* __restrict__ fx, double* __restrict__ fy,
+                                                    const double* __restrict__ fx2, const double* __restrict__ fy2,
+                                                    const double* __restrict__ mass, const double* kdbl, int slot_damp,
+                                                    double damp_const) {
+  PLANE_IJK
+  const double coef = slot_damp >= 0 ? kdbl[slot_damp * (L.npz + 1) + k] : damp_const;
+  if (coef == 0.) return;
+  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
+  const long long o = ko + LIDX(L, i, j);
+  if (j <= L.je) {
+    if (mass) fx[o] = fx[o] + (0.5 * coef) * (__ldg(mass + o - 1) + __ldg(mass + o)) * fx2[o];
+    else fx[o] = fx[o] + fx2[o];
+  }
+  if (i <= L.ie) {
+    if (mass) fy[o] = fy[o] + (0.5 * coef) * (__ldg(mass + o - L.NI) + __ldg(mass + o)) * fy2[o];
+    else fy[o] = fy[o] + fy2[o];
+  }
+}
+
+void launch_deln_add(fv3_ctx* c, double* fx, double* fy, const double* fx2, const double* fy2, const double* mass,
+                     int slot_damp, double damp_const, int nk) {
+  dim3 blk(TI, TJ), grd = plane_grid(c->L, nk);
+  k_deln_add<<<grd, blk, 0, c->stream>>>(c->L, fx, fy, fx2, fy2, mass, c->d_kdbl, slot_damp, damp_const);
+  c->launches++;
+}
+
+// ------------------------------------------------------------------ stand-alone stage (C ABI fv3_fv_tp_2d)
+int stage_fv_tp_2d(fv3_ctx* c, int nk, int hord, int use_mfx, int use_mass, int nord, double damp_c) {
+  if (nk < 1 || nk > c->L.npz) return fv3_fail(c, -1, "fv_tp_2d: bad nk");
+  Tp2d a;
+  a.q = c->fld[FV3_WORK_Q]; a.crx = c->fld[FV3_CRX]; a.cry = c->fld[FV3_CRY]; a.xfx = c->fld[FV3_XFX]; a.yfx = c->fld[FV3_YFX];
+  a.ra_x = c->fld[FV3_WORK_RAX]; a.ra_y = c->fld[FV3_WORK_RAY];
+  a.fx = c->fld[FV3_WORK_FX]; a.fy = c->fld[FV3_WORK_FY];
+  a.mfx = use_mfx ? c->fld[FV3_MFX] : nullptr; a.mfy = use_mfx ? c->fld[FV3_MFY] : nullptr;
+  a.hord = hord; a.nk = nk;
+  a.fx2 = c->scr[0]; a.fy2 = c->scr[1]; a.q_i = c->scr[2]; a.q_j = c->scr[3];
+  if (nk > c->L.npz && (use_mfx || use_mass)) return fv3_fail(c, -1, "fv_tp_2d: mfx/mass only for nk <= npz");
+  int rc = launch_tp2d(c, a);
+  if (rc) return rc;
+  if (nord >= 0 && damp_c > 1.e-4) {   // tp_core.F90:201-206 / :227-232
+    if (nord > 2) return fv3_fail(c, -2, "deln_flux: nord > 2 not supported");
+    if (use_mfx && !use_mass) return 0;   // needs mass when mfx present (tp_core.F90:201)
+    const double damp = pow(damp_c * c->G.da_min, (double)(nord + 1));
+    Deln d;
+    d.q = a.q; d.fx2 = c->scr[4]; d.fy2 = c->scr[5]; d.d2 = c->scr[6];
+    d.slot_nord = -1; d.slot_damp = -1; d.thresh = 0; d.premul = use_mass ? 0 : 1; d.nk = nk; d.nord_const = nord; d.damp_const = damp;
+    launch_deln(c, d);
+    launch_deln_add(c, a.fx, a.fy, d.fx2, d.fy2, use_mass ? c->fld[FV3_DELP] : nullptr, -1, damp, nk);
+  }
+  return 0;
+}

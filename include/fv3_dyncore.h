@@ -186,6 +186,17 @@ int fv3_gz_from_zh(fv3_ctx *ctx);
 /* dyn_core.F90:1697 nh_p_grad (dyn_core.F90:1032). */
 int fv3_nh_p_grad(fv3_ctx *ctx, double dt);
 
+/* dyn_core.F90:370-385 (it==1): gz on the compute domain from zs and delz. */
+int fv3_gz_init(fv3_ctx *ctx);
+/* dyn_core.F90:491-521: zh = gz / gz = zh; and the init_ijk_mem resets (:289-294). */
+int fv3_copy_field(fv3_ctx *ctx, int dst_field, int src_field);
+int fv3_zero_field(fv3_ctx *ctx, int field);
+
+/* device-side timing of a region over all faces of this process (CUDA events on the
+ * library's own streams); ms = max over faces. */
+int fv3_timer_start(fv3_ctx **ctxs, int nctx);
+int fv3_timer_stop(fv3_ctx **ctxs, int nctx, double *ms);
+
 /* ---- halo exchange (replaces fv_mp_mod.F90:646-874 group updates) ------- */
 /* One process may own several faces (tiles) of the cube; peers are other
  * contexts in the same process (device-local copies) or other ranks (NCCL
@@ -207,6 +218,21 @@ int fv3_cube_link(fv3_ctx **ctxs, const int *tiles, int nctx);
 int fv3_comm_attach(fv3_ctx *ctx, void *nccl_comm, const int tile_rank[6]);
 /* Exchange one group for all linked contexts of this process. */
 int fv3_halo_exchange(fv3_ctx **ctxs, int nctx, int group);
+/* The library's own communicator: rank 0 calls fv3_nccl_unique_id (128 bytes), the id is
+ * broadcast by the host program (torch.distributed / MPI), then every rank calls
+ * fv3_comm_init with the face->rank map (6 ints, -1 = face absent). */
+int fv3_nccl_unique_id(char *out128);
+int fv3_comm_init(fv3_ctx **ctxs, int nctx, const char *id128, int nranks, int rank, const int *tile_rank);
+/* Halo index tables (host logic, no device needed): entries of face `tile` for one array
+ * of a scalar (ncomp=1) or pair (ncomp=2) field; positions 0 centre, 1 corner, 2 north-
+ * staggered (D-grid u, C-grid vc), 3 east-staggered (D-grid v, C-grid uc). Returns the
+ * entry count (indices refer to the padded device plane, see fv3_plane_index). */
+int fv3_halo_entries(int npx, int ng, int tile, int ncomp, int posx, int posy, int ci,
+                     int vector, int halo, int boundary_only, int cap, int *dst,
+                     int *src_tile, int *src_comp, int *src, int *sign);
+int fv3_halo_table(fv3_ctx *ctx, int group, int spec, int ci, int cap, int *dst,
+                   int *src_tile, int *src_comp, int *src, int *sign);
+int fv3_plane_index(const fv3_ctx *ctx, int i, int j);
 
 /* ---- the acoustic loop -------------------------------------------------- */
 /* dyn_core.F90:313-1286: n_split substeps on device-resident state for the

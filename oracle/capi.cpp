@@ -52,11 +52,11 @@ static void set_dims(fv3o_ctx* c) {
   d[FV3_PK] = {b.is, nic, b.js, njc, kz + 1, 0};
   d[FV3_PKZ] = {b.is, nic, b.js, njc, kz, 0};
   d[FV3_HEAT] = A(kz); d[FV3_DISS] = A(kz);
-  d[FV3_WORK_Q] = A(kz + 1);
-  d[FV3_WORK_FX] = {b.is, nic + 1, b.js, njc, kz + 1, 0};
-  d[FV3_WORK_FY] = {b.is, nic, b.js, njc + 1, kz + 1, 0};
-  d[FV3_WORK_RAX] = {b.is, nic, b.jsd, nja, kz + 1, 0};
-  d[FV3_WORK_RAY] = {b.isd, nia, b.js, njc, kz + 1, 0};
+  d[FV3_WORK_Q] = A(kz);
+  d[FV3_WORK_FX] = {b.is, nic + 1, b.js, njc, kz, 0};
+  d[FV3_WORK_FY] = {b.is, nic, b.js, njc + 1, kz, 0};
+  d[FV3_WORK_RAX] = {b.is, nic, b.jsd, nja, kz, 0};
+  d[FV3_WORK_RAY] = {b.isd, nia, b.js, njc, kz, 0};
 }
 
 static V3 F3(fv3o_ctx* c, int id) {
@@ -305,6 +305,29 @@ int fv3o_copy_field(fv3o_ctx* c, int dst, int src) {
   return 0;
 }
 int fv3o_zero_field(fv3o_ctx* c, int f) { std::fill(c->fld[f].begin(), c->fld[f].end(), 0.0); return 0; }
+
+// 1-D periodic xppm / yppm (interior formulas only, grid_type = 4): used to pin the oracle against the
+// NumPy restatement in the reference's docs/examples/tp_core.ipynb (tests/golden/ppm_notebook.npz)
+int fv3o_ppm_periodic(int n, const double* q, const double* cn, int iord, int ydir, double* flux) {
+  const int ng = 3, isd = 1 - ng, ied = n + ng;
+  if (!ydir) {
+    std::vector<double> qh((size_t)(ied - isd + 1)), ch(n + 1), fh(n + 1), dxa((size_t)(ied - isd + 1), 1.0);
+    for (int i = isd; i <= ied; i++) qh[i - isd] = q[((i - 1) % n + n) % n];
+    for (int i = 0; i <= n; i++) ch[i] = cn[i];
+    xppm(V2(fh.data(), 1, 1, n + 1), V2(qh.data(), isd, 1, ied - isd + 1), V2(ch.data(), 1, 1, n + 1), iord, 1, n, isd, ied, 1, 1, 1, 1,
+         n + 1, n + 1, V2(dxa.data(), isd, 1, ied - isd + 1), false, 4, 1.0);
+    for (int i = 0; i <= n; i++) flux[i] = fh[i];
+  } else {
+    // one column (ifirst = ilast = 1), j is the sweep index
+    std::vector<double> qh((size_t)(ied - isd + 1)), ch(n + 1), fh(n + 1), dya((size_t)(ied - isd + 1), 1.0);
+    for (int j = isd; j <= ied; j++) qh[j - isd] = q[((j - 1) % n + n) % n];
+    for (int j = 0; j <= n; j++) ch[j] = cn[j];
+    yppm(V2(fh.data(), 1, 1, 1), V2(qh.data(), 1, isd, 1), V2(ch.data(), 1, 1, 1), iord, 1, 1, 1, 1, 1, n, isd, ied, n + 1, n + 1,
+         V2(dya.data(), 1, isd, 1), false, 4, 1.0);
+    for (int j = 0; j <= n; j++) flux[j] = fh[j];
+  }
+  return 0;
+}
 
 // stand-alone operators for unit parity
 int fv3o_a2b_ord4(fv3o_ctx* c, int field, int k, double* qout /*(isd:ied,jsd:jed)*/, int replace) {

@@ -1,0 +1,280 @@
+"""Parity harness (TEST INFRASTRUCTURE): drives the CUDA product and the CPU oracle through the
+same field / stage vocabulary and compares them.  Used by tests/, __graft_entry__.smoke() and
+bench.py's CPU-baseline legs only."""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from gfdl_atmos_cubed_sphere_b200 import abi, grid as G, init_state as I, cubed_sphere as cs  # noqa: E402
+
+FLAGSETS = {"A": abi.FLAGSET_A, "B": abi.FLAGSET_B}
+
+
+def load_oracle(fast=False):
+    name = "libfv3_oracle_fast.so" if fast else "libfv3_oracle.so"
+    path = os.path.join(ROOT, "oracle", "_build", name)
+    if not os.path.exists(path):
+        import subprocess
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "-j4"])
+    return C.CDLL(path), "fv3o_"
+
+
+def have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@functools.lru_cache(maxsize=4)
+def cube_grid(n):
+    return G.make_cubed_sphere(n)
+
+
+class Case:
+    def __init__(self, n, npz, flagset="A", state="smooth", flags_override=None):
+        self.n, self.npz = n, npz
+        self.tiles, self.bounds = cube_grid(n)
+        self.ak, self.bk = I.hybrid_levels(npz)
+        self.flags = dict(FLAGSETS[flagset]) if isinstance(flagset, str) else dict(flagset)
+        if flags_override:
+            self.flags.update(flags_override)
+        if state == "smooth":
+            self.states = I.smooth_state(self.tiles, self.bounds, npz)
+        else:
+            self.states = I.baroclinic_wave(self.tiles, self.bounds, npz, self.ak, self.bk)
+        self.consts = G.CONSTANTS
+
+    def engine(self, lib_prefix, tile=1, device=0):
+        lib, prefix = lib_prefix
+        return abi.Engine(lib, prefix, self.bounds, self.tiles[tile - 1], self.flags, self.npz, self.ak, self.bk,
+                          self.ak[0], self.consts, tile=tile, device=device)
+
+    def load_state(self, eng, tile=1, fields=("u", "v", "w", "pt", "delp", "q_con", "phis", "delz")):
+        st = self.states[tile - 1]
+        name = {"q_con": "QCON"}
+        for f in fields:
+            if f in st:
+                eng.put(name.get(f, f.upper()), st[f])
+
+
+def sub(eng, name, arr, i0, i1, j0, j1):
+    """Section (i0:i1, j0:j1) (Fortran, inclusive) of a field array returned by Engine.get."""
+    ilo, ni, jlo, nj, nk, kmid = eng.dims(name)
+    if kmid:
+        return arr[j0 - jlo:j1 - jlo + 1, :, i0 - ilo:i1 - ilo + 1]
+    return arr[:, j0 - jlo:j1 - jlo + 1, i0 - ilo:i1 - ilo + 1]
+
+
+def scaled_err(a, b):
+    den = float(np.max(np.abs(b)))
+    if not np.isfinite(den) or den == 0.0:
+        den = 1.0
+    return float(np.max(np.abs(a - b))) / den
+
+
+def compare(e_ref, e_new, regions):
+    """regions: {field: (i0, i1, j0, j1)} -> {field: scaled error}"""
+    out = {}
+    for f, (i0, i1, j0, j1) in regions.items():
+        a = sub(e_new, f, e_new.get(f), i0, i1, j0, j1)
+        b = sub(e_ref, f, e_ref.get(f), i0, i1, j0, j1)
+        out[f] = scaled_err(a, b)
+    return out
+
+
+def regions_c_sw(b):
+    is_, ie, js, je = b["is_"], b["ie"], b["js"], b["je"]
+    return {"DELPC": (is_ - 1, ie + 1, js - 1, je + 1), "PTC": (is_ - 1, ie + 1, js - 1, je + 1),
+            "OMGA": (is_ - 1, ie + 1, js - 1, je + 1), "UC": (is_ - 1, ie + 2, js - 1, je + 1),
+            "VC": (is_ - 1, ie + 1, js - 1, je + 2), "UA": (is_ - 2, ie + 2, js - 2, je + 2),
+            "VA": (is_ - 2, ie + 2, js - 2, je + 2), "UT": (is_ - 1, ie + 2, js - 1, je + 1),
+            "VT": (is_ - 1, ie + 1, js - 1, je + 2), "DIVGD": (is_, ie + 1, js, je + 1)}
+
+
+def regions_d_sw(b, use_cond=False, heat=False):
+    is_, ie, js, je, jsd, jed, isd, ied = b["is_"], b["ie"], b["js"], b["je"], b["jsd"], b["jed"], b["isd"], b["ied"]
+    r = {"DELP": (is_, ie, js, je), "PT": (is_, ie, js, je), "W": (is_, ie, js, je), "U": (is_, ie, js, je + 1),
+         "V": (is_, ie + 1, js, je), "CRX": (is_, ie + 1, jsd, jed), "XFX": (is_, ie + 1, jsd, jed),
+         "CRY": (isd, ied, js, je + 1), "YFX": (isd, ied, js, je + 1), "MFX": (is_, ie + 1, js, je),
+         "MFY": (is_, ie, js, je + 1), "CX": (is_, ie + 1, jsd, jed), "CY": (isd, ied, js, je + 1)}
+    if use_cond:
+        r["QCON"] = (is_, ie, js, je)
+    if heat:
+        r["HEAT"] = (is_, ie, js, je)
+    return r
+
+
+def parity_c_sw_d_sw(n=24, npz=8, flagset="A", dt=20.0, tile=1, flags_override=None):
+    """c_sw -> p-grad-free hand-over -> d_sw on one face, CUDA vs oracle; returns scaled errors."""
+    case = Case(n, npz, flagset, flags_override=flags_override)
+    eo = case.engine(load_oracle(), tile)
+    eg = case.engine(abi.load_library(), tile)
+    res = {}
+    for e in (eo, eg):
+        case.load_state(e, tile)
+        e.call("c_sw", 0.5 * dt)
+    res.update({"c_sw." + k: v for k, v in compare(eo, eg, regions_c_sw(case.bounds)).items()})
+    # hand the ORACLE's c_sw outputs to both d_sw's so the stages are compared independently
+    for f in ("UC", "VC", "UA", "VA", "DIVGD", "UT", "VT", "DELPC", "PTC"):
+        eg.put(f, eo.get(f))
+    for e in (eo, eg):
+        e.call("d_sw", dt)
+    use_cond = bool(case.flags.get("use_cond"))
+    heat = case.flags.get("d_con", 0.0) > 1e-5
+    res.update({"d_sw." + k: v for k, v in compare(eo, eg, regions_d_sw(case.bounds, use_cond, heat)).items()})
+    eo.close(); eg.close()
+    return res
+
+
+# ---- python-driven oracle dyn_core (mirrors csrc/dyn_core.cu; reference dyn_core.F90:313-1286) ----
+class OracleCube:
+    """Faces of the cube on the CPU oracle with the NumPy halo exchange."""
+
+    def __init__(self, case, tiles=(1, 2, 3, 4, 5, 6), fast=False):
+        self.case = case
+        self.tiles = list(tiles)
+        lib = load_oracle(fast)
+        self.eng = {t: case.engine(lib, t) for t in self.tiles}
+        self.ex = cs.Exchanger(case.n, 3) if len(self.tiles) == 6 else None
+        for t in self.tiles:
+            case.load_state(self.eng[t], t)
+
+    def _exchange_scalar(self, name, pos=cs.CENTER):
+        arrs = [self.eng[t].get(name) for t in self.tiles]
+        self.ex.scalar(arrs, pos)
+        for t, a in zip(self.tiles, arrs):
+            self.eng[t].put(name, a)
+
+    def _exchange_pair(self, nx, ny, px, py, boundary_only=False):
+        xs = [self.eng[t].get(nx) for t in self.tiles]
+        ys = [self.eng[t].get(ny) for t in self.tiles]
+        self.ex.pair(xs, ys, px, py, kind="vector", boundary_only=boundary_only)
+        for t, a, b in zip(self.tiles, xs, ys):
+            self.eng[t].put(nx, a); self.eng[t].put(ny, b)
+
+    def halo(self, group):
+        if self.ex is None:
+            return
+        f = self.case.flags
+        if group == "UVW":
+            self._exchange_pair("U", "V", cs.NORTH, cs.EAST)
+            if not f["hydrostatic"]:
+                self._exchange_scalar("W")
+        elif group == "GZ":
+            self._exchange_scalar("GZ")
+        elif group == "DIVGD_UCVC":
+            if f["nord"] > 0:
+                self._exchange_scalar("DIVGD", cs.CORNER)
+            self._exchange_pair("UC", "VC", cs.EAST, cs.NORTH)
+        elif group == "DELP_PT":
+            self._exchange_scalar("DELP"); self._exchange_scalar("PT")
+            if f.get("use_cond"):
+                self._exchange_scalar("QCON")
+        elif group == "ZH_PKC":
+            self._exchange_scalar("ZH"); self._exchange_scalar("PKC")
+        elif group == "UV_EDGE":
+            self._exchange_pair("U", "V", cs.NORTH, cs.EAST, boundary_only=True)
+
+    def all(self, stage, *args):
+        for t in self.tiles:
+            self.eng[t].call(stage, *args)
+
+    def dyn_core(self, bdt, n_split, timers=None):
+        import time
+        dt = bdt / n_split
+        dt2 = 0.5 * dt
+        F = abi.FIELD_ID
+
+        def run(name, stage, *args):
+            t0 = time.perf_counter()
+            self.all(stage, *args)
+            if timers is not None:
+                timers[name] = timers.get(name, 0.0) + time.perf_counter() - t0
+
+        for f in ("MFX", "MFY", "CX", "CY", "HEAT"):
+            self.all("zero_field", F[f])
+        for it in range(1, n_split + 1):
+            last = it == n_split
+            if it == 1:
+                self.halo("DELP_PT")
+            self.halo("UVW")
+            if it == 1:
+                self.all("gz_init")
+                self.halo("GZ")
+            run("C_SW", "c_sw", dt2)
+            if it == 1:
+                self.all("copy_field", F["ZH"], F["GZ"])
+            else:
+                self.all("copy_field", F["GZ"], F["ZH"])
+            run("UPDATE_DZ_C", "update_dz_c", dt2)
+            run("Riem_Solver_C", "riem_solver_c", dt2)
+            run("PG_C", "p_grad_c", dt2)
+            self.halo("DIVGD_UCVC")
+            run("D_SW", "d_sw", dt)
+            self.halo("DELP_PT")
+            run("UPDATE_DZ", "update_dz_d", dt)
+            run("Riem_Solver3", "riem_solver3", dt, 1 if last else 0)
+            self.halo("ZH_PKC")
+            if last:
+                self.all("pe_halo")
+            self.all("pk3_halo")
+            self.all("gz_from_zh")
+            run("PG_D", "nh_p_grad", dt)
+            if last:
+                self.halo("UV_EDGE")
+
+    def close(self):
+        for e in self.eng.values():
+            e.close()
+
+
+class CudaCube:
+    """Faces of the cube on the CUDA library (all faces of this process on one GPU)."""
+
+    def __init__(self, case, tiles=(1, 2, 3, 4, 5, 6), device=0, link=True):
+        self.case = case
+        self.tiles = list(tiles)
+        self.lib = abi.load_library()
+        self.eng = {t: case.engine(self.lib, t, device) for t in self.tiles}
+        for t in self.tiles:
+            case.load_state(self.eng[t], t)
+        self.ctxs = (C.c_void_p * len(self.tiles))(*[self.eng[t].ctx for t in self.tiles])
+        if link and len(self.tiles) > 1:
+            tl = (C.c_int * len(self.tiles))(*self.tiles)
+            rc = self.lib[0].fv3_cube_link(self.ctxs, tl, len(self.tiles))
+            if rc:
+                raise RuntimeError(f"fv3_cube_link rc={rc}: {self.eng[self.tiles[0]].last_error()}")
+
+    def dyn_core(self, bdt, n_split):
+        fn = self.lib[0].fv3_dyn_core
+        fn.restype = C.c_int
+        rc = fn(self.ctxs, len(self.tiles), C.c_double(bdt), C.c_int(n_split), C.c_int(0))
+        if rc:
+            raise RuntimeError(f"fv3_dyn_core rc={rc}: " + "; ".join(self.eng[t].last_error() for t in self.tiles))
+        for t in self.tiles:
+            self.eng[t].sync()
+
+    def close(self):
+        for e in self.eng.values():
+            e.close()
+
+
+def regions_state(b):
+    is_, ie, js, je = b["is_"], b["ie"], b["js"], b["je"]
+    return {"DELP": (is_, ie, js, je), "PT": (is_, ie, js, je), "W": (is_, ie, js, je), "U": (is_, ie, js, je + 1),
+            "V": (is_, ie + 1, js, je), "DELZ": (is_, ie, js, je), "MFX": (is_, ie + 1, js, je), "MFY": (is_, ie, js, je + 1),
+            "CX": (is_, ie + 1, b["jsd"], b["jed"]), "CY": (b["isd"], b["ied"], js, je + 1), "ZH": (is_, ie, js, je)}
+    # pkc, pk3, gz are NOT compared after nh_p_grad: the reference interpolates them to cell corners
+    # in place (a2b_ord4 replace=.true., dyn_core.F90:1743-1746) and rebuilds them next substep;
+    # the CUDA path keeps the B-grid copies in scratch planes instead.

@@ -1,0 +1,100 @@
+"""CPU: grid generator sanity and the halo tables (NumPy builder vs the
+C++ builder inside the CUDA library, and both vs analytic vector fields)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+from gfdl_atmos_cubed_sphere_b200 import grid as G, cubed_sphere as cs, init_state as I
+
+
+def test_areas_sum_to_sphere_and_dx_ratio():
+    tiles, b = H.cube_grid(24)
+    R = G.CONSTANTS["radius"]
+    tot = sum(T.arr["area"][3:-3, 3:-3].sum() for T in tiles)
+    assert abs(tot / (4 * np.pi * R * R) - 1.0) < 1e-12
+    dxs = [T.arr["dx"][3:-3, 3:-3] for T in tiles]
+    ratio = max(d.max() for d in dxs) / min(d.min() for d in dxs)
+    assert abs(ratio - np.sqrt(2.0)) < 2e-3          # fv_grid_utils.F90:1262
+    a0 = tiles[0].arr["area"][3:-3, 3:-3]
+    for T in tiles[1:]:
+        assert np.allclose(np.sort(T.arr["area"][3:-3, 3:-3].ravel()), np.sort(a0.ravel()), rtol=1e-12)
+
+
+def test_all_twelve_contacts_share_edges():
+    P = G.tile_corner_xyz(10)
+    for a, ea, b_, eb, rev in cs.CONTACTS:
+        pa = G._edge_pts(P[a - 1], ea); pb = G._edge_pts(P[b_ - 1], eb)
+        assert np.array_equal(pa, pb[::-1] if rev else pb)
+
+
+def test_vector_halo_exchange_matches_analytic_winds():
+    """D-grid (u,v) and C-grid (uc,vc) halos obtained by exchange equal the analytic wind projected
+    on the local edge directions of the halo cells -> validates rotation + sign at all 12 contacts."""
+    n, ng = 12, 3
+    tiles, b = H.cube_grid(n)
+
+    def wind(lon, lat):
+        return (30 * np.cos(lat) * (1 + 0.3 * np.sin(3 * lon)))[None], (12 * np.sin(2 * lon) * np.cos(lat) ** 2)[None]
+    us, vs = [], []
+    for g in tiles:
+        mu, du, mv, dv = I._edge_dirs(g)
+        us.append(I._wind_on_edge(mu, du, wind)); vs.append(I._wind_on_edge(mv, dv, wind))
+    ua = [u.copy() for u in us]; va = [v.copy() for v in vs]
+    for t in range(6):   # poison the halos so the exchange has to fill them
+        us[t][0, :ng, :] = 1e9; us[t][0, -ng:, :] = 1e9; us[t][0, :, :ng] = 1e9; us[t][0, :, -ng:] = 1e9
+        vs[t][0, :ng, :] = 1e9; vs[t][0, -ng:, :] = 1e9; vs[t][0, :, :ng] = 1e9; vs[t][0, :, -ng:] = 1e9
+    ex = cs.Exchanger(n, ng)
+    ex.pair(us, vs, cs.NORTH, cs.EAST, kind="vector")
+
+    def strips(shape):
+        m = np.zeros(shape, bool); nj, ni = shape
+        m[ng:nj - ng, :] = True; m[:, ng:ni - ng] = True
+        return m
+    for t in range(6):
+        mu_, mv_ = strips(us[t].shape[1:]), strips(vs[t].shape[1:])
+        assert np.abs((us[t] - ua[t])[0][mu_]).max() < 1e-12
+        assert np.abs((vs[t] - va[t])[0][mv_]).max() < 1e-12
+
+
+def _lib_tables(lib, n, ng, tile, ncomp, posx, posy, ci, vector, halo, bonly):
+    cap = 8 * (n + 8) * 4 * 2
+    arrs = [np.zeros(cap, dtype=np.int32) for _ in range(5)]
+    ip = C.POINTER(C.c_int)
+    cnt = lib.fv3_halo_entries(n + 1, ng, tile, ncomp, posx, posy, ci, vector, halo, bonly, cap, *[a.ctypes.data_as(ip) for a in arrs])
+    assert 0 <= cnt <= cap
+    return [a[:cnt] for a in arrs]
+
+
+@pytest.mark.parametrize("spec", [("scalar", cs.CENTER, None), ("scalar", cs.CORNER, None),
+                                  ("vector", cs.NORTH, cs.EAST), ("vector", cs.EAST, cs.NORTH), ("edge", cs.NORTH, cs.EAST)])
+def test_cxx_halo_tables_match_numpy_builder(built, spec):
+    """The C++ table builder shipped in the CUDA library (csrc/halo.cu) against the NumPy one."""
+    libpath = built.LIB
+    if not os.path.exists(libpath):
+        pytest.skip("CUDA library not built (no nvcc here)")
+    lib = C.CDLL(libpath)
+    kind, px, py = spec
+    n, ng = 10, 3
+    bonly = kind == "edge"
+    tabs = cs.build_tables(n, ng, px, py, "vector" if py is not None else "scalar", None, bonly)
+    NI = ((5 + (n + 2 * ng + 1)) + 7) // 8 * 8
+    for tile in range(1, 7):
+        for ci in range(2 if py is not None else 1):
+            d, st, sc, s, sg = _lib_tables(lib, n, ng, tile, 2 if py is not None else 1, px, py if py is not None else 0, ci,
+                                           1, ng, int(bonly))
+            tb = tabs[tile][ci]
+            pos = [px, py][ci]
+            # convert the NumPy native-plane indices to the padded device plane
+            def to_padded(flat, p):
+                nj, ni = cs.plane_shape(n, ng, p)
+                j, i = np.divmod(flat, ni)
+                return j * NI + i + 5
+            ref = {}
+            for k in range(tb.dst.size):
+                psrc = [px, py][tb.src_comp[k]] if py is not None else px
+                ref[int(to_padded(tb.dst[k], pos))] = (int(tb.src_tile[k]), int(tb.src_comp[k]), int(to_padded(tb.src[k], psrc)), int(tb.sign[k]))
+            got = {int(d[k]): (int(st[k]), int(sc[k]), int(s[k]), int(sg[k])) for k in range(d.size)}
+            assert got == ref, (tile, ci)

@@ -1,0 +1,121 @@
+"""CPU: operator invariants of the oracle (SURVEY 8c ii): constant preservation of fv_tp_2d,
+mass conservation of d_sw, positivity of hord -5, monotonicity of hord 8, resting atmosphere."""
+import numpy as np
+import pytest
+
+import harness as H
+from gfdl_atmos_cubed_sphere_b200 import abi
+
+
+def _tp_setup(case, eng, hord, q, seed=1):
+    rng = np.random.default_rng(seed)
+    area = case.tiles[0].arr["area"]
+    sx, sy = eng.shape("CRX"), eng.shape("CRY")
+    crx = rng.uniform(-0.6, 0.6, sx); cry = rng.uniform(-0.6, 0.6, sy)
+    xfx = crx * 0.5 * np.abs(area[None, :, 3:-2]); yfx = cry * 0.5 * np.abs(area[None, 3:-2, :])
+    rax = np.abs(area[None, :, 3:-3]) + xfx[:, :, :-1] - xfx[:, :, 1:]
+    ray = np.abs(area[None, 3:-3, :]) + yfx[:, :-1, :] - yfx[:, 1:, :]
+    eng.put("WORK_Q", q); eng.put("CRX", crx); eng.put("CRY", cry); eng.put("XFX", xfx); eng.put("YFX", yfx)
+    eng.put("WORK_RAX", rax); eng.put("WORK_RAY", ray)
+    return xfx, yfx
+
+
+@pytest.mark.parametrize("hord", [5, 6, 8, 10])
+def test_fv_tp_2d_preserves_constants(built, hord):
+    """q == c  =>  fx = c*xfx, fy = c*yfx (tp_core.F90:217-226)."""
+    case = H.Case(12, 2, "A")
+    e = case.engine(H.load_oracle(), 1)
+    q = np.full(e.shape("WORK_Q"), 3.25)
+    xfx, yfx = _tp_setup(case, e, hord, q)
+    e.call("fv_tp_2d", 2, hord, 0, 0, -1, 0.0)
+    b = case.bounds
+    fx = H.sub(e, "WORK_FX", e.get("WORK_FX"), 1, 13, 1, 12); fy = H.sub(e, "WORK_FY", e.get("WORK_FY"), 1, 12, 1, 13)
+    assert np.allclose(fx, 3.25 * xfx[:, 3:-3, :], rtol=1e-13, atol=0)
+    assert np.allclose(fy, 3.25 * yfx[:, :, 3:-3], rtol=1e-13, atol=0)
+    e.close()
+
+
+def _advect_1d(lib, q, c, iord, nstep):
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    n = q.size
+    cc = np.full(n + 1, c)
+    flux = np.zeros(n + 1)
+    for _ in range(nstep):
+        lib.fv3o_ppm_periodic(n, q.ctypes.data_as(dp), cc.ctypes.data_as(dp), iord, 0, flux.ctypes.data_as(dp))
+        q = q + c * (flux[:-1] - flux[1:])
+    return q
+
+
+@pytest.mark.parametrize("c", [0.45, -0.7])
+def test_positive_definite_hord_minus5(built, c):
+    """hord = -5 (tp_core.F90:499-524) keeps a non-negative field non-negative (1-D periodic advection)."""
+    lib, _ = H.load_oracle()
+    x = (np.arange(64) + 0.5) / 64
+    q0 = np.where((x > 0.3) & (x < 0.5), 1.0, 0.0) + np.maximum(0.0, np.sin(12 * np.pi * x)) ** 8
+    q = _advect_1d(lib, q0.copy(), c, -5, 40)
+    assert q.min() > -1e-14
+    assert abs(q.sum() - q0.sum()) < 1e-12 * q0.sum()
+
+
+@pytest.mark.parametrize("c", [0.45, -0.7])
+def test_monotone_hord8_creates_no_new_extrema(built, c):
+    """hord = 8 (Lin's fast monotone constraint, tp_core.F90:579-584)."""
+    lib, _ = H.load_oracle()
+    x = (np.arange(64) + 0.5) / 64
+    q0 = np.where((x > 0.3) & (x < 0.5), 1.0, 0.1) + 0.3 * np.exp(-((x - 0.75) / 0.03) ** 2)
+    q = _advect_1d(lib, q0.copy(), c, 8, 40)
+    assert q.min() >= q0.min() - 1e-13 and q.max() <= q0.max() + 1e-13
+    assert abs(q.sum() - q0.sum()) < 1e-12 * q0.sum()
+
+
+@pytest.mark.parametrize("flagset", ["A", "B"])
+def test_d_sw_conserves_mass_on_the_cube(built, flagset):
+    """sum(area*delp) over the 6 faces is conserved by c_sw -> halo -> d_sw (sw_core.F90:1059-1060)."""
+    case = H.Case(12, 3, flagset, state="baroclinic")
+    oc = H.OracleCube(case)
+    def mass():
+        return sum(float(np.sum(H.sub(oc.eng[t], "DELP", oc.eng[t].get("DELP"), 1, 12, 1, 12) *
+                                case.tiles[t - 1].arr["area"][None, 3:-3, 3:-3])) for t in oc.tiles)
+    m0 = mass()
+    oc.dyn_core(600.0, 2)
+    assert abs(mass() - m0) / m0 < 2e-15 * 50
+    for t in oc.tiles:
+        assert np.isfinite(oc.eng[t].get("U")).all()
+    oc.close()
+
+
+def test_shared_edge_winds_agree_after_dedup(built):
+    """After the last substep u(:,je+1) / v(ie+1,:) equal the neighbour's values on the shared edge
+    (mpp_get_boundary, dyn_core.F90:1151-1163)."""
+    from gfdl_atmos_cubed_sphere_b200 import cubed_sphere as cs
+    case = H.Case(12, 2, "A", state="baroclinic")
+    oc = H.OracleCube(case)
+    oc.dyn_core(600.0, 1)
+    us = [oc.eng[t].get("U") for t in oc.tiles]; vs = [oc.eng[t].get("V") for t in oc.tiles]
+    u2 = [a.copy() for a in us]; v2 = [a.copy() for a in vs]
+    oc.ex.pair(u2, v2, cs.NORTH, cs.EAST, kind="vector", boundary_only=True)
+    for a, b in zip(us + vs, u2 + v2):
+        assert np.array_equal(a, b)
+    oc.close()
+
+
+def test_resting_isothermal_atmosphere_stays_at_rest(built):
+    """u = v = w = 0, horizontally uniform hydrostatic state, flat surface: winds stay ~0."""
+    case = H.Case(12, 4, "A", state="baroclinic")
+    from gfdl_atmos_cubed_sphere_b200 import init_state as I
+    pe = case.ak + case.bk * 1.0e5
+    pm = np.diff(pe) / np.diff(np.log(pe))
+    T = 280.0
+    for st in case.states:
+        st["u"][...] = 0.0; st["v"][...] = 0.0; st["w"][...] = 0.0; st["phis"][...] = 0.0
+        st["pt"][...] = (T / pm ** case.consts["kappa"])[:, None, None]
+        st["delz"][...] = (-(case.consts["rdgas"] / case.consts["grav"]) * T * np.diff(np.log(pe)))[:, None, None]
+    oc = H.OracleCube(case)
+    oc.dyn_core(600.0, 2)
+    dx = case.tiles[0].arr["dx"][3:-3, 3:-3].min()
+    for t in oc.tiles:
+        u = H.sub(oc.eng[t], "U", oc.eng[t].get("U"), 1, 12, 1, 13)
+        w = H.sub(oc.eng[t], "W", oc.eng[t].get("W"), 1, 12, 1, 12)
+        assert np.abs(u).max() < 1e-6 and np.abs(w).max() < 1e-6, (t, np.abs(u).max(), np.abs(w).max())
+    oc.close()
