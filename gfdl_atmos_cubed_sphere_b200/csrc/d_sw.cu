@@ -166,7 +166,7 @@ struct WindCtx {
   }
 };
 
-__global__ void __launch_bounds__(TI* TJ) k_dsw_wind(Lay L, DevGrid G, const double* __restrict__ uc, const double* __restrict__ vc,
+__global__ void __launch_bounds__(TI* TJ, 4) k_dsw_wind(Lay L, DevGrid G, const double* __restrict__ uc, const double* __restrict__ vc,
                                                     double* __restrict__ uts, double* __restrict__ vts, double* __restrict__ crx,
                                                     double* __restrict__ cry, double* __restrict__ xfx, double* __restrict__ yfx,
                                                     double* __restrict__ cx, double* __restrict__ cy, double dt) {
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_wfin(Lay L, double* __restrict__
 // ---------------------------------------------------------------------------------------------
 // kinetic energy at cell corners (sw_core.F90:1078-1228)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TI* TJ) k_dsw_ke(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
+__global__ void __launch_bounds__(TI* TJ, 4) k_dsw_ke(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
                                                   const double* __restrict__ uc, const double* __restrict__ vc, const double* __restrict__ uts,
                                                   const double* __restrict__ vts, double* __restrict__ ke, double dt, int hord_mt) {
   PLANE_IJK
@@ -290,17 +290,29 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_ke(Lay L, DevGrid G, const doubl
   // ytp_v: advect v along y with vb (:1134)
   double k1;
   {
-    Acc va{v + ko, LIDX(L, i, 0), L.NI};
-    Acc dya{G.dy, LIDX(L, i, 0), L.NI}, rdy{G.rdy, LIDX(L, i, 0), L.NI};
-    const double f = flux_wind(va, dya, rdy, j, vb, hord_mt, npy, cube, cube && (i == 1 || i == npx));
+    double f;
+    if (cube && j >= 4 && j <= npy - 3) {
+      const long long o = ko + LIDX(L, i, j);
+      f = flux_wind_fast(v + o, L.NI, vb, G2(rdy, i, j - 1), G2(rdy, i, j), hord_mt);
+    } else {
+      Acc va{v + ko, LIDX(L, i, 0), L.NI};
+      Acc dya{G.dy, LIDX(L, i, 0), L.NI}, rdy{G.rdy, LIDX(L, i, 0), L.NI};
+      f = flux_wind(va, dya, rdy, j, vb, hord_mt, npy, cube, cube && (i == 1 || i == npx));
+    }
     k1 = vb * f;
   }
   // xtp_u: advect u along x with ub (:1191)
   double k2;
   {
-    Acc ua{u + ko, LIDX(L, 0, j), 1};
-    Acc dxa{G.dx, LIDX(L, 0, j), 1}, rdx{G.rdx, LIDX(L, 0, j), 1};
-    const double f = flux_wind(ua, dxa, rdx, i, ub, hord_mt, npx, cube, cube && (j == 1 || j == npy));
+    double f;
+    if (cube && i >= 4 && i <= npx - 3) {
+      const long long o = ko + LIDX(L, i, j);
+      f = flux_wind_fast(u + o, 1, ub, G2(rdx, i - 1, j), G2(rdx, i, j), hord_mt);
+    } else {
+      Acc ua{u + ko, LIDX(L, 0, j), 1};
+      Acc dxa{G.dx, LIDX(L, 0, j), 1}, rdx{G.rdx, LIDX(L, 0, j), 1};
+      f = flux_wind(ua, dxa, rdx, i, ub, hord_mt, npx, cube, cube && (j == 1 || j == npy));
+    }
     k2 = ub * f;
   }
   double kev = 0.5 * (k1 + k2);

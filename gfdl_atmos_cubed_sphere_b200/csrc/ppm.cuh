@@ -335,6 +335,113 @@ __device__ __forceinline__ double flux_wind(const Q& u, const D& dx, const D& rd
   return fl;
 }
 
+// ------------------------------------------------------------------ interior fast paths
+// For an interface i with 4 <= i <= n-3 every cell the flux can touch is an ordinary interior
+// cell (no cube-edge formula, no corner remap): the whole operator is register arithmetic on
+// the 6-point window q(i-3..i+2), loaded once with plain strided loads.  Operation order is
+// identical to cell_mono / cell_unlim / cell_wind_* above (the parity tests compare both).
+__device__ __forceinline__ double dm3(double qm, double q0, double qp) {
+  const double xt = 0.25 * (qp - qm);
+  return fsign(fmin(fmin(fabs(xt), max3(qm, q0, qp) - q0), q0 - min3(qm, q0, qp)), xt);
+}
+
+__device__ __forceinline__ double flux_scalar_fast(const double* __restrict__ p, int s, double c, int iord) {
+  const double a0 = __ldg(p - 3 * s), a1 = __ldg(p - 2 * s), a2 = __ldg(p - s), a3 = __ldg(p), a4 = __ldg(p + s), a5 = __ldg(p + 2 * s);
+  if (iord >= 8) {
+    const bool up = c > 0.;
+    const double qm2 = up ? a0 : a1, qm1 = up ? a1 : a2, q0 = up ? a2 : a3, qp1 = up ? a3 : a4, qp2 = up ? a4 : a5;
+    const double dmm = dm3(qm2, qm1, q0), dm0 = dm3(qm1, q0, qp1), dmp = dm3(q0, qp1, qp2);
+    const double al0 = 0.5 * (qm1 + q0) + r3 * (dmm - dm0);
+    const double al1 = 0.5 * (q0 + qp1) + r3 * (dm0 - dmp);
+    double bl, br;
+    if (iord == 8) {
+      const double xt = 2. * dm0;
+      bl = -fsign(fmin(fabs(xt), fabs(al0 - q0)), xt);
+      br = fsign(fmin(fabs(xt), fabs(al1 - q0)), xt);
+    } else {
+      bl = al0 - q0; br = al1 - q0;
+      if (fabs(dmm) + fabs(dm0) + fabs(dmp) < near_zero_tp) { bl = 0.; br = 0.; }
+      else if (fabs(3. * (bl + br)) > fabs(bl - br)) {
+        const double dqm2 = 2. * (qm1 - qm2), dqm1 = 2. * (q0 - qm1), dq0 = 2. * (qp1 - q0), dqp1 = 2. * (qp2 - qp1);
+        const double pmp_2 = dqm1, lac_2 = pmp_2 - 0.75 * dqm2;
+        br = fmin(max3(0., pmp_2, lac_2), fmax(br, min3(0., pmp_2, lac_2)));
+        const double pmp_1 = -dq0, lac_1 = pmp_1 + 0.75 * dqp1;
+        bl = fmin(max3(0., pmp_1, lac_1), fmax(bl, min3(0., pmp_1, lac_1)));
+      }
+    }
+    return up ? q0 + (1. - c) * (br - c * (bl + br)) : q0 + (1. + c) * (bl + c * (bl + br));
+  }
+  double alm = p1 * (a1 + a2) + p2 * (a0 + a3);
+  double al0 = p1 * (a2 + a3) + p2 * (a1 + a4);
+  double alp = p1 * (a3 + a4) + p2 * (a2 + a5);
+  if (iord < 0) { alm = fmax(0., alm); al0 = fmax(0., al0); alp = fmax(0., alp); }
+  auto cell = [&](double q0, double l, double r) {
+    CellU cu; cu.bl = l - q0; cu.br = r - q0; cu.b0 = cu.bl + cu.br;
+    if (iord == 5) cu.smt = cu.bl * cu.br < 0.;
+    else if (iord == -5) {
+      cu.smt = cu.bl * cu.br < 0.;
+      const double da1 = cu.br - cu.bl, a4_ = -3. * cu.b0;
+      if (fabs(da1) < -a4_) {
+        if (q0 + 0.25 / a4_ * (da1 * da1) + a4_ * r12 < 0.) {
+          if (!cu.smt) { cu.br = 0.; cu.bl = 0.; cu.b0 = 0.; }
+          else if (da1 > 0.) { cu.br = -2. * cu.bl; cu.b0 = -cu.bl; }
+          else { cu.bl = -2. * cu.br; cu.b0 = -cu.br; }
+        }
+      }
+    } else cu.smt = 3. * fabs(cu.b0) < fabs(cu.bl - cu.br);
+    return cu;
+  };
+  const CellU A = cell(a2, alm, al0), B = cell(a3, al0, alp);
+  double fx1, fl;
+  if (c > 0.) { fx1 = (1. - c) * (A.br - c * A.b0); fl = a2; }
+  else { fx1 = (1. + c) * (B.bl + c * B.b0); fl = a3; }
+  if (A.smt || B.smt) fl = fl + fx1;
+  return fl;
+}
+
+// winds: c is a distance; rm, r0 = rdx of cells i-1 and i
+__device__ __forceinline__ double flux_wind_fast(const double* __restrict__ p, int s, double c, double rm, double r0, int iord) {
+  const double a0 = __ldg(p - 3 * s), a1 = __ldg(p - 2 * s), a2 = __ldg(p - s), a3 = __ldg(p), a4 = __ldg(p + s), a5 = __ldg(p + 2 * s);
+  if (iord >= 8) {
+    const bool up = c > 0.;
+    const double um2 = up ? a0 : a1, um1 = up ? a1 : a2, u0 = up ? a2 : a3, up1 = up ? a3 : a4, up2 = up ? a4 : a5;
+    const double dmm = dm3(um2, um1, u0), dm0 = dm3(um1, u0, up1), dmp = dm3(u0, up1, up2);
+    const double al0 = 0.5 * (um1 + u0) + r3 * (dmm - dm0), al1 = 0.5 * (u0 + up1) + r3 * (dm0 - dmp);
+    double bl, br;
+    if (iord == 8) {
+      const double xt = 2. * dm0;
+      bl = -fsign(fmin(fabs(xt), fabs(al0 - u0)), xt);
+      br = fsign(fmin(fabs(xt), fabs(al1 - u0)), xt);
+    } else {
+      bl = al0 - u0; br = al1 - u0;
+      if (fabs(dm0) < near_zero_sw) {
+        if (fabs(dmm) + fabs(dmp) < near_zero_sw) { bl = 0.; br = 0.; }
+      } else if (fabs(3. * (bl + br)) > fabs(bl - br)) {
+        const double dq0 = up1 - u0, dqp1 = up2 - up1, dqm1 = u0 - um1, dqm2 = um1 - um2;
+        const double pmp_1 = -2. * dq0, lac_1 = pmp_1 + 1.5 * dqp1;
+        bl = fmin(max3(0., pmp_1, lac_1), fmax(bl, min3(0., pmp_1, lac_1)));
+        const double pmp_2 = 2. * dqm1, lac_2 = pmp_2 - 1.5 * dqm2;
+        br = fmin(max3(0., pmp_2, lac_2), fmax(br, min3(0., pmp_2, lac_2)));
+      }
+    }
+    const double cfl = c * (up ? rm : r0);
+    return up ? u0 + (1. - cfl) * (br - cfl * (bl + br)) : u0 + (1. + cfl) * (bl + cfl * (bl + br));
+  }
+  const double alm = p1 * (a1 + a2) + p2 * (a0 + a3);
+  const double al0 = p1 * (a2 + a3) + p2 * (a1 + a4);
+  const double alp = p1 * (a3 + a4) + p2 * (a2 + a5);
+  const double Abl = alm - a2, Abr = al0 - a2, Ab0 = Abl + Abr;
+  const double Bbl = al0 - a3, Bbr = alp - a3, Bb0 = Bbl + Bbr;
+  bool As, Bs;
+  if (iord == 5) { As = Abl * Abr < 0.; Bs = Bbl * Bbr < 0.; }
+  else { As = 3. * fabs(Ab0) < fabs(Abl - Abr); Bs = 3. * fabs(Bb0) < fabs(Bbl - Bbr); }
+  double fx0, fl;
+  if (c > 0.) { const double cfl = c * rm; fx0 = (1. - cfl) * (Abr - cfl * Ab0); fl = a2; }
+  else { const double cfl = c * r0; fx0 = (1. + cfl) * (Bbl + cfl * Bb0); fl = a3; }
+  if (As || Bs) fl = fl + fx0;
+  return fl;
+}
+
 __host__ inline bool hord_supported(int h) { return h == 5 || h == 6 || h == -5 || h == 8 || h == 10; }
 __host__ inline bool hord_wind_supported(int h) { return h == 5 || h == 6 || h == 8 || h == 10; }
 

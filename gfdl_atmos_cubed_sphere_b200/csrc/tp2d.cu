@@ -27,7 +27,7 @@ static inline dim3 plane_grid(const Lay& L, int nk) { return dim3((L.NI + TI - 1
   const int k = blockIdx.z;                                     \
   const long long ko = (long long)k * L.plane;
 
-__global__ void __launch_bounds__(TI* TJ) k_tp_inner(Lay L, DevGrid G, const double* __restrict__ q,
+__global__ void __launch_bounds__(TI* TJ, 4) k_tp_inner(Lay L, DevGrid G, const double* __restrict__ q,
                                                     const double* __restrict__ crx, const double* __restrict__ cry,
                                                     double* __restrict__ fx2, double* __restrict__ fy2, int ord_in) {
   PLANE_IJK
@@ -35,15 +35,25 @@ __global__ void __launch_bounds__(TI* TJ) k_tp_inner(Lay L, DevGrid G, const dou
   const bool cube = L.cube;
   // fy2 (isd:ied, js:je+1): y sweep with the dir=2 corner view  (tp_core.F90:143-148)
   if (i <= L.ied && j >= L.js && j <= L.je + 1) {
-    QAccY qa{q + ko, L, i};
-    Acc da{G.dya, LIDX(L, i, 0), L.NI};
-    fy2[ko + LIDX(L, i, j)] = flux_scalar(qa, da, j, __ldg(cry + ko + LIDX(L, i, j)), ord_in, L.npy, cube);
+    const long long o = ko + LIDX(L, i, j);
+    const double c = __ldg(cry + o);
+    if (!cube || (j >= 4 && j <= L.npy - 3)) fy2[o] = flux_scalar_fast(q + o, L.NI, c, ord_in);
+    else {
+      QAccY qa{q + ko, L, i};
+      Acc da{G.dya, LIDX(L, i, 0), L.NI};
+      fy2[o] = flux_scalar(qa, da, j, c, ord_in, L.npy, cube);
+    }
   }
   // fx2 (is:ie+1, jsd:jed): x sweep with the dir=1 corner view  (tp_core.F90:164-169)
   if (i >= L.is && i <= L.ie + 1 && j <= L.jed) {
-    QAccX qa{q + ko, L, j};
-    Acc da{G.dxa, LIDX(L, 0, j), 1};
-    fx2[ko + LIDX(L, i, j)] = flux_scalar(qa, da, i, __ldg(crx + ko + LIDX(L, i, j)), ord_in, L.npx, cube);
+    const long long o = ko + LIDX(L, i, j);
+    const double c = __ldg(crx + o);
+    if (!cube || (i >= 4 && i <= L.npx - 3)) fx2[o] = flux_scalar_fast(q + o, 1, c, ord_in);
+    else {
+      QAccX qa{q + ko, L, j};
+      Acc da{G.dxa, LIDX(L, 0, j), 1};
+      fx2[o] = flux_scalar(qa, da, i, c, ord_in, L.npx, cube);
+    }
   }
 }
 
@@ -72,7 +82,7 @@ __global__ void __launch_bounds__(TI* TJ) k_tp_qiqj(Lay L, DevGrid G, const doub
   }
 }
 
-__global__ void __launch_bounds__(TI* TJ) k_tp_outer(Lay L, DevGrid G, const double* __restrict__ q_i,
+__global__ void __launch_bounds__(TI* TJ, 4) k_tp_outer(Lay L, DevGrid G, const double* __restrict__ q_i,
                                                     const double* __restrict__ q_j, const double* __restrict__ crx,
                                                     const double* __restrict__ cry, const double* __restrict__ fx2,
                                                     const double* __restrict__ fy2, const double* __restrict__ wx,
@@ -83,15 +93,23 @@ __global__ void __launch_bounds__(TI* TJ) k_tp_outer(Lay L, DevGrid G, const dou
   const bool cube = L.cube;
   const long long o = ko + LIDX(L, i, j);
   if (j <= L.je) {  // fx (is:ie+1, js:je)  tp_core.F90:161, :193/:219
-    Acc qa{q_i + ko, LIDX(L, 0, j), 1};
-    Acc da{G.dxa, LIDX(L, 0, j), 1};
-    const double f = flux_scalar(qa, da, i, __ldg(crx + o), ord_ou, L.npx, cube);
+    double f;
+    if (!cube || (i >= 4 && i <= L.npx - 3)) f = flux_scalar_fast(q_i + o, 1, __ldg(crx + o), ord_ou);
+    else {
+      Acc qa{q_i + ko, LIDX(L, 0, j), 1};
+      Acc da{G.dxa, LIDX(L, 0, j), 1};
+      f = flux_scalar(qa, da, i, __ldg(crx + o), ord_ou, L.npx, cube);
+    }
     fx[o] = 0.5 * (f + __ldg(fx2 + o)) * __ldg(wx + o);
   }
   if (i <= L.ie) {  // fy (is:ie, js:je+1)  tp_core.F90:180, :198/:224
-    Acc qa{q_j + ko, LIDX(L, i, 0), L.NI};
-    Acc da{G.dya, LIDX(L, i, 0), L.NI};
-    const double f = flux_scalar(qa, da, j, __ldg(cry + o), ord_ou, L.npy, cube);
+    double f;
+    if (!cube || (j >= 4 && j <= L.npy - 3)) f = flux_scalar_fast(q_j + o, L.NI, __ldg(cry + o), ord_ou);
+    else {
+      Acc qa{q_j + ko, LIDX(L, i, 0), L.NI};
+      Acc da{G.dya, LIDX(L, i, 0), L.NI};
+      f = flux_scalar(qa, da, j, __ldg(cry + o), ord_ou, L.npy, cube);
+    }
     fy[o] = 0.5 * (f + __ldg(fy2 + o)) * __ldg(wy + o);
   }
 }
