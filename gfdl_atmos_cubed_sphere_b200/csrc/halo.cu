@@ -147,7 +147,7 @@ struct HaloPlan {
   int my_rank;
   void* comm;              // ncclComm_t
   double *sendbuf[6], *recvbuf[6];
-  size_t bufcap;
+  size_t bufcap[6];
   std::vector<int*> dev_alloc;
 };
 
@@ -219,7 +219,7 @@ static int halo_build(fv3_ctx* c) {
   if (!c->L.cube) return fv3_fail(c, -2, "halo exchange needs the cubed-sphere grid (grid_type < 3)");
   HaloPlan* hp = new HaloPlan();
   for (int t = 0; t < 6; t++) { hp->peer[t] = nullptr; hp->tile_rank[t] = -1; hp->sendbuf[t] = hp->recvbuf[t] = nullptr; }
-  hp->comm = nullptr; hp->my_rank = 0; hp->bufcap = 0;
+  hp->comm = nullptr; hp->my_rank = 0; for (int t = 0; t < 6; t++) hp->bufcap[t] = 0;
   c->halo = hp;
   const int me = c->tile;
   for (int g = 0; g < FV3_NUM_HALO_GROUPS; g++) {
@@ -427,12 +427,12 @@ int fv3_halo_exchange(fv3_ctx** ctxs, int nctx, int group) {
         }
         if (ns == 0 && nr == 0) continue;
         const size_t need = std::max(ns, nr);
-        if (need > hp->bufcap || !hp->sendbuf[t - 1]) {
-          const size_t cap = std::max(need, hp->bufcap);
+        if (need > hp->bufcap[t - 1] || !hp->sendbuf[t - 1]) {
+          const size_t cap = need + need / 4;
           cudaFree(hp->sendbuf[t - 1]); cudaFree(hp->recvbuf[t - 1]);
           FV3_CUDA(c, cudaMalloc(&hp->sendbuf[t - 1], cap * sizeof(double)));
           FV3_CUDA(c, cudaMalloc(&hp->recvbuf[t - 1], cap * sizeof(double)));
-          hp->bufcap = std::max(hp->bufcap, cap);
+          hp->bufcap[t - 1] = cap;
         }
         // pack
         size_t off = 0;
