@@ -17,6 +17,7 @@
 //    1392-1424; the next c_sw overwrites them anyway).
 #include "tp2d.cuh"
 #include "ppm.cuh"
+#include "tp_tile.cuh"
 #include <cmath>
 
 using namespace ppm;
@@ -614,6 +615,222 @@ static void dsw_tables(fv3_ctx* c, std::vector<int>& ki, std::vector<double>& kd
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused transport of delp, w, q_con, pt (sw_core.F90:919-1066, :1262-1283): ONE kernel per d_sw call.
+// A CTA owns a 32x16 tile of one level (tp_tile.cuh).  The Courant numbers / area fluxes are staged once and
+// shared by the fields; the mass fluxes of delp stay in shared memory and weight the fluxes of the other fields;
+// the flux divergences are applied in the epilogue (thread = one cell), so fx, fy, gx, gy never touch HBM.
+// The del-n damping fluxes (wide stencil, separate kernels) are read from global and added on the fly.
+// ---------------------------------------------------------------------------------------------
+struct DswTr {
+  const double *delp, *pt, *w, *qcon;                  // inputs (qcon/w nullable)
+  const double *crx, *cry, *xfx, *yfx;
+  const double *dpx, *dpy;                             // del-n flux of delp  (nullable)
+  const double *ptx, *pty;                             // del-n flux of pt    (nullable)
+  const double *qcx, *qcy;                             // del-n flux of q_con (nullable)
+  const double* dw;                                    // w damping increment (nullable)
+  double *delp_o, *pt_o, *w_o, *qcon_o;
+  double *mfx, *mfy;                                   // flux capacitors (accumulated)
+  const double* kdbl;
+  int hord_dp, hord_vt, hord_tm;
+};
+struct DswSmem {
+  tpt::Smem t;
+  double mfx[tpt::TY][tpt::TX + 1];
+  double mfy[tpt::TY + 1][tpt::TX];
+};
+
+// weight the unweighted fluxes of the current field by the mass fluxes (+ mass-weighted del-n flux, tp_core.F90:1390-1445)
+__device__ __forceinline__ void weight_by_mass(const Lay& L, DswSmem& S, const tpt::Tile& T, const double* __restrict__ delp,
+                                               const double* __restrict__ dx_, const double* __restrict__ dy_, double coef) {
+  using namespace tpt;
+  TPT_LOOP(TY * (TX + 1), TX + 1, r, c) {
+    double g = FX(S.t, r, c) * S.mfx[r][c];
+    if (dx_) {
+      const int o = T.idx(min(T.i0 + c, L.ie + 1), min(T.j0 + r, L.je));
+      g = g + (0.5 * coef) * (__ldg(delp + T.ko + o - 1) + __ldg(delp + T.ko + o)) * __ldg(dx_ + T.ko + o);
+    }
+    FX(S.t, r, c) = g;
+  }
+  TPT_LOOP((TY + 1) * TX, TX, r, c) {
+    double g = FY(S.t, r, c) * S.mfy[r][c];
+    if (dy_) {
+      const int o = T.idx(min(T.i0 + c, L.ie), min(T.j0 + r, L.je + 1));
+      g = g + (0.5 * coef) * (__ldg(delp + T.ko + o - T.NI) + __ldg(delp + T.ko + o)) * __ldg(dy_ + T.ko + o);
+    }
+    FY(S.t, r, c) = g;
+  }
+  __syncthreads();
+}
+
+template <bool MDP, bool MVT, bool MTM>
+__global__ void __launch_bounds__(tpt::NT, 2) k_dsw_transport(Lay L, DevGrid G, DswTr a) {
+  using namespace tpt;
+  static_assert(TX * TY == NT, "one thread per cell in the epilogue");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DswSmem& S = *reinterpret_cast<DswSmem*>(smem_raw);
+  const Tile T = make_tile(L);
+  const int k = blockIdx.z, n1 = L.npz + 1;
+  const int cr_ = threadIdx.x / TX, cc_ = threadIdx.x % TX;          // this thread's cell
+  const int ci = T.i0 + cc_, cj = T.j0 + cr_;
+  const bool cell_ok = ci <= L.ie && cj <= L.je;
+  const int co = T.idx(min(ci, L.ie), min(cj, L.je));
+  const bool lastx = T.i0 + TX > L.ie, lasty = T.j0 + TY > L.je;
+  const int in_dp = (a.hord_dp == 10) ? 8 : a.hord_dp, in_vt = (a.hord_vt == 10) ? 8 : a.hord_vt, in_tm = (a.hord_tm == 10) ? 8 : a.hord_tm;
+  const double c_dp = a.kdbl[KD_DELN * n1 + k], c_t = a.kdbl[KD_DELN_T * n1 + k];
+  // ---- delp (:919-920) -> mass fluxes
+  stage_inputs(L, G, S.t, T, a.crx, a.cry, a.xfx, a.yfx);
+  stage_q(L, S.t, T, a.delp);
+  tp_compute<MDP>(L, G, S.t, T, nullptr, nullptr, in_dp, a.hord_dp);
+  const double dp = S.t.qx[cr_ + 3][cc_ + 3];
+  const double ra = __ldg(G.rarea + co);
+  {
+    const bool damp = a.dpx && c_dp != 0.;
+    TPT_LOOP(TY * (TX + 1), TX + 1, r, c) {
+      const int i = T.i0 + c, j = T.j0 + r;
+      const int o = T.idx(min(i, L.ie + 1), min(j, L.je));
+      double m = FX(S.t, r, c) * S.t.xfx[r + 3][c];
+      if (damp) m = m + __ldg(a.dpx + T.ko + o);
+      S.mfx[r][c] = m;
+      if (i <= L.ie + 1 && j <= L.je && (c < TX || lastx)) a.mfx[T.ko + o] = a.mfx[T.ko + o] + m;   // :928-940
+    }
+    TPT_LOOP((TY + 1) * TX, TX, r, c) {
+      const int i = T.i0 + c, j = T.j0 + r;
+      const int o = T.idx(min(i, L.ie), min(j, L.je + 1));
+      double m = FY(S.t, r, c) * S.t.yfx[r][c + 3];
+      if (damp) m = m + __ldg(a.dpy + T.ko + o);
+      S.mfy[r][c] = m;
+      if (i <= L.ie && j <= L.je + 1 && (r < TY || lasty)) a.mfy[T.ko + o] = a.mfy[T.ko + o] + m;
+    }
+  }
+  // ---- w (:984-990, :1262-1270)
+  double dpn = 0.;
+  if (a.w) {
+    __syncthreads();   // every thread has read its delp (qx) and the unweighted fluxes before the next field lands
+    stage_q(L, S.t, T, a.w);
+    tp_compute<MVT>(L, G, S.t, T, nullptr, nullptr, in_vt, a.hord_vt);
+    weight_by_mass(L, S, T, a.delp, nullptr, nullptr, 0.);
+    dpn = dp + (S.mfx[cr_][cc_] - S.mfx[cr_][cc_ + 1] + S.mfy[cr_][cc_] - S.mfy[cr_ + 1][cc_]) * ra;
+    const double wq = dp * S.t.qx[cr_ + 3][cc_ + 3] + (FX(S.t, cr_, cc_) - FX(S.t, cr_, cc_ + 1) + FY(S.t, cr_, cc_) - FY(S.t, cr_ + 1, cc_)) * ra;
+    double wn = wq / dpn;
+    if (a.dw && a.kdbl[KD_DAMP4_W * n1 + k] != 0.) wn = wn + __ldg(a.dw + T.ko + co);
+    if (cell_ok) a.w_o[T.ko + co] = wn;
+  } else {
+    __syncthreads();   // mass fluxes visible
+    dpn = dp + (S.mfx[cr_][cc_] - S.mfx[cr_][cc_ + 1] + S.mfy[cr_][cc_] - S.mfy[cr_ + 1][cc_]) * ra;
+  }
+  // ---- q_con (:992-1000, :1272-1283)
+  if (a.qcon) {
+    __syncthreads();   // epilogue reads of FX/FY/qx done before the next field overwrites them
+    stage_q(L, S.t, T, a.qcon);
+    tp_compute<MDP>(L, G, S.t, T, nullptr, nullptr, in_dp, a.hord_dp);
+    const bool damp = a.qcx && c_t != 0.;
+    weight_by_mass(L, S, T, a.delp, damp ? a.qcx : nullptr, damp ? a.qcy : nullptr, c_t);
+    const double qq = dp * S.t.qx[cr_ + 3][cc_ + 3] + (FX(S.t, cr_, cc_) - FX(S.t, cr_, cc_ + 1) + FY(S.t, cr_, cc_) - FY(S.t, cr_ + 1, cc_)) * ra;
+    if (cell_ok) a.qcon_o[T.ko + co] = qq / dpn;
+  }
+  // ---- pt (:1014-1016, :1053-1066)
+  __syncthreads();
+  stage_q(L, S.t, T, a.pt);
+  tp_compute<MTM>(L, G, S.t, T, nullptr, nullptr, in_tm, a.hord_tm);
+  {
+    const bool damp = a.ptx && c_t != 0.;
+    weight_by_mass(L, S, T, a.delp, damp ? a.ptx : nullptr, damp ? a.pty : nullptr, c_t);
+    const double pq = S.t.qx[cr_ + 3][cc_ + 3] * dp + (FX(S.t, cr_, cc_) - FX(S.t, cr_, cc_ + 1) + FY(S.t, cr_, cc_) - FY(S.t, cr_ + 1, cc_)) * ra;
+    if (cell_ok) {
+      a.delp_o[T.ko + co] = dpn;
+      a.pt_o[T.ko + co] = pq / dpn;
+    }
+  }
+}
+
+// vorticity transport + momentum update (sw_core.F90:1476-1509): u += ke(i)-ke(i+1) + fy, v += ke(j)-ke(j+1) - fx
+template <bool MVT>
+__global__ void __launch_bounds__(tpt::NT, 2) k_dsw_vort_uv(Lay L, DevGrid G, const double* __restrict__ vq, const double* __restrict__ crx,
+                                                          const double* __restrict__ cry, const double* __restrict__ xfx,
+                                                          const double* __restrict__ yfx, const double* __restrict__ u,
+                                                          const double* __restrict__ v, const double* __restrict__ ke,
+                                                          double* __restrict__ uo, double* __restrict__ vo, int hord_vt) {
+  using namespace tpt;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  const Tile T = make_tile(L);
+  stage_inputs(L, G, S, T, crx, cry, xfx, yfx);
+  stage_q(L, S, T, vq);
+  tp_compute<MVT>(L, G, S, T, nullptr, nullptr, (hord_vt == 10) ? 8 : hord_vt, hord_vt);
+  const bool lastx = T.i0 + TX > L.ie, lasty = T.j0 + TY > L.je;
+  u += T.ko; v += T.ko; ke += T.ko; uo += T.ko; vo += T.ko;
+  TPT_LOOP(TY * (TX + 1), TX + 1, r, c) {   // v (is:ie+1, js:je)
+    const int i = T.i0 + c, j = T.j0 + r;
+    if (i <= L.ie + 1 && j <= L.je && (c < TX || lastx)) {
+      const int o = T.idx(i, j);
+      const double fx = FX(S, r, c) * S.xfx[r + 3][c];
+      vo[o] = __ldg(v + o) * __ldg(G.dy + o) + __ldg(ke + o) - __ldg(ke + o + T.NI) - fx;
+    }
+  }
+  TPT_LOOP((TY + 1) * TX, TX, r, c) {       // u (is:ie, js:je+1)
+    const int i = T.i0 + c, j = T.j0 + r;
+    if (i <= L.ie && j <= L.je + 1 && (r < TY || lasty)) {
+      const int o = T.idx(i, j);
+      const double fy = FY(S, r, c) * S.yfx[r][c + 3];
+      uo[o] = __ldg(u + o) * __ldg(G.dx + o) + __ldg(ke + o) - __ldg(ke + o + 1) + fy;
+    }
+  }
+}
+
+// the fused kernels write the computational domain only: copy the halo frame so a frozen halo stays frozen
+struct FrameJob { const double* src; double* dst; int i1, j1; };   // computed box is (is:i1, js:j1), array box (isd:i1+ng', ...)
+struct FrameJobs { FrameJob j[6]; int n; };
+__global__ void __launch_bounds__(TI* TJ) k_copy_frame(Lay L, FrameJobs jobs) {
+  PLANE_IJK
+  if (i < L.isd || i > L.ied + 1 || j > L.jed + 1) return;
+  const long long o = ko + LIDX(L, i, j);
+  for (int n = 0; n < jobs.n; n++) {
+    const FrameJob& f = jobs.j[n];
+    const int ihi = f.i1 + (L.ied - L.ie), jhi = f.j1 + (L.jed - L.je);   // array extents incl. halo
+    if (i > ihi || j > jhi) continue;
+    if (i >= L.is && i <= f.i1 && j >= L.js && j <= f.j1) continue;
+    f.dst[o] = __ldg(f.src + o);
+  }
+}
+
+template <bool A, bool B, bool C>
+static int launch_transport_t(fv3_ctx* c, const DswTr& a, int nk) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport<A, B, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DswSmem)));
+    attr_set = true;
+  }
+  k_dsw_transport<A, B, C><<<tpt::tile_grid(c->L, nk), tpt::NT, sizeof(DswSmem), c->stream>>>(c->L, c->G, a);
+  c->launches++;
+  return 0;
+}
+static int launch_transport(fv3_ctx* c, const DswTr& a, int nk) {
+  const int key = (a.hord_dp >= 8 ? 4 : 0) | (a.hord_vt >= 8 ? 2 : 0) | (a.hord_tm >= 8 ? 1 : 0);
+  switch (key) {
+    case 0: return launch_transport_t<false, false, false>(c, a, nk);
+    case 1: return launch_transport_t<false, false, true>(c, a, nk);
+    case 2: return launch_transport_t<false, true, false>(c, a, nk);
+    case 3: return launch_transport_t<false, true, true>(c, a, nk);
+    case 4: return launch_transport_t<true, false, false>(c, a, nk);
+    case 5: return launch_transport_t<true, false, true>(c, a, nk);
+    case 6: return launch_transport_t<true, true, false>(c, a, nk);
+    default: return launch_transport_t<true, true, true>(c, a, nk);
+  }
+}
+template <bool M>
+static int launch_vort_uv_t(fv3_ctx* c, const double* vq, const double* u, const double* v, const double* ke, double* uo, double* vo, int nk) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_vort_uv<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    attr_set = true;
+  }
+  k_dsw_vort_uv<M><<<tpt::tile_grid(c->L, nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(
+      c->L, c->G, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, c->f.hord_vt);
+  c->launches++;
+  return 0;
+}
+
 int stage_d_sw(fv3_ctx* c, double dt) {
   StageScope ts(c, "D_SW");
   const Lay& L = c->L;
@@ -651,70 +868,58 @@ int stage_d_sw(fv3_ctx* c, double dt) {
   k_dsw_wind<<<grd, blk, 0, st>>>(L, c->G, uc, vc, uts, vts, crx, cry, xfx, yfx, c->fld[FV3_CX], c->fld[FV3_CY], dt);
   c->launches++;
 
-  Tp2d tp;
-  tp.crx = crx; tp.cry = cry; tp.xfx = xfx; tp.yfx = yfx; tp.ra_x = nullptr; tp.ra_y = nullptr;
-  tp.nk = nk; tp.fx2 = fx2; tp.fy2 = fy2; tp.q_i = q_i; tp.q_j = q_j;
-  // --- delp (:919-920)
-  tp.q = delp; tp.fx = fx; tp.fy = fy; tp.mfx = nullptr; tp.mfy = nullptr; tp.hord = f.hord_dp;
-  int rc = launch_tp2d(c, tp); if (rc) return rc;
+  // --- del-n damping fluxes of delp, w, q_con, pt (wide stencils: separate launches), then ONE fused transport
   Deln dl;
-  dl.fx2 = dfx; dl.fy2 = dfy; dl.d2 = d2; dl.nk = nk; dl.thresh = 0; dl.nord_const = 0; dl.damp_const = 0;
-  if (any_deln) {
-    dl.q = delp; dl.slot_nord = KI_NORD_V; dl.slot_damp = KD_DELN; dl.premul = 1;
-    launch_deln(c, dl);
-    launch_deln_add(c, fx, fy, dfx, dfy, nullptr, KD_DELN, 0., nk);
-  }
-  // --- w (:950-990)
+  dl.d2 = d2; dl.nk = nk; dl.thresh = 0; dl.nord_const = 0; dl.damp_const = 0;
   const bool nonhydro = !f.hydrostatic;
-  if (nonhydro) {
+  DswTr tr{};
+  tr.delp = delp; tr.pt = pt; tr.w = nonhydro ? w : nullptr; tr.qcon = f.use_cond ? c->fld[FV3_QCON] : nullptr;
+  tr.crx = crx; tr.cry = cry; tr.xfx = xfx; tr.yfx = yfx;
+  tr.delp_o = c->alt_delp; tr.pt_o = c->alt_pt; tr.w_o = c->alt_w; tr.qcon_o = c->alt_qcon;
+  tr.mfx = c->fld[FV3_MFX]; tr.mfy = c->fld[FV3_MFY]; tr.kdbl = c->d_kdbl;
+  tr.hord_dp = f.hord_dp; tr.hord_vt = f.hord_vt; tr.hord_tm = f.hord_tm;
+  if (any_deln) {   // delp (:919-920)
+    dl.q = delp; dl.fx2 = dfx; dl.fy2 = dfy; dl.slot_nord = KI_NORD_V; dl.slot_damp = KD_DELN; dl.premul = 1;
+    launch_deln(c, dl);
+    tr.dpx = dfx; tr.dpy = dfy;
+  }
+  if (nonhydro) {   // w (:950-990)
     if (any_w) {
-      dl.q = w; dl.slot_nord = KI_NORD_W; dl.slot_damp = KD_DAMP4_W; dl.premul = 1;
+      dl.q = w; dl.fx2 = fx2; dl.fy2 = fy2; dl.slot_nord = KI_NORD_W; dl.slot_damp = KD_DAMP4_W; dl.premul = 1;
       launch_deln(c, dl);
+      tr.dw = dw;
     }
-    k_dsw_dw<<<grd, blk, 0, st>>>(L, c->G, w, dfx, dfy, dw, hs, ds, c->d_kdbl, f.ke_bg, dt, f.prevent_diss_cooling, f.do_diss_est);
-    c->launches++;
-    tp.q = w; tp.fx = gx; tp.fy = gy; tp.mfx = fx; tp.mfy = fy; tp.hord = f.hord_vt;
-    rc = launch_tp2d(c, tp); if (rc) return rc;
-    k_dsw_qdp<<<grd, blk, 0, st>>>(L, c->G, w, delp, gx, gy, c->alt_w);
+    k_dsw_dw<<<grd, blk, 0, st>>>(L, c->G, w, fx2, fy2, dw, hs, ds, c->d_kdbl, f.ke_bg, dt, f.prevent_diss_cooling, f.do_diss_est);
     c->launches++;
   } else {
     FV3_CUDA(c, cudaMemsetAsync(hs, 0, (size_t)L.plane * nk * sizeof(double), st));
     FV3_CUDA(c, cudaMemsetAsync(ds, 0, (size_t)L.plane * nk * sizeof(double), st));
   }
-  // --- q_con (:992-1000)
-  if (f.use_cond) {
-    tp.q = c->fld[FV3_QCON]; tp.fx = gx; tp.fy = gy; tp.mfx = fx; tp.mfy = fy; tp.hord = f.hord_dp;
-    rc = launch_tp2d(c, tp); if (rc) return rc;
-    if (any_deln_t) {
-      dl.q = c->fld[FV3_QCON]; dl.slot_nord = KI_NORD_T; dl.slot_damp = KD_DELN_T; dl.premul = 0;
-      launch_deln(c, dl);
-      launch_deln_add(c, gx, gy, dfx, dfy, delp, KD_DELN_T, 0., nk);
-    }
-    k_dsw_qdp<<<grd, blk, 0, st>>>(L, c->G, c->fld[FV3_QCON], delp, gx, gy, c->alt_qcon);
-    c->launches++;
-  }
-  // --- pt (:1014-1016) and the delp/pt update (:1053-1066)
-  tp.q = pt; tp.fx = gx; tp.fy = gy; tp.mfx = fx; tp.mfy = fy; tp.hord = f.hord_tm;
-  rc = launch_tp2d(c, tp); if (rc) return rc;
-  if (any_deln_t) {
-    dl.q = pt; dl.slot_nord = KI_NORD_T; dl.slot_damp = KD_DELN_T; dl.premul = 0;
+  if (f.use_cond && any_deln_t) {   // q_con (:992-1000)
+    dl.q = c->fld[FV3_QCON]; dl.fx2 = q_i; dl.fy2 = q_j; dl.slot_nord = KI_NORD_T; dl.slot_damp = KD_DELN_T; dl.premul = 0;
     launch_deln(c, dl);
-    launch_deln_add(c, gx, gy, dfx, dfy, delp, KD_DELN_T, 0., nk);
+    tr.qcx = q_i; tr.qcy = q_j;
   }
-  k_dsw_ptdp<<<grd, blk, 0, st>>>(L, c->G, pt, delp, fx, fy, gx, gy, c->alt_pt, c->alt_delp, c->fld[FV3_MFX], c->fld[FV3_MFY]);
-  c->launches++;
+  if (any_deln_t) {   // pt (:1014-1016)
+    dl.q = pt; dl.fx2 = fx; dl.fy2 = fy; dl.slot_nord = KI_NORD_T; dl.slot_damp = KD_DELN_T; dl.premul = 0;
+    launch_deln(c, dl);
+    tr.ptx = fx; tr.pty = fy;
+  }
+  int rc = launch_transport(c, tr, nk); if (rc) return rc;
+  {
+    FrameJobs fj{}; int n = 0;
+    fj.j[n++] = FrameJob{delp, c->alt_delp, L.ie, L.je};
+    fj.j[n++] = FrameJob{pt, c->alt_pt, L.ie, L.je};
+    if (nonhydro) fj.j[n++] = FrameJob{w, c->alt_w, L.ie, L.je};
+    if (f.use_cond) fj.j[n++] = FrameJob{c->fld[FV3_QCON], c->alt_qcon, L.ie, L.je};
+    fj.n = n;
+    k_copy_frame<<<grd, blk, 0, st>>>(L, fj);
+    c->launches++;
+  }
   std::swap(c->fld[FV3_DELP], c->alt_delp); std::swap(c->fld[FV3_PT], c->alt_pt);
+  if (nonhydro) std::swap(c->fld[FV3_W], c->alt_w);
+  if (f.use_cond) std::swap(c->fld[FV3_QCON], c->alt_qcon);
   double* delp_new = c->fld[FV3_DELP];
-  if (nonhydro) {
-    k_dsw_wfin<<<grd, blk, 0, st>>>(L, c->alt_w, delp_new, dw, c->d_kdbl, any_w ? 1 : 0);
-    c->launches++;
-    std::swap(c->fld[FV3_W], c->alt_w);
-  }
-  if (f.use_cond) {
-    k_dsw_wfin<<<grd, blk, 0, st>>>(L, c->alt_qcon, delp_new, dw, c->d_kdbl, 0);
-    c->launches++;
-    std::swap(c->fld[FV3_QCON], c->alt_qcon);
-  }
   // --- KE (:1078-1228); ke lives in fx2's plane from here (tp scratch is rewritten later, so use gx)
   double* ke = gx;      // B-grid (is:ie+1, js:je+1)
   k_dsw_ke<<<grd, blk, 0, st>>>(L, c->G, u, v, uc, vc, uts, vts, ke, dt, f.hord_mt);
@@ -738,15 +943,21 @@ int stage_d_sw(fv3_ctx* c, double dt) {
   k_dsw_damp<<<grd, blk, 0, st>>>(L, c->G, u, v, c->fld[FV3_UA], c->fld[FV3_VA], uc, vc, c->fld[FV3_DIVGD], dg, vortb, ke, dterm,
                                   c->d_kint, c->d_kdbl, dt, f.dddmp, f.d4_bg, c->b.stretched_grid);
   c->launches++;
-  // --- vorticity transport and momentum update (:1476-1509)
-  tp.q = vq; tp.fx = fx; tp.fy = fy; tp.mfx = nullptr; tp.mfy = nullptr; tp.hord = f.hord_vt;
-  tp.q_i = gy; tp.q_j = q_j;   // q_i's plane holds dterm
-  rc = launch_tp2d(c, tp); if (rc) return rc;
-  k_dsw_uv<<<grd, blk, 0, st>>>(L, c->G, u, v, ke, fx, fy, c->alt_u, c->alt_v);
-  c->launches++;
+  // --- vorticity transport and momentum update (:1476-1509), fused
+  rc = (f.hord_vt >= 8) ? launch_vort_uv_t<true>(c, vq, u, v, ke, c->alt_u, c->alt_v, nk)
+                        : launch_vort_uv_t<false>(c, vq, u, v, ke, c->alt_u, c->alt_v, nk);
+  if (rc) return rc;
+  {
+    FrameJobs fj{};
+    fj.j[0] = FrameJob{u, c->alt_u, L.ie, L.je + 1};
+    fj.j[1] = FrameJob{v, c->alt_v, L.ie + 1, L.je};
+    fj.n = 2;
+    k_copy_frame<<<grd, blk, 0, st>>>(L, fj);
+    c->launches++;
+  }
   // --- vorticity damping + dissipative heating (:1513-1600)
   if (any_v) {
-    dl.q = wk; dl.slot_nord = KI_NORD_V; dl.slot_damp = KD_DAMP4_V; dl.premul = 1;
+    dl.q = wk; dl.fx2 = dfx; dl.fy2 = dfy; dl.slot_nord = KI_NORD_V; dl.slot_damp = KD_DAMP4_V; dl.premul = 1;
     launch_deln(c, dl);   // dfx = "ut", dfy = "vt"
   }
   if (f.d_con > 1.e-5 || f.do_diss_est) {

@@ -18,8 +18,12 @@
 namespace ppm {
 
 __device__ __forceinline__ double fsign(double a, double b) { return copysign(fabs(a), b); }
-__device__ __forceinline__ double min3(double a, double b, double c) { return fmin(fmin(a, b), c); }
-__device__ __forceinline__ double max3(double a, double b, double c) { return fmax(fmax(a, b), c); }
+// compare-and-select min/max: 3 instructions (DSETP + 2 SEL) where fmin/fmax cost 6-7 on sm_100a because of their
+// NaN-quieting fix-up (seen in the SASS); the path never sees NaNs and +-0 order is irrelevant to the limiters
+__device__ __forceinline__ double mn(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double mx(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double min3(double a, double b, double c) { return mn(mn(a, b), c); }
+__device__ __forceinline__ double max3(double a, double b, double c) { return mx(mx(a, b), c); }
 
 // tp_core.F90:35-70
 constexpr double r3 = 1. / 3.;
@@ -75,7 +79,7 @@ template <class Q>
 __device__ __forceinline__ double dm_at(const Q& q, int i) {  // tp_core.F90:570-574
   const double qm = q(i - 1), q0 = q(i), qp = q(i + 1);
   const double xt = 0.25 * (qp - qm);
-  return fsign(fmin(fmin(fabs(xt), max3(qm, q0, qp) - q0), q0 - min3(qm, q0, qp)), xt);
+  return fsign(mn(mn(fabs(xt), max3(qm, q0, qp) - q0), q0 - min3(qm, q0, qp)), xt);
 }
 
 __device__ __forceinline__ void pert_std(double& al, double& ar) {  // pert_ppm iv/=0, tp_core.F90:1245-1261
@@ -105,17 +109,17 @@ __device__ __forceinline__ void cell_mono(const Q& q, const D& dxa, int i, int i
     const double al1 = 0.5 * (q0 + qp1) + r3 * (dm0 - dmp);
     if (iord == 8) {
       const double xt = 2. * dm0;
-      bl = -fsign(fmin(fabs(xt), fabs(al0 - q0)), xt);
-      br = fsign(fmin(fabs(xt), fabs(al1 - q0)), xt);
+      bl = -fsign(mn(fabs(xt), fabs(al0 - q0)), xt);
+      br = fsign(mn(fabs(xt), fabs(al1 - q0)), xt);
     } else {  // 10
       bl = al0 - q0; br = al1 - q0;
       if (fabs(dmm) + fabs(dm0) + fabs(dmp) < near_zero_tp) { bl = 0.; br = 0.; }
       else if (fabs(3. * (bl + br)) > fabs(bl - br)) {
         const double dqm2 = 2. * (qm1 - q(i - 2)), dqm1 = 2. * (q0 - qm1), dq0 = 2. * (qp1 - q0), dqp1 = 2. * (q(i + 2) - qp1);
         const double pmp_2 = dqm1, lac_2 = pmp_2 - 0.75 * dqm2;
-        br = fmin(max3(0., pmp_2, lac_2), fmax(br, min3(0., pmp_2, lac_2)));
+        br = mn(max3(0., pmp_2, lac_2), mx(br, min3(0., pmp_2, lac_2)));
         const double pmp_1 = -dq0, lac_1 = pmp_1 + 0.75 * dqp1;
-        bl = fmin(max3(0., pmp_1, lac_1), fmax(bl, min3(0., pmp_1, lac_1)));
+        bl = mn(max3(0., pmp_1, lac_1), mx(bl, min3(0., pmp_1, lac_1)));
       }
     }
     return;
@@ -124,8 +128,8 @@ __device__ __forceinline__ void cell_mono(const Q& q, const D& dxa, int i, int i
   if (i <= 1) {  // cells 0 and 1 share the clamped two-sided edge value
     double xt = edge_avg(q, dxa, 1);
     const double qa = q(-1), qb = q(0), qc = q(1), qd = q(2);
-    xt = fmax(xt, fmin(fmin(qa, qb), fmin(qc, qd)));
-    xt = fmin(xt, fmax(fmax(qa, qb), fmax(qc, qd)));
+    xt = mx(xt, mn(mn(qa, qb), mn(qc, qd)));
+    xt = mn(xt, mx(mx(qa, qb), mx(qc, qd)));
     if (i == 0) { bl = s14 * dm_at(q, -1) + s11 * (qa - qb); br = xt - qb; }
     else { bl = xt - qc; br = (s15 * qc + s11 * qd - s14 * dm_at(q, 2)) - qc; }
   } else if (i == 2) {
@@ -141,8 +145,8 @@ __device__ __forceinline__ void cell_mono(const Q& q, const D& dxa, int i, int i
   } else {  // n-1, n
     double xt = edge_avg(q, dxa, n);
     const double qa = q(n - 2), qb = q(n - 1), qc = q(n), qd = q(n + 1);
-    xt = fmax(xt, fmin(fmin(qa, qb), fmin(qc, qd)));
-    xt = fmin(xt, fmax(fmax(qa, qb), fmax(qc, qd)));
+    xt = mx(xt, mn(mn(qa, qb), mn(qc, qd)));
+    xt = mn(xt, mx(mx(qa, qb), mx(qc, qd)));
     if (i == n - 1) { bl = (s15 * qb + s11 * qa + s14 * dm_at(q, n - 2)) - qb; br = xt - qb; }
     else { bl = xt - qc; br = s11 * (qd - qc) - s14 * dm_at(q, n + 1); }
   }
@@ -160,7 +164,7 @@ __device__ __forceinline__ double al_unlim(const Q& q, const D& dxa, int i, int 
   else if (i == n - 1) al = c1 * q(n - 3) + c2 * q(n - 2) + c3 * q(n - 1);
   else if (i == n) al = edge_avg(q, dxa, n);
   else al = c3 * q(n) + c2 * q(n + 1) + c1 * q(n + 2);  // n+1
-  if (iord < 0) al = fmax(0., al);
+  if (iord < 0) al = mx(0., al);
   return al;
 }
 
@@ -222,9 +226,9 @@ __device__ __forceinline__ void cell_wind_mono(const Q& u, const D& dx, int i, i
     const double dmm = dm_at(u, i - 1), dm0 = dm_at(u, i), dmp = dm_at(u, i + 1);
     const double al0 = 0.5 * (um1 + u0) + r3 * (dmm - dm0), al1 = 0.5 * (u0 + up1) + r3 * (dm0 - dmp);
     double pmp = -2. * (up1 - u0), lac = pmp + 1.5 * (u(i + 2) - up1);
-    bl = fmin(max3(0., pmp, lac), fmax(al0 - u0, min3(0., pmp, lac)));
+    bl = mn(max3(0., pmp, lac), mx(al0 - u0, min3(0., pmp, lac)));
     pmp = 2. * (u0 - um1); lac = pmp - 1.5 * (um1 - u(i - 2));
-    br = fmin(max3(0., pmp, lac), fmax(al1 - u0, min3(0., pmp, lac)));
+    br = mn(max3(0., pmp, lac), mx(al1 - u0, min3(0., pmp, lac)));
     return;
   }
   if (i >= 3 && i <= n - 3) {
@@ -233,8 +237,8 @@ __device__ __forceinline__ void cell_wind_mono(const Q& u, const D& dx, int i, i
     const double al0 = 0.5 * (um1 + u0) + r3 * (dmm - dm0), al1 = 0.5 * (u0 + up1) + r3 * (dm0 - dmp);
     if (iord == 8) {
       const double xt = 2. * dm0;
-      bl = -fsign(fmin(fabs(xt), fabs(al0 - u0)), xt);
-      br = fsign(fmin(fabs(xt), fabs(al1 - u0)), xt);
+      bl = -fsign(mn(fabs(xt), fabs(al0 - u0)), xt);
+      br = fsign(mn(fabs(xt), fabs(al1 - u0)), xt);
     } else {  // 10, sw_core.F90:2414-2433
       bl = al0 - u0; br = al1 - u0;
       if (fabs(dm0) < near_zero_sw) {
@@ -242,9 +246,9 @@ __device__ __forceinline__ void cell_wind_mono(const Q& u, const D& dx, int i, i
       } else if (fabs(3. * (bl + br)) > fabs(bl - br)) {
         const double dq0 = up1 - u0, dqp1 = u(i + 2) - up1, dqm1 = u0 - um1, dqm2 = um1 - u(i - 2);
         const double pmp_1 = -2. * dq0, lac_1 = pmp_1 + 1.5 * dqp1;
-        bl = fmin(max3(0., pmp_1, lac_1), fmax(bl, min3(0., pmp_1, lac_1)));
+        bl = mn(max3(0., pmp_1, lac_1), mx(bl, min3(0., pmp_1, lac_1)));
         const double pmp_2 = 2. * dqm1, lac_2 = pmp_2 - 1.5 * dqm2;
-        br = fmin(max3(0., pmp_2, lac_2), fmax(br, min3(0., pmp_2, lac_2)));
+        br = mn(max3(0., pmp_2, lac_2), mx(br, min3(0., pmp_2, lac_2)));
       }
     }
     return;
@@ -342,11 +346,11 @@ __device__ __forceinline__ double flux_wind(const Q& u, const D& dx, const D& rd
 // identical to cell_mono / cell_unlim / cell_wind_* above (the parity tests compare both).
 __device__ __forceinline__ double dm3(double qm, double q0, double qp) {
   const double xt = 0.25 * (qp - qm);
-  return fsign(fmin(fmin(fabs(xt), max3(qm, q0, qp) - q0), q0 - min3(qm, q0, qp)), xt);
+  return fsign(mn(mn(fabs(xt), max3(qm, q0, qp) - q0), q0 - min3(qm, q0, qp)), xt);
 }
 
-__device__ __forceinline__ double flux_scalar_fast(const double* __restrict__ p, int s, double c, int iord) {
-  const double a0 = __ldg(p - 3 * s), a1 = __ldg(p - 2 * s), a2 = __ldg(p - s), a3 = __ldg(p), a4 = __ldg(p + s), a5 = __ldg(p + 2 * s);
+// the operator on an explicit window a0..a5 = q(i-3..i+2) (registers; the caller loads from global or shared memory)
+__device__ __forceinline__ double flux_scalar_win(double a0, double a1, double a2, double a3, double a4, double a5, double c, int iord) {
   if (iord >= 8) {
     const bool up = c > 0.;
     const double qm2 = up ? a0 : a1, qm1 = up ? a1 : a2, q0 = up ? a2 : a3, qp1 = up ? a3 : a4, qp2 = up ? a4 : a5;
@@ -356,17 +360,17 @@ __device__ __forceinline__ double flux_scalar_fast(const double* __restrict__ p,
     double bl, br;
     if (iord == 8) {
       const double xt = 2. * dm0;
-      bl = -fsign(fmin(fabs(xt), fabs(al0 - q0)), xt);
-      br = fsign(fmin(fabs(xt), fabs(al1 - q0)), xt);
+      bl = -fsign(mn(fabs(xt), fabs(al0 - q0)), xt);
+      br = fsign(mn(fabs(xt), fabs(al1 - q0)), xt);
     } else {
       bl = al0 - q0; br = al1 - q0;
       if (fabs(dmm) + fabs(dm0) + fabs(dmp) < near_zero_tp) { bl = 0.; br = 0.; }
       else if (fabs(3. * (bl + br)) > fabs(bl - br)) {
         const double dqm2 = 2. * (qm1 - qm2), dqm1 = 2. * (q0 - qm1), dq0 = 2. * (qp1 - q0), dqp1 = 2. * (qp2 - qp1);
         const double pmp_2 = dqm1, lac_2 = pmp_2 - 0.75 * dqm2;
-        br = fmin(max3(0., pmp_2, lac_2), fmax(br, min3(0., pmp_2, lac_2)));
+        br = mn(max3(0., pmp_2, lac_2), mx(br, min3(0., pmp_2, lac_2)));
         const double pmp_1 = -dq0, lac_1 = pmp_1 + 0.75 * dqp1;
-        bl = fmin(max3(0., pmp_1, lac_1), fmax(bl, min3(0., pmp_1, lac_1)));
+        bl = mn(max3(0., pmp_1, lac_1), mx(bl, min3(0., pmp_1, lac_1)));
       }
     }
     return up ? q0 + (1. - c) * (br - c * (bl + br)) : q0 + (1. + c) * (bl + c * (bl + br));
@@ -374,7 +378,7 @@ __device__ __forceinline__ double flux_scalar_fast(const double* __restrict__ p,
   double alm = p1 * (a1 + a2) + p2 * (a0 + a3);
   double al0 = p1 * (a2 + a3) + p2 * (a1 + a4);
   double alp = p1 * (a3 + a4) + p2 * (a2 + a5);
-  if (iord < 0) { alm = fmax(0., alm); al0 = fmax(0., al0); alp = fmax(0., alp); }
+  if (iord < 0) { alm = mx(0., alm); al0 = mx(0., al0); alp = mx(0., alp); }
   auto cell = [&](double q0, double l, double r) {
     CellU cu; cu.bl = l - q0; cu.br = r - q0; cu.b0 = cu.bl + cu.br;
     if (iord == 5) cu.smt = cu.bl * cu.br < 0.;
@@ -399,6 +403,10 @@ __device__ __forceinline__ double flux_scalar_fast(const double* __restrict__ p,
   return fl;
 }
 
+__device__ __forceinline__ double flux_scalar_fast(const double* __restrict__ p, int s, double c, int iord) {
+  return flux_scalar_win(__ldg(p - 3 * s), __ldg(p - 2 * s), __ldg(p - s), __ldg(p), __ldg(p + s), __ldg(p + 2 * s), c, iord);
+}
+
 // winds: c is a distance; rm, r0 = rdx of cells i-1 and i
 __device__ __forceinline__ double flux_wind_fast(const double* __restrict__ p, int s, double c, double rm, double r0, int iord) {
   const double a0 = __ldg(p - 3 * s), a1 = __ldg(p - 2 * s), a2 = __ldg(p - s), a3 = __ldg(p), a4 = __ldg(p + s), a5 = __ldg(p + 2 * s);
@@ -410,8 +418,8 @@ __device__ __forceinline__ double flux_wind_fast(const double* __restrict__ p, i
     double bl, br;
     if (iord == 8) {
       const double xt = 2. * dm0;
-      bl = -fsign(fmin(fabs(xt), fabs(al0 - u0)), xt);
-      br = fsign(fmin(fabs(xt), fabs(al1 - u0)), xt);
+      bl = -fsign(mn(fabs(xt), fabs(al0 - u0)), xt);
+      br = fsign(mn(fabs(xt), fabs(al1 - u0)), xt);
     } else {
       bl = al0 - u0; br = al1 - u0;
       if (fabs(dm0) < near_zero_sw) {
@@ -419,9 +427,9 @@ __device__ __forceinline__ double flux_wind_fast(const double* __restrict__ p, i
       } else if (fabs(3. * (bl + br)) > fabs(bl - br)) {
         const double dq0 = up1 - u0, dqp1 = up2 - up1, dqm1 = u0 - um1, dqm2 = um1 - um2;
         const double pmp_1 = -2. * dq0, lac_1 = pmp_1 + 1.5 * dqp1;
-        bl = fmin(max3(0., pmp_1, lac_1), fmax(bl, min3(0., pmp_1, lac_1)));
+        bl = mn(max3(0., pmp_1, lac_1), mx(bl, min3(0., pmp_1, lac_1)));
         const double pmp_2 = 2. * dqm1, lac_2 = pmp_2 - 1.5 * dqm2;
-        br = fmin(max3(0., pmp_2, lac_2), fmax(br, min3(0., pmp_2, lac_2)));
+        br = mn(max3(0., pmp_2, lac_2), mx(br, min3(0., pmp_2, lac_2)));
       }
     }
     const double cfl = c * (up ? rm : r0);
@@ -439,6 +447,75 @@ __device__ __forceinline__ double flux_wind_fast(const double* __restrict__ p, i
   if (c > 0.) { const double cfl = c * rm; fx0 = (1. - cfl) * (Abr - cfl * Ab0); fl = a2; }
   else { const double cfl = c * r0; fx0 = (1. + cfl) * (Bbl + cfl * Bb0); fl = a3; }
   if (As || Bs) fl = fl + fx0;
+  return fl;
+}
+
+// ------------------------------------------------------------------ two-pass form for shared-memory tiles
+// Pass 1 stores one auxiliary value per point of a line, pass 2 evaluates the flux from it:
+//   monotone family (8, 10):  aux(c) = dm of cell c                      (tp_core.F90:570-574)
+//   unlimited family (5,6,-5): aux(c) = al at the low-side face of cell c (tp_core.F90:369-373)
+// so the limiter / edge value is computed once per point instead of three times per flux.
+// dm2 == dm3 up to the sign of a zero result: max3-q0 and q0-min3 are |q0-qm| and |qp-q0| when the
+// two one-sided differences have the same sign, and one of them is 0 otherwise.
+__device__ __forceinline__ double dm2(double qm, double q0, double qp) {
+  const double a = q0 - qm, b = qp - q0, xt = 0.25 * (qp - qm);
+  const bool same = ((__double2hiint(a) ^ __double2hiint(b)) >= 0);
+  const double m = mn(mn(fabs(xt), fabs(a)), fabs(b));
+  return same ? copysign(m, xt) : 0.;
+}
+template <bool MONO>
+__device__ __forceinline__ double aux_point(int iord, double qm2, double qm1, double q0, double qp1) {
+  if (MONO) return dm2(qm1, q0, qp1);
+  const double al = p1 * (qm1 + q0) + p2 * (qm2 + qp1);
+  return iord < 0 ? mx(0., al) : al;
+}
+// monotone flux from the upwind cell's neighbourhood: q(iu-2..iu+2), dm(iu-1..iu+1)
+__device__ __forceinline__ double flux_mono_aux(double qm2, double qm1, double q0, double qp1, double qp2, double dmm, double dm0,
+                                                double dmp, double c, int iord) {
+  const double al0 = 0.5 * (qm1 + q0) + r3 * (dmm - dm0);
+  const double al1 = 0.5 * (q0 + qp1) + r3 * (dm0 - dmp);
+  double bl, br;
+  if (iord == 8) {
+    const double xt = 2. * dm0;
+    bl = -fsign(mn(fabs(xt), fabs(al0 - q0)), xt);
+    br = fsign(mn(fabs(xt), fabs(al1 - q0)), xt);
+  } else {
+    bl = al0 - q0; br = al1 - q0;
+    if (fabs(dmm) + fabs(dm0) + fabs(dmp) < near_zero_tp) { bl = 0.; br = 0.; }
+    else if (fabs(3. * (bl + br)) > fabs(bl - br)) {
+      const double dqm2 = 2. * (qm1 - qm2), dqm1 = 2. * (q0 - qm1), dq0 = 2. * (qp1 - q0), dqp1 = 2. * (qp2 - qp1);
+      const double pmp_2 = dqm1, lac_2 = pmp_2 - 0.75 * dqm2;
+      br = mn(max3(0., pmp_2, lac_2), mx(br, min3(0., pmp_2, lac_2)));
+      const double pmp_1 = -dq0, lac_1 = pmp_1 + 0.75 * dqp1;
+      bl = mn(max3(0., pmp_1, lac_1), mx(bl, min3(0., pmp_1, lac_1)));
+    }
+  }
+  return (c > 0.) ? q0 + (1. - c) * (br - c * (bl + br)) : q0 + (1. + c) * (bl + c * (bl + br));
+}
+// unlimited-family flux through the face between cells A (low side, value qa) and B (qb); alm, al0, alp = al at the
+// low face of A, the shared face, the high face of B
+__device__ __forceinline__ double flux_unlim_aux(double qa, double qb, double alm, double al0, double alp, double c, int iord) {
+  auto cell = [&](double q0, double l, double r) {
+    CellU cu; cu.bl = l - q0; cu.br = r - q0; cu.b0 = cu.bl + cu.br;
+    if (iord == 5) cu.smt = cu.bl * cu.br < 0.;
+    else if (iord == -5) {
+      cu.smt = cu.bl * cu.br < 0.;
+      const double da1 = cu.br - cu.bl, a4_ = -3. * cu.b0;
+      if (fabs(da1) < -a4_) {
+        if (q0 + 0.25 / a4_ * (da1 * da1) + a4_ * r12 < 0.) {
+          if (!cu.smt) { cu.br = 0.; cu.bl = 0.; cu.b0 = 0.; }
+          else if (da1 > 0.) { cu.br = -2. * cu.bl; cu.b0 = -cu.bl; }
+          else { cu.bl = -2. * cu.br; cu.b0 = -cu.br; }
+        }
+      }
+    } else cu.smt = 3. * fabs(cu.b0) < fabs(cu.bl - cu.br);
+    return cu;
+  };
+  const CellU A = cell(qa, alm, al0), B = cell(qb, al0, alp);
+  double fx1, fl;
+  if (c > 0.) { fx1 = (1. - c) * (A.br - c * A.b0); fl = qa; }
+  else { fx1 = (1. + c) * (B.bl + c * B.b0); fl = qb; }
+  if (A.smt || B.smt) fl = fl + fx1;
   return fl;
 }
 

@@ -3,16 +3,13 @@
 //
 // Reference semantics: model/tp_core.F90:85-241 fv_tp_2d, :245-322 copy_corners,
 // :1267-1447 deln_flux; model/sw_core.F90:1608-1737 del6_vt_flux.
-// Design (not a translation): three launches per transport, one thread per flux point,
-//   1. inner advective-form sweeps  fy2 = yppm(q), fx2 = xppm(q)   (ord_in)
-//   2. q_i, q_j  (the intermediate advected fields, one division each)
-//   3. outer sweeps on q_i / q_j (ord_ou), average with the inner fluxes, weight
-// The cube-corner "copy_corners" transposes are NOT written into q: the inner sweeps read
-// q through a remapping accessor (ppm::QAccX / QAccY), so q stays read-only and corner
-// tiles pay one predicated index swap.  Intermediates are [k][j][i] planes sized for L2
-// residency when the caller chunks k.
+// Design (not a translation): ONE launch per transport; a CTA owns a 32x16 tile of one level and
+// keeps the inner fluxes, q_i and q_j in shared memory (tp_tile.cuh).
+// The cube-corner "copy_corners" transposes are NOT written into q: corner tiles load q
+// through a remapping accessor (ppm::QAccX / QAccY), so q stays read-only.
 #include "tp2d.cuh"
 #include "ppm.cuh"
+#include "tp_tile.cuh"
 
 using namespace ppm;
 
@@ -27,90 +24,37 @@ static inline dim3 plane_grid(const Lay& L, int nk) { return dim3((L.NI + TI - 1
   const int k = blockIdx.z;                                     \
   const long long ko = (long long)k * L.plane;
 
-__global__ void __launch_bounds__(TI* TJ, 4) k_tp_inner(Lay L, DevGrid G, const double* __restrict__ q,
-                                                    const double* __restrict__ crx, const double* __restrict__ cry,
-                                                    double* __restrict__ fx2, double* __restrict__ fy2, int ord_in) {
-  PLANE_IJK
-  if (i < L.isd || i > L.ied + 1 || j > L.jed + 1) return;
-  const bool cube = L.cube;
-  // fy2 (isd:ied, js:je+1): y sweep with the dir=2 corner view  (tp_core.F90:143-148)
-  if (i <= L.ied && j >= L.js && j <= L.je + 1) {
-    const long long o = ko + LIDX(L, i, j);
-    const double c = __ldg(cry + o);
-    if (!cube || (j >= 4 && j <= L.npy - 3)) fy2[o] = flux_scalar_fast(q + o, L.NI, c, ord_in);
-    else {
-      QAccY qa{q + ko, L, i};
-      Acc da{G.dya, LIDX(L, i, 0), L.NI};
-      fy2[o] = flux_scalar(qa, da, j, c, ord_in, L.npy, cube);
+// One CTA per TX x TY tile and level: see tp_tile.cuh.  Epilogue: weight by the area flux (or the
+// mass flux, tp_core.F90:213-226) and store the tile's own faces (+ the face's last column / row).
+template <bool MONO>
+__global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, const double* __restrict__ q,
+                                                       const double* __restrict__ crx, const double* __restrict__ cry,
+                                                       const double* __restrict__ xfx, const double* __restrict__ yfx,
+                                                       const double* __restrict__ ra_x, const double* __restrict__ ra_y,
+                                                       const double* __restrict__ mfx, const double* __restrict__ mfy,
+                                                       double* __restrict__ fx, double* __restrict__ fy, int ord_in, int ord_ou) {
+  using namespace tpt;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  const Tile T = make_tile(L);
+  stage_inputs(L, G, S, T, crx, cry, xfx, yfx);
+  stage_q(L, S, T, q);
+  tp_compute<MONO>(L, G, S, T, ra_x, ra_y, ord_in, ord_ou);
+  const bool lastx = T.i0 + TX > L.ie, lasty = T.j0 + TY > L.je;
+  fx += T.ko; fy += T.ko;
+  TPT_LOOP(TY * (TX + 1), TX + 1, r, c) {
+    const int i = T.i0 + c, j = T.j0 + r;
+    if (i <= L.ie + 1 && j <= L.je && (c < TX || lastx)) {
+      const int o = T.idx(i, j);
+      fx[o] = FX(S, r, c) * (mfx ? __ldg(mfx + T.ko + o) : S.xfx[r + 3][c]);
     }
   }
-  // fx2 (is:ie+1, jsd:jed): x sweep with the dir=1 corner view  (tp_core.F90:164-169)
-  if (i >= L.is && i <= L.ie + 1 && j <= L.jed) {
-    const long long o = ko + LIDX(L, i, j);
-    const double c = __ldg(crx + o);
-    if (!cube || (i >= 4 && i <= L.npx - 3)) fx2[o] = flux_scalar_fast(q + o, 1, c, ord_in);
-    else {
-      QAccX qa{q + ko, L, j};
-      Acc da{G.dxa, LIDX(L, 0, j), 1};
-      fx2[o] = flux_scalar(qa, da, i, c, ord_in, L.npx, cube);
+  TPT_LOOP((TY + 1) * TX, TX, r, c) {
+    const int i = T.i0 + c, j = T.j0 + r;
+    if (i <= L.ie && j <= L.je + 1 && (r < TY || lasty)) {
+      const int o = T.idx(i, j);
+      fy[o] = FY(S, r, c) * (mfy ? __ldg(mfy + T.ko + o) : S.yfx[r][c + 3]);
     }
-  }
-}
-
-__global__ void __launch_bounds__(TI* TJ) k_tp_qiqj(Lay L, DevGrid G, const double* __restrict__ q,
-                                                   const double* __restrict__ xfx, const double* __restrict__ yfx,
-                                                   const double* __restrict__ ra_x, const double* __restrict__ ra_y,
-                                                   const double* __restrict__ fx2, const double* __restrict__ fy2,
-                                                   double* __restrict__ q_i, double* __restrict__ q_j) {
-  PLANE_IJK
-  if (i < L.isd || i > L.ied || j > L.jed) return;
-  const long long o = ko + LIDX(L, i, j);
-  const double qq = __ldg(q + o), ar = __ldg(G.area + LIDX(L, i, j));
-  // q_i (isd:ied, js:je)  tp_core.F90:150-159
-  if (j >= L.js && j <= L.je) {
-    const double y0 = __ldg(yfx + o), y1 = __ldg(yfx + o + L.NI);
-    const double f0 = y0 * __ldg(fy2 + o), f1 = y1 * __ldg(fy2 + o + L.NI);
-    const double ray = ra_y ? __ldg(ra_y + o) : (ar + y0 - y1);
-    q_i[o] = (qq * ar + f0 - f1) / ray;
-  }
-  // q_j (is:ie, jsd:jed)  tp_core.F90:171-178
-  if (i >= L.is && i <= L.ie) {
-    const double x0 = __ldg(xfx + o), x1 = __ldg(xfx + o + 1);
-    const double f0 = x0 * __ldg(fx2 + o), f1 = x1 * __ldg(fx2 + o + 1);
-    const double rax = ra_x ? __ldg(ra_x + o) : (ar + x0 - x1);
-    q_j[o] = (qq * ar + f0 - f1) / rax;
-  }
-}
-
-__global__ void __launch_bounds__(TI* TJ, 4) k_tp_outer(Lay L, DevGrid G, const double* __restrict__ q_i,
-                                                    const double* __restrict__ q_j, const double* __restrict__ crx,
-                                                    const double* __restrict__ cry, const double* __restrict__ fx2,
-                                                    const double* __restrict__ fy2, const double* __restrict__ wx,
-                                                    const double* __restrict__ wy, double* __restrict__ fx,
-                                                    double* __restrict__ fy, int ord_ou) {
-  PLANE_IJK
-  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
-  const bool cube = L.cube;
-  const long long o = ko + LIDX(L, i, j);
-  if (j <= L.je) {  // fx (is:ie+1, js:je)  tp_core.F90:161, :193/:219
-    double f;
-    if (!cube || (i >= 4 && i <= L.npx - 3)) f = flux_scalar_fast(q_i + o, 1, __ldg(crx + o), ord_ou);
-    else {
-      Acc qa{q_i + ko, LIDX(L, 0, j), 1};
-      Acc da{G.dxa, LIDX(L, 0, j), 1};
-      f = flux_scalar(qa, da, i, __ldg(crx + o), ord_ou, L.npx, cube);
-    }
-    fx[o] = 0.5 * (f + __ldg(fx2 + o)) * __ldg(wx + o);
-  }
-  if (i <= L.ie) {  // fy (is:ie, js:je+1)  tp_core.F90:180, :198/:224
-    double f;
-    if (!cube || (j >= 4 && j <= L.npy - 3)) f = flux_scalar_fast(q_j + o, L.NI, __ldg(cry + o), ord_ou);
-    else {
-      Acc qa{q_j + ko, LIDX(L, i, 0), L.NI};
-      Acc da{G.dya, LIDX(L, i, 0), L.NI};
-      f = flux_scalar(qa, da, j, __ldg(cry + o), ord_ou, L.npy, cube);
-    }
-    fy[o] = 0.5 * (f + __ldg(fy2 + o)) * __ldg(wy + o);
   }
 }
 
@@ -118,12 +62,18 @@ int launch_tp2d(fv3_ctx* c, const Tp2d& a) {
   if (!hord_supported(a.hord)) return fv3_fail(c, -2, "fv_tp_2d: hord " + std::to_string(a.hord) + " not supported on the GPU path (supported: 5, 6, -5, 8, 10)");
   const Lay& L = c->L;
   const int ord_in = (a.hord == 10) ? 8 : a.hord;   // tp_core.F90:136-141
-  dim3 blk(TI, TJ), grd = plane_grid(L, a.nk);
-  k_tp_inner<<<grd, blk, 0, c->stream>>>(L, c->G, a.q, a.crx, a.cry, a.fx2, a.fy2, ord_in);
-  k_tp_qiqj<<<grd, blk, 0, c->stream>>>(L, c->G, a.q, a.xfx, a.yfx, a.ra_x, a.ra_y, a.fx2, a.fy2, a.q_i, a.q_j);
-  k_tp_outer<<<grd, blk, 0, c->stream>>>(L, c->G, a.q_i, a.q_j, a.crx, a.cry, a.fx2, a.fy2, a.mfx ? a.mfx : a.xfx,
-                                         a.mfy ? a.mfy : a.yfx, a.fx, a.fy, a.hord);
-  c->launches += 3;
+  const dim3 grd = tpt::tile_grid(L, a.nk);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    attr_set = true;
+  }
+  if (a.hord >= 8)
+    k_tp_fused<true><<<grd, tpt::NT, sizeof(tpt::Smem), c->stream>>>(L, c->G, a.q, a.crx, a.cry, a.xfx, a.yfx, a.ra_x, a.ra_y, a.mfx, a.mfy, a.fx, a.fy, ord_in, a.hord);
+  else
+    k_tp_fused<false><<<grd, tpt::NT, sizeof(tpt::Smem), c->stream>>>(L, c->G, a.q, a.crx, a.cry, a.xfx, a.yfx, a.ra_x, a.ra_y, a.mfx, a.mfy, a.fx, a.fy, ord_in, a.hord);
+  c->launches += 1;
   return 0;
 }
 
