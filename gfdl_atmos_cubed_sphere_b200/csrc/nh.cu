@@ -179,7 +179,8 @@ __device__ __forceinline__ void solve_column(const SolverIn& S, long long o, lon
 }  // namespace
 
 // ---- Riem_Solver_c (nh_utils.F90:323-480) on columns [is-1, ie+1]^2 -------------------------
-__global__ void __launch_bounds__(CB) k_riem_c(Lay L, SolverIn S, const double* __restrict__ hs, double* __restrict__ gz,
+// 8 CTAs x 128 threads per SM: all columns of a C384 face are resident in ONE wave (72-88 registers gave 1.56 waves)
+__global__ void __launch_bounds__(CB, 8) k_riem_c(Lay L, SolverIn S, const double* __restrict__ hs, double* __restrict__ gz,
                                                double* __restrict__ pef, double grav) {
   COL_SETUP(L.is - 1, L.ie + 1, L.js - 1, L.je + 1)
   const int km = S.km;
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(CB) k_riem_c(Lay L, SolverIn S, const double* 
 }
 
 // ---- Riem_Solver3 (nh_core.F90:47-241) on columns [is, ie]x[js, je] -------------------------
-__global__ void __launch_bounds__(CB) k_riem3(Lay L, SolverIn S, const double* __restrict__ zs, double* __restrict__ zh,
+__global__ void __launch_bounds__(CB, 8) k_riem3(Lay L, SolverIn S, const double* __restrict__ zs, double* __restrict__ zh,
                                               double* __restrict__ w, double* __restrict__ delz, double* __restrict__ ppe,
                                               double* __restrict__ pk3, double* __restrict__ pk, double* __restrict__ pe,
                                               double* __restrict__ peln, int last_call, int fp_out, int use_logp) {
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(CB) k_dz_clamp(Lay L, const double* __restrict
 
 // ---- update_dz_d (nh_utils.F90:204-321) -----------------------------------------------------
 // edge_profile (nh_utils.F90:1638-1672, non-uniform branch, limiter = 0) for a pair of fields
-__global__ void __launch_bounds__(CB) k_edge_profile(Lay L, const double* __restrict__ q1, const double* __restrict__ q2,
+__global__ void __launch_bounds__(CB, 8) k_edge_profile(Lay L, const double* __restrict__ q1, const double* __restrict__ q2,
                                                     double* __restrict__ q1e, double* __restrict__ q2e, double* __restrict__ gam,
                                                     const double* __restrict__ dp0, int i0, int i1, int j0, int j1) {
   COL_SETUP(i0, i1, j0, j1)
