@@ -179,7 +179,7 @@ struct VaY {
 }  // namespace
 
 // ---- k_c: uc, ut, vc, vt (+ Courant scaling, sw_core.F90:159-176) and divergence_corner ----
-__global__ void __launch_bounds__(TI* TJ) k_csw_c(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
+__global__ void __launch_bounds__(TI* TJ, 4) k_csw_c(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
                                                  const double* __restrict__ utmp_, const double* __restrict__ vtmp_,
                                                  double* ua_, double* va_,
                                                  double* __restrict__ uc, double* __restrict__ vc, double* __restrict__ ut,

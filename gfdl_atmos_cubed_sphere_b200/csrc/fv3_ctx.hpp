@@ -27,7 +27,9 @@ struct Lay {
 };
 
 #ifdef __CUDACC__
-#define LIDX(L, i, j) ((long long)((i) - (L).isd + FV3_IOFF) + (long long)((j) - (L).jsd) * (L).NI)
+// in-plane index, 32-bit on purpose (a plane is < 2^31 elements; 64-bit index arithmetic was a large share of the
+// integer instructions in every plane kernel); the level offset k*plane is added as long long by the caller
+#define LIDX(L, i, j) (((i) - (L).isd + FV3_IOFF) + ((j) - (L).jsd) * (L).NI)
 #endif
 
 // pointers to the 2-D metric planes on the device
