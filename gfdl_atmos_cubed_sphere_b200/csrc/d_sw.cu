@@ -636,116 +636,118 @@ struct DswTr {
 };
 struct DswSmem {
   tpt::Smem t;
-  double mfx[tpt::TY][tpt::TX + 1];
-  double mfy[tpt::TY + 1][tpt::TX];
+  double mfx[tpt::QH][tpt::QW];   // mass fluxes incl. del-n damping, tile coordinates (west / south face of [r][c])
+  double mfy[tpt::QH][tpt::QW];
 };
+constexpr int CELL_ITERS = (tpt::TY + tpt::NW - 1) / tpt::NW;
 
 // weight the unweighted fluxes of the current field by the mass fluxes (+ mass-weighted del-n flux, tp_core.F90:1390-1445)
 __device__ __forceinline__ void weight_by_mass(const Lay& L, DswSmem& S, const tpt::Tile& T, const double* __restrict__ delp,
                                                const double* __restrict__ dx_, const double* __restrict__ dy_, double coef) {
   using namespace tpt;
-  TPT_LOOP(TY * (TX + 1), TX + 1, r, c) {
-    double g = FX(S.t, r, c) * S.mfx[r][c];
-    if (dx_) {
-      const int o = T.idx(min(T.i0 + c, L.ie + 1), min(T.j0 + r, L.je));
-      g = g + (0.5 * coef) * (__ldg(delp + T.ko + o - 1) + __ldg(delp + T.ko + o)) * __ldg(dx_ + T.ko + o);
+  const int c = T.lane, i = T.i0 - 3 + c;
+#pragma unroll
+  for (int r = 3 + T.wid; r <= TY + 3; r += NW) {
+    const int j = T.j0 - 3 + r;
+    if (c < 3 || j > L.je + 1) continue;
+    const int o = T.idx(i, j);
+    if (r < TY + 3 && j <= L.je && c <= TX + 3 && i <= L.ie + 1) {
+      double g = S.t.fx2[r][c] * S.mfx[r][c];
+      if (dx_) g = g + (0.5 * coef) * (__ldg(delp + T.ko + o - 1) + __ldg(delp + T.ko + o)) * __ldg(dx_ + T.ko + o);
+      S.t.fx2[r][c] = g;
     }
-    FX(S.t, r, c) = g;
-  }
-  TPT_LOOP((TY + 1) * TX, TX, r, c) {
-    double g = FY(S.t, r, c) * S.mfy[r][c];
-    if (dy_) {
-      const int o = T.idx(min(T.i0 + c, L.ie), min(T.j0 + r, L.je + 1));
-      g = g + (0.5 * coef) * (__ldg(delp + T.ko + o - T.NI) + __ldg(delp + T.ko + o)) * __ldg(dy_ + T.ko + o);
+    if (c <= TX + 2 && i <= L.ie) {
+      double g = S.t.fy2[r][c] * S.mfy[r][c];
+      if (dy_) g = g + (0.5 * coef) * (__ldg(delp + T.ko + o - T.NI) + __ldg(delp + T.ko + o)) * __ldg(dy_ + T.ko + o);
+      S.t.fy2[r][c] = g;
     }
-    FY(S.t, r, c) = g;
   }
   __syncthreads();
 }
 
-template <bool MDP, bool MVT, bool MTM>
+// FAM: 0 all fields use an unlimited scheme, 1 all monotone, 2 mixed (per-field choice at run time).
+// The fields are a run-time loop around ONE copy of the tile routine (instruction-cache footprint).
+template <int FAM>
 __global__ void __launch_bounds__(tpt::NT, 2) k_dsw_transport(Lay L, DevGrid G, DswTr a) {
   using namespace tpt;
-  static_assert(TX * TY == NT, "one thread per cell in the epilogue");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DswSmem& S = *reinterpret_cast<DswSmem*>(smem_raw);
   const Tile T = make_tile(L);
   const int k = blockIdx.z, n1 = L.npz + 1;
-  const int cr_ = threadIdx.x / TX, cc_ = threadIdx.x % TX;          // this thread's cell
-  const int ci = T.i0 + cc_, cj = T.j0 + cr_;
-  const bool cell_ok = ci <= L.ie && cj <= L.je;
-  const int co = T.idx(min(ci, L.ie), min(cj, L.je));
+  const int c = T.lane, i = T.i0 - 3 + c;   // tile column / global i of this lane
+  const bool xcell = c >= 3 && c <= TX + 2 && i <= L.ie;
   const bool lastx = T.i0 + TX > L.ie, lasty = T.j0 + TY > L.je;
-  const int in_dp = (a.hord_dp == 10) ? 8 : a.hord_dp, in_vt = (a.hord_vt == 10) ? 8 : a.hord_vt, in_tm = (a.hord_tm == 10) ? 8 : a.hord_tm;
   const double c_dp = a.kdbl[KD_DELN * n1 + k], c_t = a.kdbl[KD_DELN_T * n1 + k];
-  // ---- delp (:919-920) -> mass fluxes
+  const bool dwk = a.dw && a.kdbl[KD_DAMP4_W * n1 + k] != 0.;
   stage_inputs(L, G, S.t, T, a.crx, a.cry, a.xfx, a.yfx);
-  stage_q(L, S.t, T, a.delp);
-  tp_compute<MDP>(L, G, S.t, T, nullptr, nullptr, in_dp, a.hord_dp);
-  const double dp = S.t.qx[cr_ + 3][cc_ + 3];
-  const double ra = __ldg(G.rarea + co);
-  {
-    const bool damp = a.dpx && c_dp != 0.;
-    TPT_LOOP(TY * (TX + 1), TX + 1, r, c) {
-      const int i = T.i0 + c, j = T.j0 + r;
-      const int o = T.idx(min(i, L.ie + 1), min(j, L.je));
-      double m = FX(S.t, r, c) * S.t.xfx[r + 3][c];
-      if (damp) m = m + __ldg(a.dpx + T.ko + o);
-      S.mfx[r][c] = m;
-      if (i <= L.ie + 1 && j <= L.je && (c < TX || lastx)) a.mfx[T.ko + o] = a.mfx[T.ko + o] + m;   // :928-940
+  double dp[CELL_ITERS], dpn[CELL_ITERS], ra[CELL_ITERS];
+#pragma unroll 1
+  for (int f = 0; f < 4; f++) {   // 0 delp (:919-920), 1 w (:984-990), 2 q_con (:992-1000), 3 pt (:1014-1016)
+    const double* qf = f == 0 ? a.delp : f == 1 ? a.w : f == 2 ? a.qcon : a.pt;
+    if (!qf) continue;
+    const int hord = (f == 1) ? a.hord_vt : (f == 3) ? a.hord_tm : a.hord_dp;
+    stage_q(L, S.t, T, qf);
+    tp_compute<FAM>(L, G, S.t, T, nullptr, nullptr, (hord == 10) ? 8 : hord, hord);
+    if (f == 0) {
+      // mass fluxes (+ del-n damping flux) into shared memory and the flux capacitors (:928-940)
+#pragma unroll
+      for (int n = 0; n < CELL_ITERS; n++) {   // this thread's cells: rows 3 + wid + n*NW
+        const int r = 3 + T.wid + n * NW, j = T.j0 - 3 + r;
+        const bool ok = xcell && r < TY + 3 && j <= L.je;
+        dp[n] = ok ? S.t.q[r][c] : 1.;
+        ra[n] = ok ? __ldg(G.rarea + T.idx(i, j)) : 0.;
+        dpn[n] = 1.;
+      }
+      const bool damp = a.dpx && c_dp != 0.;
+#pragma unroll 1
+      for (int r = 3 + T.wid; r <= TY + 3; r += NW) {
+        const int j = T.j0 - 3 + r;
+        if (c < 3 || j > L.je + 1) continue;
+        const int o = T.idx(i, j);
+        if (r < TY + 3 && j <= L.je && c <= TX + 3 && i <= L.ie + 1) {
+          double m = S.t.fx2[r][c] * S.t.xfx[r][c];
+          if (damp) m = m + __ldg(a.dpx + T.ko + o);
+          S.mfx[r][c] = m;
+          if (c < TX + 3 || lastx) a.mfx[T.ko + o] = a.mfx[T.ko + o] + m;
+        }
+        if (c <= TX + 2 && i <= L.ie) {
+          double m = S.t.fy2[r][c] * S.t.yfx[r][c];
+          if (damp) m = m + __ldg(a.dpy + T.ko + o);
+          S.mfy[r][c] = m;
+          if (r < TY + 3 || lasty) a.mfy[T.ko + o] = a.mfy[T.ko + o] + m;
+        }
+      }
+      __syncthreads();   // mass fluxes visible; every thread has read its delp and the unweighted fluxes
+#pragma unroll
+      for (int n = 0; n < CELL_ITERS; n++) {
+        const int r = 3 + T.wid + n * NW;
+        if (xcell && r < TY + 3) dpn[n] = dp[n] + (S.mfx[r][c] - S.mfx[r][c + 1] + S.mfy[r][c] - S.mfy[r + 1][c]) * ra[n];
+      }
+      continue;
     }
-    TPT_LOOP((TY + 1) * TX, TX, r, c) {
-      const int i = T.i0 + c, j = T.j0 + r;
-      const int o = T.idx(min(i, L.ie), min(j, L.je + 1));
-      double m = FY(S.t, r, c) * S.t.yfx[r][c + 3];
-      if (damp) m = m + __ldg(a.dpy + T.ko + o);
-      S.mfy[r][c] = m;
-      if (i <= L.ie && j <= L.je + 1 && (r < TY || lasty)) a.mfy[T.ko + o] = a.mfy[T.ko + o] + m;
+    // mass-weighted fluxes (+ mass-weighted del-n flux of q_con / pt), then (q*delp + div) / delp_new  (:1053-1066, :1262-1283)
+    const bool damp = (f == 2) ? (a.qcx && c_t != 0.) : (f == 3) ? (a.ptx && c_t != 0.) : false;
+    weight_by_mass(L, S, T, a.delp, damp ? (f == 2 ? a.qcx : a.ptx) : nullptr, damp ? (f == 2 ? a.qcy : a.pty) : nullptr, c_t);
+    double* out = (f == 1) ? a.w_o : (f == 2) ? a.qcon_o : a.pt_o;
+#pragma unroll
+    for (int n = 0; n < CELL_ITERS; n++) {
+      const int r = 3 + T.wid + n * NW, j = T.j0 - 3 + r;
+      if (!(xcell && r < TY + 3 && j <= L.je)) continue;
+      const long long o = T.ko + T.idx(i, j);
+      const double div = (S.t.fx2[r][c] - S.t.fx2[r][c + 1] + S.t.fy2[r][c] - S.t.fy2[r + 1][c]) * ra[n];
+      // same operand order as the reference: w, q_con: delp*q + div (:986,:998); pt: pt*delp + div (:1061)
+      const double num = (f == 3) ? S.t.q[r][c] * dp[n] + div : dp[n] * S.t.q[r][c] + div;
+      double v = num / dpn[n];
+      if (f == 1 && dwk) v = v + __ldg(a.dw + o);
+      out[o] = v;
+      if (f == 3) a.delp_o[o] = dpn[n];
     }
-  }
-  // ---- w (:984-990, :1262-1270)
-  double dpn = 0.;
-  if (a.w) {
-    __syncthreads();   // every thread has read its delp (qx) and the unweighted fluxes before the next field lands
-    stage_q(L, S.t, T, a.w);
-    tp_compute<MVT>(L, G, S.t, T, nullptr, nullptr, in_vt, a.hord_vt);
-    weight_by_mass(L, S, T, a.delp, nullptr, nullptr, 0.);
-    dpn = dp + (S.mfx[cr_][cc_] - S.mfx[cr_][cc_ + 1] + S.mfy[cr_][cc_] - S.mfy[cr_ + 1][cc_]) * ra;
-    const double wq = dp * S.t.qx[cr_ + 3][cc_ + 3] + (FX(S.t, cr_, cc_) - FX(S.t, cr_, cc_ + 1) + FY(S.t, cr_, cc_) - FY(S.t, cr_ + 1, cc_)) * ra;
-    double wn = wq / dpn;
-    if (a.dw && a.kdbl[KD_DAMP4_W * n1 + k] != 0.) wn = wn + __ldg(a.dw + T.ko + co);
-    if (cell_ok) a.w_o[T.ko + co] = wn;
-  } else {
-    __syncthreads();   // mass fluxes visible
-    dpn = dp + (S.mfx[cr_][cc_] - S.mfx[cr_][cc_ + 1] + S.mfy[cr_][cc_] - S.mfy[cr_ + 1][cc_]) * ra;
-  }
-  // ---- q_con (:992-1000, :1272-1283)
-  if (a.qcon) {
-    __syncthreads();   // epilogue reads of FX/FY/qx done before the next field overwrites them
-    stage_q(L, S.t, T, a.qcon);
-    tp_compute<MDP>(L, G, S.t, T, nullptr, nullptr, in_dp, a.hord_dp);
-    const bool damp = a.qcx && c_t != 0.;
-    weight_by_mass(L, S, T, a.delp, damp ? a.qcx : nullptr, damp ? a.qcy : nullptr, c_t);
-    const double qq = dp * S.t.qx[cr_ + 3][cc_ + 3] + (FX(S.t, cr_, cc_) - FX(S.t, cr_, cc_ + 1) + FY(S.t, cr_, cc_) - FY(S.t, cr_ + 1, cc_)) * ra;
-    if (cell_ok) a.qcon_o[T.ko + co] = qq / dpn;
-  }
-  // ---- pt (:1014-1016, :1053-1066)
-  __syncthreads();
-  stage_q(L, S.t, T, a.pt);
-  tp_compute<MTM>(L, G, S.t, T, nullptr, nullptr, in_tm, a.hord_tm);
-  {
-    const bool damp = a.ptx && c_t != 0.;
-    weight_by_mass(L, S, T, a.delp, damp ? a.ptx : nullptr, damp ? a.pty : nullptr, c_t);
-    const double pq = S.t.qx[cr_ + 3][cc_ + 3] * dp + (FX(S.t, cr_, cc_) - FX(S.t, cr_, cc_ + 1) + FY(S.t, cr_, cc_) - FY(S.t, cr_ + 1, cc_)) * ra;
-    if (cell_ok) {
-      a.delp_o[T.ko + co] = dpn;
-      a.pt_o[T.ko + co] = pq / dpn;
-    }
+    __syncthreads();   // epilogue reads done before the next field overwrites q / fluxes
   }
 }
 
 // vorticity transport + momentum update (sw_core.F90:1476-1509): u += ke(i)-ke(i+1) + fy, v += ke(j)-ke(j+1) - fx
-template <bool MVT>
+template <int FAM>
 __global__ void __launch_bounds__(tpt::NT, 2) k_dsw_vort_uv(Lay L, DevGrid G, const double* __restrict__ vq, const double* __restrict__ crx,
                                                           const double* __restrict__ cry, const double* __restrict__ xfx,
                                                           const double* __restrict__ yfx, const double* __restrict__ u,
@@ -757,22 +759,21 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_dsw_vort_uv(Lay L, DevGrid G, co
   const Tile T = make_tile(L);
   stage_inputs(L, G, S, T, crx, cry, xfx, yfx);
   stage_q(L, S, T, vq);
-  tp_compute<MVT>(L, G, S, T, nullptr, nullptr, (hord_vt == 10) ? 8 : hord_vt, hord_vt);
+  tp_compute<FAM>(L, G, S, T, nullptr, nullptr, (hord_vt == 10) ? 8 : hord_vt, hord_vt);
   const bool lastx = T.i0 + TX > L.ie, lasty = T.j0 + TY > L.je;
   u += T.ko; v += T.ko; ke += T.ko; uo += T.ko; vo += T.ko;
-  TPT_LOOP(TY * (TX + 1), TX + 1, r, c) {   // v (is:ie+1, js:je)
-    const int i = T.i0 + c, j = T.j0 + r;
-    if (i <= L.ie + 1 && j <= L.je && (c < TX || lastx)) {
-      const int o = T.idx(i, j);
-      const double fx = FX(S, r, c) * S.xfx[r + 3][c];
+  const int c = T.lane - 3, i = T.i0 + c;
+#pragma unroll
+  for (int r = T.wid; r <= TY; r += NW) {
+    const int j = T.j0 + r;
+    if (c < 0 || j > L.je + 1) continue;
+    const int o = T.idx(i, j);
+    if (r < TY && j <= L.je && i <= L.ie + 1 && (c < TX || (c == TX && lastx))) {   // v (is:ie+1, js:je)
+      const double fx = FX(S, r, c) * S.xfx[r + 3][c + 3];
       vo[o] = __ldg(v + o) * __ldg(G.dy + o) + __ldg(ke + o) - __ldg(ke + o + T.NI) - fx;
     }
-  }
-  TPT_LOOP((TY + 1) * TX, TX, r, c) {       // u (is:ie, js:je+1)
-    const int i = T.i0 + c, j = T.j0 + r;
-    if (i <= L.ie && j <= L.je + 1 && (r < TY || lasty)) {
-      const int o = T.idx(i, j);
-      const double fy = FY(S, r, c) * S.yfx[r][c + 3];
+    if (c < TX && i <= L.ie && (r < TY || lasty)) {                                   // u (is:ie, js:je+1)
+      const double fy = FY(S, r, c) * S.yfx[r + 3][c + 3];
       uo[o] = __ldg(u + o) * __ldg(G.dx + o) + __ldg(ke + o) - __ldg(ke + o + 1) + fy;
     }
   }
@@ -794,31 +795,26 @@ __global__ void __launch_bounds__(TI* TJ) k_copy_frame(Lay L, FrameJobs jobs) {
   }
 }
 
-template <bool A, bool B, bool C>
+template <int FAM>
 static int launch_transport_t(fv3_ctx* c, const DswTr& a, int nk) {
   static bool attr_set = false;
   if (!attr_set) {
-    FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport<A, B, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DswSmem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport<FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DswSmem)));
     attr_set = true;
   }
-  k_dsw_transport<A, B, C><<<tpt::tile_grid(c->L, nk), tpt::NT, sizeof(DswSmem), c->stream>>>(c->L, c->G, a);
+  k_dsw_transport<FAM><<<tpt::tile_grid(c->L, nk), tpt::NT, sizeof(DswSmem), c->stream>>>(c->L, c->G, a);
   c->launches++;
   return 0;
 }
 static int launch_transport(fv3_ctx* c, const DswTr& a, int nk) {
-  const int key = (a.hord_dp >= 8 ? 4 : 0) | (a.hord_vt >= 8 ? 2 : 0) | (a.hord_tm >= 8 ? 1 : 0);
-  switch (key) {
-    case 0: return launch_transport_t<false, false, false>(c, a, nk);
-    case 1: return launch_transport_t<false, false, true>(c, a, nk);
-    case 2: return launch_transport_t<false, true, false>(c, a, nk);
-    case 3: return launch_transport_t<false, true, true>(c, a, nk);
-    case 4: return launch_transport_t<true, false, false>(c, a, nk);
-    case 5: return launch_transport_t<true, false, true>(c, a, nk);
-    case 6: return launch_transport_t<true, true, false>(c, a, nk);
-    default: return launch_transport_t<true, true, true>(c, a, nk);
-  }
+  const bool m_dp = a.hord_dp >= 8, m_vt = a.hord_vt >= 8, m_tm = a.hord_tm >= 8;
+  const bool vt_used = a.w != nullptr;
+  const bool all_mono = m_dp && m_tm && (m_vt || !vt_used), none_mono = !m_dp && !m_tm && (!m_vt || !vt_used);
+  if (all_mono) return launch_transport_t<1>(c, a, nk);
+  if (none_mono) return launch_transport_t<0>(c, a, nk);
+  return launch_transport_t<2>(c, a, nk);
 }
-template <bool M>
+template <int M>
 static int launch_vort_uv_t(fv3_ctx* c, const double* vq, const double* u, const double* v, const double* ke, double* uo, double* vo, int nk) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -944,8 +940,8 @@ int stage_d_sw(fv3_ctx* c, double dt) {
                                   c->d_kint, c->d_kdbl, dt, f.dddmp, f.d4_bg, c->b.stretched_grid);
   c->launches++;
   // --- vorticity transport and momentum update (:1476-1509), fused
-  rc = (f.hord_vt >= 8) ? launch_vort_uv_t<true>(c, vq, u, v, ke, c->alt_u, c->alt_v, nk)
-                        : launch_vort_uv_t<false>(c, vq, u, v, ke, c->alt_u, c->alt_v, nk);
+  rc = (f.hord_vt >= 8) ? launch_vort_uv_t<1>(c, vq, u, v, ke, c->alt_u, c->alt_v, nk)
+                        : launch_vort_uv_t<0>(c, vq, u, v, ke, c->alt_u, c->alt_v, nk);
   if (rc) return rc;
   {
     FrameJobs fj{};

@@ -463,9 +463,8 @@ __device__ __forceinline__ double dm2(double qm, double q0, double qp) {
   const double m = mn(mn(fabs(xt), fabs(a)), fabs(b));
   return same ? copysign(m, xt) : 0.;
 }
-template <bool MONO>
-__device__ __forceinline__ double aux_point(int iord, double qm2, double qm1, double q0, double qp1) {
-  if (MONO) return dm2(qm1, q0, qp1);
+__device__ __forceinline__ double aux_point(bool mono, int iord, double qm2, double qm1, double q0, double qp1) {
+  if (mono) return dm2(qm1, q0, qp1);
   const double al = p1 * (qm1 + q0) + p2 * (qm2 + qp1);
   return iord < 0 ? mx(0., al) : al;
 }

@@ -39,22 +39,20 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, const
   const Tile T = make_tile(L);
   stage_inputs(L, G, S, T, crx, cry, xfx, yfx);
   stage_q(L, S, T, q);
-  tp_compute<MONO>(L, G, S, T, ra_x, ra_y, ord_in, ord_ou);
+  tp_compute<MONO ? 1 : 0>(L, G, S, T, ra_x, ra_y, ord_in, ord_ou);
+  // epilogue: lane = column; the tile stores its own west/south faces, plus the face's last column / row
   const bool lastx = T.i0 + TX > L.ie, lasty = T.j0 + TY > L.je;
+  const int c = T.lane - 3, i = T.i0 + c;
   fx += T.ko; fy += T.ko;
-  TPT_LOOP(TY * (TX + 1), TX + 1, r, c) {
-    const int i = T.i0 + c, j = T.j0 + r;
-    if (i <= L.ie + 1 && j <= L.je && (c < TX || lastx)) {
-      const int o = T.idx(i, j);
-      fx[o] = FX(S, r, c) * (mfx ? __ldg(mfx + T.ko + o) : S.xfx[r + 3][c]);
-    }
-  }
-  TPT_LOOP((TY + 1) * TX, TX, r, c) {
-    const int i = T.i0 + c, j = T.j0 + r;
-    if (i <= L.ie && j <= L.je + 1 && (r < TY || lasty)) {
-      const int o = T.idx(i, j);
-      fy[o] = FY(S, r, c) * (mfy ? __ldg(mfy + T.ko + o) : S.yfx[r][c + 3]);
-    }
+#pragma unroll
+  for (int r = T.wid; r <= TY; r += NW) {
+    const int j = T.j0 + r;
+    if (c < 0 || j > L.je + 1) continue;
+    const int o = T.idx(i, j);
+    if (r < TY && j <= L.je && i <= L.ie + 1 && (c < TX || (c == TX && lastx)))
+      fx[o] = FX(S, r, c) * (mfx ? __ldg(mfx + T.ko + o) : S.xfx[r + 3][c + 3]);
+    if (c < TX && i <= L.ie && (r < TY || lasty))
+      fy[o] = FY(S, r, c) * (mfy ? __ldg(mfy + T.ko + o) : S.yfx[r + 3][c + 3]);
   }
 }
 
