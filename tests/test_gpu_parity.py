@@ -40,6 +40,17 @@ def test_d_sw_hord8_dddmp():
                                flags_override=dict(hord_mt=8, hord_vt=8, hord_tm=8, hord_dp=8, dddmp=0.2, nord=3)), TOL_STAGE)
 
 
+def test_d_sw_mixed_scheme_families_multi_tile():
+    """Fused delp/w/q_con/pt transport with fields in different PPM families (run-time family choice), on a face
+    that spans several 26x20 transport tiles in both directions incl. partial last tiles."""
+    _assert(H.parity_c_sw_d_sw(n=56, npz=3, flagset="B", dt=10.0,
+                               flags_override=dict(use_cond=1, hord_mt=6, hord_vt=8, hord_tm=5, hord_dp=-5)), TOL_STAGE)
+
+
+def test_d_sw_multi_tile_monotone():
+    _assert(H.parity_c_sw_d_sw(n=56, npz=2, flagset="A", dt=10.0, tile=4), TOL_STAGE)
+
+
 @pytest.mark.parametrize("hord", [5, 6, -5, 8, 10])
 @pytest.mark.parametrize("use_mfx", [0, 1])
 def test_fv_tp_2d(hord, use_mfx):
