@@ -81,7 +81,7 @@ def _ptr(a):
 def load_library():
     """The CUDA product library.  Fails loudly when it is missing: no CPU fallback."""
     here = os.path.dirname(os.path.abspath(__file__))
-    path = os.path.join(here, "csrc", "libfv3_b200.so")
+    path = os.environ.get("FV3_B200_LIB") or os.path.join(here, "csrc", "libfv3_b200.so")   # override: kernel-variant A/B runs
     if not os.path.exists(path):
         raise RuntimeError(
             f"CUDA library {path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "

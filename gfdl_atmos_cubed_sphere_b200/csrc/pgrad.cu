@@ -22,6 +22,39 @@
 #define G2(p, i, j) __ldg((G.p) + LIDX(L, (i), (j)))
 static inline dim3 plane_grid(const Lay& L, int nk) { return dim3((L.NI + TI - 1) / TI, (L.NJ + TJ - 1) / TJ, nk); }
 
+// The TI x TJ thread-block tiles of the padded plane that are NOT entirely inside an interior box, enumerated compactly
+// (bottom + top tile rows full width, then the left / right tile columns of the rows in between), so a kernel that
+// only has cube-edge work launches a few hundred CTAs per level instead of ~20 000 that exit at once.
+struct FrameGrid {
+  int nbx, a, b, cl, cr, nby;   // tile rows [0,a) and [b,nby) are frame rows; tile columns [0,cl) and [nbx-cr,nbx) frame columns
+  int count() const { return nbx * (a + nby - b) + (b - a) * (cl + cr); }
+  __device__ __forceinline__ void map(int t, int& bx, int& by) const {
+    const int nyf = a + nby - b;
+    if (t < nbx * nyf) { by = t / nbx; bx = t - by * nbx; if (by >= a) by = by - a + b; }
+    else { t -= nbx * nyf; const int nc = cl + cr, row = t / nc, cc = t - row * nc; by = a + row; bx = cc < cl ? cc : nbx - cr + (cc - cl); }
+  }
+};
+// interior box (ilo..ihi, jlo..jhi): points strictly inside need no frame work
+static inline FrameGrid frame_grid(const Lay& L, int ilo, int ihi, int jlo, int jhi) {
+  FrameGrid f;
+  f.nbx = (L.NI + TI - 1) / TI; f.nby = (L.NJ + TJ - 1) / TJ;
+  const int i0 = L.isd - FV3_IOFF, j0 = L.jsd;
+  // a tile column bx covers i0 + bx*TI .. +TI-1; it is interior iff it lies within [ilo, ihi]
+  int cl = 0; while (cl < f.nbx && i0 + cl * TI < ilo) cl++;
+  int cr = 0; while (cr < f.nbx - cl && i0 + (f.nbx - cr) * TI - 1 > ihi) cr++;
+  int a = 0; while (a < f.nby && j0 + a * TJ < jlo) a++;
+  int bt = 0; while (bt < f.nby - a && j0 + (f.nby - bt) * TJ - 1 > jhi) bt++;
+  f.cl = cl; f.cr = cr; f.a = a; f.b = f.nby - bt;
+  return f;
+}
+#define FRAME_IJK                                              \
+  int bx_, by_;                                                \
+  FG.map(blockIdx.x, bx_, by_);                                \
+  const int i = L.isd - FV3_IOFF + bx_ * TI + threadIdx.x;     \
+  const int j = L.jsd + by_ * TJ + threadIdx.y;                \
+  const int k = blockIdx.z;                                    \
+  const long long ko = (long long)k * L.plane;
+
 namespace {
 constexpr double r3 = 1. / 3.;
 constexpr double a1 = 0.5625, a2 = -0.0625;         // a2b_edge.F90:34-35
@@ -30,11 +63,13 @@ constexpr double c1 = 2. / 3., c2 = -1. / 6.;       // :54-55
 }
 
 // pass 1: qx (is:ie+1, 1:npy-1) and qy (1:npx-1, js:je+1)   (a2b_edge.F90:132-233)
-__global__ void __launch_bounds__(TI* TJ) k_a2b_1(Lay L, DevGrid G, const double* __restrict__ qin, double* __restrict__ qx,
-                                                 double* __restrict__ qy) {
-  PLANE_IJK
+// frame != 0: only the points the frame outputs of pass 2 read (the interior is done by k_a2b_fused)
+__global__ void __launch_bounds__(TI* TJ) k_a2b_1(Lay L, DevGrid G, FrameGrid FG, const double* __restrict__ qin, double* __restrict__ qx,
+                                                 double* __restrict__ qy, int frame) {
+  FRAME_IJK
   const int npx = L.npx, npy = L.npy;
   if (i < L.is - 2 || i > L.ie + 2 || j < L.js - 2 || j > L.je + 2) return;
+  if (frame && i > 5 && i < npx - 4 && j > 5 && j < npy - 4) return;
   const bool cube = L.cube;
   auto Q = [&](int ii, int jj) { return AT(qin, ii, jj); };
   if (i >= L.is && i <= L.ie + 1 && (!cube || (j >= 1 && j <= npy - 1))) {
@@ -70,11 +105,12 @@ __global__ void __launch_bounds__(TI* TJ) k_a2b_1(Lay L, DevGrid G, const double
 }
 
 // pass 2: qout on (is:ie+1, js:je+1)   (a2b_edge.F90:104-130, :141-166, :199-224, :258-288)
-__global__ void __launch_bounds__(TI* TJ) k_a2b_2(Lay L, DevGrid G, const double* __restrict__ qin, const double* __restrict__ qx,
-                                                 const double* __restrict__ qy, double* __restrict__ qout) {
-  PLANE_IJK
+__global__ void __launch_bounds__(TI* TJ) k_a2b_2(Lay L, DevGrid G, FrameGrid FG, const double* __restrict__ qin, const double* __restrict__ qx,
+                                                 const double* __restrict__ qy, double* __restrict__ qout, int frame) {
+  FRAME_IJK
   const int npx = L.npx, npy = L.npy;
   if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
+  if (frame && i >= 3 && i <= npx - 2 && j >= 3 && j <= npy - 2) return;
   auto Q = [&](int ii, int jj) { return AT(qin, ii, jj); };
   auto QX = [&](int ii, int jj) { return AT(qx, ii, jj); };
   auto QY = [&](int ii, int jj) { return AT(qy, ii, jj); };
@@ -136,12 +172,59 @@ __global__ void __launch_bounds__(TI* TJ) k_a2b_2(Lay L, DevGrid G, const double
   qout[ko + LIDX(L, i, j)] = out;
 }
 
+// Interior of a2b_ord4 in ONE kernel: outputs (i, j) in [3, npx-2]^2 use only the generic 4th-order formulas
+// (a2b_edge.F90:168-170, :226-228, :258-288 interior branch), a 4x4 stencil of qin that never leaves the face.  A CTA
+// stages a (32+3) x (16+3) tile of qin, forms qx and qy in shared memory (same expressions as the two-pass kernels) and
+// combines them; the intermediates never touch HBM (the two-pass form moved ~5x the field).
+#define AF_TX 32
+#define AF_TY 16
+__global__ void __launch_bounds__(256) k_a2b_fused(Lay L, const double* __restrict__ qin, double* __restrict__ qout) {
+  __shared__ double q[AF_TY + 3][AF_TX + 4];
+  __shared__ double qx[AF_TY + 3][AF_TX];
+  __shared__ double qy[AF_TY][AF_TX + 4];
+  const int i0 = 3 + blockIdx.x * AF_TX, j0 = 3 + blockIdx.y * AF_TY;   // first output point of the tile
+  const long long ko = (long long)blockIdx.z * L.plane;
+  const int tid = threadIdx.x, hi = L.npx - 2;                          // last output index in both directions
+  for (int e = tid; e < (AF_TY + 3) * (AF_TX + 3); e += 256) {
+    const int r = e / (AF_TX + 3), c = e - r * (AF_TX + 3);
+    q[r][c] = __ldg(qin + ko + LIDX(L, min(i0 - 2 + c, L.ie), min(j0 - 2 + r, L.je)));
+  }
+  __syncthreads();
+  for (int e = tid; e < (AF_TY + 3) * AF_TX; e += 256) {   // qx(i0+c, j0-2+r)
+    const int r = e / AF_TX, c = e - r * AF_TX;
+    qx[r][c] = b2 * (q[r][c] + q[r][c + 3]) + b1 * (q[r][c + 1] + q[r][c + 2]);
+  }
+  for (int e = tid; e < AF_TY * (AF_TX + 3); e += 256) {   // qy(i0-2+c, j0+r)
+    const int r = e / (AF_TX + 3), c = e - r * (AF_TX + 3);
+    qy[r][c] = b2 * (q[r][c] + q[r + 3][c]) + b1 * (q[r + 1][c] + q[r + 2][c]);
+  }
+  __syncthreads();
+  const int c = tid & 31;
+  for (int r = tid >> 5; r < AF_TY; r += 8) {
+    const int i = i0 + c, j = j0 + r;
+    if (i > hi || j > hi) continue;
+    const double qxx = a2 * (qx[r][c] + qx[r + 3][c]) + a1 * (qx[r + 1][c] + qx[r + 2][c]);
+    const double qyy = a2 * (qy[r][c] + qy[r][c + 3]) + a1 * (qy[r][c + 1] + qy[r][c + 2]);
+    qout[ko + LIDX(L, i, j)] = 0.5 * (qxx + qyy);
+  }
+}
+
 // qx, qy scratch = c->scr[4], c->scr[5] (free in both callers: d_sw between transports, nh_p_grad)
 int launch_a2b_ord4(fv3_ctx* c, const double* qin, double* qout, int nk, int /*replace_into_qin*/) {
   const Lay& L = c->L;
-  dim3 blk(TI, TJ), grd = plane_grid(L, nk);
-  k_a2b_1<<<grd, blk, 0, c->stream>>>(L, c->G, qin, c->scr[4], c->scr[5]);
-  k_a2b_2<<<grd, blk, 0, c->stream>>>(L, c->G, qin, c->scr[4], c->scr[5], qout);
+  dim3 blk(TI, TJ);
+  const int ni = L.npx - 4;   // outputs 3 .. npx-2
+  const int fused = L.cube && ni >= 1 && L.npx == L.npy;
+  if (fused) {
+    dim3 g((ni + AF_TX - 1) / AF_TX, (ni + AF_TY - 1) / AF_TY, nk);
+    k_a2b_fused<<<g, 256, 0, c->stream>>>(L, qin, qout);
+    c->launches++;
+  }
+  // frame: pass 1 is needed where i <= 5 || i >= npx-4 (same in j), pass 2 where i <= 2 || i >= npx-1; one grid serves both
+  const FrameGrid FG = fused ? frame_grid(L, 6, L.npx - 5, 6, L.npy - 5) : frame_grid(L, 1, 0, 1, 0);
+  dim3 grd(FG.count(), 1, nk);
+  k_a2b_1<<<grd, blk, 0, c->stream>>>(L, c->G, FG, qin, c->scr[4], c->scr[5], fused);
+  k_a2b_2<<<grd, blk, 0, c->stream>>>(L, c->G, FG, qin, c->scr[4], c->scr[5], qout, fused);
   c->launches += 2;
   return 0;
 }
