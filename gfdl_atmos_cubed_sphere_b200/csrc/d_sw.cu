@@ -782,8 +782,12 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_dsw_vort_uv(Lay L, DevGrid G, co
 // the fused kernels write the computational domain only: copy the halo frame so a frozen halo stays frozen
 struct FrameJob { const double* src; double* dst; int i1, j1; };   // computed box is (is:i1, js:j1), array box (isd:i1+ng', ...)
 struct FrameJobs { FrameJob j[6]; int n; };
-__global__ void __launch_bounds__(TI* TJ) k_copy_frame(Lay L, FrameJobs jobs) {
-  PLANE_IJK
+__global__ void __launch_bounds__(TI* TJ) k_copy_frame(Lay L, FrameGrid FG, FrameJobs jobs) {
+  int bx_, by_;
+  FG.map(blockIdx.x, bx_, by_);
+  const int i = L.isd - FV3_IOFF + bx_ * TI + threadIdx.x;
+  const int j = L.jsd + by_ * TJ + threadIdx.y;
+  const long long ko = (long long)blockIdx.z * L.plane;
   if (i < L.isd || i > L.ied + 1 || j > L.jed + 1) return;
   const long long o = ko + LIDX(L, i, j);
   for (int n = 0; n < jobs.n; n++) {
@@ -909,7 +913,7 @@ int stage_d_sw(fv3_ctx* c, double dt) {
     if (nonhydro) fj.j[n++] = FrameJob{w, c->alt_w, L.ie, L.je};
     if (f.use_cond) fj.j[n++] = FrameJob{c->fld[FV3_QCON], c->alt_qcon, L.ie, L.je};
     fj.n = n;
-    k_copy_frame<<<grd, blk, 0, st>>>(L, fj);
+    { const FrameGrid FG = frame_grid(L, L.is, L.ie, L.js, L.je); k_copy_frame<<<dim3(FG.count(), 1, nk), blk, 0, st>>>(L, FG, fj); }
     c->launches++;
   }
   std::swap(c->fld[FV3_DELP], c->alt_delp); std::swap(c->fld[FV3_PT], c->alt_pt);
@@ -948,7 +952,7 @@ int stage_d_sw(fv3_ctx* c, double dt) {
     fj.j[0] = FrameJob{u, c->alt_u, L.ie, L.je + 1};
     fj.j[1] = FrameJob{v, c->alt_v, L.ie + 1, L.je};
     fj.n = 2;
-    k_copy_frame<<<grd, blk, 0, st>>>(L, fj);
+    { const FrameGrid FG = frame_grid(L, L.is, L.ie, L.js, L.je); k_copy_frame<<<dim3(FG.count(), 1, nk), blk, 0, st>>>(L, FG, fj); }
     c->launches++;
   }
   // --- vorticity damping + dissipative heating (:1513-1600)

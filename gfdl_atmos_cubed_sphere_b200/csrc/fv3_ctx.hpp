@@ -32,6 +32,34 @@ struct Lay {
 #define LIDX(L, i, j) (((i) - (L).isd + FV3_IOFF) + ((j) - (L).jsd) * (L).NI)
 #endif
 
+#ifdef __CUDACC__
+// The 32 x 8 thread-block tiles of the padded plane that are NOT entirely inside an interior box, enumerated compactly
+// (bottom + top tile rows full width, then the left / right tile columns of the rows in between), so a kernel that
+// only has cube-edge work launches a few hundred CTAs per level instead of ~20 000 that exit at once.
+struct FrameGrid {
+  int nbx, a, b, cl, cr, nby;   // tile rows [0,a) and [b,nby) are frame rows; tile columns [0,cl) and [nbx-cr,nbx) frame columns
+  int count() const { return nbx * (a + nby - b) + (b - a) * (cl + cr); }
+  __device__ __forceinline__ void map(int t, int& bx, int& by) const {
+    const int nyf = a + nby - b;
+    if (t < nbx * nyf) { by = t / nbx; bx = t - by * nbx; if (by >= a) by = by - a + b; }
+    else { t -= nbx * nyf; const int nc = cl + cr, row = t / nc, cc = t - row * nc; by = a + row; bx = cc < cl ? cc : nbx - cr + (cc - cl); }
+  }
+};
+// interior box (ilo..ihi, jlo..jhi): points strictly inside need no frame work
+static inline FrameGrid frame_grid(const Lay& L, int ilo, int ihi, int jlo, int jhi) {
+  FrameGrid f;
+  f.nbx = (L.NI + 31) / 32; f.nby = (L.NJ + 7) / 8;
+  const int i0 = L.isd - FV3_IOFF, j0 = L.jsd;
+  // a tile column bx covers i0 + bx*TI .. +TI-1; it is interior iff it lies within [ilo, ihi]
+  int cl = 0; while (cl < f.nbx && i0 + cl * 32 < ilo) cl++;
+  int cr = 0; while (cr < f.nbx - cl && i0 + (f.nbx - cr) * 32 - 1 > ihi) cr++;
+  int a = 0; while (a < f.nby && j0 + a * 8 < jlo) a++;
+  int bt = 0; while (bt < f.nby - a && j0 + (f.nby - bt) * 8 - 1 > jhi) bt++;
+  f.cl = cl; f.cr = cr; f.a = a; f.b = f.nby - bt;
+  return f;
+}
+#endif
+
 // pointers to the 2-D metric planes on the device
 struct DevGrid {
   const double *area, *rarea, *dxa, *dya, *rdxa, *rdya, *cosa_s, *rsin2, *f0;

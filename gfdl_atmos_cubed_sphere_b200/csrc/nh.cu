@@ -32,208 +32,329 @@ constexpr double dz_min = 2.;   // nh_utils.F90:46-50
 
 struct SolverIn {
   const double *delp, *pt, *hgt /*interface heights (m): dz2 = hgt(k+1)-hgt(k)*/, *w, *ws, *q_con, *cappa;
-  double *pe /*(km+1) out: perturbation pressure*/, *pm2, *gam, *pp, *w2;
+  double *pm2, *gam, *pp, *w2;   // scratch planes [km+1][NJ][NI]
   double dt, rgrav, rdgas, akap, ptop, p_fac, a_imp;
   int km, use_cond, moist_kappa, d_grid;
 };
 
-// One column of SIM1_solver (a_imp > 0.999) or SIM_solver.  On exit: S.w2 holds the new w,
-// S.pe the perturbation pressure at interfaces, and dz2(k) is returned through out_dz(k) in
-// the order k = km..1 (the caller rebuilds heights / geopotential while it is produced).
-template <class DzSink>
-__device__ __forceinline__ void solve_column(const SolverIn& S, long long o, long long P, DzSink out_dz) {
+// One column of SIM1_solver (a_imp > 0.999) or SIM_solver, in SIX sweeps over k with the loads of NB levels issued
+// together (the first version made ten sweeps with one dependent load chain per level: ncu 78 % long-scoreboard stalls,
+// 3.4 GB of traffic per call at C384L79):
+//   A  down: pm2, p_gas' (registers only) and the forward elimination of the spline system for pp, one level behind
+//            (nh_utils.F90:377-447, :1297-1332)
+//   B  up:   back-substitution of pp                                                   (:1328-1332)
+//   C  down: forward elimination of the w system, one level behind the loads          (:1335-1361 / :1463-1496)
+//   D  up:   back-substitution of w                                                   (:1357-1361)
+//   E  down: perturbation pressure pe (:1373-1380 / :1508-1516, :1531-1535); emit(k, pe_final, pem, w2) hands every
+//            interface to the caller (pef / ppe, pk3, pe, pk, peln, w); the raw pe goes to the storage of pp
+//   F  up:   dz2 from the spline of pe (:1382-1392); out_dz(k, dz2) for k = km..1
+// The arithmetic of every statement is the reference's, in the reference's order.
+#ifndef RIEM_NB
+#define RIEM_NB 2
+#endif
+#ifndef RIEM_MINB
+#define RIEM_MINB 8
+#endif
+constexpr int NB = RIEM_NB;
+template <bool MK, bool UC, class IfaceSink, class DzSink>
+__device__ __forceinline__ void solve_column(const SolverIn& S, long long o, long long P, IfaceSink emit, DzSink out_dz) {
   const int km = S.km;
   const bool sim1 = S.d_grid ? (S.a_imp > 0.999) : true;   // nh_utils.F90:450-459, nh_core.F90:169-185
   const double alpha = sim1 ? 1.0 : S.a_imp;
   const double beta = 1. - alpha, ra = 1. / alpha, t2 = beta / alpha;
   const double t1g = sim1 ? 2. * S.dt * S.dt : 2. * (alpha * S.dt) * (alpha * S.dt);
   const double rdt = 1. / S.dt, dt = S.dt;
-  auto DM = [&](int k) { return __ldg(S.delp + o + (long long)(k - 1) * P) * S.rgrav; };
-  auto DZ = [&](int k) { return __ldg(S.hgt + o + (long long)k * P) - __ldg(S.hgt + o + (long long)(k - 1) * P); };
-  auto CP2 = [&](int k) { return S.moist_kappa ? __ldg(S.cappa + o + (long long)(k - 1) * P) : S.akap; };
-  auto GM2 = [&](int k) { return 1. / (1. - CP2(k)); };
-  auto W1 = [&](int k) { return __ldg(S.w + o + (long long)(k - 1) * P); };
-  auto PT = [&](int k) { return __ldg(S.pt + o + (long long)(k - 1) * P); };
-  // ---- pass 1: pm2, pe(k) = p_gas' (nh_utils.F90:377-447, :1297-1302)
+  // array bases stay in the constant bank (kernel parameter S); only the column offset o lives in registers
+  constexpr bool mk = MK, uc = UC;
+#define LV(k) (o + (long long)((k)-1) * P)
+#define delp S.delp
+#define hgt S.hgt
+#define pt S.pt
+#define w1 S.w
+#define qcon S.q_con
+#define cappa S.cappa
+#define pm2a S.pm2
+#define gama S.gam
+#define ppa S.pp
+#define w2a S.w2
+  // ---- A
+  double ppk;   // pp(km+1) after the sweep
   {
     double pem = S.ptop, peg = S.ptop, lpem = 0., lpeg = 0.;
     if (S.d_grid) { lpem = log(S.ptop); lpeg = lpem; }
-    for (int k = 1; k <= km; k++) {
-      const double dmr = __ldg(S.delp + o + (long long)(k - 1) * P);
-      const double pem1 = pem + dmr;
-      double pm2;
-      if (S.d_grid) {   // nh_core.F90:120-165 (logs of interface pressures)
-        const double lpem1 = log(pem1);
-        if (S.use_cond) {
-          const double peg1 = peg + dmr * (1. - __ldg(S.q_con + o + (long long)(k - 1) * P));
-          const double lpeg1 = log(peg1);
-          pm2 = (peg1 - peg) / (lpeg1 - lpeg);
-          peg = peg1; lpeg = lpeg1;
-        } else pm2 = dmr / (lpem1 - lpem);
-        lpem = lpem1;
-      } else {          // nh_utils.F90:412-447
-        if (S.use_cond) {
-          const double peg1 = peg + dmr * (1. - __ldg(S.q_con + o + (long long)(k - 1) * P));
-          pm2 = (peg1 - peg) / log(peg1 / peg);
-          peg = peg1;
-        } else pm2 = dmr / log(pem1 / pem);
+    double h_prev = __ldg(hgt + o);
+    double dm_prev = 0., pe_prev = 0., g_rat = 0., bet = 1.;
+    ppk = 0.;
+    for (int k0 = 1; k0 <= km; k0 += NB) {
+      double d[NB], h[NB], t[NB], qc[NB], cp[NB];
+#pragma unroll
+      for (int u = 0; u < NB; u++) {
+        const int kk = min(k0 + u, km);
+        d[u] = __ldg(delp + LV(kk)); h[u] = __ldg(hgt + o + (long long)kk * P); t[u] = __ldg(pt + LV(kk));
+        qc[u] = uc ? __ldg(qcon + LV(kk)) : 0.;
+        cp[u] = mk ? __ldg(cappa + LV(kk)) : S.akap;
       }
-      pem = pem1;
-      const double dm = dmr * S.rgrav;
-      S.pm2[o + (long long)(k - 1) * P] = pm2;
-      S.pe[o + (long long)(k - 1) * P] = exp(GM2(k) * log(-dm / DZ(k) * S.rdgas * PT(k))) - pm2;
+#pragma unroll
+      for (int u = 0; u < NB; u++) {
+        const int k = k0 + u;
+        if (k > km) break;
+        const double dmr = d[u];
+        const double pem1 = pem + dmr;
+        double pm2;
+        if (S.d_grid) {   // nh_core.F90:120-165 (logs of interface pressures)
+          const double lpem1 = log(pem1);
+          if (uc) {
+            const double peg1 = peg + dmr * (1. - qc[u]);
+            const double lpeg1 = log(peg1);
+            pm2 = (peg1 - peg) / (lpeg1 - lpeg);
+            peg = peg1; lpeg = lpeg1;
+          } else pm2 = dmr / (lpem1 - lpem);
+          lpem = lpem1;
+        } else {          // nh_utils.F90:412-447
+          if (uc) {
+            const double peg1 = peg + dmr * (1. - qc[u]);
+            pm2 = (peg1 - peg) / log(peg1 / peg);
+            peg = peg1;
+          } else pm2 = dmr / log(pem1 / pem);
+        }
+        pem = pem1;
+        const double dm = dmr * S.rgrav;
+        pm2a[LV(k)] = pm2;
+        const double dz = h[u] - h_prev; h_prev = h[u];
+        const double pe = exp((1. / (1. - cp[u])) * log(-dm / dz * S.rdgas * t[u])) - pm2;
+        // spline system, step k-1 (needs levels k-1 and k)
+        if (k == 2) {
+          g_rat = dm_prev / dm;
+          bet = 2. * (1. + g_rat);
+          ppa[o] = 0.;
+          ppk = 3. * (pe_prev + g_rat * pe) / bet;   // pp(2)
+          ppa[o + P] = ppk;
+        } else if (k >= 3) {
+          const double gam = g_rat / bet;   // g_rat(k-2)/bet
+          g_rat = dm_prev / dm;
+          const double bb = 2. * (1. + g_rat), dd = 3. * (pe_prev + g_rat * pe);
+          gama[LV(k - 1)] = gam;
+          bet = bb - gam;
+          ppk = (dd - ppk) / bet;
+          ppa[LV(k)] = ppk;
+        }
+        dm_prev = dm; pe_prev = pe;
+      }
+    }
+    const double gam = g_rat / bet;   // step km (bb = 2, dd = 3 pe(km))
+    gama[LV(km)] = gam;
+    bet = 2. - gam;
+    ppk = (3. * pe_prev - ppk) / bet;
+    ppa[LV(km + 1)] = ppk;
+  }
+  // ---- B
+  {
+    double nxt = ppk;
+    for (int k0 = km; k0 >= 2; k0 -= NB) {
+      double p[NB], g[NB];
+#pragma unroll
+      for (int u = 0; u < NB; u++) { const int kk = max(k0 - u, 2); p[u] = ppa[LV(kk)]; g[u] = gama[LV(kk)]; }
+#pragma unroll
+      for (int u = 0; u < NB; u++) {
+        const int k = k0 - u;
+        if (k < 2) break;
+        nxt = p[u] - g[u] * nxt; ppa[LV(k)] = nxt;
+      }
     }
   }
-  auto PE = [&](int k) -> double& { return S.pe[o + (long long)(k - 1) * P]; };
-  auto PP = [&](int k) -> double& { return S.pp[o + (long long)(k - 1) * P]; };
-  auto GAM = [&](int k) -> double& { return S.gam[o + (long long)(k - 1) * P]; };
-  auto W2 = [&](int k) -> double& { return S.w2[o + (long long)(k - 1) * P]; };
-  // ---- cubic-spline edge pressures pp (nh_utils.F90:1304-1332)
+  // ---- C
+  double w2p;   // w2(km) after the sweep
   {
-    double g_rat = DM(1) / DM(2);
-    double bet = 2. * (1. + g_rat);
-    PP(1) = 0.;
-    double ppk = 3. * (PE(1) + g_rat * PE(2)) / bet;   // pp(2)
-    PP(2) = ppk;
-    for (int k = 2; k <= km; k++) {
-      const double gam = g_rat / bet;   // g_rat(k-1)/bet
-      double bb, dd;
-      if (k < km) { g_rat = DM(k) / DM(k + 1); bb = 2. * (1. + g_rat); dd = 3. * (PE(k) + g_rat * PE(k + 1)); }
-      else { bb = 2.; dd = 3. * PE(km); }
-      GAM(k) = gam;
-      bet = bb - gam;
-      ppk = (dd - ppk) / bet;
-      PP(k + 1) = ppk;
+    double pem = S.ptop;
+    double h_prev = __ldg(hgt + o);
+    double d_p = 0., w_p = 0., g_p = 0., z_p = 0., pp_p = 0.;   // level m-1
+    double aa_k = 0., wk_k = 0., bet = 1.;
+    w2p = 0.;
+    for (int k0 = 1; k0 <= km; k0 += NB) {
+      double d[NB], h[NB], wv[NB], pv[NB], cp[NB];
+#pragma unroll
+      for (int u = 0; u < NB; u++) {
+        const int kk = min(k0 + u, km);
+        d[u] = __ldg(delp + LV(kk)); h[u] = __ldg(hgt + o + (long long)kk * P); wv[u] = __ldg(w1 + LV(kk)); pv[u] = ppa[LV(kk)];
+        cp[u] = mk ? __ldg(cappa + LV(kk)) : S.akap;
+      }
+#pragma unroll
+      for (int u = 0; u < NB; u++) {
+        const int m = k0 + u;
+        if (m > km) break;
+        const double dz = h[u] - h_prev; h_prev = h[u];
+        const double gm2 = 1. / (1. - cp[u]);
+        if (m >= 2) {
+          pem = pem + d_p;                            // pem(m) = ptop + sum_{l<m} delp(l)
+          const double aa_n = t1g * 0.5 * (g_p + gm2) / (z_p + dz) * pem;   // aa(m)
+          const double wk_n = sim1 ? 0. : t2 * aa_n * (w_p - wv[u]);        // wk(m)
+          const double dmk = d_p * S.rgrav;
+          if (m == 2) {                               // step k = 1
+            bet = dmk - aa_n;
+            w2p = sim1 ? (dmk * w_p + dt * pv[u]) / bet : (dmk * w_p + dt * pv[u] + wk_n) / bet;
+          } else {                                    // step k = m-1
+            const double gam = aa_k / bet;
+            gama[LV(m - 1)] = gam;
+            bet = dmk - (aa_k + aa_n + aa_k * gam);
+            if (sim1) w2p = (dmk * w_p + dt * (pv[u] - pp_p) - aa_k * w2p) / bet;
+            else w2p = (dmk * w_p + dt * (pv[u] - pp_p) + wk_n - wk_k - aa_k * w2p) / bet;
+          }
+          w2a[LV(m - 1)] = w2p;
+          aa_k = aa_n; wk_k = wk_n;
+        }
+        d_p = d[u]; w_p = wv[u]; g_p = gm2; z_p = dz; pp_p = pv[u];
+      }
     }
-    double nxt = PP(km + 1);
-    for (int k = km; k >= 2; k--) { nxt = PP(k) - GAM(k) * nxt; PP(k) = nxt; }
-  }
-  // ---- w solver (nh_utils.F90:1335-1361 / :1463-1496)
-  {
-    double pem = S.ptop + __ldg(S.delp + o);   // pem(2)
-    auto AA = [&](int k, double pemk) { return t1g * 0.5 * (GM2(k - 1) + GM2(k)) / (DZ(k - 1) + DZ(k)) * pemk; };
-    double aa_k1 = AA(2, pem);                // aa(2)
-    double wk_k1 = sim1 ? 0. : t2 * aa_k1 * (W1(1) - W1(2));   // wk(2)
-    double bet = DM(1) - aa_k1;
-    double w2p = sim1 ? (DM(1) * W1(1) + dt * PP(2)) / bet : (DM(1) * W1(1) + dt * PP(2) + wk_k1) / bet;
-    W2(1) = w2p;
-    double aa_k = aa_k1, wk_k = wk_k1;
-    for (int k = 2; k <= km - 1; k++) {
-      pem = pem + __ldg(S.delp + o + (long long)(k - 1) * P);   // pem(k+1)
-      const double aa_n = AA(k + 1, pem);
-      const double wk_n = sim1 ? 0. : t2 * aa_n * (W1(k) - W1(k + 1));
-      const double gam = aa_k / bet;
-      GAM(k) = gam;
-      bet = DM(k) - (aa_k + aa_n + aa_k * gam);
-      if (sim1) w2p = (DM(k) * W1(k) + dt * (PP(k + 1) - PP(k)) - aa_k * w2p) / bet;
-      else w2p = (DM(k) * W1(k) + dt * (PP(k + 1) - PP(k)) + wk_n - wk_k - aa_k * w2p) / bet;
-      W2(k) = w2p;
-      aa_k = aa_n; wk_k = wk_n;
-    }
-    pem = pem + __ldg(S.delp + o + (long long)(km - 1) * P);     // pem(km+1)
-    const double p1 = t1g * GM2(km) / DZ(km) * pem;
+    // step k = km
+    pem = pem + d_p;                                  // pem(km+1)
+    const double dmk = d_p * S.rgrav;
+    const double p1 = t1g * g_p / z_p * pem;
     const double gam = aa_k / bet;
-    GAM(km) = gam;
-    bet = DM(km) - (aa_k + p1 + aa_k * gam);
+    gama[LV(km)] = gam;
+    bet = dmk - (aa_k + p1 + aa_k * gam);
     const double wsv = __ldg(S.ws + o);
-    if (sim1) w2p = (DM(km) * W1(km) + dt * (PP(km + 1) - PP(km)) - p1 * wsv - aa_k * w2p) / bet;
-    else w2p = (DM(km) * W1(km) + dt * (PP(km + 1) - PP(km)) - wk_k + p1 * (t2 * W1(km) - ra * wsv) - aa_k * w2p) / bet;
-    W2(km) = w2p;
-    for (int k = km - 1; k >= 1; k--) { w2p = W2(k) - GAM(k + 1) * w2p; W2(k) = w2p; }
+    if (sim1) w2p = (dmk * w_p + dt * (ppk - pp_p) - p1 * wsv - aa_k * w2p) / bet;
+    else w2p = (dmk * w_p + dt * (ppk - pp_p) - wk_k + p1 * (t2 * w_p - ra * wsv) - aa_k * w2p) / bet;
+    w2a[LV(km)] = w2p;
   }
-  // ---- perturbation pressure (nh_utils.F90:1373-1380 / :1508-1516)
+  // ---- D
   {
-    double pe = 0.;
-    double pe_prev_store = 0.;
-    (void)pe_prev_store;
-    // pe(1) = 0 ; pe(k+1) = pe(k) + ...   (PE(k) for k<=km is consumed: overwrite in order)
-    double carry = 0.;   // pe(k)
-    for (int k = 1; k <= km; k++) {
-      double nxt;
-      if (sim1) nxt = carry + DM(k) * (W2(k) - W1(k)) * rdt;
-      else nxt = carry + (DM(k) * (W2(k) - W1(k)) * rdt - beta * (PP(k + 1) - PP(k))) * ra;
-      PE(k) = carry;
-      carry = nxt;
-    }
-    PE(km + 1) = carry;
-    (void)pe;
-  }
-  // ---- dz2 from the spline of pe (nh_utils.F90:1382-1392), k = km..1
-  {
-    double p1 = (PE(km) + 2. * PE(km + 1)) * r3;
-    auto DZ2 = [&](int k, double p1v) {
-      const double pm2 = S.pm2[o + (long long)(k - 1) * P];
-      return -DM(k) * S.rdgas * PT(k) * exp((CP2(k) - 1.) * log(fmax(S.p_fac * pm2, p1v + pm2)));
-    };
-    out_dz(km, DZ2(km, p1));
-    for (int k = km - 1; k >= 1; k--) {
-      const double g_rat = DM(k) / DM(k + 1), bb = 2. * (1. + g_rat);
-      p1 = (PE(k) + bb * PE(k + 1) + g_rat * PE(k + 2)) * r3 - g_rat * p1;
-      out_dz(k, DZ2(k, p1));
+    double nxt = w2p;
+    for (int k0 = km - 1; k0 >= 1; k0 -= NB) {
+      double wv[NB], g[NB];
+#pragma unroll
+      for (int u = 0; u < NB; u++) { const int kk = max(k0 - u, 1); wv[u] = w2a[LV(kk)]; g[u] = gama[LV(kk + 1)]; }
+#pragma unroll
+      for (int u = 0; u < NB; u++) {
+        const int k = k0 - u;
+        if (k < 1) break;
+        nxt = wv[u] - g[u] * nxt; w2a[LV(k)] = nxt;
+      }
     }
   }
-  if (!sim1) {   // nh_utils.F90:1531-1535
-    for (int k = 1; k <= km + 1; k++) PE(k) = PE(k) + beta * (PP(k) - PE(k));
+  // ---- E
+  double pe_k1, pe_k2;   // raw pe(km), pe(km+1) for sweep F
+  {
+    double carry = 0., prevc = 0.;   // pe(k), pe(k-1)
+    double pem = S.ptop;             // hydrostatic interface pressure pem(k)
+    double pp_k = 0.;                // pp(k): pp(1) = 0
+    for (int k0 = 1; k0 <= km; k0 += NB) {
+      double d[NB], w2v[NB], wv[NB], pn[NB];
+#pragma unroll
+      for (int u = 0; u < NB; u++) {
+        const int kk = min(k0 + u, km);
+        d[u] = __ldg(delp + LV(kk)); w2v[u] = w2a[LV(kk)]; wv[u] = __ldg(w1 + LV(kk));
+        pn[u] = sim1 ? 0. : ppa[LV(kk + 1)];
+      }
+#pragma unroll
+      for (int u = 0; u < NB; u++) {
+        const int k = k0 + u;
+        if (k > km) break;
+        const double dm = d[u] * S.rgrav;
+        double nxt;
+        if (sim1) nxt = carry + dm * (w2v[u] - wv[u]) * rdt;
+        else nxt = carry + (dm * (w2v[u] - wv[u]) * rdt - beta * (pn[u] - pp_k)) * ra;
+        ppa[LV(k)] = carry;                                           // raw pe(k)
+        emit(k, sim1 ? carry : carry + beta * (pp_k - carry), pem, w2v[u]);
+        pem = pem + d[u];
+        prevc = carry; carry = nxt; pp_k = pn[u];
+      }
+    }
+    ppa[LV(km + 1)] = carry;
+    emit(km + 1, sim1 ? carry : carry + beta * (pp_k - carry), pem, 0.);
+    pe_k1 = prevc; pe_k2 = carry;
   }
+  // ---- F
+  {
+    double p1 = (pe_k1 + 2. * pe_k2) * r3;
+    double dm_n = 0.;          // dm(k+1)
+    double pe_a = pe_k1, pe_b = pe_k2;   // pe(k+1), pe(k+2) when level k is processed (k < km)
+    for (int k0 = km; k0 >= 1; k0 -= NB) {
+      double d[NB], t[NB], pm[NB], pe[NB], cp[NB];
+#pragma unroll
+      for (int u = 0; u < NB; u++) {
+        const int kk = max(k0 - u, 1);
+        d[u] = __ldg(delp + LV(kk)); t[u] = __ldg(pt + LV(kk)); pm[u] = pm2a[LV(kk)]; pe[u] = ppa[LV(kk)];
+        cp[u] = mk ? __ldg(cappa + LV(kk)) : S.akap;
+      }
+#pragma unroll
+      for (int u = 0; u < NB; u++) {
+        const int k = k0 - u;
+        if (k < 1) break;
+        const double dm = d[u] * S.rgrav;
+        if (k < km) {
+          const double g_rat = dm / dm_n, bb = 2. * (1. + g_rat);
+          p1 = (pe[u] + bb * pe_a + g_rat * pe_b) * r3 - g_rat * p1;
+          pe_b = pe_a; pe_a = pe[u];
+        }
+        out_dz(k, -dm * S.rdgas * t[u] * exp((cp[u] - 1.) * log(fmax(S.p_fac * pm[u], p1 + pm[u]))));
+        dm_n = dm;
+      }
+    }
+  }
+#undef LV
+#undef delp
+#undef hgt
+#undef pt
+#undef w1
+#undef qcon
+#undef cappa
+#undef pm2a
+#undef gama
+#undef ppa
+#undef w2a
 }
 }  // namespace
 
 // ---- Riem_Solver_c (nh_utils.F90:323-480) on columns [is-1, ie+1]^2 -------------------------
 // 8 CTAs x 128 threads per SM: all columns of a C384 face are resident in ONE wave (72-88 registers gave 1.56 waves)
-__global__ void __launch_bounds__(CB, 8) k_riem_c(Lay L, SolverIn S, const double* __restrict__ hs, double* __restrict__ gz,
+template <bool MK, bool UC>
+__global__ void __launch_bounds__(CB, RIEM_MINB) k_riem_c(Lay L, const __grid_constant__ SolverIn S, const double* __restrict__ hs, double* __restrict__ gz,
                                                double* __restrict__ pef, double grav) {
   COL_SETUP(L.is - 1, L.ie + 1, L.js - 1, L.je + 1)
   const int km = S.km;
   double gzk = __ldg(hs + o);   // gz(km+1) = hs
-  // heights are read from gz (input, m) inside solve_column; gz is overwritten bottom-up only
-  // after the w-solver has consumed dz2, in the same backward order as nh_utils.F90:468-476
-  solve_column(S, o, P, [&](int k, double dz2) {
-    if (k == km) gz[o + (long long)km * P] = gzk;
-    gzk = gzk - dz2 * grav;
-    gz[o + (long long)(k - 1) * P] = gzk;
-  });
-  // pef = pe2 + pem (nh_utils.F90:461-465), top = ptop
-  double pem = S.ptop;
-  pef[o] = S.ptop;
-  for (int k = 2; k <= km + 1; k++) {
-    pem = pem + __ldg(S.delp + o + (long long)(k - 2) * P);
-    pef[o + (long long)(k - 1) * P] = S.pe[o + (long long)(k - 1) * P] + pem;
-  }
+  // heights are read from gz (input, m) by the sweeps A and C; gz is overwritten bottom-up by the last sweep only,
+  // in the same backward order as nh_utils.F90:468-476
+  solve_column<MK, UC>(S, o, P,
+               [&](int k, double pe2, double pem, double) {   // pef = pe2 + pem (nh_utils.F90:461-465), top = ptop
+                 pef[o + (long long)(k - 1) * P] = (k == 1) ? S.ptop : pe2 + pem;
+               },
+               [&](int k, double dz2) {
+                 if (k == km) gz[o + (long long)km * P] = gzk;
+                 gzk = gzk - dz2 * grav;
+                 gz[o + (long long)(k - 1) * P] = gzk;
+               });
 }
 
 // ---- Riem_Solver3 (nh_core.F90:47-241) on columns [is, ie]x[js, je] -------------------------
-__global__ void __launch_bounds__(CB, 8) k_riem3(Lay L, SolverIn S, const double* __restrict__ zs, double* __restrict__ zh,
+template <bool MK, bool UC>
+__global__ void __launch_bounds__(CB, RIEM_MINB) k_riem3(Lay L, const __grid_constant__ SolverIn S, const double* __restrict__ zs, double* __restrict__ zh,
                                               double* __restrict__ w, double* __restrict__ delz, double* __restrict__ ppe,
                                               double* __restrict__ pk3, double* __restrict__ pk, double* __restrict__ pe,
                                               double* __restrict__ peln, int last_call, int fp_out, int use_logp) {
   COL_SETUP(L.is, L.ie, L.js, L.je)
   const int km = S.km;
   double zk = __ldg(zs + o);
-  solve_column(S, o, P, [&](int k, double dz2) {
-    if (k == km) zh[o + (long long)km * P] = zk;
-    delz[o + (long long)(k - 1) * P] = dz2;
-    zk = zk - dz2;
-    zh[o + (long long)(k - 1) * P] = zk;
-  });
-  // w, pk3, ppe (+ pe, pk, peln on the last call)
   const double peln1 = log(S.ptop);
   const double ptk = exp(S.akap * peln1);
-  double pem = S.ptop;
-  for (int k = 1; k <= km + 1; k++) {
-    const long long ok = o + (long long)(k - 1) * P;
-    double pl, pkv;
-    if (k == 1) { pl = peln1; pkv = ptk; }
-    else {
-      pem = pem + __ldg(S.delp + o + (long long)(k - 2) * P);
-      pl = log(pem);
-      pkv = exp(S.akap * pl);
-    }
-    if (last_call) { peln[ok] = pl; pk[ok] = pkv; pe[ok] = pem; }
-    const double pe2 = S.pe[ok];
-    ppe[ok] = fp_out ? pe2 + pem : pe2;
-    pk3[ok] = (use_logp && k >= 2) ? pl : pkv;
-    if (k <= km) w[ok] = S.w2[ok];
-  }
+  solve_column<MK, UC>(S, o, P,
+               [&](int k, double pe2, double pem, double w2) {   // w, pk3, ppe (+ pe, pk, peln on the last call)
+                 const long long ok = o + (long long)(k - 1) * P;
+                 double pl, pkv;
+                 if (k == 1) { pl = peln1; pkv = ptk; }
+                 else { pl = log(pem); pkv = exp(S.akap * pl); }
+                 if (last_call) { peln[ok] = pl; pk[ok] = pkv; pe[ok] = pem; }
+                 ppe[ok] = fp_out ? pe2 + pem : pe2;
+                 pk3[ok] = (use_logp && k >= 2) ? pl : pkv;
+                 if (k <= km) w[ok] = w2;
+               },
+               [&](int k, double dz2) {
+                 if (k == km) zh[o + (long long)km * P] = zk;
+                 delz[o + (long long)(k - 1) * P] = dz2;
+                 zk = zk - dz2;
+                 zh[o + (long long)(k - 1) * P] = zk;
+               });
 }
 
 // ---- update_dz_c (nh_utils.F90:59-201) ------------------------------------------------------
@@ -454,9 +575,11 @@ int stage_riem_solver_c(fv3_ctx* c, double dt2) {
   if (c->f.fast_tau_w_sec > 1.e-5) return fv3_fail(c, -2, "Riem_Solver_c: fast_tau_w_sec not supported");
   SolverIn S = make_solver(c, dt2, 0);
   S.delp = c->fld[FV3_DELPC]; S.pt = c->fld[FV3_PTC]; S.hgt = c->fld[FV3_GZ]; S.w = c->fld[FV3_OMGA]; S.ws = c->fld[FV3_WS3];
-  S.pe = c->fld[FV3_PKC];   // perturbation pressure accumulates in pef's storage, pem added last
   const int n = L.ie - L.is + 3;
-  k_riem_c<<<col_blocks(n, n), CB, 0, c->stream>>>(L, S, c->fld[FV3_PHIS], c->fld[FV3_GZ], c->fld[FV3_PKC], c->f.grav);
+#define RIEM_C(MK, UC) k_riem_c<MK, UC><<<col_blocks(n, n), CB, 0, c->stream>>>(L, S, c->fld[FV3_PHIS], c->fld[FV3_GZ], c->fld[FV3_PKC], c->f.grav)
+  if (S.moist_kappa) { if (S.use_cond) RIEM_C(true, true); else RIEM_C(true, false); }
+  else { if (S.use_cond) RIEM_C(false, true); else RIEM_C(false, false); }
+#undef RIEM_C
   c->launches++;
   return 0;
 }
@@ -468,7 +591,6 @@ int stage_riem_solver3(fv3_ctx* c, double dt, int last_call) {
   if (c->f.fast_tau_w_sec > 1.e-5 || c->f.d2bg_zq > 0.0001) return fv3_fail(c, -2, "Riem_Solver3: fast_tau_w_sec / d2bg_zq not supported");
   SolverIn S = make_solver(c, dt, 1);
   S.delp = c->fld[FV3_DELP]; S.pt = c->fld[FV3_PT]; S.hgt = c->fld[FV3_ZH]; S.w = c->fld[FV3_W]; S.ws = c->fld[FV3_WS];
-  S.pe = c->scr[4];
   const int n = L.ie - L.is + 1;
   // zs = phis*rgrav (dyn_core.F90:247-251) into scr[5]
   {
@@ -476,9 +598,13 @@ int stage_riem_solver3(fv3_ctx* c, double dt, int last_call) {
     k_zs<<<grd2, blk2, 0, c->stream>>>(L, c->fld[FV3_PHIS], c->scr[5], 1.0 / c->f.grav);
     c->launches++;
   }
-  k_riem3<<<col_blocks(n, n), CB, 0, c->stream>>>(L, S, c->scr[5], c->fld[FV3_ZH], c->fld[FV3_W], c->fld[FV3_DELZ], c->fld[FV3_PKC],
-                                                 c->fld[FV3_PK3], c->fld[FV3_PK], c->fld[FV3_PE], c->fld[FV3_PELN], last_call,
-                                                 c->f.beta < -0.1 ? 1 : 0, c->f.use_logp);
+#define RIEM_3(MK, UC)                                                                                                              \
+  k_riem3<MK, UC><<<col_blocks(n, n), CB, 0, c->stream>>>(L, S, c->scr[5], c->fld[FV3_ZH], c->fld[FV3_W], c->fld[FV3_DELZ], c->fld[FV3_PKC], \
+                                                         c->fld[FV3_PK3], c->fld[FV3_PK], c->fld[FV3_PE], c->fld[FV3_PELN], last_call,      \
+                                                         c->f.beta < -0.1 ? 1 : 0, c->f.use_logp)
+  if (S.moist_kappa) { if (S.use_cond) RIEM_3(true, true); else RIEM_3(true, false); }
+  else { if (S.use_cond) RIEM_3(false, true); else RIEM_3(false, false); }
+#undef RIEM_3
   c->launches++;
   return 0;
 }

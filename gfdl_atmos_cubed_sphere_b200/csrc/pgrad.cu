@@ -22,31 +22,6 @@
 #define G2(p, i, j) __ldg((G.p) + LIDX(L, (i), (j)))
 static inline dim3 plane_grid(const Lay& L, int nk) { return dim3((L.NI + TI - 1) / TI, (L.NJ + TJ - 1) / TJ, nk); }
 
-// The TI x TJ thread-block tiles of the padded plane that are NOT entirely inside an interior box, enumerated compactly
-// (bottom + top tile rows full width, then the left / right tile columns of the rows in between), so a kernel that
-// only has cube-edge work launches a few hundred CTAs per level instead of ~20 000 that exit at once.
-struct FrameGrid {
-  int nbx, a, b, cl, cr, nby;   // tile rows [0,a) and [b,nby) are frame rows; tile columns [0,cl) and [nbx-cr,nbx) frame columns
-  int count() const { return nbx * (a + nby - b) + (b - a) * (cl + cr); }
-  __device__ __forceinline__ void map(int t, int& bx, int& by) const {
-    const int nyf = a + nby - b;
-    if (t < nbx * nyf) { by = t / nbx; bx = t - by * nbx; if (by >= a) by = by - a + b; }
-    else { t -= nbx * nyf; const int nc = cl + cr, row = t / nc, cc = t - row * nc; by = a + row; bx = cc < cl ? cc : nbx - cr + (cc - cl); }
-  }
-};
-// interior box (ilo..ihi, jlo..jhi): points strictly inside need no frame work
-static inline FrameGrid frame_grid(const Lay& L, int ilo, int ihi, int jlo, int jhi) {
-  FrameGrid f;
-  f.nbx = (L.NI + TI - 1) / TI; f.nby = (L.NJ + TJ - 1) / TJ;
-  const int i0 = L.isd - FV3_IOFF, j0 = L.jsd;
-  // a tile column bx covers i0 + bx*TI .. +TI-1; it is interior iff it lies within [ilo, ihi]
-  int cl = 0; while (cl < f.nbx && i0 + cl * TI < ilo) cl++;
-  int cr = 0; while (cr < f.nbx - cl && i0 + (f.nbx - cr) * TI - 1 > ihi) cr++;
-  int a = 0; while (a < f.nby && j0 + a * TJ < jlo) a++;
-  int bt = 0; while (bt < f.nby - a && j0 + (f.nby - bt) * TJ - 1 > jhi) bt++;
-  f.cl = cl; f.cr = cr; f.a = a; f.b = f.nby - bt;
-  return f;
-}
 #define FRAME_IJK                                              \
   int bx_, by_;                                                \
   FG.map(blockIdx.x, bx_, by_);                                \
