@@ -232,6 +232,7 @@ int fv3_create(const fv3_bounds_t* bd, const fv3_grid_t* grid, const fv3_flags_t
   cudaMalloc(&c->d_kdbl, sizeof(double) * 12 * (bd->npz + 1));
   std::vector<double> dp(bd->npz);
   for (int k = 0; k < bd->npz; k++) dp[k] = c->ak[k + 1] - c->ak[k] + (c->bk[k + 1] - c->bk[k]) * 1.E5;  // dyn_core.F90:242-244
+  c->d_edge_tab = nullptr;
   cudaMalloc(&c->d_dp_ref, sizeof(double) * bd->npz);
   cudaMemcpy(c->d_dp_ref, dp.data(), sizeof(double) * bd->npz, cudaMemcpyHostToDevice);
   cudaStreamSynchronize(c->stream);
@@ -249,7 +250,7 @@ void fv3_destroy(fv3_ctx* c) {
   for (auto p : alts) cudaFree(p);
   for (int i = 0; i < fv3_ctx::NSCR; i++) cudaFree(c->scr[i]);
   for (auto p : c->metric_alloc) cudaFree(p);
-  cudaFree(c->d_stage); cudaFree(c->d_kint); cudaFree(c->d_kdbl); cudaFree(c->d_dp_ref);
+  cudaFree(c->d_stage); cudaFree(c->d_kint); cudaFree(c->d_kdbl); cudaFree(c->d_dp_ref); cudaFree(c->d_edge_tab);
   for (auto& kv : c->timers) { cudaEventDestroy(kv.second.e0); cudaEventDestroy(kv.second.e1); }
   cudaStreamDestroy(c->stream);
   delete c;

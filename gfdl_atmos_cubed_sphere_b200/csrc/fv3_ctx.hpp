@@ -104,6 +104,7 @@ struct fv3_ctx {
   std::vector<int> nord_v; std::vector<double> damp_vt;
   int* d_kint; double* d_kdbl;     // device copies of per-k coefficient tables
   double* d_dp_ref;                // dp_ref(npz)  dyn_core.F90:242-244
+  double* d_edge_tab;              // edge_profile coefficient tables (nh.cu), built on first use
   long long launches;
   bool timers_on;
   std::map<std::string, StageTimer> timers;

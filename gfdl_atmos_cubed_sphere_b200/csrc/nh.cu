@@ -437,42 +437,83 @@ __global__ void __launch_bounds__(CB) k_dz_clamp(Lay L, const double* __restrict
 }
 
 // ---- update_dz_d (nh_utils.F90:204-321) -----------------------------------------------------
-// edge_profile (nh_utils.F90:1638-1672, non-uniform branch, limiter = 0) for a pair of fields
-__global__ void __launch_bounds__(CB, 8) k_edge_profile(Lay L, const double* __restrict__ q1, const double* __restrict__ q2,
-                                                    double* __restrict__ q1e, double* __restrict__ q2e, double* __restrict__ gam,
-                                                    const double* __restrict__ dp0, int i0, int i1, int j0, int j1) {
-  COL_SETUP(i0, i1, j0, j1)
-  const int km = L.npz;
-  auto Q1 = [&](int k) { return __ldg(q1 + o + (long long)(k - 1) * P); };
-  auto Q2 = [&](int k) { return __ldg(q2 + o + (long long)(k - 1) * P); };
+// edge_profile (nh_utils.F90:1638-1672, non-uniform branch, limiter = 0) for a pair of fields.
+// The tridiagonal coefficients depend on dp0 only, i.e. they are the same for every column: a one-thread kernel builds
+// the per-level tables once per context (gk, bet, gam + the four boundary scalars) instead of every column recomputing
+// them and storing gam as a full 3-D plane.  The two sweeps load NB levels at a time.
+// table layout: T[0..km) = gk(k), T[km..2km) = bet(k), T[2km..3km) = gam(k) (k = 1..km at index k-1), then
+// T[3km+0] = xt1 (top), +1 = a_bot, +2 = xt1 (bottom), +3 = xt2
+__global__ void k_edge_tables(const double* __restrict__ dp0, double* __restrict__ T, int km) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double g0 = dp0[1] / dp0[0];
-  double xt1 = 2. * g0 * (g0 + 1.);
   double bet = g0 * (g0 + 0.5);
-  double e1 = (xt1 * Q1(1) + Q1(2)) / bet, e2 = (xt1 * Q2(1) + Q2(2)) / bet;
   double gm = (1. + g0 * (g0 + 1.5)) / bet;
-  q1e[o] = e1; q2e[o] = e2; gam[o] = gm;
+  T[3 * km + 0] = 2. * g0 * (g0 + 1.);
+  T[0] = g0; T[km] = bet; T[2 * km] = gm;
   double gk = 0.;
   for (int k = 2; k <= km; k++) {
     gk = dp0[k - 2] / dp0[k - 1];
     bet = 2. + 2. * gk - gm;
-    e1 = (3. * (Q1(k - 1) + gk * Q1(k)) - e1) / bet;
-    e2 = (3. * (Q2(k - 1) + gk * Q2(k)) - e2) / bet;
     gm = gk / bet;
-    const long long ok = o + (long long)(k - 1) * P;
-    q1e[ok] = e1; q2e[ok] = e2; gam[ok] = gm;
+    T[k - 1] = gk; T[km + k - 1] = bet; T[2 * km + k - 1] = gm;
   }
   const double a_bot = 1. + gk * (gk + 1.5);
-  xt1 = 2. * gk * (gk + 1.);
-  const double xt2 = gk * (gk + 0.5) - a_bot * gm;
-  e1 = (xt1 * Q1(km) + Q1(km - 1) - a_bot * e1) / xt2;
-  e2 = (xt1 * Q2(km) + Q2(km - 1) - a_bot * e2) / xt2;
-  q1e[o + (long long)km * P] = e1; q2e[o + (long long)km * P] = e2;
-  for (int k = km; k >= 1; k--) {
-    const long long ok = o + (long long)(k - 1) * P;
-    const double g = gam[ok];
-    e1 = q1e[ok] - g * e1; e2 = q2e[ok] - g * e2;
-    q1e[ok] = e1; q2e[ok] = e2;
+  T[3 * km + 1] = a_bot;
+  T[3 * km + 2] = 2. * gk * (gk + 1.);
+  T[3 * km + 3] = gk * (gk + 0.5) - a_bot * gm;
+}
+__global__ void __launch_bounds__(CB, 8) k_edge_profile(Lay L, const double* __restrict__ q1, const double* __restrict__ q2,
+                                                    double* __restrict__ q1e, double* __restrict__ q2e, const double* __restrict__ T,
+                                                    int i0, int i1, int j0, int j1) {
+  COL_SETUP(i0, i1, j0, j1)
+  const int km = L.npz;
+  constexpr int NBE = 4;
+#define LV(k) (o + (long long)((k)-1) * P)
+  const double* __restrict__ GK = T; const double* __restrict__ BET = T + km; const double* __restrict__ GM = T + 2 * km;
+  double e1, e2, a_prev, b_prev;   // a_prev, b_prev = Q1(k-1), Q2(k-1)
+  {
+    const double a1 = __ldg(q1 + LV(1)), a2 = __ldg(q1 + LV(2)), b1 = __ldg(q2 + LV(1)), b2 = __ldg(q2 + LV(2));
+    const double xt1 = __ldg(T + 3 * km), bet = __ldg(BET);
+    e1 = (xt1 * a1 + a2) / bet; e2 = (xt1 * b1 + b2) / bet;
+    q1e[o] = e1; q2e[o] = e2;
+    a_prev = a1; b_prev = b1;
   }
+  for (int k0 = 2; k0 <= km; k0 += NBE) {
+    double a[NBE], b[NBE];
+#pragma unroll
+    for (int u = 0; u < NBE; u++) { const int kk = min(k0 + u, km); a[u] = __ldg(q1 + LV(kk)); b[u] = __ldg(q2 + LV(kk)); }
+#pragma unroll
+    for (int u = 0; u < NBE; u++) {
+      const int k = k0 + u;
+      if (k > km) break;
+      const double gk = __ldg(GK + k - 1), bet = __ldg(BET + k - 1);
+      e1 = (3. * (a_prev + gk * a[u]) - e1) / bet;
+      e2 = (3. * (b_prev + gk * b[u]) - e2) / bet;
+      q1e[LV(k)] = e1; q2e[LV(k)] = e2;
+      if (k < km) { a_prev = a[u]; b_prev = b[u]; }   // keep Q(km-1) for the bottom edge
+    }
+  }
+  {
+    const double a_bot = __ldg(T + 3 * km + 1), xt1 = __ldg(T + 3 * km + 2), xt2 = __ldg(T + 3 * km + 3);
+    const double akm = __ldg(q1 + LV(km)), bkm = __ldg(q2 + LV(km));
+    e1 = (xt1 * akm + a_prev - a_bot * e1) / xt2;
+    e2 = (xt1 * bkm + b_prev - a_bot * e2) / xt2;
+    q1e[LV(km + 1)] = e1; q2e[LV(km + 1)] = e2;
+  }
+  for (int k0 = km; k0 >= 1; k0 -= NBE) {
+    double a[NBE], b[NBE];
+#pragma unroll
+    for (int u = 0; u < NBE; u++) { const int kk = max(k0 - u, 1); a[u] = q1e[LV(kk)]; b[u] = q2e[LV(kk)]; }
+#pragma unroll
+    for (int u = 0; u < NBE; u++) {
+      const int k = k0 - u;
+      if (k < 1) break;
+      const double g = __ldg(GM + k - 1);
+      e1 = a[u] - g * e1; e2 = b[u] - g * e2;
+      q1e[LV(k)] = e1; q2e[LV(k)] = e2;
+    }
+  }
+#undef LV
 }
 // zh update from the transport fluxes (nh_utils.F90:282-299); del6 term only where damp(k) > 1e-5
 __global__ void __launch_bounds__(TI* TJ) k_dzd_upd(Lay L, DevGrid G, const double* __restrict__ zh, const double* __restrict__ fx,
@@ -630,12 +671,17 @@ int stage_update_dz_d(fv3_ctx* c, double dt) {
   for (int k = 0; k < n1; k++) { ki[k] = c->nord_v[k]; kd[k] = c->damp_vt[k] > 1.E-5 ? c->damp_vt[k] : 0.; any |= kd[k] != 0.; }
   FV3_CUDA(c, cudaMemcpyAsync(c->d_kint + KI_NORD_V * n1, ki.data(), n1 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   FV3_CUDA(c, cudaMemcpyAsync(c->d_kdbl + KD_DZ * n1, kd.data(), n1 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  double *crxa = c->scr[0], *xfxa = c->scr[1], *crya = c->scr[2], *yfxa = c->scr[3], *gam = c->scr[4];
+  double *crxa = c->scr[0], *xfxa = c->scr[1], *crya = c->scr[2], *yfxa = c->scr[3];
   double *fx = c->scr[5], *fy = c->scr[6], *fx2 = c->scr[7], *fy2 = c->scr[8], *q_i = c->scr[9], *q_j = c->scr[10];
   double *zn = c->scr[11], *dfx = c->scr[12], *dfy = c->scr[13], *d2 = c->scr[14];
   const int nix = L.ie + 1 - L.is + 1, njx = L.jed - L.jsd + 1, niy = L.ied - L.isd + 1, njy = L.je + 1 - L.js + 1;
-  k_edge_profile<<<col_blocks(nix, njx), CB, 0, c->stream>>>(L, c->fld[FV3_CRX], c->fld[FV3_XFX], crxa, xfxa, gam, c->d_dp_ref, L.is, L.ie + 1, L.jsd, L.jed);
-  k_edge_profile<<<col_blocks(niy, njy), CB, 0, c->stream>>>(L, c->fld[FV3_CRY], c->fld[FV3_YFX], crya, yfxa, gam, c->d_dp_ref, L.isd, L.ied, L.js, L.je + 1);
+  if (!c->d_edge_tab) {
+    FV3_CUDA(c, cudaMalloc(&c->d_edge_tab, sizeof(double) * (3 * km + 4)));
+    k_edge_tables<<<1, 32, 0, c->stream>>>(c->d_dp_ref, c->d_edge_tab, km);
+    c->launches++;
+  }
+  k_edge_profile<<<col_blocks(nix, njx), CB, 0, c->stream>>>(L, c->fld[FV3_CRX], c->fld[FV3_XFX], crxa, xfxa, c->d_edge_tab, L.is, L.ie + 1, L.jsd, L.jed);
+  k_edge_profile<<<col_blocks(niy, njy), CB, 0, c->stream>>>(L, c->fld[FV3_CRY], c->fld[FV3_YFX], crya, yfxa, c->d_edge_tab, L.isd, L.ied, L.js, L.je + 1);
   c->launches += 2;
   Tp2d tp;
   tp.q = c->fld[FV3_ZH]; tp.crx = crxa; tp.cry = crya; tp.xfx = xfxa; tp.yfx = yfxa; tp.ra_x = nullptr; tp.ra_y = nullptr;
