@@ -36,10 +36,11 @@ constexpr double c1 = -2. / 14., c2 = 11. / 14., c3 = 5. / 14.;
 constexpr double big_number = 1.E30;
 
 // fill_4corners views (sw_core.F90:3496-3555): dir=1 for x-fluxes, dir=2 for y-fluxes
+template <bool E>
 struct FillX {
   const double* q; Lay L;
   __device__ __forceinline__ double operator()(int i, int j) const {
-    if (L.cube) {
+    if (E && L.cube) {
       if (j == 0) {
         if (i == -1) { i = 0; j = 2; } else if (i == 0) { j = 1; }
         else if (i == L.npx + 1) { i = L.npx; j = 2; } else if (i == L.npx) { j = 1; }
@@ -51,10 +52,11 @@ struct FillX {
     return __ldg(q + LIDX(L, i, j));
   }
 };
+template <bool E>
 struct FillY {
   const double* q; Lay L;
   __device__ __forceinline__ double operator()(int i, int j) const {
-    if (L.cube) {
+    if (E && L.cube) {
       if (i == 0) {
         if (j == 0) { i = 1; } else if (j == -1) { i = 2; j = 0; }
         else if (j == L.npy) { i = 1; } else if (j == L.npy + 1) { i = 2; j = L.npy; }
@@ -105,10 +107,11 @@ __global__ void __launch_bounds__(TI* TJ) k_csw_a(Lay L, DevGrid G, const double
 
 namespace {
 // utmp with the A->C x-direction corner rotation (sw_core.F90:3166-3185)
+template <bool E>
 struct UtmpX {
   const double *ut, *vt; Lay L;
   __device__ __forceinline__ double operator()(int i, int j) const {
-    if (L.cube) {
+    if (E && L.cube) {
       if (j == 0) {
         if (i <= 0) return -__ldg(vt + LIDX(L, 0, 1 - i));
         if (i >= L.npx) return __ldg(vt + LIDX(L, L.npx, i - L.npx + 1));
@@ -121,10 +124,11 @@ struct UtmpX {
   }
 };
 // vtmp with the y-direction corner rotation (sw_core.F90:3259-3278)
+template <bool E>
 struct VtmpY {
   const double *ut, *vt; Lay L;
   __device__ __forceinline__ double operator()(int i, int j) const {
-    if (L.cube) {
+    if (E && L.cube) {
       if (i == 0) {
         if (j <= 0) return -__ldg(ut + LIDX(L, 1 - j, 0));
         if (j >= L.npy) return __ldg(ut + LIDX(L, j - L.npy + 1, L.npy));
@@ -137,10 +141,11 @@ struct VtmpY {
   }
 };
 // ua with the corner rotation used by edge_interpolate4 along x (sw_core.F90:3206-3221)
+template <bool E>
 struct UaX {
   const double *ua, *va; Lay L;
   __device__ __forceinline__ double operator()(int i, int j) const {
-    if (L.cube) {
+    if (E && L.cube) {
       if (j == 0) {
         if (i == -1) return -__ldg(va + LIDX(L, 0, 2));
         if (i == 0) return -__ldg(va + LIDX(L, 0, 1));
@@ -157,10 +162,11 @@ struct UaX {
   }
 };
 // va with the corner rotation along y (sw_core.F90:3279-3294); reads the ORIGINAL ua
+template <bool E>
 struct VaY {
   const double *ua, *va; Lay L;
   __device__ __forceinline__ double operator()(int i, int j) const {
-    if (L.cube) {
+    if (E && L.cube) {
       if (i == 0) {
         if (j == -1) return -__ldg(ua + LIDX(L, 2, 0));
         if (j == 0) return -__ldg(ua + LIDX(L, 1, 0));
@@ -179,20 +185,23 @@ struct VaY {
 }  // namespace
 
 // ---- k_c: uc, ut, vc, vt (+ Courant scaling, sw_core.F90:159-176) and divergence_corner ----
-__global__ void __launch_bounds__(TI* TJ, 4) k_csw_c(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
-                                                 const double* __restrict__ utmp_, const double* __restrict__ vtmp_,
-                                                 double* ua_, double* va_,
-                                                 double* __restrict__ uc, double* __restrict__ vc, double* __restrict__ ut,
-                                                 double* __restrict__ vt, double* __restrict__ divg_d, int nord, double dt2) {
-  PLANE_IJK
-  if (i < L.isd || i > L.ied + 1 || j > L.jed + 1) return;
+// E = false: the point is far enough from the face edges (3 <= i <= npx-2, same in j) that no one-sided formula and no
+// corner remap can apply -- the branches and the per-access index tests are compiled out (they were most of the
+// instructions of this kernel: ncu, profiles/r1_stages_ncu_v5.txt)
+template <bool E>
+__device__ __forceinline__ void csw_c_point(const Lay& L, const DevGrid& G, const double* __restrict__ u, const double* __restrict__ v,
+                                            const double* __restrict__ utmp_, const double* __restrict__ vtmp_, double* ua_, double* va_,
+                                            double* __restrict__ uc, double* __restrict__ vc, double* __restrict__ ut,
+                                            double* __restrict__ vt, double* __restrict__ divg_d, int nord, double dt2, int i, int j,
+                                            long long ko) {
   const int npx = L.npx, npy = L.npy;
-  const bool cube = L.cube;
+  const bool cube = E && L.cube;
+  const bool ortho = !L.cube;   // doubly periodic orthogonal grid: vt = vc (sw_core.F90:3296-3303)
   const long long o = ko + LIDX(L, i, j);
-  UtmpX utx{utmp_ + ko, vtmp_ + ko, L};
-  VtmpY vty{utmp_ + ko, vtmp_ + ko, L};
-  UaX uax{ua_ + ko, va_ + ko, L};
-  VaY vay{ua_ + ko, va_ + ko, L};
+  UtmpX<E> utx{utmp_ + ko, vtmp_ + ko, L};
+  VtmpY<E> vty{utmp_ + ko, vtmp_ + ko, L};
+  UaX<E> uax{ua_ + ko, va_ + ko, L};
+  VaY<E> vay{ua_ + ko, va_ + ko, L};
   // x direction: j in [js-1, je+1], i in [is-1, ie+2]
   if (j >= L.js - 1 && j <= L.je + 1 && i >= L.is - 1 && i <= L.ie + 2) {
     double ucv, utv;
@@ -218,16 +227,16 @@ __global__ void __launch_bounds__(TI* TJ, 4) k_csw_c(Lay L, DevGrid G, const dou
   // y direction: j in [js-1, je+2], i in [is-1, ie+1]
   if (j >= L.js - 1 && j <= L.je + 2 && i >= L.is - 1 && i <= L.ie + 1) {
     double vcv, vtv;
-    if (!cube) {
+    if (ortho) {
       vcv = a2 * (vty(i, j - 2) + vty(i, j + 1)) + a1 * (vty(i, j - 1) + vty(i, j));
       vtv = vcv;
-    } else if (j == 1 || j == npy) {
+    } else if (cube && (j == 1 || j == npy)) {
       vtv = edge_interpolate4(vay(i, j - 2), vay(i, j - 1), vay(i, j), vay(i, j + 1), G2(dya, i, j - 2), G2(dya, i, j - 1), G2(dya, i, j),
                               G2(dya, i, j + 1));
       vcv = (vtv > 0.) ? vtv * SG(4, i, j - 1) : vtv * SG(2, i, j);
     } else {
-      if (j == 0 || j == npy - 1) vcv = c1 * vty(i, j - 2) + c2 * vty(i, j - 1) + c3 * vty(i, j);
-      else if (j == 2 || j == npy + 1) vcv = c1 * vty(i, j + 1) + c2 * vty(i, j) + c3 * vty(i, j - 1);
+      if (cube && (j == 0 || j == npy - 1)) vcv = c1 * vty(i, j - 2) + c2 * vty(i, j - 1) + c3 * vty(i, j);
+      else if (cube && (j == 2 || j == npy + 1)) vcv = c1 * vty(i, j + 1) + c2 * vty(i, j) + c3 * vty(i, j - 1);
       else vcv = a2 * (vty(i, j - 2) + vty(i, j + 1)) + a1 * (vty(i, j - 1) + vty(i, j));
       vtv = (vcv - AT(u, i, j) * G2(cosa_v, i, j)) * G2(rsin_v, i, j);
     }
@@ -247,19 +256,21 @@ __global__ void __launch_bounds__(TI* TJ, 4) k_csw_c(Lay L, DevGrid G, const dou
     } else {
       auto uf = [&](int ii, int jj) {
         const double s = 0.5 * (SG(4, ii, jj - 1) + SG(2, ii, jj));
-        if (jj == 1 || jj == npy) return AT(u, ii, jj) * G2(dyc, ii, jj) * s;
+        if (E && (jj == 1 || jj == npy)) return AT(u, ii, jj) * G2(dyc, ii, jj) * s;
         return (AT(u, ii, jj) - 0.25 * (VA(ii, jj - 1) + VA(ii, jj)) * (CG(4, ii, jj - 1) + CG(2, ii, jj))) * G2(dyc, ii, jj) * s;
       };
       auto vf = [&](int ii, int jj) {
         const double s = 0.5 * (SG(3, ii - 1, jj) + SG(1, ii, jj));
-        if (ii == 1 || ii == npx) return AT(v, ii, jj) * G2(dxc, ii, jj) * s;
+        if (E && (ii == 1 || ii == npx)) return AT(v, ii, jj) * G2(dxc, ii, jj) * s;
         return (AT(v, ii, jj) - 0.25 * (UA(ii - 1, jj) + UA(ii, jj)) * (CG(3, ii - 1, jj) + CG(1, ii, jj))) * G2(dxc, ii, jj) * s;
       };
       double d = vf(i, j - 1) - vf(i, j) + uf(i - 1, j) - uf(i, j);
-      if (i == 1 && j == 1) d = d - vf(1, 0);
-      if (i == npx && j == 1) d = d - vf(npx, 0);
-      if (i == npx && j == npy) d = d + vf(npx, npy);
-      if (i == 1 && j == npy) d = d + vf(1, npy);
+      if (E) {
+        if (i == 1 && j == 1) d = d - vf(1, 0);
+        if (i == npx && j == 1) d = d - vf(npx, 0);
+        if (i == npx && j == npy) d = d + vf(npx, npy);
+        if (i == 1 && j == npy) d = d + vf(1, npy);
+      }
       divg_d[o] = G2(rarea_c, i, j) * d;
     }
   }
@@ -273,21 +284,34 @@ __global__ void __launch_bounds__(TI* TJ, 4) k_csw_c(Lay L, DevGrid G, const dou
     if (iy && jy) va_[o] = vay(i, j);
   }
 }
+__global__ void __launch_bounds__(TI* TJ, 4) k_csw_c(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
+                                                 const double* __restrict__ utmp_, const double* __restrict__ vtmp_,
+                                                 double* ua_, double* va_,
+                                                 double* __restrict__ uc, double* __restrict__ vc, double* __restrict__ ut,
+                                                 double* __restrict__ vt, double* __restrict__ divg_d, int nord, double dt2) {
+  PLANE_IJK
+  if (i < L.isd || i > L.ied + 1 || j > L.jed + 1) return;
+  if (L.cube && L.grid_type <= 3 && i >= 3 && i <= L.npx - 2 && j >= 3 && j <= L.npy - 2)
+    csw_c_point<false>(L, G, u, v, utmp_, vtmp_, ua_, va_, uc, vc, ut, vt, divg_d, nord, dt2, i, j, ko);
+  else
+    csw_c_point<true>(L, G, u, v, utmp_, vtmp_, ua_, va_, uc, vc, ut, vt, divg_d, nord, dt2, i, j, ko);
+}
 
 // ---- k_t: delpc, ptc, wc, ke, vort --------------------------------------------------------
-__global__ void __launch_bounds__(TI* TJ) k_csw_t(Lay L, DevGrid G, const double* __restrict__ delp, const double* __restrict__ pt,
-                                                 const double* __restrict__ w, const double* __restrict__ u, const double* __restrict__ v,
-                                                 const double* __restrict__ uc, const double* __restrict__ vc, const double* __restrict__ ua,
-                                                 const double* __restrict__ va, const double* __restrict__ ut, const double* __restrict__ vt,
-                                                 double* __restrict__ delpc, double* __restrict__ ptc, double* __restrict__ wc,
-                                                 double* __restrict__ ke, double* __restrict__ vort, int hydrostatic, double dt2) {
-  PLANE_IJK
-  if (i < L.is - 1 || i > L.ie + 1 || j < L.js - 1 || j > L.je + 1) return;
+template <bool E>
+__device__ __forceinline__ void csw_t_point(const Lay& L, const DevGrid& G, const double* __restrict__ delp, const double* __restrict__ pt,
+                                            const double* __restrict__ w, const double* __restrict__ u, const double* __restrict__ v,
+                                            const double* __restrict__ uc, const double* __restrict__ vc, const double* __restrict__ ua,
+                                            const double* __restrict__ va, const double* __restrict__ ut, const double* __restrict__ vt,
+                                            double* __restrict__ delpc, double* __restrict__ ptc, double* __restrict__ wc,
+                                            double* __restrict__ ke, double* __restrict__ vort, int hydrostatic, double dt2, int i, int j,
+                                            long long ko) {
   const int npx = L.npx, npy = L.npy;
-  const bool cube = L.cube;
+  const bool cube = E && L.cube;
+  const bool ortho = !L.cube;
   const long long o = ko + LIDX(L, i, j);
-  FillX dx_{delp + ko, L}, px_{pt + ko, L}, wx_{w + ko, L};
-  FillY dy_{delp + ko, L}, py_{pt + ko, L}, wy_{w + ko, L};
+  FillX<E> dx_{delp + ko, L}, px_{pt + ko, L}, wx_{w + ko, L};
+  FillY<E> dy_{delp + ko, L}, py_{pt + ko, L}, wy_{w + ko, L};
   // upwind fluxes through the 4 faces (sw_core.F90:214-276)
   double fx1[2], fx[2], fx2[2], fy1[2], fy[2], fy2[2];
 #pragma unroll
@@ -315,7 +339,8 @@ __global__ void __launch_bounds__(TI* TJ) k_csw_t(Lay L, DevGrid G, const double
   // KE (sw_core.F90:297-366)
   const double uav = AT(ua, i, j), vav = AT(va, i, j);
   double kx, ky;
-  if (!cube) {
+  (void)ortho;
+  if (!cube) {   // no face edge nearby (or not a cubed sphere): sw_core.F90:352-366
     kx = (uav > 0.) ? AT(uc, i, j) : AT(uc, i + 1, j);
     ky = (vav > 0.) ? AT(vc, i, j) : AT(vc, i, j + 1);
   } else {
@@ -354,6 +379,19 @@ __global__ void __launch_bounds__(TI* TJ) k_csw_t(Lay L, DevGrid G, const double
     }
     vort[o] = G2(fC, i, j) + G2(rarea_c, i, j) * vo;
   }
+}
+__global__ void __launch_bounds__(TI* TJ) k_csw_t(Lay L, DevGrid G, const double* __restrict__ delp, const double* __restrict__ pt,
+                                                 const double* __restrict__ w, const double* __restrict__ u, const double* __restrict__ v,
+                                                 const double* __restrict__ uc, const double* __restrict__ vc, const double* __restrict__ ua,
+                                                 const double* __restrict__ va, const double* __restrict__ ut, const double* __restrict__ vt,
+                                                 double* __restrict__ delpc, double* __restrict__ ptc, double* __restrict__ wc,
+                                                 double* __restrict__ ke, double* __restrict__ vort, int hydrostatic, double dt2) {
+  PLANE_IJK
+  if (i < L.is - 1 || i > L.ie + 1 || j < L.js - 1 || j > L.je + 1) return;
+  if (L.cube && i >= 3 && i <= L.npx - 2 && j >= 3 && j <= L.npy - 2)
+    csw_t_point<false>(L, G, delp, pt, w, u, v, uc, vc, ua, va, ut, vt, delpc, ptc, wc, ke, vort, hydrostatic, dt2, i, j, ko);
+  else
+    csw_t_point<true>(L, G, delp, pt, w, u, v, uc, vc, ua, va, ut, vt, delpc, ptc, wc, ke, vort, hydrostatic, dt2, i, j, ko);
 }
 
 // ---- k_u: time-centred uc, vc (sw_core.F90:414-486) ---------------------------------------
