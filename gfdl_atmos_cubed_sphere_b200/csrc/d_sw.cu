@@ -667,27 +667,27 @@ __device__ __forceinline__ void weight_by_mass(const Lay& L, DswSmem& S, const t
 
 // FAM: 0 all fields use an unlimited scheme, 1 all monotone, 2 mixed (per-field choice at run time).
 // The fields are a run-time loop around ONE copy of the tile routine (instruction-cache footprint).
-template <int FAM>
-__global__ void __launch_bounds__(tpt::NT, 2) k_dsw_transport(Lay L, DevGrid G, DswTr a) {
+template <int FAM, bool EDGE>
+__global__ void __launch_bounds__(tpt::NT, 2) k_dsw_transport(Lay L, DevGrid G, tpt::TileMap M, DswTr a) {
   using namespace tpt;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DswSmem& S = *reinterpret_cast<DswSmem*>(smem_raw);
-  const Tile T = make_tile(L);
+  const Tile T = make_tile(L, M);
   const int k = blockIdx.z, n1 = L.npz + 1;
   const int c = T.lane, i = T.i0 - 3 + c;   // tile column / global i of this lane
   const bool xcell = c >= 3 && c <= TX + 2 && i <= L.ie;
   const bool lastx = T.i0 + TX > L.ie, lasty = T.j0 + TY > L.je;
   const double c_dp = a.kdbl[KD_DELN * n1 + k], c_t = a.kdbl[KD_DELN_T * n1 + k];
   const bool dwk = a.dw && a.kdbl[KD_DAMP4_W * n1 + k] != 0.;
-  stage_inputs(L, G, S.t, T, a.crx, a.cry, a.xfx, a.yfx);
+  stage_inputs<EDGE>(L, G, S.t, T, a.crx, a.cry, a.xfx, a.yfx);
   double dp[CELL_ITERS], dpn[CELL_ITERS], ra[CELL_ITERS];
 #pragma unroll 1
   for (int f = 0; f < 4; f++) {   // 0 delp (:919-920), 1 w (:984-990), 2 q_con (:992-1000), 3 pt (:1014-1016)
     const double* qf = f == 0 ? a.delp : f == 1 ? a.w : f == 2 ? a.qcon : a.pt;
     if (!qf) continue;
     const int hord = (f == 1) ? a.hord_vt : (f == 3) ? a.hord_tm : a.hord_dp;
-    stage_q(L, S.t, T, qf);
-    tp_compute<FAM>(L, G, S.t, T, nullptr, nullptr, (hord == 10) ? 8 : hord, hord);
+    stage_q<EDGE>(L, S.t, T, qf);
+    tp_compute<FAM, EDGE>(L, G, S.t, T, nullptr, nullptr, (hord == 10) ? 8 : hord, hord);
     if (f == 0) {
       // mass fluxes (+ del-n damping flux) into shared memory and the flux capacitors (:928-940)
 #pragma unroll
@@ -747,8 +747,8 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_dsw_transport(Lay L, DevGrid G, 
 }
 
 // vorticity transport + momentum update (sw_core.F90:1476-1509): u += ke(i)-ke(i+1) + fy, v += ke(j)-ke(j+1) - fx
-template <int FAM>
-__global__ void __launch_bounds__(tpt::NT, 2) k_dsw_vort_uv(Lay L, DevGrid G, const double* __restrict__ vq, const double* __restrict__ crx,
+template <int FAM, bool EDGE>
+__global__ void __launch_bounds__(tpt::NT, 2) k_dsw_vort_uv(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ vq, const double* __restrict__ crx,
                                                           const double* __restrict__ cry, const double* __restrict__ xfx,
                                                           const double* __restrict__ yfx, const double* __restrict__ u,
                                                           const double* __restrict__ v, const double* __restrict__ ke,
@@ -756,10 +756,10 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_dsw_vort_uv(Lay L, DevGrid G, co
   using namespace tpt;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
-  const Tile T = make_tile(L);
-  stage_inputs(L, G, S, T, crx, cry, xfx, yfx);
-  stage_q(L, S, T, vq);
-  tp_compute<FAM>(L, G, S, T, nullptr, nullptr, (hord_vt == 10) ? 8 : hord_vt, hord_vt);
+  const Tile T = make_tile(L, M);
+  stage_inputs<EDGE>(L, G, S, T, crx, cry, xfx, yfx);
+  stage_q<EDGE>(L, S, T, vq);
+  tp_compute<FAM, EDGE>(L, G, S, T, nullptr, nullptr, (hord_vt == 10) ? 8 : hord_vt, hord_vt);
   const bool lastx = T.i0 + TX > L.ie, lasty = T.j0 + TY > L.je;
   u += T.ko; v += T.ko; ke += T.ko; uo += T.ko; vo += T.ko;
   const int c = T.lane - 3, i = T.i0 + c;
@@ -803,11 +803,15 @@ template <int FAM>
 static int launch_transport_t(fv3_ctx* c, const DswTr& a, int nk) {
   static bool attr_set = false;
   if (!attr_set) {
-    FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport<FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DswSmem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport<FAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DswSmem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport<FAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DswSmem)));
     attr_set = true;
   }
-  k_dsw_transport<FAM><<<tpt::tile_grid(c->L, nk), tpt::NT, sizeof(DswSmem), c->stream>>>(c->L, c->G, a);
-  c->launches++;
+  tpt::TileMap Min, Mfr; int n_in, n_fr;
+  tpt::tile_maps(c->L, Min, Mfr, n_in, n_fr);
+  if (n_in) k_dsw_transport<FAM, false><<<dim3(n_in, 1, nk), tpt::NT, sizeof(DswSmem), c->stream>>>(c->L, c->G, Min, a);
+  if (n_fr) k_dsw_transport<FAM, true><<<dim3(n_fr, 1, nk), tpt::NT, sizeof(DswSmem), c->stream>>>(c->L, c->G, Mfr, a);
+  c->launches += (n_in ? 1 : 0) + (n_fr ? 1 : 0);
   return 0;
 }
 static int launch_transport(fv3_ctx* c, const DswTr& a, int nk) {
@@ -818,16 +822,21 @@ static int launch_transport(fv3_ctx* c, const DswTr& a, int nk) {
   if (none_mono) return launch_transport_t<0>(c, a, nk);
   return launch_transport_t<2>(c, a, nk);
 }
-template <int M>
+template <int FM>
 static int launch_vort_uv_t(fv3_ctx* c, const double* vq, const double* u, const double* v, const double* ke, double* uo, double* vo, int nk) {
   static bool attr_set = false;
   if (!attr_set) {
-    FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_vort_uv<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_vort_uv<FM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_vort_uv<FM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
     attr_set = true;
   }
-  k_dsw_vort_uv<M><<<tpt::tile_grid(c->L, nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(
-      c->L, c->G, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, c->f.hord_vt);
-  c->launches++;
+  tpt::TileMap Min, Mfr; int n_in, n_fr;
+  tpt::tile_maps(c->L, Min, Mfr, n_in, n_fr);
+  if (n_in) k_dsw_vort_uv<FM, false><<<dim3(n_in, 1, nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(
+      c->L, c->G, Min, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, c->f.hord_vt);
+  if (n_fr) k_dsw_vort_uv<FM, true><<<dim3(n_fr, 1, nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(
+      c->L, c->G, Mfr, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, c->f.hord_vt);
+  c->launches += (n_in ? 1 : 0) + (n_fr ? 1 : 0);
   return 0;
 }
 

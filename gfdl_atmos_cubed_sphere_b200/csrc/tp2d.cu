@@ -26,8 +26,8 @@ static inline dim3 plane_grid(const Lay& L, int nk) { return dim3((L.NI + TI - 1
 
 // One CTA per TX x TY tile and level: see tp_tile.cuh.  Epilogue: weight by the area flux (or the
 // mass flux, tp_core.F90:213-226) and store the tile's own faces (+ the face's last column / row).
-template <bool MONO>
-__global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, const double* __restrict__ q,
+template <bool MONO, bool EDGE>
+__global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ q,
                                                        const double* __restrict__ crx, const double* __restrict__ cry,
                                                        const double* __restrict__ xfx, const double* __restrict__ yfx,
                                                        const double* __restrict__ ra_x, const double* __restrict__ ra_y,
@@ -36,10 +36,10 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, const
   using namespace tpt;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
-  const Tile T = make_tile(L);
-  stage_inputs(L, G, S, T, crx, cry, xfx, yfx);
-  stage_q(L, S, T, q);
-  tp_compute<MONO ? 1 : 0>(L, G, S, T, ra_x, ra_y, ord_in, ord_ou);
+  const Tile T = make_tile(L, M);
+  stage_inputs<EDGE>(L, G, S, T, crx, cry, xfx, yfx);
+  stage_q<EDGE>(L, S, T, q);
+  tp_compute<MONO ? 1 : 0, EDGE>(L, G, S, T, ra_x, ra_y, ord_in, ord_ou);
   // epilogue: lane = column; the tile stores its own west/south faces, plus the face's last column / row
   const bool lastx = T.i0 + TX > L.ie, lasty = T.j0 + TY > L.je;
   const int c = T.lane - 3, i = T.i0 + c;
@@ -60,18 +60,23 @@ int launch_tp2d(fv3_ctx* c, const Tp2d& a) {
   if (!hord_supported(a.hord)) return fv3_fail(c, -2, "fv_tp_2d: hord " + std::to_string(a.hord) + " not supported on the GPU path (supported: 5, 6, -5, 8, 10)");
   const Lay& L = c->L;
   const int ord_in = (a.hord == 10) ? 8 : a.hord;   // tp_core.F90:136-141
-  const dim3 grd = tpt::tile_grid(L, a.nk);
+  tpt::TileMap Min, Mfr; int n_in, n_fr;
+  tpt::tile_maps(L, Min, Mfr, n_in, n_fr);
   static bool attr_set = false;
   if (!attr_set) {
-    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
-    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
     attr_set = true;
   }
-  if (a.hord >= 8)
-    k_tp_fused<true><<<grd, tpt::NT, sizeof(tpt::Smem), c->stream>>>(L, c->G, a.q, a.crx, a.cry, a.xfx, a.yfx, a.ra_x, a.ra_y, a.mfx, a.mfy, a.fx, a.fy, ord_in, a.hord);
-  else
-    k_tp_fused<false><<<grd, tpt::NT, sizeof(tpt::Smem), c->stream>>>(L, c->G, a.q, a.crx, a.cry, a.xfx, a.yfx, a.ra_x, a.ra_y, a.mfx, a.mfy, a.fx, a.fy, ord_in, a.hord);
-  c->launches += 1;
+#define TP_LAUNCH(MONO, EDGE, M, N)                                                                                          \
+  k_tp_fused<MONO, EDGE><<<dim3(N, 1, a.nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(L, c->G, M, a.q, a.crx, a.cry, a.xfx, a.yfx, \
+                                                                                       a.ra_x, a.ra_y, a.mfx, a.mfy, a.fx, a.fy, ord_in, a.hord)
+  if (a.hord >= 8) { if (n_in) TP_LAUNCH(true, false, Min, n_in); if (n_fr) TP_LAUNCH(true, true, Mfr, n_fr); }
+  else { if (n_in) TP_LAUNCH(false, false, Min, n_in); if (n_fr) TP_LAUNCH(false, true, Mfr, n_fr); }
+#undef TP_LAUNCH
+  c->launches += (n_in ? 1 : 0) + (n_fr ? 1 : 0);
   return 0;
 }
 

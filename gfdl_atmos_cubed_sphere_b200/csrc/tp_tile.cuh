@@ -86,9 +86,18 @@ struct Tile {
   bool corner;         // tile halo overlaps a cube-corner region: q needs the two copy_corners views
   __device__ __forceinline__ int idx(int i, int j) const { return (i + ib) + (j - jb) * NI; }
 };
-__device__ __forceinline__ Tile make_tile(const Lay& L) {
+// Tile coordinates come from a FrameGrid: interior launches (EDGE = false) enumerate the rectangle of tiles whose every
+// flux is an ordinary interior one, frame launches (EDGE = true) the rest (fv3_ctx.hpp).
+struct TileMap { FrameGrid fg; int interior; };
+__device__ __forceinline__ void tile_xy(const TileMap& M, int& bx, int& by) {
+  if (M.interior) { const int nin = M.fg.nbx - M.fg.cl - M.fg.cr; by = blockIdx.x / nin; bx = blockIdx.x - by * nin; bx += M.fg.cl; by += M.fg.a; }
+  else M.fg.map(blockIdx.x, bx, by);
+}
+__device__ __forceinline__ Tile make_tile(const Lay& L, const TileMap& M) {
   Tile T;
-  T.i0 = L.is + blockIdx.x * TX; T.j0 = L.js + blockIdx.y * TY;
+  int bx, by;
+  tile_xy(M, bx, by);
+  T.i0 = L.is + bx * TX; T.j0 = L.js + by * TY;
   T.ko = (long long)blockIdx.z * L.plane;
   T.NI = L.NI; T.ib = FV3_IOFF - L.isd; T.jb = L.jsd;
   T.lane = threadIdx.x & 31; T.wid = threadIdx.x >> 5;
@@ -98,13 +107,14 @@ __device__ __forceinline__ Tile make_tile(const Lay& L) {
 
 // I: issue the per-tile inputs (no wait).  One index per point serves all five arrays; points beyond the padded plane
 // are clamped duplicates (never used by a stored result).
+template <bool EDGE>
 __device__ __forceinline__ void stage_inputs(const Lay& L, const DevGrid& G, Smem& S, const Tile& T,
                                              const double* __restrict__ crx, const double* __restrict__ cry,
                                              const double* __restrict__ xfx, const double* __restrict__ yfx) {
-  const int i = min(T.i0 - 3 + T.lane, L.ied + 1);
+  const int i = EDGE ? min(T.i0 - 3 + T.lane, L.ied + 1) : T.i0 - 3 + T.lane;
 #pragma unroll
   for (int r = T.wid; r < QH; r += NW) {
-    const int o = T.idx(i, min(T.j0 - 3 + r, L.jed + 1));
+    const int o = T.idx(i, EDGE ? min(T.j0 - 3 + r, L.jed + 1) : T.j0 - 3 + r);
     const long long g = T.ko + o;
     cp_async8(&S.crx[r][T.lane], crx + g);
     cp_async8(&S.xfx[r][T.lane], xfx + g);
@@ -115,13 +125,14 @@ __device__ __forceinline__ void stage_inputs(const Lay& L, const DevGrid& G, Sme
 }
 
 // A: issue the halo tile of q (no wait)
+template <bool EDGE>
 __device__ __forceinline__ void stage_q(const Lay& L, Smem& S, const Tile& T, const double* __restrict__ q) {
   q += T.ko;
-  const int i = min(T.i0 - 3 + T.lane, L.ied);
+  const int i = EDGE ? min(T.i0 - 3 + T.lane, L.ied) : T.i0 - 3 + T.lane;
 #pragma unroll
   for (int r = T.wid; r < QH; r += NW) {
-    const int j = min(T.j0 - 3 + r, L.jed);
-    if (T.corner) {
+    const int j = EDGE ? min(T.j0 - 3 + r, L.jed) : T.j0 - 3 + r;
+    if (EDGE && T.corner) {
       S.q[r][T.lane] = ppm::QAccX{q, L, j}(i);
       S.qi[r][T.lane] = ppm::QAccY{q, L, i}(j);
     } else {
@@ -138,22 +149,24 @@ __device__ __forceinline__ void stage_q(const Lay& L, Smem& S, const Tile& T, co
 // the same family (hord 10 runs ord 8 inside, tp_core.F90:136-141).
 // The row loops are deliberately NOT unrolled: the unrolled form of this routine, inlined once per transported field,
 // overflowed the instruction cache (ncu: 23 % of the stall samples were no_instruction).
-template <int FAM>
+// EDGE = false (interior tiles): every face of the tile, halo faces included, is an ordinary interior face and the tile
+// lies inside the face -- the cube-edge operator, the copy_corners views and all bound tests are compiled out.
+template <int FAM, bool EDGE>
 __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem& S, const Tile& T,
                                            const double* __restrict__ ra_x, const double* __restrict__ ra_y,
                                            int ord_in, int ord_ou) {
   using namespace ppm;
   const bool mono = (FAM == 2) ? (ord_ou >= 8) : (FAM == 1);
-  const bool cube = L.cube;
+  const bool cube = EDGE && L.cube;
   const int npx = L.npx, npy = L.npy, i0 = T.i0, j0 = T.j0, c = T.lane, wid = T.wid;
   const int i = i0 - 3 + c;                                     // this lane's column (cell / west-face index)
-  const bool xface = c >= 3 && c <= TX + 3 && i <= L.ie + 1;    // lane owns a west face that is needed
-  const bool xcell = c >= 3 && c <= TX + 2 && i <= L.ie;        // lane owns a cell of the tile
+  const bool xface = c >= 3 && c <= TX + 3 && (!EDGE || i <= L.ie + 1);    // lane owns a west face that is needed
+  const bool xcell = c >= 3 && c <= TX + 2 && (!EDGE || i <= L.ie);        // lane owns a cell of the tile
   const bool xfast = !cube || (i >= 4 && i <= npx - 3);
   const int cm2 = max(c - 2, 0), cm1 = max(c - 1, 0), cp1 = min(c + 1, QW - 1);
   cp_async_wait_all();
   __syncthreads();
-  const double(*qy)[QW] = T.corner ? S.qi : S.q;
+  const double(*qy)[QW] = (EDGE && T.corner) ? S.qi : S.q;
   // ---- B0: per-point limiter inputs of both sweeps (border points are clamped garbage that no face reads)
 #pragma unroll
   for (int r = wid; r < QH; r += NW) {
@@ -167,14 +180,14 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
   for (int t = wid; t < QH + TY + 1; t += NW) {
     if (t < QH) {
       const int r = t, j = j0 - 3 + r;
-      if (xface && j <= L.jed) {
+      if (xface && (!EDGE || j <= L.jed)) {
         const double cr = S.crx[r][c];
         S.fx2[r][c] = xfast ? line_flux(mono, &S.q[r][c], 1, &S.ax[r][c], 1, cr, ord_in)
                             : edge_flux(&S.q[r][0], 1, i0 - 3, G.dxa, LIDX(L, 0, j), 1, i, cr, ord_in, npx);
       }
     } else {
       const int r = t - QH + 3, j = j0 - 3 + r;
-      if (j <= L.je + 1 && i <= L.ied) {
+      if (!EDGE || (j <= L.je + 1 && i <= L.ied)) {
         const double cr = S.cry[r][c];
         S.fy2[r][c] = (!cube || (j >= 4 && j <= npy - 3)) ? line_flux(mono, &qy[r][c], QW, &S.ay[r][c], QW, cr, ord_in)
                                                           : edge_flux(&qy[0][c], QW, j0 - 3, G.dya, LIDX(L, i, 0), L.NI, j, cr, ord_in, npy);
@@ -187,7 +200,7 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
   for (int t = wid; t < TY + QH; t += NW) {
     if (t < TY) {
       const int r = t + 3, j = j0 - 3 + r;
-      if (j <= L.je && i <= L.ied) {
+      if (!EDGE || (j <= L.je && i <= L.ied)) {
         const double ar = S.area[r][c];
         const double y0 = S.yfx[r][c], y1 = S.yfx[r + 1][c];
         const double f0 = y0 * S.fy2[r][c], f1 = y1 * S.fy2[r + 1][c];
@@ -196,7 +209,7 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
       }
     } else {
       const int r = t - TY, j = j0 - 3 + r;
-      if (xcell && j <= L.jed) {
+      if (xcell && (!EDGE || j <= L.jed)) {
         const double ar = S.area[r][c];
         const double x0 = S.xfx[r][c], x1 = S.xfx[r][c + 1];
         const double f0 = x0 * S.fx2[r][c], f1 = x1 * S.fx2[r][c + 1];
@@ -224,7 +237,7 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
   for (int t = wid; t < TY + TY + 1; t += NW) {
     if (t < TY) {
       const int r = t + 3, j = j0 - 3 + r;
-      if (xface && j <= L.je) {
+      if (xface && (!EDGE || j <= L.je)) {
         const double cr = S.crx[r][c];
         const double f = xfast ? line_flux(mono, &S.qi[r][c], 1, &S.ax[r][c], 1, cr, ord_ou)
                                : edge_flux(&S.qi[r][0], 1, i0 - 3, G.dxa, LIDX(L, 0, j), 1, i, cr, ord_ou, npx);
@@ -232,7 +245,7 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
       }
     } else {
       const int r = t - TY + 3, j = j0 - 3 + r;
-      if (xcell && j <= L.je + 1) {
+      if (xcell && (!EDGE || j <= L.je + 1)) {
         const double cr = S.cry[r][c];
         const double f = (!cube || (j >= 4 && j <= npy - 3)) ? line_flux(mono, &S.qj[r][c], QW, &S.ay[r][c], QW, cr, ord_ou)
                                                              : edge_flux(&S.qj[0][c], QW, j0 - 3, G.dya, LIDX(L, i, 0), L.NI, j, cr, ord_ou, npy);
@@ -243,9 +256,28 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
   __syncthreads();
 }
 
-static inline dim3 tile_grid(const Lay& L, int nk) {
+// tile maps of a face: the interior rectangle (tiles with 4 <= every face index <= npx-3 and the whole halo inside the
+// data domain) and the frame around it
+static inline void tile_maps(const Lay& L, TileMap& in, TileMap& fr, int& n_in, int& n_fr) {
   const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;
-  return dim3((nx + TX - 1) / TX, (ny + TY - 1) / TY, nk);
+  FrameGrid f;
+  f.nbx = (nx + TX - 1) / TX; f.nby = (ny + TY - 1) / TY;
+  int cl = 0, cr = 0, a = 0, bt = 0;
+  if (L.cube) {
+    while (cl < f.nbx && L.is + cl * TX < 4) cl++;
+    while (cr < f.nbx - cl && L.is + (f.nbx - cr) * TX > L.npx - 3) cr++;
+    while (a < f.nby && L.js + a * TY < 4) a++;
+    while (bt < f.nby - a && L.js + (f.nby - bt) * TY > L.npy - 3) bt++;
+  } else {   // doubly periodic: only the tiles that overhang the face need the bound tests
+    while (cr < f.nbx && L.is + (f.nbx - cr) * TX - 1 > L.ie) cr++;
+    while (bt < f.nby && L.js + (f.nby - bt) * TY - 1 > L.je) bt++;
+  }
+  f.cl = cl; f.cr = cr; f.a = a; f.b = f.nby - bt;
+  const int nin_x = f.nbx - cl - cr, nin_y = f.b - f.a;
+  n_in = (nin_x > 0 && nin_y > 0) ? nin_x * nin_y : 0;
+  if (n_in == 0) { f.cl = f.nbx; f.cr = 0; f.a = f.nby; f.b = f.nby; }   // everything is frame
+  in.fg = f; in.interior = 1; fr.fg = f; fr.interior = 0;
+  n_fr = f.count();
 }
 
 }  // namespace tpt
