@@ -175,9 +175,11 @@ __global__ void __launch_bounds__(TI* TJ, 4) k_dsw_wind(Lay L, DevGrid G, const 
   if (i < L.isd || i > L.ied + 1 || j > L.jed + 1) return;
   WindCtx W{uc, vc, L, G, ko, dt};
   const long long o = ko + LIDX(L, i, j);
+  // away from the face edges the closed-form edge / corner cases cannot apply: plain interior formulas, no call
+  const bool inner = L.cube && i >= 3 && i <= L.npx - 2 && j >= 3 && j <= L.npy - 2;
   // ut on (is-1:ie+2, jsd:jed)
   if (j <= L.jed && i >= L.is - 1 && i <= L.ie + 2) {
-    const double ut = W.ut_final(i, j);
+    const double ut = inner ? W.UTg(i, j) : W.ut_final(i, j);
     uts[o] = ut;
     if (i >= L.is && i <= L.ie + 1) {  // :863-890, :923-927
       double xf = dt * ut, cr;
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(TI* TJ, 4) k_dsw_wind(Lay L, DevGrid G, const 
   }
   // vt on (isd:ied, js-1:je+2)
   if (i <= L.ied && j >= L.js - 1 && j <= L.je + 2) {
-    const double vt = W.vt_final(i, j);
+    const double vt = inner ? W.VTg(i, j) : W.vt_final(i, j);
     vts[o] = vt;
     if (j >= L.js && j <= L.je + 1) {  // :869-902, :933-936
       double yf = dt * vt, cr;
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_dd_uv(Lay L, DevGrid G, const do
   const int nord = kint[KI_NORD * (L.npz + 1) + k];
   if (n > nord) return;
   const int nt = nord - n;
-  const bool fill_c = (nt != 0) && L.cube;
+  const bool fill_c = (nt != 0) && L.cube && (i < 4 || i > L.npx - 4) && (j < 4 || j > L.npy - 4);   // remaps exist in the corner regions only
   if (i >= L.is - 1 - nt && i <= L.ie + 1 + nt && j >= L.js - nt && j <= L.je + 1 + nt) {
     BFillX d{dg + ko, L, fill_c};
     vcs[ko + LIDX(L, i, j)] = (d(i + 1, j) - d(i, j)) * G2(divg_u, i, j);
@@ -400,8 +402,8 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_dd_div(Lay L, DevGrid G, const d
   if (n > nord) return;
   const int nt = nord - n;
   if (i < L.is - nt || i > L.ie + 1 + nt || j < L.js - nt || j > L.je + 1 + nt) return;
-  const bool fill_c = (nt != 0) && L.cube;
   const int npx = L.npx, npy = L.npy;
+  const bool fill_c = (nt != 0) && L.cube && (i < 4 || i > npx - 4) && (j < 4 || j > npy - 4);   // remaps exist in the corner regions only
   const double s = -1.0;
   // x = vc (u-like), y = uc (v-like): fv_mp_mod.F90:1262-1277
   auto VCv = [&](int ii, int jj) -> double {
