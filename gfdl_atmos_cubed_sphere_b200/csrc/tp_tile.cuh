@@ -164,6 +164,16 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
   const bool xcell = c >= 3 && c <= TX + 2 && (!EDGE || i <= L.ie);        // lane owns a cell of the tile
   const bool xfast = !cube || (i >= 4 && i <= npx - 3);
   const int cm2 = max(c - 2, 0), cm1 = max(c - 1, 0), cp1 = min(c + 1, QW - 1);
+  // the tile's x faces that need the cube-edge operator: columns 3..2+nwc (faces i <= 3) and ce0..ce0+nec-nwc-1
+  // (faces npx-2 <= i <= npx).  They are evaluated in a separate dense pass: in the row-per-warp loops they would keep
+  // 3 lanes of every row busy with the long out-of-line operator while 29 wait (the frame tiles ran 2x slower per
+  // tile than the interior ones: profiles/r1_dsw_ncu_summary.md, v6).
+  int nwc = 0, ce0 = 0, nec = 0;
+  if (EDGE && cube) {
+    nwc = max(0, min(TX + 3, 6 - i0) - 2);
+    ce0 = max(3, npx + 1 - i0);
+    nec = nwc + max(0, min(TX + 3, npx + 3 - i0) - ce0 + 1);
+  }
   cp_async_wait_all();
   __syncthreads();
   const double(*qy)[QW] = (EDGE && T.corner) ? S.qi : S.q;
@@ -180,11 +190,7 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
   for (int t = wid; t < QH + TY + 1; t += NW) {
     if (t < QH) {
       const int r = t, j = j0 - 3 + r;
-      if (xface && (!EDGE || j <= L.jed)) {
-        const double cr = S.crx[r][c];
-        S.fx2[r][c] = xfast ? line_flux(mono, &S.q[r][c], 1, &S.ax[r][c], 1, cr, ord_in)
-                            : edge_flux(&S.q[r][0], 1, i0 - 3, G.dxa, LIDX(L, 0, j), 1, i, cr, ord_in, npx);
-      }
+      if (xface && xfast && (!EDGE || j <= L.jed)) S.fx2[r][c] = line_flux(mono, &S.q[r][c], 1, &S.ax[r][c], 1, S.crx[r][c], ord_in);
     } else {
       const int r = t - QH + 3, j = j0 - 3 + r;
       if (!EDGE || (j <= L.je + 1 && i <= L.ied)) {
@@ -192,6 +198,12 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
         S.fy2[r][c] = (!cube || (j >= 4 && j <= npy - 3)) ? line_flux(mono, &qy[r][c], QW, &S.ay[r][c], QW, cr, ord_in)
                                                           : edge_flux(&qy[0][c], QW, j0 - 3, G.dya, LIDX(L, i, 0), L.NI, j, cr, ord_in, npy);
       }
+    }
+  }
+  if (EDGE && nec > 0) {   // cube-edge x faces of all rows, densely packed over the CTA
+    for (int e = threadIdx.x; e < QH * nec; e += NT) {
+      const int r = e / nec, ci = e - r * nec, cc = ci < nwc ? 3 + ci : ce0 + (ci - nwc), j = j0 - 3 + r;
+      if (j <= L.jed) S.fx2[r][cc] = edge_flux(&S.q[r][0], 1, i0 - 3, G.dxa, LIDX(L, 0, j), 1, i0 - 3 + cc, S.crx[r][cc], ord_in, npx);
     }
   }
   __syncthreads();
@@ -237,12 +249,8 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
   for (int t = wid; t < TY + TY + 1; t += NW) {
     if (t < TY) {
       const int r = t + 3, j = j0 - 3 + r;
-      if (xface && (!EDGE || j <= L.je)) {
-        const double cr = S.crx[r][c];
-        const double f = xfast ? line_flux(mono, &S.qi[r][c], 1, &S.ax[r][c], 1, cr, ord_ou)
-                               : edge_flux(&S.qi[r][0], 1, i0 - 3, G.dxa, LIDX(L, 0, j), 1, i, cr, ord_ou, npx);
-        S.fx2[r][c] = 0.5 * (f + S.fx2[r][c]);
-      }
+      if (xface && xfast && (!EDGE || j <= L.je))
+        S.fx2[r][c] = 0.5 * (line_flux(mono, &S.qi[r][c], 1, &S.ax[r][c], 1, S.crx[r][c], ord_ou) + S.fx2[r][c]);
     } else {
       const int r = t - TY + 3, j = j0 - 3 + r;
       if (xcell && (!EDGE || j <= L.je + 1)) {
@@ -251,6 +259,13 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
                                                              : edge_flux(&S.qj[0][c], QW, j0 - 3, G.dya, LIDX(L, i, 0), L.NI, j, cr, ord_ou, npy);
         S.fy2[r][c] = 0.5 * (f + S.fy2[r][c]);
       }
+    }
+  }
+  if (EDGE && nec > 0) {
+    for (int e = threadIdx.x; e < TY * nec; e += NT) {
+      const int r = 3 + e / nec, ci = e - (r - 3) * nec, cc = ci < nwc ? 3 + ci : ce0 + (ci - nwc), j = j0 - 3 + r;
+      if (j <= L.je)
+        S.fx2[r][cc] = 0.5 * (edge_flux(&S.qi[r][0], 1, i0 - 3, G.dxa, LIDX(L, 0, j), 1, i0 - 3 + cc, S.crx[r][cc], ord_ou, npx) + S.fx2[r][cc]);
     }
   }
   __syncthreads();
