@@ -240,12 +240,17 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_ptdp(Lay L, DevGrid G, const dou
 // w damping increment and heating (sw_core.F90:951-982); hs = heat_s work plane, ds = diss_e
 __global__ void __launch_bounds__(TI* TJ) k_dsw_dw(Lay L, DevGrid G, const double* __restrict__ w, const double* __restrict__ fx2,
                                                   const double* __restrict__ fy2, double* __restrict__ dw, double* __restrict__ hs,
-                                                  double* __restrict__ ds, const double* kdbl, double kgb, double dt, int prevent, int do_diss) {
-  PLANE_IJK
+                                                  double* __restrict__ ds, const double* kdbl, double kgb, double dt, int prevent, int do_diss,
+                                                  int need_hs, int kofs) {
+  const int i = L.isd - FV3_IOFF + blockIdx.x * TI + threadIdx.x;
+  const int j = L.jsd + blockIdx.y * TJ + threadIdx.y;
+  const int k = blockIdx.z + kofs;
+  const long long ko = (long long)k * L.plane;
   if (i < L.is || i > L.ie || j < L.js || j > L.je) return;
   const long long o = ko + LIDX(L, i, j);
   const double coef = kdbl[KD_DAMP4_W * (L.npz + 1) + k];
-  if (coef == 0.) { dw[o] = 0.; hs[o] = 0.; ds[o] = 0.; return; }
+  // levels without w damping: dw is never read (the transport tests the same coefficient); hs, ds only by k_dsw_heat
+  if (coef == 0.) { if (need_hs) { hs[o] = 0.; ds[o] = 0.; } return; }
   const double dd8 = kgb * fabs(dt);
   const double d = (fx2[o] - fx2[o + 1] + fy2[o] - fy2[o + L.NI]) * G2(rarea, i, j);
   dw[o] = d;
@@ -882,6 +887,11 @@ int stage_d_sw(fv3_ctx* c, double dt) {
   // --- del-n damping fluxes of delp, w, q_con, pt (wide stencils: separate launches), then ONE fused transport
   Deln dl;
   dl.d2 = d2; dl.nk = nk; dl.thresh = 0; dl.nord_const = 0; dl.damp_const = 0;
+  auto level_range = [&](Deln& d, int slot_nord, int slot_damp) {   // levels with a nonzero coefficient, and their largest order
+    d.k_lo = nk; d.k_hi = -1; d.nord_max = 0;
+    for (int k = 0; k < nk; k++)
+      if (kd[slot_damp * n1 + k] != 0.) { d.k_lo = std::min(d.k_lo, k); d.k_hi = std::max(d.k_hi, k); d.nord_max = std::max(d.nord_max, ki[slot_nord * n1 + k]); }
+  };
   const bool nonhydro = !f.hydrostatic;
   DswTr tr{};
   tr.delp = delp; tr.pt = pt; tr.w = nonhydro ? w : nullptr; tr.qcon = f.use_cond ? c->fld[FV3_QCON] : nullptr;
@@ -890,29 +900,37 @@ int stage_d_sw(fv3_ctx* c, double dt) {
   tr.mfx = c->fld[FV3_MFX]; tr.mfy = c->fld[FV3_MFY]; tr.kdbl = c->d_kdbl;
   tr.hord_dp = f.hord_dp; tr.hord_vt = f.hord_vt; tr.hord_tm = f.hord_tm;
   if (any_deln) {   // delp (:919-920)
-    dl.q = delp; dl.fx2 = dfx; dl.fy2 = dfy; dl.slot_nord = KI_NORD_V; dl.slot_damp = KD_DELN; dl.premul = 1;
+    dl.q = delp; dl.fx2 = dfx; dl.fy2 = dfy; dl.slot_nord = KI_NORD_V; dl.slot_damp = KD_DELN; level_range(dl, KI_NORD_V, KD_DELN); dl.premul = 1;
     launch_deln(c, dl);
     tr.dpx = dfx; tr.dpy = dfy;
   }
   if (nonhydro) {   // w (:950-990)
     if (any_w) {
-      dl.q = w; dl.fx2 = fx2; dl.fy2 = fy2; dl.slot_nord = KI_NORD_W; dl.slot_damp = KD_DAMP4_W; dl.premul = 1;
+      dl.q = w; dl.fx2 = fx2; dl.fy2 = fy2; dl.slot_nord = KI_NORD_W; dl.slot_damp = KD_DAMP4_W; level_range(dl, KI_NORD_W, KD_DAMP4_W); dl.premul = 1;
       launch_deln(c, dl);
       tr.dw = dw;
     }
-    k_dsw_dw<<<grd, blk, 0, st>>>(L, c->G, w, fx2, fy2, dw, hs, ds, c->d_kdbl, f.ke_bg, dt, f.prevent_diss_cooling, f.do_diss_est);
-    c->launches++;
+    {
+      const int need_hs = (f.d_con > 1.e-5 || f.do_diss_est) ? 1 : 0;
+      Deln r; level_range(r, KI_NORD_W, KD_DAMP4_W);
+      const int k_lo = need_hs ? 0 : r.k_lo, k_hi = need_hs ? nk - 1 : r.k_hi;
+      if (k_hi >= k_lo) {
+        k_dsw_dw<<<plane_grid(L, k_hi - k_lo + 1), blk, 0, st>>>(L, c->G, w, fx2, fy2, dw, hs, ds, c->d_kdbl, f.ke_bg, dt, f.prevent_diss_cooling,
+                                                              f.do_diss_est, need_hs, k_lo);
+        c->launches++;
+      }
+    }
   } else {
     FV3_CUDA(c, cudaMemsetAsync(hs, 0, (size_t)L.plane * nk * sizeof(double), st));
     FV3_CUDA(c, cudaMemsetAsync(ds, 0, (size_t)L.plane * nk * sizeof(double), st));
   }
   if (f.use_cond && any_deln_t) {   // q_con (:992-1000)
-    dl.q = c->fld[FV3_QCON]; dl.fx2 = q_i; dl.fy2 = q_j; dl.slot_nord = KI_NORD_T; dl.slot_damp = KD_DELN_T; dl.premul = 0;
+    dl.q = c->fld[FV3_QCON]; dl.fx2 = q_i; dl.fy2 = q_j; dl.slot_nord = KI_NORD_T; dl.slot_damp = KD_DELN_T; level_range(dl, KI_NORD_T, KD_DELN_T); dl.premul = 0;
     launch_deln(c, dl);
     tr.qcx = q_i; tr.qcy = q_j;
   }
   if (any_deln_t) {   // pt (:1014-1016)
-    dl.q = pt; dl.fx2 = fx; dl.fy2 = fy; dl.slot_nord = KI_NORD_T; dl.slot_damp = KD_DELN_T; dl.premul = 0;
+    dl.q = pt; dl.fx2 = fx; dl.fy2 = fy; dl.slot_nord = KI_NORD_T; dl.slot_damp = KD_DELN_T; level_range(dl, KI_NORD_T, KD_DELN_T); dl.premul = 0;
     launch_deln(c, dl);
     tr.ptx = fx; tr.pty = fy;
   }
@@ -968,7 +986,7 @@ int stage_d_sw(fv3_ctx* c, double dt) {
   }
   // --- vorticity damping + dissipative heating (:1513-1600)
   if (any_v) {
-    dl.q = wk; dl.fx2 = dfx; dl.fy2 = dfy; dl.slot_nord = KI_NORD_V; dl.slot_damp = KD_DAMP4_V; dl.premul = 1;
+    dl.q = wk; dl.fx2 = dfx; dl.fy2 = dfy; dl.slot_nord = KI_NORD_V; dl.slot_damp = KD_DAMP4_V; level_range(dl, KI_NORD_V, KD_DAMP4_V); dl.premul = 1;
     launch_deln(c, dl);   // dfx = "ut", dfy = "vt"
   }
   if (f.d_con > 1.e-5 || f.do_diss_est) {

@@ -692,6 +692,9 @@ int stage_update_dz_d(fv3_ctx* c, double dt) {
     Deln dl;
     dl.q = c->fld[FV3_ZH]; dl.fx2 = dfx; dl.fy2 = dfy; dl.d2 = d2; dl.slot_nord = KI_NORD_V; dl.slot_damp = KD_DZ; dl.thresh = 0;
     dl.premul = 1; dl.nk = n1; dl.nord_const = 0; dl.damp_const = 0;
+    dl.k_lo = n1; dl.k_hi = -1; dl.nord_max = 0;
+    for (int k = 0; k < n1; k++)
+      if (kd[k] != 0.) { dl.k_lo = std::min(dl.k_lo, k); dl.k_hi = std::max(dl.k_hi, k); dl.nord_max = std::max(dl.nord_max, ki[k]); }
     launch_deln(c, dl);
   }
   dim3 blk(TI, TJ), grd((L.NI + TI - 1) / TI, (L.NJ + TJ - 1) / TJ, n1);

@@ -18,11 +18,12 @@ using namespace ppm;
 
 static inline dim3 plane_grid(const Lay& L, int nk) { return dim3((L.NI + TI - 1) / TI, (L.NJ + TJ - 1) / TJ, nk); }
 
-#define PLANE_IJK                                              \
+#define PLANE_IJK_OFS(kofs)                                    \
   const int i = L.isd - FV3_IOFF + blockIdx.x * TI + threadIdx.x; \
   const int j = L.jsd + blockIdx.y * TJ + threadIdx.y;          \
-  const int k = blockIdx.z;                                     \
+  const int k = blockIdx.z + (kofs);                            \
   const long long ko = (long long)k * L.plane;
+#define PLANE_IJK PLANE_IJK_OFS(0)
 
 // One CTA per TX x TY tile and level: see tp_tile.cuh.  Epilogue: weight by the area flux (or the
 // mass flux, tp_core.F90:213-226) and store the tile's own faces (+ the face's last column / row).
@@ -89,8 +90,8 @@ __device__ __forceinline__ void kparams(const int* kint, const double* kdbl, int
 
 __global__ void __launch_bounds__(TI* TJ) k_deln_first(Lay L, DevGrid G, const double* __restrict__ q, double* __restrict__ fx2,
                                                       double* __restrict__ fy2, const int* kint, const double* kdbl, int slot_nord,
-                                                      int slot_damp, int nord_const, double damp_const, int premul) {
-  PLANE_IJK
+                                                      int slot_damp, int nord_const, double damp_const, int premul, int kofs) {
+  PLANE_IJK_OFS(kofs)
   int nord; double coef;
   kparams(kint, kdbl, L.npz + 1, slot_nord, slot_damp, k, nord_const, damp_const, nord, coef);
   if (coef == 0.) return;
@@ -107,8 +108,8 @@ __global__ void __launch_bounds__(TI* TJ) k_deln_first(Lay L, DevGrid G, const d
 
 __global__ void __launch_bounds__(TI* TJ) k_deln_d2(Lay L, DevGrid G, const double* __restrict__ fx2, const double* __restrict__ fy2,
                                                    double* __restrict__ d2, const int* kint, const double* kdbl, int slot_nord,
-                                                   int slot_damp, int nord_const, double damp_const, int n) {
-  PLANE_IJK
+                                                   int slot_damp, int nord_const, double damp_const, int n, int kofs) {
+  PLANE_IJK_OFS(kofs)
   int nord; double coef;
   kparams(kint, kdbl, L.npz + 1, slot_nord, slot_damp, k, nord_const, damp_const, nord, coef);
   if (coef == 0. || n > nord) return;
@@ -120,8 +121,8 @@ __global__ void __launch_bounds__(TI* TJ) k_deln_d2(Lay L, DevGrid G, const doub
 
 __global__ void __launch_bounds__(TI* TJ) k_deln_flux(Lay L, DevGrid G, const double* __restrict__ d2, double* __restrict__ fx2,
                                                      double* __restrict__ fy2, const int* kint, const double* kdbl, int slot_nord,
-                                                     int slot_damp, int nord_const, double damp_const, int n) {
-  PLANE_IJK
+                                                     int slot_damp, int nord_const, double damp_const, int n, int kofs) {
+  PLANE_IJK_OFS(kofs)
   int nord; double coef;
   kparams(kint, kdbl, L.npz + 1, slot_nord, slot_damp, k, nord_const, damp_const, nord, coef);
   if (coef == 0. || n > nord) return;
@@ -138,21 +139,17 @@ __global__ void __launch_bounds__(TI* TJ) k_deln_flux(Lay L, DevGrid G, const do
 
 int launch_deln(fv3_ctx* c, const Deln& a) {
   const Lay& L = c->L;
-  dim3 blk(TI, TJ), grd = plane_grid(L, a.nk);
-  int nmax = a.nord_const;
-  if (a.slot_nord >= 0) {
-    nmax = 0;
-    // host copy of the per-k nord table lives in ctx (kept in sync by the d_sw prologue)
-    nmax = 2;
-  }
+  const int k_lo = a.k_hi >= a.k_lo ? a.k_lo : 0, k_hi = a.k_hi >= a.k_lo ? a.k_hi : a.nk - 1;
+  dim3 blk(TI, TJ), grd = plane_grid(L, k_hi - k_lo + 1);
+  const int nmax = a.nord_max >= 0 ? a.nord_max : (a.slot_nord >= 0 ? 2 : a.nord_const);
   k_deln_first<<<grd, blk, 0, c->stream>>>(L, c->G, a.q, a.fx2, a.fy2, c->d_kint, c->d_kdbl, a.slot_nord, a.slot_damp,
-                                           a.nord_const, a.damp_const, a.premul);
+                                           a.nord_const, a.damp_const, a.premul, k_lo);
   c->launches++;
   for (int n = 1; n <= nmax; n++) {
     k_deln_d2<<<grd, blk, 0, c->stream>>>(L, c->G, a.fx2, a.fy2, a.d2, c->d_kint, c->d_kdbl, a.slot_nord, a.slot_damp,
-                                          a.nord_const, a.damp_const, n);
+                                          a.nord_const, a.damp_const, n, k_lo);
     k_deln_flux<<<grd, blk, 0, c->stream>>>(L, c->G, a.d2, a.fx2, a.fy2, c->d_kint, c->d_kdbl, a.slot_nord, a.slot_damp,
-                                            a.nord_const, a.damp_const, n);
+                                            a.nord_const, a.damp_const, n, k_lo);
     c->launches += 2;
   }
   return 0;

@@ -1,9 +1,9 @@
 """Per-source-line warp-instruction counts of one kernel from an ncu report (needs -lineinfo and --import-source on).
 usage: python profiles/ncu_lines.py report.ncu-rep kernel-regex [top]"""
 import csv, io, subprocess, sys, collections
-rep, rx = sys.argv[1], sys.argv[2]
+rep, rx = sys.argv[1], sys.argv[2]   # rx: kernel-name regex, or id:<n> for the n-th profiled launch
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + rx],
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", *(["--kernel-id", ":::" + rx[3:]] if rx.startswith("id:") else ["--kernel-name", "regex:" + rx])],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 fname, seen_fn, hdr = None, None, None
