@@ -34,8 +34,9 @@ METRIC = "dyn_core cell-updates/sec (nx*ny*nz*n_split/s) at C384L79; d_sw HBM GB
 from gfdl_atmos_cubed_sphere_b200.parallel import tiles_of_rank, tile_rank_map  # noqa: E402
 
 
-# dram__bytes_read+write summed over the kernels of one d_sw call (ncu --set full, profiles/): filled per round
-DSW_DRAM_TRAFFIC = {}
+# dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of ONE d_sw call on one face (bytes), from the ncu
+# metrics list profiles/r1_dsw_traffic_v7.csv (python profiles/dsw_traffic.py); key = (res, npz, flag-set)
+DSW_DRAM_TRAFFIC = {(384, 79, "A"): 6.210e9}
 
 
 def dsw_algorithmic_bytes(n, npz, use_cond=False, d_con=False):
@@ -217,9 +218,12 @@ def run_ours(args):
         for t in my_tiles:
             lib[0].fv3_stage_timers(cube.eng[t].ctx, 0)
     tt = torch.tensor([t_wall], dtype=torch.float64, device="cuda")
+    ln = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)   # kernels launched by ALL ranks inside the timed region
     t_max = float(tt.item())
+    launches = int(ln.item())
     # ---- roofline leg: the dominant stage (d_sw, batched over k) on ONE face with nothing else in
     # flight, CUDA events on its launch stream.  (The per-stage timers above overlap the 6 face streams,
     # so they give shares of the step, not kernel durations.)
@@ -282,7 +286,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(hb[1].item())},
             "roofline": {"bound": "hbm", "kernel": "d_sw (all kernels of one batched-over-k d_sw call on one face)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": DSW_DRAM_TRAFFIC.get((n, npz)), "peak_source": which, "algorithmic_bytes_per_launch": alg,
+                         "traffic": DSW_DRAM_TRAFFIC.get((n, npz, args.flagset)), "peak_source": which, "algorithmic_bytes_per_launch": alg,
                          "ms_per_launch": dsw_solo_ms,
                          "launch": "one fv3_d_sw call = every kernel of d_sw for all npz levels of one face"},
             "stage_ms_per_call": {k: (v[0] / v[1] if v[1] else None) for k, v in stage_ms.items()},

@@ -23,4 +23,4 @@ for r in rows[2:]:
     v = [r[i] for i in ix]
     t = f(v[0]) * scale.get(units[ix[0]], 1.0)
     rd = f(v[1]) * bscale.get(units[ix[1]], 1.0); wr = f(v[2]) * bscale.get(units[ix[2]], 1.0)
-    print(f"{n:24s} {t:8.1f} {rd:8.1f} {wr:8.1f} {(rd+wr)/t*1e3/1e3:7.0f} {f(v[3]):6.1f} {f(v[4]):6.1f} {v[5]:>4s} {f(v[6]):5.1f} {f(v[7]):5.1f} {f(v[8]):5.1f} {f(v[9])/1e6:7.1f}")
+    print(f"{n:24s} {t:8.1f} {rd:8.1f} {wr:8.1f} {(rd+wr)/t*1e3:7.0f} {f(v[3]):6.1f} {f(v[4]):6.1f} {v[5]:>4s} {f(v[6]):5.1f} {f(v[7]):5.1f} {f(v[8]):5.1f} {f(v[9])/1e6:7.1f}")
