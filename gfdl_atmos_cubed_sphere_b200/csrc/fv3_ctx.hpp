@@ -58,6 +58,37 @@ static inline FrameGrid frame_grid(const Lay& L, int ilo, int ihi, int jlo, int 
   f.cl = cl; f.cr = cr; f.a = a; f.b = f.nby - bt;
   return f;
 }
+// The POINTS of a frame (outer box minus inner box) enumerated densely: south strip, north strip (full width), then the
+// west and east strips of the rows in between.  Edge-formula kernels launch one thread per frame point: with tile-shaped
+// launches most threads of every CTA exit at once and the few long-latency edge threads left per CTA ran at ~1 % of the
+// machine (a2b_ord4 frame passes: 50 us each for ~3000 points per level).
+struct FramePts {
+  int io0, io1, jo0, jo1, ii0, ii1, ji0, ji1;
+  __host__ __device__ int W() const { return io1 - io0 + 1; }
+  __host__ __device__ int nS() const { return W() * (ji0 - jo0); }
+  __host__ __device__ int nN() const { return W() * (jo1 - ji1); }
+  __host__ __device__ int nW() const { return (ii0 - io0) * (ji1 - ji0 + 1); }
+  __host__ __device__ int nE() const { return (io1 - ii1) * (ji1 - ji0 + 1); }
+  __host__ __device__ int count() const { return nS() + nN() + nW() + nE(); }
+  __device__ __forceinline__ bool map(int t, int& i, int& j) const {
+    const int w = W();
+    if (t < nS()) { j = jo0 + t / w; i = io0 + t % w; return true; }
+    t -= nS();
+    if (t < nN()) { j = ji1 + 1 + t / w; i = io0 + t % w; return true; }
+    t -= nN();
+    const int ww = ii0 - io0, we = io1 - ii1;
+    if (t < nW()) { j = ji0 + t / ww; i = io0 + t % ww; return true; }
+    t -= nW();
+    if (t < nE()) { j = ji0 + t / we; i = ii1 + 1 + t % we; return true; }
+    return false;
+  }
+};
+// outer box [io0,io1]x[jo0,jo1], inner (excluded) box [ii0,ii1]x[ji0,ji1]; an empty inner box makes everything "south"
+static inline FramePts frame_pts(int io0, int io1, int jo0, int jo1, int ii0, int ii1, int ji0, int ji1) {
+  FramePts f{io0, io1, jo0, jo1, ii0, ii1, ji0, ji1};
+  if (ii1 < ii0 || ji1 < ji0) { f.ii0 = io0; f.ii1 = io0 - 1; f.ji0 = jo1 + 1; f.ji1 = jo1; }   // nS = whole box
+  return f;
+}
 #endif
 
 // pointers to the 2-D metric planes on the device

@@ -39,12 +39,13 @@ constexpr double c1 = 2. / 3., c2 = -1. / 6.;       // :54-55
 
 // pass 1: qx (is:ie+1, 1:npy-1) and qy (1:npx-1, js:je+1)   (a2b_edge.F90:132-233)
 // frame != 0: only the points the frame outputs of pass 2 read (the interior is done by k_a2b_fused)
-__global__ void __launch_bounds__(TI* TJ) k_a2b_1(Lay L, DevGrid G, FrameGrid FG, const double* __restrict__ qin, double* __restrict__ qx,
-                                                 double* __restrict__ qy, int frame) {
-  FRAME_IJK
+__global__ void __launch_bounds__(128) k_a2b_1(Lay L, DevGrid G, FramePts FP, const double* __restrict__ qin, double* __restrict__ qx,
+                                               double* __restrict__ qy) {
+  int i, j;
+  if (!FP.map(blockIdx.x * 128 + threadIdx.x, i, j)) return;
+  const int k = blockIdx.z;
+  const long long ko = (long long)k * L.plane;
   const int npx = L.npx, npy = L.npy;
-  if (i < L.is - 2 || i > L.ie + 2 || j < L.js - 2 || j > L.je + 2) return;
-  if (frame && i > 5 && i < npx - 4 && j > 5 && j < npy - 4) return;
   const bool cube = L.cube;
   auto Q = [&](int ii, int jj) { return AT(qin, ii, jj); };
   if (i >= L.is && i <= L.ie + 1 && (!cube || (j >= 1 && j <= npy - 1))) {
@@ -80,12 +81,13 @@ __global__ void __launch_bounds__(TI* TJ) k_a2b_1(Lay L, DevGrid G, FrameGrid FG
 }
 
 // pass 2: qout on (is:ie+1, js:je+1)   (a2b_edge.F90:104-130, :141-166, :199-224, :258-288)
-__global__ void __launch_bounds__(TI* TJ) k_a2b_2(Lay L, DevGrid G, FrameGrid FG, const double* __restrict__ qin, const double* __restrict__ qx,
-                                                 const double* __restrict__ qy, double* __restrict__ qout, int frame) {
-  FRAME_IJK
+__global__ void __launch_bounds__(128) k_a2b_2(Lay L, DevGrid G, FramePts FP, const double* __restrict__ qin, const double* __restrict__ qx,
+                                               const double* __restrict__ qy, double* __restrict__ qout) {
+  int i, j;
+  if (!FP.map(blockIdx.x * 128 + threadIdx.x, i, j)) return;
+  const int k = blockIdx.z;
+  const long long ko = (long long)k * L.plane;
   const int npx = L.npx, npy = L.npy;
-  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
-  if (frame && i >= 3 && i <= npx - 2 && j >= 3 && j <= npy - 2) return;
   auto Q = [&](int ii, int jj) { return AT(qin, ii, jj); };
   auto QX = [&](int ii, int jj) { return AT(qx, ii, jj); };
   auto QY = [&](int ii, int jj) { return AT(qy, ii, jj); };
@@ -195,11 +197,15 @@ int launch_a2b_ord4(fv3_ctx* c, const double* qin, double* qout, int nk, int /*r
     k_a2b_fused<<<g, 256, 0, c->stream>>>(L, qin, qout);
     c->launches++;
   }
-  // frame: pass 1 is needed where i <= 5 || i >= npx-4 (same in j), pass 2 where i <= 2 || i >= npx-1; one grid serves both
-  const FrameGrid FG = fused ? frame_grid(L, 6, L.npx - 5, 6, L.npy - 5) : frame_grid(L, 1, 0, 1, 0);
-  dim3 grd(FG.count(), 1, nk);
-  k_a2b_1<<<grd, blk, 0, c->stream>>>(L, c->G, FG, qin, c->scr[4], c->scr[5], fused);
-  k_a2b_2<<<grd, blk, 0, c->stream>>>(L, c->G, FG, qin, c->scr[4], c->scr[5], qout, fused);
+  // edge passes, one thread per point: pass 1 on (is-2:ie+2)^2 where i <= 5 || i >= npx-4 (same in j) -- what the
+  // frame outputs read --, pass 2 on (is:ie+1)^2 where i <= 2 || i >= npx-1 (same in j); everything when not fused
+  const FramePts P1 = fused ? frame_pts(L.is - 2, L.ie + 2, L.js - 2, L.je + 2, 6, L.npx - 5, 6, L.npy - 5)
+                            : frame_pts(L.is - 2, L.ie + 2, L.js - 2, L.je + 2, 1, 0, 1, 0);
+  const FramePts P2 = fused ? frame_pts(L.is, L.ie + 1, L.js, L.je + 1, 3, L.npx - 2, 3, L.npy - 2)
+                            : frame_pts(L.is, L.ie + 1, L.js, L.je + 1, 1, 0, 1, 0);
+  (void)blk;
+  k_a2b_1<<<dim3((P1.count() + 127) / 128, 1, nk), 128, 0, c->stream>>>(L, c->G, P1, qin, c->scr[4], c->scr[5]);
+  k_a2b_2<<<dim3((P2.count() + 127) / 128, 1, nk), 128, 0, c->stream>>>(L, c->G, P2, qin, c->scr[4], c->scr[5], qout);
   c->launches += 2;
   return 0;
 }
