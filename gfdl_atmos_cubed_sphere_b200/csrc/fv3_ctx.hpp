@@ -39,7 +39,7 @@ struct Lay {
 struct FrameGrid {
   int nbx, a, b, cl, cr, nby;   // tile rows [0,a) and [b,nby) are frame rows; tile columns [0,cl) and [nbx-cr,nbx) frame columns
   int count() const { return nbx * (a + nby - b) + (b - a) * (cl + cr); }
-  __device__ __forceinline__ void map(int t, int& bx, int& by) const {
+  __host__ __device__ __forceinline__ void map(int t, int& bx, int& by) const {
     const int nyf = a + nby - b;
     if (t < nbx * nyf) { by = t / nbx; bx = t - by * nbx; if (by >= a) by = by - a + b; }
     else { t -= nbx * nyf; const int nc = cl + cr, row = t / nc, cc = t - row * nc; by = a + row; bx = cc < cl ? cc : nbx - cr + (cc - cl); }
@@ -70,7 +70,7 @@ struct FramePts {
   __host__ __device__ int nW() const { return (ii0 - io0) * (ji1 - ji0 + 1); }
   __host__ __device__ int nE() const { return (io1 - ii1) * (ji1 - ji0 + 1); }
   __host__ __device__ int count() const { return nS() + nN() + nW() + nE(); }
-  __device__ __forceinline__ bool map(int t, int& i, int& j) const {
+  __host__ __device__ __forceinline__ bool map(int t, int& i, int& j) const {
     const int w = W();
     if (t < nS()) { j = jo0 + t / w; i = io0 + t % w; return true; }
     t -= nS();

@@ -207,3 +207,46 @@ def test_nonhydrostatic_stages_one_by_one():
     both("nh_p_grad", dt)
     check("nh_p_grad", {"U": (is_, ie, js, je + 1), "V": (is_, ie + 1, js, je)})
     oc.close(); gc.close()
+
+
+def test_full_size_properties_c384l79():
+    """BASELINE.json's headline size, where the oracle is too slow to be the checker: size-independent properties of two
+    acoustic substeps of the full C384L79 cube (flag-set A, JW wave) --
+      * flux-form delp update conserves sum(area*delp) to round-off (sw_core.F90:1059-1060),
+      * the accumulated mass fluxes mfx reproduce the delp change exactly in every cell (dyn_core.F90:928-940),
+      * u, v on the edge shared by two faces are bitwise equal after the last substep (dyn_core.F90:1151-1163),
+      * everything stays finite and physical."""
+    n, npz = 384, 79
+    case = H.Case(n, npz, "A", state="baroclinic")
+    gc = H.CudaCube(case)
+    area = [case.tiles[t - 1].arr["area"][None, 3:-3, 3:-3] for t in gc.tiles]
+
+    def delp_of(t):
+        return H.sub(gc.eng[t], "DELP", gc.eng[t].get("DELP"), 1, n, 1, n)
+
+    d0 = {t: delp_of(t).copy() for t in gc.tiles}
+    m0 = sum(float(np.sum(d0[t] * area[t - 1])) for t in gc.tiles)
+    gc.dyn_core(2 * 225.0 / 8, 2)
+    m1 = 0.0
+    for t in gc.tiles:
+        d1 = delp_of(t)
+        m1 += float(np.sum(d1 * area[t - 1]))
+        e = gc.eng[t]
+        mfx = H.sub(e, "MFX", e.get("MFX"), 1, n + 1, 1, n)
+        mfy = H.sub(e, "MFY", e.get("MFY"), 1, n, 1, n + 1)
+        div = (mfx[:, :, :-1] - mfx[:, :, 1:] + mfy[:, :-1, :] - mfy[:, 1:, :]) / area[t - 1]
+        assert np.max(np.abs((d1 - d0[t]) - div)) / np.max(np.abs(d0[t])) < 1e-13, t
+        for f in ("U", "V", "W", "PT", "DELP", "DELZ"):
+            assert np.isfinite(e.get(f)).all(), (t, f)
+        assert np.abs(H.sub(e, "W", e.get("W"), 1, n, 1, n)).max() < 5.0
+        assert (d1 > 0).all()
+    assert abs(m1 - m0) / m0 < 1e-13
+    # contact 1E <-> 2W (fv_mp_mod.F90:499-502, aligned): v on tile 1's east edge == v on tile 2's west edge
+    v1 = H.sub(gc.eng[1], "V", gc.eng[1].get("V"), n + 1, n + 1, 1, n)
+    v2 = H.sub(gc.eng[2], "V", gc.eng[2].get("V"), 1, 1, 1, n)
+    assert np.array_equal(v1, v2)
+    # contact 2N <-> 3S (:515-518, aligned): u on tile 2's north edge == u on tile 3's south edge
+    u2 = H.sub(gc.eng[2], "U", gc.eng[2].get("U"), 1, n, n + 1, n + 1)
+    u3 = H.sub(gc.eng[3], "U", gc.eng[3].get("U"), 1, n, 1, 1)
+    assert np.array_equal(u2, u3)
+    gc.close()
