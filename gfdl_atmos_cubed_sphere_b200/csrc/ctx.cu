@@ -367,6 +367,8 @@ int fv3_pk3_halo(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_pk3_halo(c); if 
 int fv3_pe_halo(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_pe_halo(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_gz_from_zh(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_gz_from_zh(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_nh_p_grad(fv3_ctx* c, double dt) { STAGE_PROLOGUE(c) int rc = stage_nh_p_grad(c, dt); if (rc) return rc; STAGE_EPILOGUE(c) }
+int fv3_geopk(fv3_ctx* c, int cg) { STAGE_PROLOGUE(c) int rc = stage_geopk(c, cg); if (rc) return rc; STAGE_EPILOGUE(c) }
+int fv3_one_grad_p(fv3_ctx* c, double dt) { STAGE_PROLOGUE(c) int rc = stage_one_grad_p(c, dt); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_gz_init(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_gz_init(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_copy_field(fv3_ctx* c, int dst, int src) { STAGE_PROLOGUE(c) int rc = stage_copy_field(c, dst, src); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_zero_field(fv3_ctx* c, int f) { STAGE_PROLOGUE(c) int rc = stage_zero_field(c, f); if (rc) return rc; STAGE_EPILOGUE(c) }

@@ -6,6 +6,8 @@
 //   -> update_dz_c -> Riem_Solver_C -> p_grad_c -> halo(divgd@corner, uc,vc) -> d_sw
 //   -> halo(delp,pt[,q_con]) -> update_dz_d -> Riem_Solver3 -> halo(zh,pkc)
 //   -> [pe_halo] pk3_halo -> gz = zh*grav -> nh_p_grad -> [last: shared-edge u,v de-dup]
+// and the hydrostatic branch (BASELINE config 1b):
+//   halo(u,v[,delp,pt]) -> c_sw -> geopk(C) -> p_grad_c -> halo(divgd, uc,vc) -> d_sw -> halo(delp,pt) -> geopk(D) -> one_grad_p
 // One call replaces the whole it-loop; all faces owned by this process advance in lockstep
 // (each on its own stream), exchanges are fv3_halo_exchange (device-local gathers and/or NCCL).
 // Not included (documented in DESIGN.md): the post-loop d_con heating del2_cubed
@@ -26,7 +28,6 @@ extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, i
   (void)flags;
   if (!ctxs || nctx < 1 || n_split < 1) return -1;
   for (int a = 0; a < nctx; a++) {
-    if (ctxs[a]->f.hydrostatic) return fv3_fail(ctxs[a], -2, "dyn_core: hydrostatic path (geopk/one_grad_p) not supported yet");
     if (ctxs[a]->f.beta != 0.0) return fv3_fail(ctxs[a], -2, "dyn_core: beta != 0 (split_p_grad/one_grad_p) not supported");
     if (ctxs[a]->f.d_ext > 0.0) return fv3_fail(ctxs[a], -2, "dyn_core: d_ext > 0 (external-mode damping) not supported");
   }
@@ -37,8 +38,25 @@ extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, i
   FORALL(stage_zero_field(c, FV3_MFX)) FORALL(stage_zero_field(c, FV3_MFY)) FORALL(stage_zero_field(c, FV3_CX))
   FORALL(stage_zero_field(c, FV3_CY)) FORALL(stage_zero_field(c, FV3_HEAT))
   int rc;
+  const bool hydrostatic = ctxs[0]->f.hydrostatic != 0;
   for (int it = 1; it <= n_split; it++) {
     const bool last_step = (it == n_split);
+    if (hydrostatic) {   // geopk replaces the vertical solvers, one_grad_p the pressure gradient (dyn_core.F90:478-480, :905-907, :1017-1021)
+      if (linked) {
+        if (it == 1 && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;
+        if ((rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_UVW))) return rc;
+      }
+      FORALL(stage_c_sw(c, dt2))
+      FORALL(stage_geopk(c, 1))
+      FORALL(stage_p_grad_c(c, dt2))
+      if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DIVGD_UCVC))) return rc;
+      FORALL(stage_d_sw(c, dt))
+      if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;
+      FORALL(stage_geopk(c, 0))
+      FORALL(stage_one_grad_p(c, dt))
+      if (last_step && linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_UV_EDGE))) return rc;
+      continue;
+    }
     if (linked) {
       if (it == 1 && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;   // :402 (started in fv_dynamics.F90:467)
       if ((rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_UVW))) return rc;                  // :430-432

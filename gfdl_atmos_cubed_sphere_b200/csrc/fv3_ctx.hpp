@@ -171,6 +171,8 @@ int stage_pk3_halo(fv3_ctx* c);
 int stage_pe_halo(fv3_ctx* c);
 int stage_gz_from_zh(fv3_ctx* c);
 int stage_nh_p_grad(fv3_ctx* c, double dt);
+int stage_geopk(fv3_ctx* c, int cg);
+int stage_one_grad_p(fv3_ctx* c, double dt);
 int stage_gz_init(fv3_ctx* c);
 int stage_copy_field(fv3_ctx* c, int dst, int src);
 int stage_zero_field(fv3_ctx* c, int f);

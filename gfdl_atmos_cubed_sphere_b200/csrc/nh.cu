@@ -705,6 +705,90 @@ int stage_update_dz_d(fv3_ctx* c, double dt) {
   return 0;
 }
 
+// ---- geopk (dyn_core.F90:2202-2356): hydrostatic pressure / geopotential integration, one thread per column --------
+// C-grid call (cg): columns (is-1:ie+1)^2 from delpc, ptc; D-grid call: (is-2:ie+2)^2 from delp, pt, plus pkz.
+// pe is stored on (is-1:ie+1)^2, peln on (is:ie)^2, as the reference's extents (:2211-2212).
+template <bool UC>
+__global__ void __launch_bounds__(CB) k_geopk(Lay L, const double* __restrict__ delp, const double* __restrict__ pt,
+                                             const double* __restrict__ q_con, const double* __restrict__ hs, double* __restrict__ pk,
+                                             double* __restrict__ gz, double* __restrict__ pe, double* __restrict__ peln,
+                                             double* __restrict__ pkz, double ptop, double akap, double cp_air, int cg, int halo) {
+  COL_SETUP(L.is - halo, L.ie + halo, L.js - halo, L.je + halo)
+  const int km = L.npz;
+  const bool in_pe = i >= L.is - 1 && i <= L.ie + 1 && j >= L.js - 1 && j <= L.je + 1;
+  const bool in_c = i >= L.is && i <= L.ie && j >= L.js && j <= L.je;
+  const double ptk = pow(ptop, akap), peln1 = log(ptop);
+  double p1d = ptop, peg = ptop;
+  pk[o] = ptk;
+  if (in_c) peln[o] = peln1;
+  if (in_pe) pe[o] = ptop;
+  // top down (:2291-2318)
+  for (int k = 2; k <= km + 1; k++) {
+    const long long ok = o + (long long)(k - 1) * P;
+    p1d = p1d + __ldg(delp + ok - P);
+    const double lp = log(p1d);
+    pk[ok] = exp(akap * lp);
+    if (in_pe) pe[ok] = p1d;
+    if (in_c) peln[ok] = lp;
+  }
+  // bottom up.  With condensate the integration uses pkg = peg^kappa of the condensate-free pressure: peg is re-accumulated
+  // top down first (same additions in the same order as :2297-2298), stored in gz's own column as scratch, then consumed.
+  double g = __ldg(hs + o);
+  if (UC) {
+    gz[o] = ptk;   // pkg(1)
+    for (int k = 2; k <= km + 1; k++) {
+      const long long ok = o + (long long)(k - 1) * P;
+      peg = peg + __ldg(delp + ok - P) * (1. - __ldg(q_con + ok - P));
+      gz[ok] = exp(akap * log(peg));
+    }
+    double pkg_hi = gz[o + (long long)km * P];
+    gz[o + (long long)km * P] = g;
+    for (int k = km; k >= 1; k--) {
+      const long long ok = o + (long long)(k - 1) * P;
+      const double pkg_lo = gz[ok];
+      g = g + cp_air * __ldg(pt + ok) * (pkg_hi - pkg_lo);
+      gz[ok] = g;
+      pkg_hi = pkg_lo;
+    }
+  } else {
+    gz[o + (long long)km * P] = g;
+    double pk_hi = pk[o + (long long)km * P];
+    for (int k = km; k >= 1; k--) {
+      const long long ok = o + (long long)(k - 1) * P;
+      const double pk_lo = pk[ok];
+      g = g + cp_air * __ldg(pt + ok) * (pk_hi - pk_lo);
+      gz[ok] = g;
+      pk_hi = pk_lo;
+    }
+  }
+  if (!cg && in_c) {
+    double pk_lo = pk[o], ln_lo = peln[o];
+    for (int k = 1; k <= km; k++) {
+      const long long ok = o + (long long)(k - 1) * P;
+      const double pk_hi = pk[ok + P], ln_hi = peln[ok + P];
+      pkz[ok] = (pk_hi - pk_lo) / (akap * (ln_hi - ln_lo));
+      pk_lo = pk_hi; ln_lo = ln_hi;
+    }
+  }
+}
+int stage_geopk(fv3_ctx* c, int cg) {
+  StageScope ts(c, cg ? "GEOPK_C" : "GEOPK_D");
+  const Lay& L = c->L;
+  const int halo = cg ? 1 : 2, n = L.ie - L.is + 1 + 2 * halo;
+  const double* delp = c->fld[cg ? FV3_DELPC : FV3_DELP];
+  const double* pt = c->fld[cg ? FV3_PTC : FV3_PT];
+  if (c->f.use_cond)
+    k_geopk<true><<<col_blocks(n, n), CB, 0, c->stream>>>(L, delp, pt, c->fld[FV3_QCON], c->fld[FV3_PHIS], c->fld[FV3_PKC], c->fld[FV3_GZ],
+                                                          c->fld[FV3_PE], c->fld[FV3_PELN], c->fld[FV3_PKZ], c->f.ptop, c->f.kappa,
+                                                          c->f.cp_air, cg, halo);
+  else
+    k_geopk<false><<<col_blocks(n, n), CB, 0, c->stream>>>(L, delp, pt, c->fld[FV3_QCON], c->fld[FV3_PHIS], c->fld[FV3_PKC], c->fld[FV3_GZ],
+                                                           c->fld[FV3_PE], c->fld[FV3_PELN], c->fld[FV3_PKZ], c->f.ptop, c->f.kappa,
+                                                           c->f.cp_air, cg, halo);
+  c->launches++;
+  return 0;
+}
+
 int stage_pk3_halo(fv3_ctx* c) {
   const Lay& L = c->L;
   if (c->f.use_logp) return fv3_fail(c, -2, "pln_halo (use_logp) not supported");

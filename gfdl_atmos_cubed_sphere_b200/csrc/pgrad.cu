@@ -297,3 +297,51 @@ int stage_nh_p_grad(fv3_ctx* c, double dt) {
   c->launches++;
   return 0;
 }
+
+// ---- one_grad_p (dyn_core.F90:1909-2030), hydrostatic call, d_ext = 0 -------------------------------------------------
+// pk (= pe^kappa) and gz are interpolated to the cell corners into scratch planes (the reference replaces them in
+// place; nothing reads them before the next geopk rebuilds them), wk = pk(k+1) - pk(k) at the corners.
+__global__ void __launch_bounds__(TI* TJ) k_one_grad_p(Lay L, DevGrid G, const double* __restrict__ pk, const double* __restrict__ gz,
+                                                      double* __restrict__ u, double* __restrict__ v, double dt) {
+  PLANE_IJK
+  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
+  const long long P = L.plane;
+  const long long o = ko + LIDX(L, i, j);
+  auto WK = [&](long long oo) { return __ldg(pk + oo + P) - __ldg(pk + oo); };
+  if (i <= L.ie) {
+    const long long e = o + 1;
+    u[o] = G2(rdx, i, j) * (0. + u[o] + dt / (WK(o) + WK(e)) *
+                                            ((__ldg(gz + o + P) - __ldg(gz + e)) * (__ldg(pk + e + P) - __ldg(pk + o)) +
+                                             (__ldg(gz + o) - __ldg(gz + e + P)) * (__ldg(pk + o + P) - __ldg(pk + e))));
+  }
+  if (j <= L.je) {
+    const long long n = o + L.NI;
+    v[o] = G2(rdy, i, j) * (0. + v[o] + dt / (WK(o) + WK(n)) *
+                                            ((__ldg(gz + o + P) - __ldg(gz + n)) * (__ldg(pk + n + P) - __ldg(pk + o)) +
+                                             (__ldg(gz + o) - __ldg(gz + n + P)) * (__ldg(pk + o + P) - __ldg(pk + n))));
+  }
+}
+__global__ void __launch_bounds__(TI* TJ) k_set_top(Lay L, double* __restrict__ pkb, double top_value) {
+  const int i = L.isd - FV3_IOFF + blockIdx.x * TI + threadIdx.x;
+  const int j = L.jsd + blockIdx.y * TJ + threadIdx.y;
+  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
+  pkb[LIDX(L, i, j)] = top_value;
+}
+int stage_one_grad_p(fv3_ctx* c, double dt) {
+  StageScope ts(c, "PG_D");
+  const Lay& L = c->L;
+  const int km = L.npz;
+  if (!c->f.hydrostatic) return fv3_fail(c, -2, "one_grad_p: only the hydrostatic call is supported (non-hydrostatic uses nh_p_grad)");
+  if (c->f.d_ext > 0.0) return fv3_fail(c, -2, "one_grad_p: d_ext > 0 not supported");
+  double *pkb = c->scr[1], *gzb = c->scr[2];
+  const long long P = L.plane;
+  dim3 blk(TI, TJ);
+  k_set_top<<<plane_grid(L, 1), blk, 0, c->stream>>>(L, pkb, pow(c->f.ptop, c->f.kappa));   // ptk, dyn_core.F90:222,1944
+  c->launches++;
+  int rc;
+  if ((rc = launch_a2b_ord4(c, c->fld[FV3_PKC] + P, pkb + P, km, 1))) return rc;   // pk, k = 2..km+1
+  if ((rc = launch_a2b_ord4(c, c->fld[FV3_GZ], gzb, km + 1, 1))) return rc;        // gz, k = 1..km+1
+  k_one_grad_p<<<plane_grid(L, km), blk, 0, c->stream>>>(L, c->G, pkb, gzb, c->fld[FV3_U], c->fld[FV3_V], dt);
+  c->launches++;
+  return 0;
+}

@@ -26,7 +26,13 @@
 
 namespace tpt {
 
-constexpr int TX = 26, TY = 20, NW = 16, NT = NW * 32;
+#ifndef TPT_TY
+#define TPT_TY 24
+#endif
+#ifndef TPT_NW
+#define TPT_NW 16
+#endif
+constexpr int TX = 26, TY = TPT_TY, NW = TPT_NW, NT = NW * 32;
 constexpr int QW = 32, QH = TY + 6;
 
 struct Smem {

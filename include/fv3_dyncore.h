@@ -185,6 +185,11 @@ int fv3_pe_halo(fv3_ctx *ctx);
 int fv3_gz_from_zh(fv3_ctx *ctx);
 /* dyn_core.F90:1697 nh_p_grad (dyn_core.F90:1032). */
 int fv3_nh_p_grad(fv3_ctx *ctx, double dt);
+/* Hydrostatic branch.  dyn_core.F90:2202 geopk: cg != 0 is the C-grid call (dyn_core.F90:478-480: delpc, ptc -> pkc, gz,
+ * pe, peln), cg == 0 the D-grid call (:905-907: delp, pt -> pkc, gz, pe, peln, pkz).  dyn_core.F90:1909 one_grad_p
+ * (call :1019-1021, d_ext = 0): a2b_ord4 of pkc, gz and the D-grid pressure-gradient update of u, v. */
+int fv3_geopk(fv3_ctx *ctx, int cg);
+int fv3_one_grad_p(fv3_ctx *ctx, double dt);
 
 /* dyn_core.F90:370-385 (it==1): gz on the compute domain from zs and delz. */
 int fv3_gz_init(fv3_ctx *ctx);

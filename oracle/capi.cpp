@@ -286,6 +286,21 @@ int fv3o_nh_p_grad(fv3o_ctx* c, double dt) {
             bd.npx, bd.npy, bd.npz, c->f.use_logp != 0, c->f.ptop, c->f.kappa);
   return 0;
 }
+// dyn_core.F90:2202 geopk: cg != 0 -> C-grid call (:478-480, delpc/ptc), else D-grid call (:905-907, delp/pt)
+int fv3o_geopk(fv3o_ctx* c, int cg) {
+  Bd bd(c->b);
+  geopk(c->f.ptop, c->fld[FV3_PE].data(), c->fld[FV3_PELN].data(), F3(c, cg ? FV3_DELPC : FV3_DELP), F3(c, FV3_PKC), F3(c, FV3_GZ),
+        F2(c, FV3_PHIS), F3(c, cg ? FV3_PTC : FV3_PT), F3(c, FV3_QCON), F3(c, FV3_PKZ), bd.npz, c->f.kappa, c->f.cp_air, cg != 0,
+        c->f.use_cond != 0, bd);
+  return 0;
+}
+// dyn_core.F90:1909 one_grad_p (hydrostatic call :1019-1021, d_ext = 0)
+int fv3o_one_grad_p(fv3o_ctx* c, double dt) {
+  Bd bd(c->b); Grid g(c->g, bd);
+  one_grad_p(F3(c, FV3_U), F3(c, FV3_V), F3(c, FV3_PKC), F3(c, FV3_GZ), F3(c, FV3_DELP), dt, g, bd, bd.npz, c->f.ptop, c->f.kappa,
+             c->f.hydrostatic != 0);
+  return 0;
+}
 // dyn_core.F90:370-385 (it==1): gz from zs and delz on the compute domain
 int fv3o_gz_init(fv3o_ctx* c) {
   Bd bd(c->b);

@@ -192,6 +192,10 @@ void p_grad_c(double dt2, int npz, V3 delpc, V3 pkc, V3 gz, V3 uc, V3 vc, const 
               bool hydrostatic);
 void nh_p_grad(V3 u, V3 v, V3 pp, V3 gz, V3 delp, V3 pk, double dt, int ng, const Grid& g, const Bd& bd, int npx,
                int npy, int npz, bool use_logp, double ptop, double akap);
+void geopk(double ptop, double* pe, double* peln, V3 delp, V3 pk, V3 gz, V2 hs, V3 pt, V3 q_con, V3 pkz, int km, double akap,
+           double cp_air, bool CG, bool use_cond, const Bd& bd);
+void one_grad_p(V3 u, V3 v, V3 pk, V3 gz, V3 delp, double dt, const Grid& g, const Bd& bd, int npz, double ptop, double akap,
+                bool hydrostatic);
 void pk3_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed, int npz, double ptop,
               double akap, V3 pk3, V3 delp);
 void pe_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed, int npz, double ptop,

@@ -485,6 +485,80 @@ void nh_p_grad(V3 u, V3 v, V3 pp, V3 gz, V3 delp, V3 pk, double dt, int ng, cons
   }
 }
 
+// dyn_core.F90:2202-2356 geopk (not SW_DYNAMICS, not bounded_domain).  pe is (is-1:ie+1, km+1, js-1:je+1), peln (is:ie, km+1, js:je)
+void geopk(double ptop, double* pe, double* peln, V3 delp, V3 pk, V3 gz, V2 hs, V3 pt, V3 q_con, V3 pkz, int km, double akap,
+           double cp_air, bool CG, bool use_cond, const Bd& bd) {
+  const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je;
+  const double ptk = std::pow(ptop, akap), peln1 = std::log(ptop);   // dyn_core.F90:220-222
+  int ifirst, ilast, jfirst, jlast;
+  if (!CG) { ifirst = is - 2; ilast = ie + 2; jfirst = js - 2; jlast = je + 2; }
+  else { ifirst = is - 1; ilast = ie + 1; jfirst = js - 1; jlast = je + 1; }
+  const size_t nip = ie - is + 3, nie = ie - is + 1;
+  auto PE = [&](int i, int k, int j) -> double& { return pe[(i - (is - 1)) + (size_t)(k - 1) * nip + (size_t)(j - (js - 1)) * nip * (km + 1)]; };
+  auto PELN = [&](int i, int k, int j) -> double& { return peln[(i - is) + (size_t)(k - 1) * nie + (size_t)(j - js) * nie * (km + 1)]; };
+#pragma omp parallel for schedule(static)
+  for (int j = jfirst; j <= jlast; j++) {
+    L2 peg(ifirst, ilast, 1, km + 1), pkg(ifirst, ilast, 1, km + 1);
+    L1 p1d(ifirst, ilast), logp(ifirst, ilast);
+    for (int i = ifirst; i <= ilast; i++) {
+      p1d(i) = ptop; pk(i, j, 1) = ptk; gz(i, j, km + 1) = hs(i, j);
+      if (use_cond) { peg(i, 1) = ptop; pkg(i, 1) = ptk; }
+    }
+    if (j >= js && j <= je) for (int i = is; i <= ie; i++) PELN(i, 1, j) = peln1;
+    if (j > (js - 2) && j < (je + 2)) for (int i = std::max(ifirst, is - 1); i <= std::min(ilast, ie + 1); i++) PE(i, 1, j) = ptop;
+    for (int k = 2; k <= km + 1; k++) {   // top down
+      for (int i = ifirst; i <= ilast; i++) {
+        p1d(i) = p1d(i) + delp(i, j, k - 1);
+        logp(i) = std::log(p1d(i));
+        pk(i, j, k) = std::exp(akap * logp(i));
+        if (use_cond) {
+          peg(i, k) = peg(i, k - 1) + delp(i, j, k - 1) * (1. - q_con(i, j, k - 1));
+          pkg(i, k) = std::exp(akap * std::log(peg(i, k)));
+        }
+      }
+      if (j > (js - 2) && j < (je + 2)) {
+        for (int i = std::max(ifirst, is - 1); i <= std::min(ilast, ie + 1); i++) PE(i, k, j) = p1d(i);
+        if (j >= js && j <= je) for (int i = is; i <= ie; i++) PELN(i, k, j) = logp(i);
+      }
+    }
+    for (int k = km; k >= 1; k--)   // bottom up
+      for (int i = ifirst; i <= ilast; i++)
+        gz(i, j, k) = use_cond ? gz(i, j, k + 1) + cp_air * pt(i, j, k) * (pkg(i, k + 1) - pkg(i, k))
+                               : gz(i, j, k + 1) + cp_air * pt(i, j, k) * (pk(i, j, k + 1) - pk(i, j, k));
+    if (!CG && j >= js && j <= je)
+      for (int k = 1; k <= km; k++)
+        for (int i = is; i <= ie; i++) pkz(i, j, k) = (pk(i, j, k + 1) - pk(i, j, k)) / (akap * (PELN(i, k + 1, j) - PELN(i, k, j)));
+  }
+}
+
+// dyn_core.F90:1909-2030 one_grad_p, d_ext = 0 (wk1 = wk2 = 0)
+void one_grad_p(V3 u, V3 v, V3 pk, V3 gz, V3 delp, double dt, const Grid& g, const Bd& bd, int npz, double ptop, double akap,
+                bool hydrostatic) {
+  const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je, isd = bd.isd, ied = bd.ied, jsd = bd.jsd, jed = bd.jed;
+  const double top_value = hydrostatic ? std::pow(ptop, akap) : ptop;
+  for (int j = js; j <= je + 1; j++) for (int i = is; i <= ie + 1; i++) pk(i, j, 1) = top_value;
+#pragma omp parallel for schedule(static)
+  for (int k = 2; k <= npz + 1; k++) { L2 wk(isd, ied, jsd, jed); a2b_ord4(pk.k(k), wk, g, bd, true); }
+#pragma omp parallel for schedule(static)
+  for (int k = 1; k <= npz + 1; k++) { L2 wk(isd, ied, jsd, jed); a2b_ord4(gz.k(k), wk, g, bd, true); }
+#pragma omp parallel for schedule(static)
+  for (int k = 1; k <= npz; k++) {
+    L2 wk(isd, ied, jsd, jed);
+    if (hydrostatic) { for (int j = js; j <= je + 1; j++) for (int i = is; i <= ie + 1; i++) wk(i, j) = pk(i, j, k + 1) - pk(i, j, k); }
+    else a2b_ord4(delp.k(k), wk, g, bd, false);
+    for (int j = js; j <= je + 1; j++)
+      for (int i = is; i <= ie; i++)
+        u(i, j, k) = g.rdx(i, j) * (0. + u(i, j, k) + dt / (wk(i, j) + wk(i + 1, j)) *
+                                    ((gz(i, j, k + 1) - gz(i + 1, j, k)) * (pk(i + 1, j, k + 1) - pk(i, j, k)) +
+                                     (gz(i, j, k) - gz(i + 1, j, k + 1)) * (pk(i, j, k + 1) - pk(i + 1, j, k))));
+    for (int j = js; j <= je; j++)
+      for (int i = is; i <= ie + 1; i++)
+        v(i, j, k) = g.rdy(i, j) * (0. + v(i, j, k) + dt / (wk(i, j) + wk(i, j + 1)) *
+                                    ((gz(i, j, k + 1) - gz(i, j + 1, k)) * (pk(i, j + 1, k + 1) - pk(i, j, k)) +
+                                     (gz(i, j, k) - gz(i, j + 1, k + 1)) * (pk(i, j, k + 1) - pk(i, j + 1, k))));
+  }
+}
+
 // dyn_core.F90:1395-1447
 void pk3_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed, int npz, double ptop,
               double akap, V3 pk3, V3 delp) {

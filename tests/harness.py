@@ -204,11 +204,24 @@ class OracleCube:
 
         for f in ("MFX", "MFY", "CX", "CY", "HEAT"):
             self.all("zero_field", F[f])
+        hydro = bool(self.case.flags["hydrostatic"])
         for it in range(1, n_split + 1):
             last = it == n_split
             if it == 1:
                 self.halo("DELP_PT")
             self.halo("UVW")
+            if hydro:   # dyn_core.F90:478-480, :905-907, :1017-1021
+                run("C_SW", "c_sw", dt2)
+                run("GEOPK_C", "geopk", 1)
+                run("PG_C", "p_grad_c", dt2)
+                self.halo("DIVGD_UCVC")
+                run("D_SW", "d_sw", dt)
+                self.halo("DELP_PT")
+                run("GEOPK_D", "geopk", 0)
+                run("PG_D", "one_grad_p", dt)
+                if last:
+                    self.halo("UV_EDGE")
+                continue
             if it == 1:
                 self.all("gz_init")
                 self.halo("GZ")

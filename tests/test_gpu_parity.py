@@ -250,3 +250,44 @@ def test_full_size_properties_c384l79():
     u3 = H.sub(gc.eng[3], "U", gc.eng[3].get("U"), 1, n, 1, 1)
     assert np.array_equal(u2, u3)
     gc.close()
+
+
+def test_hydrostatic_stages_and_config1b():
+    """BASELINE.json configs[0] as SURVEY 8(d) restates it (1b): C48 L32 HYDROSTATIC, JW baroclinic wave (test case 13),
+    fp64 -- geopk replaces both vertical solvers, one_grad_p the pressure gradient (dyn_core.F90:478-480, :905-907,
+    :1017-1021, :1909-2030, :2202-2356).  First geopk (C- and D-grid call) and one_grad_p on their own, then three acoustic
+    substeps of the full cube against the oracle."""
+    n, npz = 48, 32
+    case = H.Case(n, npz, "A", state="baroclinic", flags_override=dict(hydrostatic=1))
+    oc = H.OracleCube(case)
+    gc = H.CudaCube(case)
+    b = case.bounds
+    is_, ie, js, je = b["is_"], b["ie"], b["js"], b["je"]
+    # geopk, D-grid call, on the initial state (halos of delp, pt first)
+    oc.halo("DELP_PT")
+    assert gc.lib[0].fv3_halo_exchange(gc.ctxs, 6, abi.HALO_ID["DELP_PT"]) == 0
+    for t in oc.tiles:
+        oc.eng[t].call("geopk", 0); gc.eng[t].call("geopk", 0)
+        res = H.compare(oc.eng[t], gc.eng[t], {"PKC": (is_ - 2, ie + 2, js - 2, je + 2), "GZ": (is_ - 2, ie + 2, js - 2, je + 2),
+                                               "PE": (is_ - 1, ie + 1, js - 1, je + 1), "PELN": (is_, ie, js, je), "PKZ": (is_, ie, js, je)})
+        _assert(res, TOL_STAGE)
+        oc.eng[t].call("one_grad_p", 100.0); gc.eng[t].call("one_grad_p", 100.0)
+        _assert(H.compare(oc.eng[t], gc.eng[t], {"U": (is_, ie, js, je + 1), "V": (is_, ie + 1, js, je)}), TOL_STAGE)
+    oc.close(); gc.close()
+    # the acoustic loop
+    oc = H.OracleCube(case)
+    gc = H.CudaCube(case)
+    oc.dyn_core(450.0, 3)
+    gc.dyn_core(450.0, 3)
+    for t in oc.tiles:
+        res = H.compare(oc.eng[t], gc.eng[t], {"DELP": (is_, ie, js, je), "PT": (is_, ie, js, je), "U": (is_, ie, js, je + 1),
+                                               "V": (is_, ie + 1, js, je), "MFX": (is_, ie + 1, js, je), "MFY": (is_, ie, js, je + 1),
+                                               "PKZ": (is_, ie, js, je), "PE": (is_ - 1, ie + 1, js, je)})
+        _assert(res, TOL_RUN)
+        # pe on its 1-wide ring, WITHOUT the four ring corners: those read the 3x3 corner halo of delp, which no exchange
+        # fills and which the reference's in-place fill_4corners leaves in a sweep-dependent state (the CUDA path remaps
+        # on the read side instead and never writes them); nothing reads pe there
+        _assert(H.compare(oc.eng[t], gc.eng[t], {"PE": (is_, ie, js - 1, je + 1)}), TOL_RUN)
+    u = gc.eng[1].get("U")
+    assert np.abs(H.sub(gc.eng[1], "U", u, 1, n, 1, n + 1)).max() < 60.0
+    oc.close(); gc.close()
