@@ -291,3 +291,21 @@ def test_hydrostatic_stages_and_config1b():
     u = gc.eng[1].get("U")
     assert np.abs(H.sub(gc.eng[1], "U", u, 1, n, 1, n + 1)).max() < 60.0
     oc.close(); gc.close()
+
+
+@pytest.mark.parametrize("n", [96, 192])
+def test_dyn_core_baseline_config_sizes(n):
+    """BASELINE.json configs[1] and [2] resolutions (C96 L79, C192 L79, non-hydrostatic, fp64): two acoustic substeps of
+    the full cube against the oracle (fast OpenMP build of the same restatement: its FMA contraction is allowed for by the
+    multi-step tolerance).  The 6-GPU NCCL run of config [2] is bit-identical to this single-process run
+    (tests/nccl_check.py), so one comparison covers both placements."""
+    npz = 79
+    case = H.Case(n, npz, "A", state="baroclinic")
+    oc = H.OracleCube(case, fast=True)
+    gc = H.CudaCube(case)
+    bdt = 2 * (225.0 / 8) * 384 / n
+    oc.dyn_core(bdt, 2)
+    gc.dyn_core(bdt, 2)
+    for t in oc.tiles:
+        _assert(H.compare(oc.eng[t], gc.eng[t], H.regions_state(case.bounds)), TOL_RUN)
+    oc.close(); gc.close()
