@@ -288,6 +288,11 @@ def run_ours(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": DSW_DRAM_TRAFFIC.get((n, npz, args.flagset)), "peak_source": which, "algorithmic_bytes_per_launch": alg,
                          "ms_per_launch": dsw_solo_ms,
+                         # secondary ceiling: fp64 CUDA-core throughput.  FLOP model: 1.1 kFLOP per cell and d_sw call
+                         # (4-5 fv_tp_2d + 2 momentum PPM sweeps + damping); peak = DFMA rate measured with
+                         # profiles/micro/fp64_rate.cu on this pool's B200 (60.4 lanes/clk/SM x 148 SMs x 1.965 GHz x 2)
+                         "fp64": {"flop_per_cell": 1100, "achieved_tflops": (1100.0 * n * n * npz / (dsw_solo_ms / 1e3) / 1e12) if dsw_solo_ms else None,
+                                  "peak_tflops": 35.1, "peak_source": "measured DFMA rate, profiles/r1_fp64_rate_b200.txt"},
                          "launch": "one fv3_d_sw call = every kernel of d_sw for all npz levels of one face"},
             "stage_ms_per_call": {k: (v[0] / v[1] if v[1] else None) for k, v in stage_ms.items()},
             "clocks": clocks,

@@ -382,26 +382,13 @@ struct BFillY {
   }
 };
 
-// n-th pass, part 1: vc = d/dx divg * divg_u, uc = d/dy divg * divg_v  (:1392-1403)
-__global__ void __launch_bounds__(TI* TJ) k_dsw_dd_uv(Lay L, DevGrid G, const double* __restrict__ dg, double* __restrict__ vcs,
-                                                     double* __restrict__ ucs, const int* kint, int n) {
-  PLANE_IJK
-  const int nord = kint[KI_NORD * (L.npz + 1) + k];
-  if (n > nord) return;
-  const int nt = nord - n;
-  const bool fill_c = (nt != 0) && L.cube && (i < 4 || i > L.npx - 4) && (j < 4 || j > L.npy - 4);   // remaps exist in the corner regions only
-  if (i >= L.is - 1 - nt && i <= L.ie + 1 + nt && j >= L.js - nt && j <= L.je + 1 + nt) {
-    BFillX d{dg + ko, L, fill_c};
-    vcs[ko + LIDX(L, i, j)] = (d(i + 1, j) - d(i, j)) * G2(divg_u, i, j);
-  }
-  if (i >= L.is - nt && i <= L.ie + 1 + nt && j >= L.js - 1 - nt && j <= L.je + 1 + nt) {
-    BFillY d{dg + ko, L, fill_c};
-    ucs[ko + LIDX(L, i, j)] = (d(i, j + 1) - d(i, j)) * G2(divg_v, i, j);
-  }
-}
-// part 2: divg = div(uc, vc) * rarea_c with fill_corners(vc,uc,VECTOR,DGRID) views (:1405-1424)
-__global__ void __launch_bounds__(TI* TJ) k_dsw_dd_div(Lay L, DevGrid G, const double* __restrict__ vcs, const double* __restrict__ ucs,
-                                                      double* __restrict__ dg, const int* kint, int n, int stretched) {
+// n-th pass of the del-2N divergence damping (sw_core.F90:1387-1424) in ONE kernel:
+//   vc = d/dx divg * divg_u, uc = d/dy divg * divg_v   (with fill_corners(divg, BGRID) when nt != 0, :1387-1403)
+//   divg = div(uc, vc) * rarea_c                        (with fill_corners(vc, uc, VECTOR, DGRID), :1405-1424)
+// uc, vc are evaluated on the fly from divg (5-point footprint, L1-resident) instead of making a round trip through two
+// scratch planes: 2 array passes per iteration instead of 6.  dgi -> dgo ping-pong (a thread reads its neighbours).
+__global__ void __launch_bounds__(TI* TJ) k_dsw_dd_iter(Lay L, DevGrid G, const double* __restrict__ dgi, double* __restrict__ dgo,
+                                                       const int* kint, int n, int stretched) {
   PLANE_IJK
   const int nord = kint[KI_NORD * (L.npz + 1) + k];
   if (n > nord) return;
@@ -409,35 +396,40 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_dd_div(Lay L, DevGrid G, const d
   if (i < L.is - nt || i > L.ie + 1 + nt || j < L.js - nt || j > L.je + 1 + nt) return;
   const int npx = L.npx, npy = L.npy;
   const bool fill_c = (nt != 0) && L.cube && (i < 4 || i > npx - 4) && (j < 4 || j > npy - 4);   // remaps exist in the corner regions only
+  const double* d = dgi + ko;
+  BFillX dx_{d, L, fill_c};
+  BFillY dy_{d, L, fill_c};
+  auto vcs = [&](int ii, int jj) { return (dx_(ii + 1, jj) - dx_(ii, jj)) * G2(divg_u, ii, jj); };   // "vc"
+  auto ucs = [&](int ii, int jj) { return (dy_(ii, jj + 1) - dy_(ii, jj)) * G2(divg_v, ii, jj); };   // "uc"
   const double s = -1.0;
   // x = vc (u-like), y = uc (v-like): fv_mp_mod.F90:1262-1277
   auto VCv = [&](int ii, int jj) -> double {
     if (fill_c) {
-      if (ii <= 0 && jj <= 0) return s * AT(ucs, jj, 1 - ii);
-      if (ii <= 0 && jj >= npy + 1) return AT(ucs, npy + 1 - jj, npy - 1 + ii);
-      if (ii >= npx && jj <= 0) return AT(ucs, npx + 1 - jj, ii - npx + 1);
-      if (ii >= npx && jj >= npy + 1) return s * AT(ucs, npx + jj - npy, npy - ii + npx - 1);
+      if (ii <= 0 && jj <= 0) return s * ucs(jj, 1 - ii);
+      if (ii <= 0 && jj >= npy + 1) return ucs(npy + 1 - jj, npy - 1 + ii);
+      if (ii >= npx && jj <= 0) return ucs(npx + 1 - jj, ii - npx + 1);
+      if (ii >= npx && jj >= npy + 1) return s * ucs(npx + jj - npy, npy - ii + npx - 1);
     }
-    return AT(vcs, ii, jj);
+    return vcs(ii, jj);
   };
   auto UCv = [&](int ii, int jj) -> double {
     if (fill_c) {
-      if (ii <= 0 && jj <= 0) return s * AT(vcs, 1 - jj, ii);
-      if (ii <= 0 && jj >= npy) return AT(vcs, jj - npy + 1, npy + 1 - ii);
-      if (ii >= npx + 1 && jj <= 0) return AT(vcs, npx - 1 + jj, 1 - ii + npx);
-      if (ii >= npx + 1 && jj >= npy) return s * AT(vcs, npx - jj + npy - 1, npy + ii - npx);
+      if (ii <= 0 && jj <= 0) return s * vcs(1 - jj, ii);
+      if (ii <= 0 && jj >= npy) return vcs(jj - npy + 1, npy + 1 - ii);
+      if (ii >= npx + 1 && jj <= 0) return vcs(npx - 1 + jj, 1 - ii + npx);
+      if (ii >= npx + 1 && jj >= npy) return s * vcs(npx - jj + npy - 1, npy + ii - npx);
     }
-    return AT(ucs, ii, jj);
+    return ucs(ii, jj);
   };
-  double d = UCv(i, j - 1) - UCv(i, j) + VCv(i - 1, j) - VCv(i, j);
+  double dv = UCv(i, j - 1) - UCv(i, j) + VCv(i - 1, j) - VCv(i, j);
   if (L.cube) {
-    if (i == 1 && j == 1) d = d - UCv(1, 0);
-    if (i == npx && j == 1) d = d - UCv(npx, 0);
-    if (i == npx && j == npy) d = d + UCv(npx, npy);
-    if (i == 1 && j == npy) d = d + UCv(1, npy);
+    if (i == 1 && j == 1) dv = dv - UCv(1, 0);
+    if (i == npx && j == 1) dv = dv - UCv(npx, 0);
+    if (i == npx && j == npy) dv = dv + UCv(npx, npy);
+    if (i == 1 && j == npy) dv = dv + UCv(1, npy);
   }
-  if (!stretched) d = d * G2(rarea_c, i, j);
-  dg[ko + LIDX(L, i, j)] = d;
+  if (!stretched) dv = dv * G2(rarea_c, i, j);
+  dgo[ko + LIDX(L, i, j)] = dv;
 }
 
 // final damping term (both branches) and ke += term.  dterm = the reference's B-grid "vort".
@@ -445,7 +437,8 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_dd_div(Lay L, DevGrid G, const d
 __global__ void __launch_bounds__(TI* TJ) k_dsw_damp(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
                                                     const double* __restrict__ ua, const double* __restrict__ va, const double* __restrict__ uc,
                                                     const double* __restrict__ vc, const double* __restrict__ divg_in,
-                                                    const double* __restrict__ dg, const double* __restrict__ vortb, double* __restrict__ ke,
+                                                    const double* __restrict__ dg_even, const double* __restrict__ dg_odd,
+                                                    const double* __restrict__ vortb, double* __restrict__ ke,
                                                     double* __restrict__ dterm, const int* kint, const double* kdbl, double dt, double dddmp,
                                                     double d4_bg, int stretched) {
   PLANE_IJK
@@ -489,7 +482,7 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_damp(Lay L, DevGrid G, const dou
     const int n2 = nord + 1;
     const double dd8 = stretched ? G.da_min * pow(d4_bg, (double)n2) : pow(G.da_min_c * d4_bg, (double)n2);
     const double damp2 = G.da_min_c * fmax(d2_bg, fmin(0.20, dddmp * vo));
-    term = damp2 * dpc + dd8 * __ldg(dg + o);
+    term = damp2 * dpc + dd8 * __ldg(((nord & 1) ? dg_odd : dg_even) + o);   // result plane of the last ping-pong pass
   }
   dterm[o] = term;
   ke[o] = ke[o] + term;
@@ -956,20 +949,20 @@ int stage_d_sw(fv3_ctx* c, double dt) {
   k_dsw_vort<<<grd, blk, 0, st>>>(L, c->G, u, v, wk, vq);
   c->launches += 2;
   // --- divergence damping (:1290-1460)
-  double *dg = gy, *vcs = dfx, *ucs = dfy, *vortb = d2, *dterm = q_i;
+  double *dg_even = gy, *dg_odd = dfx, *vortb = d2, *dterm = q_i;   // ping-pong planes of the damping passes
   if (nord_max > 0) {
-    FV3_CUDA(c, cudaMemcpyAsync(dg, c->fld[FV3_DIVGD], (size_t)L.plane * nk * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    // pass n reads plane (n-1)&1 and writes plane n&1; plane "0" of pass 1 is divg_d itself (read-only)
     for (int n = 1; n <= nord_max; n++) {
-      k_dsw_dd_uv<<<grd, blk, 0, st>>>(L, c->G, dg, vcs, ucs, c->d_kint, n);
-      k_dsw_dd_div<<<grd, blk, 0, st>>>(L, c->G, vcs, ucs, dg, c->d_kint, n, c->b.stretched_grid);
-      c->launches += 2;
+      const double* src = (n == 1) ? c->fld[FV3_DIVGD] : ((n - 1) & 1) ? dg_odd : dg_even;
+      k_dsw_dd_iter<<<grd, blk, 0, st>>>(L, c->G, src, (n & 1) ? dg_odd : dg_even, c->d_kint, n, c->b.stretched_grid);
+      c->launches++;
     }
     if (f.dddmp >= 1.E-5) {
       if (!L.cube) return fv3_fail(c, -2, "d_sw: smag_corner (dddmp>0 on a doubly-periodic grid) not supported");
       rc = launch_a2b_ord4(c, wk, vortb, nk, 0); if (rc) return rc;
     }
   }
-  k_dsw_damp<<<grd, blk, 0, st>>>(L, c->G, u, v, c->fld[FV3_UA], c->fld[FV3_VA], uc, vc, c->fld[FV3_DIVGD], dg, vortb, ke, dterm,
+  k_dsw_damp<<<grd, blk, 0, st>>>(L, c->G, u, v, c->fld[FV3_UA], c->fld[FV3_VA], uc, vc, c->fld[FV3_DIVGD], dg_even, dg_odd, vortb, ke, dterm,
                                   c->d_kint, c->d_kdbl, dt, f.dddmp, f.d4_bg, c->b.stretched_grid);
   c->launches++;
   // --- vorticity transport and momentum update (:1476-1509), fused
