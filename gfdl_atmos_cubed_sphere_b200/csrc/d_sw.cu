@@ -177,10 +177,13 @@ __global__ void __launch_bounds__(TI* TJ, 4) k_dsw_wind(Lay L, DevGrid G, const 
   const long long o = ko + LIDX(L, i, j);
   // away from the face edges the closed-form edge / corner cases cannot apply: plain interior formulas, no call
   const bool inner = L.cube && i >= 3 && i <= L.npx - 2 && j >= 3 && j <= L.npy - 2;
+  // ut, vt themselves are read again only by k_dsw_ke, and there only in the edge / corner formulas (sw_core.F90:1078-1228:
+  // i or j within two cells of a face edge); everywhere else they need not reach HBM
+  const bool keep = !L.cube || i <= 4 || i >= L.npx - 3 || j <= 4 || j >= L.npy - 3;
   // ut on (is-1:ie+2, jsd:jed)
   if (j <= L.jed && i >= L.is - 1 && i <= L.ie + 2) {
     const double ut = inner ? W.UTg(i, j) : W.ut_final(i, j);
-    uts[o] = ut;
+    if (keep) uts[o] = ut;
     if (i >= L.is && i <= L.ie + 1) {  // :863-890, :923-927
       double xf = dt * ut, cr;
       if (xf > 0.) { cr = xf * G2(rdxa, i - 1, j); xf = G2(dy, i, j) * xf * SG(3, i - 1, j); }
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(TI* TJ, 4) k_dsw_wind(Lay L, DevGrid G, const 
   // vt on (isd:ied, js-1:je+2)
   if (i <= L.ied && j >= L.js - 1 && j <= L.je + 2) {
     const double vt = inner ? W.VTg(i, j) : W.vt_final(i, j);
-    vts[o] = vt;
+    if (keep) vts[o] = vt;
     if (j >= L.js && j <= L.je + 1) {  // :869-902, :933-936
       double yf = dt * vt, cr;
       if (yf > 0.) { cr = yf * G2(rdya, i, j - 1); yf = G2(dx, i, j) * yf * SG(4, i, j - 1); }
@@ -484,7 +487,7 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_damp(Lay L, DevGrid G, const dou
     const double damp2 = G.da_min_c * fmax(d2_bg, fmin(0.20, dddmp * vo));
     term = damp2 * dpc + dd8 * __ldg(((nord & 1) ? dg_odd : dg_even) + o);   // result plane of the last ping-pong pass
   }
-  dterm[o] = term;
+  if (dterm) dterm[o] = term;
   ke[o] = ke[o] + term;
 }
 
@@ -962,7 +965,8 @@ int stage_d_sw(fv3_ctx* c, double dt) {
       rc = launch_a2b_ord4(c, wk, vortb, nk, 0); if (rc) return rc;
     }
   }
-  k_dsw_damp<<<grd, blk, 0, st>>>(L, c->G, u, v, c->fld[FV3_UA], c->fld[FV3_VA], uc, vc, c->fld[FV3_DIVGD], dg_even, dg_odd, vortb, ke, dterm,
+  k_dsw_damp<<<grd, blk, 0, st>>>(L, c->G, u, v, c->fld[FV3_UA], c->fld[FV3_VA], uc, vc, c->fld[FV3_DIVGD], dg_even, dg_odd, vortb, ke,
+                                  (f.d_con > 1.e-5 || f.do_diss_est) ? dterm : nullptr,
                                   c->d_kint, c->d_kdbl, dt, f.dddmp, f.d4_bg, c->b.stretched_grid);
   c->launches++;
   // --- vorticity transport and momentum update (:1476-1509), fused
