@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_vort(Lay L, DevGrid G, const dou
   const double vt0 = AT(u, i, j) * G2(dx, i, j), vt1 = AT(u, i, j + 1) * G2(dx, i, j + 1);
   const double ut0 = AT(v, i, j) * G2(dy, i, j), ut1 = AT(v, i + 1, j) * G2(dy, i + 1, j);
   const double w = G2(rarea, i, j) * (vt0 - vt1 - ut0 + ut1);
-  wk[o] = w;
+  if (wk) wk[o] = w;   // the relative vorticity itself is read only by the Smagorinsky and vorticity-damping branches
   vq[o] = w + G2(f0, i, j);
 }
 
@@ -482,8 +482,7 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_damp(Lay L, DevGrid G, const dou
       const double vb = __ldg(vortb + o);
       vo = fabs(dt) * sqrt(dpc * dpc + vb * vb);
     }
-    const int n2 = nord + 1;
-    const double dd8 = stretched ? G.da_min * pow(d4_bg, (double)n2) : pow(G.da_min_c * d4_bg, (double)n2);
+    const double dd8 = kdbl[KD_DD8 * (L.npz + 1) + k];   // (da_min_c*d4_bg)^(nord+1), tabulated per level by the host (a pow per thread cost 0.1 ms)
     const double damp2 = G.da_min_c * fmax(d2_bg, fmin(0.20, dddmp * vo));
     term = damp2 * dpc + dd8 * __ldg(((nord & 1) ? dg_odd : dg_even) + o);   // result plane of the last ping-pong pass
   }
@@ -615,6 +614,8 @@ static void dsw_tables(fv3_ctx* c, std::vector<int>& ki, std::vector<double>& kd
     kd[KD_DAMP4_V * n1 + kk] = (damp_v > 1.E-5) ? pow(damp_v * c->G.da_min_c, (double)(nord_v + 1)) : 0.;   // :1513-1514
     kd[KD_DELN * n1 + kk] = (damp_v > 1.e-4) ? pow(damp_v * c->G.da_min, (double)(nord_v + 1)) : 0.;       // tp_core.F90:202-203, delp (nord_v, damp_v)
     kd[KD_DELN_T * n1 + kk] = (damp_t > 1.e-4) ? pow(damp_t * c->G.da_min, (double)(nord_t + 1)) : 0.;     // pt, q_con (nord_t, damp_t)
+    kd[KD_DD8 * n1 + kk] = c->b.stretched_grid ? c->G.da_min * pow(f.d4_bg, (double)(nord_k + 1))
+                                              : pow(c->G.da_min_c * f.d4_bg, (double)(nord_k + 1));            // sw_core.F90:1427-1431
   }
 }
 
@@ -949,7 +950,7 @@ int stage_d_sw(fv3_ctx* c, double dt) {
   double* ke = gx;      // B-grid (is:ie+1, js:je+1)
   k_dsw_ke<<<grd, blk, 0, st>>>(L, c->G, u, v, uc, vc, uts, vts, ke, dt, f.hord_mt);
   double *wk = uts, *vq = vts;   // contravariant winds are dead after KE
-  k_dsw_vort<<<grd, blk, 0, st>>>(L, c->G, u, v, wk, vq);
+  k_dsw_vort<<<grd, blk, 0, st>>>(L, c->G, u, v, (f.dddmp >= 1.E-5 || any_v) ? wk : nullptr, vq);
   c->launches += 2;
   // --- divergence damping (:1290-1460)
   double *dg_even = gy, *dg_odd = dfx, *vortb = d2, *dterm = q_i;   // ping-pong planes of the damping passes

@@ -6,7 +6,7 @@
 
 // per-level parameter tables living in c->d_kint / c->d_kdbl (FV3_KSLOTS slots x (npz+1))
 enum { KI_NORD = 0, KI_NORD_V = 1, KI_NORD_W = 2, KI_NORD_T = 3 };
-enum { KD_D2BG = 0, KD_DAMP_V = 1, KD_DAMP_W = 2, KD_DAMP_T = 3, KD_DCON = 4, KD_DAMP4_W = 5, KD_DAMP4_V = 6, KD_DELN = 7, KD_DELN_T = 8, KD_DZ = 9 };
+enum { KD_D2BG = 0, KD_DAMP_V = 1, KD_DAMP_W = 2, KD_DAMP_T = 3, KD_DCON = 4, KD_DAMP4_W = 5, KD_DAMP4_V = 6, KD_DELN = 7, KD_DELN_T = 8, KD_DZ = 9, KD_DD8 = 10 };
 #define FV3_KSLOTS 12
 
 struct Tp2d {
