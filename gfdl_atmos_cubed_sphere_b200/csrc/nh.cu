@@ -515,23 +515,6 @@ __global__ void __launch_bounds__(CB, 8) k_edge_profile(Lay L, const double* __r
   }
 #undef LV
 }
-// zh update from the transport fluxes (nh_utils.F90:282-299); del6 term only where damp(k) > 1e-5
-__global__ void __launch_bounds__(TI* TJ) k_dzd_upd(Lay L, DevGrid G, const double* __restrict__ zh, const double* __restrict__ fx,
-                                                   const double* __restrict__ fy, const double* __restrict__ xfa, const double* __restrict__ yfa,
-                                                   const double* __restrict__ dfx, const double* __restrict__ dfy, const double* kdbl,
-                                                   double* __restrict__ zn) {
-  const int i = L.isd - FV3_IOFF + blockIdx.x * TI + threadIdx.x;
-  const int j = L.jsd + blockIdx.y * TJ + threadIdx.y;
-  const int k = blockIdx.z;   // 0..km
-  if (i < L.is || i > L.ie || j < L.js || j > L.je) return;
-  const long long o = LIDX(L, i, j) + (long long)k * L.plane;
-  const double ar = __ldg(G.area + LIDX(L, i, j));
-  const double rax = ar + xfa[o] - xfa[o + 1], ray = ar + yfa[o] - yfa[o + L.NI];
-  double z = (__ldg(zh + o) * ar + fx[o] - fx[o + 1] + fy[o] - fy[o + L.NI]) / (rax + ray - ar);
-  if (kdbl[KD_DZ * (L.npz + 1) + k] != 0.) z = z + (dfx[o] - dfx[o + 1] + dfy[o] - dfy[o + L.NI]) * __ldg(G.rarea + LIDX(L, i, j));
-  zn[o] = z;
-}
-
 // ---- small column / pointwise helpers -------------------------------------------------------
 __global__ void __launch_bounds__(CB) k_pk3_halo(Lay L, const double* __restrict__ delp, double* __restrict__ pk3, double ptop, double akap) {
   // ring cells: 2-wide frame around the compute domain excluding ... (dyn_core.F90:1405-1445)
@@ -683,12 +666,7 @@ int stage_update_dz_d(fv3_ctx* c, double dt) {
   k_edge_profile<<<col_blocks(nix, njx), CB, 0, c->stream>>>(L, c->fld[FV3_CRX], c->fld[FV3_XFX], crxa, xfxa, c->d_edge_tab, L.is, L.ie + 1, L.jsd, L.jed);
   k_edge_profile<<<col_blocks(niy, njy), CB, 0, c->stream>>>(L, c->fld[FV3_CRY], c->fld[FV3_YFX], crya, yfxa, c->d_edge_tab, L.isd, L.ied, L.js, L.je + 1);
   c->launches += 2;
-  Tp2d tp;
-  tp.q = c->fld[FV3_ZH]; tp.crx = crxa; tp.cry = crya; tp.xfx = xfxa; tp.yfx = yfxa; tp.ra_x = nullptr; tp.ra_y = nullptr;
-  tp.fx = fx; tp.fy = fy; tp.mfx = nullptr; tp.mfy = nullptr; tp.hord = c->f.hord_tm; tp.nk = n1;
-  tp.fx2 = fx2; tp.fy2 = fy2; tp.q_i = q_i; tp.q_j = q_j;
-  int rc = launch_tp2d(c, tp); if (rc) return rc;
-  if (any) {
+  if (any) {   // del-n damping fluxes of zh first: the transport epilogue consumes them
     Deln dl;
     dl.q = c->fld[FV3_ZH]; dl.fx2 = dfx; dl.fy2 = dfy; dl.d2 = d2; dl.slot_nord = KI_NORD_V; dl.slot_damp = KD_DZ; dl.thresh = 0;
     dl.premul = 1; dl.nk = n1; dl.nord_const = 0; dl.damp_const = 0;
@@ -697,11 +675,15 @@ int stage_update_dz_d(fv3_ctx* c, double dt) {
       if (kd[k] != 0.) { dl.k_lo = std::min(dl.k_lo, k); dl.k_hi = std::max(dl.k_hi, k); dl.nord_max = std::max(dl.nord_max, ki[k]); }
     launch_deln(c, dl);
   }
-  dim3 blk(TI, TJ), grd((L.NI + TI - 1) / TI, (L.NJ + TJ - 1) / TJ, n1);
-  k_dzd_upd<<<grd, blk, 0, c->stream>>>(L, c->G, c->fld[FV3_ZH], fx, fy, xfxa, yfxa, dfx, dfy, c->d_kdbl, zn);
+  Tp2d tp;
+  tp.q = c->fld[FV3_ZH]; tp.crx = crxa; tp.cry = crya; tp.xfx = xfxa; tp.yfx = yfxa; tp.ra_x = nullptr; tp.ra_y = nullptr;
+  tp.fx = fx; tp.fy = fy; tp.mfx = nullptr; tp.mfy = nullptr; tp.hord = c->f.hord_tm; tp.nk = n1;
+  tp.fx2 = fx2; tp.fy2 = fy2; tp.q_i = q_i; tp.q_j = q_j;
+  tp.zn = zn; tp.zn_dfx = dfx; tp.zn_dfy = dfy; tp.zn_slot = KD_DZ;   // height update fused into the transport epilogue
+  int rc = launch_tp2d(c, tp); if (rc) return rc;
   const int n = L.ie - L.is + 1;
   k_dz_clamp<<<col_blocks(n, n), CB, 0, c->stream>>>(L, zn, c->fld[FV3_ZH], c->fld[FV3_PHIS], c->fld[FV3_WS], 1.0 / c->f.grav, 1.0 / dt, 0);
-  c->launches += 2;
+  c->launches += 1;
   return 0;
 }
 

@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, tpt::
                                                        const double* __restrict__ xfx, const double* __restrict__ yfx,
                                                        const double* __restrict__ ra_x, const double* __restrict__ ra_y,
                                                        const double* __restrict__ mfx, const double* __restrict__ mfy,
-                                                       double* __restrict__ fx, double* __restrict__ fy, int ord_in, int ord_ou) {
+                                                       double* __restrict__ fx, double* __restrict__ fy, int ord_in, int ord_ou,
+                                                       tpt::ZnEpi Z) {
   using namespace tpt;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -44,6 +45,27 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, tpt::
   // epilogue: lane = column; the tile stores its own west/south faces, plus the face's last column / row
   const bool lastx = T.i0 + TX > L.ie, lasty = T.j0 + TY > L.je;
   const int c = T.lane - 3, i = T.i0 + c;
+  if (Z.zn) {
+    // update_dz_d (nh_utils.F90:282-299): the advected height straight from the tile, fluxes never stored:
+    //   zn = (zh*area + fx(i)-fx(i+1) + fy(j)-fy(j+1)) / (ra_x + ra_y - area)  [+ del-n damping flux divergence]
+    const double coef = Z.kdbl ? Z.kdbl[Z.slot * (L.npz + 1) + blockIdx.z] : 0.;
+#pragma unroll
+    for (int r = T.wid; r < TY; r += NW) {
+      const int j = T.j0 + r;
+      if (c < 0 || c >= TX || i > L.ie || j > L.je) continue;
+      const int o = T.idx(i, j);
+      const double ar = S.area[r + 3][c + 3];
+      const double x0 = S.xfx[r + 3][c + 3], x1 = S.xfx[r + 3][c + 4], y0 = S.yfx[r + 3][c + 3], y1 = S.yfx[r + 4][c + 3];
+      const double rax = ar + x0 - x1, ray = ar + y0 - y1;
+      double z = (S.q[r + 3][c + 3] * ar + FX(S, r, c) * x0 - FX(S, r, c + 1) * x1 + FY(S, r, c) * y0 - FY(S, r + 1, c) * y1) / (rax + ray - ar);
+      if (coef != 0.) {
+        const long long g = T.ko + o;
+        z = z + (Z.dfx[g] - Z.dfx[g + 1] + Z.dfy[g] - Z.dfy[g + T.NI]) * __ldg(G.rarea + o);
+      }
+      Z.zn[T.ko + o] = z;
+    }
+    return;
+  }
   fx += T.ko; fy += T.ko;
 #pragma unroll
   for (int r = T.wid; r <= TY; r += NW) {
@@ -71,9 +93,11 @@ int launch_tp2d(fv3_ctx* c, const Tp2d& a) {
     FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
     attr_set = true;
   }
+  const tpt::ZnEpi Z{a.zn, a.zn_dfx, a.zn_dfy, a.zn ? c->d_kdbl : nullptr, a.zn_slot};
+  if (a.zn && (a.ra_x || a.ra_y || a.mfx)) return fv3_fail(c, -1, "fv_tp_2d: the fused height update takes no ra_x / ra_y / mfx");
 #define TP_LAUNCH(MONO, EDGE, M, N)                                                                                          \
   k_tp_fused<MONO, EDGE><<<dim3(N, 1, a.nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(L, c->G, M, a.q, a.crx, a.cry, a.xfx, a.yfx, \
-                                                                                       a.ra_x, a.ra_y, a.mfx, a.mfy, a.fx, a.fy, ord_in, a.hord)
+                                                                                       a.ra_x, a.ra_y, a.mfx, a.mfy, a.fx, a.fy, ord_in, a.hord, Z)
   if (a.hord >= 8) { if (n_in) TP_LAUNCH(true, false, Min, n_in); if (n_fr) TP_LAUNCH(true, true, Mfr, n_fr); }
   else { if (n_in) TP_LAUNCH(false, false, Min, n_in); if (n_fr) TP_LAUNCH(false, true, Mfr, n_fr); }
 #undef TP_LAUNCH

@@ -51,6 +51,9 @@ struct Smem {
 __device__ __forceinline__ double& FX(Smem& S, int r, int c) { return S.fx2[r + 3][c + 3]; }   // r < TY, c <= TX
 __device__ __forceinline__ double& FY(Smem& S, int r, int c) { return S.fy2[r + 3][c + 3]; }   // r <= TY, c < TX
 
+// optional fused epilogue of the stand-alone transport: the height update of update_dz_d (tp2d.cu)
+struct ZnEpi { double* zn; const double *dfx, *dfy; const double* kdbl; int slot; };
+
 // strided view of a shared-memory line in sweep coordinates: value at sweep index s
 struct SAcc {
   const double* p; int stride; int org;
