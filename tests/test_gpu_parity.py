@@ -309,3 +309,27 @@ def test_dyn_core_baseline_config_sizes(n):
     for t in oc.tiles:
         _assert(H.compare(oc.eng[t], gc.eng[t], H.regions_state(case.bounds)), TOL_RUN)
     oc.close(); gc.close()
+
+
+def test_dyn_core_moist_flags():
+    """the second flag-set-A run with the non-hydrostatic defaults use_cond = T, moist_kappa = T
+    (fv_arrays.F90:1226-1227): condensate-free pressure in the Riemann solvers (nh_utils.F90:412-447, nh_core.F90:120-165),
+    per-cell cappa, q_con transported in d_sw.  Two substeps of the full cube against the oracle."""
+    n, npz = 16, 7
+    case = H.Case(n, npz, "A", state="baroclinic", flags_override=dict(use_cond=1, moist_kappa=1))
+    rng = np.random.default_rng(20241117)
+    oc = H.OracleCube(case)
+    gc = H.CudaCube(case)
+    for t in oc.tiles:
+        qc = 0.01 * rng.random(oc.eng[t].shape("QCON"))
+        cp = 0.2857 * (1.0 - 0.05 * rng.random(oc.eng[t].shape("CAPPA")))
+        for e in (oc.eng[t], gc.eng[t]):
+            e.put("QCON", qc); e.put("CAPPA", cp)
+    oc.dyn_core(800.0, 2)
+    gc.dyn_core(800.0, 2)
+    regions = dict(H.regions_state(case.bounds))
+    b = case.bounds
+    regions["QCON"] = (b["is_"], b["ie"], b["js"], b["je"])
+    for t in oc.tiles:
+        _assert(H.compare(oc.eng[t], gc.eng[t], regions), TOL_RUN)
+    oc.close(); gc.close()
