@@ -65,6 +65,7 @@ static void set_dims(fv3_ctx* c) {
   d[FV3_WORK_FY] = {b.is, nic, b.js, njc + 1, kz, 0};
   d[FV3_WORK_RAX] = {b.is, nic, b.jsd, nja, kz, 0};
   d[FV3_WORK_RAY] = {b.isd, nia, b.js, njc, kz, 0};
+  d[FV3_DP1] = A(kz);
 }
 
 // native (Fortran) <-> padded device plane repacking.  dir=0: native->device, 1: device->native

@@ -138,6 +138,7 @@ struct NcclApi {
   int (*GroupStart)();
   int (*GroupEnd)();
   const char* (*GetErrorString)(int);
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 };
 
 struct HaloPlan {
@@ -166,6 +167,7 @@ static int nccl_load(fv3_ctx* c) {
   *(void**)(&g_nccl.GroupStart) = dlsym(h, "ncclGroupStart");
   *(void**)(&g_nccl.GroupEnd) = dlsym(h, "ncclGroupEnd");
   *(void**)(&g_nccl.GetErrorString) = dlsym(h, "ncclGetErrorString");
+  *(void**)(&g_nccl.AllReduce) = dlsym(h, "ncclAllReduce");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd)
     return fv3_fail(c, -4, "libnccl is missing required symbols");
   return 0;
@@ -211,6 +213,7 @@ static void group_specs(fv3_ctx* c, int g, std::vector<FieldSpec>& s) {
       s.push_back({FV3_PKC, -1, POS_CENTER, 0, 0, kz + 1, 3, 0});
       break;
     case FV3_HALO_UV_EDGE: s.push_back({FV3_U, FV3_V, POS_NORTH, POS_EAST, 1, kz, 3, 1}); break;
+    case FV3_HALO_TRACER: s.push_back({FV3_WORK_Q, -1, POS_CENTER, 0, 0, kz, 3, 0}); break;
   }
 }
 
@@ -527,3 +530,15 @@ int fv3_halo_exchange(fv3_ctx** ctxs, int nctx, int group) {
 }
 
 }  // extern "C"
+
+// Element-wise maximum of n doubles over all ranks of the library's communicator (mp_reduce_max of the reference,
+// fv_mp_mod.F90; used by tracer_2d for the per-level CFL number).  vals: device buffer on c's device, reduced in place on
+// c's stream.  Without a communicator (single process) this is a no-op.
+int halo_allreduce_max(fv3_ctx* c, double* vals, int n) {
+  HaloPlan* hp = c->halo;
+  if (!hp || !hp->comm) return 0;
+  if (!g_nccl.AllReduce) return fv3_fail(c, -4, "libnccl has no ncclAllReduce");
+  const int nrc = g_nccl.AllReduce(vals, vals, (size_t)n, /*ncclFloat64*/ 8, /*ncclMax*/ 2, hp->comm, c->stream);
+  if (nrc != 0) return fv3_fail(c, 1000 + nrc, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"));
+  return 0;
+}

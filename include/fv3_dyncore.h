@@ -140,6 +140,7 @@ enum fv3_field_id {
   FV3_WORK_FY,  /* (is:ie, js:je+1, nk) */
   FV3_WORK_RAX, /* (is:ie, jsd:jed, nk) */
   FV3_WORK_RAY, /* (isd:ied, js:je, nk) */
+  FV3_DP1,      /* delp before dyn_core (isd:ied, jsd:jed, npz): input of tracer_2d (fv_tracer2d.F90:50,63) */
   FV3_NUM_FIELDS
 };
 /* dims = {i_lo, ni, j_lo, nj, nk, k_middle(0/1)} */
@@ -213,6 +214,7 @@ enum fv3_halo_group {
   FV3_HALO_DELP_PT,   /* i_pack(1)(+11): delp, pt[, q_con]       dyn_core.F90:823-825,851 */
   FV3_HALO_ZH_PKC,    /* i_pack(4)/(5): zh, pkc                  dyn_core.F90:945-949,980,992 */
   FV3_HALO_UV_EDGE,   /* mpp_get_boundary(u,v) last substep      dyn_core.F90:1151-1163 */
+  FV3_HALO_TRACER,    /* q_pack / mpp_update_domains(qn2)         fv_tracer2d.F90:188,282 (the tracer lives in FV3_WORK_Q) */
   FV3_NUM_HALO_GROUPS
 };
 /* Link the six (or fewer) contexts of one process into a cube. tiles[i] is
@@ -245,6 +247,14 @@ int fv3_plane_index(const fv3_ctx *ctx, int i, int j);
  * bdt is the large (k_split) time step; dt = bdt/n_split (dyn_core.F90:223).
  * flags: bit0 = capture each substep in a CUDA graph. */
 int fv3_dyn_core(fv3_ctx **ctxs, int nctx, double bdt, int n_split, int flags);
+
+/* fv_tracer2d.F90:49-295 tracer_2d_1L for ONE tracer (nq = 1, trdm = 0, id_divg_mean = 0), all faces of this process in
+ * lockstep, after fv3_dyn_core: the tracer in FV3_WORK_Q (halo included) is advected in place with the accumulated mass
+ * fluxes / Courant numbers FV3_MFX, MFY, CX, CY of the acoustic loop and dp1 = FV3_DP1; like the reference the call
+ * rescales cx, cy, mfx, mfy by 1/nsplt(k) and leaves dp1 at its last intermediate value.  The per-level CFL maximum
+ * (mp_reduce_max, :161) is reduced over the faces of the process and, when fv3_comm_init was called, over all ranks with
+ * ncclAllReduce(max).  cmax_out (nullable, npz values) receives the reduced maxima. */
+int fv3_tracer_2d(fv3_ctx **ctxs, int nctx, int hord, double *cmax_out);
 /* kernels launched by this context since creation (bench.py gpu_launches) */
 long long fv3_launch_count(const fv3_ctx *ctx);
 /* device time (ms) accumulated in a named stage since last reset:

@@ -247,6 +247,67 @@ class OracleCube:
             if last:
                 self.halo("UV_EDGE")
 
+    def tracer_2d(self, hord):
+        """tracer_2d_1L (model/fv_tracer2d.F90:49-295; nq = 1, trdm = 0, id_divg_mean = 0) on the oracle side: the pointwise
+        statements in NumPy with the reference's operation order, the fluxes from the oracle's fv_tp_2d, the q halo updates
+        from the NumPy exchange, the CFL maximum over the six faces.  Operates on WORK_Q, DP1, CX, CY, MFX, MFY (XFX, YFX
+        are overwritten) exactly like fv3_tracer_2d; returns cmax(npz)."""
+        case = self.case
+        n, npz, b = case.n, case.npz, case.bounds
+        is_, ie, js, je, isd, jsd = b["is_"], b["ie"], b["js"], b["je"], b["isd"], b["jsd"]
+        I = np.arange(is_, ie + 2); J = np.arange(js, je + 2)
+        st = {}
+        cmax = np.zeros(npz)
+        for t in self.tiles:
+            e, g = self.eng[t], case.tiles[t - 1].arr
+            cx, cy = e.get("CX"), e.get("CY")          # (npz, jsd:jed, is:ie+1), (npz, js:je+1, isd:ied)
+            dxa, dya, dx, dy, sg = g["dxa"], g["dya"], g["dx"], g["dy"], g["sin_sg"]
+            xfx = np.where(cx > 0., cx * dxa[:, I - 1 - isd] * dy[:, I - isd] * sg[2][:, I - 1 - isd],
+                           cx * dxa[:, I - isd] * dy[:, I - isd] * sg[0][:, I - isd])            # :112-118
+            yfx = np.where(cy > 0., cy * dya[J - 1 - jsd, :] * dx[J - jsd, :] * sg[3][J - 1 - jsd, :],
+                           cy * dya[J - jsd, :] * dx[J - jsd, :] * sg[1][J - jsd, :])            # :121-127
+            acx = np.abs(cx[:, js - jsd:je - jsd + 1, 0:n]); acy = np.abs(cy[:, 0:n, is_ - isd:ie - isd + 1])
+            sg5 = sg[4][js - jsd:je - jsd + 1, is_ - isd:ie - isd + 1]
+            for k in range(npz):                                                                 # :131-145
+                m = np.maximum(acx[k], acy[k])
+                if not ((k + 1) < npz // 6):
+                    m = m + 1. - sg5
+                cmax[k] = max(cmax[k], float(m.max()))
+            st[t] = dict(cx=cx, cy=cy, xfx=xfx, yfx=yfx, mfx=e.get("MFX"), mfy=e.get("MFY"), dp1=e.get("DP1"),
+                         area=g["area"], rarea=g["rarea"][js - jsd:je - jsd + 1, is_ - isd:ie - isd + 1])
+        nsplt = (1. + cmax).astype(np.int64)                                                     # mp_reduce_max :161, :170
+        for t in self.tiles:
+            s = st[t]
+            for k in range(npz):
+                if nsplt[k] > 1:                                                                 # :171-190
+                    fr = 1. / float(nsplt[k])
+                    for nm in ("cx", "xfx", "cy", "yfx", "mfx", "mfy"):
+                        s[nm][k] = s[nm][k] * fr
+            s["ra_x"] = s["area"][None, :, is_ - isd:ie - isd + 1] + s["xfx"][:, :, :-1] - s["xfx"][:, :, 1:]     # :199-201
+            s["ra_y"] = s["area"][None, js - jsd:je - jsd + 1, :] + s["yfx"][:, :-1, :] - s["yfx"][:, 1:, :]     # :203-205
+            e = self.eng[t]
+            for f, nm in (("CRX", "cx"), ("CRY", "cy"), ("XFX", "xfx"), ("YFX", "yfx"), ("WORK_RAX", "ra_x"), ("WORK_RAY", "ra_y"),
+                          ("MFX", "mfx"), ("MFY", "mfy"), ("CX", "cx"), ("CY", "cy")):
+                e.put(f, s[nm])
+        sl = (slice(None), slice(js - jsd, je - jsd + 1), slice(is_ - isd, ie - isd + 1))
+        for it in range(1, int(nsplt.max()) + 1):
+            self._exchange_scalar("WORK_Q")                                                      # q_pack :188 / qn2 :282
+            for t in self.tiles:
+                e, s = self.eng[t], st[t]
+                e.call("fv_tp_2d", npz, hord, 1, 0, 0, 0.0)
+                fx, fy = e.get("WORK_FX"), e.get("WORK_FY")
+                q = e.get("WORK_Q")
+                qi, d1 = q[sl], s["dp1"][sl]
+                dp2 = d1 + (s["mfx"][:, :, :-1] - s["mfx"][:, :, 1:] + s["mfy"][:, :-1, :] - s["mfy"][:, 1:, :]) * s["rarea"][None]   # :212
+                qn = (qi * d1 + (fx[:, :, :-1] - fx[:, :, 1:] + fy[:, :-1, :] - fy[:, 1:, :]) * s["rarea"][None]) / dp2          # :232,239,250
+                act = (it <= nsplt)[:, None, None]
+                q[sl] = np.where(act, qn, qi)
+                s["dp1"][sl] = np.where((it < nsplt)[:, None, None], dp2, d1)                    # :268-274
+                e.put("WORK_Q", q)
+        for t in self.tiles:
+            self.eng[t].put("DP1", st[t]["dp1"])
+        return cmax
+
     def close(self):
         for e in self.eng.values():
             e.close()

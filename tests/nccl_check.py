@@ -36,9 +36,27 @@ for t in my:
         if not np.array_equal(a, b):
             ok = False
             print(f"rank {rank} tile {t} field {f} differs: max {np.abs(a-b).max():.3e}")
+# tracer_2d: the CFL maximum is reduced over the ranks with ncclAllReduce(max) -- must equal the single-process reduction
+cm_d, cm_r = (C.c_double * 6)(), (C.c_double * 6)()
+for cb in (cube, ref):
+    for t in cb.tiles:
+        e = cb.eng[t]
+        e.put("WORK_Q", 1.0 + 0.01 * e.get("PT")); e.put("DP1", case.states[t - 1]["delp"])
+fn = lib[0].fv3_tracer_2d
+fn.restype = C.c_int
+assert fn(cube.ctxs, len(my), C.c_int(8), cm_d) == 0, cube.eng[my[0]].last_error()
+assert fn(ref.ctxs, 6, C.c_int(8), cm_r) == 0
+if list(cm_d) != list(cm_r):
+    ok = False
+    print(f"rank {rank}: reduced cmax differs", list(cm_d), list(cm_r))
+for t in my:
+    a, b = cube.eng[t].get("WORK_Q"), ref.eng[t].get("WORK_Q")
+    if not np.array_equal(a, b):
+        ok = False
+        print(f"rank {rank} tile {t} tracer differs: max {np.abs(a-b).max():.3e}")
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("NCCL halo exchange == single-process result:", bool(flag.item()))
+    print("NCCL halo exchange + all-reduce(max) == single-process result:", bool(flag.item()))
 dist.destroy_process_group()
 sys.exit(0 if flag.item() else 1)

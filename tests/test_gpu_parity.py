@@ -333,3 +333,60 @@ def test_dyn_core_moist_flags():
     for t in oc.tiles:
         _assert(H.compare(oc.eng[t], gc.eng[t], regions), TOL_RUN)
     oc.close(); gc.close()
+
+
+@pytest.mark.parametrize("hord", [8, -5])
+def test_tracer_2d_after_dyn_core(hord):
+    """tracer_2d_1L (fv_tracer2d.F90:49-295) with the mass fluxes / Courant numbers accumulated by the acoustic
+    loop: sub-cycling decided by the CFL maximum over all six faces (mp_reduce_max), fv_tp_2d with mass-flux weighting,
+    q = (q*dp1 + div f)/dp2.  Checks the reduced cmax, the advected tracer, dp1 and the rescaled cx, mfx against the oracle
+    (NumPy statements + the oracle's fv_tp_2d), and that the tracer mass sum(area*dp*q) is conserved."""
+    import ctypes as C
+    n, npz = 24, 8
+    case = H.Case(n, npz, "A", state="baroclinic")
+    oc = H.OracleCube(case)
+    gc = H.CudaCube(case)
+    b = case.bounds
+    is_, ie, js, je = b["is_"], b["ie"], b["js"], b["je"]
+    rng = np.random.default_rng(20241117)
+    dp1 = {t: oc.eng[t].get("DELP") for t in oc.tiles}                     # delp before dyn_core
+    oc.dyn_core(15000.0, 30)   # 30 substeps of 500 s: accumulated Courant numbers up to 1.6 at the jet levels -> sub-cycling
+    gc.dyn_core(15000.0, 30)
+    qs = {}
+    for t in oc.tiles:
+        g = case.tiles[t - 1].arr
+        lon, lat = g["agrid"][0], g["agrid"][1]
+        q = 1.0 + 0.5 * np.sin(3 * lon)[None] * np.cos(2 * lat)[None] + (lat[None] > 0.4) * 0.7 + 0.0 * dp1[t]
+        if hord == -5:
+            q = np.abs(q - 1.2)
+        qs[t] = q
+        for e in (oc.eng[t], gc.eng[t]):
+            e.put("WORK_Q", q); e.put("DP1", dp1[t])
+        for f in ("MFX", "MFY", "CX", "CY"):                              # identical inputs for the tracer step itself
+            gc.eng[t].put(f, oc.eng[t].get(f))
+    area = [case.tiles[t - 1].arr["area"][None, 3:-3, 3:-3] for t in oc.tiles]
+    m0 = sum(float(np.sum(H.sub(gc.eng[t], "WORK_Q", qs[t], 1, n, 1, n) * H.sub(gc.eng[t], "DP1", dp1[t], 1, n, 1, n) * area[t - 1]))
+             for t in gc.tiles)
+    cmax_o = oc.tracer_2d(hord)
+    cmax_g = (C.c_double * npz)()
+    fn = gc.lib[0].fv3_tracer_2d
+    fn.restype = C.c_int
+    rc = fn(gc.ctxs, 6, C.c_int(hord), cmax_g)
+    assert rc == 0, gc.eng[1].last_error()
+    assert np.allclose(np.array(cmax_g[:]), cmax_o, rtol=1e-13, atol=0)
+    assert int((1. + cmax_o).max()) >= 2, "the case must exercise sub-cycling"
+    for t in oc.tiles:
+        res = H.compare(oc.eng[t], gc.eng[t], {"WORK_Q": (is_, ie, js, je), "DP1": (is_, ie, js, je), "CX": (is_, ie + 1, b["jsd"], b["jed"]),
+                                               "MFX": (is_, ie + 1, js, je), "MFY": (is_, ie, js, je + 1)})
+        _assert(res, TOL_STAGE)
+    # tracer mass: sum(area*dp_final*q_final) = sum(area*dp1*q) with dp_final = dp1 + div(mf) accumulated over the sub-cycles
+    m1 = 0.0
+    for t in gc.tiles:
+        e = gc.eng[t]
+        q1 = H.sub(e, "WORK_Q", e.get("WORK_Q"), 1, n, 1, n)
+        mfx = H.sub(e, "MFX", e.get("MFX"), 1, n + 1, 1, n); mfy = H.sub(e, "MFY", e.get("MFY"), 1, n, 1, n + 1)
+        ns = (1. + cmax_o).astype(int)[:, None, None]
+        dpf = H.sub(e, "DP1", dp1[t], 1, n, 1, n) + ns * (mfx[:, :, :-1] - mfx[:, :, 1:] + mfy[:, :-1, :] - mfy[:, 1:, :]) / area[t - 1]
+        m1 += float(np.sum(q1 * dpf * area[t - 1]))
+    assert abs(m1 - m0) / abs(m0) < 1e-12
+    oc.close(); gc.close()
