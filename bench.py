@@ -278,7 +278,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C{n}L{npz} nonhydrostatic full cube (6 faces), n_split={n_split}, flag-set {args.flagset}, "
-                                   f"JW baroclinic wave, dt_atmos={bdt}s; faces/rank={len(tiles_of_rank(0, world))}",
+                                   f"JW baroclinic wave, set_eta L79 levels (var_hi, ptop 1 Pa), dt_atmos={bdt}s; faces/rank={len(tiles_of_rank(0, world))}",
                        "l2": "working set per stage (>= 6 fields x 96 MB per face) exceeds the 126 MB L2; no explicit flush",
                        "n_split": n_split, "faces": 6},
             "gpu_launches": int(launches),

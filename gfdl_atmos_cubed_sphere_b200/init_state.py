@@ -38,6 +38,92 @@ def hybrid_levels(npz, ptop=100.0, p0=1.0e5, eta_c=0.15, r=1.6):
     return ak, bk
 
 
+def set_eta_var_hi(km, ptop=1.0, pint=100.0e2, s_rate=1.03, rdgas=287.05, grav=9.80665):
+    """ak, bk, ks of the reference's automatic hybrid-level generator var_hi (tools/fv_eta.F90:1166-1341, the non-HIWPP,
+    UKMO-hybrid branch) as set_eta selects it for km = 79: ptop = 1 Pa, stretch_fac = 1.03, pint = 100 hPa
+    (fv_eta.F90:656-666, :296-297).  Statement-for-statement restatement incl. sm1_edge (:2313-2346, one pass)."""
+    assert km >= 26, "var_hi needs km - k_inc - 2 >= 9"
+    p00, k_inc, s0, t0 = 1.0e5, 15, 0.10, 270.0
+    pe1 = np.zeros(km + 2); peln = np.zeros(km + 2); ze = np.zeros(km + 2)      # 1-based
+    s_fac = np.zeros(km + 1); dz = np.zeros(km + 1); dlnp = np.zeros(km + 1)
+    pe1[1] = ptop; peln[1] = np.log(pe1[1]); pe1[km + 1] = p00; peln[km + 1] = np.log(pe1[km + 1])
+    ztop = rdgas / grav * t0 * (peln[km + 1] - peln[1])
+    s_inc = (1.0 - s0) / float(k_inc)
+    s_fac[km] = s0
+    for k in range(km - 1, km - k_inc - 1, -1):
+        s_fac[k] = s_fac[k + 1] + s_inc
+    s_fac[km - k_inc - 1] = 0.5 * (s_fac[km - k_inc] + s_rate)
+    for k in range(km - k_inc - 2, 8, -1):
+        s_fac[k] = s_rate * s_fac[k + 1]
+    s_fac[8] = 0.5 * (1.1 + s_rate) * s_fac[9]
+    s_fac[7] = 1.1 * s_fac[8]; s_fac[6] = 1.15 * s_fac[7]; s_fac[5] = 1.2 * s_fac[6]; s_fac[4] = 1.3 * s_fac[5]
+    s_fac[3] = 1.4 * s_fac[4]; s_fac[2] = 1.45 * s_fac[3]; s_fac[1] = 1.5 * s_fac[2]
+    sum1 = 0.0
+    for k in range(1, km + 1):
+        sum1 = sum1 + s_fac[k]
+    dz0 = ztop / sum1
+    for k in range(1, km + 1):
+        dz[k] = s_fac[k] * dz0
+    ze[km + 1] = 0.0
+    for k in range(km, 0, -1):
+        ze[k] = ze[k + 1] + dz[k]
+    for k in range(1, km + 1):                     # re-scale dz with the stretched ztop
+        dz[k] = dz[k] * (ztop / ze[1])
+    for k in range(km, 0, -1):
+        ze[k] = ze[k + 1] + dz[k]
+    # sm1_edge(..., ze, ntimes = 1): note its own dz = ze(k+1) - ze(k) (negative thicknesses)
+    df, k2, ntimes = 0.25, km - 1, 1
+    dzs = np.zeros(km + 1); flux = np.zeros(km + 2)
+    for k in range(1, km + 1):
+        dzs[k] = ze[k + 1] - ze[k]
+    for n in range(1, ntimes + 1):
+        k1 = 2 + (ntimes - n)
+        flux[k1] = 0.0; flux[k2 + 1] = 0.0
+        for k in range(k1 + 1, k2 + 1):
+            flux[k] = df * (dzs[k] - dzs[k - 1])
+        for k in range(k1, k2 + 1):
+            dzs[k] = dzs[k] - flux[k] + flux[k + 1]
+    for k in range(km, 0, -1):
+        ze[k] = ze[k + 1] - dzs[k]
+    for k in range(1, km + 1):                     # given z --> p
+        dz[k] = ze[k] - ze[k + 1]
+        dlnp[k] = grav * dz[k] / (rdgas * t0)
+    for k in range(2, km + 1):
+        peln[k] = peln[k - 1] + dlnp[k - 1]
+        pe1[k] = np.exp(peln[k])
+    ks = 0
+    for k in range(2, km + 1):
+        if pint < pe1[k]:
+            ks = k - 1
+            break
+    eta = np.zeros(km + 2)
+    for k in range(1, km + 2):
+        eta[k] = pe1[k] / pe1[km + 1]
+    ep, es = eta[ks + 1], eta[km]
+    alpha = (ep ** 2 - 2.0 * ep * es) / (es - ep) ** 2
+    beta = 2.0 * ep * es ** 2 / (es - ep) ** 2
+    gama = -(ep * es) ** 2 / (es - ep) ** 2
+    ak = np.zeros(km + 2); bk = np.zeros(km + 2)
+    for k in range(1, ks + 2):
+        ak[k] = eta[k] * 1.0e5; bk[k] = 0.0
+    for k in range(ks + 2, km + 1):
+        ak[k] = alpha * eta[k] + beta + gama / eta[k]
+        ak[k] = ak[k] * 1.0e5
+    ak[km + 1] = 0.0
+    for k in range(ks + 2, km + 1):
+        bk[k] = (pe1[k] - ak[k]) / pe1[km + 1]
+    bk[km + 1] = 1.0
+    return ak[1:].copy(), bk[1:].copy(), ks
+
+
+def model_levels(npz):
+    """Hybrid levels for a run: the reference's own set_eta result where it is restated (npz = 79), else hybrid_levels."""
+    if npz == 79:
+        ak, bk, _ = set_eta_var_hi(79)
+        return ak, bk
+    return hybrid_levels(npz)
+
+
 def _edge_dirs(g):
     """Unit tangent vectors + mid-point lon/lat of D-grid u (south) and v (west) edges."""
     lon, lat = g.arr["grid"]

@@ -45,7 +45,7 @@ class Case:
     def __init__(self, n, npz, flagset="A", state="smooth", flags_override=None):
         self.n, self.npz = n, npz
         self.tiles, self.bounds = cube_grid(n)
-        self.ak, self.bk = I.hybrid_levels(npz)
+        self.ak, self.bk = I.model_levels(npz)   # npz = 79: the reference set_eta levels (var_hi)
         self.flags = dict(FLAGSETS[flagset]) if isinstance(flagset, str) else dict(flagset)
         if flags_override:
             self.flags.update(flags_override)

@@ -98,3 +98,19 @@ def test_cxx_halo_tables_match_numpy_builder(built, spec):
                 ref[int(to_padded(tb.dst[k], pos))] = (int(tb.src_tile[k]), int(tb.src_comp[k]), int(to_padded(tb.src[k], psrc)), int(tb.sign[k]))
             got = {int(d[k]): (int(st[k]), int(sc[k]), int(s[k]), int(sg[k])) for k in range(d.size)}
             assert got == ref, (tile, ci)
+
+
+def test_set_eta_l79_levels():
+    """tools/fv_eta.F90 set_eta for km = 79 (var_hi, ptop = 1 Pa, stretch 1.03, pint = 100 hPa): structural properties of the
+    restated generator (no golden table exists in the reference: the levels are computed at run time)."""
+    from gfdl_atmos_cubed_sphere_b200 import init_state as I
+    ak, bk, ks = I.set_eta_var_hi(79)
+    assert ak.shape == (80,) and bk.shape == (80,)
+    assert ak[0] == 1.0 and bk[0] == 0.0 and ak[-1] == 0.0 and bk[-1] == 1.0
+    assert np.all(bk[:ks + 1] == 0.0) and np.all(np.diff(bk[ks:]) > 0.0)          # pure pressure above pint, sigma-like below
+    for ps in (1.0e5, 7.0e4, 5.0e4):
+        assert np.all(np.diff(ak + bk * ps) > 0.0)
+    p = ak + bk * 1.0e5
+    assert abs(p[ks] - 100.0e2) / 100.0e2 < 0.15                                  # pint is snapped to an interface near 100 hPa
+    dz = 287.05 / 9.80665 * 270.0 * np.diff(np.log(p))                            # isothermal thickness used by var_hi
+    assert 15.0 < dz[-1] < 60.0 and dz[-1] < dz[-2] < dz[-3]                       # thin, stretching layers at the surface
