@@ -207,39 +207,6 @@ __global__ void __launch_bounds__(TI* TJ, 4) k_dsw_wind(Lay L, DevGrid G, const 
 // ---------------------------------------------------------------------------------------------
 // scalar updates
 // ---------------------------------------------------------------------------------------------
-// q_out = q*delp + div(g)*rarea on the compute domain, halo copied through (sw_core.F90:985-999)
-__global__ void __launch_bounds__(TI* TJ) k_dsw_qdp(Lay L, DevGrid G, const double* __restrict__ q, const double* __restrict__ delp,
-                                                   const double* __restrict__ gx, const double* __restrict__ gy, double* __restrict__ qout) {
-  PLANE_IJK
-  if (i < L.isd || i > L.ied || j > L.jed) return;
-  const long long o = ko + LIDX(L, i, j);
-  if (i >= L.is && i <= L.ie && j >= L.js && j <= L.je)
-    qout[o] = __ldg(delp + o) * __ldg(q + o) + (gx[o] - gx[o + 1] + gy[o] - gy[o + L.NI]) * G2(rarea, i, j);
-  else
-    qout[o] = __ldg(q + o);
-}
-// pt, delp update + flux capacitors (sw_core.F90:928-940, :1053-1066)
-__global__ void __launch_bounds__(TI* TJ) k_dsw_ptdp(Lay L, DevGrid G, const double* __restrict__ pt, const double* __restrict__ delp,
-                                                    const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ gx,
-                                                    const double* __restrict__ gy, double* __restrict__ pt_out, double* __restrict__ delp_out,
-                                                    double* __restrict__ mfx, double* __restrict__ mfy) {
-  PLANE_IJK
-  if (i < L.isd || i > L.ied + 1 || j > L.jed + 1) return;
-  const long long o = ko + LIDX(L, i, j);
-  if (i >= L.is && i <= L.ie + 1 && j >= L.js && j <= L.je) mfx[o] = mfx[o] + fx[o];
-  if (i >= L.is && i <= L.ie && j >= L.js && j <= L.je + 1) mfy[o] = mfy[o] + fy[o];
-  if (i > L.ied || j > L.jed) return;
-  if (i >= L.is && i <= L.ie && j >= L.js && j <= L.je) {
-    const double ra = G2(rarea, i, j), dp = __ldg(delp + o);
-    double p = __ldg(pt + o) * dp + (gx[o] - gx[o + 1] + gy[o] - gy[o + L.NI]) * ra;
-    const double dpn = dp + (fx[o] - fx[o + 1] + fy[o] - fy[o + L.NI]) * ra;
-    delp_out[o] = dpn;
-    pt_out[o] = p / dpn;
-  } else {
-    delp_out[o] = __ldg(delp + o);
-    pt_out[o] = __ldg(pt + o);
-  }
-}
 // w damping increment and heating (sw_core.F90:951-982); hs = heat_s work plane, ds = diss_e
 __global__ void __launch_bounds__(TI* TJ) k_dsw_dw(Lay L, DevGrid G, const double* __restrict__ w, const double* __restrict__ fx2,
                                                   const double* __restrict__ fy2, double* __restrict__ dw, double* __restrict__ hs,
@@ -262,17 +229,6 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_dw(Lay L, DevGrid G, const doubl
   if (prevent) { hs[o] = dd8 - fmin(0., tmp); ds[o] = do_diss ? dd8 - tmp : 0.; }
   else { hs[o] = dd8 - tmp; ds[o] = do_diss ? dd8 - tmp : 0.; }
 }
-// w = w/delp (+dw), q_con = q_con/delp  (sw_core.F90:1262-1283); in place, pointwise
-__global__ void __launch_bounds__(TI* TJ) k_dsw_wfin(Lay L, double* __restrict__ w, const double* __restrict__ delp_new,
-                                                    const double* __restrict__ dw, const double* kdbl, int have_dw) {
-  PLANE_IJK
-  if (i < L.is || i > L.ie || j < L.js || j > L.je) return;
-  const long long o = ko + LIDX(L, i, j);
-  double v = w[o] / __ldg(delp_new + o);
-  if (have_dw && kdbl[KD_DAMP4_W * (L.npz + 1) + k] != 0.) v = v + dw[o];
-  w[o] = v;
-}
-
 // ---------------------------------------------------------------------------------------------
 // kinetic energy at cell corners (sw_core.F90:1078-1228)
 // ---------------------------------------------------------------------------------------------
@@ -490,29 +446,6 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_damp(Lay L, DevGrid G, const dou
   ke[o] = ke[o] + term;
 }
 
-// ---------------------------------------------------------------------------------------------
-// momentum update  (sw_core.F90:1500-1509), halo copied through
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TI* TJ) k_dsw_uv(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
-                                                  const double* __restrict__ ke, const double* __restrict__ fx, const double* __restrict__ fy,
-                                                  double* __restrict__ uo, double* __restrict__ vo) {
-  PLANE_IJK
-  if (i < L.isd || i > L.ied + 1 || j > L.jed + 1) return;
-  const long long o = ko + LIDX(L, i, j);
-  if (i <= L.ied) {
-    if (i >= L.is && i <= L.ie && j >= L.js && j <= L.je + 1)
-      uo[o] = __ldg(u + o) * G2(dx, i, j) + ke[o] - ke[o + 1] + fy[o];
-    else
-      uo[o] = __ldg(u + o);
-  }
-  if (j <= L.jed) {
-    if (i >= L.is && i <= L.ie + 1 && j >= L.js && j <= L.je)
-      vo[o] = __ldg(v + o) * G2(dy, i, j) + ke[o] - ke[o + L.NI] - fx[o];
-    else
-      vo[o] = __ldg(v + o);
-  }
-}
-
 // dissipative heating / dissipation estimate (:1462-1473, :1523-1586) and the vorticity-damping
 // momentum increments (:1589-1600).  ut_d, vt_d = del6_vt_flux outputs (x-flux "ut", y-flux "vt").
 __global__ void __launch_bounds__(TI* TJ) k_dsw_heat(Lay L, DevGrid G, const double* __restrict__ un, const double* __restrict__ vn,
@@ -621,7 +554,7 @@ static void dsw_tables(fv3_ctx* c, std::vector<int>& ki, std::vector<double>& kd
 
 // ---------------------------------------------------------------------------------------------
 // fused transport of delp, w, q_con, pt (sw_core.F90:919-1066, :1262-1283): ONE kernel per d_sw call.
-// A CTA owns a 32x16 tile of one level (tp_tile.cuh).  The Courant numbers / area fluxes are staged once and
+// A CTA owns a 26x24 tile of one level (tp_tile.cuh).  The Courant numbers / area fluxes are staged once and
 // shared by the fields; the mass fluxes of delp stay in shared memory and weight the fluxes of the other fields;
 // the flux divergences are applied in the epilogue (thread = one cell), so fx, fy, gx, gy never touch HBM.
 // The del-n damping fluxes (wide stencil, separate kernels) are read from global and added on the fly.

@@ -655,7 +655,7 @@ int stage_update_dz_d(fv3_ctx* c, double dt) {
   FV3_CUDA(c, cudaMemcpyAsync(c->d_kint + KI_NORD_V * n1, ki.data(), n1 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   FV3_CUDA(c, cudaMemcpyAsync(c->d_kdbl + KD_DZ * n1, kd.data(), n1 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   double *crxa = c->scr[0], *xfxa = c->scr[1], *crya = c->scr[2], *yfxa = c->scr[3];
-  double *fx = c->scr[5], *fy = c->scr[6], *fx2 = c->scr[7], *fy2 = c->scr[8], *q_i = c->scr[9], *q_j = c->scr[10];
+  double *fx = c->scr[5], *fy = c->scr[6];
   double *zn = c->scr[11], *dfx = c->scr[12], *dfy = c->scr[13], *d2 = c->scr[14];
   const int nix = L.ie + 1 - L.is + 1, njx = L.jed - L.jsd + 1, niy = L.ied - L.isd + 1, njy = L.je + 1 - L.js + 1;
   if (!c->d_edge_tab) {
@@ -678,7 +678,6 @@ int stage_update_dz_d(fv3_ctx* c, double dt) {
   Tp2d tp;
   tp.q = c->fld[FV3_ZH]; tp.crx = crxa; tp.cry = crya; tp.xfx = xfxa; tp.yfx = yfxa; tp.ra_x = nullptr; tp.ra_y = nullptr;
   tp.fx = fx; tp.fy = fy; tp.mfx = nullptr; tp.mfy = nullptr; tp.hord = c->f.hord_tm; tp.nk = n1;
-  tp.fx2 = fx2; tp.fy2 = fy2; tp.q_i = q_i; tp.q_j = q_j;
   tp.zn = zn; tp.zn_dfx = dfx; tp.zn_dfy = dfy; tp.zn_slot = KD_DZ;   // height update fused into the transport epilogue
   int rc = launch_tp2d(c, tp); if (rc) return rc;
   const int n = L.ie - L.is + 1;

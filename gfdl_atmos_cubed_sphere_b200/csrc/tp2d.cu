@@ -3,8 +3,8 @@
 //
 // Reference semantics: model/tp_core.F90:85-241 fv_tp_2d, :245-322 copy_corners,
 // :1267-1447 deln_flux; model/sw_core.F90:1608-1737 del6_vt_flux.
-// Design (not a translation): ONE launch per transport; a CTA owns a 32x16 tile of one level and
-// keeps the inner fluxes, q_i and q_j in shared memory (tp_tile.cuh).
+// Design (not a translation): ONE launch pair (interior / frame tiles) per transport; a CTA owns a 26x24 tile of one level
+// and keeps the inner fluxes, q_i and q_j in shared memory (tp_tile.cuh).
 // The cube-corner "copy_corners" transposes are NOT written into q: corner tiles load q
 // through a remapping accessor (ppm::QAccX / QAccY), so q stays read-only.
 #include "tp2d.cuh"
@@ -215,7 +215,6 @@ int stage_fv_tp_2d(fv3_ctx* c, int nk, int hord, int use_mfx, int use_mass, int 
   a.fx = c->fld[FV3_WORK_FX]; a.fy = c->fld[FV3_WORK_FY];
   a.mfx = use_mfx ? c->fld[FV3_MFX] : nullptr; a.mfy = use_mfx ? c->fld[FV3_MFY] : nullptr;
   a.hord = hord; a.nk = nk;
-  a.fx2 = c->scr[0]; a.fy2 = c->scr[1]; a.q_i = c->scr[2]; a.q_j = c->scr[3];
   if (nk > c->L.npz && (use_mfx || use_mass)) return fv3_fail(c, -1, "fv_tp_2d: mfx/mass only for nk <= npz");
   int rc = launch_tp2d(c, a);
   if (rc) return rc;

@@ -17,8 +17,6 @@ struct Tp2d {
   const double *mfx, *mfy;    // nullable: weight by xfx,yfx instead (tp_core.F90:213-226)
   int hord;
   int nk;
-  // scratch
-  double *fx2, *fy2, *q_i, *q_j;
   // optional: instead of storing fx, fy apply update_dz_d's height update (nh_utils.F90:282-299) in the epilogue:
   // zn = (q*area + div(fx, fy)) / (ra_x + ra_y - area) + del-n flux divergence (zn_dfx, zn_dfy, coefficient slot zn_slot)
   double* zn = nullptr; const double *zn_dfx = nullptr, *zn_dfy = nullptr; int zn_slot = 0;

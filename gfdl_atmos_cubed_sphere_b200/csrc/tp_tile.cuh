@@ -3,7 +3,7 @@
 // Reference semantics: model/tp_core.F90:85-241 (fv_tp_2d), :245-322 (copy_corners).
 // Why: in the three-launch form (first version) the intermediates fx2, fy2, q_i, q_j made a round trip through
 // HBM/L2 and every 6-point window was re-fetched through L1 by six different threads (ncu,
-// profiles/r1_dsw_ncu_summary.md).  Here a CTA of 16 warps owns a TX x TY = 26 x 20 block of cells of one level.
+// profiles/r1_dsw_ncu_summary.md).  Here a CTA of 16 warps owns a TX x TY = 26 x 24 block of cells of one level.
 // Every tile array is [QH][32]: the 32 lanes of a warp are the 26 cells + 3 + 3 halo columns of a row, a warp takes
 // whole rows (row index is warp-uniform, column = lane, no index arithmetic and no integer division in the body):
 //   I.  stage the Courant numbers, area fluxes and cell areas of the tile with cp.async       (once per tile)
