@@ -13,8 +13,11 @@
 // Not included (documented in DESIGN.md): the post-loop d_con heating del2_cubed
 // (dyn_core.F90:1300-1358), omega diagnostics (:1182-1215), Rayleigh friction, fast physics.
 #include "fv3_ctx.hpp"
+#include <cstdlib>
 
 extern "C" int fv3_halo_exchange(fv3_ctx** ctxs, int nctx, int group);
+extern "C" int fv3_halo_start(fv3_ctx** ctxs, int nctx, int group);
+extern "C" int fv3_halo_wait(fv3_ctx** ctxs, int nctx);
 
 #define FORALL(stmt)                                   \
   for (int a_ = 0; a_ < nctx; a_++) {                  \
@@ -39,6 +42,10 @@ extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, i
   FORALL(stage_zero_field(c, FV3_CY)) FORALL(stage_zero_field(c, FV3_HEAT))
   int rc;
   const bool hydrostatic = ctxs[0]->f.hydrostatic != 0;
+  // Overlapped delp/pt exchange (fv3_halo_start / fv3_halo_wait) is OFF by default: measured at N = 2, C384L79 it LOSES 2.6 %
+  // (209.8 vs 204.4 ms per step) -- the NCCL send/recv kernels of the side stream spin on SMs that the concurrent
+  // update_dz_d / Riem_Solver3 kernels need.  FV3_HALO_OVERLAP=1 turns it on for experiments.
+  static const bool overlap = std::getenv("FV3_HALO_OVERLAP") != nullptr;
   for (int it = 1; it <= n_split; it++) {
     const bool last_step = (it == n_split);
     if (hydrostatic) {   // geopk replaces the vertical solvers, one_grad_p the pressure gradient (dyn_core.F90:478-480, :905-907, :1017-1021)
@@ -73,9 +80,12 @@ extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, i
     FORALL(stage_p_grad_c(c, dt2))                                                        // :562
     if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DIVGD_UCVC))) return rc;   // :451,:565,:577-578
     FORALL(stage_d_sw(c, dt))                                                             // :666-812
-    if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;      // :823-825,:851
+    // delp, pt[, q_con] halos (:823-825 start, :851 complete): update_dz_d and Riem_Solver3 read the compute domain of delp, pt
+    // only, so the exchange MAY run on the side stream underneath them (see `overlap` above)
+    if (linked && (rc = (overlap ? fv3_halo_start(ctxs, nctx, FV3_HALO_DELP_PT) : fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT)))) return rc;
     FORALL(stage_update_dz_d(c, dt))                                                      // :911
     FORALL(stage_riem_solver3(c, dt, last_step ? 1 : 0))                                  // :932
+    if (linked && (rc = fv3_halo_wait(ctxs, nctx))) return rc;
     if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_ZH_PKC))) return rc;       // :945-949,:980,:992
     if (last_step) { FORALL(stage_pe_halo(c)) }                                           // :952-953
     FORALL(stage_pk3_halo(c))                                                             // :958

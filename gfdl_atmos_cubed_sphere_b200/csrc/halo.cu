@@ -150,6 +150,9 @@ struct HaloPlan {
   double *sendbuf[6], *recvbuf[6];
   size_t bufcap[6];
   std::vector<int*> dev_alloc;
+  cudaStream_t xstream;    // side stream of overlapped exchanges (fv3_halo_start / fv3_halo_wait)
+  cudaEvent_t xdone;
+  bool xpending;
 };
 
 static NcclApi g_nccl = {nullptr};
@@ -223,6 +226,7 @@ static int halo_build(fv3_ctx* c) {
   HaloPlan* hp = new HaloPlan();
   for (int t = 0; t < 6; t++) { hp->peer[t] = nullptr; hp->tile_rank[t] = -1; hp->sendbuf[t] = hp->recvbuf[t] = nullptr; }
   hp->comm = nullptr; hp->my_rank = 0; for (int t = 0; t < 6; t++) hp->bufcap[t] = 0;
+  hp->xstream = nullptr; hp->xdone = nullptr; hp->xpending = false;
   c->halo = hp;
   const int me = c->tile;
   for (int g = 0; g < FV3_NUM_HALO_GROUPS; g++) {
@@ -271,6 +275,8 @@ void halo_destroy(fv3_ctx* c) {
   for (int* p : hp->dev_alloc) cudaFree(p);
   for (int t = 0; t < 6; t++) { cudaFree(hp->sendbuf[t]); cudaFree(hp->recvbuf[t]); }
   if (hp->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(hp->comm);
+  if (hp->xstream) cudaStreamDestroy(hp->xstream);
+  if (hp->xdone) cudaEventDestroy(hp->xdone);
   delete hp;
   c->halo = nullptr;
 }
@@ -390,19 +396,33 @@ int fv3_comm_attach(fv3_ctx* c, void* nccl_comm, const int tile_rank[6]) {
   return 0;
 }
 
-int fv3_halo_exchange(fv3_ctx** ctxs, int nctx, int group) {
+}  // extern "C"
+
+// overlapped != 0: the exchange runs on ctx0's side stream after everything enqueued so far on the face streams, and the
+// face streams do NOT wait for it (fv3_halo_wait joins them): the caller may enqueue work that touches neither the halo
+// cells nor the edge cells of the group's fields in between (SURVEY 8e "Overlap": dyn_core hides the delp/pt exchange
+// behind update_dz_d + Riem_Solver3, which read the compute domain of delp, pt only).
+static int halo_exchange_impl(fv3_ctx** ctxs, int nctx, int group, int overlapped) {
   if (!ctxs || nctx < 1 || group < 0 || group >= FV3_NUM_HALO_GROUPS) return -1;
   fv3_ctx* c0 = ctxs[0];
   if (!c0->halo) return 0;   // no topology linked: frozen halo
   void* comm = c0->halo->comm;
   const int my_rank = c0->halo->my_rank;
-  // all faces of one process share ctx0's stream ordering: make ctx0's stream wait for the others
-  // (single-GPU multi-face mode enqueues every face on its own stream)
-  for (int a = 1; a < nctx; a++) {
-    cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    cudaEventRecord(ev, ctxs[a]->stream); cudaStreamWaitEvent(c0->stream, ev, 0); cudaEventDestroy(ev);
+  HaloPlan* hp0 = c0->halo;
+  if (hp0->xpending) return fv3_fail(c0, -1, "halo_exchange: an overlapped exchange is still pending (call fv3_halo_wait first)");
+  cudaSetDevice(c0->device);
+  if (overlapped && !hp0->xstream) {
+    FV3_CUDA(c0, cudaStreamCreateWithFlags(&hp0->xstream, cudaStreamNonBlocking));
+    FV3_CUDA(c0, cudaEventCreateWithFlags(&hp0->xdone, cudaEventDisableTiming));
   }
-  cudaStream_t st = c0->stream;
+  cudaStream_t st = overlapped ? hp0->xstream : c0->stream;
+  // all faces of one process share one stream ordering for the exchange: make that stream wait for the face streams
+  // (single-GPU multi-face mode enqueues every face on its own stream)
+  for (int a = 0; a < nctx; a++) {
+    if (ctxs[a]->stream == st) continue;
+    cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    cudaEventRecord(ev, ctxs[a]->stream); cudaStreamWaitEvent(st, ev, 0); cudaEventDestroy(ev);
+  }
   // ---- remote: size the message buffers, pack, send/recv, unpack
   bool any_remote = false;
   for (int a = 0; a < nctx; a++)
@@ -520,15 +540,31 @@ int fv3_halo_exchange(fv3_ctx** ctxs, int nctx, int group) {
         }
     }
   }
-  // the other faces' streams wait for the exchange
-  for (int a = 1; a < nctx; a++) {
-    cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    cudaEventRecord(ev, st); cudaStreamWaitEvent(ctxs[a]->stream, ev, 0); cudaEventDestroy(ev);
+  if (overlapped) {
+    cudaEventRecord(hp0->xdone, st);
+    hp0->xpending = true;
+  } else {
+    // the other faces' streams wait for the exchange
+    for (int a = 1; a < nctx; a++) {
+      cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      cudaEventRecord(ev, st); cudaStreamWaitEvent(ctxs[a]->stream, ev, 0); cudaEventDestroy(ev);
+    }
   }
   FV3_CUDA(c0, cudaGetLastError());
   return 0;
 }
 
+extern "C" {
+int fv3_halo_exchange(fv3_ctx** ctxs, int nctx, int group) { return halo_exchange_impl(ctxs, nctx, group, 0); }
+int fv3_halo_start(fv3_ctx** ctxs, int nctx, int group) { return halo_exchange_impl(ctxs, nctx, group, 1); }
+int fv3_halo_wait(fv3_ctx** ctxs, int nctx) {
+  if (!ctxs || nctx < 1) return -1;
+  HaloPlan* hp0 = ctxs[0]->halo;
+  if (!hp0 || !hp0->xpending) return 0;
+  for (int a = 0; a < nctx; a++) cudaStreamWaitEvent(ctxs[a]->stream, hp0->xdone, 0);
+  hp0->xpending = false;
+  return 0;
+}
 }  // extern "C"
 
 // Element-wise maximum of n doubles over all ranks of the library's communicator (mp_reduce_max of the reference,

@@ -225,6 +225,11 @@ int fv3_cube_link(fv3_ctx **ctxs, const int *tiles, int nctx);
 int fv3_comm_attach(fv3_ctx *ctx, void *nccl_comm, const int tile_rank[6]);
 /* Exchange one group for all linked contexts of this process. */
 int fv3_halo_exchange(fv3_ctx **ctxs, int nctx, int group);
+/* Overlapped form (start_group_halo_update / complete_group_halo_update of the reference, fv_mp_mod.F90:646-874): the
+ * exchange runs on a side stream; until fv3_halo_wait the caller may only enqueue work that touches neither the halo cells
+ * nor the edge cells of the group's fields.  One overlapped exchange may be pending at a time. */
+int fv3_halo_start(fv3_ctx **ctxs, int nctx, int group);
+int fv3_halo_wait(fv3_ctx **ctxs, int nctx);
 /* The library's own communicator: rank 0 calls fv3_nccl_unique_id (128 bytes), the id is
  * broadcast by the host program (torch.distributed / MPI), then every rank calls
  * fv3_comm_init with the face->rank map (6 ints, -1 = face absent). */
