@@ -119,3 +119,75 @@ def test_resting_isothermal_atmosphere_stays_at_rest(built):
         w = H.sub(oc.eng[t], "W", oc.eng[t].get("W"), 1, 12, 1, 12)
         assert np.abs(u).max() < 1e-6 and np.abs(w).max() < 1e-6, (t, np.abs(u).max(), np.abs(w).max())
     oc.close()
+
+
+def test_hydrostatic_resting_atmosphere_stays_at_rest(built):
+    """Hydrostatic branch (geopk + one_grad_p, dyn_core.F90:1909-2030, :2202-2356): u = v = 0, horizontally uniform
+    potential temperature, flat surface -> the Lin (1997) pressure-gradient terms cancel and the winds stay ~0; the delp
+    field is untouched; gz(top) - phis equals the analytic hydrostatic thickness cp*theta*(ps^kappa - ptop^kappa)."""
+    case = H.Case(12, 5, "A", state="baroclinic", flags_override=dict(hydrostatic=1))
+    pe = case.ak + case.bk * 1.0e5
+    kap, cp = case.consts["kappa"], case.consts["cp_air"]
+    theta = 300.0
+    dp = np.diff(pe)
+    for st in case.states:
+        st["u"][...] = 0.0; st["v"][...] = 0.0; st["phis"][...] = 0.0
+        st["pt"][...] = theta
+        st["delp"][...] = dp[:, None, None]
+    oc = H.OracleCube(case)
+    d0 = oc.eng[1].get("DELP").copy()
+    oc.dyn_core(600.0, 2)
+    for t in oc.tiles:
+        e = oc.eng[t]
+        u = H.sub(e, "U", e.get("U"), 1, 12, 1, 13); v = H.sub(e, "V", e.get("V"), 1, 13, 1, 12)
+        assert np.abs(u).max() < 1e-8 and np.abs(v).max() < 1e-8, (t, np.abs(u).max(), np.abs(v).max())
+    d1 = oc.eng[1].get("DELP")
+    assert np.abs(H.sub(oc.eng[1], "DELP", d1 - d0, 1, 12, 1, 12)).max() < 1e-9 * dp.max()
+    oc.close()
+    # geopk alone on the same column (fresh engine: after one_grad_p the gz field holds corner values in place)
+    e = case.engine(H.load_oracle(), 1)
+    case.load_state(e, 1)
+    e.call("geopk", 0)
+    gz = H.sub(e, "GZ", e.get("GZ"), 1, 12, 1, 12)
+    thick = cp * theta * (pe[-1] ** kap - pe[0] ** kap)
+    assert np.allclose(gz[0], thick, rtol=1e-12)
+    pkz = H.sub(e, "PKZ", e.get("PKZ"), 1, 12, 1, 12)
+    pk = pe ** kap
+    assert np.allclose(pkz[:, 0, 0], np.diff(pk) / (kap * np.diff(np.log(pe))), rtol=1e-12)
+    e.close()
+
+
+def test_tracer_2d_keeps_a_constant_tracer_constant_and_conserves_mass(built):
+    """tracer_2d_1L (fv_tracer2d.F90:49-295) with the mass fluxes accumulated by the acoustic loop: q == 1 stays 1
+    (dp2 = dp1 + div(mf) and fx = mfx make the update (dp1 + div mf)/dp2), and sum(area*dp*q) of a structured tracer is
+    conserved over the sub-cycles.  (Oracle-side restatement used as the checker of fv3_tracer_2d.)"""
+    n, npz = 12, 4
+    case = H.Case(n, npz, "A", state="baroclinic")
+    for hord, const in ((8, True), (-5, False)):
+        oc = H.OracleCube(case)
+        dp1 = {t: oc.eng[t].get("DELP") for t in oc.tiles}
+        oc.dyn_core(36000.0, 40)      # 40 substeps of 900 s at C12: accumulated Courant numbers up to 1.9 -> sub-cycling
+        q0 = {}
+        for t in oc.tiles:
+            g = case.tiles[t - 1].arr
+            q = np.ones(oc.eng[t].shape("WORK_Q")) if const else np.abs(np.sin(2 * g["agrid"][0])[None] * np.cos(g["agrid"][1])[None] + 0 * dp1[t])
+            q0[t] = q
+            oc.eng[t].put("WORK_Q", q); oc.eng[t].put("DP1", dp1[t])
+        area = {t: case.tiles[t - 1].arr["area"][None, 3:-3, 3:-3] for t in oc.tiles}
+        m0 = sum(float(np.sum(H.sub(oc.eng[t], "WORK_Q", q0[t], 1, n, 1, n) * H.sub(oc.eng[t], "DP1", dp1[t], 1, n, 1, n) * area[t])) for t in oc.tiles)
+        cmax = oc.tracer_2d(hord)
+        ns = (1. + cmax).astype(int)
+        assert ns.max() >= 2
+        m1 = 0.0
+        for t in oc.tiles:
+            e = oc.eng[t]
+            q1 = H.sub(e, "WORK_Q", e.get("WORK_Q"), 1, n, 1, n)
+            if const:
+                assert np.abs(q1 - 1.0).max() < 1e-13
+            else:
+                assert q1.min() > -1e-14                                     # hord -5 is positive definite
+            mfx = H.sub(e, "MFX", e.get("MFX"), 1, n + 1, 1, n); mfy = H.sub(e, "MFY", e.get("MFY"), 1, n, 1, n + 1)
+            dpf = H.sub(e, "DP1", dp1[t], 1, n, 1, n) + ns[:, None, None] * (mfx[:, :, :-1] - mfx[:, :, 1:] + mfy[:, :-1, :] - mfy[:, 1:, :]) / area[t]
+            m1 += float(np.sum(q1 * dpf * area[t]))
+        assert abs(m1 - m0) / abs(m0) < 1e-13
+        oc.close()
