@@ -43,7 +43,7 @@ class Grid(C.Structure):
 _FLAG_INTS = ["hord_mt", "hord_vt", "hord_tm", "hord_dp", "hord_tr", "nord", "n_sponge", "m_split",
               "hydrostatic", "do_vort_damp", "use_cond", "moist_kappa", "inline_q", "do_f3d",
               "use_logp", "convert_ke", "prevent_diss_cooling", "do_diss_est", "is_ideal_case",
-              "use_old_omega", "fill_dp", "pad_"]
+              "use_old_omega", "fill_dp", "sw_test_case"]
 _FLAG_DBLS = ["d4_bg", "d2_bg", "dddmp", "d2_bg_k1", "d2_bg_k2", "vtdm4", "d_con", "ke_bg", "d_ext",
               "a_imp", "p_fac", "beta", "lim_fac", "fast_tau_w_sec", "rf_cutoff", "d2bg_zq", "delt_max",
               "rdgas", "cp_air", "grav", "kappa", "radius", "omega", "pi", "ptop"]

@@ -204,6 +204,29 @@ __global__ void __launch_bounds__(TI* TJ, 4) k_dsw_wind(Lay L, DevGrid G, const 
   }
 }
 
+// SW_DYNAMICS build, test_case == 1 (sw_core.F90:626-651): Courant numbers / area fluxes from the PRESCRIBED C-grid winds
+__global__ void __launch_bounds__(TI* TJ) k_dsw_wind_sw1(Lay L, DevGrid G, const double* __restrict__ uc, const double* __restrict__ vc,
+                                                       double* __restrict__ crx, double* __restrict__ cry, double* __restrict__ xfx,
+                                                       double* __restrict__ yfx, double* __restrict__ cx, double* __restrict__ cy, double dt) {
+  PLANE_IJK
+  if (i < L.isd || i > L.ied + 1 || j > L.jed + 1) return;
+  const long long o = ko + LIDX(L, i, j);
+  if (j <= L.jed && i >= L.is && i <= L.ie + 1) {
+    const double sa = G2(sina_u, i, j);
+    double xf = dt * __ldg(uc + o) / sa;
+    const double cr = xf > 0. ? xf * G2(rdxa, i - 1, j) : xf * G2(rdxa, i, j);
+    xf = G2(dy, i, j) * xf * sa;
+    crx[o] = cr; xfx[o] = xf; cx[o] = cx[o] + cr;
+  }
+  if (i <= L.ied && j >= L.js && j <= L.je + 1) {
+    const double sa = G2(sina_v, i, j);
+    double yf = dt * __ldg(vc + o) / sa;
+    const double cr = yf > 0. ? yf * G2(rdya, i, j - 1) : yf * G2(rdya, i, j);
+    yf = G2(dx, i, j) * yf * sa;
+    cry[o] = cr; yfx[o] = yf; cy[o] = cy[o] + cr;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // scalar updates
 // ---------------------------------------------------------------------------------------------
@@ -659,6 +682,8 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_dsw_transport(Lay L, DevGrid G, 
       for (int n = 0; n < CELL_ITERS; n++) {
         const int r = 3 + T.wid + n * NW;
         if (xcell && r < TY + 3) dpn[n] = dp[n] + (S.mfx[r][c] - S.mfx[r][c + 1] + S.mfy[r][c] - S.mfy[r + 1][c]) * ra[n];
+        // delp is the only transported field (SW_DYNAMICS test_case 1, sw_core.F90:1055-1066): no pt epilogue will store it
+        if (!a.pt && xcell && r < TY + 3 && T.j0 - 3 + r <= L.je) a.delp_o[T.ko + T.idx(i, T.j0 - 3 + r)] = dpn[n];
       }
       continue;
     }
@@ -753,8 +778,8 @@ static int launch_transport_t(fv3_ctx* c, const DswTr& a, int nk) {
 }
 static int launch_transport(fv3_ctx* c, const DswTr& a, int nk) {
   const bool m_dp = a.hord_dp >= 8, m_vt = a.hord_vt >= 8, m_tm = a.hord_tm >= 8;
-  const bool vt_used = a.w != nullptr;
-  const bool all_mono = m_dp && m_tm && (m_vt || !vt_used), none_mono = !m_dp && !m_tm && (!m_vt || !vt_used);
+  const bool vt_used = a.w != nullptr, tm_used = a.pt != nullptr;
+  const bool all_mono = m_dp && (m_tm || !tm_used) && (m_vt || !vt_used), none_mono = !m_dp && (!m_tm || !tm_used) && (!m_vt || !vt_used);
   if (all_mono) return launch_transport_t<1>(c, a, nk);
   if (none_mono) return launch_transport_t<0>(c, a, nk);
   return launch_transport_t<2>(c, a, nk);
@@ -811,6 +836,35 @@ int stage_d_sw(fv3_ctx* c, double dt) {
   double *uc = c->fld[FV3_UC], *vc = c->fld[FV3_VC];
   double *crx = c->fld[FV3_CRX], *cry = c->fld[FV3_CRY], *xfx = c->fld[FV3_XFX], *yfx = c->fld[FV3_YFX];
 
+  if (f.sw_test_case == 1) {
+    // SW_DYNAMICS build with test_case = 1 (BASELINE config 1a): delp is advected by the prescribed uc, vc; the momentum part,
+    // pt, w, the damping of the winds are all skipped (sw_core.F90:626-651, :1055-1066, :1069, :1602)
+    k_dsw_wind_sw1<<<grd, blk, 0, st>>>(L, c->G, uc, vc, crx, cry, xfx, yfx, c->fld[FV3_CX], c->fld[FV3_CY], dt);
+    c->launches++;
+    DswTr tr{};
+    tr.delp = delp;
+    tr.crx = crx; tr.cry = cry; tr.xfx = xfx; tr.yfx = yfx;
+    tr.delp_o = c->alt_delp;
+    tr.mfx = c->fld[FV3_MFX]; tr.mfy = c->fld[FV3_MFY]; tr.kdbl = c->d_kdbl;
+    tr.hord_dp = f.hord_dp; tr.hord_vt = f.hord_dp; tr.hord_tm = f.hord_dp;
+    if (any_deln) {   // :919-920 (nord = nord_v, damp_c = damp_v apply in the SW build too)
+      Deln dl;
+      dl.d2 = d2; dl.nk = nk; dl.thresh = 0; dl.nord_const = 0; dl.damp_const = 0;
+      dl.q = delp; dl.fx2 = dfx; dl.fy2 = dfy; dl.slot_nord = KI_NORD_V; dl.slot_damp = KD_DELN; dl.premul = 1;
+      dl.k_lo = nk; dl.k_hi = -1; dl.nord_max = 0;
+      for (int k = 0; k < nk; k++)
+        if (kd[KD_DELN * n1 + k] != 0.) { dl.k_lo = std::min(dl.k_lo, k); dl.k_hi = std::max(dl.k_hi, k); dl.nord_max = std::max(dl.nord_max, ki[KI_NORD_V * n1 + k]); }
+      launch_deln(c, dl);
+      tr.dpx = dfx; tr.dpy = dfy;
+    }
+    int rc1 = launch_transport(c, tr, nk); if (rc1) return rc1;
+    FrameJobs fj{};
+    fj.j[0] = FrameJob{delp, c->alt_delp, L.ie, L.je}; fj.n = 1;
+    { const FrameGrid FG = frame_grid(L, L.is, L.ie, L.js, L.je); k_copy_frame<<<dim3(FG.count(), 1, nk), blk, 0, st>>>(L, FG, fj); }
+    c->launches++;
+    std::swap(c->fld[FV3_DELP], c->alt_delp);
+    return 0;
+  }
   k_dsw_wind<<<grd, blk, 0, st>>>(L, c->G, uc, vc, uts, vts, crx, cry, xfx, yfx, c->fld[FV3_CX], c->fld[FV3_CY], dt);
   c->launches++;
 

@@ -6,6 +6,7 @@
 //   -> update_dz_c -> Riem_Solver_C -> p_grad_c -> halo(divgd@corner, uc,vc) -> d_sw
 //   -> halo(delp,pt[,q_con]) -> update_dz_d -> Riem_Solver3 -> halo(zh,pkc)
 //   -> [pe_halo] pk3_halo -> gz = zh*grav -> nh_p_grad -> [last: shared-edge u,v de-dup]
+// the SW_DYNAMICS / test_case = 1 branch (BASELINE config 1a, flags.sw_test_case = 1):  d_sw (advection of delp only) -> halo(delp)
 // and the hydrostatic branch (BASELINE config 1b):
 //   halo(u,v[,delp,pt]) -> c_sw -> geopk(C) -> p_grad_c -> halo(divgd, uc,vc) -> d_sw -> halo(delp,pt) -> geopk(D) -> one_grad_p
 // One call replaces the whole it-loop; all faces owned by this process advance in lockstep
@@ -46,8 +47,18 @@ extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, i
   // (209.8 vs 204.4 ms per step) -- the NCCL send/recv kernels of the side stream spin on SMs that the concurrent
   // update_dz_d / Riem_Solver3 kernels need.  FV3_HALO_OVERLAP=1 turns it on for experiments.
   static const bool overlap = std::getenv("FV3_HALO_OVERLAP") != nullptr;
+  const bool sw_advection = ctxs[0]->f.sw_test_case == 1;
   for (int it = 1; it <= n_split; it++) {
     const bool last_step = (it == n_split);
+    if (sw_advection) {
+      // SW_DYNAMICS build, test_case = 1 (BASELINE config 1a): every `test_case > 1` block of the loop is skipped
+      // (dyn_core.F90:394-395 c_sw, :567-581 uc/vc exchange, :998-1176 pressure gradient); what is left is d_sw
+      // (pure advection of delp by the prescribed uc, vc) and the delp halo update (:823-851)
+      if (linked && it == 1 && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;
+      FORALL(stage_d_sw(c, dt))
+      if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;
+      continue;
+    }
     if (hydrostatic) {   // geopk replaces the vertical solvers, one_grad_p the pressure gradient (dyn_core.F90:478-480, :905-907, :1017-1021)
       if (linked) {
         if (it == 1 && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;

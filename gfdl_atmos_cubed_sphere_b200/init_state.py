@@ -270,3 +270,69 @@ def smooth_state(tiles, bounds, npz, seed=20241117, consts=None):
         for nm in ("delp", "pt", "w", "q_con"):
             _patch_corners(s[nm], ng, n)
     return states
+
+
+# ---- SW_DYNAMICS test case 1: cosine bell in solid-body rotation (BASELINE config 1a) ----------------------
+def great_circle_dist(lon1, lat1, lon2, lat2, radius):
+    """fv_grid_utils.F90:1974-1996 (haversine form)."""
+    beta = 2.0 * np.arcsin(np.sqrt(np.sin((lat1 - lat2) / 2.0) ** 2 + np.cos(lat1) * np.cos(lat2) * np.sin((lon1 - lon2) / 2.0) ** 2))
+    return radius * beta
+
+
+def cosine_bell_height(lon, lat, radius, lon_c=0.5 * np.pi, lat_c=0.0, gh0=1.0):
+    """test_cases.F90:923-941 (case 1): h = gh0/2 (1 + cos(pi r / r0)) inside r0 = radius/3 of the centre, 0 outside."""
+    r0 = radius / 3.0
+    r = great_circle_dist(lon_c, lat_c, lon, lat, radius)
+    return np.where(r < r0, gh0 * 0.5 * (1.0 + np.cos(np.pi * r / r0)), 0.0)
+
+
+def cosine_bell(tiles, bounds, alpha=0.0, consts=None):
+    """Williamson test case 1 as the SW_DYNAMICS build initialises it (test_cases.F90:923-942 + init_winds with
+    defOnGrid = 1, :211-503): delp = bell height (npz = 1), C-grid winds uc, vc from differences of the stream function
+    psi_b = -Ubar R (sin(lat) cos(alpha) - cos(lon) cos(lat) sin(alpha)) at the cell corners (:330-335, :405-420), halo by the
+    C-grid vector exchange (:421).  Ubar = 2 pi R / 12 days (:924).  Returns 6 dicts of native-extent arrays (1, nj, ni);
+    u, v are the D-grid analogue from psi at the cell centres (defOnGrid = 2 formulas, :428-443) for completeness, pt = 1."""
+    cst = dict(CONSTANTS)
+    if consts:
+        cst.update(consts)
+    R = cst["radius"]
+    ubar = 2.0 * np.pi * R / (12.0 * 86400.0)
+    n, ng = bounds["ie"], bounds["ng"]
+    ex = cs.Exchanger(n, ng)
+
+    def psi_of(lon, lat):
+        return -ubar * R * (np.sin(lat) * np.cos(alpha) - np.cos(lon) * np.cos(lat) * np.sin(alpha))
+
+    states = []
+    for g in tiles:
+        lon, lat = g.arr["agrid"]
+        lonb, latb = g.arr["grid"]
+        st = {}
+        st["delp"] = cosine_bell_height(lon, lat, R)[None].copy()
+        st["pt"] = np.ones_like(st["delp"])
+        psi_b = psi_of(lonb, latb)                                    # (nj+1, ni+1)
+        psi = psi_of(lon, lat)                                        # (nj, ni)
+        dx, dy, dxc, dyc = g.arr["dx"], g.arr["dy"], g.arr["dxc"], g.arr["dyc"]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            vc = (psi_b[:, 1:] - psi_b[:, :-1]) / dx                  # (nj+1, ni)   :405-411
+            uc = -(psi_b[1:, :] - psi_b[:-1, :]) / dy                 # (nj, ni+1)   :412-418
+            v = np.zeros_like(uc); u = np.zeros_like(vc)
+            v[:, 1:-1] = (psi[:, 1:] - psi[:, :-1]) / dxc[:, 1:-1]    # :428-434
+            u[1:-1, :] = -(psi[1:, :] - psi[:-1, :]) / dyc[1:-1, :]   # :435-441
+        for a in (uc, vc, u, v):
+            a[~np.isfinite(a)] = 0.0
+        st["uc_direct"], st["vc_direct"] = uc[None].copy(), vc[None].copy()   # analytic everywhere incl. the halo (tests)
+        # the reference computes the compute domain only and fills the halo by the exchange
+        ucc, vcc = np.zeros_like(uc), np.zeros_like(vc)
+        ucc[ng:ng + n, ng:ng + n + 1] = uc[ng:ng + n, ng:ng + n + 1]
+        vcc[ng:ng + n + 1, ng:ng + n] = vc[ng:ng + n + 1, ng:ng + n]
+        st["uc"], st["vc"] = ucc[None].copy(), vcc[None].copy()
+        st["u"], st["v"] = u[None].copy(), v[None].copy()
+        states.append(st)
+    ex.scalar([s["delp"] for s in states], cs.CENTER)
+    ex.scalar([s["pt"] for s in states], cs.CENTER)
+    ex.pair([s["uc"] for s in states], [s["vc"] for s in states], cs.EAST, cs.NORTH, kind="vector")
+    ex.pair([s["u"] for s in states], [s["v"] for s in states], cs.NORTH, cs.EAST, kind="vector")
+    for s in states:
+        _patch_corners(s["delp"], ng, n)
+    return states

@@ -72,7 +72,11 @@ typedef struct fv3_flags_t {
   int nord, n_sponge, m_split;
   int hydrostatic, do_vort_damp, use_cond, moist_kappa, inline_q, do_f3d;
   int use_logp, convert_ke, prevent_diss_cooling, do_diss_est, is_ideal_case;
-  int use_old_omega, fill_dp, pad_;
+  int use_old_omega, fill_dp;
+  int sw_test_case;     /* 0: the full (non-SW_DYNAMICS) path.  1: SW_DYNAMICS build with test_case = 1 (BASELINE config 1a):
+                         * d_sw advects delp with Courant numbers built from the PRESCRIBED uc, vc and skips the momentum
+                         * part (sw_core.F90:626-651, 1025-1026, 1069, 1602-1604); dyn_core skips c_sw, the vertical
+                         * solvers and the pressure gradient (dyn_core.F90:394-395, 567-581, 998-1176). */
   double d4_bg, d2_bg, dddmp, d2_bg_k1, d2_bg_k2, vtdm4, d_con, ke_bg, d_ext;
   double a_imp, p_fac, beta, lim_fac, fast_tau_w_sec, rf_cutoff, d2bg_zq, delt_max;
   /* constants_mod (FMS, not in the reference repo): run-time parameters */

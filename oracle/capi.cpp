@@ -220,7 +220,7 @@ int fv3o_d_sw(fv3o_ctx* c, double dt) {
     a.dddmp = f.dddmp; a.d2_bg = d2_divg_[k]; a.d4_bg = f.d4_bg; a.damp_v = c->damp_vt[k - 1]; a.damp_w = damp_w_[k];
     a.damp_t = damp_t_[k]; a.d_con = d_con_k_[k]; a.kgb = f.ke_bg; a.hydrostatic = f.hydrostatic != 0;
     a.use_cond = f.use_cond != 0; a.do_f3d = false; a.prevent_diss_cooling = f.prevent_diss_cooling != 0;
-    a.do_diss_est = f.do_diss_est != 0; a.lim_fac = f.lim_fac;
+    a.do_diss_est = f.do_diss_est != 0; a.lim_fac = f.lim_fac; a.sw_test_case = f.sw_test_case;
     L2 heat_s(bd.is, bd.ie, bd.js, bd.je), diss_e(bd.is, bd.ie, bd.js, bd.je), z_rat(bd.isd, bd.ied, bd.jsd, bd.jed, 1.0);
     // note the aliasing at dyn_core.F90:762: d_sw's delpc dummy is dyn_core's vt work array
     d_sw(F2(c, FV3_VT, k), F2(c, FV3_DELP, k), F2(c, FV3_PTC, k), F2(c, FV3_PT, k), F2(c, FV3_U, k), F2(c, FV3_V, k),

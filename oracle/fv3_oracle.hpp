@@ -168,6 +168,7 @@ struct DswArgs {
   double dt; int hord_tr, hord_mt, hord_vt, hord_tm, hord_dp; int nord, nord_v, nord_w, nord_t;
   double dddmp, d2_bg, d4_bg, damp_v, damp_w, damp_t, d_con, kgb; bool hydrostatic, use_cond;
   bool do_f3d, prevent_diss_cooling, do_diss_est; double lim_fac;
+  int sw_test_case = 0;   // 1: SW_DYNAMICS build, test_case = 1 (pure advection by the prescribed uc, vc)
 };
 void d_sw(V2 delpc, V2 delp, V2 ptc, V2 pt, V2 u, V2 v, V2 w, V2 uc, V2 vc, V2 ua, V2 va, V2 divg_d,
           V2 xflux, V2 yflux, V2 cx, V2 cy, V2 crx_adv, V2 cry_adv, V2 xfx_adv, V2 yfx_adv, V2 q_con,

@@ -958,6 +958,7 @@ void ytp_v(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed, V
 }
 
 // sw_core.F90:494-1606 (non-SW_DYNAMICS; inline_q=F; flagstruct%do_f3d only without ROT3)
+// + the SW_DYNAMICS / test_case == 1 pure-advection branch (a.sw_test_case == 1, BASELINE config 1a)
 void d_sw(V2 delpc, V2 delp, V2 ptc, V2 pt, V2 u, V2 v, V2 w, V2 uc, V2 vc, V2 ua, V2 va, V2 divg_d,
           V2 xflux, V2 yflux, V2 cx, V2 cy, V2 crx_adv, V2 cry_adv, V2 xfx_adv, V2 yfx_adv, V2 q_con,
           V2 z_rat, V2 heat_source, V2 diss_est, const DswArgs& a, const Grid& g, const Bd& bd) {
@@ -975,6 +976,40 @@ void d_sw(V2 delpc, V2 delp, V2 ptc, V2 pt, V2 u, V2 v, V2 w, V2 uc, V2 vc, V2 u
   L2 gx(is, ie + 1, js, je), gy(is, ie, js, je + 1);
   double damp, damp2, damp4, dd8;
   int is2, ie1, js2, je1;
+
+  if (a.sw_test_case == 1) {
+    // sw_core.F90:626-651 (SW_DYNAMICS, test_case == 1): Courant numbers and area fluxes from the prescribed C-grid winds
+    for (int j = jsd; j <= jed; j++)
+      for (int i = is; i <= ie + 1; i++) {
+        xfx_adv(i, j) = dt * uc(i, j) / g.sina_u(i, j);
+        if (xfx_adv(i, j) > 0.) crx_adv(i, j) = xfx_adv(i, j) * g.rdxa(i - 1, j);
+        else crx_adv(i, j) = xfx_adv(i, j) * g.rdxa(i, j);
+        xfx_adv(i, j) = g.dy(i, j) * xfx_adv(i, j) * g.sina_u(i, j);
+      }
+    for (int j = js; j <= je + 1; j++)
+      for (int i = isd; i <= ied; i++) {
+        yfx_adv(i, j) = dt * vc(i, j) / g.sina_v(i, j);
+        if (yfx_adv(i, j) > 0.) cry_adv(i, j) = yfx_adv(i, j) * g.rdya(i, j - 1);
+        else cry_adv(i, j) = yfx_adv(i, j) * g.rdya(i, j);
+        yfx_adv(i, j) = g.dx(i, j) * yfx_adv(i, j) * g.sina_v(i, j);
+      }
+    // :909-940 common part: ra_x, ra_y, transport of delp, flux capacitors
+    for (int j = jsd; j <= jed; j++) for (int i = is; i <= ie; i++) ra_x(i, j) = g.area(i, j) + xfx_adv(i, j) - xfx_adv(i + 1, j);
+    for (int j = js; j <= je; j++) for (int i = isd; i <= ied; i++) ra_y(i, j) = g.area(i, j) + yfx_adv(i, j) - yfx_adv(i, j + 1);
+    fv_tp_2d(delp, crx_adv, cry_adv, npx, npy, a.hord_dp, fx, fy, xfx_adv, yfx_adv, g, bd, ra_x, ra_y, a.lim_fac,
+             nullptr, nullptr, nullptr, true, a.nord_v, a.damp_v);
+    for (int j = jsd; j <= jed; j++) for (int i = is; i <= ie + 1; i++) cx(i, j) = cx(i, j) + crx_adv(i, j);
+    for (int j = js; j <= je; j++) for (int i = is; i <= ie + 1; i++) xflux(i, j) = xflux(i, j) + fx(i, j);
+    for (int j = js; j <= je + 1; j++) {
+      for (int i = isd; i <= ied; i++) cy(i, j) = cy(i, j) + cry_adv(i, j);
+      for (int i = is; i <= ie; i++) yflux(i, j) = yflux(i, j) + fy(i, j);
+    }
+    // :1055-1066 with SW_DYNAMICS: only delp is updated (pt untouched); :1069, :1602: the momentum part is skipped
+    for (int j = js; j <= je; j++)
+      for (int i = is; i <= ie; i++)
+        delp(i, j) = delp(i, j) + (fx(i, j) - fx(i + 1, j) + fy(i, j) - fy(i, j + 1)) * g.rarea(i, j);
+    return;
+  }
 
   if (grid_type < 3) {
     if (bounded) {

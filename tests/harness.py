@@ -42,7 +42,7 @@ def cube_grid(n):
 
 
 class Case:
-    def __init__(self, n, npz, flagset="A", state="smooth", flags_override=None):
+    def __init__(self, n, npz, flagset="A", state="smooth", flags_override=None, state_kw=None):
         self.n, self.npz = n, npz
         self.tiles, self.bounds = cube_grid(n)
         self.ak, self.bk = I.model_levels(npz)   # npz = 79: the reference set_eta levels (var_hi)
@@ -51,6 +51,10 @@ class Case:
             self.flags.update(flags_override)
         if state == "smooth":
             self.states = I.smooth_state(self.tiles, self.bounds, npz)
+        elif state == "cosine_bell":   # SW_DYNAMICS test case 1 (BASELINE config 1a): npz = 1, flags.sw_test_case = 1
+            assert npz == 1
+            self.flags["sw_test_case"] = 1
+            self.states = I.cosine_bell(self.tiles, self.bounds, **(state_kw or {}))
         else:
             self.states = I.baroclinic_wave(self.tiles, self.bounds, npz, self.ak, self.bk)
         self.consts = G.CONSTANTS
@@ -60,7 +64,7 @@ class Case:
         return abi.Engine(lib, prefix, self.bounds, self.tiles[tile - 1], self.flags, self.npz, self.ak, self.bk,
                           self.ak[0], self.consts, tile=tile, device=device)
 
-    def load_state(self, eng, tile=1, fields=("u", "v", "w", "pt", "delp", "q_con", "phis", "delz")):
+    def load_state(self, eng, tile=1, fields=("u", "v", "w", "pt", "delp", "q_con", "phis", "delz", "uc", "vc")):
         st = self.states[tile - 1]
         name = {"q_con": "QCON"}
         for f in fields:
@@ -209,6 +213,10 @@ class OracleCube:
             last = it == n_split
             if it == 1:
                 self.halo("DELP_PT")
+            if self.case.flags.get("sw_test_case") == 1:   # SW_DYNAMICS, test_case 1: d_sw + delp halo only (dyn_core.F90:394, 569, 998)
+                run("D_SW", "d_sw", dt)
+                self.halo("DELP_PT")
+                continue
             self.halo("UVW")
             if hydro:   # dyn_core.F90:478-480, :905-907, :1017-1021
                 run("C_SW", "c_sw", dt2)
