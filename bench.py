@@ -35,8 +35,8 @@ from gfdl_atmos_cubed_sphere_b200.parallel import tiles_of_rank, tile_rank_map  
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of ONE d_sw call on one face (bytes), from the ncu
-# metrics list profiles/r1_dsw_traffic_v8.csv (python profiles/dsw_traffic.py); key = (res, npz, flag-set)
-DSW_DRAM_TRAFFIC = {(384, 79, "A"): 4.964e9}
+# metrics list profiles/r1_dsw_traffic_v10.csv (python profiles/dsw_traffic.py); key = (res, npz, flag-set)
+DSW_DRAM_TRAFFIC = {(384, 79, "A"): 4.952e9}
 
 
 def dsw_algorithmic_bytes(n, npz, use_cond=False, d_con=False):

@@ -577,7 +577,7 @@ static void dsw_tables(fv3_ctx* c, std::vector<int>& ki, std::vector<double>& kd
 
 // ---------------------------------------------------------------------------------------------
 // fused transport of delp, w, q_con, pt (sw_core.F90:919-1066, :1262-1283): ONE kernel per d_sw call.
-// A CTA owns a 26x24 tile of one level (tp_tile.cuh).  The Courant numbers / area fluxes are staged once and
+// A CTA owns a 26x26 tile of one level (tp_tile.cuh).  The Courant numbers / area fluxes are staged once and
 // shared by the fields; the mass fluxes of delp stay in shared memory and weight the fluxes of the other fields;
 // the flux divergences are applied in the epilogue (thread = one cell), so fx, fy, gx, gy never touch HBM.
 // The del-n damping fluxes (wide stencil, separate kernels) are read from global and added on the fly.

@@ -3,7 +3,7 @@
 //
 // Reference semantics: model/tp_core.F90:85-241 fv_tp_2d, :245-322 copy_corners,
 // :1267-1447 deln_flux; model/sw_core.F90:1608-1737 del6_vt_flux.
-// Design (not a translation): ONE launch pair (interior / frame tiles) per transport; a CTA owns a 26x24 tile of one level
+// Design (not a translation): ONE launch pair (interior / frame tiles) per transport; a CTA owns a 26x26 tile of one level
 // and keeps the inner fluxes, q_i and q_j in shared memory (tp_tile.cuh).
 // The cube-corner "copy_corners" transposes are NOT written into q: corner tiles load q
 // through a remapping accessor (ppm::QAccX / QAccY), so q stays read-only.

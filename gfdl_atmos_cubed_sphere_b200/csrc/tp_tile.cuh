@@ -3,15 +3,15 @@
 // Reference semantics: model/tp_core.F90:85-241 (fv_tp_2d), :245-322 (copy_corners).
 // Why: in the three-launch form (first version) the intermediates fx2, fy2, q_i, q_j made a round trip through
 // HBM/L2 and every 6-point window was re-fetched through L1 by six different threads (ncu,
-// profiles/r1_dsw_ncu_summary.md).  Here a CTA of 16 warps owns a TX x TY = 26 x 24 block of cells of one level.
+// profiles/r1_dsw_ncu_summary.md).  Here a CTA of 16 warps owns a TX x TY = 26 x 26 block of cells of one level.
 // Every tile array is [QH][32]: the 32 lanes of a warp are the 26 cells + 3 + 3 halo columns of a row, a warp takes
 // whole rows (row index is warp-uniform, column = lane, no index arithmetic and no integer division in the body):
 //   I.  stage the Courant numbers, area fluxes and cell areas of the tile with cp.async       (once per tile)
 //   A.  stage the halo tile of q (cube-corner tiles: both copy_corners views)                 (per field)
-//   B0. per-point limiter input (dm or al) of both sweeps
+//   B0. per-point limiter input (dm or al) of both sweeps                     [-DTPT_AUX only]
 //   B.  inner fluxes fx2 (all rows), fy2 (rows 3..TY+3)                       [ord_in]
 //   C.  q_i (rows 3..TY+2, all columns), q_j (all rows, columns 3..TX+2)      [one division each]
-//   C2. per-point limiter input of q_i (x lines) and q_j (y lines)
+//   C2. per-point limiter input of q_i (x lines) and q_j (y lines)            [-DTPT_AUX only]
 //   D.  outer fluxes, averaged with the inner ones in place                   [ord_ou]
 // All global reads happen in I/A with every load of the tile in flight at once (the first fused version read crx,
 // xfx, area inside B, C, D and spent 45 % of its issue slots stalled on those loads: ncu long_scoreboard).
@@ -26,8 +26,21 @@
 
 namespace tpt {
 
+// Two forms of the limiter inputs, both parity-green (profiles/r1_dsw_ncu_summary.md, v10):
+//   default    : recomputed in registers from the q window the flux loads anyway (TPT_NOAUX) -- 12 tile arrays, which lets
+//                the tile be 26 rows high at 2 CTAs per SM (row tasks per phase 59 / 58 / 53 on 16 warps)
+//   -DTPT_AUX  : one auxiliary value per point in shared memory (two extra passes + 2 barriers per field); 14 arrays, so
+//                at most 24 rows at 2 CTAs per SM.  Measured at C384L79: d_sw 3.76 ms (AUX, 24) / 3.77 (NOAUX, 24) /
+//                3.61 (NOAUX, 26) / 3.65 (NOAUX, 28)
+#ifndef TPT_AUX
+#define TPT_NOAUX
+#endif
 #ifndef TPT_TY
+#ifdef TPT_NOAUX
+#define TPT_TY 26
+#else
 #define TPT_TY 24
+#endif
 #endif
 #ifndef TPT_NW
 #define TPT_NW 16
@@ -40,8 +53,10 @@ struct Smem {
   double crx[QH][QW], xfx[QH][QW], cry[QH][QW], yfx[QH][QW], area[QH][QW];
   // per field
   double q[QH][QW];     // q, copy_corners(dir=1) view
+#ifndef TPT_NOAUX
   double ax[QH][QW];    // x-sweep limiter input (dm or al, ppm::aux_point) of q, later of q_i
   double ay[QH][QW];    // y-sweep limiter input of q, later of q_j
+#endif
   double fx2[QH][QW];   // inner x flux; rows 3..TY+2 hold the averaged outer flux after phase D
   double fy2[QH][QW];   // inner y flux; rows 3..TY+3 hold the averaged outer flux after phase D
   double qi[QH][QW];    // phases A-B: q in the copy_corners(dir=2) view (cube-corner tiles); C-D: q_i
@@ -85,6 +100,23 @@ __device__ __forceinline__ double line_flux(bool mono, const double* q, int sq, 
     return ppm::flux_mono_aux(p[-2 * sq], p[-sq], p[0], p[sq], p[2 * sq], d[-sa], d[0], d[sa], c, iord);
   }
   return ppm::flux_unlim_aux(q[-sq], q[0], a[-sa], a[0], a[sa], c, iord);
+}
+
+// TPT_NOAUX form: no limiter-input arrays.  The 5 (monotone) / 6 (unlimited) values of q the flux reads anyway contain every
+// operand of the three dm / al values it needs, so they are recomputed in registers: +2 limiter evaluations per flux, but
+// 3 shared-memory loads per flux, the two aux passes (6 loads + 2 stores per point) and 2 of the 5 barriers per field go away
+// (ncu, profiles/r1_dsw_ncu_summary.md: the shared-memory data pipe is at 60 % of peak next to 58 % issue-active).
+// Same operations on the same operands as the aux form => bit-identical results.
+__device__ __forceinline__ double line_flux_na(bool mono, const double* q, int sq, double c, int iord) {
+  if (mono) {
+    const int u = (c > 0.) ? -1 : 0;
+    const double* p = q + u * sq;
+    const double a = p[-2 * sq], b = p[-sq], m = p[0], d = p[sq], e = p[2 * sq];
+    return ppm::flux_mono_aux(a, b, m, d, e, ppm::dm2(a, b, m), ppm::dm2(b, m, d), ppm::dm2(m, d, e), c, iord);
+  }
+  const double a0 = q[-3 * sq], a1 = q[-2 * sq], a2 = q[-sq], a3 = q[0], a4 = q[sq], a5 = q[2 * sq];
+  return ppm::flux_unlim_aux(a2, a3, ppm::aux_point(false, iord, a0, a1, a2, a3), ppm::aux_point(false, iord, a1, a2, a3, a4),
+                             ppm::aux_point(false, iord, a2, a3, a4, a5), c, iord);
 }
 
 struct Tile {
@@ -186,6 +218,7 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
   cp_async_wait_all();
   __syncthreads();
   const double(*qy)[QW] = (EDGE && T.corner) ? S.qi : S.q;
+#ifndef TPT_NOAUX
   // ---- B0: per-point limiter inputs of both sweeps (border points are clamped garbage that no face reads)
 #pragma unroll
   for (int r = wid; r < QH; r += NW) {
@@ -194,17 +227,22 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
     S.ay[r][c] = aux_point(mono, ord_in, qy[r2][c], qy[r1][c], qy[r][c], qy[r3][c]);
   }
   __syncthreads();
+#define TPT_LF(qp, sq, ap, sa, cr, ord) line_flux(mono, qp, sq, ap, sa, cr, ord)
+#else
+  (void)cm2; (void)cm1; (void)cp1;
+#define TPT_LF(qp, sq, ap, sa, cr, ord) line_flux_na(mono, qp, sq, cr, ord)
+#endif
   // ---- B: inner sweeps; task t < QH: fx2 row t (tp_core.F90:164-169), else fy2 row t-QH+3 (:143-148)
 #pragma unroll
   for (int t = wid; t < QH + TY + 1; t += NW) {
     if (t < QH) {
       const int r = t, j = j0 - 3 + r;
-      if (xface && xfast && (!EDGE || j <= L.jed)) S.fx2[r][c] = line_flux(mono, &S.q[r][c], 1, &S.ax[r][c], 1, S.crx[r][c], ord_in);
+      if (xface && xfast && (!EDGE || j <= L.jed)) S.fx2[r][c] = TPT_LF(&S.q[r][c], 1, &S.ax[r][c], 1, S.crx[r][c], ord_in);
     } else {
       const int r = t - QH + 3, j = j0 - 3 + r;
       if (!EDGE || (j <= L.je + 1 && i <= L.ied)) {
         const double cr = S.cry[r][c];
-        S.fy2[r][c] = (!cube || (j >= 4 && j <= npy - 3)) ? line_flux(mono, &qy[r][c], QW, &S.ay[r][c], QW, cr, ord_in)
+        S.fy2[r][c] = (!cube || (j >= 4 && j <= npy - 3)) ? TPT_LF(&qy[r][c], QW, &S.ay[r][c], QW, cr, ord_in)
                                                           : edge_flux(&qy[0][c], QW, j0 - 3, G.dya, LIDX(L, i, 0), L.NI, j, cr, ord_in, npy);
       }
     }
@@ -240,6 +278,7 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
     }
   }
   __syncthreads();
+#ifndef TPT_NOAUX
   // ---- C2: limiter inputs of q_i (x lines, rows 3..TY+2) and q_j (y lines, all rows)
 #pragma unroll
   for (int t = wid; t < TY + QH; t += NW) {
@@ -253,18 +292,19 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
     }
   }
   __syncthreads();
+#endif
   // ---- D: outer sweeps, averaged with the inner fluxes in place (tp_core.F90:161,180,193-198)
 #pragma unroll
   for (int t = wid; t < TY + TY + 1; t += NW) {
     if (t < TY) {
       const int r = t + 3, j = j0 - 3 + r;
       if (xface && xfast && (!EDGE || j <= L.je))
-        S.fx2[r][c] = 0.5 * (line_flux(mono, &S.qi[r][c], 1, &S.ax[r][c], 1, S.crx[r][c], ord_ou) + S.fx2[r][c]);
+        S.fx2[r][c] = 0.5 * (TPT_LF(&S.qi[r][c], 1, &S.ax[r][c], 1, S.crx[r][c], ord_ou) + S.fx2[r][c]);
     } else {
       const int r = t - TY + 3, j = j0 - 3 + r;
       if (xcell && (!EDGE || j <= L.je + 1)) {
         const double cr = S.cry[r][c];
-        const double f = (!cube || (j >= 4 && j <= npy - 3)) ? line_flux(mono, &S.qj[r][c], QW, &S.ay[r][c], QW, cr, ord_ou)
+        const double f = (!cube || (j >= 4 && j <= npy - 3)) ? TPT_LF(&S.qj[r][c], QW, &S.ay[r][c], QW, cr, ord_ou)
                                                              : edge_flux(&S.qj[0][c], QW, j0 - 3, G.dya, LIDX(L, i, 0), L.NI, j, cr, ord_ou, npy);
         S.fy2[r][c] = 0.5 * (f + S.fy2[r][c]);
       }
@@ -278,6 +318,7 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
     }
   }
   __syncthreads();
+#undef TPT_LF
 }
 
 // tile maps of a face: the interior rectangle (tiles with 4 <= every face index <= npx-3 and the whole halo inside the

@@ -42,7 +42,7 @@ def test_d_sw_hord8_dddmp():
 
 def test_d_sw_mixed_scheme_families_multi_tile():
     """Fused delp/w/q_con/pt transport with fields in different PPM families (run-time family choice), on a face
-    that spans several 26x24 transport tiles in both directions incl. partial last tiles."""
+    that spans several 26x26 transport tiles in both directions incl. partial last tiles."""
     _assert(H.parity_c_sw_d_sw(n=56, npz=3, flagset="B", dt=10.0,
                                flags_override=dict(use_cond=1, hord_mt=6, hord_vt=8, hord_tm=5, hord_dp=-5)), TOL_STAGE)
 
