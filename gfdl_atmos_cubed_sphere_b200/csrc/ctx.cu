@@ -164,6 +164,7 @@ int fv3_create(const fv3_bounds_t* bd, const fv3_grid_t* grid, const fv3_flags_t
   if (bd->ng != 3) return -2;
   if (bd->is != 1 || bd->js != 1 || bd->ie != bd->npx - 1 || bd->je != bd->npy - 1) return -2;  // one face per context
   if (bd->npx != bd->npy) return -2;
+  if (flags->sw_test_case != 0 && flags->sw_test_case != 1) return -2;   // only test_case 1 of the SW_DYNAMICS build is built
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return (int)cudaErrorNoDevice;
   fv3_ctx* c = new fv3_ctx();

@@ -116,11 +116,24 @@ def set_eta_var_hi(km, ptop=1.0, pint=100.0e2, s_rate=1.03, rdgas=287.05, grav=9
     return ak[1:].copy(), bk[1:].copy(), ks
 
 
+# set_eta, km = 32, default npz_type (fv_eta.F90:410-428: ks = 7, ak = a32, bk = b32); table values from tools/fv_eta.h:114-136
+_A32 = (100.00000, 400.00000, 818.60211, 1378.88653, 2091.79519, 2983.64084, 4121.78960, 5579.22148, 6907.19063, 7735.78639,
+        8197.66476, 8377.95525, 8331.69594, 8094.72213, 7690.85756, 7139.01788, 6464.80251, 5712.35727, 4940.05347, 4198.60465,
+        3516.63294, 2905.19863, 2366.73733, 1899.19455, 1497.78137, 1156.25252, 867.79199, 625.59324, 423.21322, 254.76613,
+        115.06646, 0.00000, 0.00000)
+_B32 = (0.00000, 0.00000, 0.00000, 0.00000, 0.00000, 0.00000, 0.00000, 0.00000, 0.00513, 0.01969, 0.04299, 0.07477, 0.11508,
+        0.16408, 0.22198, 0.28865, 0.36281, 0.44112, 0.51882, 0.59185, 0.65810, 0.71694, 0.76843, 0.81293, 0.85100, 0.88331,
+        0.91055, 0.93338, 0.95244, 0.96828, 0.98142, 0.99223, 1.00000)
+
+
 def model_levels(npz):
-    """Hybrid levels for a run: the reference's own set_eta result where it is restated (npz = 79), else hybrid_levels."""
+    """Hybrid levels for a run: the reference's own set_eta result where it is restated -- npz = 79 (var_hi generator) and
+    npz = 32 (the a32/b32 table: BASELINE config 1b, C48 L32) -- else the generic hybrid_levels."""
     if npz == 79:
         ak, bk, _ = set_eta_var_hi(79)
         return ak, bk
+    if npz == 32:
+        return np.array(_A32, dtype=np.float64), np.array(_B32, dtype=np.float64)
     return hybrid_levels(npz)
 
 
