@@ -19,7 +19,7 @@ FIELDS = ["U", "V", "W", "DELZ", "PT", "DELP", "QCON", "CAPPA", "PHIS", "OMGA", 
           "WORK_Q", "WORK_FX", "WORK_FY", "WORK_RAX", "WORK_RAY", "DP1"]
 FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
 
-HALO_GROUPS = ["UVW", "GZ", "DIVGD_UCVC", "DELP_PT", "ZH_PKC", "UV_EDGE", "TRACER"]
+HALO_GROUPS = ["UVW", "GZ", "DIVGD_UCVC", "DELP_PT", "ZH_PKC", "UV_EDGE", "TRACER", "HEAT", "OMGA"]
 HALO_ID = {n: i for i, n in enumerate(HALO_GROUPS)}
 
 

@@ -11,10 +11,11 @@
 //   halo(u,v[,delp,pt]) -> c_sw -> geopk(C) -> p_grad_c -> halo(divgd, uc,vc) -> d_sw -> halo(delp,pt) -> geopk(D) -> one_grad_p
 // One call replaces the whole it-loop; all faces owned by this process advance in lockstep
 // (each on its own stream), exchanges are fv3_halo_exchange (device-local gathers and/or NCCL).
-// Not included (documented in DESIGN.md): the post-loop d_con heating del2_cubed
-// (dyn_core.F90:1300-1358), omega diagnostics (:1182-1215), Rayleigh friction, fast physics.
+// After the loop (:1300-1356): halo(heat_source) -> del2_cubed -> heating of pt (d_con > 0; csrc/dyn_post.cu).
+// Not included (documented in DESIGN.md): omega diagnostics (:1182-1215), Rayleigh friction, fast physics.
 #include "fv3_ctx.hpp"
 #include <cstdlib>
+#include <algorithm>
 
 extern "C" int fv3_halo_exchange(fv3_ctx** ctxs, int nctx, int group);
 extern "C" int fv3_halo_start(fv3_ctx** ctxs, int nctx, int group);
@@ -104,11 +105,29 @@ extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, i
     FORALL(stage_nh_p_grad(c, dt))                                                        // :1032
     if (last_step && linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_UV_EDGE))) return rc;   // :1151-1163
   }
+  // dyn_core.F90:1300-1356: the dissipative heating accumulated over the substeps is filtered and added to pt
+  if (!sw_advection && ctxs[0]->f.d_con > 1.e-5 && fv3_n_con(ctxs[0]->f, ctxs[0]->L.npz) != 0) {
+    const int nf_ke = std::min(3, ctxs[0]->f.nord + 1);
+    if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_HEAT))) return rc;         // :2401
+    FORALL(stage_del2_cubed(c, FV3_HEAT, 0.20 * c->G.da_min, nf_ke))                      // :1303
+    FORALL(stage_dcon_heating(c, bdt))                                                    // :1305-1356
+  }
   for (int a = 0; a < nctx; a++) {
     cudaSetDevice(ctxs[a]->device);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fv3_fail(ctxs[a], (int)e, std::string("dyn_core: ") + cudaGetErrorString(e));
   }
+  return 0;
+}
+
+// del2_cubed incl. its halo update on all faces of this process (the omega filter of fv_dynamics.F90:637-642 is
+// fv3_del2_cubed_cube(ctxs, n, FV3_OMGA, 0.18 * da_min, nf_omega))
+extern "C" int fv3_del2_cubed_cube(fv3_ctx** ctxs, int nctx, int field, double cd, int nmax) {
+  if (!ctxs || nctx < 1) return -1;
+  if (field != FV3_HEAT && field != FV3_OMGA) return fv3_fail(ctxs[0], -1, "del2_cubed_cube: field must be FV3_HEAT or FV3_OMGA");
+  int rc;
+  if (ctxs[0]->halo != nullptr && (rc = fv3_halo_exchange(ctxs, nctx, field == FV3_HEAT ? FV3_HALO_HEAT : FV3_HALO_OMGA))) return rc;
+  FORALL(stage_del2_cubed(c, field, cd, nmax))
   return 0;
 }
 

@@ -217,6 +217,8 @@ static void group_specs(fv3_ctx* c, int g, std::vector<FieldSpec>& s) {
       break;
     case FV3_HALO_UV_EDGE: s.push_back({FV3_U, FV3_V, POS_NORTH, POS_EAST, 1, kz, 3, 1}); break;
     case FV3_HALO_TRACER: s.push_back({FV3_WORK_Q, -1, POS_CENTER, 0, 0, kz, 3, 0}); break;
+    case FV3_HALO_HEAT: s.push_back({FV3_HEAT, -1, POS_CENTER, 0, 0, kz, 3, 0}); break;
+    case FV3_HALO_OMGA: s.push_back({FV3_OMGA, -1, POS_CENTER, 0, 0, kz, 3, 0}); break;
   }
 }
 

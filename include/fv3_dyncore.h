@@ -193,6 +193,12 @@ int fv3_nh_p_grad(fv3_ctx *ctx, double dt);
 /* Hydrostatic branch.  dyn_core.F90:2202 geopk: cg != 0 is the C-grid call (dyn_core.F90:478-480: delpc, ptc -> pkc, gz,
  * pe, peln), cg == 0 the D-grid call (:905-907: delp, pt -> pkc, gz, pe, peln, pkz).  dyn_core.F90:1909 one_grad_p
  * (call :1019-1021, d_ext = 0): a2b_ord4 of pkc, gz and the D-grid pressure-gradient update of u, v. */
+/* del2_cubed (dyn_core.F90:2356-2465) on FV3_HEAT or FV3_OMGA; the halo of the field must be current (fv3_halo_exchange with
+ * FV3_HALO_HEAT / FV3_HALO_OMGA, or fv3_del2_cubed_cube which does both).  nmax passes (at most 3). */
+int fv3_del2_cubed(fv3_ctx *ctx, int field, double cd, int nmax);
+int fv3_del2_cubed_cube(fv3_ctx **ctxs, int nctx, int field, double cd, int nmax);
+/* dyn_core.F90:1305-1356: filtered heat_source -> pt (levels 1..n_con, limited by delt_max); part of fv3_dyn_core */
+int fv3_dcon_heating(fv3_ctx *ctx, double bdt);
 int fv3_geopk(fv3_ctx *ctx, int cg);
 int fv3_one_grad_p(fv3_ctx *ctx, double dt);
 
@@ -219,6 +225,8 @@ enum fv3_halo_group {
   FV3_HALO_ZH_PKC,    /* i_pack(4)/(5): zh, pkc                  dyn_core.F90:945-949,980,992 */
   FV3_HALO_UV_EDGE,   /* mpp_get_boundary(u,v) last substep      dyn_core.F90:1151-1163 */
   FV3_HALO_TRACER,    /* q_pack / mpp_update_domains(qn2)         fv_tracer2d.F90:188,282 (the tracer lives in FV3_WORK_Q) */
+  FV3_HALO_HEAT,      /* mpp_update_domains(heat_source) inside del2_cubed   dyn_core.F90:1303, 2401 */
+  FV3_HALO_OMGA,      /* mpp_update_domains(omga) inside del2_cubed          fv_dynamics.F90:640, dyn_core.F90:2401 */
   FV3_NUM_HALO_GROUPS
 };
 /* Link the six (or fewer) contexts of one process into a cube. tiles[i] is

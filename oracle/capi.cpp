@@ -302,6 +302,22 @@ int fv3o_one_grad_p(fv3o_ctx* c, double dt) {
              c->f.hydrostatic != 0);
   return 0;
 }
+// dyn_core.F90:2356 del2_cubed on one field (FV3_HEAT: :1303 with cd = 0.20 da_min, nmax = min(3, nord+1); FV3_OMGA:
+// fv_dynamics.F90:640 with cd = 0.18 da_min, nmax = nf_omega).  The caller has exchanged the halo of the field.
+int fv3o_del2_cubed(fv3o_ctx* c, int field, double cd, int nmax) {
+  if (field != FV3_HEAT && field != FV3_OMGA) return -1;
+  Bd bd(c->b); Grid g(c->g, bd);
+  del2_cubed(F3(c, field), cd, g, bd, bd.npz, nmax);
+  return 0;
+}
+// dyn_core.F90:1300-1356 without the del2_cubed call
+int fv3o_dcon_heating(fv3o_ctx* c, double bdt) {
+  Bd bd(c->b);
+  const int n_con = n_con_levels(c->f, bd.npz);
+  if (n_con == 0 || !(c->f.d_con > 1.e-5)) return 0;
+  dcon_heating(F3(c, FV3_PT), F3(c, FV3_HEAT), F3(c, FV3_DELP), F3(c, FV3_DELZ), F3(c, FV3_PKZ), n_con, bdt, c->f, bd);
+  return 0;
+}
 // dyn_core.F90:370-385 (it==1): gz from zs and delz on the compute domain
 int fv3o_gz_init(fv3o_ctx* c) {
   Bd bd(c->b);

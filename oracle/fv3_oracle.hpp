@@ -189,6 +189,9 @@ void riem_solver3(int ms, double dt, int is, int ie, int js, int je, int km, int
                   V3 delp, V3 zh, double* pe /*(is-1:ie+1,km+1,js-1:je+1)*/, V3 ppe, V3 pk3, V3 pk,
                   double* peln /*(is:ie,km+1,js:je)*/, V2 ws, double p_fac, double a_imp, bool use_logp,
                   bool use_cond, bool moist_kappa, bool last_call, bool fp_out, const Consts& c);
+void del2_cubed(V3 q, double cd, const Grid& g, const Bd& bd, int km, int nmax);
+int n_con_levels(const fv3_flags_t& f, int npz);
+void dcon_heating(V3 pt, V3 heat_source, V3 delp, V3 delz, V3 pkz, int n_con, double bdt, const fv3_flags_t& f, const Bd& bd);
 void p_grad_c(double dt2, int npz, V3 delpc, V3 pkc, V3 gz, V3 uc, V3 vc, const Bd& bd, V2 rdxc, V2 rdyc,
               bool hydrostatic);
 void nh_p_grad(V3 u, V3 v, V3 pp, V3 gz, V3 delp, V3 pk, double dt, int ng, const Grid& g, const Bd& bd, int npx,

@@ -603,4 +603,77 @@ void pe_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// dyn_core.F90:2356-2465 del2_cubed: nmax (<= 3) passes of a del-2 filter on an A-grid scalar whose halo has been updated by
+// the caller (the mpp_update_domains at :2401 is the harness's / dyn_core's exchange).  Non-USE_SG build (del6_u / del6_v).
+void del2_cubed(V3 q, double cd, const Grid& g, const Bd& bd, int km, int nmax) {
+  const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je, isd = bd.isd, ied = bd.ied, jsd = bd.jsd, jed = bd.jed;
+  const int npx = bd.npx, npy = bd.npy;
+  const double r3 = 1. / 3.;
+  const int ntimes = std::min(3, nmax);
+  for (int n = 1; n <= ntimes; n++) {
+    const int nt = ntimes - n;
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= km; k++) {
+      L2 fx(isd, ied + 1, jsd, jed), fy(isd, ied, jsd, jed + 1);
+      V2 qk = q.k(k);
+      if (bd.sw_corner) { qk(1, 1) = (qk(1, 1) + qk(0, 1) + qk(1, 0)) * r3; qk(0, 1) = qk(1, 1); qk(1, 0) = qk(1, 1); }
+      if (bd.se_corner) { qk(ie, 1) = (qk(ie, 1) + qk(npx, 1) + qk(ie, 0)) * r3; qk(npx, 1) = qk(ie, 1); qk(ie, 0) = qk(ie, 1); }
+      if (bd.ne_corner) { qk(ie, je) = (qk(ie, je) + qk(npx, je) + qk(ie, npy)) * r3; qk(npx, je) = qk(ie, je); qk(ie, npy) = qk(ie, je); }
+      if (bd.nw_corner) { qk(1, je) = (qk(1, je) + qk(0, je) + qk(1, npy)) * r3; qk(0, je) = qk(1, je); qk(1, npy) = qk(1, je); }
+      if (nt > 0 && !bd.bounded_domain) copy_corners(qk, npx, npy, 1, bd);
+      for (int j = js - nt; j <= je + nt; j++)
+        for (int i = is - nt; i <= ie + 1 + nt; i++) fx(i, j) = g.del6_v(i, j) * (qk(i - 1, j) - qk(i, j));
+      if (nt > 0 && !bd.bounded_domain) copy_corners(qk, npx, npy, 2, bd);
+      for (int j = js - nt; j <= je + 1 + nt; j++)
+        for (int i = is - nt; i <= ie + nt; i++) fy(i, j) = g.del6_u(i, j) * (qk(i, j - 1) - qk(i, j));
+      for (int j = js - nt; j <= je + nt; j++)
+        for (int i = is - nt; i <= ie + nt; i++)
+          qk(i, j) = qk(i, j) + cd * g.rarea(i, j) * (fx(i, j) - fx(i + 1, j) + fy(i, j) - fy(i, j + 1));
+    }
+  }
+}
+
+// dyn_core.F90:296-307: number of levels that receive the dissipative heating
+int n_con_levels(const fv3_flags_t& f, int npz) {
+  if (f.convert_ke || (f.do_vort_damp && f.vtdm4 > 1.E-4)) return npz;
+  if (f.d2_bg_k1 < 1.E-3) return 0;
+  return (f.d2_bg_k2 < 1.E-3) ? 1 : 2;
+}
+
+// dyn_core.F90:1305-1356: the filtered heat_source becomes a temperature tendency, limited by delt_max, added to pt
+// (pt = cp*(virtual temperature / pkz) scaling of the acoustic loop).  moist_kappa = F branch for the non-hydrostatic case.
+void dcon_heating(V3 pt, V3 heat_source, V3 delp, V3 delz, V3 pkz, int n_con, double bdt, const fv3_flags_t& f, const Bd& bd) {
+  const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je;
+  const double rdg = -f.rdgas / f.grav, cv_air = f.cp_air - f.rdgas, k1k = f.kappa / (1. - f.kappa);
+  if (f.hydrostatic) {
+    for (int j = js; j <= je; j++)
+      for (int k = 1; k <= n_con; k++) {
+        if (k < 3) {
+          for (int i = is; i <= ie; i++) pt(i, j, k) = pt(i, j, k) + heat_source(i, j, k) / (f.cp_air * delp(i, j, k) * pkz(i, j, k));
+        } else {
+          for (int i = is; i <= ie; i++) {
+            const double dtmp = heat_source(i, j, k) / (f.cp_air * delp(i, j, k));
+            pt(i, j, k) = pt(i, j, k) + fsign(std::min(std::fabs(bdt) * f.delt_max, std::fabs(dtmp)), dtmp) / pkz(i, j, k);
+            heat_source(i, j, k) = dtmp;
+          }
+        }
+      }
+  } else {
+    for (int k = 1; k <= n_con; k++) {
+      double delt = std::fabs(bdt * f.delt_max);
+      if (k == 1) delt = 0.1 * delt;
+      if (k == 2) delt = 0.5 * delt;
+      for (int j = js; j <= je; j++)
+        for (int i = is; i <= ie; i++) {
+          pkz(i, j, k) = std::exp(k1k * std::log(rdg * delp(i, j, k) / delz(i, j, k) * pt(i, j, k)));
+          const double dtmp = heat_source(i, j, k) / (cv_air * delp(i, j, k));
+          pt(i, j, k) = pt(i, j, k) + fsign(std::min(delt, std::fabs(dtmp)), dtmp) / pkz(i, j, k);
+          heat_source(i, j, k) = dtmp;
+        }
+    }
+  }
+}
+
 }  // namespace fv3o

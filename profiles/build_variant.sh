@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p variants/obj_$name
-for s in ctx tp2d c_sw d_sw nh pgrad halo dyn_core tracer; do
+for s in ctx tp2d c_sw d_sw nh pgrad halo dyn_core tracer dyn_post; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" -c gfdl_atmos_cubed_sphere_b200/csrc/$s.cu -o variants/obj_$name/$s.o &
 done
 wait

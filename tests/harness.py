@@ -189,6 +189,10 @@ class OracleCube:
             self._exchange_scalar("ZH"); self._exchange_scalar("PKC")
         elif group == "UV_EDGE":
             self._exchange_pair("U", "V", cs.NORTH, cs.EAST, boundary_only=True)
+        elif group == "HEAT":
+            self._exchange_scalar("HEAT")
+        elif group == "OMGA":
+            self._exchange_scalar("OMGA")
 
     def all(self, stage, *args):
         for t in self.tiles:
@@ -254,6 +258,30 @@ class OracleCube:
             run("PG_D", "nh_p_grad", dt)
             if last:
                 self.halo("UV_EDGE")
+        self.dcon_heating(bdt)
+
+    def n_con(self):
+        """dyn_core.F90:296-307"""
+        f = self.case.flags
+        if f.get("convert_ke") or (f.get("do_vort_damp") and f.get("vtdm4", 0.0) > 1e-4):
+            return self.case.npz
+        if f.get("d2_bg_k1", 0.0) < 1e-3:
+            return 0
+        return 1 if f.get("d2_bg_k2", 0.0) < 1e-3 else 2
+
+    def del2_cubed(self, field, cd, nmax):
+        """del2_cubed incl. its halo update (dyn_core.F90:2356-2465) on every face."""
+        self.halo(field if field != "HEAT" else "HEAT")
+        self.all("del2_cubed", abi.FIELD_ID[field], float(cd), int(nmax))
+
+    def dcon_heating(self, bdt):
+        """dyn_core.F90:1300-1356 (the SW_DYNAMICS branch returns before it)."""
+        f = self.case.flags
+        if f.get("sw_test_case") == 1 or not (f.get("d_con", 0.0) > 1e-5) or self.n_con() == 0:
+            return
+        da_min = self.case.tiles[0].da_min
+        self.del2_cubed("HEAT", 0.20 * da_min, min(3, f["nord"] + 1))
+        self.all("dcon_heating", float(bdt))
 
     def tracer_2d(self, hord):
         """tracer_2d_1L (model/fv_tracer2d.F90:49-295; nq = 1, trdm = 0, id_divg_mean = 0) on the oracle side: the pointwise
@@ -344,6 +372,15 @@ class CudaCube:
         rc = fn(self.ctxs, len(self.tiles), C.c_double(bdt), C.c_int(n_split), C.c_int(0))
         if rc:
             raise RuntimeError(f"fv3_dyn_core rc={rc}: " + "; ".join(self.eng[t].last_error() for t in self.tiles))
+        for t in self.tiles:
+            self.eng[t].sync()
+
+    def del2_cubed(self, field, cd, nmax):
+        fn = self.lib[0].fv3_del2_cubed_cube
+        fn.restype = C.c_int
+        rc = fn(self.ctxs, len(self.tiles), C.c_int(abi.FIELD_ID[field]), C.c_double(cd), C.c_int(nmax))
+        if rc:
+            raise RuntimeError(f"fv3_del2_cubed_cube rc={rc}: " + "; ".join(self.eng[t].last_error() for t in self.tiles))
         for t in self.tiles:
             self.eng[t].sync()
 

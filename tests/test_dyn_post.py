@@ -1,0 +1,111 @@
+"""Post-loop part of dyn_core: del2_cubed (dyn_core.F90:2356-2465; also the omega filter of fv_dynamics.F90:637-642) and the
+dissipative-heating update of pt (dyn_core.F90:1300-1356)."""
+import numpy as np
+import pytest
+
+import harness as H
+
+NG = 3
+
+
+def _omega_case(n=16, npz=4, flagset="A"):
+    case = H.Case(n, npz, flagset, state="baroclinic")
+    rng = np.random.default_rng(7)
+    fields = []
+    for g in case.tiles:
+        lon, lat = g.arr["agrid"]
+        kk = np.arange(1, npz + 1)[:, None, None]
+        f = np.sin(3 * lon + 0.3 * kk)[...] * np.cos(2 * lat)[None] + 0.2 * rng.standard_normal((npz,) + lon.shape)
+        fields.append(f)
+    return case, fields
+
+
+def _integral(cube, case, name):
+    n = case.n
+    return sum(float((cube.eng[t + 1].get(name)[:, NG:NG + n, NG:NG + n] * case.tiles[t].arr["area"][None, NG:NG + n, NG:NG + n]).sum())
+               for t in range(6))
+
+
+@pytest.mark.parametrize("nmax", [1, 2, 3])
+def test_oracle_del2_cubed_properties(nmax):
+    """A constant stays constant; a noisy field loses variance; the area integral moves only through the corner averaging
+    (the filter itself is in flux form)."""
+    case, fields = _omega_case()
+    n = case.n
+    oc = H.OracleCube(case)
+    cd = 0.18 * case.tiles[0].da_min
+    for t in range(6):
+        oc.eng[t + 1].put("OMGA", np.full_like(fields[t], 2.5))
+    oc.del2_cubed("OMGA", cd, nmax)
+    for t in range(6):
+        assert np.abs(oc.eng[t + 1].get("OMGA")[:, NG:NG + n, NG:NG + n] - 2.5).max() < 1e-13
+    for t in range(6):
+        oc.eng[t + 1].put("OMGA", fields[t])
+    i0 = _integral(oc, case, "OMGA")
+    v0 = sum(float(np.var(fields[t][:, NG:NG + n, NG:NG + n])) for t in range(6))
+    a0 = sum(float(np.abs(fields[t][:, NG:NG + n, NG:NG + n] * case.tiles[t].arr["area"][None, NG:NG + n, NG:NG + n]).sum()) for t in range(6))
+    oc.del2_cubed("OMGA", cd, nmax)
+    v1 = sum(float(np.var(oc.eng[t + 1].get("OMGA")[:, NG:NG + n, NG:NG + n])) for t in range(6))
+    i1 = _integral(oc, case, "OMGA")
+    oc.close()
+    assert v1 < 0.9 * v0
+    assert abs(i1 - i0) < 2e-3 * a0      # 8 corners x 3 averaged cells of 6 x 16^2 cells
+
+
+def test_oracle_dcon_heating_warms_and_is_bounded():
+    """Flag-set B (d_con = 1): after dyn_core the accumulated heat source has been turned into a temperature tendency
+    (heat_source holds K per step, |.| limited by delt_max * bdt scaled by the sponge factors) and pt changed accordingly."""
+    case = H.Case(12, 5, "B", state="baroclinic")
+    a = H.OracleCube(case)
+    bdt = 600.0
+    a.dyn_core(bdt, 2)
+    # same run without the post-loop step
+    b = H.OracleCube(case)
+    b.dcon_heating = lambda bdt: None
+    b.dyn_core(bdt, 2)
+    n = case.n
+    changed = 0.0
+    for t in a.tiles:
+        pa, pb = a.eng[t].get("PT")[:, NG:NG + n, NG:NG + n], b.eng[t].get("PT")[:, NG:NG + n, NG:NG + n]
+        pkz = a.eng[t].get("PKZ")
+        d = (pa - pb) * pkz                    # K
+        lim = abs(bdt) * case.flags["delt_max"] * np.array([0.1, 0.5, 1, 1, 1])[:, None, None]
+        assert (np.abs(d) <= lim * (1 + 1e-12)).all()
+        changed = max(changed, float(np.abs(d).max()))
+        assert np.isfinite(pa).all()
+    a.close(); b.close()
+    assert changed > 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nmax", [1, 2, 3])
+def test_cuda_del2_cubed_matches_oracle(nmax):
+    case, fields = _omega_case(n=32, npz=3)
+    oc, gc = H.OracleCube(case), H.CudaCube(case)
+    cd = 0.18 * case.tiles[0].da_min
+    for t in range(6):
+        oc.eng[t + 1].put("OMGA", fields[t]); gc.eng[t + 1].put("OMGA", fields[t])
+    oc.del2_cubed("OMGA", cd, nmax); gc.del2_cubed("OMGA", cd, nmax)
+    b = case.bounds
+    for t in oc.tiles:
+        err = H.compare(oc.eng[t], gc.eng[t], {"OMGA": (b["is_"], b["ie"], b["js"], b["je"])})["OMGA"]
+        assert err < 1e-13, (t, err)
+    oc.close(); gc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hydro", [0, 1])
+def test_cuda_dyn_core_with_dcon_heating(hydro):
+    """Flag-set B through fv3_dyn_core incl. the post-loop heating; pt, heat_source and pkz against the oracle."""
+    case = H.Case(16, 6, "B", state="baroclinic", flags_override=dict(hydrostatic=hydro))
+    oc, gc = H.OracleCube(case), H.CudaCube(case)
+    oc.dyn_core(800.0, 2); gc.dyn_core(800.0, 2)
+    b = case.bounds
+    reg = (b["is_"], b["ie"], b["js"], b["je"])
+    for t in oc.tiles:
+        res = H.compare(oc.eng[t], gc.eng[t], {"PT": reg, "HEAT": reg, "PKZ": reg, "DELP": reg})
+        for f, e in res.items():
+            assert e < (1e-9 if f != "HEAT" else 1e-7), (t, f, e)
+    hs = gc.eng[1].get("HEAT")
+    assert np.abs(hs).max() > 0.0
+    oc.close(); gc.close()
