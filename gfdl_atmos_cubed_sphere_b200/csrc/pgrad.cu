@@ -9,6 +9,7 @@
 // them back in place (the reference's replace=.true.), so the A-grid arrays stay readable by
 // neighbouring threads; nothing downstream reads the replaced arrays before they are rebuilt.
 #include "fv3_ctx.hpp"
+#include <algorithm>
 #include <cmath>
 
 #define TI 32
@@ -36,14 +37,21 @@ constexpr double a1 = 0.5625, a2 = -0.0625;         // a2b_edge.F90:34-35
 constexpr double b1 = 7. / 12., b2 = -1. / 12.;     // :39-40
 constexpr double c1 = 2. / 3., c2 = -1. / 6.;       // :54-55
 }
+// Up to four independent a2b_ord4 calls in one launch triple (nh_p_grad interpolates pp, pk3, gz, delp back to back,
+// dyn_core.F90:1743-1746 + nh_p_grad): the cube-edge passes are latency-bound launches of a few thousand points per level,
+// so four of them in one grid cost about what one does.  Field = blockIdx.y (edge passes) or blockIdx.z / nkmax (interior).
+struct A2bBatch { const double* qin[4]; double* qout[4]; double* qx[4]; double* qy[4]; int nk[4]; int nkmax; };
 
 // pass 1: qx (is:ie+1, 1:npy-1) and qy (1:npx-1, js:je+1)   (a2b_edge.F90:132-233)
 // frame != 0: only the points the frame outputs of pass 2 read (the interior is done by k_a2b_fused)
-__global__ void __launch_bounds__(128) k_a2b_1(Lay L, DevGrid G, FramePts FP, const double* __restrict__ qin, double* __restrict__ qx,
-                                               double* __restrict__ qy) {
+__global__ void __launch_bounds__(128) k_a2b_1(Lay L, DevGrid G, FramePts FP, A2bBatch B) {
   int i, j;
   if (!FP.map(blockIdx.x * 128 + threadIdx.x, i, j)) return;
-  const int k = blockIdx.z;
+  const int k = blockIdx.z, fld = blockIdx.y;
+  if (k >= B.nk[fld]) return;
+  const double* __restrict__ qin = B.qin[fld];
+  double* __restrict__ qx = B.qx[fld];
+  double* __restrict__ qy = B.qy[fld];
   const long long ko = (long long)k * L.plane;
   const int npx = L.npx, npy = L.npy;
   const bool cube = L.cube;
@@ -81,11 +89,15 @@ __global__ void __launch_bounds__(128) k_a2b_1(Lay L, DevGrid G, FramePts FP, co
 }
 
 // pass 2: qout on (is:ie+1, js:je+1)   (a2b_edge.F90:104-130, :141-166, :199-224, :258-288)
-__global__ void __launch_bounds__(128) k_a2b_2(Lay L, DevGrid G, FramePts FP, const double* __restrict__ qin, const double* __restrict__ qx,
-                                               const double* __restrict__ qy, double* __restrict__ qout) {
+__global__ void __launch_bounds__(128) k_a2b_2(Lay L, DevGrid G, FramePts FP, A2bBatch B) {
   int i, j;
   if (!FP.map(blockIdx.x * 128 + threadIdx.x, i, j)) return;
-  const int k = blockIdx.z;
+  const int k = blockIdx.z, fld = blockIdx.y;
+  if (k >= B.nk[fld]) return;
+  const double* __restrict__ qin = B.qin[fld];
+  const double* __restrict__ qx = B.qx[fld];
+  const double* __restrict__ qy = B.qy[fld];
+  double* __restrict__ qout = B.qout[fld];
   const long long ko = (long long)k * L.plane;
   const int npx = L.npx, npy = L.npy;
   auto Q = [&](int ii, int jj) { return AT(qin, ii, jj); };
@@ -155,12 +167,16 @@ __global__ void __launch_bounds__(128) k_a2b_2(Lay L, DevGrid G, FramePts FP, co
 // combines them; the intermediates never touch HBM (the two-pass form moved ~5x the field).
 #define AF_TX 32
 #define AF_TY 16
-__global__ void __launch_bounds__(256) k_a2b_fused(Lay L, const double* __restrict__ qin, double* __restrict__ qout) {
+__global__ void __launch_bounds__(256) k_a2b_fused(Lay L, A2bBatch B) {
   __shared__ double q[AF_TY + 3][AF_TX + 4];
   __shared__ double qx[AF_TY + 3][AF_TX];
   __shared__ double qy[AF_TY][AF_TX + 4];
+  const int fld = blockIdx.z / B.nkmax, kk = blockIdx.z - fld * B.nkmax;
+  if (kk >= B.nk[fld]) return;
+  const double* __restrict__ qin = B.qin[fld];
+  double* __restrict__ qout = B.qout[fld];
   const int i0 = 3 + blockIdx.x * AF_TX, j0 = 3 + blockIdx.y * AF_TY;   // first output point of the tile
-  const long long ko = (long long)blockIdx.z * L.plane;
+  const long long ko = (long long)kk * L.plane;
   const int tid = threadIdx.x, hi = L.npx - 2;                          // last output index in both directions
   for (int e = tid; e < (AF_TY + 3) * (AF_TX + 3); e += 256) {
     const int r = e / (AF_TX + 3), c = e - r * (AF_TX + 3);
@@ -186,15 +202,21 @@ __global__ void __launch_bounds__(256) k_a2b_fused(Lay L, const double* __restri
   }
 }
 
-// qx, qy scratch = c->scr[4], c->scr[5] (free in both callers: d_sw between transports, nh_p_grad)
-int launch_a2b_ord4(fv3_ctx* c, const double* qin, double* qout, int nk, int /*replace_into_qin*/) {
+// n <= 4 fields; qx, qy scratch of field f = c->scr[scr0 + 2 f], c->scr[scr0 + 2 f + 1]
+int launch_a2b_ord4_batch(fv3_ctx* c, int n, const double* const* qin, double* const* qout, const int* nk, int scr0) {
   const Lay& L = c->L;
-  dim3 blk(TI, TJ);
+  if (n < 1 || n > 4 || scr0 + 2 * n > fv3_ctx::NSCR) return fv3_fail(c, -1, "a2b_ord4 batch: bad field count / scratch range");
+  A2bBatch B{};
+  B.nkmax = 0;
+  for (int f = 0; f < n; f++) {
+    B.qin[f] = qin[f]; B.qout[f] = qout[f]; B.qx[f] = c->scr[scr0 + 2 * f]; B.qy[f] = c->scr[scr0 + 2 * f + 1]; B.nk[f] = nk[f];
+    B.nkmax = std::max(B.nkmax, nk[f]);
+  }
   const int ni = L.npx - 4;   // outputs 3 .. npx-2
   const int fused = L.cube && ni >= 1 && L.npx == L.npy;
   if (fused) {
-    dim3 g((ni + AF_TX - 1) / AF_TX, (ni + AF_TY - 1) / AF_TY, nk);
-    k_a2b_fused<<<g, 256, 0, c->stream>>>(L, qin, qout);
+    dim3 g((ni + AF_TX - 1) / AF_TX, (ni + AF_TY - 1) / AF_TY, B.nkmax * n);
+    k_a2b_fused<<<g, 256, 0, c->stream>>>(L, B);
     c->launches++;
   }
   // edge passes, one thread per point: pass 1 on (is-2:ie+2)^2 where i <= 5 || i >= npx-4 (same in j) -- what the
@@ -203,11 +225,14 @@ int launch_a2b_ord4(fv3_ctx* c, const double* qin, double* qout, int nk, int /*r
                             : frame_pts(L.is - 2, L.ie + 2, L.js - 2, L.je + 2, 1, 0, 1, 0);
   const FramePts P2 = fused ? frame_pts(L.is, L.ie + 1, L.js, L.je + 1, 3, L.npx - 2, 3, L.npy - 2)
                             : frame_pts(L.is, L.ie + 1, L.js, L.je + 1, 1, 0, 1, 0);
-  (void)blk;
-  k_a2b_1<<<dim3((P1.count() + 127) / 128, 1, nk), 128, 0, c->stream>>>(L, c->G, P1, qin, c->scr[4], c->scr[5]);
-  k_a2b_2<<<dim3((P2.count() + 127) / 128, 1, nk), 128, 0, c->stream>>>(L, c->G, P2, qin, c->scr[4], c->scr[5], qout);
+  k_a2b_1<<<dim3((P1.count() + 127) / 128, n, B.nkmax), 128, 0, c->stream>>>(L, c->G, P1, B);
+  k_a2b_2<<<dim3((P2.count() + 127) / 128, n, B.nkmax), 128, 0, c->stream>>>(L, c->G, P2, B);
   c->launches += 2;
   return 0;
+}
+// single field; qx, qy scratch = c->scr[4], c->scr[5] (free in both callers: d_sw between transports, one_grad_p)
+int launch_a2b_ord4(fv3_ctx* c, const double* qin, double* qout, int nk, int /*replace_into_qin*/) {
+  return launch_a2b_ord4_batch(c, 1, &qin, &qout, &nk, 4);
 }
 
 // ---- p_grad_c (dyn_core.F90:1635-1694), in place on uc, vc ---------------------------------
@@ -289,10 +314,12 @@ int stage_nh_p_grad(fv3_ctx* c, double dt) {
   k_nh_top<<<g1, blk, 0, c->stream>>>(L, ppb, pkb, top_value);
   c->launches++;
   int rc;
-  if ((rc = launch_a2b_ord4(c, c->fld[FV3_PKC] + P, ppb + P, km, 1))) return rc;   // pp, k = 2..km+1
-  if ((rc = launch_a2b_ord4(c, c->fld[FV3_PK3] + P, pkb + P, km, 1))) return rc;   // pk, k = 2..km+1
-  if ((rc = launch_a2b_ord4(c, c->fld[FV3_GZ], gzb, km + 1, 1))) return rc;        // gz, k = 1..km+1
-  if ((rc = launch_a2b_ord4(c, c->fld[FV3_DELP], dpb, km, 0))) return rc;          // delp -> wk1
+  {  // pp, pk (k = 2..km+1), gz (k = 1..km+1), delp -> wk1: four a2b_ord4 calls in one launch triple; scratch scr[4..11]
+    const double* qin[4] = {c->fld[FV3_PKC] + P, c->fld[FV3_PK3] + P, c->fld[FV3_GZ], c->fld[FV3_DELP]};
+    double* qout[4] = {ppb + P, pkb + P, gzb, dpb};
+    const int nks[4] = {km, km, km + 1, km};
+    if ((rc = launch_a2b_ord4_batch(c, 4, qin, qout, nks, 4))) return rc;
+  }
   k_nh_pgrad<<<plane_grid(L, km), blk, 0, c->stream>>>(L, c->G, ppb, pkb, gzb, dpb, c->fld[FV3_U], c->fld[FV3_V], dt);
   c->launches++;
   return 0;
@@ -339,8 +366,12 @@ int stage_one_grad_p(fv3_ctx* c, double dt) {
   k_set_top<<<plane_grid(L, 1), blk, 0, c->stream>>>(L, pkb, pow(c->f.ptop, c->f.kappa));   // ptk, dyn_core.F90:222,1944
   c->launches++;
   int rc;
-  if ((rc = launch_a2b_ord4(c, c->fld[FV3_PKC] + P, pkb + P, km, 1))) return rc;   // pk, k = 2..km+1
-  if ((rc = launch_a2b_ord4(c, c->fld[FV3_GZ], gzb, km + 1, 1))) return rc;        // gz, k = 1..km+1
+  {  // pk (k = 2..km+1) and gz (k = 1..km+1) in one launch triple; scratch scr[4..7]
+    const double* qin[2] = {c->fld[FV3_PKC] + P, c->fld[FV3_GZ]};
+    double* qout[2] = {pkb + P, gzb};
+    const int nks[2] = {km, km + 1};
+    if ((rc = launch_a2b_ord4_batch(c, 2, qin, qout, nks, 4))) return rc;
+  }
   k_one_grad_p<<<plane_grid(L, km), blk, 0, c->stream>>>(L, c->G, pkb, gzb, c->fld[FV3_U], c->fld[FV3_V], dt);
   c->launches++;
   return 0;
