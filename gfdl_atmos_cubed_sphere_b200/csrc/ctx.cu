@@ -370,6 +370,7 @@ int fv3_pe_halo(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_pe_halo(c); if (r
 int fv3_gz_from_zh(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_gz_from_zh(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_nh_p_grad(fv3_ctx* c, double dt) { STAGE_PROLOGUE(c) int rc = stage_nh_p_grad(c, dt); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_del2_cubed(fv3_ctx* c, int field, double cd, int nmax) { STAGE_PROLOGUE(c) int rc = stage_del2_cubed(c, field, cd, nmax); if (rc) return rc; STAGE_EPILOGUE(c) }
+int fv3_pt_to_theta(fv3_ctx* c, double zvir) { STAGE_PROLOGUE(c) int rc = stage_pt_to_theta(c, zvir); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_dcon_heating(fv3_ctx* c, double bdt) { STAGE_PROLOGUE(c) int rc = stage_dcon_heating(c, bdt); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_geopk(fv3_ctx* c, int cg) { STAGE_PROLOGUE(c) int rc = stage_geopk(c, cg); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_one_grad_p(fv3_ctx* c, double dt) { STAGE_PROLOGUE(c) int rc = stage_one_grad_p(c, dt); if (rc) return rc; STAGE_EPILOGUE(c) }

@@ -115,6 +115,22 @@ __global__ void __launch_bounds__(TI* TJ) k_dcon_heat(Lay L, double* __restrict_
   hs[o] = dtmp;
 }
 
+// fv_dynamics.F90:303-328, :377-398
+__global__ void __launch_bounds__(TI* TJ) k_pt_to_theta(Lay L, double* __restrict__ pt, const double* __restrict__ delp, const double* __restrict__ delz,
+                                                      const double* __restrict__ qv, const double* __restrict__ qcon, double* __restrict__ dp1,
+                                                      double* __restrict__ pkz, double zvir, double rdg, double kappa, int hydrostatic, int use_cond) {
+  const int i = L.is + blockIdx.x * TI + threadIdx.x;
+  const int j = L.js + blockIdx.y * TJ + threadIdx.y;
+  if (i > L.ie || j > L.je) return;
+  const long long o = (long long)blockIdx.z * L.plane + LIDX(L, i, j);
+  const double d1 = zvir * __ldg(qv + o), p = pt[o];
+  dp1[o] = d1;
+  double pz;
+  if (!hydrostatic) { pz = exp(kappa * log(rdg * __ldg(delp + o) * p * (1. + d1) / __ldg(delz + o))); pkz[o] = pz; }
+  else pz = pkz[o];
+  pt[o] = use_cond ? p * (1. + d1) * (1. - __ldg(qcon + o)) / pz : p * (1. + d1) / pz;
+}
+
 }  // namespace
 
 // dyn_core.F90:296-307
@@ -156,6 +172,22 @@ int stage_dcon_heating(fv3_ctx* c, double bdt) {
   k_dcon_heat<<<grd, blk, 0, c->stream>>>(L, c->fld[FV3_PT], c->fld[FV3_HEAT], c->fld[FV3_DELP], c->fld[FV3_DELZ], c->fld[FV3_PKZ], bdt,
                                            f.delt_max, f.cp_air, f.cp_air - f.rdgas, -f.rdgas / f.grav, f.kappa / (1. - f.kappa),
                                            f.hydrostatic ? 1 : 0);
+  c->launches++;
+  return 0;
+}
+
+// fv_dynamics.F90:303-328 + :377-398: the entry conversion of fv_dynamics (temperature -> virtual potential temperature,
+// pkz from the gas law); specific humidity is read from FV3_WORK_Q, dp1 = zvir q_v is left in FV3_DP1
+int stage_pt_to_theta(fv3_ctx* c, double zvir) {
+  StageScope ts(c, "PT_TO_THETA");
+  const fv3_flags_t& f = c->f;
+  if (f.moist_kappa) return fv3_fail(c, -2, "pt_to_theta: moist_kappa (moist_cv) not supported");
+  const Lay& L = c->L;
+  const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;
+  const dim3 blk(TI, TJ), grd((nx + TI - 1) / TI, (ny + TJ - 1) / TJ, L.npz);
+  k_pt_to_theta<<<grd, blk, 0, c->stream>>>(L, c->fld[FV3_PT], c->fld[FV3_DELP], c->fld[FV3_DELZ], c->fld[FV3_WORK_Q], c->fld[FV3_QCON],
+                                             c->fld[FV3_DP1], c->fld[FV3_PKZ], zvir, -f.rdgas / f.grav, f.kappa, f.hydrostatic ? 1 : 0,
+                                             f.use_cond ? 1 : 0);
   c->launches++;
   return 0;
 }

@@ -174,6 +174,7 @@ int stage_nh_p_grad(fv3_ctx* c, double dt);
 int stage_geopk(fv3_ctx* c, int cg);
 int stage_del2_cubed(fv3_ctx* c, int field, double cd, int nmax);
 int stage_dcon_heating(fv3_ctx* c, double bdt);
+int stage_pt_to_theta(fv3_ctx* c, double zvir);
 int fv3_n_con(const fv3_flags_t& f, int npz);
 int stage_one_grad_p(fv3_ctx* c, double dt);
 int stage_gz_init(fv3_ctx* c);

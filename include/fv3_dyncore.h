@@ -197,6 +197,9 @@ int fv3_nh_p_grad(fv3_ctx *ctx, double dt);
  * FV3_HALO_HEAT / FV3_HALO_OMGA, or fv3_del2_cubed_cube which does both).  nmax passes (at most 3). */
 int fv3_del2_cubed(fv3_ctx *ctx, int field, double cd, int nmax);
 int fv3_del2_cubed_cube(fv3_ctx **ctxs, int nctx, int field, double cd, int nmax);
+/* Entry conversion of fv_dynamics (fv_dynamics.F90:303-328, 377-398; moist_kappa = F): dp1 = zvir*q_v (q_v in FV3_WORK_Q, result
+ * in FV3_DP1), non-hydrostatic pkz = exp(kappa*log(rdg*delp*pt*(1+dp1)/delz)), pt = pt*(1+dp1)[*(1-q_con)]/pkz. */
+int fv3_pt_to_theta(fv3_ctx *ctx, double zvir);
 /* dyn_core.F90:1305-1356: filtered heat_source -> pt (levels 1..n_con, limited by delt_max); part of fv3_dyn_core */
 int fv3_dcon_heating(fv3_ctx *ctx, double bdt);
 int fv3_geopk(fv3_ctx *ctx, int cg);

@@ -310,6 +310,13 @@ int fv3o_del2_cubed(fv3o_ctx* c, int field, double cd, int nmax) {
   del2_cubed(F3(c, field), cd, g, bd, bd.npz, nmax);
   return 0;
 }
+// fv_dynamics.F90:303-328, :377-398: specific humidity in FV3_WORK_Q (read only when zvir != 0 is meaningful; it is multiplied anyway)
+int fv3o_pt_to_theta(fv3o_ctx* c, double zvir) {
+  if (c->f.moist_kappa) return -2;
+  Bd bd(c->b);
+  pt_to_theta(F3(c, FV3_PT), F3(c, FV3_DELP), F3(c, FV3_DELZ), F3(c, FV3_WORK_Q), F3(c, FV3_QCON), F3(c, FV3_DP1), F3(c, FV3_PKZ), zvir, c->f, bd);
+  return 0;
+}
 // dyn_core.F90:1300-1356 without the del2_cubed call
 int fv3o_dcon_heating(fv3o_ctx* c, double bdt) {
   Bd bd(c->b);

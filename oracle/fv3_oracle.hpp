@@ -189,6 +189,7 @@ void riem_solver3(int ms, double dt, int is, int ie, int js, int je, int km, int
                   V3 delp, V3 zh, double* pe /*(is-1:ie+1,km+1,js-1:je+1)*/, V3 ppe, V3 pk3, V3 pk,
                   double* peln /*(is:ie,km+1,js:je)*/, V2 ws, double p_fac, double a_imp, bool use_logp,
                   bool use_cond, bool moist_kappa, bool last_call, bool fp_out, const Consts& c);
+void pt_to_theta(V3 pt, V3 delp, V3 delz, V3 qv, V3 q_con, V3 dp1, V3 pkz, double zvir, const fv3_flags_t& f, const Bd& bd);
 void del2_cubed(V3 q, double cd, const Grid& g, const Bd& bd, int km, int nmax);
 int n_con_levels(const fv3_flags_t& f, int npz);
 void dcon_heating(V3 pt, V3 heat_source, V3 delp, V3 delz, V3 pkz, int n_con, double bdt, const fv3_flags_t& f, const Bd& bd);

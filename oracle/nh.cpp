@@ -676,4 +676,20 @@ void dcon_heating(V3 pt, V3 heat_source, V3 delp, V3 delz, V3 pkz, int n_con, do
   }
 }
 
+// fv_dynamics.F90:303-328, :377-398 (not SW_DYNAMICS; moist_kappa = F): dp1 = zvir q_v, pkz from the gas law (non-hydrostatic;
+// the hydrostatic pkz comes from p_var / the previous remap), pt -> virtual potential (density) temperature pt (1+dp1)[(1-q_con)]/pkz
+void pt_to_theta(V3 pt, V3 delp, V3 delz, V3 qv, V3 q_con, V3 dp1, V3 pkz, double zvir, const fv3_flags_t& f, const Bd& bd) {
+  const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je;
+  const double rdg = -f.rdgas / f.grav;
+#pragma omp parallel for schedule(static)
+  for (int k = 1; k <= bd.npz; k++)
+    for (int j = js; j <= je; j++)
+      for (int i = is; i <= ie; i++) {
+        dp1(i, j, k) = zvir * qv(i, j, k);
+        if (!f.hydrostatic) pkz(i, j, k) = std::exp(f.kappa * std::log(rdg * delp(i, j, k) * pt(i, j, k) * (1. + dp1(i, j, k)) / delz(i, j, k)));
+        if (f.use_cond) pt(i, j, k) = pt(i, j, k) * (1. + dp1(i, j, k)) * (1. - q_con(i, j, k)) / pkz(i, j, k);
+        else pt(i, j, k) = pt(i, j, k) * (1. + dp1(i, j, k)) / pkz(i, j, k);
+      }
+}
+
 }  // namespace fv3o

@@ -109,3 +109,66 @@ def test_cuda_dyn_core_with_dcon_heating(hydro):
     hs = gc.eng[1].get("HEAT")
     assert np.abs(hs).max() > 0.0
     oc.close(); gc.close()
+
+
+def _theta_case(hydro=0, use_cond=0):
+    case = H.Case(12, 5, "A", state="baroclinic", flags_override=dict(hydrostatic=hydro, use_cond=use_cond))
+    rng = np.random.default_rng(3)
+    qv = [1e-3 * (1.0 + rng.random((5,) + g.arr["agrid"][0].shape)) for g in case.tiles]
+    qc = [1e-4 * rng.random((5,) + g.arr["agrid"][0].shape) for g in case.tiles]
+    return case, qv, qc
+
+
+def _load_theta(e, case, t, qv, qc, T):
+    e.put("WORK_Q", qv[t]); e.put("QCON", qc[t]); e.put("PT", T)
+    if case.flags["hydrostatic"]:
+        n = case.n
+        e.put("PKZ", np.full((5, n, n), 1.0) * (np.linspace(5.0, 45.0, 5)[:, None, None]))
+
+
+@pytest.mark.parametrize("hydro,use_cond", [(0, 0), (0, 1), (1, 0)])
+def test_oracle_pt_to_theta_matches_the_formulas(hydro, use_cond):
+    """fv_dynamics.F90:303-328, 377-398 against the same expressions in NumPy."""
+    case, qv, qc = _theta_case(hydro, use_cond)
+    lib = H.load_oracle()
+    zvir = 0.6078
+    cst = case.consts
+    for t in (0, 3):
+        e = case.engine(lib, t + 1)
+        case.load_state(e, t + 1)
+        T = 250.0 + 30.0 * np.cos(case.tiles[t].arr["agrid"][1])[None] + np.arange(5)[:, None, None]
+        _load_theta(e, case, t, qv, qc, T)
+        pkz_in = e.get("PKZ")
+        e.call("pt_to_theta", zvir)
+        n = case.n
+        sl = (slice(None), slice(NG, NG + n), slice(NG, NG + n))
+        d1 = zvir * qv[t][sl]
+        delp, delz = e.get("DELP")[sl], e.get("DELZ")
+        if hydro:
+            pkz = pkz_in
+        else:
+            pkz = np.exp(cst["kappa"] * np.log(-cst["rdgas"] / cst["grav"] * delp * T[sl] * (1 + d1) / delz))
+        want = T[sl] * (1 + d1) * ((1 - qc[t][sl]) if use_cond else 1.0) / pkz
+        assert np.abs(e.get("PT")[sl] / want - 1).max() < 1e-14
+        assert np.abs(e.get("PKZ") / pkz - 1).max() < 1e-14
+        assert np.abs(e.get("DP1")[sl] - d1).max() == 0.0
+        e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hydro,use_cond", [(0, 0), (0, 1), (1, 0)])
+def test_cuda_pt_to_theta_matches_oracle(hydro, use_cond):
+    case, qv, qc = _theta_case(hydro, use_cond)
+    from gfdl_atmos_cubed_sphere_b200 import abi
+    eo, eg = case.engine(H.load_oracle(), 2), case.engine(abi.load_library(), 2)
+    T = 250.0 + 30.0 * np.cos(case.tiles[1].arr["agrid"][1])[None] + np.arange(5)[:, None, None]
+    for e in (eo, eg):
+        case.load_state(e, 2)
+        _load_theta(e, case, 1, qv, qc, T)
+        e.call("pt_to_theta", 0.6078)
+    b = case.bounds
+    reg = (b["is_"], b["ie"], b["js"], b["je"])
+    res = H.compare(eo, eg, {"PT": reg, "PKZ": reg, "DP1": reg})
+    for f, err in res.items():
+        assert err < 1e-13, (f, err)
+    eo.close(); eg.close()
