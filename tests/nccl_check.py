@@ -11,7 +11,7 @@ from gfdl_atmos_cubed_sphere_b200 import abi
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-case = H.Case(24, 6, "A", state="baroclinic")
+case = H.Case(24, 6, os.environ.get("FV3_CHECK_FLAGSET", "A"), state="baroclinic")
 lib = abi.load_library()
 my = B.tiles_of_rank(rank, world)
 cube = H.CudaCube(case, tiles=my, device=local, link=True) if len(my) > 1 else H.CudaCube(case, tiles=my, device=local, link=False)
