@@ -52,3 +52,12 @@ def test_oracle_is_not_reachable_from_the_package():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "libfv3_oracle" not in src and "fv3o_" not in src, f
+
+
+def test_unbuilt_sw_test_cases_are_rejected(built):
+    """Only test_case 1 of the SW_DYNAMICS build exists (BASELINE config 1a); other values are an argument error (-2), with or
+    without a GPU -- the check precedes any device work."""
+    _lib(built)
+    case = H.Case(8, 1, "A", flags_override=dict(sw_test_case=2))
+    with pytest.raises(RuntimeError, match="rc=-2"):
+        case.engine(abi.load_library(), 1)
