@@ -780,6 +780,8 @@ static int launch_transport(fv3_ctx* c, const DswTr& a, int nk) {
   const bool m_dp = a.hord_dp >= 8, m_vt = a.hord_vt >= 8, m_tm = a.hord_tm >= 8;
   const bool vt_used = a.w != nullptr, tm_used = a.pt != nullptr;
   const bool all_mono = m_dp && (m_tm || !tm_used) && (m_vt || !vt_used), none_mono = !m_dp && (!m_tm || !tm_used) && (!m_vt || !vt_used);
+  const bool rare = hord_is_rare(a.hord_dp) || (tm_used && hord_is_rare(a.hord_tm)) || (vt_used && hord_is_rare(a.hord_vt));
+  if (rare) return launch_transport_t<2>(c, a, nk);   // the general instantiation carries the less common schemes
   if (all_mono) return launch_transport_t<1>(c, a, nk);
   if (none_mono) return launch_transport_t<0>(c, a, nk);
   return launch_transport_t<2>(c, a, nk);
@@ -807,8 +809,8 @@ int stage_d_sw(fv3_ctx* c, double dt) {
   const Lay& L = c->L;
   const fv3_flags_t& f = c->f;
   const int nk = L.npz;
-  if (!hord_supported(f.hord_dp) || !hord_supported(f.hord_tm) || !hord_supported(f.hord_vt) || !hord_wind_supported(f.hord_mt))
-    return fv3_fail(c, -2, "d_sw: unsupported hord (supported: 5, 6, -5, 8, 10; hord_mt: 5, 6, 8, 10)");
+  if (!hord_supported(f.hord_dp, f.lim_fac) || !hord_supported(f.hord_tm, f.lim_fac) || !hord_supported(f.hord_vt, f.lim_fac) || !hord_wind_supported(f.hord_mt))
+    return fv3_fail(c, -2, "d_sw: unsupported hord (supported: -5, 1..6, 8..13 [1 only with lim_fac = 1]; hord_mt: 5, 6, 8, 10)");
   if (f.inline_q) return fv3_fail(c, -2, "d_sw: inline_q not supported");
   if (f.do_f3d) return fv3_fail(c, -2, "d_sw: do_f3d not supported");
   if (f.nord > 3) return fv3_fail(c, -2, "d_sw: nord > 3 not supported");
@@ -958,8 +960,9 @@ int stage_d_sw(fv3_ctx* c, double dt) {
                                   c->d_kint, c->d_kdbl, dt, f.dddmp, f.d4_bg, c->b.stretched_grid);
   c->launches++;
   // --- vorticity transport and momentum update (:1476-1509), fused
-  rc = (f.hord_vt >= 8) ? launch_vort_uv_t<1>(c, vq, u, v, ke, c->alt_u, c->alt_v, nk)
-                        : launch_vort_uv_t<0>(c, vq, u, v, ke, c->alt_u, c->alt_v, nk);
+  rc = hord_is_rare(f.hord_vt) ? launch_vort_uv_t<2>(c, vq, u, v, ke, c->alt_u, c->alt_v, nk)
+       : (f.hord_vt >= 8)      ? launch_vort_uv_t<1>(c, vq, u, v, ke, c->alt_u, c->alt_v, nk)
+                               : launch_vort_uv_t<0>(c, vq, u, v, ke, c->alt_u, c->alt_v, nk);
   if (rc) return rc;
   {
     FrameJobs fj{};

@@ -646,7 +646,7 @@ int stage_update_dz_d(fv3_ctx* c, double dt) {
   StageScope ts(c, "UPDATE_DZ");
   const Lay& L = c->L;
   const int km = L.npz, n1 = km + 1;
-  if (!ppm::hord_supported(c->f.hord_tm)) return fv3_fail(c, -2, "update_dz_d: unsupported hord_tm");
+  if (!ppm::hord_supported(c->f.hord_tm, c->f.lim_fac)) return fv3_fail(c, -2, "update_dz_d: unsupported hord_tm");
   // damp(km+1) = damp(km), ndif(km+1) = ndif(km)  (nh_utils.F90:240-241); tables set by the d_sw prologue
   c->damp_vt[km] = c->damp_vt[km - 1]; c->nord_v[km] = c->nord_v[km - 1];
   std::vector<int> ki(n1); std::vector<double> kd(n1);

@@ -90,6 +90,75 @@ __device__ __forceinline__ void pert_std(double& al, double& ar) {  // pert_ppm 
   } else { al = 0.; ar = 0.; }
 }
 
+// pert_ppm with iv == 0 for one cell (positive-definite constraint of iord 9 / 13, tp_core.F90:1222-1244)
+__device__ __forceinline__ void pert_pd(double a0, double& al, double& ar) {
+  if (a0 <= 0.) { al = 0.; ar = 0.; return; }
+  const double a4 = -3. * (ar + al), da1 = ar - al;
+  if (fabs(da1) < -a4) {
+    const double fmin_ = a0 + 0.25 / a4 * (da1 * da1) + a4 * r12;
+    if (fmin_ < 0.) {
+      if (ar > 0. && al > 0.) { ar = 0.; al = 0.; }
+      else if (da1 > 0.) ar = -2. * al;
+      else al = -2. * ar;
+    }
+  }
+}
+// Out of line: the rarely used schemes must not grow the hot 8 / 10 / 5 / 6 loop bodies (instruction cache, tp_tile.cuh).
+// (bl, br) of an ordinary interior cell in the dm family for the schemes beyond 8 and 10: 11 (van Leer emulation, ppm_fac = 1.5,
+// tp_core.F90:598-604), 12 (Lin & Rood positive definite, :605-627), 9 / 13 (unconstrained + pert_ppm(iv=0), :628-635)
+static __device__ __noinline__ void mono_blbr_other(double q0, double al0, double al1, double dm0, int iord, double& bl, double& br) {
+  if (iord == 11) {
+    const double xt = 1.5 * dm0;
+    bl = -fsign(mn(fabs(xt), fabs(al0 - q0)), xt);
+    br = fsign(mn(fabs(xt), fabs(al1 - q0)), xt);
+  } else if (iord == 12) {
+    bl = al0 - q0; br = al1 - q0;
+    const double a4 = -3. * (bl + br), da1 = br - bl;
+    const bool ext5 = br * bl > 0., ext6 = fabs(da1) < -a4;
+    if (ext6) {
+      if (q0 + 0.25 / a4 * (da1 * da1) + a4 * r12 < 0.) {
+        if (ext5) { br = 0.; bl = 0.; }
+        else if (da1 > 0.) br = -2. * bl;
+        else bl = -2. * br;
+      }
+    }
+  } else {   // 9, 13
+    bl = al0 - q0; br = al1 - q0;
+    pert_pd(q0, bl, br);
+  }
+}
+// al family, mord = |iord| in 1..4 (tp_core.F90:401-486): flux through the face between cells A (value qa) and B (qb) from
+// al at the low face of A (alm), the shared face (al0) and the high face of B (alp).  lim_fac == 1 (checked on the host).
+static __device__ __noinline__ double flux_al_low(double qa, double qb, double alm, double al0, double alp, double c, int mord) {
+  if (mord == 2) {
+    if (c > 0.) return qa + (1. - c) * (al0 - qa - c * (alm + al0 - (qa + qa)));
+    return qb + (1. + c) * (al0 - qb + c * (al0 + alp - (qb + qb)));
+  }
+  const double Abl = alm - qa, Abr = al0 - qa, Ab0 = Abl + Abr;
+  const double Bbl = al0 - qb, Bbr = alp - qb, Bb0 = Bbl + Bbr;
+  const double Ax0 = fabs(Ab0), Axt = fabs(Abl - Abr), Bx0 = fabs(Bb0), Bxt = fabs(Bbl - Bbr);
+  if (mord == 1) {
+    const bool As = Ax0 < Axt, Bs = Bx0 < Bxt;
+    double fx1, fl;
+    if (c > 0.) { fx1 = (1. - c) * (Abr - c * Ab0); fl = qa; }
+    else { fx1 = (1. + c) * (Bbl + c * Bb0); fl = qb; }
+    if (As || Bs) fl = fl + fx1;
+    return fl;
+  }
+  const bool A5 = Ax0 < Axt, A6 = 3. * Ax0 < Axt, B5 = Bx0 < Bxt, B6 = 3. * Bx0 < Bxt;
+  if (mord == 3) {
+    if (c > 0.) return (A5 || B6) ? qa + (1. - c) * (Abr - c * Ab0) : qa;
+    return (A6 || B5) ? qb + (1. + c) * (Bbl + c * Bb0) : qb;
+  }
+  // mord == 4
+  const bool hi5 = (A5 && B5) || (A6 || B6);
+  double fx1, fl;
+  if (c > 0.) { fx1 = (1. - c) * (Abr - c * Ab0); fl = qa; }
+  else { fx1 = (1. + c) * (Bbl + c * Bb0); fl = qb; }
+  if (hi5) fl = fl + fx1;
+  return fl;
+}
+
 // dxa-weighted two-sided edge value (tp_core.F90:376-377 / :647-648); e = first cell inside
 // the face on the high side of the edge (e = 1 for the west/south edge, e = n for east/north)
 template <class Q, class D>
@@ -100,7 +169,9 @@ __device__ __forceinline__ double edge_avg(const Q& q, const D& d, int e) {
 
 // ------------------------------------------------------------------ scalar transport (xppm/yppm)
 // monotone family: (bl, br) of cell i.  n = npx (or npy).  tp_core.F90:563-681
-template <class Q, class D>
+// RARE = false compiles the schemes beyond 8 / 10 (dm family) and 5 / 6 / -5 (al family) out: the hot instantiations of the
+// transport kernels must not carry their code or their out-of-line calls (measured: +4.6 % on d_sw when they did)
+template <bool RARE = true, class Q, class D>
 __device__ __forceinline__ void cell_mono(const Q& q, const D& dxa, int i, int iord, int n, bool cube, double& bl, double& br) {
   if (!cube || (i >= 3 && i <= n - 3)) {
     const double qm1 = q(i - 1), q0 = q(i), qp1 = q(i + 1);
@@ -111,7 +182,7 @@ __device__ __forceinline__ void cell_mono(const Q& q, const D& dxa, int i, int i
       const double xt = 2. * dm0;
       bl = -fsign(mn(fabs(xt), fabs(al0 - q0)), xt);
       br = fsign(mn(fabs(xt), fabs(al1 - q0)), xt);
-    } else {  // 10
+    } else if (iord == 10 || !RARE) {
       bl = al0 - q0; br = al1 - q0;
       if (fabs(dmm) + fabs(dm0) + fabs(dmp) < near_zero_tp) { bl = 0.; br = 0.; }
       else if (fabs(3. * (bl + br)) > fabs(bl - br)) {
@@ -121,7 +192,7 @@ __device__ __forceinline__ void cell_mono(const Q& q, const D& dxa, int i, int i
         const double pmp_1 = -dq0, lac_1 = pmp_1 + 0.75 * dqp1;
         bl = mn(max3(0., pmp_1, lac_1), mx(bl, min3(0., pmp_1, lac_1)));
       }
-    }
+    } else if (RARE) mono_blbr_other(q0, al0, al1, dm0, iord, bl, br);
     return;
   }
   // cube-edge cells
@@ -197,15 +268,18 @@ __device__ __forceinline__ CellU cell_unlim(const Q& q, const D& dxa, int i, int
 }
 
 // flux through interface i for Courant number c.  tp_core.F90:549-558, :701-707
-template <class Q, class D>
+template <bool RARE = true, class Q, class D>
 __device__ __forceinline__ double flux_scalar(const Q& q, const D& dxa, int i, double c, int iord, int n, bool cube) {
   if (iord >= 8) {
     const int iu = (c > 0.) ? i - 1 : i;
     double bl, br;
-    cell_mono(q, dxa, iu, iord, n, cube, bl, br);
+    cell_mono<RARE>(q, dxa, iu, iord, n, cube, bl, br);
     const double qu = q(iu);
     return (c > 0.) ? qu + (1. - c) * (br - c * (bl + br)) : qu + (1. + c) * (bl + c * (bl + br));
   }
+  if (RARE && iord >= 1 && iord <= 4)   // no smt override at the cube-edge cells for these (tp_core.F90:536-545 is inside the 5 / -5 / 6 branch)
+    return flux_al_low(q(i - 1), q(i), al_unlim(q, dxa, i - 1, iord, n, cube), al_unlim(q, dxa, i, iord, n, cube),
+                       al_unlim(q, dxa, i + 1, iord, n, cube), c, iord);
   const CellU a = cell_unlim(q, dxa, i - 1, iord, n, cube);
   const CellU b = cell_unlim(q, dxa, i, iord, n, cube);
   double fx1, fl;
@@ -469,6 +543,7 @@ __device__ __forceinline__ double aux_point(bool mono, int iord, double qm2, dou
   return iord < 0 ? mx(0., al) : al;
 }
 // monotone flux from the upwind cell's neighbourhood: q(iu-2..iu+2), dm(iu-1..iu+1)
+template <bool RARE = true>
 __device__ __forceinline__ double flux_mono_aux(double qm2, double qm1, double q0, double qp1, double qp2, double dmm, double dm0,
                                                 double dmp, double c, int iord) {
   const double al0 = 0.5 * (qm1 + q0) + r3 * (dmm - dm0);
@@ -478,7 +553,7 @@ __device__ __forceinline__ double flux_mono_aux(double qm2, double qm1, double q
     const double xt = 2. * dm0;
     bl = -fsign(mn(fabs(xt), fabs(al0 - q0)), xt);
     br = fsign(mn(fabs(xt), fabs(al1 - q0)), xt);
-  } else {
+  } else if (iord == 10 || !RARE) {
     bl = al0 - q0; br = al1 - q0;
     if (fabs(dmm) + fabs(dm0) + fabs(dmp) < near_zero_tp) { bl = 0.; br = 0.; }
     else if (fabs(3. * (bl + br)) > fabs(bl - br)) {
@@ -488,12 +563,14 @@ __device__ __forceinline__ double flux_mono_aux(double qm2, double qm1, double q
       const double pmp_1 = -dq0, lac_1 = pmp_1 + 0.75 * dqp1;
       bl = mn(max3(0., pmp_1, lac_1), mx(bl, min3(0., pmp_1, lac_1)));
     }
-  }
+  } else mono_blbr_other(q0, al0, al1, dm0, iord, bl, br);
   return (c > 0.) ? q0 + (1. - c) * (br - c * (bl + br)) : q0 + (1. + c) * (bl + c * (bl + br));
 }
 // unlimited-family flux through the face between cells A (low side, value qa) and B (qb); alm, al0, alp = al at the
 // low face of A, the shared face, the high face of B
+template <bool RARE = true>
 __device__ __forceinline__ double flux_unlim_aux(double qa, double qb, double alm, double al0, double alp, double c, int iord) {
+  if (RARE && iord >= 1 && iord <= 4) return flux_al_low(qa, qb, alm, al0, alp, c, iord);
   auto cell = [&](double q0, double l, double r) {
     CellU cu; cu.bl = l - q0; cu.br = r - q0; cu.b0 = cu.bl + cu.br;
     if (iord == 5) cu.smt = cu.bl * cu.br < 0.;
@@ -518,7 +595,14 @@ __device__ __forceinline__ double flux_unlim_aux(double qa, double qb, double al
   return fl;
 }
 
-__host__ inline bool hord_supported(int h) { return h == 5 || h == 6 || h == -5 || h == 8 || h == 10; }
+// every member of tp_valid_schemes (tp_core.F90:78) except 7 (its flux needs the limited (bl, br) of BOTH cells of a face,
+// :683-695); hord = 1 reads lim_fac (:404), only the default lim_fac = 1 is built
+__host__ inline bool hord_supported(int h, double lim_fac = 1.0) {
+  if (h == 1) return lim_fac == 1.0;
+  return h == -5 || (h >= 2 && h <= 6) || (h >= 8 && h <= 13);
+}
+// schemes outside the common five run in the general (FAM = 2) instantiations of the tile kernels
+__host__ inline bool hord_is_rare(int h) { return !(h == 5 || h == 6 || h == -5 || h == 8 || h == 10); }
 __host__ inline bool hord_wind_supported(int h) { return h == 5 || h == 6 || h == 8 || h == 10; }
 
 }  // namespace ppm

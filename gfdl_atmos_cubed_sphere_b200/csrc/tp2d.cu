@@ -27,7 +27,7 @@ static inline dim3 plane_grid(const Lay& L, int nk) { return dim3((L.NI + TI - 1
 
 // One CTA per TX x TY tile and level: see tp_tile.cuh.  Epilogue: weight by the area flux (or the
 // mass flux, tp_core.F90:213-226) and store the tile's own faces (+ the face's last column / row).
-template <bool MONO, bool EDGE>
+template <int FAM, bool EDGE>
 __global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ q,
                                                        const double* __restrict__ crx, const double* __restrict__ cry,
                                                        const double* __restrict__ xfx, const double* __restrict__ yfx,
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, tpt::
   const Tile T = make_tile(L, M);
   stage_inputs<EDGE>(L, G, S, T, crx, cry, xfx, yfx);
   stage_q<EDGE>(L, S, T, q);
-  tp_compute<MONO ? 1 : 0, EDGE>(L, G, S, T, ra_x, ra_y, ord_in, ord_ou);
+  tp_compute<FAM, EDGE>(L, G, S, T, ra_x, ra_y, ord_in, ord_ou);
   // epilogue: lane = column; the tile stores its own west/south faces, plus the face's last column / row
   const bool lastx = T.i0 + TX > L.ie, lasty = T.j0 + TY > L.je;
   const int c = T.lane - 3, i = T.i0 + c;
@@ -80,26 +80,29 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, tpt::
 }
 
 int launch_tp2d(fv3_ctx* c, const Tp2d& a) {
-  if (!hord_supported(a.hord)) return fv3_fail(c, -2, "fv_tp_2d: hord " + std::to_string(a.hord) + " not supported on the GPU path (supported: 5, 6, -5, 8, 10)");
+  if (!hord_supported(a.hord, c->f.lim_fac)) return fv3_fail(c, -2, "fv_tp_2d: hord " + std::to_string(a.hord) + " not supported on the GPU path (supported: -5, 1..6, 8..13; 1 only with lim_fac = 1)");
   const Lay& L = c->L;
   const int ord_in = (a.hord == 10) ? 8 : a.hord;   // tp_core.F90:136-141
   tpt::TileMap Min, Mfr; int n_in, n_fr;
   tpt::tile_maps(L, Min, Mfr, n_in, n_fr);
   static bool attr_set = false;
   if (!attr_set) {
-    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
-    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
-    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
-    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c, cudaFuncSetAttribute(k_tp_fused<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
     attr_set = true;
   }
   const tpt::ZnEpi Z{a.zn, a.zn_dfx, a.zn_dfy, a.zn ? c->d_kdbl : nullptr, a.zn_slot};
   if (a.zn && (a.ra_x || a.ra_y || a.mfx)) return fv3_fail(c, -1, "fv_tp_2d: the fused height update takes no ra_x / ra_y / mfx");
-#define TP_LAUNCH(MONO, EDGE, M, N)                                                                                          \
-  k_tp_fused<MONO, EDGE><<<dim3(N, 1, a.nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(L, c->G, M, a.q, a.crx, a.cry, a.xfx, a.yfx, \
-                                                                                       a.ra_x, a.ra_y, a.mfx, a.mfy, a.fx, a.fy, ord_in, a.hord, Z)
-  if (a.hord >= 8) { if (n_in) TP_LAUNCH(true, false, Min, n_in); if (n_fr) TP_LAUNCH(true, true, Mfr, n_fr); }
-  else { if (n_in) TP_LAUNCH(false, false, Min, n_in); if (n_fr) TP_LAUNCH(false, true, Mfr, n_fr); }
+#define TP_LAUNCH(FAM, EDGE, M, N)                                                                                           \
+  k_tp_fused<FAM, EDGE><<<dim3(N, 1, a.nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(L, c->G, M, a.q, a.crx, a.cry, a.xfx, a.yfx, \
+                                                                                      a.ra_x, a.ra_y, a.mfx, a.mfy, a.fx, a.fy, ord_in, a.hord, Z)
+  if (hord_is_rare(a.hord)) { if (n_in) TP_LAUNCH(2, false, Min, n_in); if (n_fr) TP_LAUNCH(2, true, Mfr, n_fr); }   // general instantiation
+  else if (a.hord >= 8) { if (n_in) TP_LAUNCH(1, false, Min, n_in); if (n_fr) TP_LAUNCH(1, true, Mfr, n_fr); }
+  else { if (n_in) TP_LAUNCH(0, false, Min, n_in); if (n_fr) TP_LAUNCH(0, true, Mfr, n_fr); }
 #undef TP_LAUNCH
   c->launches += (n_in ? 1 : 0) + (n_fr ? 1 : 0);
   return 0;

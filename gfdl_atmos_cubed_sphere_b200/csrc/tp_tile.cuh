@@ -84,22 +84,24 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // cube-edge faces (the one-sided formulas of tp_core.F90:643-681): rare, kept out of line so the interior
 // path stays small (instruction cache) and its register allocation is not driven by this code
+template <bool RARE>
 static __device__ __noinline__ double edge_flux(const double* ql, int sq, int org, const double* dl, long long dbase,
                                                 long long dstride, int i, double c, int iord, int n) {
   SAcc qa{ql, sq, org};
   ppm::Acc da{dl, dbase, dstride};
-  return ppm::flux_scalar(qa, da, i, c, iord, n, true);
+  return ppm::flux_scalar<RARE>(qa, da, i, c, iord, n, true);
 }
 
 // interior flux through the low-side face of line element m (between elements m-1 and m); q, a = element m of the line
+template <bool RARE>
 __device__ __forceinline__ double line_flux(bool mono, const double* q, int sq, const double* a, int sa, double c, int iord) {
   if (mono) {
     const int u = (c > 0.) ? -1 : 0;
     const double* p = q + u * sq;
     const double* d = a + u * sa;
-    return ppm::flux_mono_aux(p[-2 * sq], p[-sq], p[0], p[sq], p[2 * sq], d[-sa], d[0], d[sa], c, iord);
+    return ppm::flux_mono_aux<RARE>(p[-2 * sq], p[-sq], p[0], p[sq], p[2 * sq], d[-sa], d[0], d[sa], c, iord);
   }
-  return ppm::flux_unlim_aux(q[-sq], q[0], a[-sa], a[0], a[sa], c, iord);
+  return ppm::flux_unlim_aux<RARE>(q[-sq], q[0], a[-sa], a[0], a[sa], c, iord);
 }
 
 // TPT_NOAUX form: no limiter-input arrays.  The 5 (monotone) / 6 (unlimited) values of q the flux reads anyway contain every
@@ -107,15 +109,16 @@ __device__ __forceinline__ double line_flux(bool mono, const double* q, int sq, 
 // 3 shared-memory loads per flux, the two aux passes (6 loads + 2 stores per point) and 2 of the 5 barriers per field go away
 // (ncu, profiles/r1_dsw_ncu_summary.md: the shared-memory data pipe is at 60 % of peak next to 58 % issue-active).
 // Same operations on the same operands as the aux form => bit-identical results.
+template <bool RARE>
 __device__ __forceinline__ double line_flux_na(bool mono, const double* q, int sq, double c, int iord) {
   if (mono) {
     const int u = (c > 0.) ? -1 : 0;
     const double* p = q + u * sq;
     const double a = p[-2 * sq], b = p[-sq], m = p[0], d = p[sq], e = p[2 * sq];
-    return ppm::flux_mono_aux(a, b, m, d, e, ppm::dm2(a, b, m), ppm::dm2(b, m, d), ppm::dm2(m, d, e), c, iord);
+    return ppm::flux_mono_aux<RARE>(a, b, m, d, e, ppm::dm2(a, b, m), ppm::dm2(b, m, d), ppm::dm2(m, d, e), c, iord);
   }
   const double a0 = q[-3 * sq], a1 = q[-2 * sq], a2 = q[-sq], a3 = q[0], a4 = q[sq], a5 = q[2 * sq];
-  return ppm::flux_unlim_aux(a2, a3, ppm::aux_point(false, iord, a0, a1, a2, a3), ppm::aux_point(false, iord, a1, a2, a3, a4),
+  return ppm::flux_unlim_aux<RARE>(a2, a3, ppm::aux_point(false, iord, a0, a1, a2, a3), ppm::aux_point(false, iord, a1, a2, a3, a4),
                              ppm::aux_point(false, iord, a2, a3, a4, a5), c, iord);
 }
 
@@ -198,6 +201,7 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
                                            int ord_in, int ord_ou) {
   using namespace ppm;
   const bool mono = (FAM == 2) ? (ord_ou >= 8) : (FAM == 1);
+  constexpr bool RARE = (FAM == 2);   // only the general instantiation carries the schemes beyond 5, 6, -5, 8, 10
   const bool cube = EDGE && L.cube;
   const int npx = L.npx, npy = L.npy, i0 = T.i0, j0 = T.j0, c = T.lane, wid = T.wid;
   const int i = i0 - 3 + c;                                     // this lane's column (cell / west-face index)
@@ -227,10 +231,10 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
     S.ay[r][c] = aux_point(mono, ord_in, qy[r2][c], qy[r1][c], qy[r][c], qy[r3][c]);
   }
   __syncthreads();
-#define TPT_LF(qp, sq, ap, sa, cr, ord) line_flux(mono, qp, sq, ap, sa, cr, ord)
+#define TPT_LF(qp, sq, ap, sa, cr, ord) line_flux<RARE>(mono, qp, sq, ap, sa, cr, ord)
 #else
   (void)cm2; (void)cm1; (void)cp1;
-#define TPT_LF(qp, sq, ap, sa, cr, ord) line_flux_na(mono, qp, sq, cr, ord)
+#define TPT_LF(qp, sq, ap, sa, cr, ord) line_flux_na<RARE>(mono, qp, sq, cr, ord)
 #endif
   // ---- B: inner sweeps; task t < QH: fx2 row t (tp_core.F90:164-169), else fy2 row t-QH+3 (:143-148)
 #pragma unroll
@@ -243,14 +247,14 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
       if (!EDGE || (j <= L.je + 1 && i <= L.ied)) {
         const double cr = S.cry[r][c];
         S.fy2[r][c] = (!cube || (j >= 4 && j <= npy - 3)) ? TPT_LF(&qy[r][c], QW, &S.ay[r][c], QW, cr, ord_in)
-                                                          : edge_flux(&qy[0][c], QW, j0 - 3, G.dya, LIDX(L, i, 0), L.NI, j, cr, ord_in, npy);
+                                                          : edge_flux<RARE>(&qy[0][c], QW, j0 - 3, G.dya, LIDX(L, i, 0), L.NI, j, cr, ord_in, npy);
       }
     }
   }
   if (EDGE && nec > 0) {   // cube-edge x faces of all rows, densely packed over the CTA
     for (int e = threadIdx.x; e < QH * nec; e += NT) {
       const int r = e / nec, ci = e - r * nec, cc = ci < nwc ? 3 + ci : ce0 + (ci - nwc), j = j0 - 3 + r;
-      if (j <= L.jed) S.fx2[r][cc] = edge_flux(&S.q[r][0], 1, i0 - 3, G.dxa, LIDX(L, 0, j), 1, i0 - 3 + cc, S.crx[r][cc], ord_in, npx);
+      if (j <= L.jed) S.fx2[r][cc] = edge_flux<RARE>(&S.q[r][0], 1, i0 - 3, G.dxa, LIDX(L, 0, j), 1, i0 - 3 + cc, S.crx[r][cc], ord_in, npx);
     }
   }
   __syncthreads();
@@ -305,7 +309,7 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
       if (xcell && (!EDGE || j <= L.je + 1)) {
         const double cr = S.cry[r][c];
         const double f = (!cube || (j >= 4 && j <= npy - 3)) ? TPT_LF(&S.qj[r][c], QW, &S.ay[r][c], QW, cr, ord_ou)
-                                                             : edge_flux(&S.qj[0][c], QW, j0 - 3, G.dya, LIDX(L, i, 0), L.NI, j, cr, ord_ou, npy);
+                                                             : edge_flux<RARE>(&S.qj[0][c], QW, j0 - 3, G.dya, LIDX(L, i, 0), L.NI, j, cr, ord_ou, npy);
         S.fy2[r][c] = 0.5 * (f + S.fy2[r][c]);
       }
     }
@@ -314,7 +318,7 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
     for (int e = threadIdx.x; e < TY * nec; e += NT) {
       const int r = 3 + e / nec, ci = e - (r - 3) * nec, cc = ci < nwc ? 3 + ci : ce0 + (ci - nwc), j = j0 - 3 + r;
       if (j <= L.je)
-        S.fx2[r][cc] = 0.5 * (edge_flux(&S.qi[r][0], 1, i0 - 3, G.dxa, LIDX(L, 0, j), 1, i0 - 3 + cc, S.crx[r][cc], ord_ou, npx) + S.fx2[r][cc]);
+        S.fx2[r][cc] = 0.5 * (edge_flux<RARE>(&S.qi[r][0], 1, i0 - 3, G.dxa, LIDX(L, 0, j), 1, i0 - 3 + cc, S.crx[r][cc], ord_ou, npx) + S.fx2[r][cc]);
     }
   }
   __syncthreads();

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(TI* TJ) k_tr_scale(Lay L, double* __restrict__
 }
 
 // one sub-cycle `it` (1-based) of all levels: fv_tp_2d with mass-flux weighting + the tracer update (:206-275)
-template <bool MONO, bool EDGE>
+template <int FAM, bool EDGE>
 __global__ void __launch_bounds__(tpt::NT, 2) k_tr_step(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ q, double* __restrict__ qo,
                                                       double* __restrict__ dp1, const double* __restrict__ cx, const double* __restrict__ cy,
                                                       const double* __restrict__ xfx, const double* __restrict__ yfx,
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tr_step(Lay L, DevGrid G, tpt::T
   }
   stage_inputs<EDGE>(L, G, S, T, cx, cy, xfx, yfx);
   stage_q<EDGE>(L, S, T, q);
-  tp_compute<MONO ? 1 : 0, EDGE>(L, G, S, T, nullptr, nullptr, ord_in, ord_ou);
+  tp_compute<FAM, EDGE>(L, G, S, T, nullptr, nullptr, ord_in, ord_ou);
 #pragma unroll
   for (int r = T.wid; r < TY; r += NW) {
     const int j = T.j0 + r;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tr_step(Lay L, DevGrid G, tpt::T
 extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_out) {
   if (!ctxs || nctx < 1) return -1;
   fv3_ctx* c0 = ctxs[0];
-  if (!hord_supported(hord)) return fv3_fail(c0, -2, "tracer_2d: hord " + std::to_string(hord) + " not supported (supported: 5, 6, -5, 8, 10)");
+  if (!hord_supported(hord, c0->f.lim_fac)) return fv3_fail(c0, -2, "tracer_2d: hord " + std::to_string(hord) + " not supported (supported: -5, 1..6, 8..13; 1 only with lim_fac = 1)");
   const int npz = c0->L.npz;
   const bool linked = c0->halo != nullptr;
   std::vector<double> cmax(npz, 0.), tmp(npz);
@@ -179,10 +179,12 @@ extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_ou
   }
   static bool attr_set = false;
   if (!attr_set) {
-    FV3_CUDA(c0, cudaFuncSetAttribute(k_tr_step<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
-    FV3_CUDA(c0, cudaFuncSetAttribute(k_tr_step<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
-    FV3_CUDA(c0, cudaFuncSetAttribute(k_tr_step<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
-    FV3_CUDA(c0, cudaFuncSetAttribute(k_tr_step<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c0, cudaFuncSetAttribute(k_tr_step<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c0, cudaFuncSetAttribute(k_tr_step<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c0, cudaFuncSetAttribute(k_tr_step<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c0, cudaFuncSetAttribute(k_tr_step<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c0, cudaFuncSetAttribute(k_tr_step<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
+    FV3_CUDA(c0, cudaFuncSetAttribute(k_tr_step<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tpt::Smem)));
     attr_set = true;
   }
   // ---- sub-cycles
@@ -195,12 +197,13 @@ extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_ou
       int* d_ns = (int*)((double*)d_cmax[a] + 2 * npz);
       tpt::TileMap Min, Mfr; int n_in, n_fr;
       tpt::tile_maps(L, Min, Mfr, n_in, n_fr);
-#define TR_LAUNCH(MONO, EDGE, MAP, N)                                                                                             \
-  k_tr_step<MONO, EDGE><<<dim3(N, 1, npz), tpt::NT, sizeof(tpt::Smem), c->stream>>>(                                               \
+#define TR_LAUNCH(FAM, EDGE, MAP, N)                                                                                              \
+  k_tr_step<FAM, EDGE><<<dim3(N, 1, npz), tpt::NT, sizeof(tpt::Smem), c->stream>>>(                                               \
       L, c->G, MAP, c->fld[FV3_WORK_Q], alt[a], c->fld[FV3_DP1], c->fld[FV3_CX], c->fld[FV3_CY], c->fld[FV3_XFX], c->fld[FV3_YFX], \
       c->fld[FV3_MFX], c->fld[FV3_MFY], d_ns, it, ord_in, hord)
-      if (hord >= 8) { if (n_in) TR_LAUNCH(true, false, Min, n_in); if (n_fr) TR_LAUNCH(true, true, Mfr, n_fr); }
-      else { if (n_in) TR_LAUNCH(false, false, Min, n_in); if (n_fr) TR_LAUNCH(false, true, Mfr, n_fr); }
+      if (hord_is_rare(hord)) { if (n_in) TR_LAUNCH(2, false, Min, n_in); if (n_fr) TR_LAUNCH(2, true, Mfr, n_fr); }
+      else if (hord >= 8) { if (n_in) TR_LAUNCH(1, false, Min, n_in); if (n_fr) TR_LAUNCH(1, true, Mfr, n_fr); }
+      else { if (n_in) TR_LAUNCH(0, false, Min, n_in); if (n_fr) TR_LAUNCH(0, true, Mfr, n_fr); }
 #undef TR_LAUNCH
       c->launches += (n_in ? 1 : 0) + (n_fr ? 1 : 0);
       std::swap(c->fld[FV3_WORK_Q], alt[a]);   // the halo exchange of the next sub-cycle reads fld[WORK_Q]

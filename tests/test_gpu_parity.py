@@ -51,20 +51,20 @@ def test_d_sw_multi_tile_monotone():
     _assert(H.parity_c_sw_d_sw(n=56, npz=2, flagset="A", dt=10.0, tile=4), TOL_STAGE)
 
 
-@pytest.mark.parametrize("hord", [5, 6, -5, 8, 10])
-@pytest.mark.parametrize("use_mfx", [0, 1])
-def test_fv_tp_2d(hord, use_mfx):
-    """Stand-alone fv_tp_2d (tp_core.F90:85) incl. the mass-flux weighted form and deln_flux."""
-    case = H.Case(20, 5, "A")
+ALL_HORD = [5, 6, -5, 8, 10, 1, 2, 3, 4, 9, 11, 12, 13]   # tp_valid_schemes (tp_core.F90:78) without 7
+
+
+def _fv_tp_2d_parity(n, npz, hord, use_mfx):
+    case = H.Case(n, npz, "A")
     eo = case.engine(H.load_oracle(), 1)
     eg = case.engine(abi.load_library(), 1)
     rng = np.random.default_rng(20241117)
     st = case.states[0]
     b = case.bounds
     q = st["pt"].copy()
-    if hord == -5:
-        q = np.abs(q - 300.0)          # positive definite field with zeros
-    shapes = {n: eo.shape(n) for n in ("CRX", "CRY", "XFX", "YFX", "WORK_RAX", "WORK_RAY", "MFX", "MFY")}
+    if hord in (-5, 9, 12, 13):
+        q = np.abs(q - 300.0)          # positive definite field with zeros: the positivity constraints act
+    shapes = {nm: eo.shape(nm) for nm in ("CRX", "CRY", "XFX", "YFX", "WORK_RAX", "WORK_RAY", "MFX", "MFY")}
     crx = rng.uniform(-0.6, 0.6, shapes["CRX"]); cry = rng.uniform(-0.6, 0.6, shapes["CRY"])
     area = case.tiles[0].arr["area"]
     xfx = crx * 0.5 * np.abs(area[:, 3:-2][None, :, :shapes["XFX"][2]]); yfx = cry * 0.5 * np.abs(area[3:-2, :][None, :shapes["YFX"][1], :])
@@ -74,13 +74,28 @@ def test_fv_tp_2d(hord, use_mfx):
     for e in (eo, eg):
         e.put("WORK_Q", q); e.put("CRX", crx); e.put("CRY", cry); e.put("XFX", xfx); e.put("YFX", yfx)
         e.put("WORK_RAX", rax); e.put("WORK_RAY", ray); e.put("MFX", mfx); e.put("MFY", mfy); e.put("DELP", st["delp"])
-        e.call("fv_tp_2d", 5, hord, use_mfx, use_mfx, 2 if use_mfx else 1, 0.05)
+        e.call("fv_tp_2d", npz, hord, use_mfx, use_mfx, 2 if use_mfx else 1, 0.05)
     res = H.compare(eo, eg, {"WORK_FX": (b["is_"], b["ie"] + 1, b["js"], b["je"]), "WORK_FY": (b["is_"], b["ie"], b["js"], b["je"] + 1)})
+    eo.close(); eg.close()
     _assert(res, TOL_STAGE)
 
 
+@pytest.mark.parametrize("hord", ALL_HORD)
+@pytest.mark.parametrize("use_mfx", [0, 1])
+def test_fv_tp_2d(hord, use_mfx):
+    """Stand-alone fv_tp_2d (tp_core.F90:85) incl. the mass-flux weighted form and deln_flux, every supported scheme; a 20 x 20
+    face is one (corner) tile of the transport kernel: the general cube-edge path."""
+    _fv_tp_2d_parity(20, 5, hord, use_mfx)
+
+
+@pytest.mark.parametrize("hord", ALL_HORD)
+def test_fv_tp_2d_multi_tile(hord):
+    """A 56 x 56 face = 3 x 3 transport tiles: interior tile (edge code compiled out), edge and corner tiles, partial last tiles."""
+    _fv_tp_2d_parity(56, 2, hord, 1)
+
+
 def test_unsupported_hord_is_an_error():
-    case = H.Case(16, 3, "A", flags_override=dict(hord_dp=13))
+    case = H.Case(16, 3, "A", flags_override=dict(hord_dp=7))   # 7: the one member of tp_valid_schemes that is not built
     eg = case.engine(abi.load_library(), 1)
     case.load_state(eg, 1)
     eg.call("c_sw", 5.0)
