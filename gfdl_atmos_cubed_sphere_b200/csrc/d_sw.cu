@@ -810,7 +810,7 @@ int stage_d_sw(fv3_ctx* c, double dt) {
   const fv3_flags_t& f = c->f;
   const int nk = L.npz;
   if (!hord_supported(f.hord_dp, f.lim_fac) || !hord_supported(f.hord_tm, f.lim_fac) || !hord_supported(f.hord_vt, f.lim_fac) || !hord_wind_supported(f.hord_mt))
-    return fv3_fail(c, -2, "d_sw: unsupported hord (supported: -5, 1..6, 8..13 [1 only with lim_fac = 1]; hord_mt: 5, 6, 8, 10)");
+    return fv3_fail(c, -2, "d_sw: unsupported hord (supported: -5, 1..13 [1 only with lim_fac = 1]; hord_mt: 5, 6, 8, 10)");
   if (f.inline_q) return fv3_fail(c, -2, "d_sw: inline_q not supported");
   if (f.do_f3d) return fv3_fail(c, -2, "d_sw: do_f3d not supported");
   if (f.nord > 3) return fv3_fail(c, -2, "d_sw: nord > 3 not supported");

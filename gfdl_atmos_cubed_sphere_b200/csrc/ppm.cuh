@@ -159,6 +159,18 @@ static __device__ __noinline__ double flux_al_low(double qa, double qb, double a
   return fl;
 }
 
+// iord == 7 (tp_core.F90:683-695): the flux tests smt5 = bl*br < 0 of BOTH cells of the face, so it needs the (positive-definite
+// limited, :605-627) bl, br of cell A (low side, value qa) and of cell B (qb)
+__device__ __forceinline__ double flux_pd7_from_cells(double qa, double qb, double Abl, double Abr, double Bbl, double Bbr, double c) {
+  const double Ab0 = Abl + Abr, Bb0 = Bbl + Bbr;
+  const bool As = Abl * Abr < 0., Bs = Bbl * Bbr < 0.;
+  double fx1, fl;
+  if (c > 0.) { fx1 = (1. - c) * (Abr - c * Ab0); fl = qa; }
+  else { fx1 = (1. + c) * (Bbl + c * Bb0); fl = qb; }
+  if (As || Bs) fl = fl + fx1;
+  return fl;
+}
+
 // dxa-weighted two-sided edge value (tp_core.F90:376-377 / :647-648); e = first cell inside
 // the face on the high side of the edge (e = 1 for the west/south edge, e = n for east/north)
 template <class Q, class D>
@@ -270,6 +282,12 @@ __device__ __forceinline__ CellU cell_unlim(const Q& q, const D& dxa, int i, int
 // flux through interface i for Courant number c.  tp_core.F90:549-558, :701-707
 template <bool RARE = true, class Q, class D>
 __device__ __forceinline__ double flux_scalar(const Q& q, const D& dxa, int i, double c, int iord, int n, bool cube) {
+  if (RARE && iord == 7) {   // the limiter of 7 is the one of 12 (:605); cube-edge cells get the same one-sided overrides
+    double Abl, Abr, Bbl, Bbr;
+    cell_mono<true>(q, dxa, i - 1, 12, n, cube, Abl, Abr);
+    cell_mono<true>(q, dxa, i, 12, n, cube, Bbl, Bbr);
+    return flux_pd7_from_cells(q(i - 1), q(i), Abl, Abr, Bbl, Bbr, c);
+  }
   if (iord >= 8) {
     const int iu = (c > 0.) ? i - 1 : i;
     double bl, br;
@@ -542,6 +560,15 @@ __device__ __forceinline__ double aux_point(bool mono, int iord, double qm2, dou
   const double al = p1 * (qm1 + q0) + p2 * (qm2 + qp1);
   return iord < 0 ? mx(0., al) : al;
 }
+// iord == 7 on an interior line: a0..a5 = q(i-3..i+2) around the face between cells a2 and a3 (out of line: general instantiation only)
+static __device__ __noinline__ double flux_pd7_line(double a0, double a1, double a2, double a3, double a4, double a5, double c) {
+  const double d1 = dm2(a0, a1, a2), d2 = dm2(a1, a2, a3), d3 = dm2(a2, a3, a4), d4 = dm2(a3, a4, a5);
+  const double alA = 0.5 * (a1 + a2) + r3 * (d1 - d2), alS = 0.5 * (a2 + a3) + r3 * (d2 - d3), alB = 0.5 * (a3 + a4) + r3 * (d3 - d4);
+  double Abl, Abr, Bbl, Bbr;
+  mono_blbr_other(a2, alA, alS, d2, 12, Abl, Abr);
+  mono_blbr_other(a3, alS, alB, d3, 12, Bbl, Bbr);
+  return flux_pd7_from_cells(a2, a3, Abl, Abr, Bbl, Bbr, c);
+}
 // monotone flux from the upwind cell's neighbourhood: q(iu-2..iu+2), dm(iu-1..iu+1)
 template <bool RARE = true>
 __device__ __forceinline__ double flux_mono_aux(double qm2, double qm1, double q0, double qp1, double qp2, double dmm, double dm0,
@@ -595,11 +622,10 @@ __device__ __forceinline__ double flux_unlim_aux(double qa, double qb, double al
   return fl;
 }
 
-// every member of tp_valid_schemes (tp_core.F90:78) except 7 (its flux needs the limited (bl, br) of BOTH cells of a face,
-// :683-695); hord = 1 reads lim_fac (:404), only the default lim_fac = 1 is built
+// every member of tp_valid_schemes (tp_core.F90:78); hord = 1 reads lim_fac (:404), only the default lim_fac = 1 is built
 __host__ inline bool hord_supported(int h, double lim_fac = 1.0) {
   if (h == 1) return lim_fac == 1.0;
-  return h == -5 || (h >= 2 && h <= 6) || (h >= 8 && h <= 13);
+  return h == -5 || (h >= 2 && h <= 13);
 }
 // schemes outside the common five run in the general (FAM = 2) instantiations of the tile kernels
 __host__ inline bool hord_is_rare(int h) { return !(h == 5 || h == 6 || h == -5 || h == 8 || h == 10); }

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, tpt::
 }
 
 int launch_tp2d(fv3_ctx* c, const Tp2d& a) {
-  if (!hord_supported(a.hord, c->f.lim_fac)) return fv3_fail(c, -2, "fv_tp_2d: hord " + std::to_string(a.hord) + " not supported on the GPU path (supported: -5, 1..6, 8..13; 1 only with lim_fac = 1)");
+  if (!hord_supported(a.hord, c->f.lim_fac)) return fv3_fail(c, -2, "fv_tp_2d: hord " + std::to_string(a.hord) + " not supported on the GPU path (supported: -5, 1..13; 1 only with lim_fac = 1)");
   const Lay& L = c->L;
   const int ord_in = (a.hord == 10) ? 8 : a.hord;   // tp_core.F90:136-141
   tpt::TileMap Min, Mfr; int n_in, n_fr;

@@ -95,6 +95,7 @@ static __device__ __noinline__ double edge_flux(const double* ql, int sq, int or
 // interior flux through the low-side face of line element m (between elements m-1 and m); q, a = element m of the line
 template <bool RARE>
 __device__ __forceinline__ double line_flux(bool mono, const double* q, int sq, const double* a, int sa, double c, int iord) {
+  if (RARE && mono && iord == 7) return ppm::flux_pd7_line(q[-3 * sq], q[-2 * sq], q[-sq], q[0], q[sq], q[2 * sq], c);
   if (mono) {
     const int u = (c > 0.) ? -1 : 0;
     const double* p = q + u * sq;
@@ -111,6 +112,7 @@ __device__ __forceinline__ double line_flux(bool mono, const double* q, int sq, 
 // Same operations on the same operands as the aux form => bit-identical results.
 template <bool RARE>
 __device__ __forceinline__ double line_flux_na(bool mono, const double* q, int sq, double c, int iord) {
+  if (RARE && mono && iord == 7) return ppm::flux_pd7_line(q[-3 * sq], q[-2 * sq], q[-sq], q[0], q[sq], q[2 * sq], c);
   if (mono) {
     const int u = (c > 0.) ? -1 : 0;
     const double* p = q + u * sq;
@@ -200,7 +202,7 @@ __device__ __forceinline__ void tp_compute(const Lay& L, const DevGrid& G, Smem&
                                            const double* __restrict__ ra_x, const double* __restrict__ ra_y,
                                            int ord_in, int ord_ou) {
   using namespace ppm;
-  const bool mono = (FAM == 2) ? (ord_ou >= 8) : (FAM == 1);
+  const bool mono = (FAM == 2) ? (ord_ou >= 7) : (FAM == 1);   // dm family: iord >= 7 (tp_core.F90:364, 563)
   constexpr bool RARE = (FAM == 2);   // only the general instantiation carries the schemes beyond 5, 6, -5, 8, 10
   const bool cube = EDGE && L.cube;
   const int npx = L.npx, npy = L.npy, i0 = T.i0, j0 = T.j0, c = T.lane, wid = T.wid;

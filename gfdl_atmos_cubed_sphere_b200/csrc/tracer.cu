@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tr_step(Lay L, DevGrid G, tpt::T
 extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_out) {
   if (!ctxs || nctx < 1) return -1;
   fv3_ctx* c0 = ctxs[0];
-  if (!hord_supported(hord, c0->f.lim_fac)) return fv3_fail(c0, -2, "tracer_2d: hord " + std::to_string(hord) + " not supported (supported: -5, 1..6, 8..13; 1 only with lim_fac = 1)");
+  if (!hord_supported(hord, c0->f.lim_fac)) return fv3_fail(c0, -2, "tracer_2d: hord " + std::to_string(hord) + " not supported (supported: -5, 1..13; 1 only with lim_fac = 1)");
   const int npz = c0->L.npz;
   const bool linked = c0->halo != nullptr;
   std::vector<double> cmax(npz, 0.), tmp(npz);

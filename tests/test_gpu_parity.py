@@ -51,7 +51,7 @@ def test_d_sw_multi_tile_monotone():
     _assert(H.parity_c_sw_d_sw(n=56, npz=2, flagset="A", dt=10.0, tile=4), TOL_STAGE)
 
 
-ALL_HORD = [5, 6, -5, 8, 10, 1, 2, 3, 4, 9, 11, 12, 13]   # tp_valid_schemes (tp_core.F90:78) without 7
+ALL_HORD = [5, 6, -5, 8, 10, 1, 2, 3, 4, 7, 9, 11, 12, 13]   # tp_valid_schemes (tp_core.F90:78)
 
 
 def _fv_tp_2d_parity(n, npz, hord, use_mfx):
@@ -62,7 +62,7 @@ def _fv_tp_2d_parity(n, npz, hord, use_mfx):
     st = case.states[0]
     b = case.bounds
     q = st["pt"].copy()
-    if hord in (-5, 9, 12, 13):
+    if hord in (-5, 7, 9, 12, 13):
         q = np.abs(q - 300.0)          # positive definite field with zeros: the positivity constraints act
     shapes = {nm: eo.shape(nm) for nm in ("CRX", "CRY", "XFX", "YFX", "WORK_RAX", "WORK_RAY", "MFX", "MFY")}
     crx = rng.uniform(-0.6, 0.6, shapes["CRX"]); cry = rng.uniform(-0.6, 0.6, shapes["CRY"])
@@ -95,7 +95,7 @@ def test_fv_tp_2d_multi_tile(hord):
 
 
 def test_unsupported_hord_is_an_error():
-    case = H.Case(16, 3, "A", flags_override=dict(hord_dp=7))   # 7: the one member of tp_valid_schemes that is not built
+    case = H.Case(16, 3, "A", flags_override=dict(hord_dp=14))   # not a member of tp_valid_schemes (tp_core.F90:78)
     eg = case.engine(abi.load_library(), 1)
     case.load_state(eg, 1)
     eg.call("c_sw", 5.0)
