@@ -37,3 +37,21 @@ def test_ppm_matches_reference_notebook(built, ydir):
         worst = max(worst, err)
         assert err < 5e-15, (k, err)
     print("worst", worst)
+
+
+def test_oracle_matches_its_round1_signatures(built):
+    """Regression fixture of the oracle itself (tests/golden/make_oracle_selfcheck.py): 2 substeps of the 6-face C12L4 cube,
+    flag-sets A and B, hydrostatic and not; sums and 16 sampled values of every prognostic field on two faces."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(os.path.dirname(GOLD), "make_oracle_selfcheck.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    z = np.load(os.path.join(os.path.dirname(GOLD), "oracle_selfcheck.npz"))
+    got = {}
+    for flagset in ("A", "B"):
+        for hydro in (0, 1):
+            got.update(mk.run(flagset, hydro))
+    assert set(got) == set(z.files)
+    for k in z.files:
+        ref = z[k]
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert np.abs(got[k] - ref).max() <= 1e-12 * scale, k
