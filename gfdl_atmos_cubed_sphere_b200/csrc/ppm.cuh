@@ -13,17 +13,28 @@
 // Supported schemes: 5, 6, -5 (unlimited family) and 8, 10 (monotone family); the host
 // rejects the others (no silent fallback).
 #pragma once
+#include <cstring>
 #include "fv3_ctx.hpp"
 
+// The pure-arithmetic routines below are also compiled for the host (PPM_HD) so that tests/host_ppm_test.cu can check the very
+// expressions the kernels run against the oracle on a machine without a GPU (tests/test_host_device_math.py).
+#define PPM_HD __host__ __device__
 namespace ppm {
+PPM_HD __forceinline__ int hi_word(double x) {
+#ifdef __CUDA_ARCH__
+  return __double2hiint(x);
+#else
+  long long b; memcpy(&b, &x, sizeof b); return (int)(b >> 32);
+#endif
+}
 
-__device__ __forceinline__ double fsign(double a, double b) { return copysign(fabs(a), b); }
+PPM_HD __forceinline__ double fsign(double a, double b) { return copysign(fabs(a), b); }
 // compare-and-select min/max: 3 instructions (DSETP + 2 SEL) where fmin/fmax cost 6-7 on sm_100a because of their
 // NaN-quieting fix-up (seen in the SASS); the path never sees NaNs and +-0 order is irrelevant to the limiters
-__device__ __forceinline__ double mn(double a, double b) { return a < b ? a : b; }
-__device__ __forceinline__ double mx(double a, double b) { return a > b ? a : b; }
-__device__ __forceinline__ double min3(double a, double b, double c) { return mn(mn(a, b), c); }
-__device__ __forceinline__ double max3(double a, double b, double c) { return mx(mx(a, b), c); }
+PPM_HD __forceinline__ double mn(double a, double b) { return a < b ? a : b; }
+PPM_HD __forceinline__ double mx(double a, double b) { return a > b ? a : b; }
+PPM_HD __forceinline__ double min3(double a, double b, double c) { return mn(mn(a, b), c); }
+PPM_HD __forceinline__ double max3(double a, double b, double c) { return mx(mx(a, b), c); }
 
 // tp_core.F90:35-70
 constexpr double r3 = 1. / 3.;
@@ -82,7 +93,7 @@ __device__ __forceinline__ double dm_at(const Q& q, int i) {  // tp_core.F90:570
   return fsign(mn(mn(fabs(xt), max3(qm, q0, qp) - q0), q0 - min3(qm, q0, qp)), xt);
 }
 
-__device__ __forceinline__ void pert_std(double& al, double& ar) {  // pert_ppm iv/=0, tp_core.F90:1245-1261
+PPM_HD __forceinline__ void pert_std(double& al, double& ar) {  // pert_ppm iv/=0, tp_core.F90:1245-1261
   if (al * ar < 0.) {
     const double da1 = al - ar, da2 = da1 * da1, a6da = 3. * (al + ar) * da1;
     if (a6da < -da2) ar = -2. * al;
@@ -91,7 +102,7 @@ __device__ __forceinline__ void pert_std(double& al, double& ar) {  // pert_ppm 
 }
 
 // pert_ppm with iv == 0 for one cell (positive-definite constraint of iord 9 / 13, tp_core.F90:1222-1244)
-__device__ __forceinline__ void pert_pd(double a0, double& al, double& ar) {
+PPM_HD __forceinline__ void pert_pd(double a0, double& al, double& ar) {
   if (a0 <= 0.) { al = 0.; ar = 0.; return; }
   const double a4 = -3. * (ar + al), da1 = ar - al;
   if (fabs(da1) < -a4) {
@@ -106,7 +117,7 @@ __device__ __forceinline__ void pert_pd(double a0, double& al, double& ar) {
 // Out of line: the rarely used schemes must not grow the hot 8 / 10 / 5 / 6 loop bodies (instruction cache, tp_tile.cuh).
 // (bl, br) of an ordinary interior cell in the dm family for the schemes beyond 8 and 10: 11 (van Leer emulation, ppm_fac = 1.5,
 // tp_core.F90:598-604), 12 (Lin & Rood positive definite, :605-627), 9 / 13 (unconstrained + pert_ppm(iv=0), :628-635)
-static __device__ __noinline__ void mono_blbr_other(double q0, double al0, double al1, double dm0, int iord, double& bl, double& br) {
+static PPM_HD __noinline__ void mono_blbr_other(double q0, double al0, double al1, double dm0, int iord, double& bl, double& br) {
   if (iord == 11) {
     const double xt = 1.5 * dm0;
     bl = -fsign(mn(fabs(xt), fabs(al0 - q0)), xt);
@@ -129,7 +140,7 @@ static __device__ __noinline__ void mono_blbr_other(double q0, double al0, doubl
 }
 // al family, mord = |iord| in 1..4 (tp_core.F90:401-486): flux through the face between cells A (value qa) and B (qb) from
 // al at the low face of A (alm), the shared face (al0) and the high face of B (alp).  lim_fac == 1 (checked on the host).
-static __device__ __noinline__ double flux_al_low(double qa, double qb, double alm, double al0, double alp, double c, int mord) {
+static PPM_HD __noinline__ double flux_al_low(double qa, double qb, double alm, double al0, double alp, double c, int mord) {
   if (mord == 2) {
     if (c > 0.) return qa + (1. - c) * (al0 - qa - c * (alm + al0 - (qa + qa)));
     return qb + (1. + c) * (al0 - qb + c * (al0 + alp - (qb + qb)));
@@ -161,7 +172,7 @@ static __device__ __noinline__ double flux_al_low(double qa, double qb, double a
 
 // iord == 7 (tp_core.F90:683-695): the flux tests smt5 = bl*br < 0 of BOTH cells of the face, so it needs the (positive-definite
 // limited, :605-627) bl, br of cell A (low side, value qa) and of cell B (qb)
-__device__ __forceinline__ double flux_pd7_from_cells(double qa, double qb, double Abl, double Abr, double Bbl, double Bbr, double c) {
+PPM_HD __forceinline__ double flux_pd7_from_cells(double qa, double qb, double Abl, double Abr, double Bbl, double Bbr, double c) {
   const double Ab0 = Abl + Abr, Bb0 = Bbl + Bbr;
   const bool As = Abl * Abr < 0., Bs = Bbl * Bbr < 0.;
   double fx1, fl;
@@ -436,7 +447,7 @@ __device__ __forceinline__ double flux_wind(const Q& u, const D& dx, const D& rd
 // cell (no cube-edge formula, no corner remap): the whole operator is register arithmetic on
 // the 6-point window q(i-3..i+2), loaded once with plain strided loads.  Operation order is
 // identical to cell_mono / cell_unlim / cell_wind_* above (the parity tests compare both).
-__device__ __forceinline__ double dm3(double qm, double q0, double qp) {
+PPM_HD __forceinline__ double dm3(double qm, double q0, double qp) {
   const double xt = 0.25 * (qp - qm);
   return fsign(mn(mn(fabs(xt), max3(qm, q0, qp) - q0), q0 - min3(qm, q0, qp)), xt);
 }
@@ -549,19 +560,19 @@ __device__ __forceinline__ double flux_wind_fast(const double* __restrict__ p, i
 // so the limiter / edge value is computed once per point instead of three times per flux.
 // dm2 == dm3 up to the sign of a zero result: max3-q0 and q0-min3 are |q0-qm| and |qp-q0| when the
 // two one-sided differences have the same sign, and one of them is 0 otherwise.
-__device__ __forceinline__ double dm2(double qm, double q0, double qp) {
+PPM_HD __forceinline__ double dm2(double qm, double q0, double qp) {
   const double a = q0 - qm, b = qp - q0, xt = 0.25 * (qp - qm);
-  const bool same = ((__double2hiint(a) ^ __double2hiint(b)) >= 0);
+  const bool same = ((hi_word(a) ^ hi_word(b)) >= 0);
   const double m = mn(mn(fabs(xt), fabs(a)), fabs(b));
   return same ? copysign(m, xt) : 0.;
 }
-__device__ __forceinline__ double aux_point(bool mono, int iord, double qm2, double qm1, double q0, double qp1) {
+PPM_HD __forceinline__ double aux_point(bool mono, int iord, double qm2, double qm1, double q0, double qp1) {
   if (mono) return dm2(qm1, q0, qp1);
   const double al = p1 * (qm1 + q0) + p2 * (qm2 + qp1);
   return iord < 0 ? mx(0., al) : al;
 }
 // iord == 7 on an interior line: a0..a5 = q(i-3..i+2) around the face between cells a2 and a3 (out of line: general instantiation only)
-static __device__ __noinline__ double flux_pd7_line(double a0, double a1, double a2, double a3, double a4, double a5, double c) {
+static PPM_HD __noinline__ double flux_pd7_line(double a0, double a1, double a2, double a3, double a4, double a5, double c) {
   const double d1 = dm2(a0, a1, a2), d2 = dm2(a1, a2, a3), d3 = dm2(a2, a3, a4), d4 = dm2(a3, a4, a5);
   const double alA = 0.5 * (a1 + a2) + r3 * (d1 - d2), alS = 0.5 * (a2 + a3) + r3 * (d2 - d3), alB = 0.5 * (a3 + a4) + r3 * (d3 - d4);
   double Abl, Abr, Bbl, Bbr;
@@ -571,7 +582,7 @@ static __device__ __noinline__ double flux_pd7_line(double a0, double a1, double
 }
 // monotone flux from the upwind cell's neighbourhood: q(iu-2..iu+2), dm(iu-1..iu+1)
 template <bool RARE = true>
-__device__ __forceinline__ double flux_mono_aux(double qm2, double qm1, double q0, double qp1, double qp2, double dmm, double dm0,
+PPM_HD __forceinline__ double flux_mono_aux(double qm2, double qm1, double q0, double qp1, double qp2, double dmm, double dm0,
                                                 double dmp, double c, int iord) {
   const double al0 = 0.5 * (qm1 + q0) + r3 * (dmm - dm0);
   const double al1 = 0.5 * (q0 + qp1) + r3 * (dm0 - dmp);
@@ -596,7 +607,7 @@ __device__ __forceinline__ double flux_mono_aux(double qm2, double qm1, double q
 // unlimited-family flux through the face between cells A (low side, value qa) and B (qb); alm, al0, alp = al at the
 // low face of A, the shared face, the high face of B
 template <bool RARE = true>
-__device__ __forceinline__ double flux_unlim_aux(double qa, double qb, double alm, double al0, double alp, double c, int iord) {
+PPM_HD __forceinline__ double flux_unlim_aux(double qa, double qb, double alm, double al0, double alp, double c, int iord) {
   if (RARE && iord >= 1 && iord <= 4) return flux_al_low(qa, qb, alm, al0, alp, c, iord);
   auto cell = [&](double q0, double l, double r) {
     CellU cu; cu.bl = l - q0; cu.br = r - q0; cu.b0 = cu.bl + cu.br;

@@ -111,7 +111,7 @@ __device__ __forceinline__ double line_flux(bool mono, const double* q, int sq, 
 // (ncu, profiles/r1_dsw_ncu_summary.md: the shared-memory data pipe is at 60 % of peak next to 58 % issue-active).
 // Same operations on the same operands as the aux form => bit-identical results.
 template <bool RARE>
-__device__ __forceinline__ double line_flux_na(bool mono, const double* q, int sq, double c, int iord) {
+PPM_HD __forceinline__ double line_flux_na(bool mono, const double* q, int sq, double c, int iord) {   // host too: tests/host_ppm_test.cu
   if (RARE && mono && iord == 7) return ppm::flux_pd7_line(q[-3 * sq], q[-2 * sq], q[-sq], q[0], q[sq], q[2 * sq], c);
   if (mono) {
     const int u = (c > 0.) ? -1 : 0;

@@ -1,0 +1,75 @@
+"""CPU: the flux arithmetic the CUDA tile kernels execute (ppm.cuh, tp_tile.cuh::line_flux_na -- compiled __host__ __device__) run on
+the HOST and compared with the oracle's xppm / yppm for every scheme of tp_valid_schemes.  GPU time is scarce; this keeps the
+kernels' scalar math pinned to the oracle on every CPU run.  (The device build is unaffected: its SASS is byte-identical with
+and without the host annotations.)"""
+import ctypes as C
+import os
+import shutil
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import harness as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+ALL = [-5, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13]
+COMMON = [-5, 5, 6, 8, 10]
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    if not os.path.exists(NVCC):
+        pytest.skip("nvcc not available")
+    out = str(tmp_path_factory.mktemp("hostppm") / "host_ppm_test")
+    subprocess.check_call([NVCC, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out,
+                           os.path.join(ROOT, "tests", "host_ppm_test.cu")], stderr=subprocess.DEVNULL)
+    return out
+
+
+def _host_flux(exe, q, c, iord, stride, rare):
+    blob = struct.pack("4i", q.size, iord, stride, rare) + q.tobytes() + c.tobytes()
+    r = subprocess.run([exe], input=blob, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    return np.frombuffer(r.stdout, dtype=np.float64)
+
+
+def _oracle_flux(q, c, iord, ydir):
+    lib, _ = H.load_oracle()
+    dp = C.POINTER(C.c_double)
+    flux = np.zeros(q.size + 1)
+    assert lib.fv3o_ppm_periodic(q.size, q.ctypes.data_as(dp), c.ctypes.data_as(dp), iord, ydir, flux.ctypes.data_as(dp)) == 0
+    return flux
+
+
+def _data(seed, positive):
+    rng = np.random.default_rng(seed)
+    n = 96
+    x = (np.arange(n) + 0.5) / n
+    q = np.sin(2 * np.pi * x) + 0.5 * np.sign(np.sin(6 * np.pi * x)) + 0.1 * rng.standard_normal(n)
+    if positive:
+        q = np.maximum(q, 0.0)           # zeros and positive bumps: the positive-definite constraints act
+    c = rng.uniform(-0.9, 0.9, n + 1)    # both upwind directions, face by face
+    return np.ascontiguousarray(q), np.ascontiguousarray(c)
+
+
+@pytest.mark.parametrize("iord", ALL)
+def test_kernel_flux_arithmetic_on_the_host_matches_the_oracle(built, exe, iord):
+    for seed, positive in ((1, False), (2, True)):
+        q, c = _data(seed, positive)
+        for stride, ydir in ((1, 0), (7, 1)):
+            got = _host_flux(exe, q, c, iord, stride, 1)
+            want = _oracle_flux(q, c, iord, ydir)
+            err = np.abs(got - want).max() / max(1.0, np.abs(want).max())
+            assert err < 1e-14, (iord, seed, stride, err)
+
+
+@pytest.mark.parametrize("iord", COMMON)
+def test_hot_instantiation_equals_general_one(built, exe, iord):
+    """RARE = false (what the FAM 0 / 1 kernels compile) gives bit-identical fluxes for the schemes it serves."""
+    q, c = _data(3, iord == -5)
+    a = _host_flux(exe, q, c, iord, 1, 0)
+    b = _host_flux(exe, q, c, iord, 1, 1)
+    assert np.array_equal(a, b)
