@@ -48,7 +48,13 @@ constexpr double near_zero_sw = 1.E-9;    // sw_core.F90:39
 // strided 1-D view: value at sweep index s is p[base + s*stride]
 struct Acc {
   const double* p; long long base; long long stride;
-  __device__ __forceinline__ double operator()(int s) const { return __ldg(p + base + (long long)s * stride); }
+  PPM_HD __forceinline__ double operator()(int s) const {
+#ifdef __CUDA_ARCH__
+    return __ldg(p + base + (long long)s * stride);
+#else
+    return p[base + (long long)s * stride];
+#endif
+  }
 };
 
 // scalar field with the copy_corners(dir=1) view, x sweep along row j (tp_core.F90:257-286)
@@ -87,7 +93,7 @@ struct QAccY {
 };
 
 template <class Q>
-__device__ __forceinline__ double dm_at(const Q& q, int i) {  // tp_core.F90:570-574
+PPM_HD __forceinline__ double dm_at(const Q& q, int i) {  // tp_core.F90:570-574
   const double qm = q(i - 1), q0 = q(i), qp = q(i + 1);
   const double xt = 0.25 * (qp - qm);
   return fsign(mn(mn(fabs(xt), max3(qm, q0, qp) - q0), q0 - min3(qm, q0, qp)), xt);
@@ -185,7 +191,7 @@ PPM_HD __forceinline__ double flux_pd7_from_cells(double qa, double qb, double A
 // dxa-weighted two-sided edge value (tp_core.F90:376-377 / :647-648); e = first cell inside
 // the face on the high side of the edge (e = 1 for the west/south edge, e = n for east/north)
 template <class Q, class D>
-__device__ __forceinline__ double edge_avg(const Q& q, const D& d, int e) {
+PPM_HD __forceinline__ double edge_avg(const Q& q, const D& d, int e) {
   return 0.5 * (((2. * d(e - 1) + d(e - 2)) * q(e - 1) - d(e - 1) * q(e - 2)) / (d(e - 2) + d(e - 1)) +
                 ((2. * d(e) + d(e + 1)) * q(e) - d(e) * q(e + 1)) / (d(e) + d(e + 1)));
 }
@@ -195,7 +201,7 @@ __device__ __forceinline__ double edge_avg(const Q& q, const D& d, int e) {
 // RARE = false compiles the schemes beyond 8 / 10 (dm family) and 5 / 6 / -5 (al family) out: the hot instantiations of the
 // transport kernels must not carry their code or their out-of-line calls (measured: +4.6 % on d_sw when they did)
 template <bool RARE = true, class Q, class D>
-__device__ __forceinline__ void cell_mono(const Q& q, const D& dxa, int i, int iord, int n, bool cube, double& bl, double& br) {
+PPM_HD __forceinline__ void cell_mono(const Q& q, const D& dxa, int i, int iord, int n, bool cube, double& bl, double& br) {
   if (!cube || (i >= 3 && i <= n - 3)) {
     const double qm1 = q(i - 1), q0 = q(i), qp1 = q(i + 1);
     const double dmm = dm_at(q, i - 1), dm0 = dm_at(q, i), dmp = dm_at(q, i + 1);
@@ -249,7 +255,7 @@ __device__ __forceinline__ void cell_mono(const Q& q, const D& dxa, int i, int i
 
 // unlimited family: edge value al(i).  tp_core.F90:369-392
 template <class Q, class D>
-__device__ __forceinline__ double al_unlim(const Q& q, const D& dxa, int i, int iord, int n, bool cube) {
+PPM_HD __forceinline__ double al_unlim(const Q& q, const D& dxa, int i, int iord, int n, bool cube) {
   double al;
   if (!cube || (i >= 3 && i <= n - 2)) al = p1 * (q(i - 1) + q(i)) + p2 * (q(i - 2) + q(i + 1));
   else if (i == 0) al = c1 * q(-2) + c2 * q(-1) + c3 * q(0);
@@ -266,7 +272,7 @@ struct CellU { double bl, br, b0; bool smt; };
 
 // unlimited family cell (5, 6, -5).  tp_core.F90:491-546
 template <class Q, class D>
-__device__ __forceinline__ CellU cell_unlim(const Q& q, const D& dxa, int i, int iord, int n, bool cube) {
+PPM_HD __forceinline__ CellU cell_unlim(const Q& q, const D& dxa, int i, int iord, int n, bool cube) {
   CellU c;
   const double q0 = q(i);
   c.bl = al_unlim(q, dxa, i, iord, n, cube) - q0;
@@ -292,7 +298,7 @@ __device__ __forceinline__ CellU cell_unlim(const Q& q, const D& dxa, int i, int
 
 // flux through interface i for Courant number c.  tp_core.F90:549-558, :701-707
 template <bool RARE = true, class Q, class D>
-__device__ __forceinline__ double flux_scalar(const Q& q, const D& dxa, int i, double c, int iord, int n, bool cube) {
+PPM_HD __forceinline__ double flux_scalar(const Q& q, const D& dxa, int i, double c, int iord, int n, bool cube) {
   if (RARE && iord == 7) {   // the limiter of 7 is the one of 12 (:605); cube-edge cells get the same one-sided overrides
     double Abl, Abr, Bbl, Bbr;
     cell_mono<true>(q, dxa, i - 1, 12, n, cube, Abl, Abr);
@@ -322,7 +328,7 @@ __device__ __forceinline__ double flux_scalar(const Q& q, const D& dxa, int i, d
 // zero = the row/column of this sweep is a face edge line (j==1||j==npy for xtp_u),
 // where bl=br=0 at the two cells touching the face corner (sw_core.F90:2206-2210,2451-2455)
 template <class Q, class D>
-__device__ __forceinline__ void cell_wind_mono(const Q& u, const D& dx, int i, int iord, int n, bool cube, bool zero,
+PPM_HD __forceinline__ void cell_wind_mono(const Q& u, const D& dx, int i, int iord, int n, bool cube, bool zero,
                                                double& bl, double& br) {
   if (!cube) {   // "Other grids" branch, sw_core.F90:2494-2505
     const double um1 = u(i - 1), u0 = u(i), up1 = u(i + 1);
@@ -388,7 +394,7 @@ __device__ __forceinline__ void cell_wind_mono(const Q& u, const D& dx, int i, i
 
 // iord < 8 family (5, 6[,7]) for the winds.  sw_core.F90:2187-2377
 template <class Q, class D>
-__device__ __forceinline__ CellU cell_wind_unlim(const Q& u, const D& dx, int i, int iord, int n, bool cube, bool zero) {
+PPM_HD __forceinline__ CellU cell_wind_unlim(const Q& u, const D& dx, int i, int iord, int n, bool cube, bool zero) {
   CellU c;
   auto alg = [&](int m) { return p1 * (u(m - 1) + u(m)) + p2 * (u(m - 2) + u(m + 1)); };
   if (!cube || (i >= 3 && i <= n - 3)) {
@@ -423,7 +429,7 @@ __device__ __forceinline__ CellU cell_wind_unlim(const Q& u, const D& dx, int i,
 
 // flux of the wind itself through interface i; c is a DISTANCE, cfl = c * rdx(upwind)
 template <class Q, class D>
-__device__ __forceinline__ double flux_wind(const Q& u, const D& dx, const D& rdx, int i, double c, int iord, int n,
+PPM_HD __forceinline__ double flux_wind(const Q& u, const D& dx, const D& rdx, int i, double c, int iord, int n,
                                             bool cube, bool zero) {
   if (iord >= 8) {
     const int iu = (c > 0.) ? i - 1 : i;

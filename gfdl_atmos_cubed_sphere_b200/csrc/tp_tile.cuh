@@ -72,7 +72,7 @@ struct ZnEpi { double* zn; const double *dfx, *dfy; const double* kdbl; int slot
 // strided view of a shared-memory line in sweep coordinates: value at sweep index s
 struct SAcc {
   const double* p; int stride; int org;
-  __device__ __forceinline__ double operator()(int s) const { return p[(s - org) * stride]; }
+  PPM_HD __forceinline__ double operator()(int s) const { return p[(s - org) * stride]; }
 };
 
 // 8-byte asynchronous global -> shared copy (LDGSTS): no register staging, all copies of a tile in flight together

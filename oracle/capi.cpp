@@ -368,6 +368,33 @@ int fv3o_ppm_periodic(int n, const double* q, const double* cn, int iord, int yd
   return 0;
 }
 
+// One full cube-face line of xppm / yppm (is = 1, ie = n, cube-edge formulas active at both ends): q and dxa carry the 3-cell
+// halo (index -2..n+3), cn and flux the faces 1..n+1.  Used by tests/test_host_device_math.py to pin the cube-edge operator.
+int fv3o_ppm_cube_line(int n, const double* q, const double* cn, const double* dxa, int iord, int ydir, double* flux) {
+  const int isd = -2, ied = n + 3, npx = n + 1;
+  std::vector<double> qh(q, q + n + 6), dh(dxa, dxa + n + 6), ch(cn, cn + n + 1), fh(n + 1);
+  if (!ydir) {
+    xppm(V2(fh.data(), 1, 1, n + 1), V2(qh.data(), isd, 1, n + 6), V2(ch.data(), 1, 1, n + 1), iord, 1, n, isd, ied, 1, 1, 1, 1,
+         npx, npx, V2(dh.data(), isd, 1, n + 6), false, 0, 1.0);
+  } else {   // one column (ifirst = ilast = 1), j is the sweep index
+    yppm(V2(fh.data(), 1, 1, 1), V2(qh.data(), 1, isd, 1), V2(ch.data(), 1, 1, 1), iord, 1, 1, 1, 1, 1, n, isd, ied, npx, npx,
+         V2(dh.data(), 1, isd, 1), false, 0, 1.0);
+  }
+  for (int i = 0; i <= n; i++) flux[i] = fh[i];
+  return 0;
+}
+// One full cube-face line of xtp_u (row j of a face with npy = npx): u, dx, rdx carry the halo (-2..n+3), c and flux the faces
+// 1..n+1.  j = 1 or npy is a face-edge line (bl = br = 0 at the corner cells, sw_core.F90:2206-2210).
+int fv3o_xtp_u_line(int n, int j, const double* u, const double* cn, const double* dx, const double* rdx, int iord, double* flux) {
+  const int isd = -2, ied = n + 3, npx = n + 1;
+  std::vector<double> uh(u, u + n + 6), dh(dx, dx + n + 6), rh(rdx, rdx + n + 6), ch(cn, cn + n + 1), fh(n + 1);
+  // js = j, je = j - 1: the routine sweeps rows js..je+1 = the single row j
+  xtp_u(1, n, j, j - 1, isd, ied, j, j, V2(ch.data(), 1, j, n + 1), V2(uh.data(), isd, j, n + 6), V2(nullptr, 0, 0, 0),
+        V2(fh.data(), 1, j, n + 1), iord, V2(dh.data(), isd, j, n + 6), V2(rh.data(), isd, j, n + 6), npx, npx, 0, false, 1.0);
+  for (int i = 0; i <= n; i++) flux[i] = fh[i];
+  return 0;
+}
+
 // stand-alone operators for unit parity
 int fv3o_a2b_ord4(fv3o_ctx* c, int field, int k, double* qout /*(isd:ied,jsd:jed)*/, int replace) {
   Bd bd(c->b); Grid g(c->g, bd);
