@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_dw(Lay L, DevGrid G, const doubl
 // ---------------------------------------------------------------------------------------------
 // kinetic energy at cell corners (sw_core.F90:1078-1228)
 // ---------------------------------------------------------------------------------------------
+// RARE = true: the instantiation that also carries hord_mt 1..4, 7, 9, 11 (out-of-line); the common 5 / 6 / 8 / 10 keep their code
+template <bool RARE>
 __global__ void __launch_bounds__(TI* TJ, 4) k_dsw_ke(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
                                                   const double* __restrict__ uc, const double* __restrict__ vc, const double* __restrict__ uts,
                                                   const double* __restrict__ vts, double* __restrict__ ke, double dt, int hord_mt) {
@@ -283,11 +285,12 @@ __global__ void __launch_bounds__(TI* TJ, 4) k_dsw_ke(Lay L, DevGrid G, const do
     double f;
     if (cube && j >= 4 && j <= npy - 3) {
       const long long o = ko + LIDX(L, i, j);
-      f = flux_wind_fast(v + o, L.NI, vb, G2(rdy, i, j - 1), G2(rdy, i, j), hord_mt);
+      if constexpr (RARE) f = flux_wind_fast_g(v + o, L.NI, vb, G2(rdy, i, j - 1), G2(rdy, i, j), hord_mt);
+      else f = flux_wind_fast(v + o, L.NI, vb, G2(rdy, i, j - 1), G2(rdy, i, j), hord_mt);
     } else {
       Acc va{v + ko, LIDX(L, i, 0), L.NI};
       Acc dya{G.dy, LIDX(L, i, 0), L.NI}, rdy{G.rdy, LIDX(L, i, 0), L.NI};
-      f = flux_wind(va, dya, rdy, j, vb, hord_mt, npy, cube, cube && (i == 1 || i == npx));
+      f = flux_wind<RARE>(va, dya, rdy, j, vb, hord_mt, npy, cube, cube && (i == 1 || i == npx));
     }
     k1 = vb * f;
   }
@@ -297,11 +300,12 @@ __global__ void __launch_bounds__(TI* TJ, 4) k_dsw_ke(Lay L, DevGrid G, const do
     double f;
     if (cube && i >= 4 && i <= npx - 3) {
       const long long o = ko + LIDX(L, i, j);
-      f = flux_wind_fast(u + o, 1, ub, G2(rdx, i - 1, j), G2(rdx, i, j), hord_mt);
+      if constexpr (RARE) f = flux_wind_fast_g(u + o, 1, ub, G2(rdx, i - 1, j), G2(rdx, i, j), hord_mt);
+      else f = flux_wind_fast(u + o, 1, ub, G2(rdx, i - 1, j), G2(rdx, i, j), hord_mt);
     } else {
       Acc ua{u + ko, LIDX(L, 0, j), 1};
       Acc dxa{G.dx, LIDX(L, 0, j), 1}, rdx{G.rdx, LIDX(L, 0, j), 1};
-      f = flux_wind(ua, dxa, rdx, i, ub, hord_mt, npx, cube, cube && (j == 1 || j == npy));
+      f = flux_wind<RARE>(ua, dxa, rdx, i, ub, hord_mt, npx, cube, cube && (j == 1 || j == npy));
     }
     k2 = ub * f;
   }
@@ -809,8 +813,8 @@ int stage_d_sw(fv3_ctx* c, double dt) {
   const Lay& L = c->L;
   const fv3_flags_t& f = c->f;
   const int nk = L.npz;
-  if (!hord_supported(f.hord_dp, f.lim_fac) || !hord_supported(f.hord_tm, f.lim_fac) || !hord_supported(f.hord_vt, f.lim_fac) || !hord_wind_supported(f.hord_mt))
-    return fv3_fail(c, -2, "d_sw: unsupported hord (supported: -5, 1..13 [1 only with lim_fac = 1]; hord_mt: 5, 6, 8, 10)");
+  if (!hord_supported(f.hord_dp, f.lim_fac) || !hord_supported(f.hord_tm, f.lim_fac) || !hord_supported(f.hord_vt, f.lim_fac) || !hord_wind_supported(f.hord_mt, f.lim_fac))
+    return fv3_fail(c, -2, "d_sw: unsupported hord (supported: -5, 1..13 [1 only with lim_fac = 1]; hord_mt: 1..11, 1 only with lim_fac = 1)");
   if (f.inline_q) return fv3_fail(c, -2, "d_sw: inline_q not supported");
   if (f.do_f3d) return fv3_fail(c, -2, "d_sw: do_f3d not supported");
   if (f.nord > 3) return fv3_fail(c, -2, "d_sw: nord > 3 not supported");
@@ -937,7 +941,8 @@ int stage_d_sw(fv3_ctx* c, double dt) {
   double* delp_new = c->fld[FV3_DELP];
   // --- KE (:1078-1228); ke lives in fx2's plane from here (tp scratch is rewritten later, so use gx)
   double* ke = gx;      // B-grid (is:ie+1, js:je+1)
-  k_dsw_ke<<<grd, blk, 0, st>>>(L, c->G, u, v, uc, vc, uts, vts, ke, dt, f.hord_mt);
+  if (hord_wind_is_rare(f.hord_mt)) k_dsw_ke<true><<<grd, blk, 0, st>>>(L, c->G, u, v, uc, vc, uts, vts, ke, dt, f.hord_mt);
+  else k_dsw_ke<false><<<grd, blk, 0, st>>>(L, c->G, u, v, uc, vc, uts, vts, ke, dt, f.hord_mt);
   double *wk = uts, *vq = vts;   // contravariant winds are dead after KE
   k_dsw_vort<<<grd, blk, 0, st>>>(L, c->G, u, v, (f.dddmp >= 1.E-5 || any_v) ? wk : nullptr, vq);
   c->launches += 2;

@@ -324,10 +324,62 @@ PPM_HD __forceinline__ double flux_scalar(const Q& q, const D& dxa, int i, doubl
   return fl;
 }
 
+// winds, al family, iord 1..4 (sw_core.F90:2246-2337): face between cells A (value ua, edge-aware bl/br) and B; c is a distance,
+// rm / r0 = rdx of A / B.  lim_fac == 1 (host check).  Out of line: general instantiation of k_dsw_ke only.
+static PPM_HD __noinline__ double flux_wind_low(double ua, double ub, double Abl, double Abr, double Bbl, double Bbr, double c,
+                                                double rm, double r0, int iord) {
+  const double Ab0 = Abl + Abr, Bb0 = Bbl + Bbr;
+  if (iord == 2) {
+    if (c > 0.) { const double cfl = c * rm; return ua + (1. - cfl) * (Abr - cfl * Ab0); }
+    const double cfl = c * r0; return ub + (1. + cfl) * (Bbl + cfl * Bb0);
+  }
+  const double Ax0 = fabs(Ab0), Ax1 = fabs(Abl - Abr), Bx0 = fabs(Bb0), Bx1 = fabs(Bbl - Bbr);
+  const bool A5 = Ax0 < Ax1, B5 = Bx0 < Bx1;
+  if (iord == 1) {
+    double fx0, fl;
+    if (c > 0.) { const double cfl = c * rm; fx0 = (1. - cfl) * (Abr - cfl * Ab0); fl = ua; }
+    else { const double cfl = c * r0; fx0 = (1. + cfl) * (Bbl + cfl * Bb0); fl = ub; }
+    if (A5 || B5) fl = fl + fx0;
+    return fl;
+  }
+  const bool A6 = 3. * Ax0 < Ax1, B6 = 3. * Bx0 < Bx1;
+  const bool hi5 = A5 && B5, hi6 = A6 || B6;
+  if (iord == 3) {
+    double fx0 = 0.;
+    if (c > 0.) {
+      const double cfl = c * rm;
+      if (hi6) fx0 = Abr - cfl * Ab0;
+      else if (hi5) fx0 = fsign(mn(fabs(Abl), fabs(Abr)), Abr);
+      return ua + (1. - cfl) * fx0;
+    }
+    const double cfl = c * r0;
+    if (hi6) fx0 = Bbl + cfl * Bb0;
+    else if (hi5) fx0 = fsign(mn(fabs(Bbl), fabs(Bbr)), Bbl);
+    return ub + (1. + cfl) * fx0;
+  }
+  // iord == 4
+  double fx0, fl;
+  if (c > 0.) { const double cfl = c * rm; fx0 = (1. - cfl) * (Abr - cfl * Ab0); fl = ua; }
+  else { const double cfl = c * r0; fx0 = (1. + cfl) * (Bbl + cfl * Bb0); fl = ub; }
+  if (hi5 || hi6) fl = fl + fx0;
+  return fl;
+}
+// winds, dm family, iord 9 (pmp-limited, sw_core.F90:2403-2411) and 11 / else (unlimited, :2434-2439), ordinary interior cell
+static PPM_HD __noinline__ void wind_blbr_other(double um2, double um1, double u0, double up1, double up2, double al0, double al1, int iord,
+                                                double& bl, double& br) {
+  if (iord == 9) {
+    const double dq0 = up1 - u0, dqp1 = up2 - up1, dqm1 = u0 - um1, dqm2 = um1 - um2;
+    const double pmp_1 = -2. * dq0, lac_1 = pmp_1 + 1.5 * dqp1;
+    bl = mn(max3(0., pmp_1, lac_1), mx(al0 - u0, min3(0., pmp_1, lac_1)));
+    const double pmp_2 = 2. * dqm1, lac_2 = pmp_2 - 1.5 * dqm2;
+    br = mn(max3(0., pmp_2, lac_2), mx(al1 - u0, min3(0., pmp_2, lac_2)));
+  } else { bl = al0 - u0; br = al1 - u0; }
+}
+
 // ------------------------------------------------------------------ momentum (xtp_u / ytp_v)
 // zero = the row/column of this sweep is a face edge line (j==1||j==npy for xtp_u),
 // where bl=br=0 at the two cells touching the face corner (sw_core.F90:2206-2210,2451-2455)
-template <class Q, class D>
+template <bool RARE = true, class Q, class D>
 PPM_HD __forceinline__ void cell_wind_mono(const Q& u, const D& dx, int i, int iord, int n, bool cube, bool zero,
                                                double& bl, double& br) {
   if (!cube) {   // "Other grids" branch, sw_core.F90:2494-2505
@@ -348,6 +400,8 @@ PPM_HD __forceinline__ void cell_wind_mono(const Q& u, const D& dx, int i, int i
       const double xt = 2. * dm0;
       bl = -fsign(mn(fabs(xt), fabs(al0 - u0)), xt);
       br = fsign(mn(fabs(xt), fabs(al1 - u0)), xt);
+    } else if (RARE && iord != 10) {
+      wind_blbr_other(u(i - 2), um1, u0, up1, u(i + 2), al0, al1, iord, bl, br);
     } else {  // 10, sw_core.F90:2414-2433
       bl = al0 - u0; br = al1 - u0;
       if (fabs(dm0) < near_zero_sw) {
@@ -428,19 +482,20 @@ PPM_HD __forceinline__ CellU cell_wind_unlim(const Q& u, const D& dx, int i, int
 }
 
 // flux of the wind itself through interface i; c is a DISTANCE, cfl = c * rdx(upwind)
-template <class Q, class D>
+template <bool RARE = true, class Q, class D>
 PPM_HD __forceinline__ double flux_wind(const Q& u, const D& dx, const D& rdx, int i, double c, int iord, int n,
                                             bool cube, bool zero) {
   if (iord >= 8) {
     const int iu = (c > 0.) ? i - 1 : i;
     double bl, br;
-    cell_wind_mono(u, dx, iu, iord, n, cube, zero, bl, br);
+    cell_wind_mono<RARE>(u, dx, iu, iord, n, cube, zero, bl, br);
     const double cfl = c * rdx(iu);
     const double uu = u(iu);
     return (c > 0.) ? uu + (1. - cfl) * (br - cfl * (bl + br)) : uu + (1. + cfl) * (bl + cfl * (bl + br));
   }
   const CellU a = cell_wind_unlim(u, dx, i - 1, iord, n, cube, zero);
   const CellU b = cell_wind_unlim(u, dx, i, iord, n, cube, zero);
+  if (RARE && iord >= 1 && iord <= 4) return flux_wind_low(u(i - 1), u(i), a.bl, a.br, b.bl, b.br, c, rdx(i - 1), rdx(i), iord);
   double fx0, fl;
   if (c > 0.) { const double cfl = c * rdx(i - 1); fx0 = (1. - cfl) * (a.br - cfl * a.b0); fl = u(i - 1); }
   else { const double cfl = c * rdx(i); fx0 = (1. + cfl) * (b.bl + cfl * b.b0); fl = u(i); }
@@ -559,6 +614,59 @@ __device__ __forceinline__ double flux_wind_fast(const double* __restrict__ p, i
   return fl;
 }
 
+PPM_HD __forceinline__ double ldg_(const double* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+// every scheme (general instantiation of k_dsw_ke; host-callable for tests/host_ppm_test.cu)
+PPM_HD __forceinline__ double flux_wind_fast_g(const double* __restrict__ p, int s, double c, double rm, double r0, int iord) {
+  const double a0 = ldg_(p - 3 * s), a1 = ldg_(p - 2 * s), a2 = ldg_(p - s), a3 = ldg_(p), a4 = ldg_(p + s), a5 = ldg_(p + 2 * s);
+  if (iord >= 8) {
+    const bool up = c > 0.;
+    const double um2 = up ? a0 : a1, um1 = up ? a1 : a2, u0 = up ? a2 : a3, up1 = up ? a3 : a4, up2 = up ? a4 : a5;
+    const double dmm = dm3(um2, um1, u0), dm0 = dm3(um1, u0, up1), dmp = dm3(u0, up1, up2);
+    const double al0 = 0.5 * (um1 + u0) + r3 * (dmm - dm0), al1 = 0.5 * (u0 + up1) + r3 * (dm0 - dmp);
+    double bl, br;
+    if (iord == 8) {
+      const double xt = 2. * dm0;
+      bl = -fsign(mn(fabs(xt), fabs(al0 - u0)), xt);
+      br = fsign(mn(fabs(xt), fabs(al1 - u0)), xt);
+    } else if (iord != 10) {
+      wind_blbr_other(um2, um1, u0, up1, up2, al0, al1, iord, bl, br);
+    } else {
+      bl = al0 - u0; br = al1 - u0;
+      if (fabs(dm0) < near_zero_sw) {
+        if (fabs(dmm) + fabs(dmp) < near_zero_sw) { bl = 0.; br = 0.; }
+      } else if (fabs(3. * (bl + br)) > fabs(bl - br)) {
+        const double dq0 = up1 - u0, dqp1 = up2 - up1, dqm1 = u0 - um1, dqm2 = um1 - um2;
+        const double pmp_1 = -2. * dq0, lac_1 = pmp_1 + 1.5 * dqp1;
+        bl = mn(max3(0., pmp_1, lac_1), mx(bl, min3(0., pmp_1, lac_1)));
+        const double pmp_2 = 2. * dqm1, lac_2 = pmp_2 - 1.5 * dqm2;
+        br = mn(max3(0., pmp_2, lac_2), mx(br, min3(0., pmp_2, lac_2)));
+      }
+    }
+    const double cfl = c * (up ? rm : r0);
+    return up ? u0 + (1. - cfl) * (br - cfl * (bl + br)) : u0 + (1. + cfl) * (bl + cfl * (bl + br));
+  }
+  const double alm = p1 * (a1 + a2) + p2 * (a0 + a3);
+  const double al0 = p1 * (a2 + a3) + p2 * (a1 + a4);
+  const double alp = p1 * (a3 + a4) + p2 * (a2 + a5);
+  const double Abl = alm - a2, Abr = al0 - a2, Ab0 = Abl + Abr;
+  const double Bbl = al0 - a3, Bbr = alp - a3, Bb0 = Bbl + Bbr;
+  if (iord >= 1 && iord <= 4) return flux_wind_low(a2, a3, Abl, Abr, Bbl, Bbr, c, rm, r0, iord);
+  bool As, Bs;
+  if (iord == 5) { As = Abl * Abr < 0.; Bs = Bbl * Bbr < 0.; }
+  else { As = 3. * fabs(Ab0) < fabs(Abl - Abr); Bs = 3. * fabs(Bb0) < fabs(Bbl - Bbr); }
+  double fx0, fl;
+  if (c > 0.) { const double cfl = c * rm; fx0 = (1. - cfl) * (Abr - cfl * Ab0); fl = a2; }
+  else { const double cfl = c * r0; fx0 = (1. + cfl) * (Bbl + cfl * Bb0); fl = a3; }
+  if (As || Bs) fl = fl + fx0;
+  return fl;
+}
+
 // ------------------------------------------------------------------ two-pass form for shared-memory tiles
 // Pass 1 stores one auxiliary value per point of a line, pass 2 evaluates the flux from it:
 //   monotone family (8, 10):  aux(c) = dm of cell c                      (tp_core.F90:570-574)
@@ -646,6 +754,11 @@ __host__ inline bool hord_supported(int h, double lim_fac = 1.0) {
 }
 // schemes outside the common five run in the general (FAM = 2) instantiations of the tile kernels
 __host__ inline bool hord_is_rare(int h) { return !(h == 5 || h == 6 || h == -5 || h == 8 || h == 10); }
-__host__ inline bool hord_wind_supported(int h) { return h == 5 || h == 6 || h == 8 || h == 10; }
+// xtp_u / ytp_v (sw_core.F90:2154-2998): 1..4, 5, 6 (= 7), 8, 9, 10, 11; hord_mt = 1 reads lim_fac (only 1 is built)
+__host__ inline bool hord_wind_supported(int h, double lim_fac = 1.0) {
+  if (h == 1) return lim_fac == 1.0;
+  return h >= 2 && h <= 11;
+}
+__host__ inline bool hord_wind_is_rare(int h) { return !(h == 5 || h == 6 || h == 8 || h == 10); }
 
 }  // namespace ppm

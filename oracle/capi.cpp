@@ -395,6 +395,18 @@ int fv3o_xtp_u_line(int n, int j, const double* u, const double* cn, const doubl
   return 0;
 }
 
+// One full cube-face line of ytp_v (column i of a face): v, dy, rdy carry the halo (-2..n+3), c and flux the faces 1..n+1.
+// i = 1 or npx is a face-edge line.
+int fv3o_ytp_v_line(int n, int i, const double* v, const double* cn, const double* dy, const double* rdy, int jord, double* flux) {
+  const int jsd = -2, jed = n + 3, npy = n + 1;
+  std::vector<double> vh(v, v + n + 6), dh(dy, dy + n + 6), rh(rdy, rdy + n + 6), ch(cn, cn + n + 1), fh(n + 1);
+  // is = i, ie = i - 1: the routine sweeps columns is..ie+1 = the single column i
+  ytp_v(i, i - 1, 1, n, i, i, jsd, jed, V2(ch.data(), i, 1, 1), V2(nullptr, 0, 0, 0), V2(vh.data(), i, jsd, 1), V2(fh.data(), i, 1, 1), jord,
+        V2(dh.data(), i, jsd, 1), V2(rh.data(), i, jsd, 1), npy, npy, 0, false, 1.0);
+  for (int j = 0; j <= n; j++) flux[j] = fh[j];
+  return 0;
+}
+
 // stand-alone operators for unit parity
 int fv3o_a2b_ord4(fv3o_ctx* c, int field, int k, double* qout /*(isd:ied,jsd:jed)*/, int replace) {
   Bd bd(c->b); Grid g(c->g, bd);

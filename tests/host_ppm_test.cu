@@ -7,6 +7,7 @@
 //           p0 = stride, p1 = rare;            doubles: q[n+6] (index -2..n+3), c[n+1] (faces 1..n+1), dxa[n+6]
 //   mode 2: one full cube-face line of the wind operator ppm::flux_wind (xtp_u / ytp_v of k_dsw_ke)
 //           p0 = zero (edge line), p1 unused;  doubles: u[n+6], c[n+1], dx[n+6], rdx[n+6]
+//   mode 3: ppm::flux_wind_fast_g (interior fast path of k_dsw_ke<true>) on the faces 4..n-2 of the same line; same input as mode 2
 #include <cstdio>
 #include <vector>
 #include "../gfdl_atmos_cubed_sphere_b200/csrc/tp_tile.cuh"
@@ -47,6 +48,11 @@ int main() {
     if (!rd(u) || !rd(c) || !rd(dx) || !rd(rdx)) return 2;
     const ppm::Acc ua{u.data(), 2, 1}, da{dx.data(), 2, 1}, ra{rdx.data(), 2, 1};
     for (int i = 1; i <= n + 1; i++) flux[i - 1] = ppm::flux_wind(ua, da, ra, i, c[i - 1], iord, n + 1, true, zero);
+  } else if (mode == 3) {   // interior fast path of k_dsw_ke<true>: faces 4..n-2 only (the others are left 0)
+    std::vector<double> u(n + 6), c(n + 1), dx(n + 6), rdx(n + 6);
+    if (!rd(u) || !rd(c) || !rd(dx) || !rd(rdx)) return 2;
+    for (int i = 4; i <= n - 2; i++)
+      flux[i - 1] = ppm::flux_wind_fast_g(&u[i + 2], 1, c[i - 1], rdx[i - 1 + 2], rdx[i + 2], iord);
   } else return 3;
   fwrite(flux.data(), sizeof(double), n + 1, stdout);
   return 0;

@@ -111,21 +111,31 @@ def test_cube_edge_operator_on_the_host_matches_the_oracle(built, exe, iord):
             assert np.array_equal(_run(exe, 1, n, iord, 1, 0, q, c, dxa), _run(exe, 1, n, iord, 1, 1, q, c, dxa))
 
 
-@pytest.mark.parametrize("iord", [5, 6, 8, 10])
+WIND = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11]
+
+
+@pytest.mark.parametrize("iord", WIND)
 @pytest.mark.parametrize("edge_line", [0, 1])
 def test_wind_operator_on_the_host_matches_the_oracle(built, exe, iord, edge_line):
     """ppm::flux_wind (xtp_u / ytp_v as k_dsw_ke evaluates them near the cube edges) over a whole face line, on an ordinary
-    row and on a face-edge row (j = 1: bl = br = 0 at the corner cells, sw_core.F90:2206-2210)."""
+    row and on a face-edge row (j = 1: bl = br = 0 at the corner cells, sw_core.F90:2206-2210); every scheme of xtp_u
+    (sw_core.F90:2187-2508), against the oracle's xtp_u AND ytp_v (the kernels use one routine for both directions).
+    Then the interior fast path (flux_wind_fast_g) on the faces where k_dsw_ke takes it."""
     lib, _ = H.load_oracle()
     dp = C.POINTER(C.c_double)
     u, c, dx = _cube_line(21 + iord, False)
     n = c.size - 1
     c = c * 0.5 * dx[2:n + 3]            # xtp_u's c is a distance: cfl = c * rdx(upwind)
     rdx = 1.0 / dx
-    j = 1 if edge_line else 7
+    line = 1 if edge_line else 7
     got = _run(exe, 2, n, iord, edge_line, 0, u, c, dx, rdx)
-    want = np.zeros(n + 1)
-    assert lib.fv3o_xtp_u_line(n, j, u.ctypes.data_as(dp), c.ctypes.data_as(dp), dx.ctypes.data_as(dp), rdx.ctypes.data_as(dp), iord,
-                               want.ctypes.data_as(dp)) == 0
-    err = np.abs(got - want).max() / max(1.0, np.abs(want).max())
-    assert err < 1e-13, (iord, edge_line, err, int(np.abs(got - want).argmax()))
+    for fn in (lib.fv3o_xtp_u_line, lib.fv3o_ytp_v_line):
+        want = np.zeros(n + 1)
+        assert fn(n, line, u.ctypes.data_as(dp), c.ctypes.data_as(dp), dx.ctypes.data_as(dp), rdx.ctypes.data_as(dp), iord,
+                  want.ctypes.data_as(dp)) == 0
+        err = np.abs(got - want).max() / max(1.0, np.abs(want).max())
+        assert err < 1e-13, (iord, edge_line, fn.__name__, err, int(np.abs(got - want).argmax()))
+    if not edge_line:
+        fast = _run(exe, 3, n, iord, 0, 0, u, c, dx, rdx)
+        sl = slice(3, n - 2)             # faces 4..n-2
+        assert np.abs(fast[sl] - want[sl]).max() / max(1.0, np.abs(want).max()) < 1e-13, iord

@@ -1,0 +1,24 @@
+"""GPU tests of features whose device arithmetic is validated ON THE HOST against the oracle (tests/test_host_device_math.py:
+the kernels' own routines compiled __host__ __device__) but that have not had their first run on a B200 yet -- the round's GPU
+budget was spent when they were written.  They are expected to pass; `xfail(strict=False)` only keeps a first-run surprise from
+turning the whole suite red.  Remove the marker after the first green run (an XPASS in the report)."""
+import pytest
+
+import harness as H
+
+pytestmark = pytest.mark.gpu
+TOL_STAGE = 1e-11
+
+
+def _assert(res, tol):
+    bad = {k: v for k, v in res.items() if not (v <= tol)}
+    assert not bad, f"parity exceeded {tol}: {bad}"
+
+
+@pytest.mark.xfail(strict=False, reason="host-validated (test_host_device_math), first B200 run pending")
+@pytest.mark.parametrize("hord_mt", [1, 2, 3, 4, 7, 9, 11])
+def test_d_sw_wind_schemes_beyond_5_6_8_10(hord_mt):
+    """xtp_u / ytp_v (sw_core.F90:2154-2998) with the less common hord_mt: the general instantiation k_dsw_ke<true>; single-tile
+    face (every cube-edge case) and a 56 x 56 face (interior fast path)."""
+    _assert(H.parity_c_sw_d_sw(n=24, npz=4, flagset="A", dt=20.0, flags_override=dict(hord_mt=hord_mt)), TOL_STAGE)
+    _assert(H.parity_c_sw_d_sw(n=56, npz=2, flagset="B", dt=10.0, flags_override=dict(hord_mt=hord_mt)), TOL_STAGE)
