@@ -251,3 +251,27 @@ def test_scheme_diffusivity_ordering(built):
         r = {iord: float((_advect_1d(lib, q0.copy(), 0.45, iord, 80) ** 2).sum()) for iord in (2, 5, 3, 4, 6)}
         assert min(r[2], r[5], r[3]) > r[4] > r[6], r
         assert max(r[2], r[5], r[3]) / min(r[2], r[5], r[3]) < 1.002, r
+
+
+@pytest.mark.parametrize("hydro", [0, 1])
+def test_unperturbed_jablonowski_williamson_state_stays_steady(built, hydro):
+    """Known answer for the COMPOSITE path: the Jablonowski-Williamson initial state without the perturbation
+    (test_cases.F90:1575-1890, case 13) is a steady solution of the primitive equations: u ~ 35 m/s in geostrophic and
+    hydrostatic balance.  A wrong sign or metric factor in the Coriolis / vorticity flux, the pressure gradient or the vertical
+    solver would accelerate the jet by f*u ~ 12 m/s per hour; the discrete path (c_sw, d_sw, Riemann solvers, nh_p_grad, 6-face
+    exchange, no vertical remap, 8 levels) holds it to < 1 m/s after one hour (measured 0.56), with |w| a few mm/s."""
+    from gfdl_atmos_cubed_sphere_b200 import init_state as I
+    n, npz = 24, 8
+    case = H.Case(n, npz, "A", state="baroclinic", flags_override=dict(hydrostatic=hydro))   # 1: geopk + one_grad_p branch
+    case.states = I.baroclinic_wave(case.tiles, case.bounds, npz, case.ak, case.bk, perturb=False, w_amp=0.0)
+    oc = H.OracleCube(case, fast=True)
+    u0 = {t: oc.eng[t].get("U").copy() for t in oc.tiles}
+    d0 = {t: oc.eng[t].get("DELP").copy() for t in oc.tiles}
+    assert max(np.abs(H.sub(oc.eng[t], "U", u0[t], 1, n, 1, n + 1)).max() for t in oc.tiles) > 30.0    # there is a jet to hold
+    oc.dyn_core(3600.0, 8)
+    du = max(np.abs(H.sub(oc.eng[t], "U", oc.eng[t].get("U") - u0[t], 1, n, 1, n + 1)).max() for t in oc.tiles)
+    dd = max(np.abs(H.sub(oc.eng[t], "DELP", (oc.eng[t].get("DELP") - d0[t]) / d0[t], 1, n, 1, n)).max() for t in oc.tiles)
+    w = 0.0 if hydro else max(np.abs(H.sub(oc.eng[t], "W", oc.eng[t].get("W"), 1, n, 1, n)).max() for t in oc.tiles)
+    oc.close()
+    print("JW steady state, hydrostatic =", hydro, ": max|du| =", du, "rel d(delp) =", dd, "max|w| =", w)
+    assert du < 1.0 and dd < 3e-3 and w < 0.02, (du, dd, w)
