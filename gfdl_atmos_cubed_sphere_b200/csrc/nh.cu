@@ -516,6 +516,8 @@ __global__ void __launch_bounds__(CB, 8) k_edge_profile(Lay L, const double* __r
 #undef LV
 }
 // ---- small column / pointwise helpers -------------------------------------------------------
+// LOGP: pln_halo (dyn_core.F90:1449-1496, use_logp) instead of pk3_halo (:1395-1447)
+template <bool LOGP>
 __global__ void __launch_bounds__(CB) k_pk3_halo(Lay L, const double* __restrict__ delp, double* __restrict__ pk3, double ptop, double akap) {
   // ring cells: 2-wide frame around the compute domain excluding ... (dyn_core.F90:1405-1445)
   const int n = L.ie - L.is + 1;
@@ -534,7 +536,7 @@ __global__ void __launch_bounds__(CB) k_pk3_halo(Lay L, const double* __restrict
   double pe = ptop;
   for (int k = 1; k <= L.npz; k++) {
     pe = pe + __ldg(delp + o + (long long)(k - 1) * L.plane);
-    pk3[o + (long long)k * L.plane] = exp(akap * log(pe));
+    pk3[o + (long long)k * L.plane] = LOGP ? log(pe) : exp(akap * log(pe));
   }
 }
 __global__ void __launch_bounds__(CB) k_pe_halo(Lay L, const double* __restrict__ delp, double* __restrict__ pe, double ptop) {
@@ -772,9 +774,9 @@ int stage_geopk(fv3_ctx* c, int cg) {
 
 int stage_pk3_halo(fv3_ctx* c) {
   const Lay& L = c->L;
-  if (c->f.use_logp) return fv3_fail(c, -2, "pln_halo (use_logp) not supported");
   const int n = L.ie - L.is + 1, nring = 4 * n + 4 * (n + 4);
-  k_pk3_halo<<<(nring + CB - 1) / CB, CB, 0, c->stream>>>(L, c->fld[FV3_DELP], c->fld[FV3_PK3], c->f.ptop, c->f.kappa);
+  if (c->f.use_logp) k_pk3_halo<true><<<(nring + CB - 1) / CB, CB, 0, c->stream>>>(L, c->fld[FV3_DELP], c->fld[FV3_PK3], c->f.ptop, c->f.kappa);
+  else k_pk3_halo<false><<<(nring + CB - 1) / CB, CB, 0, c->stream>>>(L, c->fld[FV3_DELP], c->fld[FV3_PK3], c->f.ptop, c->f.kappa);
   c->launches++;
   return 0;
 }

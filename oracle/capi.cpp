@@ -263,7 +263,8 @@ int fv3o_riem_solver3(fv3o_ctx* c, double dt, int last_call) {
 }
 int fv3o_pk3_halo(fv3o_ctx* c) {
   Bd bd(c->b);
-  pk3_halo(bd.is, bd.ie, bd.js, bd.je, bd.isd, bd.ied, bd.jsd, bd.jed, bd.npz, c->f.ptop, c->f.kappa, F3(c, FV3_PK3), F3(c, FV3_DELP));
+  if (c->f.use_logp) pln_halo(bd.is, bd.ie, bd.js, bd.je, bd.isd, bd.ied, bd.jsd, bd.jed, bd.npz, c->f.ptop, F3(c, FV3_PK3), F3(c, FV3_DELP));   // dyn_core.F90:955-959
+  else pk3_halo(bd.is, bd.ie, bd.js, bd.je, bd.isd, bd.ied, bd.jsd, bd.jed, bd.npz, c->f.ptop, c->f.kappa, F3(c, FV3_PK3), F3(c, FV3_DELP));
   return 0;
 }
 int fv3o_pe_halo(fv3o_ctx* c) {

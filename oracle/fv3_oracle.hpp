@@ -201,6 +201,7 @@ void geopk(double ptop, double* pe, double* peln, V3 delp, V3 pk, V3 gz, V2 hs, 
            double cp_air, bool CG, bool use_cond, const Bd& bd);
 void one_grad_p(V3 u, V3 v, V3 pk, V3 gz, V3 delp, double dt, const Grid& g, const Bd& bd, int npz, double ptop, double akap,
                 bool hydrostatic);
+void pln_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed, int npz, double ptop, V3 pk3, V3 delp);
 void pk3_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed, int npz, double ptop,
               double akap, V3 pk3, V3 delp);
 void pe_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed, int npz, double ptop,

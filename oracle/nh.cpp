@@ -579,6 +579,25 @@ void pk3_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed
   }
 }
 
+// dyn_core.F90:1449-1496 (use_logp: pk3 holds log(pe) instead of pe**akap)
+void pln_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed, int npz, double ptop, V3 pk3, V3 delp) {
+  (void)isd; (void)ied; (void)jsd; (void)jed;
+  for (int j = js; j <= je; j++) {
+    const int ii[4] = {is - 2, is - 1, ie + 1, ie + 2};
+    for (int n = 0; n < 4; n++) {
+      double pet = ptop;
+      for (int k = 1; k <= npz; k++) { pet = pet + delp(ii[n], j, k); pk3(ii[n], j, k + 1) = std::log(pet); }
+    }
+  }
+  for (int i = is - 2; i <= ie + 2; i++) {
+    const int jj[4] = {js - 2, js - 1, je + 1, je + 2};
+    for (int n = 0; n < 4; n++) {
+      double pet = ptop;
+      for (int k = 1; k <= npz; k++) { pet = pet + delp(i, jj[n], k); pk3(i, jj[n], k + 1) = std::log(pet); }
+    }
+  }
+}
+
 // dyn_core.F90:1498-1526
 void pe_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed, int npz, double ptop,
              double* pe, V3 delp) {

@@ -275,3 +275,19 @@ def test_unperturbed_jablonowski_williamson_state_stays_steady(built, hydro):
     oc.close()
     print("JW steady state, hydrostatic =", hydro, ": max|du| =", du, "rel d(delp) =", dd, "max|w| =", w)
     assert du < 1.0 and dd < 3e-3 and w < 0.02, (du, dd, w)
+
+
+def test_use_logp_formulation_is_a_small_perturbation(built):
+    """use_logp = T puts log(pe) instead of pe**kappa into pk3 (nh_core.F90:222-230, pln_halo dyn_core.F90:1449-1496, peln1 at the
+    top of nh_p_grad :1726): the same pressure-gradient force up to truncation error.  After two substeps the winds of the two
+    formulations differ by millimetres per second (measured 3e-3 m/s, largest next to the cube edges); a halo ring holding the
+    wrong quantity would show up as metres per second there."""
+    res = {}
+    for lp in (0, 1):
+        case = H.Case(16, 6, "A", state="baroclinic", flags_override=dict(use_logp=lp))
+        oc = H.OracleCube(case)
+        oc.dyn_core(800.0, 2)
+        res[lp] = {t: oc.eng[t].get("U") for t in oc.tiles}
+        oc.close()
+    du = max(float(np.abs(res[0][t] - res[1][t])[:, 3:-3, 3:-3].max()) for t in res[0])
+    assert 0.0 < du < 0.02, du
