@@ -252,7 +252,7 @@ void fv3_destroy(fv3_ctx* c) {
   for (auto p : alts) cudaFree(p);
   for (int i = 0; i < fv3_ctx::NSCR; i++) cudaFree(c->scr[i]);
   for (auto p : c->metric_alloc) cudaFree(p);
-  cudaFree(c->d_stage); cudaFree(c->d_kint); cudaFree(c->d_kdbl); cudaFree(c->d_dp_ref); cudaFree(c->d_edge_tab);
+  cudaFree(c->d_stage); cudaFree(c->d_kint); cudaFree(c->d_kdbl); cudaFree(c->d_dp_ref); cudaFree(c->d_edge_tab); cudaFree(c->d_rff);
   for (auto& kv : c->timers) { cudaEventDestroy(kv.second.e0); cudaEventDestroy(kv.second.e1); }
   cudaStreamDestroy(c->stream);
   delete c;

@@ -136,6 +136,7 @@ struct fv3_ctx {
   int* d_kint; double* d_kdbl;     // device copies of per-k coefficient tables
   double* d_dp_ref;                // dp_ref(npz)  dyn_core.F90:242-244
   double* d_edge_tab;              // edge_profile coefficient tables (nh.cu), built on first use
+  double* d_rff = nullptr; int k_rf = 0;   // Rayleigh damping table of the vertical solvers (fast_tau_w_sec > 0), built by the first solver call
   long long launches;
   bool timers_on;
   std::map<std::string, StageTimer> timers;

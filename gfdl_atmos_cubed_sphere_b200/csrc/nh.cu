@@ -35,6 +35,8 @@ struct SolverIn {
   double *pm2, *gam, *pp, *w2;   // scratch planes [km+1][NJ][NI]
   double dt, rgrav, rdgas, akap, ptop, p_fac, a_imp;
   int km, use_cond, moist_kappa, d_grid;
+  // appended (keeps the constant-bank offsets of everything above): Rayleigh damping of w, rff(1:k_rf) (nh_utils.F90:356-368)
+  const double* rff; int k_rf;
 };
 
 // One column of SIM1_solver (a_imp > 0.999) or SIM_solver, in SIX sweeps over k with the loads of NB levels issued
@@ -56,7 +58,9 @@ struct SolverIn {
 #define RIEM_MINB 8
 #endif
 constexpr int NB = RIEM_NB;
-template <bool MK, bool UC, class IfaceSink, class DzSink>
+// RF: fast_tau_w_sec > 0 -- w2(k <= k_rf) *= rff(k) after the back-substitution (nh_utils.F90:1363-1371, :1498-1506), applied where
+// sweep E loads the final w2.  A template flag so that the default instantiations keep their exact code.
+template <bool MK, bool UC, bool RF, class IfaceSink, class DzSink>
 __device__ __forceinline__ void solve_column(const SolverIn& S, long long o, long long P, IfaceSink emit, DzSink out_dz) {
   const int km = S.km;
   const bool sim1 = S.d_grid ? (S.a_imp > 0.999) : true;   // nh_utils.F90:450-459, nh_core.F90:169-185
@@ -244,6 +248,7 @@ __device__ __forceinline__ void solve_column(const SolverIn& S, long long o, lon
       for (int u = 0; u < NB; u++) {
         const int kk = min(k0 + u, km);
         d[u] = __ldg(delp + LV(kk)); w2v[u] = w2a[LV(kk)]; wv[u] = __ldg(w1 + LV(kk));
+        if (RF && kk <= S.k_rf) w2v[u] = w2v[u] * __ldg(S.rff + kk - 1);
         pn[u] = sim1 ? 0. : ppa[LV(kk + 1)];
       }
 #pragma unroll
@@ -308,7 +313,7 @@ __device__ __forceinline__ void solve_column(const SolverIn& S, long long o, lon
 
 // ---- Riem_Solver_c (nh_utils.F90:323-480) on columns [is-1, ie+1]^2 -------------------------
 // 8 CTAs x 128 threads per SM: all columns of a C384 face are resident in ONE wave (72-88 registers gave 1.56 waves)
-template <bool MK, bool UC>
+template <bool MK, bool UC, bool RF>
 __global__ void __launch_bounds__(CB, RIEM_MINB) k_riem_c(Lay L, const __grid_constant__ SolverIn S, const double* __restrict__ hs, double* __restrict__ gz,
                                                double* __restrict__ pef, double grav) {
   COL_SETUP(L.is - 1, L.ie + 1, L.js - 1, L.je + 1)
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(CB, RIEM_MINB) k_riem_c(Lay L, const __grid_co
   double gzk = __ldg(hs + o);   // gz(km+1) = hs
   // heights are read from gz (input, m) by the sweeps A and C; gz is overwritten bottom-up by the last sweep only,
   // in the same backward order as nh_utils.F90:468-476
-  solve_column<MK, UC>(S, o, P,
+  solve_column<MK, UC, RF>(S, o, P,
                [&](int k, double pe2, double pem, double) {   // pef = pe2 + pem (nh_utils.F90:461-465), top = ptop
                  pef[o + (long long)(k - 1) * P] = (k == 1) ? S.ptop : pe2 + pem;
                },
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(CB, RIEM_MINB) k_riem_c(Lay L, const __grid_co
 }
 
 // ---- Riem_Solver3 (nh_core.F90:47-241) on columns [is, ie]x[js, je] -------------------------
-template <bool MK, bool UC>
+template <bool MK, bool UC, bool RF>
 __global__ void __launch_bounds__(CB, RIEM_MINB) k_riem3(Lay L, const __grid_constant__ SolverIn S, const double* __restrict__ zs, double* __restrict__ zh,
                                               double* __restrict__ w, double* __restrict__ delz, double* __restrict__ ppe,
                                               double* __restrict__ pk3, double* __restrict__ pk, double* __restrict__ pe,
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(CB, RIEM_MINB) k_riem3(Lay L, const __grid_con
   double zk = __ldg(zs + o);
   const double peln1 = log(S.ptop);
   const double ptk = exp(S.akap * peln1);
-  solve_column<MK, UC>(S, o, P,
+  solve_column<MK, UC, RF>(S, o, P,
                [&](int k, double pe2, double pem, double w2) {   // w, pk3, ppe (+ pe, pk, peln on the last call)
                  const long long ok = o + (long long)(k - 1) * P;
                  double pl, pkv;
@@ -579,7 +584,32 @@ static SolverIn make_solver(fv3_ctx* c, double dt, int d_grid) {
   S.km = c->L.npz; S.use_cond = f.use_cond; S.moist_kappa = f.moist_kappa && (d_grid || f.use_cond); S.d_grid = d_grid;
   S.q_con = c->fld[FV3_QCON]; S.cappa = c->fld[FV3_CAPPA];
   S.pm2 = c->scr[0]; S.gam = c->scr[1]; S.pp = c->scr[2]; S.w2 = c->scr[3];
+  S.rff = nullptr; S.k_rf = 0;
   return S;
+}
+
+// nh_utils.F90:356-368: the Rayleigh table is set up ONCE, by the first solver call of the context, with that call's dt (the
+// reference keeps it in SAVEd module variables); pfull as fv_dynamics.F90:276-280 with p_ref = 1.e5 (fv_arrays.F90 default)
+static int rayleigh_setup(fv3_ctx* c, double dt, SolverIn& S) {
+  const fv3_flags_t& f = c->f;
+  if (!(f.fast_tau_w_sec > 1.e-5)) return 0;
+  const int km = c->L.npz;
+  if (!c->d_rff) {
+    std::vector<double> rff(km, 1.0);
+    c->k_rf = 0;
+    for (int k = 1; k <= km; k++) {
+      const double ph1 = c->ak[k - 1] + c->bk[k - 1] * 1.e5, ph2 = c->ak[k] + c->bk[k] * 1.e5;
+      const double pfull = (ph2 - ph1) / log(ph2 / ph1);
+      if (pfull > f.rf_cutoff) break;
+      c->k_rf = k;
+      const double sn = sin(0.5 * f.pi * log(f.rf_cutoff / pfull) / log(f.rf_cutoff / f.ptop));
+      rff[k - 1] = 1.0 / (1.0 + dt / f.fast_tau_w_sec * (sn * sn));
+    }
+    FV3_CUDA(c, cudaMalloc(&c->d_rff, sizeof(double) * km));
+    FV3_CUDA(c, cudaMemcpy(c->d_rff, rff.data(), sizeof(double) * km, cudaMemcpyHostToDevice));
+  }
+  S.rff = c->d_rff; S.k_rf = c->k_rf;
+  return 0;
 }
 
 int stage_update_dz_c(fv3_ctx* c, double dt2) {
@@ -598,11 +628,15 @@ int stage_riem_solver_c(fv3_ctx* c, double dt2) {
   StageScope ts(c, "Riem_Solver_C");
   const Lay& L = c->L;
   if (c->f.a_imp <= 0.5) return fv3_fail(c, -2, "Riem_Solver_c: a_imp <= 0.5 (RIM_2D / SIM3p0) not supported");
-  if (c->f.fast_tau_w_sec > 1.e-5) return fv3_fail(c, -2, "Riem_Solver_c: fast_tau_w_sec not supported");
   SolverIn S = make_solver(c, dt2, 0);
+  { int rc = rayleigh_setup(c, dt2, S); if (rc) return rc; }
   S.delp = c->fld[FV3_DELPC]; S.pt = c->fld[FV3_PTC]; S.hgt = c->fld[FV3_GZ]; S.w = c->fld[FV3_OMGA]; S.ws = c->fld[FV3_WS3];
   const int n = L.ie - L.is + 3;
-#define RIEM_C(MK, UC) k_riem_c<MK, UC><<<col_blocks(n, n), CB, 0, c->stream>>>(L, S, c->fld[FV3_PHIS], c->fld[FV3_GZ], c->fld[FV3_PKC], c->f.grav)
+#define RIEM_C(MK, UC)                                                                                                                    \
+  do {                                                                                                                                    \
+    if (S.rff) k_riem_c<MK, UC, true><<<col_blocks(n, n), CB, 0, c->stream>>>(L, S, c->fld[FV3_PHIS], c->fld[FV3_GZ], c->fld[FV3_PKC], c->f.grav); \
+    else k_riem_c<MK, UC, false><<<col_blocks(n, n), CB, 0, c->stream>>>(L, S, c->fld[FV3_PHIS], c->fld[FV3_GZ], c->fld[FV3_PKC], c->f.grav);    \
+  } while (0)
   if (S.moist_kappa) { if (S.use_cond) RIEM_C(true, true); else RIEM_C(true, false); }
   else { if (S.use_cond) RIEM_C(false, true); else RIEM_C(false, false); }
 #undef RIEM_C
@@ -614,8 +648,9 @@ int stage_riem_solver3(fv3_ctx* c, double dt, int last_call) {
   StageScope ts(c, "Riem_Solver3");
   const Lay& L = c->L;
   if (c->f.a_imp <= 0.5) return fv3_fail(c, -2, "Riem_Solver3: a_imp <= 0.5 (RIM_2D / SIM3) not supported");
-  if (c->f.fast_tau_w_sec > 1.e-5 || c->f.d2bg_zq > 0.0001) return fv3_fail(c, -2, "Riem_Solver3: fast_tau_w_sec / d2bg_zq not supported");
+  if (c->f.d2bg_zq > 0.0001) return fv3_fail(c, -2, "Riem_Solver3: d2bg_zq (imp_diff_w) not supported");
   SolverIn S = make_solver(c, dt, 1);
+  { int rc = rayleigh_setup(c, dt, S); if (rc) return rc; }
   S.delp = c->fld[FV3_DELP]; S.pt = c->fld[FV3_PT]; S.hgt = c->fld[FV3_ZH]; S.w = c->fld[FV3_W]; S.ws = c->fld[FV3_WS];
   const int n = L.ie - L.is + 1;
   // zs = phis*rgrav (dyn_core.F90:247-251) into scr[5]
@@ -624,13 +659,15 @@ int stage_riem_solver3(fv3_ctx* c, double dt, int last_call) {
     k_zs<<<grd2, blk2, 0, c->stream>>>(L, c->fld[FV3_PHIS], c->scr[5], 1.0 / c->f.grav);
     c->launches++;
   }
-#define RIEM_3(MK, UC)                                                                                                              \
-  k_riem3<MK, UC><<<col_blocks(n, n), CB, 0, c->stream>>>(L, S, c->scr[5], c->fld[FV3_ZH], c->fld[FV3_W], c->fld[FV3_DELZ], c->fld[FV3_PKC], \
-                                                         c->fld[FV3_PK3], c->fld[FV3_PK], c->fld[FV3_PE], c->fld[FV3_PELN], last_call,      \
-                                                         c->f.beta < -0.1 ? 1 : 0, c->f.use_logp)
+#define RIEM_3A(MK, UC, RF)                                                                                                         \
+  k_riem3<MK, UC, RF><<<col_blocks(n, n), CB, 0, c->stream>>>(L, S, c->scr[5], c->fld[FV3_ZH], c->fld[FV3_W], c->fld[FV3_DELZ], c->fld[FV3_PKC], \
+                                                             c->fld[FV3_PK3], c->fld[FV3_PK], c->fld[FV3_PE], c->fld[FV3_PELN], last_call,      \
+                                                             c->f.beta < -0.1 ? 1 : 0, c->f.use_logp)
+#define RIEM_3(MK, UC) do { if (S.rff) RIEM_3A(MK, UC, true); else RIEM_3A(MK, UC, false); } while (0)
   if (S.moist_kappa) { if (S.use_cond) RIEM_3(true, true); else RIEM_3(true, false); }
   else { if (S.use_cond) RIEM_3(false, true); else RIEM_3(false, false); }
 #undef RIEM_3
+#undef RIEM_3A
   c->launches++;
   return 0;
 }

@@ -22,6 +22,8 @@ struct fv3o_ctx {
   std::string err;
   // per-k damping arrays shared between d_sw and update_dz_d (dyn_core.F90:186-187)
   std::vector<double> damp_vt; std::vector<int> nord_v;
+  // Rayleigh damping table of nh_utils (SAVEd rff, k_rf, RFw_initialized, nh_utils.F90:53-55)
+  std::vector<double> rff; int k_rf = 0; bool rf_init = false;
   explicit fv3o_ctx(const fv3_bounds_t& b_, const fv3_grid_t& g_, const fv3_flags_t& f_) : b(b_), g(g_), f(f_) {}
 };
 
@@ -156,10 +158,28 @@ int fv3o_update_dz_c(fv3o_ctx* c, double dt2) {
   return 0;
 }
 // dyn_core.F90:531-536
+// nh_utils.F90:356-368: set up once, by the first solver call, with that call's dt.  pfull as fv_dynamics.F90:276-280 with
+// p_ref = 1.e5 (fv_arrays.F90 default).
+static void rayleigh_init(fv3o_ctx* c, double dt) {
+  if (c->rf_init || !(c->f.fast_tau_w_sec > 1.e-5)) return;
+  c->rf_init = true;
+  const int km = c->b.npz;
+  c->rff.assign(km, 1.0); c->k_rf = 0;
+  for (int k = 1; k <= km; k++) {
+    const double ph1 = c->ak[k - 1] + c->bk[k - 1] * 1.e5, ph2 = c->ak[k] + c->bk[k] * 1.e5;
+    const double pfull = (ph2 - ph1) / std::log(ph2 / ph1);
+    if (pfull > c->f.rf_cutoff) break;
+    c->k_rf = k;
+    const double sn = std::sin(0.5 * c->f.pi * std::log(c->f.rf_cutoff / pfull) / std::log(c->f.rf_cutoff / c->f.ptop));
+    c->rff[k - 1] = 1.0 / (1.0 + dt / c->f.fast_tau_w_sec * (sn * sn));
+  }
+}
 int fv3o_riem_solver_c(fv3o_ctx* c, double dt2) {
   Bd bd(c->b);
   Consts k{c->f.rdgas, c->f.cp_air, c->f.grav, c->f.kappa, c->f.radius, c->f.omega, c->f.pi};
   const int ms = std::max(1, c->f.m_split / 2);
+  rayleigh_init(c, dt2);
+  if (c->rf_init) { k.rff = c->rff.data(); k.k_rf = c->k_rf; }
   riem_solver_c(ms, dt2, bd.is, bd.ie, bd.js, bd.je, bd.npz, bd.ng, c->f.kappa, F3(c, FV3_CAPPA), c->f.cp_air, c->f.ptop,
                 F2(c, FV3_PHIS), F3(c, FV3_OMGA), F3(c, FV3_PTC), F3(c, FV3_QCON), F3(c, FV3_DELPC), F3(c, FV3_GZ),
                 F3(c, FV3_PKC), F2(c, FV3_WS3), c->f.p_fac, c->f.a_imp, c->f.use_cond != 0, c->f.moist_kappa != 0, k);
@@ -254,6 +274,8 @@ int fv3o_riem_solver3(fv3o_ctx* c, double dt, int last_call) {
   Bd bd(c->b);
   Consts k{c->f.rdgas, c->f.cp_air, c->f.grav, c->f.kappa, c->f.radius, c->f.omega, c->f.pi};
   std::vector<double> zs = zs_of(c);
+  rayleigh_init(c, dt);
+  if (c->rf_init) { k.rff = c->rff.data(); k.k_rf = c->k_rf; }
   riem_solver3(c->f.m_split, dt, bd.is, bd.ie, bd.js, bd.je, bd.npz, bd.ng, bd.isd, bd.ied, bd.jsd, bd.jed, c->f.kappa,
                F3(c, FV3_CAPPA), c->f.cp_air, c->f.ptop, V2(zs.data(), bd.isd, bd.jsd, bd.ied - bd.isd + 1), F3(c, FV3_QCON),
                F3(c, FV3_W), F3(c, FV3_DELZ), F3(c, FV3_PT), F3(c, FV3_DELP), F3(c, FV3_ZH), c->fld[FV3_PE].data(),

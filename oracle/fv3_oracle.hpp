@@ -175,7 +175,12 @@ void d_sw(V2 delpc, V2 delp, V2 ptc, V2 pt, V2 u, V2 v, V2 w, V2 uc, V2 vc, V2 u
           V2 z_rat, V2 heat_source, V2 diss_est, const DswArgs& a, const Grid& g, const Bd& bd);
 
 // ---- nh_utils.F90 / nh_core.F90 / dyn_core.F90 ----
-struct Consts { double rdgas, cp_air, grav, kappa, radius, omega, pi; };
+struct Consts {
+  double rdgas, cp_air, grav, kappa, radius, omega, pi;
+  // Rayleigh damping of w (fast_tau_w_sec > 0): nh_utils.F90 keeps rff(1:k_rf) as SAVEd module state, set up by the FIRST solver call
+  // with that call's dt (:356-368) and reused by every later one; the caller owns it here
+  const double* rff = nullptr; int k_rf = 0;
+};
 void update_dz_c(int is, int ie, int js, int je, int km, int ng, double dt, const double* dp0, V2 zs, V2 area,
                  V3 ut, V3 vt, V3 gz, V2 ws, const Bd& bd);
 void update_dz_d(int* ndif, double* damp, int hord, int is, int ie, int js, int je, int km, int ng, int npx,

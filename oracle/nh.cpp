@@ -158,7 +158,8 @@ struct S2 {
 
 // nh_utils.F90:1277-1394
 static void sim1_solver(double dt, int is, int ie, int km, double rgas, S2& gm2, S2& cp2, S2& pe, S2& dm2, S2& pm2,
-                        S2& pem, S2& w2, S2& dz2, S2& pt2, const double* ws /*ws[i-is]*/, double p_fac) {
+                        S2& pem, S2& w2, S2& dz2, S2& pt2, const double* ws /*ws[i-is]*/, double p_fac,
+                        const double* rff = nullptr, int k_rf = 0) {
   S2 aa(is, ie, km), bb(is, ie, km), dd(is, ie, km), w1(is, ie, km), g_rat(is, ie, km), gam(is, ie, km), pp(is, ie, km + 1);
   std::vector<double> p1v(ie - is + 1), betv(ie - is + 1);
   auto p1 = [&](int i) -> double& { return p1v[i - is]; };
@@ -212,6 +213,8 @@ static void sim1_solver(double dt, int is, int ie, int km, double rgas, S2& gm2,
   }
   for (int k = km - 1; k >= 1; k--)
     for (int i = is; i <= ie; i++) w2(i, k) = w2(i, k) - gam(i, k + 1) * w2(i, k + 1);
+  if (rff)   // Rayleigh damping of w, nh_utils.F90:1363-1371
+    for (int k = 1; k <= k_rf; k++) for (int i = is; i <= ie; i++) w2(i, k) = w2(i, k) * rff[k - 1];
   for (int i = is; i <= ie; i++) pe(i, 1) = 0.;
   for (int k = 1; k <= km; k++)
     for (int i = is; i <= ie; i++) pe(i, k + 1) = pe(i, k) + dm2(i, k) * (w2(i, k) - w1(i, k)) * rdt;
@@ -230,7 +233,8 @@ static void sim1_solver(double dt, int is, int ie, int km, double rgas, S2& gm2,
 
 // nh_utils.F90:1396-1537 (scale_m = 0)
 static void sim_solver(double dt, int is, int ie, int km, double rgas, S2& gm2, S2& cp2, S2& pe2, S2& dm2, S2& pm2,
-                       S2& pem, S2& w2, S2& dz2, S2& pt2, const double* ws, double alpha, double p_fac, double scale_m) {
+                       S2& pem, S2& w2, S2& dz2, S2& pt2, const double* ws, double alpha, double p_fac, double scale_m,
+                       const double* rff = nullptr, int k_rf = 0) {
   S2 aa(is, ie, km), bb(is, ie, km), dd(is, ie, km), w1(is, ie, km), wk(is, ie, km), g_rat(is, ie, km), gam(is, ie, km), pp(is, ie, km + 1);
   std::vector<double> p1v(ie - is + 1), wk1v(ie - is + 1), betv(ie - is + 1);
   auto p1 = [&](int i) -> double& { return p1v[i - is]; };
@@ -289,6 +293,8 @@ static void sim_solver(double dt, int is, int ie, int km, double rgas, S2& gm2, 
   }
   for (int k = km - 1; k >= 1; k--)
     for (int i = is; i <= ie; i++) w2(i, k) = w2(i, k) - gam(i, k + 1) * w2(i, k + 1);
+  if (rff)   // nh_utils.F90:1498-1506
+    for (int k = 1; k <= k_rf; k++) for (int i = is; i <= ie; i++) w2(i, k) = w2(i, k) * rff[k - 1];
   for (int i = is; i <= ie; i++) pe2(i, 1) = 0.;
   for (int k = 1; k <= km; k++)
     for (int i = is; i <= ie; i++)
@@ -340,7 +346,7 @@ void riem_solver_c(int ms, double dt, int is, int ie, int js, int je, int km, in
     std::vector<double> wsr(ie1 - is1 + 1);
     for (int i = is1; i <= ie1; i++) wsr[i - is1] = ws(i, j);
     // a_imp > 0.5 -> SIM1_solver (nh_utils.F90:456-458); other solvers out of contract
-    sim1_solver(dt, is1, ie1, km, c.rdgas, gm2, cp2, pe2, dm, pm2, pem, w2, dz2, pt2, wsr.data(), p_fac);
+    sim1_solver(dt, is1, ie1, km, c.rdgas, gm2, cp2, pe2, dm, pm2, pem, w2, dz2, pt2, wsr.data(), p_fac, c.rff, c.k_rf);
     (void)a_imp;
     for (int k = 2; k <= km + 1; k++) for (int i = is1; i <= ie1; i++) pef(i, j, k) = pe2(i, k) + pem(i, k);
     for (int i = is1; i <= ie1; i++) gz(i, j, km + 1) = hs(i, j);
@@ -392,9 +398,9 @@ void riem_solver3(int ms, double dt, int is, int ie, int js, int je, int km, int
     std::vector<double> wsr(ie - is + 1);
     for (int i = is; i <= ie; i++) wsr[i - is] = ws(i, j);
     if (a_imp > 0.999)
-      sim1_solver(dt, is, ie, km, c.rdgas, gm2, cp2, pe2, dm, pm2, pem, w2, dz2, pt2, wsr.data(), p_fac);
+      sim1_solver(dt, is, ie, km, c.rdgas, gm2, cp2, pe2, dm, pm2, pem, w2, dz2, pt2, wsr.data(), p_fac, c.rff, c.k_rf);
     else
-      sim_solver(dt, is, ie, km, c.rdgas, gm2, cp2, pe2, dm, pm2, pem, w2, dz2, pt2, wsr.data(), a_imp, p_fac, 0.0);
+      sim_solver(dt, is, ie, km, c.rdgas, gm2, cp2, pe2, dm, pm2, pem, w2, dz2, pt2, wsr.data(), a_imp, p_fac, 0.0, c.rff, c.k_rf);
     for (int k = 1; k <= km; k++)
       for (int i = is; i <= ie; i++) { w(i, j, k) = w2(i, k); delz(i, j, k) = dz2(i, k); }
     if (last_call) {

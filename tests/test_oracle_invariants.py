@@ -291,3 +291,23 @@ def test_use_logp_formulation_is_a_small_perturbation(built):
         oc.close()
     du = max(float(np.abs(res[0][t] - res[1][t])[:, 3:-3, 3:-3].max()) for t in res[0])
     assert 0.0 < du < 0.02, du
+
+
+def test_rayleigh_damping_of_w_acts_above_rf_cutoff_only(built):
+    """fast_tau_w_sec > 0 (nh_utils.F90:356-368, 1363-1371): w of the levels with pfull <= rf_cutoff is multiplied by
+    rff(k) = 1/(1 + dt/tau sin^2(pi/2 log(rf_cutoff/pfull)/log(rf_cutoff/ptop))) in both vertical solvers; the levels below are
+    touched only through the coupling of the implicit solve."""
+    res = {}
+    for tau in (0.0, 300.0):
+        case = H.Case(12, 8, "A", state="baroclinic", flags_override=dict(fast_tau_w_sec=tau, rf_cutoff=3.0e3))
+        oc = H.OracleCube(case)
+        oc.dyn_core(600.0, 2)
+        res[tau] = np.abs(oc.eng[1].get("W")[:, 3:-3, 3:-3]).max(axis=(1, 2))
+        oc.close()
+    pe = case.ak + case.bk * 1.0e5
+    pfull = np.diff(pe) / np.diff(np.log(pe))
+    damped = pfull <= 3.0e3
+    assert damped.sum() >= 2 and (~damped).sum() >= 3
+    assert (res[300.0][damped] < res[0.0][damped]).all()
+    assert res[300.0][0] < 0.8 * res[0.0][0]                                    # strongest at the top
+    assert np.abs(res[300.0][~damped] / res[0.0][~damped] - 1.0)[1:].max() < 0.01
