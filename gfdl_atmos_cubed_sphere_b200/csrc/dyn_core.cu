@@ -34,7 +34,10 @@ extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, i
   if (!ctxs || nctx < 1 || n_split < 1) return -1;
   for (int a = 0; a < nctx; a++) {
     if (ctxs[a]->f.beta != 0.0) return fv3_fail(ctxs[a], -2, "dyn_core: beta != 0 (split_p_grad/one_grad_p) not supported");
-    if (ctxs[a]->f.d_ext > 0.0) return fv3_fail(ctxs[a], -2, "dyn_core: d_ext > 0 (external-mode damping) not supported");
+    // d_ext > 0 builds divg2 (dyn_core.F90:745-747, 791-797, 828-845), which only one_grad_p reads (:1021, :1030): with nh_p_grad
+    // (non-hydrostatic, beta = 0) it has no effect on any result and is accepted; the hydrostatic use is not built
+    if (ctxs[a]->f.d_ext > 0.0 && ctxs[a]->f.hydrostatic)
+      return fv3_fail(ctxs[a], -2, "dyn_core: d_ext > 0 with the hydrostatic one_grad_p (external-mode damping) not supported");
   }
   const double dt = bdt / (double)n_split;   // dyn_core.F90:223
   const double dt2 = 0.5 * dt;
