@@ -4,12 +4,15 @@
 Contract (see task statement / BASELINE.json):
   python bench.py --gpus N --steps K --warmup W            -> our CUDA path
   python bench.py --impl reference --gpus N --steps K ...  -> the reference's CPU path
-                                                              (C++ oracle port, all host threads)
-One "step" = one dyn_core call (n_split acoustic substeps) over the full cubed sphere
+                                                              (C++ oracle port, all host cores)
+One "step" of our arm = one dyn_core call (n_split acoustic substeps) over the full cubed sphere
 (6 faces, halo exchanges included).  metric = nx*ny*nz*n_split*ntiles / t.
 N=1: all 6 faces of C384L79 on one GPU (device-local halo gathers); N>1: faces are spread over
 min(N,6) ranks (one process per GPU, NCCL P2P for off-rank faces) -> "strong" scaling: total
 work is fixed at the full C384L79 cube.
+The reference arm runs the SAME configuration (C384L79 full cube, same flags, same initial state) on the host cores;
+one of its steps is a bounded sample of the workload: a dyn_core call of --ref-substeps (default 1) acoustic substeps
+(every substep costs the same), counted as that many cell updates.
 """
 from __future__ import annotations
 
@@ -26,17 +29,23 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "dyn_core cell-updates/sec (nx*ny*nz*n_split/s) at C384L79; d_sw HBM GB/s"
 
+from gfdl_atmos_cubed_sphere_b200.parallel import tiles_of_rank  # noqa: E402
 
-from gfdl_atmos_cubed_sphere_b200.parallel import tiles_of_rank, tile_rank_map  # noqa: E402
 
-
-# dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of ONE d_sw call on one face (bytes), from the ncu
-# metrics list profiles/r1_dsw_traffic_v10.csv (python profiles/dsw_traffic.py); key = (res, npz, flag-set)
-DSW_DRAM_TRAFFIC = {(384, 79, "A"): 4.952e9}
+def dsw_dram_traffic(n, npz, flagset):
+    """dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of ONE d_sw call on one face, from the committed
+    ncu metrics list of this round (profiles/r2_dsw_traffic.json, written by profiles/dsw_traffic.py --json from the csv of
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum ... profiles/prof_dsw.py`).  None when
+    the kernels changed after the last capture was committed (the file records the git blob of csrc/d_sw.cu it was taken on)."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r2_dsw_traffic.json")))
+        ent = rec.get(f"C{n}L{npz}{flagset}")
+        return (float(ent["bytes"]), ent) if ent else (None, None)
+    except Exception:
+        return None, None
 
 
 def dsw_algorithmic_bytes(n, npz, use_cond=False, d_con=False):
@@ -84,15 +93,22 @@ class ClockSampler:
 
 
 def build_case(n, npz, flagset="A"):
-    import harness as H
-    return H.Case(n, npz, flagset, state="baroclinic")
+    from gfdl_atmos_cubed_sphere_b200 import Case
+    return Case(n, npz, flagset, state="baroclinic")
+
+
+def workload_config(args):
+    """Identical in both arms: the configuration the metric is quoted on."""
+    return {"workload": f"C{args.res}L{args.npz} nonhydrostatic full cube (6 faces), n_split={args.n_split}, flag-set {args.flagset}, "
+                        f"JW baroclinic wave, set_eta L79 levels (var_hi, ptop 1 Pa), dt_atmos={args.dt_atmos}s",
+            "l2": "working set per stage (>= 6 fields x 96 MB per face) exceeds the 126 MB L2; no explicit flush",
+            "n_split": args.n_split, "faces": 6}
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    import harness as H
-    from gfdl_atmos_cubed_sphere_b200 import abi
+    from gfdl_atmos_cubed_sphere_b200 import abi, CudaCube
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -107,30 +123,9 @@ def run_ours(args):
     my_tiles = tiles_of_rank(rank, world)
     case = build_case(n, npz, args.flagset)
     lib = abi.load_library()
-    cube = None
-    if my_tiles:
-        cube = H.CudaCube(case, tiles=my_tiles, device=local, link=True) if (len(my_tiles) > 1 or world > 1) else None
-        if cube is None:
-            cube = H.CudaCube(case, tiles=my_tiles, device=local, link=False)
-        if len(my_tiles) == 1 and world > 1:
-            tl = (C.c_int * 1)(*my_tiles)
-            rc = lib[0].fv3_cube_link(cube.ctxs, tl, 1)
-            assert rc == 0
+    cube = CudaCube.for_rank(case, rank, world, device=local)
     if world > 1:
-        # our own NCCL communicator over the ACTIVE ranks; the unique id travels through torch.distributed
-        active = min(world, 6)
-        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            raw = C.create_string_buffer(128)
-            assert lib[0].fv3_nccl_unique_id(raw) == 0
-            idbuf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
-        dist.broadcast(idbuf, 0)
-        if my_tiles:
-            raw = bytes(idbuf.cpu().numpy().tobytes())
-            tr = (C.c_int * 6)(*tile_rank_map(world))
-            rc = lib[0].fv3_comm_init(cube.ctxs, len(my_tiles), C.c_char_p(raw), active, rank, tr)
-            if rc:
-                raise RuntimeError(f"fv3_comm_init rc={rc}: {cube.eng[my_tiles[0]].last_error()}")
+        CudaCube.attach_nccl(cube, rank, world)   # the library's own NCCL communicator over the active ranks
 
     def barrier():
         torch.cuda.synchronize()
@@ -191,7 +186,6 @@ def run_ours(args):
         sampler.start()
     barrier()
     # CUDA events on the library's own launch streams (torch events only see torch's stream)
-    t_wall0 = time.perf_counter()
     if cube is not None:
         lib[0].fv3_timer_start(cube.ctxs, len(my_tiles))
     for _ in range(args.steps):
@@ -202,7 +196,6 @@ def run_ours(args):
         lib[0].fv3_timer_stop(cube.ctxs, len(my_tiles), C.byref(ms))
         t_wall = ms.value / 1e3
     barrier()
-    t_host = time.perf_counter() - t_wall0
     clocks = sampler.finish() if sampler else None
     stage_ms = {}
     launches = 0
@@ -273,20 +266,20 @@ def run_ours(args):
         which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6650 GB/s)"
         alg = dsw_algorithmic_bytes(n, npz, bool(case.flags.get("use_cond")), case.flags.get("d_con", 0) > 1e-5)
         achieved = (alg / 1e9) / (dsw_solo_ms / 1e3) if dsw_solo_ms else None
+        traffic, traffic_src = dsw_dram_traffic(n, npz, args.flagset)
+        cfg = workload_config(args)
+        cfg["faces_per_rank"] = len(tiles_of_rank(0, world))
         line = {
             "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C{n}L{npz} nonhydrostatic full cube (6 faces), n_split={n_split}, flag-set {args.flagset}, "
-                                   f"JW baroclinic wave, set_eta L79 levels (var_hi, ptop 1 Pa), dt_atmos={bdt}s; faces/rank={len(tiles_of_rank(0, world))}",
-                       "l2": "working set per stage (>= 6 fields x 96 MB per face) exceeds the 126 MB L2; no explicit flush",
-                       "n_split": n_split, "faces": 6},
+            "config": cfg,
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": int(hb[0].item()),
                     "d2h_bytes_per_step": int(hb[1].item())},
             "roofline": {"bound": "hbm", "kernel": "d_sw (all kernels of one batched-over-k d_sw call on one face)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": DSW_DRAM_TRAFFIC.get((n, npz, args.flagset)), "peak_source": which, "algorithmic_bytes_per_launch": alg,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": which, "algorithmic_bytes_per_launch": alg,
                          "ms_per_launch": dsw_solo_ms,
                          # secondary ceiling: fp64 CUDA-core throughput.  FLOP model: 1.1 kFLOP per cell and d_sw call
                          # (4-5 fv_tp_2d + 2 momentum PPM sweeps + damping); peak = DFMA rate measured with
@@ -298,57 +291,65 @@ def run_ours(args):
             "clocks": clocks,
         }
         if args.cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, steps=3)   # ~10 s of CPU work on the 16 host threads (3 x 3.2 s)
+            # bounded sample of the SAME workload: 2 acoustic substeps of the C384L79 cube on all host cores (~10-25 s)
+            del pinned
+            line["cpu_baseline"] = cpu_reference(args, case, steps=2, warmup=1, budget_s=40.0)[0]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, res=None, steps=1):
-    """The oracle port (fast build, OpenMP over k / j like the reference) on the host cores,
-    on a bounded sample of the same workload: the full cube at C{res}L{npz}, one dyn_core call."""
-    import harness as H
-    res = res or args.cpu_res
-    case = build_case(res, args.npz, args.flagset)
-    oc = H.OracleCube(case, fast=True)
+def cpu_reference(args, case=None, steps=5, warmup=1, budget_s=200.0):
+    """The oracle port (timing build: -O3, OpenMP over k / j like the reference's own threading, automatic arrays from a
+    per-thread stack, 6-tile halo exchange inside the library) on ALL host cores, on the configuration of the metric.
+    One step = one dyn_core call of --ref-substeps acoustic substeps (bounded sample: every substep costs the same).
+    Returns (cpu_baseline dict, executed steps, seconds per step)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import harness as H   # test infrastructure: the one place bench.py executes oracle/
+    case = case or build_case(args.res, args.npz, args.flagset)
     lib = H.load_oracle(fast=True)[0]
-    cores = lib.fv3o_max_threads()
-    bdt = args.dt_atmos * res / args.res   # same Courant number as the headline resolution
-    oc.dyn_core(bdt, 1)                    # warm-up (first touch)
-    best = None
+    cores = int(lib.fv3o_use_all_cores())    # torchrun exports OMP_NUM_THREADS=1 to its workers: take every core anyway
+    oc = H.OracleCube(case, fast=True)
+    ns = max(1, args.ref_substeps)
+    bdt = args.dt_atmos * ns / args.n_split   # same acoustic time step as the GPU arm
+    t0 = time.perf_counter()
+    for _ in range(max(1, warmup)):
+        oc.dyn_core(bdt, ns)                  # first touch of every array, thread pool start
+    t_warm = (time.perf_counter() - t0) / max(1, warmup)
+    steps_exec = int(max(1, min(steps, budget_s // max(t_warm, 1e-3))))
     timers = {}
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        oc.dyn_core(bdt, args.n_split, timers)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
+    t0 = time.perf_counter()
+    for _ in range(steps_exec):
+        oc.dyn_core(bdt, ns, timers)
+    wall = time.perf_counter() - t0
     oc.close()
-    cells = res * res * args.npz * args.n_split * 6
-    return {"value": cells / best, "unit": "cell-updates/s", "cores": int(cores), "kind": "port",
-            "sample": f"full cube C{res}L{args.npz}, one dyn_core call of n_split={args.n_split} substeps "
-                      f"(C++ oracle -O3 -march=x86-64-v3 -fopenmp, NumPy halo exchange; cell-updates/s is "
-                      f"resolution-independent to first order), best of {steps} calls, wall {best:.2f}s",
-            "wall_s": best, "stage_seconds": {k: round(v, 3) for k, v in timers.items()}}
+    cells = args.res * args.res * args.npz * ns * 6
+    stage_s = sum(timers.values())
+    cb = {"value": cells * steps_exec / wall, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+          "sample": f"full cube C{args.res}L{args.npz} (the configuration of the metric), {steps_exec} dyn_core call(s) of {ns} acoustic "
+                    f"substep(s) each after {max(1, warmup)} warm-up call(s); C++ oracle port, timing build (-O3 -march=x86-64-v3 "
+                    f"-fopenmp, halo exchange inside the library), {cores} OpenMP threads",
+          "wall_s": wall, "steps": steps_exec, "substeps_per_step": ns,
+          "halo_and_driver_share": round(1.0 - stage_s / wall, 4),
+          "stage_seconds_per_step": {k: round(v / steps_exec, 4) for k, v in timers.items()}}
+    return cb, steps_exec, wall / steps_exec
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # warm-up steps are bounded samples too
-    for _ in range(min(args.warmup, 1)):
-        pass
-    cb = cpu_baseline(args, steps=max(1, min(args.steps, 2)))
+    cb, steps_exec, s_per_step = cpu_reference(args, steps=args.steps, warmup=max(1, min(args.warmup, 2)), budget_s=200.0)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "cell-updates/s",
-            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": cb["wall_s"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"C{args.res}L{args.npz} nonhydrostatic full cube (6 faces), n_split={args.n_split}, "
-                                   f"flag-set {args.flagset}; each step a bounded sample at C{args.cpu_res}"},
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps_exec, "steps_requested": args.steps,
+            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "the reference Fortran cannot be built here (no Fortran compiler, FMS not vendored): "
-                    "this arm times the C++ restatement (oracle port) on all host threads"}
+            "note": "the reference Fortran cannot be built here (no Fortran compiler, FMS not vendored): this arm times the C++ "
+                    "restatement (oracle port) on all host cores; one step = a bounded sample (ref-substeps acoustic substeps) of "
+                    "the same C384L79 workload, steps = the number of steps actually executed"}
     print(json.dumps(line))
 
 
@@ -363,7 +364,7 @@ def main():
     ap.add_argument("--n-split", dest="n_split", type=int, default=8)
     ap.add_argument("--dt-atmos", dest="dt_atmos", type=float, default=225.0)
     ap.add_argument("--flagset", default="A")
-    ap.add_argument("--cpu-res", dest="cpu_res", type=int, default=96)
+    ap.add_argument("--ref-substeps", dest="ref_substeps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -18,9 +18,17 @@
 #include "tp2d.cuh"
 #include "ppm.cuh"
 #include "tp_tile.cuh"
+#include "tp_line.cuh"
 #include <cmath>
 
 using namespace ppm;
+
+// FV3_TP_LINES=0 falls back to the first-generation tile kernel on the interior tiles too (A/B timing, bisecting)
+static bool use_line_kernels() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("FV3_TP_LINES"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
 
 #define TI 32
 #define TJ 8
@@ -745,6 +753,82 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_dsw_vort_uv(Lay L, DevGrid G, tp
   }
 }
 
+// ---- interior tiles, line-per-warp form (tp_line.cuh): delp, [w,] pt transported phase-major by a CTA that is persistent over
+// a chunk of levels.  Same arithmetic as k_dsw_transport (the mass fluxes of delp weight the other fields' fluxes in the outer
+// sweep, the flux divergences are applied in the epilogue); launched when no del-n flux and no q_con is in play.
+template <int FAM, int NF, int HORD>
+__global__ void __launch_bounds__(tp2::NT, 1) k_dsw_transport2(Lay L, DevGrid G, tpt::TileMap M, DswTr a, int nk, int kch) {
+  static_assert(NF == 2 || NF == 3, "fields: delp, [w,] pt");
+  const double* src[4 + NF];
+  src[0] = a.crx; src[1] = a.cry; src[2] = a.xfx; src[3] = a.yfx; src[4] = a.delp;
+  if (NF == 3) src[5] = a.w;
+  src[3 + NF] = a.pt;
+  int ord_in[NF], ord_ou[NF];
+  ord_ou[0] = a.hord_dp; if (NF == 3) ord_ou[1] = a.hord_vt; ord_ou[NF - 1] = a.hord_tm;
+#pragma unroll
+  for (int f = 0; f < NF; f++) ord_in[f] = (ord_ou[f] == 10) ? 8 : ord_ou[f];   // tp_core.F90:136-141
+  const int n1 = L.npz + 1;
+  // this thread's epilogue cell is the same on every level: its 1/area stays in a register
+  double ra = 0.;
+  {
+    const tp2::Geo T = tp2::make_geo(L, M);
+    if (T.wid < tp2::TY) ra = __ldg(G.rarea + tp2::gidx(T, T.i0 - 3 + T.lane, T.j0 + T.wid));
+  }
+  tp2::run_tile<FAM, NF, 2, tp2::W_MASS, HORD, 32>(L, G, M, src, nk, kch, ord_in, ord_ou,
+    [&](tp2::Smem<NF, 2>& S, const tp2::Geo& T, int k, long long ko, int r) {   // the flux capacitors' old values (read-modify-write, :928-940)
+      const int c = T.lane;
+      if (c < 3 || c > tp2::TX + 2) return;
+      const long long g = ko + tp2::gidx(T, T.i0 - 3 + c, T.j0 - 3 + r);
+      tpt::cp_async8(&S.ep[0][r * tp2::P + c], a.mfx + g);
+      tpt::cp_async8(&S.ep[1][r * tp2::P + c], a.mfy + g);
+    },
+    [&](tp2::Smem<NF, 2>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
+      const int c = T.lane;
+      if (c < 3 || c > tp2::TX + 2) return;
+      const int o = r * tp2::P + c;
+      const long long g = ko + tp2::gidx(T, T.i0 - 3 + c, T.j0 - 3 + r);
+      const double mx0 = S.qi[0][o], mx1 = S.qi[0][o + 1], my0 = S.qj[0][o], my1 = S.qj[0][o + tp2::P];
+      const double dp = S.in[b][tp2::A_Q][o];
+      a.mfx[g] = S.ep[0][o] + mx0;   // the tile's own west / south faces
+      a.mfy[g] = S.ep[1][o] + my0;
+      const double dpn = dp + (mx0 - mx1 + my0 - my1) * ra;
+#pragma unroll
+      for (int f = 1; f < NF; f++) {
+        const double div = (S.qi[f][o] - S.qi[f][o + 1] + S.qj[f][o] - S.qj[f][o + tp2::P]) * ra;
+        const double q = S.in[b][tp2::A_Q + f][o];
+        double v = (q * dp + div) / dpn;
+        if (NF == 3 && f == 1) {
+          if (a.dw && a.kdbl[KD_DAMP4_W * n1 + k] != 0.) v = v + __ldg(a.dw + g);
+          a.w_o[g] = v;
+        } else a.pt_o[g] = v;
+      }
+      a.delp_o[g] = dpn;
+    });
+}
+
+// 16 warps, two CTAs per SM (one transported field: the other CTA's sweeps hide this one's barriers and epilogue loads)
+template <int FAM, int HORD>
+__global__ void __launch_bounds__(512, 2) k_dsw_vort_uv2(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ vq, const double* __restrict__ crx,
+                                                       const double* __restrict__ cry, const double* __restrict__ xfx,
+                                                       const double* __restrict__ yfx, const double* __restrict__ u,
+                                                       const double* __restrict__ v, const double* __restrict__ ke,
+                                                       double* __restrict__ uo, double* __restrict__ vo, int hord_vt, int nk, int kch) {
+  const double* src[5] = {crx, cry, xfx, yfx, vq};
+  const int ord_ou[1] = {hord_vt}, ord_in[1] = {(hord_vt == 10) ? 8 : hord_vt};
+  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, 16>(L, G, M, src, nk, kch, ord_in, ord_ou,
+    [&](tp2::Smem<1, 0>&, const tp2::Geo&, int, long long, int) {},
+    [&](tp2::Smem<1, 0>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
+      const int c = T.lane;
+      if (c < 3 || c > tp2::TX + 2) return;
+      const int o = r * tp2::P + c;
+      const int gi = tp2::gidx(T, T.i0 - 3 + c, T.j0 - 3 + r);
+      const long long g = ko + gi;
+      const double kev = __ldg(ke + g);
+      vo[g] = __ldg(v + g) * __ldg(G.dy + gi) + kev - __ldg(ke + g + T.NI) - S.qi[0][o];
+      uo[g] = __ldg(u + g) * __ldg(G.dx + gi) + kev - __ldg(ke + g + 1) + S.qj[0][o];
+    });
+}
+
 // the fused kernels write the computational domain only: copy the halo frame so a frozen halo stays frozen
 struct FrameJob { const double* src; double* dst; int i1, j1; };   // computed box is (is:i1, js:j1), array box (isd:i1+ng', ...)
 struct FrameJobs { FrameJob j[6]; int n; };
@@ -775,7 +859,32 @@ static int launch_transport_t(fv3_ctx* c, const DswTr& a, int nk) {
   }
   tpt::TileMap Min, Mfr; int n_in, n_fr;
   tpt::tile_maps(c->L, Min, Mfr, n_in, n_fr);
-  if (n_in) k_dsw_transport<FAM, false><<<dim3(n_in, 1, nk), tpt::NT, sizeof(DswSmem), c->stream>>>(c->L, c->G, Min, a);
+  // interior tiles: the line-per-warp kernel when only delp, [w,] pt are transported and no del-n flux is added
+  const bool lines = FAM != 2 && use_line_kernels() && a.pt && !a.qcon && !a.dpx && !a.ptx && !a.qcx;
+  if (n_in && lines) {
+    constexpr int F2 = FAM == 2 ? 0 : FAM;
+    const int kch = tp2::level_chunk(nk), nch = (nk + kch - 1) / kch;
+    // the scheme is a compile-time constant of the kernel when every field uses the same common one (hord 10 / 8 / 5 / 6)
+    const bool same = a.hord_dp == a.hord_tm && (!a.w || a.hord_dp == a.hord_vt);
+    const int hs = same ? a.hord_dp : tp2::ORD_RT;
+#define TR2_LAUNCH(NF_, H_)                                                                                                        \
+    do {                                                                                                                           \
+      FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport2<F2, NF_, H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<NF_, 2>))); \
+      k_dsw_transport2<F2, NF_, H_><<<dim3(n_in, nch), tp2::NT, sizeof(tp2::Smem<NF_, 2>), c->stream>>>(c->L, c->G, Min, a, nk, kch);    \
+    } while (0)
+    if (a.w) {
+      if constexpr (F2 == 1) {
+        if (hs == 10) TR2_LAUNCH(3, 10);
+        else if (hs == 8) TR2_LAUNCH(3, 8);
+        else TR2_LAUNCH(3, tp2::ORD_RT);
+      } else {
+        if (hs == 5) TR2_LAUNCH(3, 5);
+        else if (hs == 6) TR2_LAUNCH(3, 6);
+        else TR2_LAUNCH(3, tp2::ORD_RT);
+      }
+    } else TR2_LAUNCH(2, tp2::ORD_RT);
+#undef TR2_LAUNCH
+  } else if (n_in) k_dsw_transport<FAM, false><<<dim3(n_in, 1, nk), tpt::NT, sizeof(DswSmem), c->stream>>>(c->L, c->G, Min, a);
   if (n_fr) k_dsw_transport<FAM, true><<<dim3(n_fr, 1, nk), tpt::NT, sizeof(DswSmem), c->stream>>>(c->L, c->G, Mfr, a);
   c->launches += (n_in ? 1 : 0) + (n_fr ? 1 : 0);
   return 0;
@@ -800,7 +909,27 @@ static int launch_vort_uv_t(fv3_ctx* c, const double* vq, const double* u, const
   }
   tpt::TileMap Min, Mfr; int n_in, n_fr;
   tpt::tile_maps(c->L, Min, Mfr, n_in, n_fr);
-  if (n_in) k_dsw_vort_uv<FM, false><<<dim3(n_in, 1, nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(
+  if (n_in && FM != 2 && use_line_kernels()) {
+    constexpr int F2 = FM == 2 ? 0 : FM;
+    const int kch = tp2::level_chunk(nk), nch = (nk + kch - 1) / kch;
+    const int h = c->f.hord_vt;
+#define VU2_LAUNCH(H_)                                                                                                            \
+    do {                                                                                                                          \
+      FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_vort_uv2<F2, H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<1>))); \
+      k_dsw_vort_uv2<F2, H_><<<dim3(n_in, nch), 512, sizeof(tp2::Smem<1>), c->stream>>>(                                         \
+          c->L, c->G, Min, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, h, nk, kch);    \
+    } while (0)
+    if constexpr (F2 == 1) {
+      if (h == 10) VU2_LAUNCH(10);
+      else if (h == 8) VU2_LAUNCH(8);
+      else VU2_LAUNCH(tp2::ORD_RT);
+    } else {
+      if (h == 5) VU2_LAUNCH(5);
+      else if (h == 6) VU2_LAUNCH(6);
+      else VU2_LAUNCH(tp2::ORD_RT);
+    }
+#undef VU2_LAUNCH
+  } else if (n_in) k_dsw_vort_uv<FM, false><<<dim3(n_in, 1, nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(
       c->L, c->G, Min, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, c->f.hord_vt);
   if (n_fr) k_dsw_vort_uv<FM, true><<<dim3(n_fr, 1, nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(
       c->L, c->G, Mfr, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, c->f.hord_vt);

@@ -10,6 +10,7 @@
 #include "tp2d.cuh"
 #include "ppm.cuh"
 #include "tp_tile.cuh"
+#include "tp_line.cuh"
 
 using namespace ppm;
 
@@ -79,6 +80,33 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, tpt::
   }
 }
 
+// interior tiles of the fused height update (update_dz_d, nh_utils.F90:282-299) in the line-per-warp form (tp_line.cuh)
+template <int FAM, int HORD>
+__global__ void __launch_bounds__(512, 2) k_tp_zn2(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ q, const double* __restrict__ crx,
+                                                 const double* __restrict__ cry, const double* __restrict__ xfx, const double* __restrict__ yfx,
+                                                 int ord_in_, int ord_ou_, tpt::ZnEpi Z, int nk, int kch) {
+  const double* src[5] = {crx, cry, xfx, yfx, q};
+  const int ord_in[1] = {ord_in_}, ord_ou[1] = {ord_ou_};
+  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, 16>(L, G, M, src, nk, kch, ord_in, ord_ou,
+    [&](tp2::Smem<1, 0>&, const tp2::Geo&, int, long long, int) {},
+    [&](tp2::Smem<1, 0>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
+      const int c = T.lane;
+      if (c < 3 || c > tp2::TX + 2) return;
+      const int o = r * tp2::P + c;
+      const int gi = tp2::gidx(T, T.i0 - 3 + c, T.j0 - 3 + r);
+      const double ar = S.area[o];
+      const double x0 = S.in[b][tp2::A_XFX][o], x1 = S.in[b][tp2::A_XFX][o + 1], y0 = S.in[b][tp2::A_YFX][o], y1 = S.in[b][tp2::A_YFX][o + tp2::P];
+      const double rax = ar + x0 - x1, ray = ar + y0 - y1;
+      double z = (S.in[b][tp2::A_Q][o] * ar + S.qi[0][o] - S.qi[0][o + 1] + S.qj[0][o] - S.qj[0][o + tp2::P]) / (rax + ray - ar);
+      const double coef = Z.kdbl ? Z.kdbl[Z.slot * (L.npz + 1) + k] : 0.;
+      if (coef != 0.) {
+        const long long g = ko + gi;
+        z = z + (Z.dfx[g] - Z.dfx[g + 1] + Z.dfy[g] - Z.dfy[g + T.NI]) * __ldg(G.rarea + gi);
+      }
+      Z.zn[ko + gi] = z;
+    });
+}
+
 int launch_tp2d(fv3_ctx* c, const Tp2d& a) {
   if (!hord_supported(a.hord, c->f.lim_fac)) return fv3_fail(c, -2, "fv_tp_2d: hord " + std::to_string(a.hord) + " not supported on the GPU path (supported: -5, 1..13; 1 only with lim_fac = 1)");
   const Lay& L = c->L;
@@ -97,6 +125,26 @@ int launch_tp2d(fv3_ctx* c, const Tp2d& a) {
   }
   const tpt::ZnEpi Z{a.zn, a.zn_dfx, a.zn_dfy, a.zn ? c->d_kdbl : nullptr, a.zn_slot};
   if (a.zn && (a.ra_x || a.ra_y || a.mfx)) return fv3_fail(c, -1, "fv_tp_2d: the fused height update takes no ra_x / ra_y / mfx");
+  // interior tiles of the fused height update: line-per-warp kernel (FV3_TP_LINES=0 keeps the first-generation tile kernel)
+  static int lines_on = -1;
+  if (lines_on < 0) { const char* e = getenv("FV3_TP_LINES"); lines_on = (e && e[0] == '0') ? 0 : 1; }
+  if (a.zn && n_in && lines_on && !hord_is_rare(a.hord)) {
+    const int kch = tp2::level_chunk(a.nk), nch = (a.nk + kch - 1) / kch;
+#define ZN2_LAUNCH(F_, H_)                                                                                                         \
+    do {                                                                                                                           \
+      FV3_CUDA(c, cudaFuncSetAttribute(k_tp_zn2<F_, H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<1>)));   \
+      k_tp_zn2<F_, H_><<<dim3(n_in, nch), 512, sizeof(tp2::Smem<1>), c->stream>>>(L, c->G, Min, a.q, a.crx, a.cry, a.xfx, a.yfx,   \
+                                                                                     ord_in, a.hord, Z, a.nk, kch);                 \
+    } while (0)
+    if (a.hord == 10) ZN2_LAUNCH(1, 10);
+    else if (a.hord == 8) ZN2_LAUNCH(1, 8);
+    else if (a.hord == 5) ZN2_LAUNCH(0, 5);
+    else if (a.hord == 6) ZN2_LAUNCH(0, 6);
+    else ZN2_LAUNCH(0, tp2::ORD_RT);   // -5
+#undef ZN2_LAUNCH
+    c->launches++;
+    n_in = 0;   // only the frame tiles are left for the general kernel
+  }
 #define TP_LAUNCH(FAM, EDGE, M, N)                                                                                           \
   k_tp_fused<FAM, EDGE><<<dim3(N, 1, a.nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(L, c->G, M, a.q, a.crx, a.cry, a.xfx, a.yfx, \
                                                                                       a.ra_x, a.ra_y, a.mfx, a.mfy, a.fx, a.fy, ord_in, a.hord, Z)

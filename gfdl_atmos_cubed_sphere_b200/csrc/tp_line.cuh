@@ -1,0 +1,348 @@
+// fv_tp_2d on a shared-memory tile, LINE-PER-WARP form (round 2) -- the interior-tile instance of the Lin-Rood transport.
+//
+// Reference semantics: model/tp_core.F90:85-241 (fv_tp_2d), :324-712 (xppm), :715-1152 (yppm) away from the cube edges.
+//
+// Why a second form (profiles/r1_dsw_ncu_v10.txt): the first tile kernel (tp_tile.cuh) evaluates every flux from scratch --
+// a thread re-derives the three dm / al values of the upwind cell from a 5-6 point window, so every limiter input is computed
+// three times and every q value is read from shared memory five times; the kernel sat on issue slots (66 %), the fp64 pipe
+// (42 %) and the shared-memory crossbar (46 %) at once.  Here a warp owns a whole 32-cell LINE of the 32 x 32 halo tile, one cell
+// per lane:
+//   * the PPM edge values are computed ONCE per cell (dm, al, then bl / br) and handed to the neighbour lane with warp
+//     shuffles (dm <- lane-1, al <- lane+1); each lane forms the two candidate fluxes its cell can feed (through its low face
+//     if the wind blows from the high side, through its high face otherwise) and the face picks one (one more shuffle);
+//   * x lines are tile rows (lane = column); y lines are tile COLUMNS (lane = row): every tile array has a pitch of 33 doubles,
+//     which makes both access patterns bank-conflict free, so the same routine serves both sweeps;
+//   * the inner flux of a face stays in a register of the lane that owns the face until the outer sweep averages it (the same
+//     warp runs the inner and the outer sweep of a line); q_i / q_j are formed by the inner line task itself (the flux of the
+//     next face arrives by shuffle), so a level needs three barriers in all -- whatever the number of fields;
+//   * several fields are transported PHASE-major (all inner sweeps, barrier, all outer sweeps): the Courant numbers, area
+//     fluxes and 1/ra of a line are loaded once for all fields;
+//   * a CTA (32 warps, one per SM) is persistent over a chunk of levels and double-buffers its inputs: level k+1 streams in with
+//     cp.async while level k computes; cell areas are staged once per tile.
+// Only tiles whose every flux (halo fluxes included) is an ordinary interior flux run here; the frame tiles keep the general
+// kernel of tp_tile.cuh (cube-edge operators, copy_corners views, bound tests).  Same tiling (26 x 26) as tp_tile.cuh.
+//
+// ra_x / ra_y: formed as area + xfx(i) - xfx(i+1) (tp_core.F90 callers in d_sw / update_dz_d, sw_core.F90:905-917); q_i / q_j
+// multiply by the reciprocal (one division per line and level instead of one per cell and field): <= 1 ulp from the divide.
+#pragma once
+#include "ppm.cuh"
+#include "tp_tile.cuh"
+#include <cstdlib>
+#include <cstdio>
+
+namespace tp2 {
+
+constexpr int TX = 26, TY = 26, QW = 32, QH = 32, P = 33;
+constexpr int NW = 32, NT = NW * 32;
+constexpr int ASZ = QH * P;      // doubles per tile array
+constexpr int GUARD = 72;        // >= 2*P + 2: the neighbour reads of lanes 0, 1, 30, 31 fall into the guards (values never used)
+static_assert(tpt::TX == TX && tpt::TY == TY, "tp_line.cuh and tp_tile.cuh must tile a face identically");
+
+enum { A_CRX = 0, A_CRY = 1, A_XFX = 2, A_YFX = 3, A_Q = 4 };
+// what the outer sweep leaves in qi (x faces) / qj (y faces):
+//   W_AREA: flux * area flux (xfx / yfx) for every field         (tp_core.F90:193-198 without mfx)
+//   W_MASS: field 0: flux * area flux = the mass flux; field f > 0: flux * mass flux   (sw_core.F90:928-940, tp_core.F90:213-226)
+//   W_RAW : the unweighted Lin-Rood flux 0.5 * (outer + inner)
+enum { W_AREA = 0, W_MASS = 1, W_RAW = 2 };
+
+template <int NF, int NEP = 0>
+struct Smem {
+  double g0[GUARD];
+  double in[2][4 + NF][ASZ];   // per level, double-buffered: crx, cry, xfx, yfx, q_0 .. q_{NF-1}
+  double area[ASZ];
+  double qi[NF][ASZ];          // q_i (tp_core.F90:150-159); after the outer sweep: the x fluxes
+  double qj[NF][ASZ];          // q_j (:171-178);            after the outer sweep: the y fluxes
+  double ep[NEP > 0 ? NEP : 1][NEP > 0 ? ASZ : 1];   // operands of the epilogue fetched with cp.async while the sweeps run
+  double g1[GUARD];
+};
+
+__device__ __forceinline__ double up1(double x) { return __shfl_up_sync(0xffffffffu, x, 1); }
+__device__ __forceinline__ double dn1(double x) { return __shfl_down_sync(0xffffffffu, x, 1); }
+
+// Unweighted upwind PPM fluxes through the LOW-side face of this lane's cell for NF fields of one 32-cell line held one cell per
+// lane.  o = this lane's element in every tile array, sa = element stride between lanes; cl / cr = Courant number of this
+// lane's low face / of the next lane's low face.  Valid for lanes 3..29 (cells 2..29 are reconstructed).  Same operations on
+// the same operands as ppm::flux_mono_aux / flux_unlim_aux.  FAM 1: iord 8, 10 (tp_core.F90:563-637, 701-707); FAM 0: 5, 6, -5
+// (:369-373, 491-558).  ORD: the scheme as a compile-time constant when every field uses the same one, else ORD_RT (ord[f]).
+// The routine is written stage by stage over the fields (every stage a fully unrolled loop over f) and without divergent
+// branches, so that the NF dependency chains -- each with four shuffle round trips -- interleave: with one CTA of 32 warps per SM
+// (64 registers per thread) instruction-level parallelism is what hides the fp64 / shuffle latencies (ncu, first version of
+// this file: 55 % issue-active with the fields evaluated one after the other).
+constexpr int ORD_RT = 99;
+template <int FAM, int NF, int ORD>
+__device__ __forceinline__ void line_fluxes(const double (*__restrict__ q)[ASZ], int o, int sa, int lane, double cl, double cr,
+                                            const int (&ord)[NF], double (&q0)[NF], double (&flux)[NF]) {
+  using namespace ppm;
+  if (FAM == 1) {
+    double qm[NF], qp[NF], dm0[NF], dmm[NF], dmp[NF], al0[NF], al1[NF], bl[NF], br[NF], FR[NF], FL[NF];
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      qm[f] = q[f][o - sa]; q0[f] = q[f][o]; qp[f] = q[f][o + sa];
+      dm0[f] = dm2(qm[f], q0[f], qp[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      dmm[f] = up1(dm0[f]);
+      if (ORD != 8) dmp[f] = dn1(dm0[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < NF; f++) al0[f] = 0.5 * (qm[f] + q0[f]) + r3 * (dmm[f] - dm0[f]);
+#pragma unroll
+    for (int f = 0; f < NF; f++) al1[f] = dn1(al0[f]);
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      const int iord = (ORD == ORD_RT) ? ord[f] : ORD;
+      // iord 8 (tp_core.F90:591-597)
+      const double xt = 2. * dm0[f];
+      const double bl8 = -fsign(mn(fabs(xt), fabs(al0[f] - q0[f])), xt);
+      const double br8 = fsign(mn(fabs(xt), fabs(al1[f] - q0[f])), xt);
+      if (ORD == 8) { bl[f] = bl8; br[f] = br8; continue; }
+      // iord 10 (:605-627 with the pmp / lac constraint), branch-free: the constraint applies where the parabola overshoots
+      double b_l = al0[f] - q0[f], b_r = al1[f] - q0[f];
+      const bool flat = fabs(dmm[f]) + fabs(dm0[f]) + fabs(dmp[f]) < near_zero_tp;
+      const bool over = fabs(3. * (b_l + b_r)) > fabs(b_l - b_r);
+      const double qm2 = q[f][o - 2 * sa], qp2 = q[f][o + 2 * sa];
+      const double dqm2 = 2. * (qm[f] - qm2), dqm1 = 2. * (q0[f] - qm[f]), dq0 = 2. * (qp[f] - q0[f]), dqp1 = 2. * (qp2 - qp[f]);
+      const double pmp_2 = dqm1, lac_2 = pmp_2 - 0.75 * dqm2;
+      const double brl = mn(max3(0., pmp_2, lac_2), mx(b_r, min3(0., pmp_2, lac_2)));
+      const double pmp_1 = -dq0, lac_1 = pmp_1 + 0.75 * dqp1;
+      const double bll = mn(max3(0., pmp_1, lac_1), mx(b_l, min3(0., pmp_1, lac_1)));
+      if (over) { b_l = bll; b_r = brl; }
+      if (flat) { b_l = 0.; b_r = 0.; }
+      if (ORD == ORD_RT && iord == 8) { b_l = bl8; b_r = br8; }
+      bl[f] = b_l; br[f] = b_r;
+    }
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      const double b0 = bl[f] + br[f];
+      FR[f] = q0[f] + (1. - cr) * (br[f] - cr * b0);   // through the high face, wind from this cell (Courant number > 0 there)
+      FL[f] = q0[f] + (1. + cl) * (bl[f] + cl * b0);   // through the low face, wind from this cell (Courant number <= 0)
+    }
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      const double FRm = up1(FR[f]);
+      flux[f] = cl > 0. ? FRm : FL[f];
+    }
+  } else {
+    double qm[NF], al0[NF], al1[NF], F1R[NF], F1L[NF];
+    bool smt[NF];
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      const int iord = (ORD == ORD_RT) ? ord[f] : ORD;
+      const double qm2 = q[f][o - 2 * sa], qp = q[f][o + sa];
+      qm[f] = q[f][o - sa]; q0[f] = q[f][o];
+      double a = p1 * (qm[f] + q0[f]) + p2 * (qm2 + qp);
+      if (iord < 0) a = mx(0., a);
+      al0[f] = a;
+    }
+#pragma unroll
+    for (int f = 0; f < NF; f++) al1[f] = dn1(al0[f]);
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      const int iord = (ORD == ORD_RT) ? ord[f] : ORD;
+      double bl = al0[f] - q0[f], br = al1[f] - q0[f], b0 = bl + br;
+      bool sm_;
+      if (iord == 5) sm_ = bl * br < 0.;
+      else if (iord == -5) {
+        sm_ = bl * br < 0.;
+        const double da1 = br - bl, a4 = -3. * b0;
+        if (fabs(da1) < -a4) {
+          if (q0[f] + 0.25 / a4 * (da1 * da1) + a4 * r12 < 0.) {
+            if (!sm_) { br = 0.; bl = 0.; b0 = 0.; }
+            else if (da1 > 0.) { br = -2. * bl; b0 = -bl; }
+            else { bl = -2. * br; b0 = -br; }
+          }
+        }
+      } else sm_ = 3. * fabs(b0) < fabs(bl - br);
+      smt[f] = sm_;
+      F1R[f] = (1. - cr) * (br - cr * b0);
+      F1L[f] = (1. + cl) * (bl + cl * b0);
+    }
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      const double F1Rm = up1(F1R[f]);
+      const unsigned sm = __ballot_sync(0xffffffffu, smt[f]);
+      const bool smtA = ((sm << 1) >> lane) & 1u;          // smt of the cell on the low side of the face
+      double fl = cl > 0. ? qm[f] : q0[f];
+      if (smtA || smt[f]) fl = fl + (cl > 0. ? F1Rm : F1L[f]);
+      flux[f] = fl;
+    }
+  }
+}
+
+// inner sweep of one line for all fields (tp_core.F90:143-148 / 164-169) + the intermediate field it feeds (:150-159 / 171-178).
+// o = this lane's element, sa = lane stride; cr_ / xf_ = Courant numbers / area fluxes of the sweep direction.
+template <int FAM, int NF, int ORD>
+__device__ __forceinline__ void inner_line(const double* __restrict__ cr_, const double* __restrict__ xf_, const double* __restrict__ area,
+                                           const double (*__restrict__ q)[ASZ], double (*__restrict__ qout)[ASZ], int o, int sa, int lane,
+                                           const int (&ord)[NF], double (&fin)[NF]) {
+  const double cl = cr_[o], cr = cr_[o + sa], xl = xf_[o], xr = xf_[o + sa], ar = area[o];
+  const double rra = 1. / (ar + xl - xr);
+  double q0[NF], g[NF];
+  line_fluxes<FAM, NF, ORD>(q, o, sa, lane, cl, cr, ord, q0, fin);
+#pragma unroll
+  for (int f = 0; f < NF; f++) g[f] = fin[f] * xl;
+#pragma unroll
+  for (int f = 0; f < NF; f++) {
+    const double g1 = dn1(g[f]);
+    qout[f][o] = (q0[f] * ar + g[f] - g1) * rra;
+  }
+}
+
+// outer sweep of one line for all fields, averaged with the inner flux and weighted (tp_core.F90:161, 180, 193-226); in place
+template <int FAM, int NF, int WMODE, int ORD>
+__device__ __forceinline__ void outer_line(const double* __restrict__ cr_, const double* __restrict__ xf_, double (*__restrict__ q)[ASZ], int o,
+                                           int sa, int lane, const int (&ord)[NF], const double (&fin)[NF]) {
+  const double cl = cr_[o], cr = cr_[o + sa];
+  const double xl = (WMODE == W_RAW) ? 1. : xf_[o];
+  double q0[NF], fo[NF];
+  // the fields interleaved (one staged evaluation) when their working set fits the 64 registers of a 1024-thread CTA: the
+  // branch-free iord = 10 constraint keeps ~12 doubles live per field, so there the fields go one after the other
+  constexpr bool SEQ = (FAM == 1 && ORD != 8 && NF > 1);
+  if (SEQ) {
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      const int o1[1] = {ord[f]};
+      double q1[1], f1[1];
+      line_fluxes<FAM, 1, ORD>(q + f, o, sa, lane, cl, cr, o1, q1, f1);
+      fo[f] = f1[0];
+    }
+  } else line_fluxes<FAM, NF, ORD>(q, o, sa, lane, cl, cr, ord, q0, fo);
+  double m = 0.;
+#pragma unroll
+  for (int f = 0; f < NF; f++) {
+    const double F = 0.5 * (fo[f] + fin[f]);
+    double out;
+    if (WMODE == W_RAW) out = F;
+    else if (WMODE == W_AREA || f == 0) { out = F * xl; m = out; }
+    else out = F * m;
+    q[f][o] = out;
+  }
+}
+
+struct Geo { int i0, j0, NI, ib, jb, lane, wid; };
+__device__ __forceinline__ int gidx(const Geo& T, int i, int j) { return (i + T.ib) + (j - T.jb) * T.NI; }
+
+__device__ __forceinline__ Geo make_geo(const Lay& L, const tpt::TileMap& M) {
+  Geo T;
+  int bx, by;
+  tpt::tile_xy(M, bx, by);
+  T.i0 = L.is + bx * TX; T.j0 = L.js + by * TY;
+  T.NI = L.NI; T.ib = FV3_IOFF - L.isd; T.jb = L.jsd;
+  T.lane = threadIdx.x & 31; T.wid = threadIdx.x >> 5;
+  return T;
+}
+
+// issue the inputs of one level into buffer b: 32 / NWC elements of every array per thread (row = warp (+ NWC), column = lane)
+template <int NF, int NEP, int NWC>
+__device__ __forceinline__ void stage_level(Smem<NF, NEP>& S, int b, const double* const (&src)[4 + NF], long long g, int so, int NI) {
+#pragma unroll
+  for (int i = 0; i < 32 / NWC; i++)
+#pragma unroll
+    for (int a = 0; a < 4 + NF; a++) tpt::cp_async8(&S.in[b][a][so + i * NWC * P], src[a] + g + (long long)i * NWC * NI);
+}
+
+#ifdef FV3_TP2_PROF
+#define TP2_CLK(i) do { const long long t_ = clock64(); prof[i] += t_ - tprev; tprev = t_; } while (0)
+#else
+#define TP2_CLK(i)
+#endif
+// The two sweeps of one staged level by a CTA of NWC warps (32: one line per warp and direction; 16: two).  Warp w owns the
+// x lines (tile rows) w, w + NWC and the y lines (tile columns) (w + NWC/2) mod NWC, + NWC -- the offset spreads the lines that
+// have no outer task (rows / columns 0..2, 29..31) over different warps.  On return (after a barrier) qi[f] / qj[f] hold the
+// fluxes through the west / south face of element [r][c] = cell (i0-3+c, j0-3+r): x faces valid for rows 3..28, columns 3..29;
+// y faces for rows 3..29, columns 3..28.
+template <int FAM, int NF, int NEP, int WMODE, int HORD, int NWC>
+__device__ __forceinline__ void compute_level(Smem<NF, NEP>& S, int b, const Geo& T, const int (&ord_in)[NF], const int (&ord_ou)[NF]
+#ifdef FV3_TP2_PROF
+                                              , long long (&prof)[8], long long& tprev
+#endif
+) {
+  constexpr int OI = (HORD == ORD_RT) ? ORD_RT : (HORD == 10 ? 8 : HORD), OO = HORD;   // tp_core.F90:136-141
+  constexpr int LPW = 32 / NWC;
+  double finx[LPW][NF], finy[LPW][NF];
+  const int yc0 = (T.wid + NWC / 2) & (NWC - 1);
+#pragma unroll
+  for (int i = 0; i < LPW; i++)
+    inner_line<FAM, NF, OI>(S.in[b][A_CRX], S.in[b][A_XFX], S.area, S.in[b] + A_Q, S.qj, (T.wid + i * NWC) * P + T.lane, 1, T.lane, ord_in, finx[i]);
+  TP2_CLK(1);
+#pragma unroll
+  for (int i = 0; i < LPW; i++)
+    inner_line<FAM, NF, OI>(S.in[b][A_CRY], S.in[b][A_YFX], S.area, S.in[b] + A_Q, S.qi, T.lane * P + yc0 + i * NWC, P, T.lane, ord_in, finy[i]);
+  TP2_CLK(2);
+  __syncthreads();
+  TP2_CLK(3);
+#pragma unroll
+  for (int i = 0; i < LPW; i++) {
+    const int r = T.wid + i * NWC;
+    if (r >= 3 && r <= TY + 2) outer_line<FAM, NF, WMODE, OO>(S.in[b][A_CRX], S.in[b][A_XFX], S.qi, r * P + T.lane, 1, T.lane, ord_ou, finx[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < LPW; i++) {
+    const int c = yc0 + i * NWC;
+    if (c >= 3 && c <= TX + 2) outer_line<FAM, NF, WMODE, OO>(S.in[b][A_CRY], S.in[b][A_YFX], S.qj, T.lane * P + c, P, T.lane, ord_ou, finy[i]);
+  }
+  TP2_CLK(4);
+  __syncthreads();
+  TP2_CLK(5);
+}
+
+// Persistent-over-k driver: the CTA (NWC warps) owns interior tile blockIdx.x and the levels [blockIdx.y*kch, +kch) of nk.
+//   src: the 4 + NF source arrays (level-0 based; the level offset is added here)
+//   pre(S, T, k, ko, r): called for every tile row r = 3..28 this warp finishes, right after level k is staged: may issue cp.async
+//        into S.ep[.][r*P + lane] for the operands its epilogue needs (they arrive while the sweeps run; no global-load latency
+//        is left in the epilogue, which nothing would overlap in a one-CTA-per-SM kernel)
+//   epi(S, b, T, k, ko, r): the per-level epilogue of row r (reads S.qi / S.qj / S.in[b][A_Q + f] / S.ep)
+//   HORD: the transport scheme of every field as a compile-time constant, or ORD_RT (per-field ord_in / ord_ou at run time)
+template <int FAM, int NF, int NEP, int WMODE, int HORD, int NWC, class Pre, class Epi>
+__device__ __forceinline__ void run_tile(const Lay& L, const DevGrid& G, const tpt::TileMap& M, const double* const (&src)[4 + NF], int nk, int kch,
+                                         const int (&ord_in)[NF], const int (&ord_ou)[NF], Pre&& pre, Epi&& epi) {
+  extern __shared__ __align__(16) unsigned char smem_raw2[];
+  Smem<NF, NEP>& S = *reinterpret_cast<Smem<NF, NEP>*>(smem_raw2);
+  const Geo T = make_geo(L, M);
+  const int k0 = blockIdx.y * kch, k1 = min(nk, k0 + kch);
+  if (k0 >= k1) return;
+  const int so = T.wid * P + T.lane;
+  const int g2 = gidx(T, T.i0 - 3 + T.lane, T.j0 - 3 + T.wid);
+#pragma unroll
+  for (int i = 0; i < 32 / NWC; i++) tpt::cp_async8(&S.area[so + i * NWC * P], G.area + g2 + i * NWC * T.NI);
+  stage_level<NF, NEP, NWC>(S, 0, src, (long long)k0 * L.plane + g2, so, T.NI);
+#ifdef FV3_TP2_PROF
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
+  for (int k = k0; k < k1; k++) {
+    const int b = (k - k0) & 1;
+    const long long ko = (long long)k * L.plane;
+    tpt::cp_async_wait_all();
+    __syncthreads();            // level k is in buffer b; every warp is done with the previous level (buffer b^1, qi, qj, ep)
+    if (k + 1 < k1) stage_level<NF, NEP, NWC>(S, b ^ 1, src, (long long)(k + 1) * L.plane + g2, so, T.NI);
+    if (NEP > 0) {
+#pragma unroll
+      for (int i = 0; i < 32 / NWC; i++) { const int r = 3 + T.wid + i * NWC; if (r <= TY + 2) pre(S, T, k, ko, r); }
+    }
+    TP2_CLK(0);
+#ifdef FV3_TP2_PROF
+    compute_level<FAM, NF, NEP, WMODE, HORD, NWC>(S, b, T, ord_in, ord_ou, prof, tprev);
+#else
+    compute_level<FAM, NF, NEP, WMODE, HORD, NWC>(S, b, T, ord_in, ord_ou);
+#endif
+    if (NEP > 0) tpt::cp_async_wait_all();   // this thread's own epilogue operands (read back by the thread that fetched them)
+#pragma unroll
+    for (int i = 0; i < 32 / NWC; i++) { const int r = 3 + T.wid + i * NWC; if (r <= TY + 2) epi(S, b, T, k, ko, r); }
+    TP2_CLK(6);
+  }
+#ifdef FV3_TP2_PROF
+  if (NF == 3 && blockIdx.x == 40 && blockIdx.y == 2 && T.lane == 0 && (T.wid % 5 == 0 || T.wid == 31))
+    printf("tp2prof warp %2d levels %d: wait+bar %lld | Bx %lld By %lld bar %lld | D %lld bar %lld | epi %lld  (clk per level)\n", T.wid, k1 - k0,
+           prof[0] / (k1 - k0), prof[1] / (k1 - k0), prof[2] / (k1 - k0), prof[3] / (k1 - k0), prof[4] / (k1 - k0), prof[5] / (k1 - k0), prof[6] / (k1 - k0));
+#endif
+}
+
+// interior tiles are launched as a (tiles, level chunks) grid of one-CTA-per-SM kernels
+static inline int level_chunk(int nk) {
+  static int kch = 0;
+  if (!kch) { const char* e = getenv("FV3_TP2_KCH"); kch = e ? atoi(e) : 8; if (kch < 1) kch = 1; }
+  return kch < nk ? kch : nk;
+}
+
+}  // namespace tp2

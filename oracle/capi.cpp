@@ -8,6 +8,7 @@
 #include "fv3_oracle.hpp"
 #include <string>
 #include <cstdio>
+#include <map>
 #include <omp.h>
 
 using namespace fv3o;
@@ -107,6 +108,8 @@ int fv3o_get_field(fv3o_ctx* c, int field, double* host) {
 int fv3o_sync(fv3o_ctx*) { return 0; }
 int fv3o_set_threads(int n) { omp_set_num_threads(n); return omp_get_max_threads(); }
 int fv3o_max_threads(void) { return omp_get_max_threads(); }
+// all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers)
+int fv3o_use_all_cores(void) { omp_set_num_threads(omp_get_num_procs()); return omp_get_max_threads(); }
 
 // tp_core.F90:85, batched over nk levels (same field conventions as fv3_fv_tp_2d)
 int fv3o_fv_tp_2d(fv3o_ctx* c, int nk, int hord, int use_mfx, int use_mass, int nord, double damp_c) {
@@ -298,6 +301,7 @@ int fv3o_pe_halo(fv3o_ctx* c) {
 int fv3o_gz_from_zh(fv3o_ctx* c) {
   Bd bd(c->b);
   V3 gz = F3(c, FV3_GZ), zh = F3(c, FV3_ZH);
+#pragma omp parallel for schedule(static)
   for (int k = 1; k <= bd.npz + 1; k++)
     for (int j = bd.js - 2; j <= bd.je + 2; j++)
       for (int i = bd.is - 2; i <= bd.ie + 2; i++) gz(i, j, k) = zh(i, j, k) * c->f.grav;
@@ -363,10 +367,63 @@ int fv3o_gz_init(fv3o_ctx* c) {
 // dyn_core.F90:491-521: zh = gz (it==1) or gz = zh
 int fv3o_copy_field(fv3o_ctx* c, int dst, int src) {
   if (c->fld[dst].size() != c->fld[src].size()) return -1;
-  c->fld[dst] = c->fld[src];
+  double* d = c->fld[dst].data(); const double* s = c->fld[src].data();
+  const ptrdiff_t n = (ptrdiff_t)c->fld[dst].size();
+#pragma omp parallel for schedule(static)
+  for (ptrdiff_t i = 0; i < n; i++) d[i] = s[i];
   return 0;
 }
-int fv3o_zero_field(fv3o_ctx* c, int f) { std::fill(c->fld[f].begin(), c->fld[f].end(), 0.0); return 0; }
+int fv3o_zero_field(fv3o_ctx* c, int f) {
+  double* d = c->fld[f].data(); const ptrdiff_t n = (ptrdiff_t)c->fld[f].size();
+#pragma omp parallel for schedule(static)
+  for (ptrdiff_t i = 0; i < n; i++) d[i] = 0.0;
+  return 0;
+}
+
+// ---- 6-tile halo exchange inside the library (the FMS group updates of dyn_core.F90:350-1169; FMS itself is not in the
+// reference checkout).  The index / sign tables are built by gfdl_atmos_cubed_sphere_b200/cubed_sphere.py (the tables the
+// NumPy exchange of the harness uses, tests/test_grid_and_halo.py validates them) and registered once per table id.
+struct HaloTab { std::vector<long long> dst, src; std::vector<int> src_tile, src_comp; std::vector<double> sign; };
+static std::map<int, std::vector<HaloTab>>& halo_registry() { static std::map<int, std::vector<HaloTab>> r; return r; }
+
+int fv3o_halo_set_table(int table_id, int tile, int comp, long long n, const long long* dst, const int* src_tile, const int* src_comp,
+                        const long long* src, const double* sign) {
+  if (tile < 1 || tile > 6 || comp < 0 || comp > 1) return -1;
+  auto& v = halo_registry()[table_id];
+  if (v.size() != 12) v.assign(12, HaloTab());
+  HaloTab& t = v[(tile - 1) * 2 + comp];
+  t.dst.assign(dst, dst + n); t.src.assign(src, src + n); t.src_tile.assign(src_tile, src_tile + n);
+  t.src_comp.assign(src_comp, src_comp + n); t.sign.assign(sign, sign + n);
+  return 0;
+}
+// ctxs[0..5] = tiles 1..6.  field_y < 0: scalar exchange of field_x; else the (x, y) pair with the table's component swaps / signs.
+// Sources are compute-domain points, destinations halo (or, for the boundary-only tables, north / east edge) points: never the
+// same point, so the gather runs in place.
+int fv3o_halo_exchange(fv3o_ctx** ctxs, int field_x, int field_y, int table_id) {
+  auto it = halo_registry().find(table_id);
+  if (it == halo_registry().end()) return -1;
+  const std::vector<HaloTab>& tabs = it->second;
+  const int ncomp = field_y < 0 ? 1 : 2;
+  const int fields[2] = {field_x, field_y};
+  const int nk = ctxs[0]->dim[field_x].nk;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int job = 0; job < 6 * ncomp; job++) {
+    for (int k = 0; k < nk; k++) {
+      const int t = job / ncomp, ci = job % ncomp;
+      const HaloTab& tb = tabs[t * 2 + ci];
+      const FieldDim& dd = ctxs[t]->dim[fields[ci]];
+      double* dp = ctxs[t]->fld[fields[ci]].data() + (size_t)k * dd.ni * dd.nj;
+      const size_t n = tb.dst.size();
+      for (size_t e = 0; e < n; e++) {
+        const int sf = fields[tb.src_comp[e]];
+        const fv3o_ctx* sc = ctxs[tb.src_tile[e] - 1];
+        const FieldDim& sd = sc->dim[sf];
+        dp[tb.dst[e]] = sc->fld[sf][(size_t)k * sd.ni * sd.nj + tb.src[e]] * tb.sign[e];
+      }
+    }
+  }
+  return 0;
+}
 
 // 1-D periodic xppm / yppm (interior formulas only, grid_type = 4): used to pin the oracle against the
 // NumPy restatement in the reference's docs/examples/tp_core.ipynb (tests/golden/ppm_notebook.npz)

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
 #include "../include/fv3_dyncore.h"
@@ -31,6 +32,7 @@ struct V2 {
   }
 };
 // Owning local array (Fortran automatic array).
+#ifndef FV3O_ARENA
 struct L2 : V2 {
   std::vector<double> buf;
   L2(int ilo, int ihi, int jlo, int jhi, double fill = 0.0)
@@ -38,7 +40,61 @@ struct L2 : V2 {
     p = buf.data(); i0 = ilo; j0 = jlo; ni = ihi - ilo + 1;
   }
   L2(const L2&) = delete;
+  void fill(double v) { std::fill(buf.begin(), buf.end(), v); }
 };
+#else
+// Timing build (-DFV3O_ARENA): like a Fortran automatic array the storage comes from a per-thread stack (LIFO bump
+// allocator, no malloc / munmap / page faults per level) and is NOT initialised unless a fill value is given.  With
+// FV3O_POISON=1 in the environment every such array is filled with signalling garbage (NaN) first, which is how
+// tests/test_oracle_invariants.py proves that no routine reads an element it did not write.
+struct Arena {
+  char* base = nullptr; size_t cap = 0, top = 0;
+  static Arena& get() { thread_local Arena a; return a; }
+  static bool poison() { static const bool p = [] { const char* e = std::getenv("FV3O_POISON"); return e && e[0] == '1'; }(); return p; }
+  double* push(size_t n) {
+    const size_t bytes = (n * sizeof(double) + 63) & ~(size_t)63;
+    if (!base) { cap = (size_t)1 << 30; base = (char*)std::malloc(cap); }   // 1 GiB of address space per thread, touched lazily
+    if (top + bytes > cap) return nullptr;
+    double* r = (double*)(base + top); top += bytes;
+    return r;
+  }
+  void pop(size_t n) { top -= (n * sizeof(double) + 63) & ~(size_t)63; }
+};
+struct L2 : V2 {
+  size_t n_; bool heap_;
+  void init(int ilo, int ihi, int jlo, int jhi) {
+    n_ = (size_t)(ihi - ilo + 1) * (size_t)(jhi - jlo + 1);
+    p = Arena::get().push(n_); heap_ = (p == nullptr);
+    if (heap_) p = (double*)std::malloc(n_ * sizeof(double));
+    i0 = ilo; j0 = jlo; ni = ihi - ilo + 1;
+  }
+  L2(int ilo, int ihi, int jlo, int jhi) {
+    init(ilo, ihi, jlo, jhi);
+    if (Arena::poison()) { const double nan = std::nan(""); for (size_t i = 0; i < n_; i++) p[i] = nan; }
+  }
+  L2(int ilo, int ihi, int jlo, int jhi, double fillv) { init(ilo, ihi, jlo, jhi); fill(fillv); }
+  ~L2() { if (heap_) std::free(p); else Arena::get().pop(n_); }
+  L2(const L2&) = delete;
+  void fill(double v) { for (size_t i = 0; i < n_; i++) p[i] = v; }
+};
+#endif
+// raw automatic 3-D work array (update_dz_d's crx_adv ... yfx_adv): zero-filled vector in the parity build, stack storage in the
+// timing build
+#ifndef FV3O_ARENA
+struct LRaw { std::vector<double> v; explicit LRaw(size_t n) : v(n) {} double* data() { return v.data(); } };
+#else
+struct LRaw {
+  double* p; size_t n_; bool heap_;
+  explicit LRaw(size_t n) : n_(n) {
+    p = Arena::get().push(n); heap_ = (p == nullptr);
+    if (heap_) p = (double*)std::malloc(n * sizeof(double));
+    if (Arena::poison()) { const double nan = std::nan(""); for (size_t i = 0; i < n; i++) p[i] = nan; }
+  }
+  ~LRaw() { if (heap_) std::free(p); else Arena::get().pop(n_); }
+  LRaw(const LRaw&) = delete;
+  double* data() { return p; }
+};
+#endif
 struct L1 {
   std::vector<double> buf; int i0;
   L1(int ilo, int ihi, double fill = 0.0) : buf((size_t)(ihi - ilo + 1), fill), i0(ilo) {}

@@ -106,8 +106,8 @@ void update_dz_d(int* ndif, double* damp, int hord, int is, int ie, int js, int 
   damp[km] = damp[km - 1];   // damp(km+1) = damp(km)
   ndif[km] = ndif[km - 1];
   const int isd = is - ng, ied = ie + ng, jsd = js - ng, jed = je + ng;
-  std::vector<double> b1((size_t)(ie + 1 - is + 1) * (jed - jsd + 1) * (km + 1)), b2(b1.size());
-  std::vector<double> b3((size_t)(ied - isd + 1) * (je + 1 - js + 1) * (km + 1)), b4(b3.size());
+  const size_t nb1 = (size_t)(ie + 1 - is + 1) * (jed - jsd + 1) * (km + 1), nb3 = (size_t)(ied - isd + 1) * (je + 1 - js + 1) * (km + 1);
+  LRaw b1(nb1), b2(nb1), b3(nb3), b4(nb3);
   V3 crx_adv(b1.data(), is, ie + 1, jsd, jed), xfx_adv(b2.data(), is, ie + 1, jsd, jed);
   V3 cry_adv(b3.data(), isd, ied, js, je + 1), yfx_adv(b4.data(), isd, ied, js, je + 1);
 #pragma omp parallel for schedule(static)

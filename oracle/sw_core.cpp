@@ -1404,8 +1404,8 @@ void d_sw(V2 delpc, V2 delp, V2 ptc, V2 pt, V2 u, V2 v, V2 w, V2 uc, V2 vc, V2 u
     damp4 = std::pow(a.damp_v * g.da_min_c, (double)(a.nord_v + 1));
     del6_vt_flux(a.nord_v, npx, npy, damp4, wk, vort, ut, vt, g, bd);
   } else if (a.do_diss_est) {
-    std::fill(ut.buf.begin(), ut.buf.end(), 0.);
-    std::fill(vt.buf.begin(), vt.buf.end(), 0.);
+    ut.fill(0.);
+    vt.fill(0.);
   }
 
   if (a.d_con > 1.e-5 || a.do_diss_est) {

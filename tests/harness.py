@@ -16,7 +16,7 @@ if ROOT not in sys.path:
 
 from gfdl_atmos_cubed_sphere_b200 import abi, grid as G, init_state as I, cubed_sphere as cs  # noqa: E402
 
-FLAGSETS = {"A": abi.FLAGSET_A, "B": abi.FLAGSET_B}
+from gfdl_atmos_cubed_sphere_b200.cube import Case, CudaCube, FLAGSETS, cube_grid  # noqa: E402,F401  (the product's driver)
 
 
 def load_oracle(fast=False):
@@ -34,42 +34,6 @@ def have_gpu():
         return torch.cuda.is_available()
     except Exception:
         return False
-
-
-@functools.lru_cache(maxsize=4)
-def cube_grid(n):
-    return G.make_cubed_sphere(n)
-
-
-class Case:
-    def __init__(self, n, npz, flagset="A", state="smooth", flags_override=None, state_kw=None):
-        self.n, self.npz = n, npz
-        self.tiles, self.bounds = cube_grid(n)
-        self.ak, self.bk = I.model_levels(npz)   # npz = 79: the reference set_eta levels (var_hi)
-        self.flags = dict(FLAGSETS[flagset]) if isinstance(flagset, str) else dict(flagset)
-        if flags_override:
-            self.flags.update(flags_override)
-        if state == "smooth":
-            self.states = I.smooth_state(self.tiles, self.bounds, npz)
-        elif state == "cosine_bell":   # SW_DYNAMICS test case 1 (BASELINE config 1a): npz = 1, flags.sw_test_case = 1
-            assert npz == 1
-            self.flags["sw_test_case"] = 1
-            self.states = I.cosine_bell(self.tiles, self.bounds, **(state_kw or {}))
-        else:
-            self.states = I.baroclinic_wave(self.tiles, self.bounds, npz, self.ak, self.bk)
-        self.consts = G.CONSTANTS
-
-    def engine(self, lib_prefix, tile=1, device=0):
-        lib, prefix = lib_prefix
-        return abi.Engine(lib, prefix, self.bounds, self.tiles[tile - 1], self.flags, self.npz, self.ak, self.bk,
-                          self.ak[0], self.consts, tile=tile, device=device)
-
-    def load_state(self, eng, tile=1, fields=("u", "v", "w", "pt", "delp", "q_con", "phis", "delz", "uc", "vc")):
-        st = self.states[tile - 1]
-        name = {"q_con": "QCON"}
-        for f in fields:
-            if f in st:
-                eng.put(name.get(f, f.upper()), st[f])
 
 
 def sub(eng, name, arr, i0, i1, j0, j1):
@@ -145,22 +109,59 @@ def parity_c_sw_d_sw(n=24, npz=8, flagset="A", dt=20.0, tile=1, flags_override=N
 class OracleCube:
     """Faces of the cube on the CPU oracle with the NumPy halo exchange."""
 
-    def __init__(self, case, tiles=(1, 2, 3, 4, 5, 6), fast=False):
+    def __init__(self, case, tiles=(1, 2, 3, 4, 5, 6), fast=False, numpy_halo=False):
         self.case = case
         self.tiles = list(tiles)
         lib = load_oracle(fast)
+        self.lib = lib
+        self.numpy_halo = numpy_halo or os.environ.get("FV3O_NUMPY_HALO") == "1" or len(self.tiles) != 6
         self.eng = {t: case.engine(lib, t) for t in self.tiles}
         self.ex = cs.Exchanger(case.n, 3) if len(self.tiles) == 6 else None
         for t in self.tiles:
             case.load_state(self.eng[t], t)
 
+    # the exchange runs inside the oracle library (fv3o_halo_exchange) on the tables of cubed_sphere.py; FV3O_NUMPY_HALO=1
+    # selects the NumPy gather on the same tables (tests/test_grid_and_halo.py compares the two)
+    _table_ids = {}
+
+    def _table(self, pos_x, pos_y=None, kind="scalar", boundary_only=False):
+        key = (self.case.n, pos_x, pos_y, kind, boundary_only)
+        ids = OracleCube._table_ids
+        if key not in ids:
+            tabs = self.ex.tables(pos_x, pos_y, kind, boundary_only=boundary_only)
+            tid = len(ids) + 1
+            fn = self.lib[0].fv3o_halo_set_table
+            fn.restype = C.c_int
+            for t in range(1, 7):
+                for ci, tb in enumerate(tabs[t]):
+                    dst = np.ascontiguousarray(tb.dst, dtype=np.int64); src = np.ascontiguousarray(tb.src, dtype=np.int64)
+                    st = np.ascontiguousarray(tb.src_tile, dtype=np.int32); sc = np.ascontiguousarray(tb.src_comp, dtype=np.int32)
+                    sg = np.ascontiguousarray(tb.sign, dtype=np.float64)
+                    rc = fn(C.c_int(tid), C.c_int(t), C.c_int(ci), C.c_longlong(dst.size), dst.ctypes.data_as(C.c_void_p),
+                            st.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p),
+                            sg.ctypes.data_as(C.c_void_p))
+                    assert rc == 0
+            ids[key] = tid
+        return ids[key]
+
+    def _lib_exchange(self, fx, fy, tid):
+        fn = self.lib[0].fv3o_halo_exchange
+        fn.restype = C.c_int
+        ctxs = (C.c_void_p * 6)(*[self.eng[t].ctx for t in (1, 2, 3, 4, 5, 6)])
+        rc = fn(ctxs, C.c_int(abi.FIELD_ID[fx]), C.c_int(abi.FIELD_ID[fy] if fy else -1), C.c_int(tid))
+        assert rc == 0, f"fv3o_halo_exchange rc={rc}"
+
     def _exchange_scalar(self, name, pos=cs.CENTER):
+        if not self.numpy_halo:
+            return self._lib_exchange(name, None, self._table(pos))
         arrs = [self.eng[t].get(name) for t in self.tiles]
         self.ex.scalar(arrs, pos)
         for t, a in zip(self.tiles, arrs):
             self.eng[t].put(name, a)
 
     def _exchange_pair(self, nx, ny, px, py, boundary_only=False):
+        if not self.numpy_halo:
+            return self._lib_exchange(nx, ny, self._table(px, py, "vector", boundary_only))
         xs = [self.eng[t].get(nx) for t in self.tiles]
         ys = [self.eng[t].get(ny) for t in self.tiles]
         self.ex.pair(xs, ys, px, py, kind="vector", boundary_only=boundary_only)
@@ -343,46 +344,6 @@ class OracleCube:
         for t in self.tiles:
             self.eng[t].put("DP1", st[t]["dp1"])
         return cmax
-
-    def close(self):
-        for e in self.eng.values():
-            e.close()
-
-
-class CudaCube:
-    """Faces of the cube on the CUDA library (all faces of this process on one GPU)."""
-
-    def __init__(self, case, tiles=(1, 2, 3, 4, 5, 6), device=0, link=True):
-        self.case = case
-        self.tiles = list(tiles)
-        self.lib = abi.load_library()
-        self.eng = {t: case.engine(self.lib, t, device) for t in self.tiles}
-        for t in self.tiles:
-            case.load_state(self.eng[t], t)
-        self.ctxs = (C.c_void_p * len(self.tiles))(*[self.eng[t].ctx for t in self.tiles])
-        if link and len(self.tiles) > 1:
-            tl = (C.c_int * len(self.tiles))(*self.tiles)
-            rc = self.lib[0].fv3_cube_link(self.ctxs, tl, len(self.tiles))
-            if rc:
-                raise RuntimeError(f"fv3_cube_link rc={rc}: {self.eng[self.tiles[0]].last_error()}")
-
-    def dyn_core(self, bdt, n_split):
-        fn = self.lib[0].fv3_dyn_core
-        fn.restype = C.c_int
-        rc = fn(self.ctxs, len(self.tiles), C.c_double(bdt), C.c_int(n_split), C.c_int(0))
-        if rc:
-            raise RuntimeError(f"fv3_dyn_core rc={rc}: " + "; ".join(self.eng[t].last_error() for t in self.tiles))
-        for t in self.tiles:
-            self.eng[t].sync()
-
-    def del2_cubed(self, field, cd, nmax):
-        fn = self.lib[0].fv3_del2_cubed_cube
-        fn.restype = C.c_int
-        rc = fn(self.ctxs, len(self.tiles), C.c_int(abi.FIELD_ID[field]), C.c_double(cd), C.c_int(nmax))
-        if rc:
-            raise RuntimeError(f"fv3_del2_cubed_cube rc={rc}: " + "; ".join(self.eng[t].last_error() for t in self.tiles))
-        for t in self.tiles:
-            self.eng[t].sync()
 
     def close(self):
         for e in self.eng.values():
