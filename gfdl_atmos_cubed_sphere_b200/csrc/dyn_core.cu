@@ -30,9 +30,14 @@ extern "C" int fv3_halo_wait(fv3_ctx** ctxs, int nctx);
   }
 
 extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, int flags) {
-  (void)flags;
   if (!ctxs || nctx < 1 || n_split < 1) return -1;
+  if (flags != 0) return fv3_fail(ctxs[0], -2, "dyn_core: flags must be 0 (no option bits are defined)");
   for (int a = 0; a < nctx; a++) {
+    // the loop below branches on the first context's switches: the linked faces must agree on them
+    const fv3_flags_t &f0 = ctxs[0]->f, &fa = ctxs[a]->f;
+    if (fa.hydrostatic != f0.hydrostatic || fa.sw_test_case != f0.sw_test_case || fa.d_con != f0.d_con || fa.use_cond != f0.use_cond ||
+        fa.nord != f0.nord || ctxs[a]->L.npz != ctxs[0]->L.npz || ctxs[a]->L.npx != ctxs[0]->L.npx)
+      return fv3_fail(ctxs[a], -1, "dyn_core: the linked contexts disagree on hydrostatic / sw_test_case / d_con / use_cond / nord / npx / npz");
     if (ctxs[a]->f.beta != 0.0) return fv3_fail(ctxs[a], -2, "dyn_core: beta != 0 (split_p_grad/one_grad_p) not supported");
     // d_ext > 0 builds divg2 (dyn_core.F90:745-747, 791-797, 828-845), which only one_grad_p reads (:1021, :1030): with nh_p_grad
     // (non-hydrostatic, beta = 0) it has no effect on any result and is accepted; the hydrostatic use is not built
@@ -75,6 +80,7 @@ extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, i
       FORALL(stage_d_sw(c, dt))
       if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;
       FORALL(stage_geopk(c, 0))
+      if (last_step) { FORALL(stage_copy_field(c, FV3_PK, FV3_PKC)) }   // :1001-1010: remap_step .and. hydrostatic: pk = pkc
       FORALL(stage_one_grad_p(c, dt))
       if (last_step && linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_UV_EDGE))) return rc;
       continue;

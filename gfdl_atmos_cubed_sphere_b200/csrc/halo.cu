@@ -147,6 +147,7 @@ struct HaloPlan {
   int tile_rank[6];        // rank owning each face (-1: absent -> halo frozen)
   int my_rank;
   void* comm;              // ncclComm_t
+  bool comm_owned;         // created by fv3_comm_init (destroyed with the context) / borrowed through fv3_comm_attach
   double *sendbuf[6], *recvbuf[6];
   size_t bufcap[6];
   std::vector<int*> dev_alloc;
@@ -227,7 +228,7 @@ static int halo_build(fv3_ctx* c) {
   if (!c->L.cube) return fv3_fail(c, -2, "halo exchange needs the cubed-sphere grid (grid_type < 3)");
   HaloPlan* hp = new HaloPlan();
   for (int t = 0; t < 6; t++) { hp->peer[t] = nullptr; hp->tile_rank[t] = -1; hp->sendbuf[t] = hp->recvbuf[t] = nullptr; }
-  hp->comm = nullptr; hp->my_rank = 0; for (int t = 0; t < 6; t++) hp->bufcap[t] = 0;
+  hp->comm = nullptr; hp->comm_owned = false; hp->my_rank = 0; for (int t = 0; t < 6; t++) hp->bufcap[t] = 0;
   hp->xstream = nullptr; hp->xdone = nullptr; hp->xpending = false;
   c->halo = hp;
   const int me = c->tile;
@@ -276,7 +277,7 @@ void halo_destroy(fv3_ctx* c) {
   HaloPlan* hp = c->halo;
   for (int* p : hp->dev_alloc) cudaFree(p);
   for (int t = 0; t < 6; t++) { cudaFree(hp->sendbuf[t]); cudaFree(hp->recvbuf[t]); }
-  if (hp->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(hp->comm);
+  if (hp->comm && hp->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(hp->comm);
   if (hp->xstream) cudaStreamDestroy(hp->xstream);
   if (hp->xdone) cudaEventDestroy(hp->xdone);
   delete hp;
@@ -387,14 +388,24 @@ int fv3_comm_init(fv3_ctx** ctxs, int nctx, const char* id128, int nranks, int r
   // all contexts share the communicator handle (only ctx 0 destroys it)
   for (int a = 1; a < nctx; a++) ctxs[a]->halo->comm = nullptr;
   ctxs[0]->halo->comm = comm;
+  ctxs[0]->halo->comm_owned = true;
   return 0;
 }
-int fv3_comm_attach(fv3_ctx* c, void* nccl_comm, const int tile_rank[6]) {
-  if (!c || !c->halo) return -1;
-  int rc = nccl_load(c);
+// a communicator owned by the caller (halo_destroy leaves it alone)
+int fv3_comm_attach(fv3_ctx** ctxs, int nctx, void* nccl_comm, int rank, const int tile_rank[6]) {
+  if (!ctxs || nctx < 1 || !nccl_comm || !tile_rank || rank < 0) return -1;
+  fv3_ctx* c0 = ctxs[0];
+  int rc = nccl_load(c0);
   if (rc) return rc;
-  c->halo->comm = nccl_comm;
-  for (int t = 0; t < 6; t++) c->halo->tile_rank[t] = tile_rank[t];
+  for (int a = 0; a < nctx; a++)
+    if (!ctxs[a]->halo) return fv3_fail(ctxs[a], -1, "comm_attach: call fv3_cube_link first");
+  for (int a = 0; a < nctx; a++) {
+    HaloPlan* hp = ctxs[a]->halo;
+    hp->comm = (a == 0) ? nccl_comm : nullptr;   // the exchange reads the handle of the first context (as fv3_comm_init sets it)
+    hp->comm_owned = false;
+    hp->my_rank = rank;
+    for (int t = 0; t < 6; t++) hp->tile_rank[t] = tile_rank[t];
+  }
   return 0;
 }
 

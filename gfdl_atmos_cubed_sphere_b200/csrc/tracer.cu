@@ -125,7 +125,21 @@ extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_ou
   const int npz = c0->L.npz;
   const bool linked = c0->halo != nullptr;
   std::vector<double> cmax(npz, 0.), tmp(npz);
-  std::vector<unsigned long long*> d_cmax(nctx);
+  std::vector<unsigned long long*> d_cmax(nctx, nullptr);
+  std::vector<double*> q_home(nctx);
+  for (int a = 0; a < nctx; a++) q_home[a] = ctxs[a]->fld[FV3_WORK_Q];
+  // whatever path leaves this function: the tracer pointer of every context is its own allocation again (the sub-cycles
+  // ping-pong fld[WORK_Q] with a scratch plane because the halo exchange reads fld[WORK_Q]) and the per-call tables are freed
+  struct Cleanup {
+    fv3_ctx** ctxs; int n; std::vector<double*>& home; std::vector<unsigned long long*>& tab;
+    ~Cleanup() {
+      for (int a = 0; a < n; a++) {
+        cudaSetDevice(ctxs[a]->device);
+        ctxs[a]->fld[FV3_WORK_Q] = home[a];
+        if (tab[a]) { cudaStreamSynchronize(ctxs[a]->stream); cudaFree(tab[a]); }
+      }
+    }
+  } cleanup{ctxs, nctx, q_home, d_cmax};
   // ---- xfx, yfx, cmax
   for (int a = 0; a < nctx; a++) {
     fv3_ctx* c = ctxs[a];
@@ -163,7 +177,7 @@ extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_ou
     nmax = std::max(nmax, nsplt[k]);
   }
   const int ord_in = (hord == 10) ? 8 : hord;
-  std::vector<double*> alt(nctx), q_home(nctx);
+  std::vector<double*> alt(nctx);
   for (int a = 0; a < nctx; a++) {
     fv3_ctx* c = ctxs[a];
     cudaSetDevice(c->device);
@@ -175,7 +189,6 @@ extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_ou
                                                                         c->fld[FV3_MFX], c->fld[FV3_MFY], d_frac);
     c->launches++;
     alt[a] = c->scr[0];               // ping-pong partner (a scratch plane: npz+1 levels >= npz)
-    q_home[a] = c->fld[FV3_WORK_Q];   // the tracer must end up in its own allocation again
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -217,7 +230,6 @@ extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_ou
       c->fld[FV3_WORK_Q] = q_home[a];
     }
     FV3_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaFree(d_cmax[a]);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fv3_fail(c, (int)e, std::string("tracer_2d: ") + cudaGetErrorString(e));
   }

@@ -235,9 +235,10 @@ enum fv3_halo_group {
 /* Link the six (or fewer) contexts of one process into a cube. tiles[i] is
  * the face number (1..6) of ctxs[i]. */
 int fv3_cube_link(fv3_ctx **ctxs, const int *tiles, int nctx);
-/* Attach an NCCL communicator (ncclComm_t passed as void*) and the
- * tile->rank map (6 ints, -1 = not present) for off-process faces. */
-int fv3_comm_attach(fv3_ctx *ctx, void *nccl_comm, const int tile_rank[6]);
+/* Attach a communicator the CALLER owns (ncclComm_t passed as void*; the library never
+ * destroys it) to the linked contexts of this process: `rank` = this process's rank in it,
+ * tile_rank = the rank owning each face (6 ints, -1 = face absent -> its halo stays frozen). */
+int fv3_comm_attach(fv3_ctx **ctxs, int nctx, void *nccl_comm, int rank, const int tile_rank[6]);
 /* Exchange one group for all linked contexts of this process. */
 int fv3_halo_exchange(fv3_ctx **ctxs, int nctx, int group);
 /* Overlapped form (start_group_halo_update / complete_group_halo_update of the reference, fv_mp_mod.F90:646-874): the
@@ -265,7 +266,9 @@ int fv3_plane_index(const fv3_ctx *ctx, int i, int j);
 /* dyn_core.F90:313-1286: n_split substeps on device-resident state for the
  * linked contexts of this process (nctx faces), halo exchanges included.
  * bdt is the large (k_split) time step; dt = bdt/n_split (dyn_core.F90:223).
- * flags: bit0 = capture each substep in a CUDA graph. */
+ * flags: must be 0 (no option bits are defined; the call fails with -2 otherwise).
+ * Hydrostatic branch: on the last substep pk = pkc on the compute domain (dyn_core.F90:1001-1010), so the
+ * pk a caller downloads for the remapping is current. */
 int fv3_dyn_core(fv3_ctx **ctxs, int nctx, double bdt, int n_split, int flags);
 
 /* fv_tracer2d.F90:49-295 tracer_2d_1L for ONE tracer (nq = 1, trdm = 0, id_divg_mean = 0), all faces of this process in

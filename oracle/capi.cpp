@@ -322,6 +322,15 @@ int fv3o_geopk(fv3o_ctx* c, int cg) {
         c->f.use_cond != 0, bd);
   return 0;
 }
+// dyn_core.F90:1001-1010 (remap_step .and. hydrostatic): pk = pkc on the compute domain
+int fv3o_pk_from_pkc(fv3o_ctx* c) {
+  Bd bd(c->b);
+  V3 pk = F3(c, FV3_PK), pkc = F3(c, FV3_PKC);
+  for (int k = 1; k <= bd.npz + 1; k++)
+    for (int j = bd.js; j <= bd.je; j++)
+      for (int i = bd.is; i <= bd.ie; i++) pk(i, j, k) = pkc(i, j, k);
+  return 0;
+}
 // dyn_core.F90:1909 one_grad_p (hydrostatic call :1019-1021, d_ext = 0)
 int fv3o_one_grad_p(fv3o_ctx* c, double dt) {
   Bd bd(c->b); Grid g(c->g, bd);

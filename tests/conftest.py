@@ -18,6 +18,6 @@ def built():
     """Oracle (and, where nvcc exists, the CUDA library) are built once per session."""
     import __graft_entry__ as g
     g.build_oracle()
-    if os.path.exists("/usr/local/cuda/bin/nvcc") and not os.path.exists(g.LIB):
-        g.build_cuda()
+    if os.path.exists("/usr/local/cuda/bin/nvcc"):
+        g.build_cuda()   # mtime-incremental: a no-op when the library is newer than every source and header
     return g

@@ -58,6 +58,11 @@ def compare(e_ref, e_new, regions):
         a = sub(e_new, f, e_new.get(f), i0, i1, j0, j1)
         b = sub(e_ref, f, e_ref.get(f), i0, i1, j0, j1)
         out[f] = scaled_err(a, b)
+    log = os.environ.get("FV3_PARITY_LOG")   # per-field error record of a test run (how the tolerances in tests/ were set)
+    if log:
+        import json
+        with open(log, "a") as fh:
+            fh.write(json.dumps({"test": os.environ.get("PYTEST_CURRENT_TEST", ""), "err": out}) + "\n")
     return out
 
 
@@ -231,6 +236,8 @@ class OracleCube:
                 run("D_SW", "d_sw", dt)
                 self.halo("DELP_PT")
                 run("GEOPK_D", "geopk", 0)
+                if last:
+                    self.all("pk_from_pkc")   # dyn_core.F90:1001-1010
                 run("PG_D", "one_grad_p", dt)
                 if last:
                     self.halo("UV_EDGE")

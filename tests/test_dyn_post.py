@@ -105,7 +105,7 @@ def test_cuda_dyn_core_with_dcon_heating(hydro):
     for t in oc.tiles:
         res = H.compare(oc.eng[t], gc.eng[t], {"PT": reg, "HEAT": reg, "PKZ": reg, "DELP": reg})
         for f, e in res.items():
-            assert e < (1e-9 if f != "HEAT" else 1e-7), (t, f, e)
+            assert e < 1e-10, (t, f, e)   # multi-substep tolerance of tests/test_gpu_parity.py (measured: heat_source 1.4e-12)
     hs = gc.eng[1].get("HEAT")
     assert np.abs(hs).max() > 0.0
     oc.close(); gc.close()

@@ -1,8 +1,18 @@
 """-m gpu: CUDA path vs CPU oracle through the C ABI, same seeded inputs.
 
-Tolerance (fp64, stated by north_star as "a stated fp64 tolerance"): max-abs error
-scaled by the field's max-abs value <= 1e-11 per kernel call, <= 1e-9 after a multi-substep
-dyn_core call.  (Not bit-exact: nvcc contracts a*b+c into FMA; limiter branches are exact.)
+Tolerance (fp64; north_star: "a stated fp64 tolerance"; SURVEY 8c: 1e-12 per call, 1e-10 after a multi-substep run): max-abs
+error scaled by the field's max-abs value.  Not bit-exact: nvcc contracts a*b+c into FMA, the oracle's parity build does not;
+limiter branches are exact.  Set from the per-field error record of a full B200 run (FV3_PARITY_LOG, profiles/r2_parity_errors.md):
+
+  per kernel call     1e-12   every horizontal operator: c_sw, d_sw, fv_tp_2d (all 14 schemes), del2_cubed, tracer_2d, a2b_ord4,
+                              halo exchange (measured <= 6e-14)
+                      1e-11   w, u, v right after a vertical solver / pressure-gradient stage (measured 5.9e-12 / 1.3e-12): w is a
+                              residual of two nearly balanced forces and is scaled here by max|w| ~ 0.1 m/s, i.e. 1e-12 m/s
+                              absolute; the pressure gradient differences pk*gz products four orders larger than the result
+                      1e-9    ws, ws3 = (zs - zh(km+1)) / dt: a difference of two nearly equal heights (nh_utils.F90:186, 306)
+  multi-substep run   1e-10   every prognostic and flux accumulator except w after 8 substeps at C16 (measured <= 6e-12) and after
+                              2 substeps at C96 / C192 / C384 L79 (measured <= 6.4e-11 in u, v)
+                      1e-9    w (measured 2.6e-10 relative to max|w| = 0.1 m/s at C96L79: 3e-11 m/s absolute)
 """
 import numpy as np
 import pytest
@@ -11,8 +21,17 @@ import harness as H
 from gfdl_atmos_cubed_sphere_b200 import abi
 
 pytestmark = pytest.mark.gpu
-TOL_STAGE = 1e-11
-TOL_RUN = 1e-9
+TOL_STAGE = 1e-12
+TOL_SOLVER = 1e-11     # w, u, v after a column-solver / pressure-gradient stage
+TOL_RUN = 1e-10
+TOL_RUN_W = 1e-9
+TOL_WS = 1e-9
+
+
+def _assert_run(res):
+    """multi-substep tolerance: 1e-10, w 1e-9 (see the header)"""
+    bad = {k: v for k, v in res.items() if not (v <= (TOL_RUN_W if k == "W" else TOL_RUN))}
+    assert not bad, f"parity exceeded {TOL_RUN} (w: {TOL_RUN_W}): {bad}"
 
 
 def _assert(res, tol):
@@ -105,15 +124,15 @@ def test_unsupported_hord_is_an_error():
 
 @pytest.mark.parametrize("flagset", ["A", "B"])
 def test_dyn_core_full_cube(flagset):
-    """6 faces, device-local halo exchange, 2 acoustic substeps vs the oracle + NumPy exchange."""
+    """6 faces, device-local halo exchange, 8 acoustic substeps (one dyn_core call of the headline n_split) vs the oracle."""
     case = H.Case(16, 6, flagset, state="baroclinic")
     oc = H.OracleCube(case)
     gc = H.CudaCube(case)
-    oc.dyn_core(800.0, 2)
-    gc.dyn_core(800.0, 2)
+    oc.dyn_core(3200.0, 8)
+    gc.dyn_core(3200.0, 8)
     for t in oc.tiles:
         res = H.compare(oc.eng[t], gc.eng[t], H.regions_state(case.bounds))
-        _assert(res, TOL_RUN)
+        _assert_run(res)
         for f in ("U", "W", "PT"):
             assert np.isfinite(gc.eng[t].get(f)).all() or True
     # the run must stay physical (no blow-up): |w| small, |u| ~ 35 m/s
@@ -188,7 +207,7 @@ def test_nonhydrostatic_stages_one_by_one():
             res = H.compare(oc.eng[t], gc.eng[t], regions)
             # ws = (zs - zh(km+1)) / dt is a difference of two nearly equal heights (nh_utils.F90:186,306): its
             # round-off is amplified by cancellation, so it gets the multi-step tolerance
-            bad = {k: v for k, v in res.items() if not (v <= (TOL_RUN if k in ("WS", "WS3") else TOL_STAGE))}
+            bad = {k: v for k, v in res.items() if not (v <= (TOL_WS if k in ("WS", "WS3") else TOL_SOLVER if k in ("W", "U", "V") else TOL_STAGE))}
             assert not bad, f"{stage}, face {t}: {bad}"
         for t in oc.tiles:               # re-synchronise: the next stage starts from identical inputs
             for f in sync_fields:
@@ -287,7 +306,7 @@ def test_hydrostatic_stages_and_config1b():
                                                "PE": (is_ - 1, ie + 1, js - 1, je + 1), "PELN": (is_, ie, js, je), "PKZ": (is_, ie, js, je)})
         _assert(res, TOL_STAGE)
         oc.eng[t].call("one_grad_p", 100.0); gc.eng[t].call("one_grad_p", 100.0)
-        _assert(H.compare(oc.eng[t], gc.eng[t], {"U": (is_, ie, js, je + 1), "V": (is_, ie + 1, js, je)}), TOL_STAGE)
+        _assert(H.compare(oc.eng[t], gc.eng[t], {"U": (is_, ie, js, je + 1), "V": (is_, ie + 1, js, je)}), TOL_SOLVER)
     oc.close(); gc.close()
     # the acoustic loop
     oc = H.OracleCube(case)
@@ -297,8 +316,12 @@ def test_hydrostatic_stages_and_config1b():
     for t in oc.tiles:
         res = H.compare(oc.eng[t], gc.eng[t], {"DELP": (is_, ie, js, je), "PT": (is_, ie, js, je), "U": (is_, ie, js, je + 1),
                                                "V": (is_, ie + 1, js, je), "MFX": (is_, ie + 1, js, je), "MFY": (is_, ie, js, je + 1),
-                                               "PKZ": (is_, ie, js, je), "PE": (is_ - 1, ie + 1, js, je)})
+                                               "PKZ": (is_, ie, js, je), "PE": (is_ - 1, ie + 1, js, je), "PK": (is_, ie, js, je)})
         _assert(res, TOL_RUN)
+        # pk = pkc on the last substep (dyn_core.F90:1001-1010): the pk a caller downloads for the remap is pe**kappa
+        pe = H.sub(gc.eng[t], "PE", gc.eng[t].get("PE"), is_, ie, js, je)          # (nj, npz+1, ni)
+        pk = H.sub(gc.eng[t], "PK", gc.eng[t].get("PK"), is_, ie, js, je)          # (npz+1, nj, ni)
+        assert np.abs(pk - np.transpose(pe, (1, 0, 2)) ** case.consts["kappa"]).max() / pk.max() < 1e-13
         # pe on its 1-wide ring, WITHOUT the four ring corners: those read the 3x3 corner halo of delp, which no exchange
         # fills and which the reference's in-place fill_4corners leaves in a sweep-dependent state (the CUDA path remaps
         # on the read side instead and never writes them); nothing reads pe there
@@ -308,10 +331,10 @@ def test_hydrostatic_stages_and_config1b():
     oc.close(); gc.close()
 
 
-@pytest.mark.parametrize("n", [96, 192])
+@pytest.mark.parametrize("n", [96, 192, 384])
 def test_dyn_core_baseline_config_sizes(n):
-    """BASELINE.json configs[1] and [2] resolutions (C96 L79, C192 L79, non-hydrostatic, fp64): two acoustic substeps of
-    the full cube against the oracle (fast OpenMP build of the same restatement: its FMA contraction is allowed for by the
+    """BASELINE.json configs[1], [2] and [3] (the headline) resolutions (C96 / C192 / C384 L79, non-hydrostatic, fp64): two
+    acoustic substeps of the full cube against the oracle (fast OpenMP build of the same restatement: its FMA contraction is allowed for by the
     multi-step tolerance).  The 6-GPU NCCL run of config [2] is bit-identical to this single-process run
     (tests/nccl_check.py), so one comparison covers both placements."""
     npz = 79
@@ -322,7 +345,7 @@ def test_dyn_core_baseline_config_sizes(n):
     oc.dyn_core(bdt, 2)
     gc.dyn_core(bdt, 2)
     for t in oc.tiles:
-        _assert(H.compare(oc.eng[t], gc.eng[t], H.regions_state(case.bounds)), TOL_RUN)
+        _assert_run(H.compare(oc.eng[t], gc.eng[t], H.regions_state(case.bounds)))
     oc.close(); gc.close()
 
 

@@ -1,13 +1,13 @@
-"""GPU tests of features whose device arithmetic is validated ON THE HOST against the oracle (tests/test_host_device_math.py:
-the kernels' own routines compiled __host__ __device__) but that have not had their first run on a B200 yet -- the round's GPU
-budget was spent when they were written.  They are expected to pass; `xfail(strict=False)` only keeps a first-run surprise from
-turning the whole suite red.  Remove the marker after the first green run (an XPASS in the report)."""
+"""GPU parity of the less common scheme / flag variants: hord_mt 1-4, 7, 9, 11 (general instantiation of k_dsw_ke), use_logp
+(pln_halo), fast_tau_w_sec > 0 (Rayleigh-damping instantiations of the column solvers).  Written at the end of round 1 with an
+xfail(strict=False) guard for their first B200 run; all passed on the round-1 driver run (GPUTEST_r01: 10 xpassed) and in every
+round-2 run, so the guard is gone and a regression here fails the suite."""
 import pytest
 
 import harness as H
 
 pytestmark = pytest.mark.gpu
-TOL_STAGE = 1e-11
+TOL_STAGE = 1e-12   # tolerances: see the header of tests/test_gpu_parity.py
 
 
 def _assert(res, tol):
@@ -15,7 +15,6 @@ def _assert(res, tol):
     assert not bad, f"parity exceeded {tol}: {bad}"
 
 
-@pytest.mark.xfail(strict=False, reason="host-validated (test_host_device_math), first B200 run pending")
 @pytest.mark.parametrize("hord_mt", [1, 2, 3, 4, 7, 9, 11])
 def test_d_sw_wind_schemes_beyond_5_6_8_10(hord_mt):
     """xtp_u / ytp_v (sw_core.F90:2154-2998) with the less common hord_mt: the general instantiation k_dsw_ke<true>; single-tile
@@ -24,7 +23,6 @@ def test_d_sw_wind_schemes_beyond_5_6_8_10(hord_mt):
     _assert(H.parity_c_sw_d_sw(n=56, npz=2, flagset="B", dt=10.0, flags_override=dict(hord_mt=hord_mt)), TOL_STAGE)
 
 
-@pytest.mark.xfail(strict=False, reason="pln_halo kernel variant: first B200 run pending")
 def test_dyn_core_use_logp():
     """use_logp = T: pk3 carries log(pe) (Riem_Solver3, nh_core.F90:222-230), pln_halo replaces pk3_halo (dyn_core.F90:955-959,
     1449-1496), nh_p_grad takes peln1 at the top (:1726)."""
@@ -33,11 +31,12 @@ def test_dyn_core_use_logp():
     oc, gc = H.OracleCube(case), H.CudaCube(case)
     oc.dyn_core(800.0, 2); gc.dyn_core(800.0, 2)
     for t in oc.tiles:
-        _assert(H.compare(oc.eng[t], gc.eng[t], H.regions_state(case.bounds)), 1e-9)
+        res = H.compare(oc.eng[t], gc.eng[t], H.regions_state(case.bounds))
+        _assert({k: v for k, v in res.items() if k != "W"}, 1e-10)
+        _assert({"W": res["W"]}, 1e-9)
     oc.close(); gc.close()
 
 
-@pytest.mark.xfail(strict=False, reason="RF instantiations of the column solvers: first B200 run pending")
 @pytest.mark.parametrize("a_imp", [1.0, 0.75])
 def test_dyn_core_rayleigh_damping_of_w(a_imp):
     """fast_tau_w_sec > 0 in SIM1_solver (a_imp = 1) and SIM_solver (0.75): k_riem_c<.,.,true> / k_riem3<.,.,true>."""
@@ -45,5 +44,7 @@ def test_dyn_core_rayleigh_damping_of_w(a_imp):
     oc, gc = H.OracleCube(case), H.CudaCube(case)
     oc.dyn_core(800.0, 2); gc.dyn_core(800.0, 2)
     for t in oc.tiles:
-        _assert(H.compare(oc.eng[t], gc.eng[t], H.regions_state(case.bounds)), 1e-9)
+        res = H.compare(oc.eng[t], gc.eng[t], H.regions_state(case.bounds))
+        _assert({k: v for k, v in res.items() if k != "W"}, 1e-10)
+        _assert({"W": res["W"]}, 1e-9)
     oc.close(); gc.close()
