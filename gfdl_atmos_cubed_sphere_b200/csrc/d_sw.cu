@@ -23,11 +23,12 @@
 
 using namespace ppm;
 
-// FV3_TP_LINES=0 falls back to the first-generation tile kernel on the interior tiles too (A/B timing, bisecting)
-static bool use_line_kernels() {
+// FV3_TP_LINES: 2 (default) line-per-warp kernels on interior and frame tiles, 1 on the interior tiles only, 0 nowhere (the
+// first-generation tile kernel of tp_tile.cuh everywhere) -- A/B timing and bisecting
+static int use_line_kernels() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("FV3_TP_LINES"); on = (e && e[0] == '0') ? 0 : 1; }
-  return on != 0;
+  if (on < 0) { const char* e = getenv("FV3_TP_LINES"); on = e ? atoi(e) : 2; }
+  return on;
 }
 
 #define TI 32
@@ -756,7 +757,7 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_dsw_vort_uv(Lay L, DevGrid G, tp
 // ---- interior tiles, line-per-warp form (tp_line.cuh): delp, [w,] pt transported phase-major by a CTA that is persistent over
 // a chunk of levels.  Same arithmetic as k_dsw_transport (the mass fluxes of delp weight the other fields' fluxes in the outer
 // sweep, the flux divergences are applied in the epilogue); launched when no del-n flux and no q_con is in play.
-template <int FAM, int NF, int HORD>
+template <int FAM, int NF, int HORD, bool EDGE>
 __global__ void __launch_bounds__(tp2::NT, 1) k_dsw_transport2(Lay L, DevGrid G, tpt::TileMap M, DswTr a, int nk, int kch) {
   static_assert(NF == 2 || NF == 3, "fields: delp, [w,] pt");
   const double* src[4 + NF];
@@ -770,27 +771,35 @@ __global__ void __launch_bounds__(tp2::NT, 1) k_dsw_transport2(Lay L, DevGrid G,
   const int n1 = L.npz + 1;
   // this thread's epilogue cell is the same on every level: its 1/area stays in a register
   double ra = 0.;
+  bool lastx, lasty;
   {
     const tp2::Geo T = tp2::make_geo(L, M);
-    if (T.wid < tp2::TY) ra = __ldg(G.rarea + tp2::gidx(T, T.i0 - 3 + T.lane, T.j0 + T.wid));
+    const int i = T.i0 - 3 + T.lane, j = T.j0 + T.wid;
+    if (T.wid < tp2::TY && (!EDGE || (i <= L.ied && j <= L.jed))) ra = __ldg(G.rarea + tp2::gidx(T, i, j));
+    lastx = T.i0 + tp2::TX > L.ie; lasty = T.j0 + tp2::TY > L.je;
   }
-  tp2::run_tile<FAM, NF, 2, tp2::W_MASS, HORD, 32>(L, G, M, src, nk, kch, ord_in, ord_ou,
-    [&](tp2::Smem<NF, 2>& S, const tp2::Geo& T, int k, long long ko, int r) {   // the flux capacitors' old values (read-modify-write, :928-940)
-      const int c = T.lane;
-      if (c < 3 || c > tp2::TX + 2) return;
-      const long long g = ko + tp2::gidx(T, T.i0 - 3 + c, T.j0 - 3 + r);
+  tp2::run_tile<FAM, NF, 2, tp2::W_MASS, HORD, 32, EDGE>(L, G, M, src, nk, kch, ord_in, ord_ou,
+    [&](tp2::Smem<NF, 2, EDGE>& S, const tp2::Geo& T, int k, long long ko, int r) {   // the flux capacitors' old values (read-modify-write, :928-940)
+      const int c = T.lane, i = T.i0 - 3 + c, j = T.j0 - 3 + r;
+      if (c < 3 || c > tp2::TX + 3 || (EDGE && (i > L.ie + 1 || j > L.je + 1))) return;
+      const long long g = ko + tp2::gidx(T, i, j);
       tpt::cp_async8(&S.ep[0][r * tp2::P + c], a.mfx + g);
       tpt::cp_async8(&S.ep[1][r * tp2::P + c], a.mfy + g);
     },
-    [&](tp2::Smem<NF, 2>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
-      const int c = T.lane;
-      if (c < 3 || c > tp2::TX + 2) return;
+    [&](tp2::Smem<NF, 2, EDGE>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
+      const int c = T.lane, i = T.i0 - 3 + c, j = T.j0 - 3 + r;
+      if (c < 3 || c > tp2::TX + 3 || (EDGE && (i > L.ie + 1 || j > L.je + 1))) return;
       const int o = r * tp2::P + c;
-      const long long g = ko + tp2::gidx(T, T.i0 - 3 + c, T.j0 - 3 + r);
-      const double mx0 = S.qi[0][o], mx1 = S.qi[0][o + 1], my0 = S.qj[0][o], my1 = S.qj[0][o + tp2::P];
+      const long long g = ko + tp2::gidx(T, i, j);
+      const double mx0 = S.qi[0][o], my0 = S.qj[0][o];
+      // flux capacitors: the tile's own west / south faces, plus the face's last column / row of faces
+      const bool xface = r <= tp2::TY + 2 && (!EDGE || j <= L.je) && (c <= tp2::TX + 2 || (EDGE && lastx));
+      const bool yface = c <= tp2::TX + 2 && (!EDGE || i <= L.ie) && (r <= tp2::TY + 2 || (EDGE && lasty));
+      if (xface) a.mfx[g] = S.ep[0][o] + mx0;
+      if (yface) a.mfy[g] = S.ep[1][o] + my0;
+      if (r > tp2::TY + 2 || c > tp2::TX + 2 || (EDGE && (i > L.ie || j > L.je))) return;   // not a cell of the tile
+      const double mx1 = S.qi[0][o + 1], my1 = S.qj[0][o + tp2::P];
       const double dp = S.in[b][tp2::A_Q][o];
-      a.mfx[g] = S.ep[0][o] + mx0;   // the tile's own west / south faces
-      a.mfy[g] = S.ep[1][o] + my0;
       const double dpn = dp + (mx0 - mx1 + my0 - my1) * ra;
 #pragma unroll
       for (int f = 1; f < NF; f++) {
@@ -807,7 +816,7 @@ __global__ void __launch_bounds__(tp2::NT, 1) k_dsw_transport2(Lay L, DevGrid G,
 }
 
 // 16 warps, two CTAs per SM (one transported field: the other CTA's sweeps hide this one's barriers and epilogue loads)
-template <int FAM, int HORD>
+template <int FAM, int HORD, bool EDGE>
 __global__ void __launch_bounds__(512, 2) k_dsw_vort_uv2(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ vq, const double* __restrict__ crx,
                                                        const double* __restrict__ cry, const double* __restrict__ xfx,
                                                        const double* __restrict__ yfx, const double* __restrict__ u,
@@ -815,17 +824,21 @@ __global__ void __launch_bounds__(512, 2) k_dsw_vort_uv2(Lay L, DevGrid G, tpt::
                                                        double* __restrict__ uo, double* __restrict__ vo, int hord_vt, int nk, int kch) {
   const double* src[5] = {crx, cry, xfx, yfx, vq};
   const int ord_ou[1] = {hord_vt}, ord_in[1] = {(hord_vt == 10) ? 8 : hord_vt};
-  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, 16>(L, G, M, src, nk, kch, ord_in, ord_ou,
-    [&](tp2::Smem<1, 0>&, const tp2::Geo&, int, long long, int) {},
-    [&](tp2::Smem<1, 0>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
-      const int c = T.lane;
-      if (c < 3 || c > tp2::TX + 2) return;
+  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, 16, EDGE>(L, G, M, src, nk, kch, ord_in, ord_ou,
+    [&](tp2::Smem<1, 0, EDGE>&, const tp2::Geo&, int, long long, int) {},
+    [&](tp2::Smem<1, 0, EDGE>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
+      const int c = T.lane, i = T.i0 - 3 + c, j = T.j0 - 3 + r;
+      if (c < 3 || c > tp2::TX + 3 || (EDGE && (i > L.ie + 1 || j > L.je + 1))) return;
+      const bool lastx = T.i0 + tp2::TX > L.ie, lasty = T.j0 + tp2::TY > L.je;
       const int o = r * tp2::P + c;
-      const int gi = tp2::gidx(T, T.i0 - 3 + c, T.j0 - 3 + r);
+      const int gi = tp2::gidx(T, i, j);
       const long long g = ko + gi;
       const double kev = __ldg(ke + g);
-      vo[g] = __ldg(v + g) * __ldg(G.dy + gi) + kev - __ldg(ke + g + T.NI) - S.qi[0][o];
-      uo[g] = __ldg(u + g) * __ldg(G.dx + gi) + kev - __ldg(ke + g + 1) + S.qj[0][o];
+      // v on (is:ie+1, js:je): west faces; u on (is:ie, js:je+1): south faces
+      if (r <= tp2::TY + 2 && (!EDGE || j <= L.je) && (c <= tp2::TX + 2 || (EDGE && lastx)))
+        vo[g] = __ldg(v + g) * __ldg(G.dy + gi) + kev - __ldg(ke + g + T.NI) - S.qi[0][o];
+      if (c <= tp2::TX + 2 && (!EDGE || i <= L.ie) && (r <= tp2::TY + 2 || (EDGE && lasty)))
+        uo[g] = __ldg(u + g) * __ldg(G.dx + gi) + kev - __ldg(ke + g + 1) + S.qj[0][o];
     });
 }
 
@@ -859,18 +872,25 @@ static int launch_transport_t(fv3_ctx* c, const DswTr& a, int nk) {
   }
   tpt::TileMap Min, Mfr; int n_in, n_fr;
   tpt::tile_maps(c->L, Min, Mfr, n_in, n_fr);
-  // interior tiles: the line-per-warp kernel when only delp, [w,] pt are transported and no del-n flux is added
+  // the line-per-warp kernels (tp_line.cuh) when only delp, [w,] pt are transported with the common schemes and no del-n flux
+  // is added; interior tiles and frame tiles are separate instantiations (the frame one carries the cube-edge cells)
   const bool lines = FAM != 2 && use_line_kernels() && a.pt && !a.qcon && !a.dpx && !a.ptx && !a.qcx;
-  if (n_in && lines) {
+  const bool lines_fr = lines && use_line_kernels() > 1;
+  if (lines) {
     constexpr int F2 = FAM == 2 ? 0 : FAM;
-    const int kch = tp2::level_chunk(nk), nch = (nk + kch - 1) / kch;
+    const int kch = tp2::level_chunk(nk), nch = (nk + kch - 1) / kch, kch_fr = (kch + 1) / 2, nch_fr = (nk + kch_fr - 1) / kch_fr;
     // the scheme is a compile-time constant of the kernel when every field uses the same common one (hord 10 / 8 / 5 / 6)
     const bool same = a.hord_dp == a.hord_tm && (!a.w || a.hord_dp == a.hord_vt);
     const int hs = same ? a.hord_dp : tp2::ORD_RT;
-#define TR2_LAUNCH(NF_, H_)                                                                                                        \
+#define TR2_LAUNCH1(NF_, H_, E_, MAP_, N_)                                                                                         \
     do {                                                                                                                           \
-      FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport2<F2, NF_, H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<NF_, 2>))); \
-      k_dsw_transport2<F2, NF_, H_><<<dim3(n_in, nch), tp2::NT, sizeof(tp2::Smem<NF_, 2>), c->stream>>>(c->L, c->G, Min, a, nk, kch);    \
+      FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport2<F2, NF_, H_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<NF_, 2, E_>))); \
+      k_dsw_transport2<F2, NF_, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), tp2::NT, sizeof(tp2::Smem<NF_, 2, E_>), c->stream>>>(c->L, c->G, MAP_, a, nk, E_ ? kch_fr : kch); \
+    } while (0)
+#define TR2_LAUNCH(NF_, H_)                                                        \
+    do {                                                                           \
+      if (n_in) TR2_LAUNCH1(NF_, H_, false, Min, n_in);                            \
+      if (n_fr && lines_fr) TR2_LAUNCH1(NF_, H_, true, Mfr, n_fr);                 \
     } while (0)
     if (a.w) {
       if constexpr (F2 == 1) {
@@ -884,8 +904,9 @@ static int launch_transport_t(fv3_ctx* c, const DswTr& a, int nk) {
       }
     } else TR2_LAUNCH(2, tp2::ORD_RT);
 #undef TR2_LAUNCH
+#undef TR2_LAUNCH1
   } else if (n_in) k_dsw_transport<FAM, false><<<dim3(n_in, 1, nk), tpt::NT, sizeof(DswSmem), c->stream>>>(c->L, c->G, Min, a);
-  if (n_fr) k_dsw_transport<FAM, true><<<dim3(n_fr, 1, nk), tpt::NT, sizeof(DswSmem), c->stream>>>(c->L, c->G, Mfr, a);
+  if (n_fr && !lines_fr) k_dsw_transport<FAM, true><<<dim3(n_fr, 1, nk), tpt::NT, sizeof(DswSmem), c->stream>>>(c->L, c->G, Mfr, a);
   c->launches += (n_in ? 1 : 0) + (n_fr ? 1 : 0);
   return 0;
 }
@@ -909,15 +930,21 @@ static int launch_vort_uv_t(fv3_ctx* c, const double* vq, const double* u, const
   }
   tpt::TileMap Min, Mfr; int n_in, n_fr;
   tpt::tile_maps(c->L, Min, Mfr, n_in, n_fr);
-  if (n_in && FM != 2 && use_line_kernels()) {
+  const bool lines = FM != 2 && use_line_kernels(), lines_fr = lines && use_line_kernels() > 1;
+  if (lines) {
     constexpr int F2 = FM == 2 ? 0 : FM;
-    const int kch = tp2::level_chunk(nk), nch = (nk + kch - 1) / kch;
+    const int kch = tp2::level_chunk(nk), nch = (nk + kch - 1) / kch, kch_fr = (kch + 1) / 2, nch_fr = (nk + kch_fr - 1) / kch_fr;
     const int h = c->f.hord_vt;
-#define VU2_LAUNCH(H_)                                                                                                            \
+#define VU2_LAUNCH1(H_, E_, MAP_, N_)                                                                                             \
     do {                                                                                                                          \
-      FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_vort_uv2<F2, H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<1>))); \
-      k_dsw_vort_uv2<F2, H_><<<dim3(n_in, nch), 512, sizeof(tp2::Smem<1>), c->stream>>>(                                         \
-          c->L, c->G, Min, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, h, nk, kch);    \
+      FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_vort_uv2<F2, H_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<1, 0, E_>))); \
+      k_dsw_vort_uv2<F2, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), 512, sizeof(tp2::Smem<1, 0, E_>), c->stream>>>(                                           \
+          c->L, c->G, MAP_, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, h, nk, E_ ? kch_fr : kch); \
+    } while (0)
+#define VU2_LAUNCH(H_)                                                 \
+    do {                                                               \
+      if (n_in) VU2_LAUNCH1(H_, false, Min, n_in);                     \
+      if (n_fr && lines_fr) VU2_LAUNCH1(H_, true, Mfr, n_fr);          \
     } while (0)
     if constexpr (F2 == 1) {
       if (h == 10) VU2_LAUNCH(10);
@@ -929,9 +956,10 @@ static int launch_vort_uv_t(fv3_ctx* c, const double* vq, const double* u, const
       else VU2_LAUNCH(tp2::ORD_RT);
     }
 #undef VU2_LAUNCH
+#undef VU2_LAUNCH1
   } else if (n_in) k_dsw_vort_uv<FM, false><<<dim3(n_in, 1, nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(
       c->L, c->G, Min, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, c->f.hord_vt);
-  if (n_fr) k_dsw_vort_uv<FM, true><<<dim3(n_fr, 1, nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(
+  if (n_fr && !lines_fr) k_dsw_vort_uv<FM, true><<<dim3(n_fr, 1, nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(
       c->L, c->G, Mfr, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, c->f.hord_vt);
   c->launches += (n_in ? 1 : 0) + (n_fr ? 1 : 0);
   return 0;

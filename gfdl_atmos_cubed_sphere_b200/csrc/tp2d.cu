@@ -81,19 +81,19 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, tpt::
 }
 
 // interior tiles of the fused height update (update_dz_d, nh_utils.F90:282-299) in the line-per-warp form (tp_line.cuh)
-template <int FAM, int HORD>
+template <int FAM, int HORD, bool EDGE>
 __global__ void __launch_bounds__(512, 2) k_tp_zn2(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ q, const double* __restrict__ crx,
                                                  const double* __restrict__ cry, const double* __restrict__ xfx, const double* __restrict__ yfx,
                                                  int ord_in_, int ord_ou_, tpt::ZnEpi Z, int nk, int kch) {
   const double* src[5] = {crx, cry, xfx, yfx, q};
   const int ord_in[1] = {ord_in_}, ord_ou[1] = {ord_ou_};
-  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, 16>(L, G, M, src, nk, kch, ord_in, ord_ou,
-    [&](tp2::Smem<1, 0>&, const tp2::Geo&, int, long long, int) {},
-    [&](tp2::Smem<1, 0>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
-      const int c = T.lane;
-      if (c < 3 || c > tp2::TX + 2) return;
+  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, 16, EDGE>(L, G, M, src, nk, kch, ord_in, ord_ou,
+    [&](tp2::Smem<1, 0, EDGE>&, const tp2::Geo&, int, long long, int) {},
+    [&](tp2::Smem<1, 0, EDGE>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
+      const int c = T.lane, i = T.i0 - 3 + c, j = T.j0 - 3 + r;
+      if (c < 3 || c > tp2::TX + 2 || r > tp2::TY + 2 || (EDGE && (i > L.ie || j > L.je))) return;
       const int o = r * tp2::P + c;
-      const int gi = tp2::gidx(T, T.i0 - 3 + c, T.j0 - 3 + r);
+      const int gi = tp2::gidx(T, i, j);
       const double ar = S.area[o];
       const double x0 = S.in[b][tp2::A_XFX][o], x1 = S.in[b][tp2::A_XFX][o + 1], y0 = S.in[b][tp2::A_YFX][o], y1 = S.in[b][tp2::A_YFX][o + tp2::P];
       const double rax = ar + x0 - x1, ray = ar + y0 - y1;
@@ -125,16 +125,23 @@ int launch_tp2d(fv3_ctx* c, const Tp2d& a) {
   }
   const tpt::ZnEpi Z{a.zn, a.zn_dfx, a.zn_dfy, a.zn ? c->d_kdbl : nullptr, a.zn_slot};
   if (a.zn && (a.ra_x || a.ra_y || a.mfx)) return fv3_fail(c, -1, "fv_tp_2d: the fused height update takes no ra_x / ra_y / mfx");
-  // interior tiles of the fused height update: line-per-warp kernel (FV3_TP_LINES=0 keeps the first-generation tile kernel)
+  // the fused height update with the common schemes: line-per-warp kernels (tp_line.cuh) on the interior and on the frame tiles
+  // (FV3_TP_LINES=1: interior only, 0: the first-generation tile kernel everywhere)
   static int lines_on = -1;
-  if (lines_on < 0) { const char* e = getenv("FV3_TP_LINES"); lines_on = (e && e[0] == '0') ? 0 : 1; }
-  if (a.zn && n_in && lines_on && !hord_is_rare(a.hord)) {
-    const int kch = tp2::level_chunk(a.nk), nch = (a.nk + kch - 1) / kch;
-#define ZN2_LAUNCH(F_, H_)                                                                                                         \
+  if (lines_on < 0) { const char* e = getenv("FV3_TP_LINES"); lines_on = e ? atoi(e) : 2; }
+  if (a.zn && lines_on && !hord_is_rare(a.hord)) {
+    const int kch = tp2::level_chunk(a.nk), nch = (a.nk + kch - 1) / kch, kch_fr = (kch + 1) / 2, nch_fr = (a.nk + kch_fr - 1) / kch_fr;
+#define ZN2_LAUNCH1(F_, H_, E_, MAP_, N_)                                                                                          \
     do {                                                                                                                           \
-      FV3_CUDA(c, cudaFuncSetAttribute(k_tp_zn2<F_, H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<1>)));   \
-      k_tp_zn2<F_, H_><<<dim3(n_in, nch), 512, sizeof(tp2::Smem<1>), c->stream>>>(L, c->G, Min, a.q, a.crx, a.cry, a.xfx, a.yfx,   \
-                                                                                     ord_in, a.hord, Z, a.nk, kch);                 \
+      FV3_CUDA(c, cudaFuncSetAttribute(k_tp_zn2<F_, H_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<1, 0, E_>))); \
+      k_tp_zn2<F_, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), 512, sizeof(tp2::Smem<1, 0, E_>), c->stream>>>(L, c->G, MAP_, a.q, a.crx, a.cry, a.xfx, a.yfx,    \
+                                                                                  ord_in, a.hord, Z, a.nk, E_ ? kch_fr : kch);     \
+      c->launches++;                                                                                                               \
+    } while (0)
+#define ZN2_LAUNCH(F_, H_)                                                          \
+    do {                                                                            \
+      if (n_in) { ZN2_LAUNCH1(F_, H_, false, Min, n_in); n_in = 0; }                \
+      if (n_fr && lines_on > 1) { ZN2_LAUNCH1(F_, H_, true, Mfr, n_fr); n_fr = 0; } \
     } while (0)
     if (a.hord == 10) ZN2_LAUNCH(1, 10);
     else if (a.hord == 8) ZN2_LAUNCH(1, 8);
@@ -142,8 +149,7 @@ int launch_tp2d(fv3_ctx* c, const Tp2d& a) {
     else if (a.hord == 6) ZN2_LAUNCH(0, 6);
     else ZN2_LAUNCH(0, tp2::ORD_RT);   // -5
 #undef ZN2_LAUNCH
-    c->launches++;
-    n_in = 0;   // only the frame tiles are left for the general kernel
+#undef ZN2_LAUNCH1
   }
 #define TP_LAUNCH(FAM, EDGE, M, N)                                                                                           \
   k_tp_fused<FAM, EDGE><<<dim3(N, 1, a.nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(L, c->G, M, a.q, a.crx, a.cry, a.xfx, a.yfx, \

@@ -45,9 +45,12 @@ enum { A_CRX = 0, A_CRY = 1, A_XFX = 2, A_YFX = 3, A_Q = 4 };
 //   W_RAW : the unweighted Lin-Rood flux 0.5 * (outer + inner)
 enum { W_AREA = 0, W_MASS = 1, W_RAW = 2 };
 
-template <int NF, int NEP = 0>
+template <int NF, int NEP = 0, bool EDGE = false>
 struct Smem {
   double g0[GUARD];
+  // frame tiles: dxa (x lines) / dya (y lines) at the four cells around the low (e = 1) and the high (e = n) cube edge of every line
+  // of the tile, [direction][line][edge][e-2 .. e+1] -- k-invariant, filled once per tile (the two-sided edge value :376-377, 647-648)
+  double et[EDGE ? 2 * 32 * 2 * 4 : 1];
   double in[2][4 + NF][ASZ];   // per level, double-buffered: crx, cry, xfx, yfx, q_0 .. q_{NF-1}
   double area[ASZ];
   double qi[NF][ASZ];          // q_i (tp_core.F90:150-159); after the outer sweep: the x fluxes
@@ -69,10 +72,20 @@ __device__ __forceinline__ double dn1(double x) { return __shfl_down_sync(0xffff
 // (64 registers per thread) instruction-level parallelism is what hides the fp64 / shuffle latencies (ncu, first version of
 // this file: 55 % issue-active with the fields evaluated one after the other).
 constexpr int ORD_RT = 99;
-template <int FAM, int NF, int ORD>
+// Frame tiles (EDGE = true): a line that crosses a cube edge carries the reference's one-sided cells / faces.  ic = base + lane
+// is the sweep index (i for x lines, j for y lines) of a lane's cell, n = npx (npy), d -> dxa (dya) at sweep index 0 of the line
+// with stride ds.  The few lanes concerned re-derive their (bl, br) / al from the line in shared memory (tp_core.F90:643-681
+// monotone family, :374-392 and :536-545 unlimited family); the other lanes of the warp idle meanwhile.
+struct EdgeLine { bool on; int base, n; const double* et; };   // et -> this line's [edge][4] metric table in shared memory
+__device__ __forceinline__ double edge_avg4(double qm2, double qm1, double q0, double qp1, const double* d) {   // ppm::edge_avg on the tabulated metric
+  return 0.5 * (((2. * d[1] + d[0]) * qm1 - d[1] * qm2) / (d[0] + d[1]) + ((2. * d[2] + d[3]) * q0 - d[2] * qp1) / (d[2] + d[3]));
+}
+template <int FAM, int NF, int ORD, bool EDGE>
 __device__ __forceinline__ void line_fluxes(const double (*__restrict__ q)[ASZ], int o, int sa, int lane, double cl, double cr,
-                                            const int (&ord)[NF], double (&q0)[NF], double (&flux)[NF]) {
+                                            const int (&ord)[NF], double (&q0)[NF], double (&flux)[NF], const EdgeLine& E) {
   using namespace ppm;
+  const int ic = EDGE ? E.base + lane : 0;
+  const bool ecell = EDGE && E.on && ((ic >= 0 && ic <= 2) || (ic >= E.n - 2 && ic <= E.n));   // cells with one-sided (bl, br)
   if (FAM == 1) {
     double qm[NF], qp[NF], dm0[NF], dmm[NF], dmp[NF], al0[NF], al1[NF], bl[NF], br[NF], FR[NF], FL[NF];
 #pragma unroll
@@ -83,7 +96,7 @@ __device__ __forceinline__ void line_fluxes(const double (*__restrict__ q)[ASZ],
 #pragma unroll
     for (int f = 0; f < NF; f++) {
       dmm[f] = up1(dm0[f]);
-      if (ORD != 8) dmp[f] = dn1(dm0[f]);
+      if (ORD != 8 || EDGE) dmp[f] = dn1(dm0[f]);
     }
 #pragma unroll
     for (int f = 0; f < NF; f++) al0[f] = 0.5 * (qm[f] + q0[f]) + r3 * (dmm[f] - dm0[f]);
@@ -96,6 +109,36 @@ __device__ __forceinline__ void line_fluxes(const double (*__restrict__ q)[ASZ],
       const double xt = 2. * dm0[f];
       const double bl8 = -fsign(mn(fabs(xt), fabs(al0[f] - q0[f])), xt);
       const double br8 = fsign(mn(fabs(xt), fabs(al1[f] - q0[f])), xt);
+      if (EDGE && ecell) {   // tp_core.F90:643-681 (every monotone scheme), cell form of ppm::cell_mono
+        const double* ql = q[f] + o;
+        auto qa = [&](int i) { return ql[(i - ic) * sa]; };
+        const int n = E.n;
+        double b_l, b_r;
+        if (ic <= 1) {
+          const double a = qa(-1), b = qa(0), c = qa(1), d = qa(2);
+          double xe = edge_avg4(a, b, c, d, E.et);
+          xe = mx(xe, mn(mn(a, b), mn(c, d)));
+          xe = mn(xe, mx(mx(a, b), mx(c, d)));
+          if (ic == 0) { b_l = s14 * dmm[f] + s11 * (a - b); b_r = xe - b; }
+          else { b_l = xe - c; b_r = (s15 * c + s11 * d - s14 * dmp[f]) - c; }
+        } else if (ic == 2) {
+          b_l = (s15 * qa(1) + s11 * q0[f] - s14 * dm0[f]) - q0[f];
+          b_r = al1[f] - q0[f];
+        } else if (ic == n - 2) {
+          b_l = al0[f] - q0[f];
+          b_r = (s15 * qa(n - 1) + s11 * q0[f] + s14 * dm0[f]) - q0[f];
+        } else {
+          const double a = qa(n - 2), b = qa(n - 1), c = qa(n), d = qa(n + 1);
+          double xe = edge_avg4(a, b, c, d, E.et + 4);
+          xe = mx(xe, mn(mn(a, b), mn(c, d)));
+          xe = mn(xe, mx(mx(a, b), mx(c, d)));
+          if (ic == n - 1) { b_l = (s15 * b + s11 * a + s14 * dmm[f]) - b; b_r = xe - b; }
+          else { b_l = xe - c; b_r = s11 * (d - c) - s14 * dmp[f]; }
+        }
+        pert_std(b_l, b_r);
+        bl[f] = b_l; br[f] = b_r;
+        continue;
+      }
       if (ORD == 8) { bl[f] = bl8; br[f] = br8; continue; }
       // iord 10 (:605-627 with the pmp / lac constraint), branch-free: the constraint applies where the parabola overshoots
       double b_l = al0[f] - q0[f], b_r = al1[f] - q0[f];
@@ -132,6 +175,17 @@ __device__ __forceinline__ void line_fluxes(const double (*__restrict__ q)[ASZ],
       const double qm2 = q[f][o - 2 * sa], qp = q[f][o + sa];
       qm[f] = q[f][o - sa]; q0[f] = q[f][o];
       double a = p1 * (qm[f] + q0[f]) + p2 * (qm2 + qp);
+      if (EDGE && E.on && ((ic >= 0 && ic <= 2) || (ic >= E.n - 1 && ic <= E.n + 1))) {   // faces with a one-sided edge value (:374-392)
+        const double* ql = q[f] + o;
+        auto qa = [&](int i) { return ql[(i - ic) * sa]; };
+        const int n = E.n;
+        if (ic == 0) a = c1 * qa(-2) + c2 * qa(-1) + c3 * qa(0);
+        else if (ic == 1) a = edge_avg4(qa(-1), qa(0), qa(1), qa(2), E.et);
+        else if (ic == 2) a = c3 * qa(1) + c2 * qa(2) + c1 * qa(3);
+        else if (ic == n - 1) a = c1 * qa(n - 3) + c2 * qa(n - 2) + c3 * qa(n - 1);
+        else if (ic == n) a = edge_avg4(qa(n - 2), qa(n - 1), qa(n), qa(n + 1), E.et + 4);
+        else a = c3 * qa(n) + c2 * qa(n + 1) + c1 * qa(n + 2);
+      }
       if (iord < 0) a = mx(0., a);
       al0[f] = a;
     }
@@ -154,6 +208,7 @@ __device__ __forceinline__ void line_fluxes(const double (*__restrict__ q)[ASZ],
           }
         }
       } else sm_ = 3. * fabs(b0) < fabs(bl - br);
+      if (EDGE && E.on && (ic == 0 || ic == 1 || ic == E.n - 1 || ic == E.n)) sm_ = bl * br < 0.;   // :536-545
       smt[f] = sm_;
       F1R[f] = (1. - cr) * (br - cr * b0);
       F1L[f] = (1. + cl) * (bl + cl * b0);
@@ -172,14 +227,14 @@ __device__ __forceinline__ void line_fluxes(const double (*__restrict__ q)[ASZ],
 
 // inner sweep of one line for all fields (tp_core.F90:143-148 / 164-169) + the intermediate field it feeds (:150-159 / 171-178).
 // o = this lane's element, sa = lane stride; cr_ / xf_ = Courant numbers / area fluxes of the sweep direction.
-template <int FAM, int NF, int ORD>
+template <int FAM, int NF, int ORD, bool EDGE>
 __device__ __forceinline__ void inner_line(const double* __restrict__ cr_, const double* __restrict__ xf_, const double* __restrict__ area,
-                                           const double (*__restrict__ q)[ASZ], double (*__restrict__ qout)[ASZ], int o, int sa, int lane,
-                                           const int (&ord)[NF], double (&fin)[NF]) {
+                                           const double (*q)[ASZ], double (*qout)[ASZ], int o, int sa, int lane,
+                                           const int (&ord)[NF], double (&fin)[NF], const EdgeLine& E) {
   const double cl = cr_[o], cr = cr_[o + sa], xl = xf_[o], xr = xf_[o + sa], ar = area[o];
   const double rra = 1. / (ar + xl - xr);
   double q0[NF], g[NF];
-  line_fluxes<FAM, NF, ORD>(q, o, sa, lane, cl, cr, ord, q0, fin);
+  line_fluxes<FAM, NF, ORD, EDGE>(q, o, sa, lane, cl, cr, ord, q0, fin, E);
 #pragma unroll
   for (int f = 0; f < NF; f++) g[f] = fin[f] * xl;
 #pragma unroll
@@ -190,9 +245,9 @@ __device__ __forceinline__ void inner_line(const double* __restrict__ cr_, const
 }
 
 // outer sweep of one line for all fields, averaged with the inner flux and weighted (tp_core.F90:161, 180, 193-226); in place
-template <int FAM, int NF, int WMODE, int ORD>
+template <int FAM, int NF, int WMODE, int ORD, bool EDGE>
 __device__ __forceinline__ void outer_line(const double* __restrict__ cr_, const double* __restrict__ xf_, double (*__restrict__ q)[ASZ], int o,
-                                           int sa, int lane, const int (&ord)[NF], const double (&fin)[NF]) {
+                                           int sa, int lane, const int (&ord)[NF], const double (&fin)[NF], const EdgeLine& E) {
   const double cl = cr_[o], cr = cr_[o + sa];
   const double xl = (WMODE == W_RAW) ? 1. : xf_[o];
   double q0[NF], fo[NF];
@@ -204,10 +259,10 @@ __device__ __forceinline__ void outer_line(const double* __restrict__ cr_, const
     for (int f = 0; f < NF; f++) {
       const int o1[1] = {ord[f]};
       double q1[1], f1[1];
-      line_fluxes<FAM, 1, ORD>(q + f, o, sa, lane, cl, cr, o1, q1, f1);
+      line_fluxes<FAM, 1, ORD, EDGE>(q + f, o, sa, lane, cl, cr, o1, q1, f1, E);
       fo[f] = f1[0];
     }
-  } else line_fluxes<FAM, NF, ORD>(q, o, sa, lane, cl, cr, ord, q0, fo);
+  } else line_fluxes<FAM, NF, ORD, EDGE>(q, o, sa, lane, cl, cr, ord, q0, fo, E);
   double m = 0.;
 #pragma unroll
   for (int f = 0; f < NF; f++) {
@@ -220,7 +275,7 @@ __device__ __forceinline__ void outer_line(const double* __restrict__ cr_, const
   }
 }
 
-struct Geo { int i0, j0, NI, ib, jb, lane, wid; };
+struct Geo { int i0, j0, NI, ib, jb, lane, wid; bool corner; };
 __device__ __forceinline__ int gidx(const Geo& T, int i, int j) { return (i + T.ib) + (j - T.jb) * T.NI; }
 
 __device__ __forceinline__ Geo make_geo(const Lay& L, const tpt::TileMap& M) {
@@ -230,16 +285,37 @@ __device__ __forceinline__ Geo make_geo(const Lay& L, const tpt::TileMap& M) {
   T.i0 = L.is + bx * TX; T.j0 = L.js + by * TY;
   T.NI = L.NI; T.ib = FV3_IOFF - L.isd; T.jb = L.jsd;
   T.lane = threadIdx.x & 31; T.wid = threadIdx.x >> 5;
+  // the tile's halo overlaps a cube-corner region: q is needed in both copy_corners views (tp_core.F90:245-322)
+  T.corner = L.cube && (T.i0 - 3 <= 0 || T.i0 + TX + 2 >= L.npx) && (T.j0 - 3 <= 0 || T.j0 + TY + 2 >= L.npy);
   return T;
 }
 
-// issue the inputs of one level into buffer b: 32 / NWC elements of every array per thread (row = warp (+ NWC), column = lane)
-template <int NF, int NEP, int NWC>
-__device__ __forceinline__ void stage_level(Smem<NF, NEP>& S, int b, const double* const (&src)[4 + NF], long long g, int so, int NI) {
+// issue the inputs of one level into buffer b: 32 / NWC elements of every array per thread (row = warp (+ NWC), column = lane).
+// g = level offset + in-plane index of the thread's first element (frame tiles: index clamped to the padded plane), dj = in-plane
+// distance to its next element (NWC rows; frame tiles whose second row falls off the plane repeat the last row).
+// skip_q: cube-corner tiles stage their q views themselves (stage_corner_q)
+template <int NF, int NEP, int NWC, bool EDGE>
+__device__ __forceinline__ void stage_level(Smem<NF, NEP, EDGE>& S, int b, const double* const (&src)[4 + NF], long long g, int so, int dj, bool skip_q) {
 #pragma unroll
   for (int i = 0; i < 32 / NWC; i++)
 #pragma unroll
-    for (int a = 0; a < 4 + NF; a++) tpt::cp_async8(&S.in[b][a][so + i * NWC * P], src[a] + g + (long long)i * NWC * NI);
+    for (int a = 0; a < 4 + NF; a++)
+      if (a < 4 || !skip_q) tpt::cp_async8(&S.in[b][a][so + i * NWC * P], src[a] + g + (long long)i * dj);
+}
+// cube-corner tiles: the copy_corners(dir = 1) view of every field into the level buffer (read by the x lines) and the dir = 2 view
+// into qi (read, then overwritten with q_i, by the y lines -- a column of qi is only ever touched by the warp that owns it)
+template <int NF, int NEP, int NWC, bool EDGE>
+__device__ __forceinline__ void stage_corner_q(const Lay& L, Smem<NF, NEP, EDGE>& S, int b, const Geo& T, const double* const (&src)[4 + NF], long long ko) {
+  const int i = min(T.i0 - 3 + T.lane, L.ied);
+#pragma unroll
+  for (int n = 0; n < 32 / NWC; n++) {
+    const int r = T.wid + n * NWC, j = min(T.j0 - 3 + r, L.jed);
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      S.in[b][A_Q + f][r * P + T.lane] = ppm::QAccX{src[A_Q + f] + ko, L, j}(i);
+      S.qi[f][r * P + T.lane] = ppm::QAccY{src[A_Q + f] + ko, L, i}(j);
+    }
+  }
 }
 
 #ifdef FV3_TP2_PROF
@@ -252,8 +328,9 @@ __device__ __forceinline__ void stage_level(Smem<NF, NEP>& S, int b, const doubl
 // have no outer task (rows / columns 0..2, 29..31) over different warps.  On return (after a barrier) qi[f] / qj[f] hold the
 // fluxes through the west / south face of element [r][c] = cell (i0-3+c, j0-3+r): x faces valid for rows 3..28, columns 3..29;
 // y faces for rows 3..29, columns 3..28.
-template <int FAM, int NF, int NEP, int WMODE, int HORD, int NWC>
-__device__ __forceinline__ void compute_level(Smem<NF, NEP>& S, int b, const Geo& T, const int (&ord_in)[NF], const int (&ord_ou)[NF]
+template <int FAM, int NF, int NEP, int WMODE, int HORD, int NWC, bool EDGE>
+__device__ __forceinline__ void compute_level(const Lay& L, const DevGrid& G, Smem<NF, NEP, EDGE>& S, int b, const Geo& T, const int (&ord_in)[NF],
+                                              const int (&ord_ou)[NF]
 #ifdef FV3_TP2_PROF
                                               , long long (&prof)[8], long long& tprev
 #endif
@@ -262,51 +339,75 @@ __device__ __forceinline__ void compute_level(Smem<NF, NEP>& S, int b, const Geo
   constexpr int LPW = 32 / NWC;
   double finx[LPW][NF], finy[LPW][NF];
   const int yc0 = (T.wid + NWC / 2) & (NWC - 1);
+  const bool cube = EDGE && L.cube;
+  const double (*qy)[ASZ] = (EDGE && T.corner) ? S.qi : S.in[b] + A_Q;   // the field as the y sweeps see it
 #pragma unroll
-  for (int i = 0; i < LPW; i++)
-    inner_line<FAM, NF, OI>(S.in[b][A_CRX], S.in[b][A_XFX], S.area, S.in[b] + A_Q, S.qj, (T.wid + i * NWC) * P + T.lane, 1, T.lane, ord_in, finx[i]);
+  for (int i = 0; i < LPW; i++) {
+    const int r = T.wid + i * NWC;
+    const EdgeLine E{cube, T.i0 - 3, L.npx, S.et + r * 8};
+    inner_line<FAM, NF, OI, EDGE>(S.in[b][A_CRX], S.in[b][A_XFX], S.area, S.in[b] + A_Q, S.qj, r * P + T.lane, 1, T.lane, ord_in, finx[i], E);
+  }
   TP2_CLK(1);
 #pragma unroll
-  for (int i = 0; i < LPW; i++)
-    inner_line<FAM, NF, OI>(S.in[b][A_CRY], S.in[b][A_YFX], S.area, S.in[b] + A_Q, S.qi, T.lane * P + yc0 + i * NWC, P, T.lane, ord_in, finy[i]);
+  for (int i = 0; i < LPW; i++) {
+    const int c = yc0 + i * NWC;
+    const EdgeLine E{cube, T.j0 - 3, L.npy, S.et + 256 + c * 8};
+    inner_line<FAM, NF, OI, EDGE>(S.in[b][A_CRY], S.in[b][A_YFX], S.area, qy, S.qi, T.lane * P + c, P, T.lane, ord_in, finy[i], E);
+  }
   TP2_CLK(2);
   __syncthreads();
   TP2_CLK(3);
 #pragma unroll
   for (int i = 0; i < LPW; i++) {
     const int r = T.wid + i * NWC;
-    if (r >= 3 && r <= TY + 2) outer_line<FAM, NF, WMODE, OO>(S.in[b][A_CRX], S.in[b][A_XFX], S.qi, r * P + T.lane, 1, T.lane, ord_ou, finx[i]);
+    const EdgeLine E{cube, T.i0 - 3, L.npx, S.et + r * 8};
+    if (r >= 3 && r <= TY + 2) outer_line<FAM, NF, WMODE, OO, EDGE>(S.in[b][A_CRX], S.in[b][A_XFX], S.qi, r * P + T.lane, 1, T.lane, ord_ou, finx[i], E);
   }
 #pragma unroll
   for (int i = 0; i < LPW; i++) {
     const int c = yc0 + i * NWC;
-    if (c >= 3 && c <= TX + 2) outer_line<FAM, NF, WMODE, OO>(S.in[b][A_CRY], S.in[b][A_YFX], S.qj, T.lane * P + c, P, T.lane, ord_ou, finy[i]);
+    const EdgeLine E{cube, T.j0 - 3, L.npy, S.et + 256 + c * 8};
+    if (c >= 3 && c <= TX + 2) outer_line<FAM, NF, WMODE, OO, EDGE>(S.in[b][A_CRY], S.in[b][A_YFX], S.qj, T.lane * P + c, P, T.lane, ord_ou, finy[i], E);
   }
   TP2_CLK(4);
   __syncthreads();
   TP2_CLK(5);
 }
 
-// Persistent-over-k driver: the CTA (NWC warps) owns interior tile blockIdx.x and the levels [blockIdx.y*kch, +kch) of nk.
+// Persistent-over-k driver: the CTA (NWC warps) owns tile blockIdx.x of the map (interior rectangle: EDGE = false, or the frame
+// around it: EDGE = true) and the levels [blockIdx.y*kch, +kch) of nk.
 //   src: the 4 + NF source arrays (level-0 based; the level offset is added here)
 //   pre(S, T, k, ko, r): called for every tile row r = 3..28 this warp finishes, right after level k is staged: may issue cp.async
 //        into S.ep[.][r*P + lane] for the operands its epilogue needs (they arrive while the sweeps run; no global-load latency
 //        is left in the epilogue, which nothing would overlap in a one-CTA-per-SM kernel)
-//   epi(S, b, T, k, ko, r): the per-level epilogue of row r (reads S.qi / S.qj / S.in[b][A_Q + f] / S.ep)
+//   epi(S, b, T, k, ko, r): the per-level epilogue of row r (reads S.qi / S.qj / S.in[b][A_Q + f] / S.ep); frame tiles are also
+//        called for r = 29 (the south faces of the face's last row)
 //   HORD: the transport scheme of every field as a compile-time constant, or ORD_RT (per-field ord_in / ord_ou at run time)
-template <int FAM, int NF, int NEP, int WMODE, int HORD, int NWC, class Pre, class Epi>
+template <int FAM, int NF, int NEP, int WMODE, int HORD, int NWC, bool EDGE, class Pre, class Epi>
 __device__ __forceinline__ void run_tile(const Lay& L, const DevGrid& G, const tpt::TileMap& M, const double* const (&src)[4 + NF], int nk, int kch,
                                          const int (&ord_in)[NF], const int (&ord_ou)[NF], Pre&& pre, Epi&& epi) {
   extern __shared__ __align__(16) unsigned char smem_raw2[];
-  Smem<NF, NEP>& S = *reinterpret_cast<Smem<NF, NEP>*>(smem_raw2);
+  Smem<NF, NEP, EDGE>& S = *reinterpret_cast<Smem<NF, NEP, EDGE>*>(smem_raw2);
   const Geo T = make_geo(L, M);
   const int k0 = blockIdx.y * kch, k1 = min(nk, k0 + kch);
   if (k0 >= k1) return;
   const int so = T.wid * P + T.lane;
-  const int g2 = gidx(T, T.i0 - 3 + T.lane, T.j0 - 3 + T.wid);
+  // frame tiles may overhang the face: indices are clamped to the padded plane (duplicates are never used by a stored result)
+  const int ig = EDGE ? min(T.i0 - 3 + T.lane, L.ied + 1) : T.i0 - 3 + T.lane;
+  const int jg = EDGE ? min(T.j0 - 3 + T.wid, L.jed + 1) : T.j0 - 3 + T.wid;
+  const int g2 = gidx(T, ig, jg);
+  const int dj = (EDGE ? min(T.j0 - 3 + T.wid + NWC, L.jed + 1) - jg : NWC) * T.NI;
+  const bool cq = EDGE && T.corner;
+  constexpr int REPI = EDGE ? TY + 3 : TY + 2;   // last tile row with an epilogue
+  if (EDGE && L.cube && threadIdx.x < 128) {      // the lines' cube-edge metric table (visible after the first level-start barrier)
+    const int dir = threadIdx.x >> 6, line = (threadIdx.x >> 1) & 31, e = (threadIdx.x & 1) ? (dir ? L.npy : L.npx) : 1;
+    double* t = S.et + dir * 256 + line * 8 + (threadIdx.x & 1) * 4;
+    if (dir == 0) { const int j = min(T.j0 - 3 + line, L.jed); for (int m = 0; m < 4; m++) t[m] = __ldg(G.dxa + gidx(T, e - 2 + m, j)); }
+    else { const int i = min(T.i0 - 3 + line, L.ied); for (int m = 0; m < 4; m++) t[m] = __ldg(G.dya + gidx(T, i, e - 2 + m)); }
+  }
 #pragma unroll
-  for (int i = 0; i < 32 / NWC; i++) tpt::cp_async8(&S.area[so + i * NWC * P], G.area + g2 + i * NWC * T.NI);
-  stage_level<NF, NEP, NWC>(S, 0, src, (long long)k0 * L.plane + g2, so, T.NI);
+  for (int i = 0; i < 32 / NWC; i++) tpt::cp_async8(&S.area[so + i * NWC * P], G.area + g2 + i * dj);
+  stage_level<NF, NEP, NWC, EDGE>(S, 0, src, (long long)k0 * L.plane + g2, so, dj, cq);
 #ifdef FV3_TP2_PROF
   long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
 #endif
@@ -315,20 +416,24 @@ __device__ __forceinline__ void run_tile(const Lay& L, const DevGrid& G, const t
     const long long ko = (long long)k * L.plane;
     tpt::cp_async_wait_all();
     __syncthreads();            // level k is in buffer b; every warp is done with the previous level (buffer b^1, qi, qj, ep)
-    if (k + 1 < k1) stage_level<NF, NEP, NWC>(S, b ^ 1, src, (long long)(k + 1) * L.plane + g2, so, T.NI);
+    if (k + 1 < k1) stage_level<NF, NEP, NWC, EDGE>(S, b ^ 1, src, (long long)(k + 1) * L.plane + g2, so, dj, cq);
     if (NEP > 0) {
 #pragma unroll
-      for (int i = 0; i < 32 / NWC; i++) { const int r = 3 + T.wid + i * NWC; if (r <= TY + 2) pre(S, T, k, ko, r); }
+      for (int i = 0; i < 32 / NWC; i++) { const int r = 3 + T.wid + i * NWC; if (r <= REPI) pre(S, T, k, ko, r); }
+    }
+    if (cq) {                   // (warp-uniform, CTA-uniform) the four corner tiles of a face: q through the remapping accessors
+      stage_corner_q<NF, NEP, NWC, EDGE>(L, S, b, T, src, ko);
+      __syncthreads();
     }
     TP2_CLK(0);
 #ifdef FV3_TP2_PROF
-    compute_level<FAM, NF, NEP, WMODE, HORD, NWC>(S, b, T, ord_in, ord_ou, prof, tprev);
+    compute_level<FAM, NF, NEP, WMODE, HORD, NWC, EDGE>(L, G, S, b, T, ord_in, ord_ou, prof, tprev);
 #else
-    compute_level<FAM, NF, NEP, WMODE, HORD, NWC>(S, b, T, ord_in, ord_ou);
+    compute_level<FAM, NF, NEP, WMODE, HORD, NWC, EDGE>(L, G, S, b, T, ord_in, ord_ou);
 #endif
     if (NEP > 0) tpt::cp_async_wait_all();   // this thread's own epilogue operands (read back by the thread that fetched them)
 #pragma unroll
-    for (int i = 0; i < 32 / NWC; i++) { const int r = 3 + T.wid + i * NWC; if (r <= TY + 2) epi(S, b, T, k, ko, r); }
+    for (int i = 0; i < 32 / NWC; i++) { const int r = 3 + T.wid + i * NWC; if (r <= REPI) epi(S, b, T, k, ko, r); }
     TP2_CLK(6);
   }
 #ifdef FV3_TP2_PROF
