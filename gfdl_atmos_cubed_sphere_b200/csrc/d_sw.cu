@@ -23,8 +23,9 @@
 
 using namespace ppm;
 
-// FV3_TP_LINES: 2 (default) line-per-warp kernels on interior and frame tiles, 1 on the interior tiles only, 0 nowhere (the
-// first-generation tile kernel of tp_tile.cuh everywhere) -- A/B timing and bisecting
+// FV3_TP_LINES: 2 (default) line-per-warp kernels on the interior tiles and, for the multi-field transport, on the frame tiles;
+// 3: on the frame tiles of the single-field transports too; 1: interior tiles only; 0: nowhere (the first-generation tile kernel
+// of tp_tile.cuh everywhere) -- A/B timing and bisecting
 static int use_line_kernels() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("FV3_TP_LINES"); on = e ? atoi(e) : 2; }
@@ -815,16 +816,17 @@ __global__ void __launch_bounds__(tp2::NT, 1) k_dsw_transport2(Lay L, DevGrid G,
     });
 }
 
-// 16 warps, two CTAs per SM (one transported field: the other CTA's sweeps hide this one's barriers and epilogue loads)
+// interior tiles: 16 warps, two CTAs per SM (one transported field: the other CTA's sweeps hide this one's barriers and epilogue
+// loads); frame tiles: 32 warps, one CTA per SM (their cube-edge tables do not fit twice)
 template <int FAM, int HORD, bool EDGE>
-__global__ void __launch_bounds__(512, 2) k_dsw_vort_uv2(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ vq, const double* __restrict__ crx,
+__global__ void __launch_bounds__(EDGE ? 1024 : 512, EDGE ? 1 : 2) k_dsw_vort_uv2(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ vq, const double* __restrict__ crx,
                                                        const double* __restrict__ cry, const double* __restrict__ xfx,
                                                        const double* __restrict__ yfx, const double* __restrict__ u,
                                                        const double* __restrict__ v, const double* __restrict__ ke,
                                                        double* __restrict__ uo, double* __restrict__ vo, int hord_vt, int nk, int kch) {
   const double* src[5] = {crx, cry, xfx, yfx, vq};
   const int ord_ou[1] = {hord_vt}, ord_in[1] = {(hord_vt == 10) ? 8 : hord_vt};
-  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, 16, EDGE>(L, G, M, src, nk, kch, ord_in, ord_ou,
+  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, EDGE ? 32 : 16, EDGE>(L, G, M, src, nk, kch, ord_in, ord_ou,
     [&](tp2::Smem<1, 0, EDGE>&, const tp2::Geo&, int, long long, int) {},
     [&](tp2::Smem<1, 0, EDGE>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
       const int c = T.lane, i = T.i0 - 3 + c, j = T.j0 - 3 + r;
@@ -930,7 +932,9 @@ static int launch_vort_uv_t(fv3_ctx* c, const double* vq, const double* u, const
   }
   tpt::TileMap Min, Mfr; int n_in, n_fr;
   tpt::tile_maps(c->L, Min, Mfr, n_in, n_fr);
-  const bool lines = FM != 2 && use_line_kernels(), lines_fr = lines && use_line_kernels() > 1;
+  // frame tiles of a single transported field: the first-generation kernel (two CTAs per SM) is faster than the line kernel with its
+  // cube-edge tables (one CTA per SM): measured 217 vs 281 us at C384L79 (profiles/r2_dsw_kernels.md); FV3_TP_LINES=3 forces lines
+  const bool lines = FM != 2 && use_line_kernels(), lines_fr = lines && use_line_kernels() > 2;
   if (lines) {
     constexpr int F2 = FM == 2 ? 0 : FM;
     const int kch = tp2::level_chunk(nk), nch = (nk + kch - 1) / kch, kch_fr = (kch + 1) / 2, nch_fr = (nk + kch_fr - 1) / kch_fr;
@@ -938,7 +942,7 @@ static int launch_vort_uv_t(fv3_ctx* c, const double* vq, const double* u, const
 #define VU2_LAUNCH1(H_, E_, MAP_, N_)                                                                                             \
     do {                                                                                                                          \
       FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_vort_uv2<F2, H_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<1, 0, E_>))); \
-      k_dsw_vort_uv2<F2, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), 512, sizeof(tp2::Smem<1, 0, E_>), c->stream>>>(                                           \
+      k_dsw_vort_uv2<F2, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), E_ ? 1024 : 512, sizeof(tp2::Smem<1, 0, E_>), c->stream>>>(                                           \
           c->L, c->G, MAP_, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, h, nk, E_ ? kch_fr : kch); \
     } while (0)
 #define VU2_LAUNCH(H_)                                                 \

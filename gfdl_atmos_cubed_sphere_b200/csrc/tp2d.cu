@@ -82,12 +82,12 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, tpt::
 
 // interior tiles of the fused height update (update_dz_d, nh_utils.F90:282-299) in the line-per-warp form (tp_line.cuh)
 template <int FAM, int HORD, bool EDGE>
-__global__ void __launch_bounds__(512, 2) k_tp_zn2(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ q, const double* __restrict__ crx,
+__global__ void __launch_bounds__(EDGE ? 1024 : 512, EDGE ? 1 : 2) k_tp_zn2(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ q, const double* __restrict__ crx,
                                                  const double* __restrict__ cry, const double* __restrict__ xfx, const double* __restrict__ yfx,
                                                  int ord_in_, int ord_ou_, tpt::ZnEpi Z, int nk, int kch) {
   const double* src[5] = {crx, cry, xfx, yfx, q};
   const int ord_in[1] = {ord_in_}, ord_ou[1] = {ord_ou_};
-  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, 16, EDGE>(L, G, M, src, nk, kch, ord_in, ord_ou,
+  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, EDGE ? 32 : 16, EDGE>(L, G, M, src, nk, kch, ord_in, ord_ou,
     [&](tp2::Smem<1, 0, EDGE>&, const tp2::Geo&, int, long long, int) {},
     [&](tp2::Smem<1, 0, EDGE>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
       const int c = T.lane, i = T.i0 - 3 + c, j = T.j0 - 3 + r;
@@ -125,8 +125,8 @@ int launch_tp2d(fv3_ctx* c, const Tp2d& a) {
   }
   const tpt::ZnEpi Z{a.zn, a.zn_dfx, a.zn_dfy, a.zn ? c->d_kdbl : nullptr, a.zn_slot};
   if (a.zn && (a.ra_x || a.ra_y || a.mfx)) return fv3_fail(c, -1, "fv_tp_2d: the fused height update takes no ra_x / ra_y / mfx");
-  // the fused height update with the common schemes: line-per-warp kernels (tp_line.cuh) on the interior and on the frame tiles
-  // (FV3_TP_LINES=1: interior only, 0: the first-generation tile kernel everywhere)
+  // the fused height update with the common schemes: line-per-warp kernel (tp_line.cuh) on the interior tiles; the frame tiles keep
+  // the first-generation kernel (faster for a single field, see launch_vort_uv_t in d_sw.cu) unless FV3_TP_LINES=3
   static int lines_on = -1;
   if (lines_on < 0) { const char* e = getenv("FV3_TP_LINES"); lines_on = e ? atoi(e) : 2; }
   if (a.zn && lines_on && !hord_is_rare(a.hord)) {
@@ -134,14 +134,14 @@ int launch_tp2d(fv3_ctx* c, const Tp2d& a) {
 #define ZN2_LAUNCH1(F_, H_, E_, MAP_, N_)                                                                                          \
     do {                                                                                                                           \
       FV3_CUDA(c, cudaFuncSetAttribute(k_tp_zn2<F_, H_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<1, 0, E_>))); \
-      k_tp_zn2<F_, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), 512, sizeof(tp2::Smem<1, 0, E_>), c->stream>>>(L, c->G, MAP_, a.q, a.crx, a.cry, a.xfx, a.yfx,    \
+      k_tp_zn2<F_, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), E_ ? 1024 : 512, sizeof(tp2::Smem<1, 0, E_>), c->stream>>>(L, c->G, MAP_, a.q, a.crx, a.cry, a.xfx, a.yfx,    \
                                                                                   ord_in, a.hord, Z, a.nk, E_ ? kch_fr : kch);     \
       c->launches++;                                                                                                               \
     } while (0)
 #define ZN2_LAUNCH(F_, H_)                                                          \
     do {                                                                            \
       if (n_in) { ZN2_LAUNCH1(F_, H_, false, Min, n_in); n_in = 0; }                \
-      if (n_fr && lines_on > 1) { ZN2_LAUNCH1(F_, H_, true, Mfr, n_fr); n_fr = 0; } \
+      if (n_fr && lines_on > 2) { ZN2_LAUNCH1(F_, H_, true, Mfr, n_fr); n_fr = 0; } \
     } while (0)
     if (a.hord == 10) ZN2_LAUNCH(1, 10);
     else if (a.hord == 8) ZN2_LAUNCH(1, 8);

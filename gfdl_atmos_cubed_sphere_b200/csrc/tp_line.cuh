@@ -48,8 +48,11 @@ enum { W_AREA = 0, W_MASS = 1, W_RAW = 2 };
 template <int NF, int NEP = 0, bool EDGE = false>
 struct Smem {
   double g0[GUARD];
-  // frame tiles: dxa (x lines) / dya (y lines) at the four cells around the low (e = 1) and the high (e = n) cube edge of every line
-  // of the tile, [direction][line][edge][e-2 .. e+1] -- k-invariant, filled once per tile (the two-sided edge value :376-377, 647-648)
+  // frame tiles: the fluxes through the cube-edge faces of every line (sweep index 1..3 and n-2..n: six slots), evaluated densely by
+  // dense_edge_fluxes before the line tasks run, [field][direction][line][slot]
+  double ef[EDGE ? NF * 2 * 32 * 6 : 1];
+  // frame tiles: dxa (x lines) / dya (y lines) at the four cells around the low (e = 1) and the high (e = n) cube edge of every
+  // line, [direction][line][edge][e-2 .. e+1] -- k-invariant, filled once per tile (the two-sided edge value, :376-377, 647-648)
   double et[EDGE ? 2 * 32 * 2 * 4 : 1];
   double in[2][4 + NF][ASZ];   // per level, double-buffered: crx, cry, xfx, yfx, q_0 .. q_{NF-1}
   double area[ASZ];
@@ -72,20 +75,19 @@ __device__ __forceinline__ double dn1(double x) { return __shfl_down_sync(0xffff
 // (64 registers per thread) instruction-level parallelism is what hides the fp64 / shuffle latencies (ncu, first version of
 // this file: 55 % issue-active with the fields evaluated one after the other).
 constexpr int ORD_RT = 99;
-// Frame tiles (EDGE = true): a line that crosses a cube edge carries the reference's one-sided cells / faces.  ic = base + lane
-// is the sweep index (i for x lines, j for y lines) of a lane's cell, n = npx (npy), d -> dxa (dya) at sweep index 0 of the line
-// with stride ds.  The few lanes concerned re-derive their (bl, br) / al from the line in shared memory (tp_core.F90:643-681
-// monotone family, :374-392 and :536-545 unlimited family); the other lanes of the warp idle meanwhile.
-struct EdgeLine { bool on; int base, n; const double* et; };   // et -> this line's [edge][4] metric table in shared memory
-__device__ __forceinline__ double edge_avg4(double qm2, double qm1, double q0, double qp1, const double* d) {   // ppm::edge_avg on the tabulated metric
-  return 0.5 * (((2. * d[1] + d[0]) * qm1 - d[1] * qm2) / (d[0] + d[1]) + ((2. * d[2] + d[3]) * q0 - d[2] * qp1) / (d[2] + d[3]));
-}
+// Frame tiles (EDGE = true): the faces next to a cube edge (sweep index 1..3 and n-2..n) take the reference's one-sided operator
+// (tp_core.F90:374-392, 536-545, 643-681).  Their fluxes are NOT formed by the lanes that own them -- three lanes of a line would
+// run the long operator while 29 wait, once per line, field and sweep -- but densely, all lanes busy, by dense_edge_fluxes into
+// Smem::ef; the line task only picks them up.  ic = base + lane is the sweep index of a lane's cell / low face, n = npx (npy),
+// ef -> the six slots of this line for field 0 (field stride 2*32*6).
+struct EdgeLine { bool on; int base, n; const double* ef; };
+constexpr int EF_FIELD = 2 * 32 * 6;
+__device__ __forceinline__ int edge_slot(int ic, int n) { return (ic >= 1 && ic <= 3) ? ic - 1 : (ic >= n - 2 && ic <= n) ? ic - (n - 2) + 3 : -1; }
 template <int FAM, int NF, int ORD, bool EDGE>
 __device__ __forceinline__ void line_fluxes(const double (*__restrict__ q)[ASZ], int o, int sa, int lane, double cl, double cr,
                                             const int (&ord)[NF], double (&q0)[NF], double (&flux)[NF], const EdgeLine& E) {
   using namespace ppm;
-  const int ic = EDGE ? E.base + lane : 0;
-  const bool ecell = EDGE && E.on && ((ic >= 0 && ic <= 2) || (ic >= E.n - 2 && ic <= E.n));   // cells with one-sided (bl, br)
+  const int eslot = (EDGE && E.on) ? edge_slot(E.base + lane, E.n) : -1;   // >= 0: this lane's low face is a cube-edge face
   if (FAM == 1) {
     double qm[NF], qp[NF], dm0[NF], dmm[NF], dmp[NF], al0[NF], al1[NF], bl[NF], br[NF], FR[NF], FL[NF];
 #pragma unroll
@@ -96,7 +98,7 @@ __device__ __forceinline__ void line_fluxes(const double (*__restrict__ q)[ASZ],
 #pragma unroll
     for (int f = 0; f < NF; f++) {
       dmm[f] = up1(dm0[f]);
-      if (ORD != 8 || EDGE) dmp[f] = dn1(dm0[f]);
+      if (ORD != 8) dmp[f] = dn1(dm0[f]);
     }
 #pragma unroll
     for (int f = 0; f < NF; f++) al0[f] = 0.5 * (qm[f] + q0[f]) + r3 * (dmm[f] - dm0[f]);
@@ -109,36 +111,6 @@ __device__ __forceinline__ void line_fluxes(const double (*__restrict__ q)[ASZ],
       const double xt = 2. * dm0[f];
       const double bl8 = -fsign(mn(fabs(xt), fabs(al0[f] - q0[f])), xt);
       const double br8 = fsign(mn(fabs(xt), fabs(al1[f] - q0[f])), xt);
-      if (EDGE && ecell) {   // tp_core.F90:643-681 (every monotone scheme), cell form of ppm::cell_mono
-        const double* ql = q[f] + o;
-        auto qa = [&](int i) { return ql[(i - ic) * sa]; };
-        const int n = E.n;
-        double b_l, b_r;
-        if (ic <= 1) {
-          const double a = qa(-1), b = qa(0), c = qa(1), d = qa(2);
-          double xe = edge_avg4(a, b, c, d, E.et);
-          xe = mx(xe, mn(mn(a, b), mn(c, d)));
-          xe = mn(xe, mx(mx(a, b), mx(c, d)));
-          if (ic == 0) { b_l = s14 * dmm[f] + s11 * (a - b); b_r = xe - b; }
-          else { b_l = xe - c; b_r = (s15 * c + s11 * d - s14 * dmp[f]) - c; }
-        } else if (ic == 2) {
-          b_l = (s15 * qa(1) + s11 * q0[f] - s14 * dm0[f]) - q0[f];
-          b_r = al1[f] - q0[f];
-        } else if (ic == n - 2) {
-          b_l = al0[f] - q0[f];
-          b_r = (s15 * qa(n - 1) + s11 * q0[f] + s14 * dm0[f]) - q0[f];
-        } else {
-          const double a = qa(n - 2), b = qa(n - 1), c = qa(n), d = qa(n + 1);
-          double xe = edge_avg4(a, b, c, d, E.et + 4);
-          xe = mx(xe, mn(mn(a, b), mn(c, d)));
-          xe = mn(xe, mx(mx(a, b), mx(c, d)));
-          if (ic == n - 1) { b_l = (s15 * b + s11 * a + s14 * dmm[f]) - b; b_r = xe - b; }
-          else { b_l = xe - c; b_r = s11 * (d - c) - s14 * dmp[f]; }
-        }
-        pert_std(b_l, b_r);
-        bl[f] = b_l; br[f] = b_r;
-        continue;
-      }
       if (ORD == 8) { bl[f] = bl8; br[f] = br8; continue; }
       // iord 10 (:605-627 with the pmp / lac constraint), branch-free: the constraint applies where the parabola overshoots
       double b_l = al0[f] - q0[f], b_r = al1[f] - q0[f];
@@ -165,6 +137,7 @@ __device__ __forceinline__ void line_fluxes(const double (*__restrict__ q)[ASZ],
     for (int f = 0; f < NF; f++) {
       const double FRm = up1(FR[f]);
       flux[f] = cl > 0. ? FRm : FL[f];
+      if (EDGE && eslot >= 0) flux[f] = E.ef[f * EF_FIELD + eslot];
     }
   } else {
     double qm[NF], al0[NF], al1[NF], F1R[NF], F1L[NF];
@@ -175,17 +148,6 @@ __device__ __forceinline__ void line_fluxes(const double (*__restrict__ q)[ASZ],
       const double qm2 = q[f][o - 2 * sa], qp = q[f][o + sa];
       qm[f] = q[f][o - sa]; q0[f] = q[f][o];
       double a = p1 * (qm[f] + q0[f]) + p2 * (qm2 + qp);
-      if (EDGE && E.on && ((ic >= 0 && ic <= 2) || (ic >= E.n - 1 && ic <= E.n + 1))) {   // faces with a one-sided edge value (:374-392)
-        const double* ql = q[f] + o;
-        auto qa = [&](int i) { return ql[(i - ic) * sa]; };
-        const int n = E.n;
-        if (ic == 0) a = c1 * qa(-2) + c2 * qa(-1) + c3 * qa(0);
-        else if (ic == 1) a = edge_avg4(qa(-1), qa(0), qa(1), qa(2), E.et);
-        else if (ic == 2) a = c3 * qa(1) + c2 * qa(2) + c1 * qa(3);
-        else if (ic == n - 1) a = c1 * qa(n - 3) + c2 * qa(n - 2) + c3 * qa(n - 1);
-        else if (ic == n) a = edge_avg4(qa(n - 2), qa(n - 1), qa(n), qa(n + 1), E.et + 4);
-        else a = c3 * qa(n) + c2 * qa(n + 1) + c1 * qa(n + 2);
-      }
       if (iord < 0) a = mx(0., a);
       al0[f] = a;
     }
@@ -208,7 +170,6 @@ __device__ __forceinline__ void line_fluxes(const double (*__restrict__ q)[ASZ],
           }
         }
       } else sm_ = 3. * fabs(b0) < fabs(bl - br);
-      if (EDGE && E.on && (ic == 0 || ic == 1 || ic == E.n - 1 || ic == E.n)) sm_ = bl * br < 0.;   // :536-545
       smt[f] = sm_;
       F1R[f] = (1. - cr) * (br - cr * b0);
       F1L[f] = (1. + cl) * (bl + cl * b0);
@@ -221,6 +182,7 @@ __device__ __forceinline__ void line_fluxes(const double (*__restrict__ q)[ASZ],
       double fl = cl > 0. ? qm[f] : q0[f];
       if (smtA || smt[f]) fl = fl + (cl > 0. ? F1Rm : F1L[f]);
       flux[f] = fl;
+      if (EDGE && eslot >= 0) flux[f] = E.ef[f * EF_FIELD + eslot];
     }
   }
 }
@@ -259,7 +221,8 @@ __device__ __forceinline__ void outer_line(const double* __restrict__ cr_, const
     for (int f = 0; f < NF; f++) {
       const int o1[1] = {ord[f]};
       double q1[1], f1[1];
-      line_fluxes<FAM, 1, ORD, EDGE>(q + f, o, sa, lane, cl, cr, o1, q1, f1, E);
+      const EdgeLine Ef{E.on, E.base, E.n, E.ef + f * EF_FIELD};
+      line_fluxes<FAM, 1, ORD, EDGE>(q + f, o, sa, lane, cl, cr, o1, q1, f1, Ef);
       fo[f] = f1[0];
     }
   } else line_fluxes<FAM, NF, ORD, EDGE>(q, o, sa, lane, cl, cr, ord, q0, fo, E);
@@ -318,6 +281,54 @@ __device__ __forceinline__ void stage_corner_q(const Lay& L, Smem<NF, NEP, EDGE>
   }
 }
 
+// dxa / dya of a line at the cells around its two cube edges, from the per-tile table: sweep indices -1..2 and n-2..n+1
+struct EdgeMetric {
+  const double* t; int n;
+  __device__ __forceinline__ double operator()(int i) const { return i <= 2 ? t[i + 1] : t[4 + i - (n - 2)]; }
+};
+// Frame tiles: the fluxes through the cube-edge faces of lines l0..l1 of both directions for all fields, one face per thread
+// (dense enumeration: every lane of the participating warps has a face), by the general per-face operator of the first-generation
+// kernel (tpt::edge_flux -> ppm::flux_scalar: upwind cell first, one-sided (bl, br) / al of that cell from the line in shared
+// memory, dxa / dya from the per-tile table).  qx / qy: the field as the x / y sweeps see it.
+template <int NF, int NEP, int NWC>
+__device__ __forceinline__ void dense_edge_fluxes(const Lay& L, const DevGrid& G, Smem<NF, NEP, true>& S, int b, const Geo& T,
+                                                  const double (*qx)[ASZ], const double (*qy)[ASZ], const int (&ord)[NF], int l0, int l1) {
+  // slots present in this tile, per direction: face index 1..3 (slots 0..2) and n-2..n (slots 3..5) that fall on columns 3..29
+  int sx[6], sy[6], nsx = 0, nsy = 0;
+#pragma unroll
+  for (int s_ = 0; s_ < 6; s_++) {
+    const int ix = (s_ < 3 ? 1 + s_ : L.npx - 5 + s_) - (T.i0 - 3), iy = (s_ < 3 ? 1 + s_ : L.npy - 5 + s_) - (T.j0 - 3);
+    if (ix >= 3 && ix <= TX + 3) sx[nsx++] = s_;
+    if (iy >= 3 && iy <= TY + 3) sy[nsy++] = s_;
+  }
+  const int nl = l1 - l0 + 1, ntx = nsx * nl, nty = nsy * nl, per_f = ntx + nty, total = per_f * NF;
+  for (int e = threadIdx.x; e < total; e += NWC * 32) {
+    const int f = e / per_f, r_ = e - f * per_f;
+    const bool xd = r_ < ntx;
+    const int q_ = xd ? r_ : r_ - ntx;
+    const int si = q_ / nl, line = l0 + q_ - si * nl;   // slot-major: the lanes of a warp share the face, i.e. the one-sided branch
+    int slot = 0;
+#pragma unroll
+    for (int m = 0; m < 6; m++) if (m == si) slot = xd ? sx[m] : sy[m];
+    const int n = xd ? L.npx : L.npy;
+    const int face = slot < 3 ? 1 + slot : n - 5 + slot;          // sweep index of the face
+    int io = 0; const int* ordp = ord;
+#pragma unroll
+    for (int m = 0; m < NF; m++) if (m == f) io = ordp[m];
+    if (xd) {
+      const int r = line, c = face - (T.i0 - 3);
+      const tpt::SAcc qa{qx[f] + r * P, 1, T.i0 - 3};
+      const EdgeMetric da{S.et + r * 8, n};
+      S.ef[f * EF_FIELD + r * 6 + slot] = ppm::flux_scalar<false>(qa, da, face, S.in[b][A_CRX][r * P + c], io, n, true);
+    } else {
+      const int c = line, r = face - (T.j0 - 3);
+      const tpt::SAcc qa{qy[f] + c, P, T.j0 - 3};
+      const EdgeMetric da{S.et + 256 + c * 8, n};
+      S.ef[f * EF_FIELD + 192 + c * 6 + slot] = ppm::flux_scalar<false>(qa, da, face, S.in[b][A_CRY][r * P + c], io, n, true);
+    }
+  }
+}
+
 #ifdef FV3_TP2_PROF
 #define TP2_CLK(i) do { const long long t_ = clock64(); prof[i] += t_ - tprev; tprev = t_; } while (0)
 #else
@@ -341,32 +352,44 @@ __device__ __forceinline__ void compute_level(const Lay& L, const DevGrid& G, Sm
   const int yc0 = (T.wid + NWC / 2) & (NWC - 1);
   const bool cube = EDGE && L.cube;
   const double (*qy)[ASZ] = (EDGE && T.corner) ? S.qi : S.in[b] + A_Q;   // the field as the y sweeps see it
+  if constexpr (EDGE) {
+    if (cube) {   // (CTA-uniform) inner fluxes through the cube-edge faces of all 32 + 32 lines
+      dense_edge_fluxes<NF, NEP, NWC>(L, G, S, b, T, S.in[b] + A_Q, qy, ord_in, 0, QH - 1);
+      __syncthreads();
+    }
+  }
 #pragma unroll
   for (int i = 0; i < LPW; i++) {
     const int r = T.wid + i * NWC;
-    const EdgeLine E{cube, T.i0 - 3, L.npx, S.et + r * 8};
+    const EdgeLine E{cube, T.i0 - 3, L.npx, S.ef + r * 6};
     inner_line<FAM, NF, OI, EDGE>(S.in[b][A_CRX], S.in[b][A_XFX], S.area, S.in[b] + A_Q, S.qj, r * P + T.lane, 1, T.lane, ord_in, finx[i], E);
   }
   TP2_CLK(1);
 #pragma unroll
   for (int i = 0; i < LPW; i++) {
     const int c = yc0 + i * NWC;
-    const EdgeLine E{cube, T.j0 - 3, L.npy, S.et + 256 + c * 8};
+    const EdgeLine E{cube, T.j0 - 3, L.npy, S.ef + 192 + c * 6};
     inner_line<FAM, NF, OI, EDGE>(S.in[b][A_CRY], S.in[b][A_YFX], S.area, qy, S.qi, T.lane * P + c, P, T.lane, ord_in, finy[i], E);
   }
   TP2_CLK(2);
   __syncthreads();
   TP2_CLK(3);
+  if constexpr (EDGE) {
+    if (cube) {   // outer fluxes through the cube-edge faces of the 26 + 26 lines of the tile proper
+      dense_edge_fluxes<NF, NEP, NWC>(L, G, S, b, T, S.qi, S.qj, ord_ou, 3, TY + 2);
+      __syncthreads();
+    }
+  }
 #pragma unroll
   for (int i = 0; i < LPW; i++) {
     const int r = T.wid + i * NWC;
-    const EdgeLine E{cube, T.i0 - 3, L.npx, S.et + r * 8};
+    const EdgeLine E{cube, T.i0 - 3, L.npx, S.ef + r * 6};
     if (r >= 3 && r <= TY + 2) outer_line<FAM, NF, WMODE, OO, EDGE>(S.in[b][A_CRX], S.in[b][A_XFX], S.qi, r * P + T.lane, 1, T.lane, ord_ou, finx[i], E);
   }
 #pragma unroll
   for (int i = 0; i < LPW; i++) {
     const int c = yc0 + i * NWC;
-    const EdgeLine E{cube, T.j0 - 3, L.npy, S.et + 256 + c * 8};
+    const EdgeLine E{cube, T.j0 - 3, L.npy, S.ef + 192 + c * 6};
     if (c >= 3 && c <= TX + 2) outer_line<FAM, NF, WMODE, OO, EDGE>(S.in[b][A_CRY], S.in[b][A_YFX], S.qj, T.lane * P + c, P, T.lane, ord_ou, finy[i], E);
   }
   TP2_CLK(4);
