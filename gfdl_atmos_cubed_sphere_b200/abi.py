@@ -16,7 +16,7 @@ _dp = C.POINTER(C.c_double)
 FIELDS = ["U", "V", "W", "DELZ", "PT", "DELP", "QCON", "CAPPA", "PHIS", "OMGA", "UA", "VA", "UC", "VC",
           "MFX", "MFY", "CX", "CY", "DELPC", "PTC", "UT", "VT", "DIVGD", "CRX", "CRY", "XFX", "YFX",
           "GZ", "ZH", "PKC", "PK3", "WS3", "WS", "PE", "PELN", "PK", "PKZ", "HEAT", "DISS",
-          "WORK_Q", "WORK_FX", "WORK_FY", "WORK_RAX", "WORK_RAY", "DP1"]
+          "WORK_Q", "WORK_FX", "WORK_FY", "WORK_RAX", "WORK_RAY", "DP1", "DU", "DV"]
 FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
 
 HALO_GROUPS = ["UVW", "GZ", "DIVGD_UCVC", "DELP_PT", "ZH_PKC", "UV_EDGE", "TRACER", "HEAT", "OMGA"]

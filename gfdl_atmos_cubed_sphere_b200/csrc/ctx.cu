@@ -66,6 +66,7 @@ static void set_dims(fv3_ctx* c) {
   d[FV3_WORK_RAX] = {b.is, nic, b.jsd, nja, kz, 0};
   d[FV3_WORK_RAY] = {b.isd, nia, b.js, njc, kz, 0};
   d[FV3_DP1] = A(kz);
+  d[FV3_DU] = d[FV3_U]; d[FV3_DV] = d[FV3_V];
 }
 
 // native (Fortran) <-> padded device plane repacking.  dir=0: native->device, 1: device->native
@@ -374,6 +375,15 @@ int fv3_pt_to_theta(fv3_ctx* c, double zvir) { STAGE_PROLOGUE(c) int rc = stage_
 int fv3_dcon_heating(fv3_ctx* c, double bdt) { STAGE_PROLOGUE(c) int rc = stage_dcon_heating(c, bdt); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_geopk(fv3_ctx* c, int cg) { STAGE_PROLOGUE(c) int rc = stage_geopk(c, cg); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_one_grad_p(fv3_ctx* c, double dt) { STAGE_PROLOGUE(c) int rc = stage_one_grad_p(c, dt); if (rc) return rc; STAGE_EPILOGUE(c) }
+// split_p_grad (non-hydrostatic) / grad1_p_update (hydrostatic) with beta_d >= 0 (dyn_core.F90:1018-1028); FV3_DU, FV3_DV carry the
+// hydrostatic increment from call to call
+int fv3_split_p_grad(fv3_ctx* c, double dt, double beta_d) {
+  STAGE_PROLOGUE(c)
+  if (beta_d < 0.) return fv3_fail(c, -1, "split_p_grad: beta_d must be >= 0");
+  int rc = c->f.hydrostatic ? stage_one_grad_p(c, dt, beta_d) : stage_nh_p_grad(c, dt, beta_d);
+  if (rc) return rc;
+  STAGE_EPILOGUE(c)
+}
 int fv3_gz_init(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_gz_init(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_copy_field(fv3_ctx* c, int dst, int src) { STAGE_PROLOGUE(c) int rc = stage_copy_field(c, dst, src); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_zero_field(fv3_ctx* c, int f) { STAGE_PROLOGUE(c) int rc = stage_zero_field(c, f); if (rc) return rc; STAGE_EPILOGUE(c) }

@@ -38,7 +38,9 @@ extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, i
     if (fa.hydrostatic != f0.hydrostatic || fa.sw_test_case != f0.sw_test_case || fa.d_con != f0.d_con || fa.use_cond != f0.use_cond ||
         fa.nord != f0.nord || ctxs[a]->L.npz != ctxs[0]->L.npz || ctxs[a]->L.npx != ctxs[0]->L.npx)
       return fv3_fail(ctxs[a], -1, "dyn_core: the linked contexts disagree on hydrostatic / sw_test_case / d_con / use_cond / nord / npx / npz");
-    if (ctxs[a]->f.beta != 0.0) return fv3_fail(ctxs[a], -2, "dyn_core: beta != 0 (split_p_grad/one_grad_p) not supported");
+    // beta > 0: split_p_grad / grad1_p_update; beta < -0.1 selects one_grad_p in the non-hydrostatic branch (:1029-1030), not built
+    if (fa.beta != f0.beta) return fv3_fail(ctxs[a], -1, "dyn_core: the linked contexts disagree on beta");
+    if (fa.beta < 0.0) return fv3_fail(ctxs[a], -2, "dyn_core: beta < 0 (one_grad_p in the non-hydrostatic branch) not supported");
     // d_ext > 0 builds divg2 (dyn_core.F90:745-747, 791-797, 828-845), which only one_grad_p reads (:1021, :1030): with nh_p_grad
     // (non-hydrostatic, beta = 0) it has no effect on any result and is accepted; the hydrostatic use is not built
     if (ctxs[a]->f.d_ext > 0.0 && ctxs[a]->f.hydrostatic)
@@ -52,6 +54,9 @@ extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, i
   FORALL(stage_zero_field(c, FV3_CY)) FORALL(stage_zero_field(c, FV3_HEAT))
   int rc;
   const bool hydrostatic = ctxs[0]->f.hydrostatic != 0;
+  // beta > 0 (dyn_core.F90:278-283): the hydrostatic pressure-gradient increments du, dv of the previous substep start at zero
+  const double beta = ctxs[0]->f.beta;
+  if (beta > 0.) { FORALL(stage_zero_field(c, FV3_DU)) FORALL(stage_zero_field(c, FV3_DV)) }
   // Overlapped delp/pt exchange (fv3_halo_start / fv3_halo_wait) is OFF by default: measured at N = 2, C384L79 it LOSES 2.6 %
   // (209.8 vs 204.4 ms per step) -- the NCCL send/recv kernels of the side stream spin on SMs that the concurrent
   // update_dz_d / Riem_Solver3 kernels need.  FV3_HALO_OVERLAP=1 turns it on for experiments.
@@ -81,7 +86,8 @@ extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, i
       if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;
       FORALL(stage_geopk(c, 0))
       if (last_step) { FORALL(stage_copy_field(c, FV3_PK, FV3_PKC)) }   // :1001-1010: remap_step .and. hydrostatic: pk = pkc
-      FORALL(stage_one_grad_p(c, dt))
+      if (beta > 0.) { FORALL(stage_one_grad_p(c, dt, it == 1 ? 0. : beta)) }   // :1018-1019 grad1_p_update, beta_d (:404-406)
+      else { FORALL(stage_one_grad_p(c, dt)) }
       if (last_step && linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_UV_EDGE))) return rc;
       continue;
     }
@@ -111,7 +117,8 @@ extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, i
     if (last_step) { FORALL(stage_pe_halo(c)) }                                           // :952-953
     FORALL(stage_pk3_halo(c))                                                             // :958
     FORALL(stage_gz_from_zh(c))                                                           // :982-989
-    FORALL(stage_nh_p_grad(c, dt))                                                        // :1032
+    if (beta > 0.) { FORALL(stage_nh_p_grad(c, dt, it == 1 ? 0. : beta)) }                // :1027-1028 split_p_grad
+    else { FORALL(stage_nh_p_grad(c, dt)) }                                               // :1032
     if (last_step && linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_UV_EDGE))) return rc;   // :1151-1163
   }
   // dyn_core.F90:1300-1356: the dissipative heating accumulated over the substeps is filtered and added to pt

@@ -171,13 +171,13 @@ int stage_riem_solver3(fv3_ctx* c, double dt, int last_call);
 int stage_pk3_halo(fv3_ctx* c);
 int stage_pe_halo(fv3_ctx* c);
 int stage_gz_from_zh(fv3_ctx* c);
-int stage_nh_p_grad(fv3_ctx* c, double dt);
+int stage_nh_p_grad(fv3_ctx* c, double dt, double beta_d = -1.);   // beta_d >= 0: split_p_grad
 int stage_geopk(fv3_ctx* c, int cg);
 int stage_del2_cubed(fv3_ctx* c, int field, double cd, int nmax);
 int stage_dcon_heating(fv3_ctx* c, double bdt);
 int stage_pt_to_theta(fv3_ctx* c, double zvir);
 int fv3_n_con(const fv3_flags_t& f, int npz);
-int stage_one_grad_p(fv3_ctx* c, double dt);
+int stage_one_grad_p(fv3_ctx* c, double dt, double beta_d = -1.);  // beta_d >= 0: grad1_p_update
 int stage_gz_init(fv3_ctx* c);
 int stage_copy_field(fv3_ctx* c, int dst, int src);
 int stage_zero_field(fv3_ctx* c, int f);

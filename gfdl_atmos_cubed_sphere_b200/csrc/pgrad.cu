@@ -275,35 +275,51 @@ __global__ void __launch_bounds__(TI* TJ) k_nh_top(Lay L, double* __restrict__ p
   ppb[LIDX(L, i, j)] = 0.;
   pkb[LIDX(L, i, j)] = top_value;
 }
+// SPLIT: split_p_grad (dyn_core.F90:1795-1905, beta > 0): u first takes beta times the hydrostatic increment of the PREVIOUS substep
+// (du, dv), the current one is stored and enters with weight alpha = 1 - beta
+template <bool SPLIT>
 __global__ void __launch_bounds__(TI* TJ) k_nh_pgrad(Lay L, DevGrid G, const double* __restrict__ pp, const double* __restrict__ pk,
                                                     const double* __restrict__ gz, const double* __restrict__ dpb, double* __restrict__ u,
-                                                    double* __restrict__ v, double dt) {
+                                                    double* __restrict__ v, double* __restrict__ du, double* __restrict__ dv, double beta,
+                                                    double dt) {
   PLANE_IJK
   if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
   const long long P = L.plane;
   const long long o = ko + LIDX(L, i, j);
+  const double alpha = 1. - beta;
   auto WKo = [&](long long oo) { return __ldg(pk + oo + P) - __ldg(pk + oo); };
   if (i <= L.ie) {
     const long long e = o + 1;
     const double du1 = dt / (WKo(o) + WKo(e)) *
                        ((__ldg(gz + o + P) - __ldg(gz + e)) * (__ldg(pk + e + P) - __ldg(pk + o)) +
                         (__ldg(gz + o) - __ldg(gz + e + P)) * (__ldg(pk + o + P) - __ldg(pk + e)));
-    u[o] = (u[o] + du1 + dt / (__ldg(dpb + o) + __ldg(dpb + e)) *
-                             ((__ldg(gz + o + P) - __ldg(gz + e)) * (__ldg(pp + e + P) - __ldg(pp + o)) +
-                              (__ldg(gz + o) - __ldg(gz + e + P)) * (__ldg(pp + o + P) - __ldg(pp + e)))) * G2(rdx, i, j);
+    const double nh = dt / (__ldg(dpb + o) + __ldg(dpb + e)) *
+                      ((__ldg(gz + o + P) - __ldg(gz + e)) * (__ldg(pp + e + P) - __ldg(pp + o)) +
+                       (__ldg(gz + o) - __ldg(gz + e + P)) * (__ldg(pp + o + P) - __ldg(pp + e)));
+    if (SPLIT) {
+      const double u1 = u[o] + beta * du[o];
+      du[o] = du1;
+      u[o] = (u1 + alpha * du1 + nh) * G2(rdx, i, j);
+    } else u[o] = (u[o] + du1 + nh) * G2(rdx, i, j);
   }
   if (j <= L.je) {
     const long long n = o + L.NI;
     const double dv1 = dt / (WKo(o) + WKo(n)) *
                        ((__ldg(gz + o + P) - __ldg(gz + n)) * (__ldg(pk + n + P) - __ldg(pk + o)) +
                         (__ldg(gz + o) - __ldg(gz + n + P)) * (__ldg(pk + o + P) - __ldg(pk + n)));
-    v[o] = (v[o] + dv1 + dt / (__ldg(dpb + o) + __ldg(dpb + n)) *
-                             ((__ldg(gz + o + P) - __ldg(gz + n)) * (__ldg(pp + n + P) - __ldg(pp + o)) +
-                              (__ldg(gz + o) - __ldg(gz + n + P)) * (__ldg(pp + o + P) - __ldg(pp + n)))) * G2(rdy, i, j);
+    const double nh = dt / (__ldg(dpb + o) + __ldg(dpb + n)) *
+                      ((__ldg(gz + o + P) - __ldg(gz + n)) * (__ldg(pp + n + P) - __ldg(pp + o)) +
+                       (__ldg(gz + o) - __ldg(gz + n + P)) * (__ldg(pp + o + P) - __ldg(pp + n)));
+    if (SPLIT) {
+      const double v1 = v[o] + beta * dv[o];
+      dv[o] = dv1;
+      v[o] = (v1 + alpha * dv1 + nh) * G2(rdy, i, j);
+    } else v[o] = (v[o] + dv1 + nh) * G2(rdy, i, j);
   }
 }
 
-int stage_nh_p_grad(fv3_ctx* c, double dt) {
+// beta_d < 0: nh_p_grad (dyn_core.F90:1032); beta_d >= 0: split_p_grad with that beta (:1028; 0 on the first substep, :404-406)
+int stage_nh_p_grad(fv3_ctx* c, double dt, double beta_d) {
   StageScope ts(c, "PG_D");
   const Lay& L = c->L;
   const int km = L.npz;
@@ -320,7 +336,8 @@ int stage_nh_p_grad(fv3_ctx* c, double dt) {
     const int nks[4] = {km, km, km + 1, km};
     if ((rc = launch_a2b_ord4_batch(c, 4, qin, qout, nks, 4))) return rc;
   }
-  k_nh_pgrad<<<plane_grid(L, km), blk, 0, c->stream>>>(L, c->G, ppb, pkb, gzb, dpb, c->fld[FV3_U], c->fld[FV3_V], dt);
+  if (beta_d >= 0.) k_nh_pgrad<true><<<plane_grid(L, km), blk, 0, c->stream>>>(L, c->G, ppb, pkb, gzb, dpb, c->fld[FV3_U], c->fld[FV3_V], c->fld[FV3_DU], c->fld[FV3_DV], beta_d, dt);
+  else k_nh_pgrad<false><<<plane_grid(L, km), blk, 0, c->stream>>>(L, c->G, ppb, pkb, gzb, dpb, c->fld[FV3_U], c->fld[FV3_V], nullptr, nullptr, 0., dt);
   c->launches++;
   return 0;
 }
@@ -328,24 +345,39 @@ int stage_nh_p_grad(fv3_ctx* c, double dt) {
 // ---- one_grad_p (dyn_core.F90:1909-2030), hydrostatic call, d_ext = 0 -------------------------------------------------
 // pk (= pe^kappa) and gz are interpolated to the cell corners into scratch planes (the reference replaces them in
 // place; nothing reads them before the next geopk rebuilds them), wk = pk(k+1) - pk(k) at the corners.
+// GRAD1: grad1_p_update (dyn_core.F90:2033-2116, hydrostatic, beta > 0, d_ext = 0 so divg2 = 0): the beta-weighted increment of the
+// previous substep first, the current one stored in du, dv and applied with weight 1 - beta
+template <bool GRAD1>
 __global__ void __launch_bounds__(TI* TJ) k_one_grad_p(Lay L, DevGrid G, const double* __restrict__ pk, const double* __restrict__ gz,
-                                                      double* __restrict__ u, double* __restrict__ v, double dt) {
+                                                      double* __restrict__ u, double* __restrict__ v, double* __restrict__ du,
+                                                      double* __restrict__ dv, double beta, double dt) {
   PLANE_IJK
   if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
   const long long P = L.plane;
   const long long o = ko + LIDX(L, i, j);
+  const double alpha = 1. - beta;
   auto WK = [&](long long oo) { return __ldg(pk + oo + P) - __ldg(pk + oo); };
   if (i <= L.ie) {
     const long long e = o + 1;
-    u[o] = G2(rdx, i, j) * (0. + u[o] + dt / (WK(o) + WK(e)) *
-                                            ((__ldg(gz + o + P) - __ldg(gz + e)) * (__ldg(pk + e + P) - __ldg(pk + o)) +
-                                             (__ldg(gz + o) - __ldg(gz + e + P)) * (__ldg(pk + o + P) - __ldg(pk + e))));
+    const double d1 = dt / (WK(o) + WK(e)) *
+                      ((__ldg(gz + o + P) - __ldg(gz + e)) * (__ldg(pk + e + P) - __ldg(pk + o)) +
+                       (__ldg(gz + o) - __ldg(gz + e + P)) * (__ldg(pk + o + P) - __ldg(pk + e)));
+    if (GRAD1) {
+      const double u1 = u[o] + beta * du[o];
+      du[o] = d1;
+      u[o] = (u1 + 0. - 0. + alpha * d1) * G2(rdx, i, j);
+    } else u[o] = G2(rdx, i, j) * (0. + u[o] + d1);
   }
   if (j <= L.je) {
     const long long n = o + L.NI;
-    v[o] = G2(rdy, i, j) * (0. + v[o] + dt / (WK(o) + WK(n)) *
-                                            ((__ldg(gz + o + P) - __ldg(gz + n)) * (__ldg(pk + n + P) - __ldg(pk + o)) +
-                                             (__ldg(gz + o) - __ldg(gz + n + P)) * (__ldg(pk + o + P) - __ldg(pk + n))));
+    const double d1 = dt / (WK(o) + WK(n)) *
+                      ((__ldg(gz + o + P) - __ldg(gz + n)) * (__ldg(pk + n + P) - __ldg(pk + o)) +
+                       (__ldg(gz + o) - __ldg(gz + n + P)) * (__ldg(pk + o + P) - __ldg(pk + n)));
+    if (GRAD1) {
+      const double v1 = v[o] + beta * dv[o];
+      dv[o] = d1;
+      v[o] = (v1 + 0. - 0. + alpha * d1) * G2(rdy, i, j);
+    } else v[o] = G2(rdy, i, j) * (0. + v[o] + d1);
   }
 }
 __global__ void __launch_bounds__(TI* TJ) k_set_top(Lay L, double* __restrict__ pkb, double top_value) {
@@ -354,7 +386,8 @@ __global__ void __launch_bounds__(TI* TJ) k_set_top(Lay L, double* __restrict__ 
   if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
   pkb[LIDX(L, i, j)] = top_value;
 }
-int stage_one_grad_p(fv3_ctx* c, double dt) {
+// beta_d < 0: one_grad_p (dyn_core.F90:1021); beta_d >= 0: grad1_p_update with that beta (:1019)
+int stage_one_grad_p(fv3_ctx* c, double dt, double beta_d) {
   StageScope ts(c, "PG_D");
   const Lay& L = c->L;
   const int km = L.npz;
@@ -372,7 +405,8 @@ int stage_one_grad_p(fv3_ctx* c, double dt) {
     const int nks[2] = {km, km + 1};
     if ((rc = launch_a2b_ord4_batch(c, 2, qin, qout, nks, 4))) return rc;
   }
-  k_one_grad_p<<<plane_grid(L, km), blk, 0, c->stream>>>(L, c->G, pkb, gzb, c->fld[FV3_U], c->fld[FV3_V], dt);
+  if (beta_d >= 0.) k_one_grad_p<true><<<plane_grid(L, km), blk, 0, c->stream>>>(L, c->G, pkb, gzb, c->fld[FV3_U], c->fld[FV3_V], c->fld[FV3_DU], c->fld[FV3_DV], beta_d, dt);
+  else k_one_grad_p<false><<<plane_grid(L, km), blk, 0, c->stream>>>(L, c->G, pkb, gzb, c->fld[FV3_U], c->fld[FV3_V], nullptr, nullptr, 0., dt);
   c->launches++;
   return 0;
 }

@@ -145,6 +145,8 @@ enum fv3_field_id {
   FV3_WORK_RAX, /* (is:ie, jsd:jed, nk) */
   FV3_WORK_RAY, /* (isd:ied, js:je, nk) */
   FV3_DP1,      /* delp before dyn_core (isd:ied, jsd:jed, npz): input of tracer_2d (fv_tracer2d.F90:50,63) */
+  FV3_DU,       /* (isd:ied, jsd:jed+1, npz) hydrostatic pressure-gradient increment of u kept between substeps when beta > 0 */
+  FV3_DV,       /* (isd:ied+1, jsd:jed, npz)   (module arrays du, dv of dyn_core.F90:278-283, 1866-1870, 2098-2099)          */
   FV3_NUM_FIELDS
 };
 /* dims = {i_lo, ni, j_lo, nj, nk, k_middle(0/1)} */
@@ -204,6 +206,10 @@ int fv3_pt_to_theta(fv3_ctx *ctx, double zvir);
 int fv3_dcon_heating(fv3_ctx *ctx, double bdt);
 int fv3_geopk(fv3_ctx *ctx, int cg);
 int fv3_one_grad_p(fv3_ctx *ctx, double dt);
+/* beta > 0 (dyn_core.F90:1018-1019, 1027-1028): split_p_grad (non-hydrostatic, :1795-1905) / grad1_p_update (hydrostatic,
+ * :2033-2116) with beta_d = beta (0 on the first substep of a call, :404-406); the previous substep's hydrostatic increments
+ * live in FV3_DU, FV3_DV.  fv3_dyn_core takes this branch when flags.beta > 0. */
+int fv3_split_p_grad(fv3_ctx *ctx, double dt, double beta_d);
 
 /* dyn_core.F90:370-385 (it==1): gz on the compute domain from zs and delz. */
 int fv3_gz_init(fv3_ctx *ctx);

@@ -61,6 +61,7 @@ static void set_dims(fv3o_ctx* c) {
   d[FV3_WORK_RAX] = {b.is, nic, b.jsd, nja, kz, 0};
   d[FV3_WORK_RAY] = {b.isd, nia, b.js, njc, kz, 0};
   d[FV3_DP1] = A(kz);
+  d[FV3_DU] = d[FV3_U]; d[FV3_DV] = d[FV3_V];
 }
 
 static V3 F3(fv3o_ctx* c, int id) {
@@ -305,6 +306,16 @@ int fv3o_gz_from_zh(fv3o_ctx* c) {
   for (int k = 1; k <= bd.npz + 1; k++)
     for (int j = bd.js - 2; j <= bd.je + 2; j++)
       for (int i = bd.is - 2; i <= bd.ie + 2; i++) gz(i, j, k) = zh(i, j, k) * c->f.grav;
+  return 0;
+}
+// dyn_core.F90:1028 split_p_grad / :1019 grad1_p_update (beta > 0): beta_d = 0 on the first substep of a call (:404-406)
+int fv3o_split_p_grad(fv3o_ctx* c, double dt, double beta_d) {
+  Bd bd(c->b); Grid g(c->g, bd);
+  if (c->f.hydrostatic)
+    grad1_p_update(F3(c, FV3_U), F3(c, FV3_V), F3(c, FV3_PKC), F3(c, FV3_GZ), F3(c, FV3_DU), F3(c, FV3_DV), dt, g, bd, bd.npz, c->f.ptop, c->f.kappa, beta_d);
+  else
+    split_p_grad(F3(c, FV3_U), F3(c, FV3_V), F3(c, FV3_PKC), F3(c, FV3_GZ), F3(c, FV3_DELP), F3(c, FV3_PK3), F3(c, FV3_DU), F3(c, FV3_DV), beta_d, dt,
+                 g, bd, bd.npz, c->f.use_logp != 0, c->f.ptop, c->f.kappa);
   return 0;
 }
 // dyn_core.F90:1032

@@ -260,6 +260,9 @@ void nh_p_grad(V3 u, V3 v, V3 pp, V3 gz, V3 delp, V3 pk, double dt, int ng, cons
                int npy, int npz, bool use_logp, double ptop, double akap);
 void geopk(double ptop, double* pe, double* peln, V3 delp, V3 pk, V3 gz, V2 hs, V3 pt, V3 q_con, V3 pkz, int km, double akap,
            double cp_air, bool CG, bool use_cond, const Bd& bd);
+void split_p_grad(V3 u, V3 v, V3 pp, V3 gz, V3 delp, V3 pk, V3 du, V3 dv, double beta, double dt, const Grid& g, const Bd& bd, int npz,
+                  bool use_logp, double ptop, double akap);
+void grad1_p_update(V3 u, V3 v, V3 pk, V3 gz, V3 du, V3 dv, double dt, const Grid& g, const Bd& bd, int npz, double ptop, double akap, double beta);
 void one_grad_p(V3 u, V3 v, V3 pk, V3 gz, V3 delp, double dt, const Grid& g, const Bd& bd, int npz, double ptop, double akap,
                 bool hydrostatic);
 void pln_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed, int npz, double ptop, V3 pk3, V3 delp);

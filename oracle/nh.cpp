@@ -537,6 +537,79 @@ void geopk(double ptop, double* pe, double* peln, V3 delp, V3 pk, V3 gz, V2 hs, 
   }
 }
 
+// dyn_core.F90:1795-1905 split_p_grad (beta > 0, non-hydrostatic): du, dv = the hydrostatic increment of the previous substep
+void split_p_grad(V3 u, V3 v, V3 pp, V3 gz, V3 delp, V3 pk, V3 du, V3 dv, double beta, double dt, const Grid& g, const Bd& bd, int npz,
+                  bool use_logp, double ptop, double akap) {
+  const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je, isd = bd.isd, ied = bd.ied, jsd = bd.jsd, jed = bd.jed;
+  const double top_value = use_logp ? std::log(ptop) : std::pow(ptop, akap);
+  const double alpha = 1. - beta;
+  for (int j = js; j <= je + 1; j++) for (int i = is; i <= ie + 1; i++) { pp(i, j, 1) = 0.; pk(i, j, 1) = top_value; }
+#pragma omp parallel for schedule(static)
+  for (int k = 1; k <= npz + 1; k++) {
+    L2 wk1(isd, ied, jsd, jed);
+    if (k != 1) { a2b_ord4(pp.k(k), wk1, g, bd, true); a2b_ord4(pk.k(k), wk1, g, bd, true); }
+    a2b_ord4(gz.k(k), wk1, g, bd, true);
+  }
+#pragma omp parallel for schedule(static)
+  for (int k = 1; k <= npz; k++) {
+    L2 wk1(isd, ied, jsd, jed), wk(is, ie + 1, js, je + 1);
+    a2b_ord4(delp.k(k), wk1, g, bd, false);
+    for (int j = js; j <= je + 1; j++) for (int i = is; i <= ie + 1; i++) wk(i, j) = pk(i, j, k + 1) - pk(i, j, k);
+    for (int j = js; j <= je + 1; j++)
+      for (int i = is; i <= ie; i++) {
+        u(i, j, k) = u(i, j, k) + beta * du(i, j, k);
+        du(i, j, k) = dt / (wk(i, j) + wk(i + 1, j)) *
+                      ((gz(i, j, k + 1) - gz(i + 1, j, k)) * (pk(i + 1, j, k + 1) - pk(i, j, k)) +
+                       (gz(i, j, k) - gz(i + 1, j, k + 1)) * (pk(i, j, k + 1) - pk(i + 1, j, k)));
+        u(i, j, k) = (u(i, j, k) + alpha * du(i, j, k) + dt / (wk1(i, j) + wk1(i + 1, j)) *
+                      ((gz(i, j, k + 1) - gz(i + 1, j, k)) * (pp(i + 1, j, k + 1) - pp(i, j, k)) +
+                       (gz(i, j, k) - gz(i + 1, j, k + 1)) * (pp(i, j, k + 1) - pp(i + 1, j, k)))) * g.rdx(i, j);
+      }
+    for (int j = js; j <= je; j++)
+      for (int i = is; i <= ie + 1; i++) {
+        v(i, j, k) = v(i, j, k) + beta * dv(i, j, k);
+        dv(i, j, k) = dt / (wk(i, j) + wk(i, j + 1)) *
+                      ((gz(i, j, k + 1) - gz(i, j + 1, k)) * (pk(i, j + 1, k + 1) - pk(i, j, k)) +
+                       (gz(i, j, k) - gz(i, j + 1, k + 1)) * (pk(i, j, k + 1) - pk(i, j + 1, k)));
+        v(i, j, k) = (v(i, j, k) + alpha * dv(i, j, k) + dt / (wk1(i, j) + wk1(i, j + 1)) *
+                      ((gz(i, j, k + 1) - gz(i, j + 1, k)) * (pp(i, j + 1, k + 1) - pp(i, j, k)) +
+                       (gz(i, j, k) - gz(i, j + 1, k + 1)) * (pp(i, j, k + 1) - pp(i, j + 1, k)))) * g.rdy(i, j);
+      }
+  }
+}
+
+// dyn_core.F90:2033-2116 grad1_p_update (beta > 0, hydrostatic), d_ext = 0 (divg2 = 0, dyn_core.F90:745-747)
+void grad1_p_update(V3 u, V3 v, V3 pk, V3 gz, V3 du, V3 dv, double dt, const Grid& g, const Bd& bd, int npz, double ptop, double akap, double beta) {
+  const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je, isd = bd.isd, ied = bd.ied, jsd = bd.jsd, jed = bd.jed;
+  const double alpha = 1. - beta, top_value = std::pow(ptop, akap);
+  for (int j = js; j <= je + 1; j++) for (int i = is; i <= ie + 1; i++) pk(i, j, 1) = top_value;
+#pragma omp parallel for schedule(static)
+  for (int k = 2; k <= npz + 1; k++) { L2 wk(isd, ied, jsd, jed); a2b_ord4(pk.k(k), wk, g, bd, true); }
+#pragma omp parallel for schedule(static)
+  for (int k = 1; k <= npz + 1; k++) { L2 wk(isd, ied, jsd, jed); a2b_ord4(gz.k(k), wk, g, bd, true); }
+#pragma omp parallel for schedule(static)
+  for (int k = 1; k <= npz; k++) {
+    L2 wk(isd, ied, jsd, jed);
+    for (int j = js; j <= je + 1; j++) for (int i = is; i <= ie + 1; i++) wk(i, j) = pk(i, j, k + 1) - pk(i, j, k);
+    for (int j = js; j <= je + 1; j++)
+      for (int i = is; i <= ie; i++) {
+        u(i, j, k) = u(i, j, k) + beta * du(i, j, k);
+        du(i, j, k) = dt / (wk(i, j) + wk(i + 1, j)) *
+                      ((gz(i, j, k + 1) - gz(i + 1, j, k)) * (pk(i + 1, j, k + 1) - pk(i, j, k)) +
+                       (gz(i, j, k) - gz(i + 1, j, k + 1)) * (pk(i, j, k + 1) - pk(i + 1, j, k)));
+        u(i, j, k) = (u(i, j, k) + 0. - 0. + alpha * du(i, j, k)) * g.rdx(i, j);
+      }
+    for (int j = js; j <= je; j++)
+      for (int i = is; i <= ie + 1; i++) {
+        v(i, j, k) = v(i, j, k) + beta * dv(i, j, k);
+        dv(i, j, k) = dt / (wk(i, j) + wk(i, j + 1)) *
+                      ((gz(i, j, k + 1) - gz(i, j + 1, k)) * (pk(i, j + 1, k + 1) - pk(i, j, k)) +
+                       (gz(i, j, k) - gz(i, j + 1, k + 1)) * (pk(i, j, k + 1) - pk(i, j + 1, k)));
+        v(i, j, k) = (v(i, j, k) + 0. - 0. + alpha * dv(i, j, k)) * g.rdy(i, j);
+      }
+  }
+}
+
 // dyn_core.F90:1909-2030 one_grad_p, d_ext = 0 (wk1 = wk2 = 0)
 void one_grad_p(V3 u, V3 v, V3 pk, V3 gz, V3 delp, double dt, const Grid& g, const Bd& bd, int npz, double ptop, double akap,
                 bool hydrostatic) {

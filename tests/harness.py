@@ -219,6 +219,10 @@ class OracleCube:
         for f in ("MFX", "MFY", "CX", "CY", "HEAT"):
             self.all("zero_field", F[f])
         hydro = bool(self.case.flags["hydrostatic"])
+        beta = float(self.case.flags.get("beta", 0.0))
+        if beta > 0.0:
+            for f in ("DU", "DV"):
+                self.all("zero_field", F[f])
         for it in range(1, n_split + 1):
             last = it == n_split
             if it == 1:
@@ -238,7 +242,10 @@ class OracleCube:
                 run("GEOPK_D", "geopk", 0)
                 if last:
                     self.all("pk_from_pkc")   # dyn_core.F90:1001-1010
-                run("PG_D", "one_grad_p", dt)
+                if beta > 0.0:
+                    run("PG_D", "split_p_grad", dt, 0.0 if it == 1 else beta)   # grad1_p_update, dyn_core.F90:1018-1019
+                else:
+                    run("PG_D", "one_grad_p", dt)
                 if last:
                     self.halo("UV_EDGE")
                 continue
@@ -263,7 +270,10 @@ class OracleCube:
                 self.all("pe_halo")
             self.all("pk3_halo")
             self.all("gz_from_zh")
-            run("PG_D", "nh_p_grad", dt)
+            if beta > 0.0:
+                run("PG_D", "split_p_grad", dt, 0.0 if it == 1 else beta)       # dyn_core.F90:1027-1028
+            else:
+                run("PG_D", "nh_p_grad", dt)
             if last:
                 self.halo("UV_EDGE")
         self.dcon_heating(bdt)

@@ -435,3 +435,22 @@ def test_tracer_2d_after_dyn_core(hord):
         m1 += float(np.sum(q1 * dpf * area[t - 1]))
     assert abs(m1 - m0) / abs(m0) < 1e-12
     oc.close(); gc.close()
+
+
+@pytest.mark.parametrize("hydro", [0, 1])
+def test_dyn_core_beta_split_pressure_gradient(hydro):
+    """beta > 0: split_p_grad (non-hydrostatic, dyn_core.F90:1795-1905) / grad1_p_update (hydrostatic, :2033-2116): the
+    hydrostatic pressure-gradient increment of the previous substep enters with weight beta (du, dv carried in FV3_DU / FV3_DV,
+    beta_d = 0 on the first substep, :404-406).  Three substeps of the full cube against the oracle."""
+    case = H.Case(16, 6, "A", state="baroclinic", flags_override=dict(beta=0.4, hydrostatic=hydro))
+    oc, gc = H.OracleCube(case), H.CudaCube(case)
+    oc.dyn_core(900.0, 3); gc.dyn_core(900.0, 3)
+    b = case.bounds
+    reg = dict(H.regions_state(b))
+    reg["DU"] = reg["U"]; reg["DV"] = reg["V"]
+    if hydro:
+        for f in ("W", "DELZ", "ZH"):
+            reg.pop(f)
+    for t in oc.tiles:
+        _assert_run(H.compare(oc.eng[t], gc.eng[t], reg))
+    oc.close(); gc.close()

@@ -311,3 +311,33 @@ def test_rayleigh_damping_of_w_acts_above_rf_cutoff_only(built):
     assert (res[300.0][damped] < res[0.0][damped]).all()
     assert res[300.0][0] < 0.8 * res[0.0][0]                                    # strongest at the top
     assert np.abs(res[300.0][~damped] / res[0.0][~damped] - 1.0)[1:].max() < 0.01
+
+
+def test_split_p_grad_reduces_to_nh_p_grad_and_keeps_the_jet_steady(built):
+    """beta > 0 (split_p_grad, dyn_core.F90:1795-1905): (a) with beta_d = 0 it is nh_p_grad plus the bookkeeping of du, dv;
+    (b) in a steady state the hydrostatic increment is the same every substep, so weighting the previous one with beta and the
+    current one with 1 - beta changes nothing to first order: the unperturbed JW jet stays as steady as with beta = 0."""
+    from gfdl_atmos_cubed_sphere_b200 import init_state as I
+    n, npz = 16, 6
+    case = H.Case(n, npz, "A", state="baroclinic")
+    ea, eb = case.engine(H.load_oracle(), 1), case.engine(H.load_oracle(), 1)
+    for e in (ea, eb):
+        case.load_state(e, 1)
+        e.call("gz_init"); e.call("copy_field", H.abi.FIELD_ID["ZH"], H.abi.FIELD_ID["GZ"])
+        e.call("riem_solver3", 100.0, 0); e.call("pk3_halo"); e.call("gz_from_zh")
+    ea.call("nh_p_grad", 100.0)
+    eb.call("split_p_grad", 100.0, 0.0)
+    for f in ("U", "V"):
+        assert np.array_equal(ea.get(f), eb.get(f)), f
+    assert np.abs(eb.get("DU")).max() > 0.0
+    ea.close(); eb.close()
+    res = {}
+    for beta in (0.0, 0.4):
+        case = H.Case(24, 8, "A", state="baroclinic", flags_override=dict(beta=beta))
+        case.states = I.baroclinic_wave(case.tiles, case.bounds, 8, case.ak, case.bk, perturb=False, w_amp=0.0)
+        oc = H.OracleCube(case, fast=True)
+        u0 = {t: oc.eng[t].get("U").copy() for t in oc.tiles}
+        oc.dyn_core(3600.0, 8)
+        res[beta] = max(np.abs(H.sub(oc.eng[t], "U", oc.eng[t].get("U") - u0[t], 1, 24, 1, 25)).max() for t in oc.tiles)
+        oc.close()
+    assert res[0.4] < 1.0 and abs(res[0.4] - res[0.0]) < 0.3, res
