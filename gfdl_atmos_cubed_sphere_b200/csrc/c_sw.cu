@@ -17,6 +17,10 @@
 
 #define TI 32
 #define TJ 8
+// resident CTAs per SM the register allocation of the load-latency-bound kernels is sized for (A/B: profiles/r2_dsw_summary.md)
+#ifndef PLANE_MINB
+#define PLANE_MINB 6
+#endif
 #define PLANE_IJK                                              \
   const int i = L.isd - FV3_IOFF + blockIdx.x * TI + threadIdx.x; \
   const int j = L.jsd + blockIdx.y * TJ + threadIdx.y;          \
@@ -222,7 +226,8 @@ __device__ __forceinline__ void csw_c_point(const Lay& L, const DevGrid& G, cons
     }
     uc[o] = ucv;
     // sw_core.F90:159-167
-    ut[o] = (utv > 0.) ? dt2 * utv * G2(dy, i, j) * SG(3, i - 1, j) : dt2 * utv * G2(dy, i, j) * SG(1, i, j);
+    { const double s3 = SG(3, i - 1, j), s1 = SG(1, i, j), dyv = G2(dy, i, j);   // both candidates loaded before utv is known
+      ut[o] = (utv > 0.) ? dt2 * utv * dyv * s3 : dt2 * utv * dyv * s1; }
   }
   // y direction: j in [js-1, je+2], i in [is-1, ie+1]
   if (j >= L.js - 1 && j <= L.je + 2 && i >= L.is - 1 && i <= L.ie + 1) {
@@ -242,7 +247,8 @@ __device__ __forceinline__ void csw_c_point(const Lay& L, const DevGrid& G, cons
     }
     vc[o] = vcv;
     // sw_core.F90:168-176
-    vt[o] = (vtv > 0.) ? dt2 * vtv * G2(dx, i, j) * SG(4, i, j - 1) : dt2 * vtv * G2(dx, i, j) * SG(2, i, j);
+    { const double s4 = SG(4, i, j - 1), s2 = SG(2, i, j), dxv = G2(dx, i, j);
+      vt[o] = (vtv > 0.) ? dt2 * vtv * dxv * s4 : dt2 * vtv * dxv * s2; }
   }
   // divergence_corner (sw_core.F90:1797-1843), corners [is, ie+1]^2; uses the un-rotated ua, va
   if (nord > 0 && i >= L.is && i <= L.ie + 1 && j >= L.js && j <= L.je + 1) {
@@ -284,7 +290,55 @@ __device__ __forceinline__ void csw_c_point(const Lay& L, const DevGrid& G, cons
     if (iy && jy) va_[o] = vay(i, j);
   }
 }
-__global__ void __launch_bounds__(TI* TJ, 4) k_csw_c(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
+// The same for a point with 3 <= i <= npx-2, 3 <= j <= npy-2 of a cubed-sphere face (grid_type <= 3), written with plain offsets
+// from ONE in-plane index: the generic routine computes an index (and, through its accessors, the remap tests the E = false
+// instantiation folds away only partly) for each of its ~55 loads -- 586 warp instructions per thread (profiles/r2_dsw_summary.md).
+// Same operations in the same order.
+__device__ __forceinline__ void csw_c_interior(const Lay& L, const DevGrid& G, const double* __restrict__ u, const double* __restrict__ v,
+                                               const double* __restrict__ utmp, const double* __restrict__ vtmp, const double* __restrict__ ua,
+                                               const double* __restrict__ va, double* __restrict__ uc, double* __restrict__ vc,
+                                               double* __restrict__ ut, double* __restrict__ vt, double* __restrict__ divg_d, int nord,
+                                               double dt2, int o2, long long ko) {
+  const int NI = L.NI;
+  const long long P = L.plane, o = ko + o2;
+  const double* sg = G.sin_sg + o2; const double* cg = G.cos_sg + o2;
+  const double* up = u + o; const double* vp = v + o;
+  const double u00 = __ldg(up), v00 = __ldg(vp);
+  {
+    const double* t = utmp + o;
+    const double ucv = a2 * (__ldg(t - 2) + __ldg(t + 1)) + a1 * (__ldg(t - 1) + __ldg(t));
+    const double utv = (ucv - v00 * __ldg(G.cosa_u + o2)) * __ldg(G.rsin_u + o2);
+    const double s3 = __ldg(sg + 2 * P - 1), s1 = __ldg(sg), dyv = __ldg(G.dy + o2);
+    uc[o] = ucv;
+    ut[o] = (utv > 0.) ? dt2 * utv * dyv * s3 : dt2 * utv * dyv * s1;
+  }
+  {
+    const double* t = vtmp + o;
+    const double vcv = a2 * (__ldg(t - 2 * NI) + __ldg(t + NI)) + a1 * (__ldg(t - NI) + __ldg(t));
+    const double vtv = (vcv - u00 * __ldg(G.cosa_v + o2)) * __ldg(G.rsin_v + o2);
+    const double s4 = __ldg(sg + 3 * P - NI), s2 = __ldg(sg + P), dxv = __ldg(G.dx + o2);
+    vc[o] = vcv;
+    vt[o] = (vtv > 0.) ? dt2 * vtv * dxv * s4 : dt2 * vtv * dxv * s2;
+  }
+  if (nord > 0) {   // divergence_corner (sw_core.F90:1797-1843) at corner (i, j): uf at (i-1, j), (i, j); vf at (i, j-1), (i, j)
+    const double* uap = ua + o; const double* vap = va + o;
+    // uf(ii,jj) = (u - 0.25*(va(jj-1)+va(jj))*(cos_sg4(jj-1)+cos_sg2(jj))) * dyc * (0.5*(sin_sg4(jj-1)+sin_sg2(jj)))
+    auto uf = [&](int d) {   // d = 0: (i, j), d = -1: (i-1, j)
+      const double s = 0.5 * (__ldg(sg + 3 * P + d - NI) + __ldg(sg + P + d));
+      return (__ldg(up + d) - 0.25 * (__ldg(vap + d - NI) + __ldg(vap + d)) * (__ldg(cg + 3 * P + d - NI) + __ldg(cg + P + d))) * __ldg(G.dyc + o2 + d) * s;
+    };
+    auto vf = [&](int d) {   // d = 0: (i, j), d = -NI: (i, j-1)
+      const double s = 0.5 * (__ldg(sg + 2 * P + d - 1) + __ldg(sg + d));
+      return (__ldg(vp + d) - 0.25 * (__ldg(uap + d - 1) + __ldg(uap + d)) * (__ldg(cg + 2 * P + d - 1) + __ldg(cg + d))) * __ldg(G.dxc + o2 + d) * s;
+    };
+    const double dv = vf(-NI) - vf(0) + uf(-1) - uf(0);
+    divg_d[o] = __ldg(G.rarea_c + o2) * dv;
+  }
+}
+#ifndef CSWC_MINB
+#define CSWC_MINB 4   // 64 registers: at 6 CTAs per SM (40 registers) this kernel spills 140 bytes (measured 440 / 457 / 491 us at 4 / 6 / 3)
+#endif
+__global__ void __launch_bounds__(TI* TJ, CSWC_MINB) k_csw_c(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
                                                  const double* __restrict__ utmp_, const double* __restrict__ vtmp_,
                                                  double* ua_, double* va_,
                                                  double* __restrict__ uc, double* __restrict__ vc, double* __restrict__ ut,
@@ -292,7 +346,7 @@ __global__ void __launch_bounds__(TI* TJ, 4) k_csw_c(Lay L, DevGrid G, const dou
   PLANE_IJK
   if (i < L.isd || i > L.ied + 1 || j > L.jed + 1) return;
   if (L.cube && L.grid_type <= 3 && i >= 3 && i <= L.npx - 2 && j >= 3 && j <= L.npy - 2)
-    csw_c_point<false>(L, G, u, v, utmp_, vtmp_, ua_, va_, uc, vc, ut, vt, divg_d, nord, dt2, i, j, ko);
+    csw_c_interior(L, G, u, v, utmp_, vtmp_, ua_, va_, uc, vc, ut, vt, divg_d, nord, dt2, LIDX(L, i, j), ko);
   else
     csw_c_point<true>(L, G, u, v, utmp_, vtmp_, ua_, va_, uc, vc, ut, vt, divg_d, nord, dt2, i, j, ko);
 }
@@ -314,6 +368,23 @@ __device__ __forceinline__ void csw_t_point(const Lay& L, const DevGrid& G, cons
   FillY<E> dy_{delp + ko, L}, py_{pt + ko, L}, wy_{w + ko, L};
   // upwind fluxes through the 4 faces (sw_core.F90:214-276)
   double fx1[2], fx[2], fx2[2], fy1[2], fy[2], fy2[2];
+  if (!E) {
+    // interior points: BOTH upwind candidates of every face are loaded before the winds are known (the 5-point cross of delp,
+    // pt, w: 15 + 4 independent loads) instead of 12 loads whose addresses depend on the sign of ut / vt -- the dependent form
+    // costs two memory round trips per thread and the kernel was load-latency bound (ncu long_scoreboard 12.9 cycles per issue
+    // at 40 % of the DRAM bandwidth, profiles/r2/r2_substep_limiters.txt)
+    const double* dp_ = delp + o; const double* pt_ = pt + o; const double* w_ = w + o;
+    const int NI = L.NI;
+    const double u0 = __ldg(ut + o), u1 = __ldg(ut + o + 1), v0 = __ldg(vt + o), v1 = __ldg(vt + o + NI);
+    const double dW = __ldg(dp_ - 1), dC = __ldg(dp_), dE = __ldg(dp_ + 1), dS = __ldg(dp_ - NI), dN = __ldg(dp_ + NI);
+    const double pW = __ldg(pt_ - 1), pC = __ldg(pt_), pE = __ldg(pt_ + 1), pS = __ldg(pt_ - NI), pN = __ldg(pt_ + NI);
+    double wW = 0., wC = 0., wE = 0., wS = 0., wN = 0.;
+    if (!hydrostatic) { wW = __ldg(w_ - 1); wC = __ldg(w_); wE = __ldg(w_ + 1); wS = __ldg(w_ - NI); wN = __ldg(w_ + NI); }
+    fx1[0] = u0 * (u0 > 0. ? dW : dC); fx[0] = fx1[0] * (u0 > 0. ? pW : pC); fx2[0] = hydrostatic ? 0. : fx1[0] * (u0 > 0. ? wW : wC);
+    fx1[1] = u1 * (u1 > 0. ? dC : dE); fx[1] = fx1[1] * (u1 > 0. ? pC : pE); fx2[1] = hydrostatic ? 0. : fx1[1] * (u1 > 0. ? wC : wE);
+    fy1[0] = v0 * (v0 > 0. ? dS : dC); fy[0] = fy1[0] * (v0 > 0. ? pS : pC); fy2[0] = hydrostatic ? 0. : fy1[0] * (v0 > 0. ? wS : wC);
+    fy1[1] = v1 * (v1 > 0. ? dC : dN); fy[1] = fy1[1] * (v1 > 0. ? pC : pN); fy2[1] = hydrostatic ? 0. : fy1[1] * (v1 > 0. ? wC : wN);
+  } else
 #pragma unroll
   for (int s = 0; s < 2; s++) {
     const int ii = i + s;
@@ -340,9 +411,10 @@ __device__ __forceinline__ void csw_t_point(const Lay& L, const DevGrid& G, cons
   const double uav = AT(ua, i, j), vav = AT(va, i, j);
   double kx, ky;
   (void)ortho;
-  if (!cube) {   // no face edge nearby (or not a cubed sphere): sw_core.F90:352-366
-    kx = (uav > 0.) ? AT(uc, i, j) : AT(uc, i + 1, j);
-    ky = (vav > 0.) ? AT(vc, i, j) : AT(vc, i, j + 1);
+  if (!cube) {   // no face edge nearby (or not a cubed sphere): sw_core.F90:352-366; both candidates loaded, then selected
+    const double uc0 = AT(uc, i, j), uc1 = AT(uc, i + 1, j), vc0 = AT(vc, i, j), vc1 = AT(vc, i, j + 1);
+    kx = (uav > 0.) ? uc0 : uc1;
+    ky = (vav > 0.) ? vc0 : vc1;
   } else {
     if (uav > 0.) {
       if (i == 1) kx = AT(uc, 1, j) * SG(1, 1, j) + AT(v, 1, j) * CG(1, 1, j);
@@ -380,7 +452,7 @@ __device__ __forceinline__ void csw_t_point(const Lay& L, const DevGrid& G, cons
     vort[o] = G2(fC, i, j) + G2(rarea_c, i, j) * vo;
   }
 }
-__global__ void __launch_bounds__(TI* TJ) k_csw_t(Lay L, DevGrid G, const double* __restrict__ delp, const double* __restrict__ pt,
+__global__ void __launch_bounds__(TI* TJ, PLANE_MINB) k_csw_t(Lay L, DevGrid G, const double* __restrict__ delp, const double* __restrict__ pt,
                                                  const double* __restrict__ w, const double* __restrict__ u, const double* __restrict__ v,
                                                  const double* __restrict__ uc, const double* __restrict__ vc, const double* __restrict__ ua,
                                                  const double* __restrict__ va, const double* __restrict__ ut, const double* __restrict__ vt,
@@ -407,14 +479,16 @@ __global__ void __launch_bounds__(TI* TJ) k_csw_u(Lay L, DevGrid G, const double
     double fy1;
     if (cube && (i == 1 || i == npx)) fy1 = dt2 * AT(v, i, j);
     else fy1 = dt2 * (AT(v, i, j) - uc[o] * G2(cosa_u, i, j)) / G2(sina_u, i, j);
-    const double fyv = (fy1 > 0.) ? AT(vort, i, j) : AT(vort, i, j + 1);
+    const double vo0 = AT(vort, i, j), vo1 = AT(vort, i, j + 1);
+    const double fyv = (fy1 > 0.) ? vo0 : vo1;
     uc[o] = uc[o] + fy1 * fyv + G2(rdxc, i, j) * (AT(ke, i - 1, j) - AT(ke, i, j));
   }
   if (i <= L.ie) {
     double fx1;
     if (cube && (j == 1 || j == npy)) fx1 = dt2 * AT(u, i, j);
     else fx1 = dt2 * (AT(u, i, j) - vc[o] * G2(cosa_v, i, j)) / G2(sina_v, i, j);
-    const double fxv = (fx1 > 0.) ? AT(vort, i, j) : AT(vort, i + 1, j);
+    const double vo0 = AT(vort, i, j), vo1 = AT(vort, i + 1, j);
+    const double fxv = (fx1 > 0.) ? vo0 : vo1;
     vc[o] = vc[o] - fx1 * fxv + G2(rdyc, i, j) * (AT(ke, i, j - 1) - AT(ke, i, j));
   }
 }

@@ -34,6 +34,9 @@ static int use_line_kernels() {
 
 #define TI 32
 #define TJ 8
+#ifndef PLANE_MINB
+#define PLANE_MINB 6
+#endif
 #define PLANE_IJK                                              \
   const int i = L.isd - FV3_IOFF + blockIdx.x * TI + threadIdx.x; \
   const int j = L.jsd + blockIdx.y * TJ + threadIdx.y;          \
@@ -177,7 +180,7 @@ struct WindCtx {
   }
 };
 
-__global__ void __launch_bounds__(TI* TJ, 4) k_dsw_wind(Lay L, DevGrid G, const double* __restrict__ uc, const double* __restrict__ vc,
+__global__ void __launch_bounds__(TI* TJ, PLANE_MINB) k_dsw_wind(Lay L, DevGrid G, const double* __restrict__ uc, const double* __restrict__ vc,
                                                     double* __restrict__ uts, double* __restrict__ vts, double* __restrict__ crx,
                                                     double* __restrict__ cry, double* __restrict__ xfx, double* __restrict__ yfx,
                                                     double* __restrict__ cx, double* __restrict__ cy, double dt) {
@@ -195,10 +198,12 @@ __global__ void __launch_bounds__(TI* TJ, 4) k_dsw_wind(Lay L, DevGrid G, const 
     const double ut = inner ? W.UTg(i, j) : W.ut_final(i, j);
     if (keep) uts[o] = ut;
     if (i >= L.is && i <= L.ie + 1) {  // :863-890, :923-927
+      // both upwind candidates of the metric terms are loaded before the sign of ut is known (one memory round trip, not two)
+      const double rm = G2(rdxa, i - 1, j), r0 = G2(rdxa, i, j), s3 = SG(3, i - 1, j), s1 = SG(1, i, j), dyv = G2(dy, i, j), cx0 = cx[o];
       double xf = dt * ut, cr;
-      if (xf > 0.) { cr = xf * G2(rdxa, i - 1, j); xf = G2(dy, i, j) * xf * SG(3, i - 1, j); }
-      else { cr = xf * G2(rdxa, i, j); xf = G2(dy, i, j) * xf * SG(1, i, j); }
-      crx[o] = cr; xfx[o] = xf; cx[o] = cx[o] + cr;
+      if (xf > 0.) { cr = xf * rm; xf = dyv * xf * s3; }
+      else { cr = xf * r0; xf = dyv * xf * s1; }
+      crx[o] = cr; xfx[o] = xf; cx[o] = cx0 + cr;
     }
   }
   // vt on (isd:ied, js-1:je+2)
@@ -206,10 +211,11 @@ __global__ void __launch_bounds__(TI* TJ, 4) k_dsw_wind(Lay L, DevGrid G, const 
     const double vt = inner ? W.VTg(i, j) : W.vt_final(i, j);
     if (keep) vts[o] = vt;
     if (j >= L.js && j <= L.je + 1) {  // :869-902, :933-936
+      const double rm = G2(rdya, i, j - 1), r0 = G2(rdya, i, j), s4 = SG(4, i, j - 1), s2 = SG(2, i, j), dxv = G2(dx, i, j), cy0 = cy[o];
       double yf = dt * vt, cr;
-      if (yf > 0.) { cr = yf * G2(rdya, i, j - 1); yf = G2(dx, i, j) * yf * SG(4, i, j - 1); }
-      else { cr = yf * G2(rdya, i, j); yf = G2(dx, i, j) * yf * SG(2, i, j); }
-      cry[o] = cr; yfx[o] = yf; cy[o] = cy[o] + cr;
+      if (yf > 0.) { cr = yf * rm; yf = dxv * yf * s4; }
+      else { cr = yf * r0; yf = dxv * yf * s2; }
+      cry[o] = cr; yfx[o] = yf; cy[o] = cy0 + cr;
     }
   }
 }
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_dw(Lay L, DevGrid G, const doubl
 // ---------------------------------------------------------------------------------------------
 // RARE = true: the instantiation that also carries hord_mt 1..4, 7, 9, 11 (out-of-line); the common 5 / 6 / 8 / 10 keep their code
 template <bool RARE>
-__global__ void __launch_bounds__(TI* TJ, 4) k_dsw_ke(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
+__global__ void __launch_bounds__(TI* TJ, PLANE_MINB) k_dsw_ke(Lay L, DevGrid G, const double* __restrict__ u, const double* __restrict__ v,
                                                   const double* __restrict__ uc, const double* __restrict__ vc, const double* __restrict__ uts,
                                                   const double* __restrict__ vts, double* __restrict__ ke, double dt, int hord_mt) {
   PLANE_IJK
@@ -391,6 +397,20 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_dd_iter(Lay L, DevGrid G, const 
   const int nt = nord - n;
   if (i < L.is - nt || i > L.ie + 1 + nt || j < L.js - nt || j > L.je + 1 + nt) return;
   const int npx = L.npx, npy = L.npy;
+  if (i >= 4 && i <= npx - 4 && j >= 4 && j <= npy - 4) {
+    // away from the face edges (96 % of the points at C384): the 5-point cross of divg with plain offsets from one index.  The
+    // general path below carries the fill_corners remap tests and the face-corner terms through every access and was
+    // instruction bound (262 warp instructions per thread at 75 % issue-active, profiles/r2_dsw_summary.md).  Same operations.
+    const int o2 = LIDX(L, i, j), NI = L.NI;
+    const double* d = dgi + ko + o2;
+    const double dC = __ldg(d), dW = __ldg(d - 1), dE = __ldg(d + 1), dS = __ldg(d - NI), dN = __ldg(d + NI);
+    const double ucS = (dC - dS) * __ldg(G.divg_v + o2 - NI), ucC = (dN - dC) * __ldg(G.divg_v + o2);
+    const double vcW = (dC - dW) * __ldg(G.divg_u + o2 - 1), vcC = (dE - dC) * __ldg(G.divg_u + o2);
+    double dv = ucS - ucC + vcW - vcC;
+    if (!stretched) dv = dv * __ldg(G.rarea_c + o2);
+    dgo[ko + o2] = dv;
+    return;
+  }
   const bool fill_c = (nt != 0) && L.cube && (i < 4 || i > npx - 4) && (j < 4 || j > npy - 4);   // remaps exist in the corner regions only
   const double* d = dgi + ko;
   BFillX dx_{d, L, fill_c};

@@ -374,6 +374,35 @@ __global__ void __launch_bounds__(TI* TJ) k_dzc_adv(Lay L, DevGrid G, const doub
   const int km = L.npz;
   const long long P = L.plane;
   const double* gzk = gz + (long long)(k - 1) * P;
+  if (L.cube && i >= 2 && i <= L.npx - 2 && j >= 2 && j <= L.npy - 2) {
+    // points whose 5-point cross touches no face-corner remap (all but a 2-wide ring): plain offsets from one index.  The general
+    // path below evaluates the fill_4corners remap tests on every access and made the kernel instruction bound (358 warp
+    // instructions per thread, 80 % issue-active: profiles/r2_dsw_summary.md)
+    const int o2 = LIDX(L, i, j), NI = L.NI;
+    const double* g = gzk + o2;
+    double x0, x1, y0, y1;
+    if (k == 1 || k == km + 1) {
+      const int ka = (k == 1) ? 1 : km, kb = (k == 1) ? 2 : km - 1;
+      const double r0 = (k == 1) ? dp0[0] / (dp0[0] + dp0[1]) : dp0[km - 1] / (dp0[km - 2] + dp0[km - 1]);
+      const double* ua = ut + o2 + (long long)(ka - 1) * P; const double* ub = ut + o2 + (long long)(kb - 1) * P;
+      const double* va = vt + o2 + (long long)(ka - 1) * P; const double* vb = vt + o2 + (long long)(kb - 1) * P;
+      const double a0 = __ldg(ua), a1 = __ldg(ua + 1), c0 = __ldg(va), c1 = __ldg(va + NI);
+      x0 = a0 + (a0 - __ldg(ub)) * r0; x1 = a1 + (a1 - __ldg(ub + 1)) * r0;
+      y0 = c0 + (c0 - __ldg(vb)) * r0; y1 = c1 + (c1 - __ldg(vb + NI)) * r0;
+    } else {
+      const double r0 = 1. / (dp0[k - 2] + dp0[k - 1]), da = dp0[k - 1], db = dp0[k - 2];
+      const double* ua = ut + o2 + (long long)(k - 2) * P; const double* ub = ua + P;
+      const double* va = vt + o2 + (long long)(k - 2) * P; const double* vb = va + P;
+      x0 = (da * __ldg(ua) + db * __ldg(ub)) * r0; x1 = (da * __ldg(ua + 1) + db * __ldg(ub + 1)) * r0;
+      y0 = (da * __ldg(va) + db * __ldg(vb)) * r0; y1 = (da * __ldg(va + NI) + db * __ldg(vb + NI)) * r0;
+    }
+    const double gW = __ldg(g - 1), gC = __ldg(g), gE = __ldg(g + 1), gS = __ldg(g - NI), gN = __ldg(g + NI);
+    const double ar = __ldg(G.area + o2);
+    const double fx0 = x0 * ((x0 > 0.) ? gW : gC), fx1 = x1 * ((x1 > 0.) ? gC : gE);
+    const double fy0 = y0 * ((y0 > 0.) ? gS : gC), fy1 = y1 * ((y1 > 0.) ? gC : gN);
+    gzn[o2 + (long long)(k - 1) * P] = (gC * ar + fx0 - fx1 + fy0 - fy1) / (ar + x0 - x1 + y0 - y1);
+    return;
+  }
   auto U = [&](int ii, int jj, int kk) { return __ldg(ut + LIDX(L, ii, jj) + (long long)(kk - 1) * P); };
   auto V = [&](int ii, int jj, int kk) { return __ldg(vt + LIDX(L, ii, jj) + (long long)(kk - 1) * P); };
   double r0 = 0., r1 = 0.;
@@ -418,13 +447,15 @@ __global__ void __launch_bounds__(TI* TJ) k_dzc_adv(Lay L, DevGrid G, const doub
     return __ldg(gzk + LIDX(L, ii, jj));
   };
   const double x0 = XF(i, j), x1 = XF(i + 1, j), y0 = YF(i, j), y1 = YF(i, j + 1);
-  const double fx0 = x0 * ((x0 > 0.) ? GX(i - 1, j) : GX(i, j));
-  const double fx1 = x1 * ((x1 > 0.) ? GX(i, j) : GX(i + 1, j));
-  const double fy0 = y0 * ((y0 > 0.) ? GY(i, j - 1) : GY(i, j));
-  const double fy1 = y1 * ((y1 > 0.) ? GY(i, j) : GY(i, j + 1));
+  // both upwind candidates of every face are loaded before the winds are known: one memory round trip instead of two
+  const double gW = GX(i - 1, j), gCx = GX(i, j), gE = GX(i + 1, j), gS = GY(i, j - 1), gC = GY(i, j), gN = GY(i, j + 1);
   const double ar = __ldg(G.area + LIDX(L, i, j));
+  const double fx0 = x0 * ((x0 > 0.) ? gW : gCx);
+  const double fx1 = x1 * ((x1 > 0.) ? gCx : gE);
+  const double fy0 = y0 * ((y0 > 0.) ? gS : gC);
+  const double fy1 = y1 * ((y1 > 0.) ? gC : gN);
   // gz2(i,j) at the centre is the array after BOTH fills (dir=2 last), nh_utils.F90:163,177
-  gzn[LIDX(L, i, j) + (long long)(k - 1) * P] = (GY(i, j) * ar + fx0 - fx1 + fy0 - fy1) / (ar + x0 - x1 + y0 - y1);
+  gzn[LIDX(L, i, j) + (long long)(k - 1) * P] = (gC * ar + fx0 - fx1 + fy0 - fy1) / (ar + x0 - x1 + y0 - y1);
 }
 // ws and the monotonic-height clamp (nh_utils.F90:183-199 / :303-319); writes h in place
 __global__ void __launch_bounds__(CB) k_dz_clamp(Lay L, const double* __restrict__ hn, double* __restrict__ h, const double* __restrict__ phis,

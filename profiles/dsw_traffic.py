@@ -1,6 +1,7 @@
 """DRAM traffic of ONE d_sw call from an ncu metrics list
 (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv ... python profiles/prof_dsw.py).
-Sums the kernels of the LAST complete d_sw call (from one k_dsw_wind launch to the next).  usage: dsw_traffic.py list.csv"""
+Sums the kernels of the LAST complete d_sw call (from one k_dsw_wind launch to the next).
+usage: dsw_traffic.py list.csv [--json profiles/r2_dsw_traffic.json KEY]   (KEY e.g. C384L79A: the entry bench.py reads for roofline.traffic)"""
 import csv, sys, collections
 rows = list(csv.reader(open(sys.argv[1], errors="ignore")))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
@@ -24,3 +25,11 @@ for x in sel:
     a = agg.setdefault(x["name"], [0, 0., 0., 0.]); a[0] += 1; a[1] += x.get("gpu__time_duration.sum", 0); a[2] += x.get("dram__bytes_read.sum", 0); a[3] += x.get("dram__bytes_write.sum", 0)
 for n, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"  {n:32s} x{a[0]} {a[1]:8.1f} us  rd {a[2]/1e6:8.1f} MB  wr {a[3]/1e6:8.1f} MB")
+
+if "--json" in sys.argv:
+    import json, os, subprocess
+    out, key = sys.argv[sys.argv.index("--json") + 1], sys.argv[sys.argv.index("--json") + 2]
+    rec = json.load(open(out)) if os.path.exists(out) else {}
+    rec[key] = {"bytes": rd + wr, "read": rd, "write": wr, "launches": len(sel), "ncu_serialised_ms": t / 1e3, "csv": os.path.basename(sys.argv[1]),
+                "kernels": {n: {"launches": a[0], "us": round(a[1], 1), "read_MB": round(a[2] / 1e6, 1), "write_MB": round(a[3] / 1e6, 1)} for n, a in agg.items()}}
+    json.dump(rec, open(out, "w"), indent=1)
