@@ -404,8 +404,9 @@ __device__ __forceinline__ void csw_t_point(const Lay& L, const DevGrid& G, cons
   const double dp0 = dy_(i, j), pt0 = py_(i, j);
   const double dpc = dp0 + (fx1[0] - fx1[1] + fy1[0] - fy1[1]) * ra;
   delpc[o] = dpc;
-  ptc[o] = (pt0 * dp0 + (fx[0] - fx[1] + fy[0] - fy[1]) * ra) / dpc;
-  if (!hydrostatic) wc[o] = (wy_(i, j) * dp0 + (fx2[0] - fx2[1] + fy2[0] - fy2[1]) * ra) / dpc;
+  const double rdpc = 1. / dpc;   // one division for ptc and wc (<= 1 ulp from the two of sw_core.F90:279-283)
+  ptc[o] = (pt0 * dp0 + (fx[0] - fx[1] + fy[0] - fy[1]) * ra) * rdpc;
+  if (!hydrostatic) wc[o] = (wy_(i, j) * dp0 + (fx2[0] - fx2[1] + fy2[0] - fy2[1]) * ra) * rdpc;
 
   // KE (sw_core.F90:297-366)
   const double uav = AT(ua, i, j), vav = AT(va, i, j);

@@ -822,11 +822,12 @@ __global__ void __launch_bounds__(tp2::NT, 1) k_dsw_transport2(Lay L, DevGrid G,
       const double mx1 = S.qi[0][o + 1], my1 = S.qj[0][o + tp2::P];
       const double dp = S.in[b][tp2::A_Q][o];
       const double dpn = dp + (mx0 - mx1 + my0 - my1) * ra;
+      const double rdpn = 1. / dpn;   // one division for w and pt (<= 1 ulp from the two divisions of sw_core.F90:986, 1061)
 #pragma unroll
       for (int f = 1; f < NF; f++) {
         const double div = (S.qi[f][o] - S.qi[f][o + 1] + S.qj[f][o] - S.qj[f][o + tp2::P]) * ra;
         const double q = S.in[b][tp2::A_Q + f][o];
-        double v = (q * dp + div) / dpn;
+        double v = (q * dp + div) * rdpn;
         if (NF == 3 && f == 1) {
           if (a.dw && a.kdbl[KD_DAMP4_W * n1 + k] != 0.) v = v + __ldg(a.dw + g);
           a.w_o[g] = v;
@@ -836,17 +837,20 @@ __global__ void __launch_bounds__(tp2::NT, 1) k_dsw_transport2(Lay L, DevGrid G,
     });
 }
 
-// interior tiles: 16 warps, two CTAs per SM (one transported field: the other CTA's sweeps hide this one's barriers and epilogue
-// loads); frame tiles: 32 warps, one CTA per SM (their cube-edge tables do not fit twice)
+// one transported field; TP2_NF1_NWC warps per CTA on the interior tiles (16: two CTAs per SM), 32 on the frame tiles (their
+// cube-edge tables do not fit twice)
+#ifndef TP2_NF1_NWC
+#define TP2_NF1_NWC 32   // measured at C384L79: 401 us (one CTA of 32 warps per SM) vs 420 us (two CTAs of 16)
+#endif
 template <int FAM, int HORD, bool EDGE>
-__global__ void __launch_bounds__(EDGE ? 1024 : 512, EDGE ? 1 : 2) k_dsw_vort_uv2(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ vq, const double* __restrict__ crx,
+__global__ void __launch_bounds__(EDGE ? 1024 : TP2_NF1_NWC * 32, EDGE ? 1 : 32 / TP2_NF1_NWC) k_dsw_vort_uv2(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ vq, const double* __restrict__ crx,
                                                        const double* __restrict__ cry, const double* __restrict__ xfx,
                                                        const double* __restrict__ yfx, const double* __restrict__ u,
                                                        const double* __restrict__ v, const double* __restrict__ ke,
                                                        double* __restrict__ uo, double* __restrict__ vo, int hord_vt, int nk, int kch) {
   const double* src[5] = {crx, cry, xfx, yfx, vq};
   const int ord_ou[1] = {hord_vt}, ord_in[1] = {(hord_vt == 10) ? 8 : hord_vt};
-  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, EDGE ? 32 : 16, EDGE>(L, G, M, src, nk, kch, ord_in, ord_ou,
+  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, EDGE ? 32 : TP2_NF1_NWC, EDGE>(L, G, M, src, nk, kch, ord_in, ord_ou,
     [&](tp2::Smem<1, 0, EDGE>&, const tp2::Geo&, int, long long, int) {},
     [&](tp2::Smem<1, 0, EDGE>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
       const int c = T.lane, i = T.i0 - 3 + c, j = T.j0 - 3 + r;
@@ -962,7 +966,7 @@ static int launch_vort_uv_t(fv3_ctx* c, const double* vq, const double* u, const
 #define VU2_LAUNCH1(H_, E_, MAP_, N_)                                                                                             \
     do {                                                                                                                          \
       FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_vort_uv2<F2, H_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<1, 0, E_>))); \
-      k_dsw_vort_uv2<F2, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), E_ ? 1024 : 512, sizeof(tp2::Smem<1, 0, E_>), c->stream>>>(                                           \
+      k_dsw_vort_uv2<F2, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), E_ ? 1024 : TP2_NF1_NWC * 32, sizeof(tp2::Smem<1, 0, E_>), c->stream>>>(                                           \
           c->L, c->G, MAP_, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, h, nk, E_ ? kch_fr : kch); \
     } while (0)
 #define VU2_LAUNCH(H_)                                                 \

@@ -82,12 +82,12 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tp_fused(Lay L, DevGrid G, tpt::
 
 // interior tiles of the fused height update (update_dz_d, nh_utils.F90:282-299) in the line-per-warp form (tp_line.cuh)
 template <int FAM, int HORD, bool EDGE>
-__global__ void __launch_bounds__(EDGE ? 1024 : 512, EDGE ? 1 : 2) k_tp_zn2(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ q, const double* __restrict__ crx,
+__global__ void __launch_bounds__(1024, 1) k_tp_zn2(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ q, const double* __restrict__ crx,
                                                  const double* __restrict__ cry, const double* __restrict__ xfx, const double* __restrict__ yfx,
                                                  int ord_in_, int ord_ou_, tpt::ZnEpi Z, int nk, int kch) {
   const double* src[5] = {crx, cry, xfx, yfx, q};
   const int ord_in[1] = {ord_in_}, ord_ou[1] = {ord_ou_};
-  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, EDGE ? 32 : 16, EDGE>(L, G, M, src, nk, kch, ord_in, ord_ou,
+  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, 32, EDGE>(L, G, M, src, nk, kch, ord_in, ord_ou,
     [&](tp2::Smem<1, 0, EDGE>&, const tp2::Geo&, int, long long, int) {},
     [&](tp2::Smem<1, 0, EDGE>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
       const int c = T.lane, i = T.i0 - 3 + c, j = T.j0 - 3 + r;
@@ -134,7 +134,7 @@ int launch_tp2d(fv3_ctx* c, const Tp2d& a) {
 #define ZN2_LAUNCH1(F_, H_, E_, MAP_, N_)                                                                                          \
     do {                                                                                                                           \
       FV3_CUDA(c, cudaFuncSetAttribute(k_tp_zn2<F_, H_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<1, 0, E_>))); \
-      k_tp_zn2<F_, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), E_ ? 1024 : 512, sizeof(tp2::Smem<1, 0, E_>), c->stream>>>(L, c->G, MAP_, a.q, a.crx, a.cry, a.xfx, a.yfx,    \
+      k_tp_zn2<F_, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), 1024, sizeof(tp2::Smem<1, 0, E_>), c->stream>>>(L, c->G, MAP_, a.q, a.crx, a.cry, a.xfx, a.yfx,    \
                                                                                   ord_in, a.hord, Z, a.nk, E_ ? kch_fr : kch);     \
       c->launches++;                                                                                                               \
     } while (0)
