@@ -139,10 +139,35 @@ struct NcclApi {
   int (*GroupEnd)();
   const char* (*GetErrorString)(int);
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
+};
+
+// Peer-mapped exchange (one process per GPU on one NVLink / NVSwitch node): every rank owns an ARENA of receive buffers and
+// arrival flags in its device memory and maps the arenas of all ranks with CUDA IPC.  A face's pack kernel stores straight into
+// the receiver's buffer over NVLink, a one-thread kernel publishes the sequence number in the receiver's flag, the receiver's
+// one-thread wait kernel holds its stream until the flag arrives, then the unpack kernel runs.  No NCCL kernel (their channel
+// CTAs spin on SMs the compute kernels need, which is why overlapping the NCCL exchange LOST time: DESIGN.md 4) and no host
+// round trip are on the data path.  Buffers are per (receiving face, sending face, phase, parity of the sequence number): a
+// buffer is rewritten two exchanges of the same phase later, by which time the writer has received the other side's message of
+// the exchange in between -- which that side sent after it unpacked this buffer (stream order).  NCCL remains the bootstrap
+// (all-gather of the IPC handles and layouts) and the fallback.
+constexpr int P2P_MAXR = 8;
+struct P2PArena {
+  bool on = false;
+  int nranks = 0, my_rank = 0;
+  char* base = nullptr; size_t bytes = 0;
+  char* peer[P2P_MAXR] = {nullptr};
+  // layout of every rank's arena (byte offsets, -1: none): buffers [rank][recv face][send face][group][parity], flags [..][group]
+  std::vector<long long> boff, foff;
+  unsigned long long seq[FV3_NUM_HALO_GROUPS] = {0};
+  int* d_err = nullptr;
+  long long& B(int r, int f, int t, int g, int par) { return boff[((((size_t)r * 6 + f) * 6 + t) * FV3_NUM_HALO_GROUPS + g) * 2 + par]; }
+  long long& F(int r, int f, int t, int g) { return foff[(((size_t)r * 6 + f) * 6 + t) * FV3_NUM_HALO_GROUPS + g]; }
 };
 
 struct HaloPlan {
   GroupPlan grp[FV3_NUM_HALO_GROUPS];
+  P2PArena* p2p = nullptr;   // owned by the first context of the process
   fv3_ctx* peer[6];        // contexts of the faces owned by this process (nullptr otherwise)
   int tile_rank[6];        // rank owning each face (-1: absent -> halo frozen)
   int my_rank;
@@ -157,6 +182,7 @@ struct HaloPlan {
 };
 
 static NcclApi g_nccl = {nullptr};
+static int p2p_setup(fv3_ctx** ctxs, int nctx, int nranks, int rank);
 static int nccl_load(fv3_ctx* c) {
   if (g_nccl.lib) return 0;
   void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
@@ -172,6 +198,7 @@ static int nccl_load(fv3_ctx* c) {
   *(void**)(&g_nccl.GroupEnd) = dlsym(h, "ncclGroupEnd");
   *(void**)(&g_nccl.GetErrorString) = dlsym(h, "ncclGetErrorString");
   *(void**)(&g_nccl.AllReduce) = dlsym(h, "ncclAllReduce");
+  *(void**)(&g_nccl.AllGather) = dlsym(h, "ncclAllGather");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd)
     return fv3_fail(c, -4, "libnccl is missing required symbols");
   return 0;
@@ -277,6 +304,12 @@ void halo_destroy(fv3_ctx* c) {
   HaloPlan* hp = c->halo;
   for (int* p : hp->dev_alloc) cudaFree(p);
   for (int t = 0; t < 6; t++) { cudaFree(hp->sendbuf[t]); cudaFree(hp->recvbuf[t]); }
+  if (hp->p2p) {
+    P2PArena* a = hp->p2p;
+    for (int r = 0; r < a->nranks; r++) if (r != a->my_rank && a->peer[r]) cudaIpcCloseMemHandle(a->peer[r]);
+    cudaFree(a->base); cudaFree(a->d_err);
+    delete a;
+  }
   if (hp->comm && hp->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(hp->comm);
   if (hp->xstream) cudaStreamDestroy(hp->xstream);
   if (hp->xdone) cudaEventDestroy(hp->xdone);
@@ -303,6 +336,22 @@ __global__ void k_halo_unpack(double* __restrict__ dst, const double* __restrict
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   dst[(long long)blockIdx.y * plane + d[e]] = (double)sg[e] * buf[(long long)blockIdx.y * n + e];
+}
+
+// publish / await the sequence number of a peer-mapped message (one thread each).  The wait gives up after ~2e9 polls (a protocol
+// error must not hang the GPU): it raises *err and lets the stream continue.
+__global__ void k_p2p_signal(volatile unsigned long long* flag, unsigned long long seq) {
+  __threadfence_system();
+  *flag = seq;
+  __threadfence_system();
+}
+__global__ void k_p2p_wait(const volatile unsigned long long* flag, unsigned long long seq, int* err) {
+  unsigned long long n = 0;
+  while (*flag < seq) {
+    if (++n > 2000000000ull) { atomicExch(err, 1); break; }
+    __nanosleep(64);
+  }
+  __threadfence_system();
 }
 
 extern "C" {
@@ -389,7 +438,7 @@ int fv3_comm_init(fv3_ctx** ctxs, int nctx, const char* id128, int nranks, int r
   for (int a = 1; a < nctx; a++) ctxs[a]->halo->comm = nullptr;
   ctxs[0]->halo->comm = comm;
   ctxs[0]->halo->comm_owned = true;
-  return 0;
+  return p2p_setup(ctxs, nctx, nranks, rank);
 }
 // a communicator owned by the caller (halo_destroy leaves it alone)
 int fv3_comm_attach(fv3_ctx** ctxs, int nctx, void* nccl_comm, int rank, const int tile_rank[6]) {
@@ -406,10 +455,111 @@ int fv3_comm_attach(fv3_ctx** ctxs, int nctx, void* nccl_comm, int rank, const i
     hp->my_rank = rank;
     for (int t = 0; t < 6; t++) hp->tile_rank[t] = tile_rank[t];
   }
-  return 0;
+  int nranks = 0;
+  for (int t = 0; t < 6; t++) nranks = std::max(nranks, tile_rank[t] + 1);
+  return p2p_setup(ctxs, nctx, nranks, rank);
 }
 
 }  // extern "C"
+
+// ---- peer-mapped exchange: arena layout, IPC handle exchange (collective over the communicator) --------------------------------
+static size_t msg_elems(const GroupPlan& gp, int t /*remote face, 0-based*/, bool recv) {
+  size_t n = 0;
+  for (size_t si = 0; si < gp.specs.size(); si++) {
+    const int ncomp = gp.specs[si].fy >= 0 ? 2 : 1;
+    for (int ci = 0; ci < ncomp; ci++)
+      for (int sc = 0; sc < ncomp; sc++)
+        n += (size_t)(recv ? gp.tab[si][ci][t][sc].n : gp.send[si][t][ci][sc].n) * gp.specs[si].nk;
+  }
+  return n;
+}
+static int p2p_setup(fv3_ctx** ctxs, int nctx, int nranks, int rank) {
+  fv3_ctx* c0 = ctxs[0];
+  const char* e = getenv("FV3_HALO_P2P");
+  if (e && e[0] == '0') return 0;                                   // FV3_HALO_P2P=0: NCCL send / recv on the data path
+  if (nranks < 2 || nranks > P2P_MAXR || !g_nccl.AllGather) return 0;
+  void* comm = c0->halo->comm;
+  constexpr int G = FV3_NUM_HALO_GROUPS;
+  P2PArena* A = new P2PArena();
+  A->nranks = nranks; A->my_rank = rank;
+  A->boff.assign((size_t)nranks * 6 * 6 * G * 2, -1); A->foff.assign((size_t)nranks * 6 * 6 * G, -1);
+  size_t off = 0;
+  for (int pass = 0; pass < 2; pass++) {                            // flags first, then the buffers (256-byte aligned)
+    for (int a = 0; a < nctx; a++) {
+      HaloPlan* hp = ctxs[a]->halo; const int f = ctxs[a]->tile - 1;
+      for (int t = 0; t < 6; t++) {
+        const int r = hp->tile_rank[t];
+        if (r < 0 || r == rank || hp->peer[t]) continue;
+        for (int g = 0; g < G; g++) {
+          const size_t nr = msg_elems(hp->grp[g], t, true);
+          if (!nr) continue;
+          if (pass == 0) { A->F(rank, f, t, g) = (long long)off; off += 128; }
+          else for (int par = 0; par < 2; par++) { A->B(rank, f, t, g, par) = (long long)off; off += (nr * sizeof(double) + 255) / 256 * 256; }
+        }
+      }
+    }
+    off = (off + 255) / 256 * 256;
+  }
+  A->bytes = off > 0 ? off : 256;
+  cudaSetDevice(c0->device);
+  bool ok = cudaMalloc(&A->base, A->bytes) == cudaSuccess && cudaMemset(A->base, 0, A->bytes) == cudaSuccess &&
+            cudaMalloc(&A->d_err, sizeof(int)) == cudaSuccess && cudaMemset(A->d_err, 0, sizeof(int)) == cudaSuccess;
+  // record = IPC handle + this rank's slice of the layout tables; all-gathered over the communicator
+  const size_t nB = (size_t)6 * 6 * G * 2, nF = (size_t)6 * 6 * G, rec = sizeof(cudaIpcMemHandle_t) + (nB + nF) * sizeof(long long);
+  std::vector<char> mine(rec, 0), all(rec * nranks, 0);
+  cudaIpcMemHandle_t h; memset(&h, 0, sizeof h);
+  ok = ok && cudaIpcGetMemHandle(&h, A->base) == cudaSuccess;
+  int okflag = ok ? 1 : 0;
+  memcpy(mine.data(), &h, sizeof h);
+  memcpy(mine.data() + sizeof h, &A->boff[(size_t)rank * nB], nB * sizeof(long long));
+  memcpy(mine.data() + sizeof h + nB * sizeof(long long), &A->foff[(size_t)rank * nF], nF * sizeof(long long));
+  if (!ok) memset(mine.data(), 0xff, sizeof h);                      // marks "no arena" for the peers
+  char *d_mine = nullptr, *d_all = nullptr;
+  FV3_CUDA(c0, cudaMalloc(&d_mine, rec)); FV3_CUDA(c0, cudaMalloc(&d_all, rec * nranks));
+  FV3_CUDA(c0, cudaMemcpy(d_mine, mine.data(), rec, cudaMemcpyHostToDevice));
+  const int nrc = g_nccl.AllGather(d_mine, d_all, rec, /*ncclChar*/ 0, comm, c0->stream);
+  if (nrc != 0) { cudaFree(d_mine); cudaFree(d_all); return fv3_fail(c0, 1000 + nrc, "ncclAllGather (peer-mapped halo setup) failed"); }
+  FV3_CUDA(c0, cudaStreamSynchronize(c0->stream));
+  FV3_CUDA(c0, cudaMemcpy(all.data(), d_all, rec * nranks, cudaMemcpyDeviceToHost));
+  cudaFree(d_mine); cudaFree(d_all);
+  for (int r = 0; r < nranks && okflag; r++) {
+    const char* p = all.data() + rec * r;
+    bool none = true;
+    for (size_t b = 0; b < sizeof(cudaIpcMemHandle_t); b++) if ((unsigned char)p[b] != 0xff) { none = false; break; }
+    if (none) { okflag = 0; break; }
+    memcpy(&A->boff[(size_t)r * nB], p + sizeof h, nB * sizeof(long long));
+    memcpy(&A->foff[(size_t)r * nF], p + sizeof h + nB * sizeof(long long), nF * sizeof(long long));
+    if (r == rank) { A->peer[r] = A->base; continue; }
+    cudaIpcMemHandle_t hr; memcpy(&hr, p, sizeof hr);
+    void* q = nullptr;
+    if (cudaIpcOpenMemHandle(&q, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); okflag = 0; break; }
+    A->peer[r] = (char*)q;
+  }
+  // every rank must take the same path: agree on success with a max-reduce of the failure flag
+  {
+    double* d_f = nullptr; double fl = okflag ? 0. : 1.;
+    FV3_CUDA(c0, cudaMalloc(&d_f, sizeof(double)));
+    FV3_CUDA(c0, cudaMemcpy(d_f, &fl, sizeof fl, cudaMemcpyHostToDevice));
+    if (g_nccl.AllReduce(d_f, d_f, 1, /*ncclFloat64*/ 8, /*ncclMax*/ 2, comm, c0->stream) != 0) fl = 1.;
+    else { cudaStreamSynchronize(c0->stream); cudaMemcpy(&fl, d_f, sizeof fl, cudaMemcpyDeviceToHost); }
+    cudaFree(d_f);
+    if (fl != 0.) okflag = 0;
+  }
+  if (!okflag) {   // stay on NCCL send / recv
+    for (int r = 0; r < nranks; r++) if (r != rank && A->peer[r]) cudaIpcCloseMemHandle(A->peer[r]);
+    cudaFree(A->base); cudaFree(A->d_err); delete A;
+    return 0;
+  }
+  A->on = true;
+  c0->halo->p2p = A;
+  return 0;
+}
+// 1 when the peer-mapped exchange is active for this process's faces, else 0; *err (nullable) receives the arrival-timeout flag
+extern "C" int fv3_halo_p2p_status(fv3_ctx* c, int* err) {
+  if (!c || !c->halo || !c->halo->p2p || !c->halo->p2p->on) { if (err) *err = 0; return 0; }
+  if (err) { cudaSetDevice(c->device); cudaMemcpy(err, c->halo->p2p->d_err, sizeof(int), cudaMemcpyDeviceToHost); }
+  return 1;
+}
 
 // overlapped != 0: the exchange runs on ctx0's side stream after everything enqueued so far on the face streams, and the
 // face streams do NOT wait for it (fv3_halo_wait joins them): the caller may enqueue work that touches neither the halo
@@ -446,6 +596,10 @@ static int halo_exchange_impl(fv3_ctx** ctxs, int nctx, int group, int overlappe
   if (any_remote && !comm) return fv3_fail(c0, -1, "halo_exchange: remote faces but no communicator");
   struct Msg { fv3_ctx* c; int tile; int rank; size_t nsend, nrecv; };
   std::vector<Msg> msgs;
+  P2PArena* A = hp0->p2p;
+  const bool p2p = any_remote && A && A->on;
+  const unsigned long long seq = p2p ? ++A->seq[group] : 0;
+  const int par = (int)(seq & 1);
   if (any_remote) {
     for (int a = 0; a < nctx; a++) {
       fv3_ctx* c = ctxs[a]; HaloPlan* hp = c->halo; GroupPlan& gp = hp->grp[group];
@@ -463,7 +617,15 @@ static int halo_exchange_impl(fv3_ctx** ctxs, int nctx, int group, int overlappe
         }
         if (ns == 0 && nr == 0) continue;
         const size_t need = std::max(ns, nr);
-        if (need > hp->bufcap[t - 1] || !hp->sendbuf[t - 1]) {
+        // peer-mapped mode: the pack kernels store into the receiver's arena: its buffer for (its face t, my face, phase, parity)
+        double* pack_dst = nullptr;
+        if (p2p) {
+          if (ns) {
+            const long long bo = A->B(r, t - 1, c->tile - 1, group, par), fo = A->F(r, t - 1, c->tile - 1, group);
+            if (bo < 0 || fo < 0) return fv3_fail(c, -1, "halo_exchange: the receiving rank's arena has no buffer for this message");
+            pack_dst = (double*)(A->peer[r] + bo);
+          }
+        } else if (need > hp->bufcap[t - 1] || !hp->sendbuf[t - 1]) {
           const size_t cap = need + need / 4;
           cudaFree(hp->sendbuf[t - 1]); cudaFree(hp->recvbuf[t - 1]);
           FV3_CUDA(c, cudaMalloc(&hp->sendbuf[t - 1], cap * sizeof(double)));
@@ -481,10 +643,14 @@ static int halo_exchange_impl(fv3_ctx** ctxs, int nctx, int group, int overlappe
               if (!tb.n) continue;
               const double* src = c->fld[sc == 0 ? fs.fx : fs.fy];
               dim3 g((tb.n + 127) / 128, fs.nk);
-              k_halo_pack<<<g, 128, 0, st>>>(hp->sendbuf[t - 1] + off, src, tb.src, tb.n, c->L.plane);
+              k_halo_pack<<<g, 128, 0, st>>>((p2p ? pack_dst : hp->sendbuf[t - 1]) + off, src, tb.src, tb.n, c->L.plane);
               c->launches++;
               off += (size_t)tb.n * fs.nk;
             }
+        }
+        if (p2p && ns) {   // the message is complete in the receiver's memory: publish its sequence number there
+          k_p2p_signal<<<1, 1, 0, st>>>((volatile unsigned long long*)(A->peer[r] + A->F(r, t - 1, c->tile - 1, group)), seq);
+          c->launches++;
         }
         msgs.push_back({c, t, r, ns, nr});
       }
@@ -497,8 +663,9 @@ static int halo_exchange_impl(fv3_ctx** ctxs, int nctx, int group, int overlappe
       const int yl = (my_rank < y.rank) ? y.c->tile : y.tile, yh = (my_rank < y.rank) ? y.tile : y.c->tile;
       return xl != yl ? xl < yl : xh < yh;
     });
-    g_nccl.GroupStart();
+    if (!p2p) g_nccl.GroupStart();
     for (const Msg& m : msgs) {
+      if (p2p) break;
       HaloPlan* hp = m.c->halo;
       // tag-free ordering: one message per (my face, peer face) pair and phase; NCCL matches
       // sends and receives between a pair of ranks in issue order, and both ranks enumerate
@@ -508,7 +675,7 @@ static int halo_exchange_impl(fv3_ctx** ctxs, int nctx, int group, int overlappe
       if (m.nsend) g_nccl.Send(hp->sendbuf[m.tile - 1], m.nsend, /*ncclDouble*/ 8, m.rank, comm, st);
       if (m.nrecv) g_nccl.Recv(hp->recvbuf[m.tile - 1], m.nrecv, 8, m.rank, comm, st);
     }
-    const int nrc = g_nccl.GroupEnd();
+    const int nrc = p2p ? 0 : g_nccl.GroupEnd();
     if (nrc != 0) return fv3_fail(c0, 1000 + nrc, "ncclGroupEnd failed");
   }
   // ---- local gathers.  Two-phase so that no face reads a halo another gather is writing:
@@ -539,6 +706,15 @@ static int halo_exchange_impl(fv3_ctx** ctxs, int nctx, int group, int overlappe
   for (const Msg& m : msgs) {
     fv3_ctx* c = m.c; HaloPlan* hp = c->halo; GroupPlan& gp = hp->grp[group];
     size_t off = 0;
+    const double* rbuf = hp->recvbuf[m.tile - 1];
+    if (p2p) {
+      if (!m.nrecv) continue;
+      const long long bo = A->B(A->my_rank, c->tile - 1, m.tile - 1, group, par), fo = A->F(A->my_rank, c->tile - 1, m.tile - 1, group);
+      if (bo < 0 || fo < 0) return fv3_fail(c, -1, "halo_exchange: no arena buffer for an expected message");
+      rbuf = (const double*)(A->base + bo);
+      k_p2p_wait<<<1, 1, 0, st>>>((const volatile unsigned long long*)(A->base + fo), seq, A->d_err);   // holds the stream until the sender's flag arrives
+      c->launches++;
+    }
     for (size_t si = 0; si < gp.specs.size(); si++) {
       const FieldSpec& fs = gp.specs[si];
       const int ncomp = fs.fy >= 0 ? 2 : 1;
@@ -547,7 +723,7 @@ static int halo_exchange_impl(fv3_ctx** ctxs, int nctx, int group, int overlappe
           const DevTable& tb = gp.tab[si][ci][m.tile - 1][sc];
           if (!tb.n) continue;
           dim3 g((tb.n + 127) / 128, fs.nk);
-          k_halo_unpack<<<g, 128, 0, st>>>(c->fld[ci == 0 ? fs.fx : fs.fy], hp->recvbuf[m.tile - 1] + off, tb.dst, tb.sign, tb.n, c->L.plane);
+          k_halo_unpack<<<g, 128, 0, st>>>(c->fld[ci == 0 ? fs.fx : fs.fy], rbuf + off, tb.dst, tb.sign, tb.n, c->L.plane);
           c->launches++;
           off += (size_t)tb.n * fs.nk;
         }

@@ -257,6 +257,11 @@ int fv3_halo_wait(fv3_ctx **ctxs, int nctx);
  * fv3_comm_init with the face->rank map (6 ints, -1 = face absent). */
 int fv3_nccl_unique_id(char *out128);
 int fv3_comm_init(fv3_ctx **ctxs, int nctx, const char *id128, int nranks, int rank, const int *tile_rank);
+/* fv3_comm_init / fv3_comm_attach also try to set up the PEER-MAPPED exchange (ranks on one NVLink / NVSwitch node): every rank maps
+ * the others' receive arenas with CUDA IPC, pack kernels store straight into the receiver's buffer, one-thread kernels publish /
+ * await a sequence number; no NCCL kernel on the data path (FV3_HALO_P2P=0 in the environment, or any failure of the IPC setup on
+ * any rank, keeps NCCL send / recv).  Returns 1 when it is active for ctx's process; *err (nullable) = 1 after an arrival timeout. */
+int fv3_halo_p2p_status(fv3_ctx *ctx, int *err);
 /* Halo index tables (host logic, no device needed): entries of face `tile` for one array
  * of a scalar (ncomp=1) or pair (ncomp=2) field; positions 0 centre, 1 corner, 2 north-
  * staggered (D-grid u, C-grid vc), 3 east-staggered (D-grid v, C-grid uc). Returns the

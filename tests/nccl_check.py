@@ -76,6 +76,15 @@ if cube is not None:
         if not np.array_equal(a, b):
             ok = False
             print(f"rank {rank} tile {t} tracer differs: max {np.abs(a-b).max():.3e}")
+    # which exchange carried the data: peer-mapped (CUDA IPC arenas, no NCCL kernel on the data path) or NCCL send / recv
+    perr = C.c_int(0)
+    fn = lib[0].fv3_halo_p2p_status
+    fn.restype = C.c_int
+    on = fn(cube.eng[my[0]].ctx, C.byref(perr))
+    want = os.environ.get("FV3_CHECK_EXPECT_P2P")
+    print(f"rank {rank}: halo exchange = {'peer-mapped' if on == 1 else 'nccl'}, arrival timeout flag = {perr.value}")
+    if perr.value != 0 or (want is not None and on != int(want)):
+        ok = False
     if os.environ.get("FV3_CHECK_ATTACH") == "1":
         cube.close()      # must NOT destroy the borrowed communicator ...
         assert nccl.ncclCommDestroy(comm) == 0   # ... so the owner can
