@@ -126,6 +126,8 @@ def run_ours(args):
     cube = CudaCube.for_rank(case, rank, world, device=local)
     if world > 1:
         CudaCube.attach_nccl(cube, rank, world)   # the library's own NCCL communicator over the active ranks
+    if args.transport_fp32 and cube is not None:
+        cube.set_transport_fp32(True)             # BASELINE config 5 (not the headline): fp32 PPM sweeps on d_sw's interior tiles
 
     def barrier():
         torch.cuda.synchronize()
@@ -272,7 +274,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 (fp32 PPM sweeps on d_sw interior tiles: --transport-fp32)" if args.transport_fp32 else "f64", "data": "synthetic",
             "config": cfg,
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": int(hb[0].item()),
@@ -366,6 +369,8 @@ def main():
     ap.add_argument("--flagset", default="A")
     ap.add_argument("--ref-substeps", dest="ref_substeps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--transport-fp32", dest="transport_fp32", action="store_true",
+                    help="mixed precision (BASELINE config 5): fv3_set_transport_fp32; the default headline run is all fp64")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -307,6 +307,11 @@ int fv3_sync(fv3_ctx* c) {
 }
 
 long long fv3_launch_count(const fv3_ctx* c) { return c ? c->launches : -1; }
+int fv3_set_transport_fp32(fv3_ctx* c, int on) {
+  if (!c) return -1;
+  c->tp_fp32 = on ? 1 : 0;
+  return 0;
+}
 
 int fv3_stage_timers(fv3_ctx* c, int enable) {
   if (!c) return -1;

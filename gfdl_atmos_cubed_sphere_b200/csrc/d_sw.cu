@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_dsw_vort_uv(Lay L, DevGrid G, tp
 // ---- interior tiles, line-per-warp form (tp_line.cuh): delp, [w,] pt transported phase-major by a CTA that is persistent over
 // a chunk of levels.  Same arithmetic as k_dsw_transport (the mass fluxes of delp weight the other fields' fluxes in the outer
 // sweep, the flux divergences are applied in the epilogue); launched when no del-n flux and no q_con is in play.
-template <int FAM, int NF, int HORD, bool EDGE>
+template <int FAM, int NF, int HORD, bool EDGE, typename R = double>
 __global__ void __launch_bounds__(tp2::NT, 1) k_dsw_transport2(Lay L, DevGrid G, tpt::TileMap M, DswTr a, int nk, int kch) {
   static_assert(NF == 2 || NF == 3, "fields: delp, [w,] pt");
   const double* src[4 + NF];
@@ -799,34 +799,34 @@ __global__ void __launch_bounds__(tp2::NT, 1) k_dsw_transport2(Lay L, DevGrid G,
     if (T.wid < tp2::TY && (!EDGE || (i <= L.ied && j <= L.jed))) ra = __ldg(G.rarea + tp2::gidx(T, i, j));
     lastx = T.i0 + tp2::TX > L.ie; lasty = T.j0 + tp2::TY > L.je;
   }
-  tp2::run_tile<FAM, NF, 2, tp2::W_MASS, HORD, 32, EDGE>(L, G, M, src, nk, kch, ord_in, ord_ou,
-    [&](tp2::Smem<NF, 2, EDGE>& S, const tp2::Geo& T, int k, long long ko, int r) {   // the flux capacitors' old values (read-modify-write, :928-940)
+  tp2::run_tile<FAM, NF, 2, tp2::W_MASS, HORD, 32, EDGE, R>(L, G, M, src, nk, kch, ord_in, ord_ou,
+    [&](tp2::Smem<NF, 2, EDGE, R>& S, const tp2::Geo& T, int k, long long ko, int r) {   // the flux capacitors' old values (read-modify-write, :928-940)
       const int c = T.lane, i = T.i0 - 3 + c, j = T.j0 - 3 + r;
       if (c < 3 || c > tp2::TX + 3 || (EDGE && (i > L.ie + 1 || j > L.je + 1))) return;
       const long long g = ko + tp2::gidx(T, i, j);
       tpt::cp_async8(&S.ep[0][r * tp2::P + c], a.mfx + g);
       tpt::cp_async8(&S.ep[1][r * tp2::P + c], a.mfy + g);
     },
-    [&](tp2::Smem<NF, 2, EDGE>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
+    [&](tp2::Smem<NF, 2, EDGE, R>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
       const int c = T.lane, i = T.i0 - 3 + c, j = T.j0 - 3 + r;
       if (c < 3 || c > tp2::TX + 3 || (EDGE && (i > L.ie + 1 || j > L.je + 1))) return;
       const int o = r * tp2::P + c;
       const long long g = ko + tp2::gidx(T, i, j);
-      const double mx0 = S.qi[0][o], my0 = S.qj[0][o];
+      const double mx0 = (double)S.qi[0][o], my0 = (double)S.qj[0][o];
       // flux capacitors: the tile's own west / south faces, plus the face's last column / row of faces
       const bool xface = r <= tp2::TY + 2 && (!EDGE || j <= L.je) && (c <= tp2::TX + 2 || (EDGE && lastx));
       const bool yface = c <= tp2::TX + 2 && (!EDGE || i <= L.ie) && (r <= tp2::TY + 2 || (EDGE && lasty));
       if (xface) a.mfx[g] = S.ep[0][o] + mx0;
       if (yface) a.mfy[g] = S.ep[1][o] + my0;
       if (r > tp2::TY + 2 || c > tp2::TX + 2 || (EDGE && (i > L.ie || j > L.je))) return;   // not a cell of the tile
-      const double mx1 = S.qi[0][o + 1], my1 = S.qj[0][o + tp2::P];
-      const double dp = S.in[b][tp2::A_Q][o];
+      const double mx1 = (double)S.qi[0][o + 1], my1 = (double)S.qj[0][o + tp2::P];
+      const double dp = S.q64(b, 0, o);
       const double dpn = dp + (mx0 - mx1 + my0 - my1) * ra;
       const double rdpn = 1. / dpn;   // one division for w and pt (<= 1 ulp from the two divisions of sw_core.F90:986, 1061)
 #pragma unroll
       for (int f = 1; f < NF; f++) {
-        const double div = (S.qi[f][o] - S.qi[f][o + 1] + S.qj[f][o] - S.qj[f][o + tp2::P]) * ra;
-        const double q = S.in[b][tp2::A_Q + f][o];
+        const double div = ((double)S.qi[f][o] - (double)S.qi[f][o + 1] + (double)S.qj[f][o] - (double)S.qj[f][o + tp2::P]) * ra;
+        const double q = S.q64(b, f, o);
         double v = (q * dp + div) * rdpn;
         if (NF == 3 && f == 1) {
           if (a.dw && a.kdbl[KD_DAMP4_W * n1 + k] != 0.) v = v + __ldg(a.dw + g);
@@ -842,7 +842,7 @@ __global__ void __launch_bounds__(tp2::NT, 1) k_dsw_transport2(Lay L, DevGrid G,
 #ifndef TP2_NF1_NWC
 #define TP2_NF1_NWC 32   // measured at C384L79: 401 us (one CTA of 32 warps per SM) vs 420 us (two CTAs of 16)
 #endif
-template <int FAM, int HORD, bool EDGE>
+template <int FAM, int HORD, bool EDGE, typename R = double>
 __global__ void __launch_bounds__(EDGE ? 1024 : TP2_NF1_NWC * 32, EDGE ? 1 : 32 / TP2_NF1_NWC) k_dsw_vort_uv2(Lay L, DevGrid G, tpt::TileMap M, const double* __restrict__ vq, const double* __restrict__ crx,
                                                        const double* __restrict__ cry, const double* __restrict__ xfx,
                                                        const double* __restrict__ yfx, const double* __restrict__ u,
@@ -850,9 +850,9 @@ __global__ void __launch_bounds__(EDGE ? 1024 : TP2_NF1_NWC * 32, EDGE ? 1 : 32 
                                                        double* __restrict__ uo, double* __restrict__ vo, int hord_vt, int nk, int kch) {
   const double* src[5] = {crx, cry, xfx, yfx, vq};
   const int ord_ou[1] = {hord_vt}, ord_in[1] = {(hord_vt == 10) ? 8 : hord_vt};
-  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, EDGE ? 32 : TP2_NF1_NWC, EDGE>(L, G, M, src, nk, kch, ord_in, ord_ou,
-    [&](tp2::Smem<1, 0, EDGE>&, const tp2::Geo&, int, long long, int) {},
-    [&](tp2::Smem<1, 0, EDGE>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
+  tp2::run_tile<FAM, 1, 0, tp2::W_AREA, HORD, EDGE ? 32 : TP2_NF1_NWC, EDGE, R>(L, G, M, src, nk, kch, ord_in, ord_ou,
+    [&](tp2::Smem<1, 0, EDGE, R>&, const tp2::Geo&, int, long long, int) {},
+    [&](tp2::Smem<1, 0, EDGE, R>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
       const int c = T.lane, i = T.i0 - 3 + c, j = T.j0 - 3 + r;
       if (c < 3 || c > tp2::TX + 3 || (EDGE && (i > L.ie + 1 || j > L.je + 1))) return;
       const bool lastx = T.i0 + tp2::TX > L.ie, lasty = T.j0 + tp2::TY > L.je;
@@ -862,9 +862,9 @@ __global__ void __launch_bounds__(EDGE ? 1024 : TP2_NF1_NWC * 32, EDGE ? 1 : 32 
       const double kev = __ldg(ke + g);
       // v on (is:ie+1, js:je): west faces; u on (is:ie, js:je+1): south faces
       if (r <= tp2::TY + 2 && (!EDGE || j <= L.je) && (c <= tp2::TX + 2 || (EDGE && lastx)))
-        vo[g] = __ldg(v + g) * __ldg(G.dy + gi) + kev - __ldg(ke + g + T.NI) - S.qi[0][o];
+        vo[g] = __ldg(v + g) * __ldg(G.dy + gi) + kev - __ldg(ke + g + T.NI) - (double)S.qi[0][o];
       if (c <= tp2::TX + 2 && (!EDGE || i <= L.ie) && (r <= tp2::TY + 2 || (EDGE && lasty)))
-        uo[g] = __ldg(u + g) * __ldg(G.dx + gi) + kev - __ldg(ke + g + 1) + S.qj[0][o];
+        uo[g] = __ldg(u + g) * __ldg(G.dx + gi) + kev - __ldg(ke + g + 1) + (double)S.qj[0][o];
     });
 }
 
@@ -901,7 +901,8 @@ static int launch_transport_t(fv3_ctx* c, const DswTr& a, int nk) {
   // the line-per-warp kernels (tp_line.cuh) when only delp, [w,] pt are transported with the common schemes and no del-n flux
   // is added; interior tiles and frame tiles are separate instantiations (the frame one carries the cube-edge cells)
   const bool lines = FAM != 2 && use_line_kernels() && a.pt && !a.qcon && !a.dpx && !a.ptx && !a.qcx;
-  const bool lines_fr = lines && use_line_kernels() > 1;
+  const bool fp32 = lines && c->tp_fp32;
+  const bool lines_fr = (lines && use_line_kernels() > 1) || fp32;
   if (lines) {
     constexpr int F2 = FAM == 2 ? 0 : FAM;
     const int kch = tp2::level_chunk(nk), nch = (nk + kch - 1) / kch, kch_fr = (kch + 1) / 2, nch_fr = (nk + kch_fr - 1) / kch_fr;
@@ -913,8 +914,17 @@ static int launch_transport_t(fv3_ctx* c, const DswTr& a, int nk) {
       FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport2<F2, NF_, H_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<NF_, 2, E_>))); \
       k_dsw_transport2<F2, NF_, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), tp2::NT, sizeof(tp2::Smem<NF_, 2, E_>), c->stream>>>(c->L, c->G, MAP_, a, nk, E_ ? kch_fr : kch); \
     } while (0)
+#define TR2_LAUNCH32(NF_, H_)                                                                                                      \
+    do {                                                                                                                           \
+      /* fp32 sweeps (strict float: tp_line.cuh): the interior and the frame instantiation give a shared face the same flux bit for bit */ \
+      FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport2<F2, NF_, H_, false, tp2::sf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<NF_, 2, false, tp2::sf>))); \
+      FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport2<F2, NF_, H_, true, tp2::sf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<NF_, 2, true, tp2::sf>))); \
+      if (n_in) k_dsw_transport2<F2, NF_, H_, false, tp2::sf><<<dim3(n_in, nch), tp2::NT, sizeof(tp2::Smem<NF_, 2, false, tp2::sf>), c->stream>>>(c->L, c->G, Min, a, nk, kch); \
+      if (n_fr) k_dsw_transport2<F2, NF_, H_, true, tp2::sf><<<dim3(n_fr, nch_fr), tp2::NT, sizeof(tp2::Smem<NF_, 2, true, tp2::sf>), c->stream>>>(c->L, c->G, Mfr, a, nk, kch_fr); \
+    } while (0)
 #define TR2_LAUNCH(NF_, H_)                                                        \
     do {                                                                           \
+      if (fp32) { TR2_LAUNCH32(NF_, H_); break; }                                  \
       if (n_in) TR2_LAUNCH1(NF_, H_, false, Min, n_in);                            \
       if (n_fr && lines_fr) TR2_LAUNCH1(NF_, H_, true, Mfr, n_fr);                 \
     } while (0)
@@ -931,6 +941,7 @@ static int launch_transport_t(fv3_ctx* c, const DswTr& a, int nk) {
     } else TR2_LAUNCH(2, tp2::ORD_RT);
 #undef TR2_LAUNCH
 #undef TR2_LAUNCH1
+#undef TR2_LAUNCH32
   } else if (n_in) k_dsw_transport<FAM, false><<<dim3(n_in, 1, nk), tpt::NT, sizeof(DswSmem), c->stream>>>(c->L, c->G, Min, a);
   if (n_fr && !lines_fr) k_dsw_transport<FAM, true><<<dim3(n_fr, 1, nk), tpt::NT, sizeof(DswSmem), c->stream>>>(c->L, c->G, Mfr, a);
   c->launches += (n_in ? 1 : 0) + (n_fr ? 1 : 0);
@@ -958,7 +969,7 @@ static int launch_vort_uv_t(fv3_ctx* c, const double* vq, const double* u, const
   tpt::tile_maps(c->L, Min, Mfr, n_in, n_fr);
   // frame tiles of a single transported field: the first-generation kernel (two CTAs per SM) is faster than the line kernel with its
   // cube-edge tables (one CTA per SM): measured 217 vs 281 us at C384L79 (profiles/r2_dsw_kernels.md); FV3_TP_LINES=3 forces lines
-  const bool lines = FM != 2 && use_line_kernels(), lines_fr = lines && use_line_kernels() > 2;
+  const bool lines = FM != 2 && use_line_kernels(), fp32 = lines && c->tp_fp32, lines_fr = lines && use_line_kernels() > 2;
   if (lines) {
     constexpr int F2 = FM == 2 ? 0 : FM;
     const int kch = tp2::level_chunk(nk), nch = (nk + kch - 1) / kch, kch_fr = (kch + 1) / 2, nch_fr = (nk + kch_fr - 1) / kch_fr;
@@ -969,9 +980,17 @@ static int launch_vort_uv_t(fv3_ctx* c, const double* vq, const double* u, const
       k_dsw_vort_uv2<F2, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), E_ ? 1024 : TP2_NF1_NWC * 32, sizeof(tp2::Smem<1, 0, E_>), c->stream>>>(                                           \
           c->L, c->G, MAP_, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, h, nk, E_ ? kch_fr : kch); \
     } while (0)
+#define VU2_LAUNCH32(H_)                                                                                                          \
+    do {                                                                                                                          \
+      /* every u, v point is updated by exactly one tile (no flux is applied from two sides), so the frame tiles may keep the fp64 kernel */ \
+      FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_vort_uv2<F2, H_, false, tp2::sf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<1, 0, false, tp2::sf>))); \
+      k_dsw_vort_uv2<F2, H_, false, tp2::sf><<<dim3(n_in, nch), TP2_NF1_NWC * 32, sizeof(tp2::Smem<1, 0, false, tp2::sf>), c->stream>>>(                                     \
+          c->L, c->G, Min, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, h, nk, kch); \
+    } while (0)
 #define VU2_LAUNCH(H_)                                                 \
     do {                                                               \
-      if (n_in) VU2_LAUNCH1(H_, false, Min, n_in);                     \
+      if (n_in && fp32) VU2_LAUNCH32(H_);                              \
+      else if (n_in) VU2_LAUNCH1(H_, false, Min, n_in);                \
       if (n_fr && lines_fr) VU2_LAUNCH1(H_, true, Mfr, n_fr);          \
     } while (0)
     if constexpr (F2 == 1) {
@@ -985,6 +1004,7 @@ static int launch_vort_uv_t(fv3_ctx* c, const double* vq, const double* u, const
     }
 #undef VU2_LAUNCH
 #undef VU2_LAUNCH1
+#undef VU2_LAUNCH32
   } else if (n_in) k_dsw_vort_uv<FM, false><<<dim3(n_in, 1, nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(
       c->L, c->G, Min, vq, c->fld[FV3_CRX], c->fld[FV3_CRY], c->fld[FV3_XFX], c->fld[FV3_YFX], u, v, ke, uo, vo, c->f.hord_vt);
   if (n_fr && !lines_fr) k_dsw_vort_uv<FM, true><<<dim3(n_fr, 1, nk), tpt::NT, sizeof(tpt::Smem), c->stream>>>(

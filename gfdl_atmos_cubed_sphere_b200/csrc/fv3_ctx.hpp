@@ -138,6 +138,7 @@ struct fv3_ctx {
   double* d_edge_tab;              // edge_profile coefficient tables (nh.cu), built on first use
   double* d_rff = nullptr; int k_rf = 0;   // Rayleigh damping table of the vertical solvers (fast_tau_w_sec > 0), built by the first solver call
   long long launches;
+  int tp_fp32 = 0;   // fv3_set_transport_fp32: the interior-tile PPM sweeps of d_sw compute in fp32 (fp64 storage and updates)
   bool timers_on;
   std::map<std::string, StageTimer> timers;
   HaloPlan* halo;

@@ -81,6 +81,15 @@ class CudaCube:
         for t in self.tiles:
             self.eng[t].sync()
 
+    def set_transport_fp32(self, on=True):
+        """fv3_set_transport_fp32 on every face: fp32 PPM sweeps on the interior tiles of d_sw (BASELINE config 5)."""
+        fn = self.lib[0].fv3_set_transport_fp32
+        fn.restype = C.c_int
+        for t in self.tiles:
+            rc = fn(self.eng[t].ctx, C.c_int(1 if on else 0))
+            if rc:
+                raise RuntimeError(f"fv3_set_transport_fp32 rc={rc}")
+
     def del2_cubed(self, field, cd, nmax):
         fn = self.lib[0].fv3_del2_cubed_cube
         fn.restype = C.c_int

@@ -262,6 +262,12 @@ int fv3_comm_init(fv3_ctx **ctxs, int nctx, const char *id128, int nranks, int r
  * await a sequence number; no NCCL kernel on the data path (FV3_HALO_P2P=0 in the environment, or any failure of the IPC setup on
  * any rank, keeps NCCL send / recv).  Returns 1 when it is active for ctx's process; *err (nullable) = 1 after an arrival timeout. */
 int fv3_halo_p2p_status(fv3_ctx *ctx, int *err);
+/* Mixed precision (BASELINE config 5: "fp32 transport / fp64 Riemann"; the reference's analogue is its 32-bit build, a compile-time
+ * choice, not a namelist flag -- hence a setter, not a member of fv3_flags_t).  on = 1: the PPM sweeps of d_sw's interior tiles
+ * (fv_tp_2d of delp, w, pt and of the vorticity) compute in fp32 from fp64 fields; the fluxes are applied to the fp64 prognostics
+ * in fp64, so the flux-form update stays conservative.  Cube-edge (frame) tiles, the height transport of update_dz_d, the column
+ * solvers and every other stage stay fp64.  Default 0 (everything fp64: the configuration every parity number refers to). */
+int fv3_set_transport_fp32(fv3_ctx *ctx, int on);
 /* Halo index tables (host logic, no device needed): entries of face `tile` for one array
  * of a scalar (ncomp=1) or pair (ncomp=2) field; positions 0 centre, 1 corner, 2 north-
  * staggered (D-grid u, C-grid vc), 3 east-staggered (D-grid v, C-grid uc). Returns the

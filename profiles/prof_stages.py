@@ -2,7 +2,7 @@
 (CUDA events on the launch stream, nothing else in flight).  The stages run on the initial state in the
 dyn_core order; a single face has no valid halo after the first substep, so this driver is for timing and
 ncu launch lists only (parity lives in tests/).
-   usage: python profiles/prof_stages.py [res] [npz] [flagset] [reps]"""
+   usage: python profiles/prof_stages.py [res] [npz] [flagset] [reps]      (FV3_TRANSPORT_FP32=1: fv3_set_transport_fp32)"""
 import ctypes as C
 import os
 import sys
@@ -18,6 +18,8 @@ fs = sys.argv[3] if len(sys.argv) > 3 else "A"
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 case = H.Case(res, npz, fs, state="baroclinic")
 e = case.engine(abi.load_library(), 1)
+if os.environ.get("FV3_TRANSPORT_FP32") == "1":
+    e.lib.fv3_set_transport_fp32(e.ctx, 1)
 dt = 225.0 / 8 * 384 / res
 F = abi.FIELD_ID
 one = (C.c_void_p * 1)(e.ctx)
@@ -39,6 +41,6 @@ for rep in range(reps + 1):
         if rep > 0:
             tot[name] = tot.get(name, 0.0) + ms.value / reps
 s = sum(tot.values())
-print(f"one face C{res}L{npz} flag-set {fs}: {s:.3f} ms per substep (sum of stages, each alone)")
+print(f"one face C{res}L{npz} flag-set {fs}{' fp32 sweeps' if os.environ.get('FV3_TRANSPORT_FP32') == '1' else ''}: {s:.3f} ms per substep (sum of stages, each alone)")
 for k, v in tot.items():
     print(f"  {k:14s} {v:8.3f} ms {100 * v / s:5.1f}%")
