@@ -137,7 +137,7 @@ def run_ours(args):
 
     def step():
         if cube is not None:
-            cube.dyn_core(bdt, n_split)
+            cube.dyn_core(bdt, n_split, graph=args.graph)
 
     # pinned host copies of the prognostic state for the e2e (host-buffer) leg
     e2e_fields = ["U", "V", "W", "DELZ", "PT", "DELP", "PHIS"]
@@ -160,7 +160,7 @@ def run_ours(args):
                 p = pinned[(t, f)]
                 e.check(e._fn("put_field")(e.ctx, abi.FIELD_ID[f], C.c_void_p(p.data_ptr())), "put_field")
                 h2d += p.numel() * 8
-        cube.dyn_core(bdt, n_split)
+        cube.dyn_core(bdt, n_split, graph=args.graph)
         for t in my_tiles:
             e = cube.eng[t]
             for f in ("U", "V", "W", "DELZ", "PT", "DELP"):
@@ -271,6 +271,7 @@ def run_ours(args):
         traffic, traffic_src = dsw_dram_traffic(n, npz, args.flagset)
         cfg = workload_config(args)
         cfg["faces_per_rank"] = len(tiles_of_rank(0, world))
+        cfg["launch"] = "CUDA graph (FV3_DYN_GRAPH)" if args.graph and world == 1 else "direct kernel launches"
         line = {
             "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True,
@@ -369,6 +370,8 @@ def main():
     ap.add_argument("--flagset", default="A")
     ap.add_argument("--ref-substeps", dest="ref_substeps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--graph", action="store_true",
+                    help="fv3_dyn_core(FV3_DYN_GRAPH): the step as one CUDA graph (single-process runs; bit-identical to the direct launches)")
     ap.add_argument("--transport-fp32", dest="transport_fp32", action="store_true",
                     help="mixed precision (BASELINE config 5): fv3_set_transport_fp32; the default headline run is all fp64")
     args = ap.parse_args()

@@ -248,6 +248,7 @@ void fv3_destroy(fv3_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   halo_destroy(c);
+  fv3_free_graphs(c);
   for (int i = 0; i < FV3_NUM_FIELDS; i++) cudaFree(c->fld[i]);
   double* alts[6] = {c->alt_delp, c->alt_pt, c->alt_w, c->alt_u, c->alt_v, c->alt_qcon};
   for (auto p : alts) cudaFree(p);

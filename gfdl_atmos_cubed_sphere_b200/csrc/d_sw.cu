@@ -1025,9 +1025,11 @@ int stage_d_sw(fv3_ctx* c, double dt) {
   if (f.nord > 3) return fv3_fail(c, -2, "d_sw: nord > 3 not supported");
   std::vector<int> ki; std::vector<double> kd;
   dsw_tables(c, ki, kd);
-  FV3_CUDA(c, cudaMemcpyAsync(c->d_kint, ki.data(), ki.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  FV3_CUDA(c, cudaMemcpyAsync(c->d_kdbl, kd.data(), kd.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  // the tables are consumed asynchronously; ki/kd are pageable -> copy is staged by the driver before return
+  if (!c->capturing) {   // graph capture (dyn_core.cu): the tables depend on the flags only and were uploaded by an earlier direct call
+    FV3_CUDA(c, cudaMemcpyAsync(c->d_kint, ki.data(), ki.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    FV3_CUDA(c, cudaMemcpyAsync(c->d_kdbl, kd.data(), kd.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // the tables are consumed asynchronously; ki/kd are pageable -> copy is staged by the driver before return
+  }
   const int n1 = nk + 1;
   bool any_w = false, any_v = false, any_deln = false, any_deln_t = false, any_n0 = false, any_nn = false;
   int nord_max = 0;

@@ -16,6 +16,7 @@
 #include "fv3_ctx.hpp"
 #include <cstdlib>
 #include <algorithm>
+#include <vector>
 
 extern "C" int fv3_halo_exchange(fv3_ctx** ctxs, int nctx, int group);
 extern "C" int fv3_halo_start(fv3_ctx** ctxs, int nctx, int group);
@@ -29,9 +30,130 @@ extern "C" int fv3_halo_wait(fv3_ctx** ctxs, int nctx);
     if (rc_) return rc_;                               \
   }
 
+static int dyn_core_direct(fv3_ctx** ctxs, int nctx, double bdt, int n_split);
+static int dyn_core_graph(fv3_ctx** ctxs, int nctx, double bdt, int n_split);
+
 extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, int flags) {
   if (!ctxs || nctx < 1 || n_split < 1) return -1;
-  if (flags != 0) return fv3_fail(ctxs[0], -2, "dyn_core: flags must be 0 (no option bits are defined)");
+  if (flags & ~FV3_DYN_GRAPH) return fv3_fail(ctxs[0], -2, "dyn_core: unknown flag bit (defined: FV3_DYN_GRAPH = 1)");
+  int rc = (flags & FV3_DYN_GRAPH) ? dyn_core_graph(ctxs, nctx, bdt, n_split) : dyn_core_direct(ctxs, nctx, bdt, n_split);
+  if (!rc) for (int a = 0; a < nctx; a++) ctxs[a]->dyn_calls++;
+  return rc;
+}
+
+// ---- FV3_DYN_GRAPH: the whole call (n_split substeps of every face of this process, exchanges included) as ONE CUDA graph.
+// Captured once per (context list, bdt, n_split, precision mode, ping-pong state) with stream capture of the very same launch
+// sequence the direct path issues -- the face streams are forked from / joined into the first face's stream -- and replayed
+// afterwards with a single cudaGraphLaunch; results are bit-identical to the direct path (same kernels, same arguments, same
+// order per stream).  What the host must keep in step with a replay: the fld <-> alt ping-pong pointers (a graph is bound to the
+// pointer state it was captured in and leaves the state it recorded at the end of the capture) and the launch counter.
+// Falls back to the direct path (same results) when a capture would not be valid: first call of a context (it performs the lazy
+// allocations / one-time tables), remote faces (the peer-mapped exchange passes sequence numbers as kernel arguments, NCCL calls
+// are not captured here), stage timers on, overlapped exchange.
+struct DynGraph {
+  std::vector<fv3_ctx*> ctxs; double bdt; int n_split; int tp_fp32;
+  std::vector<double*> ptr_in, ptr_out;   // fld[] + alt_* of every context at the start / end of the captured call
+  long long launches;                     // per context: launches the captured call accounts for (same on every face)
+  std::vector<long long> launches_ctx;
+  cudaGraphExec_t exec;
+};
+struct DynGraphs { std::vector<DynGraph> g; };
+void fv3_free_graphs(fv3_ctx* c) {
+  if (!c->graphs) return;
+  for (auto& g : c->graphs->g) cudaGraphExecDestroy(g.exec);
+  delete c->graphs; c->graphs = nullptr;
+}
+static void ptr_state(fv3_ctx** ctxs, int nctx, std::vector<double*>& out) {
+  out.clear();
+  for (int a = 0; a < nctx; a++) {
+    fv3_ctx* c = ctxs[a];
+    for (int i = 0; i < FV3_NUM_FIELDS; i++) out.push_back(c->fld[i]);
+    for (double* p : {c->alt_delp, c->alt_pt, c->alt_w, c->alt_u, c->alt_v, c->alt_qcon}) out.push_back(p);
+  }
+}
+static void set_ptr_state(fv3_ctx** ctxs, int nctx, const std::vector<double*>& in) {
+  size_t n = 0;
+  for (int a = 0; a < nctx; a++) {
+    fv3_ctx* c = ctxs[a];
+    for (int i = 0; i < FV3_NUM_FIELDS; i++) c->fld[i] = in[n++];
+    c->alt_delp = in[n++]; c->alt_pt = in[n++]; c->alt_w = in[n++]; c->alt_u = in[n++]; c->alt_v = in[n++]; c->alt_qcon = in[n++];
+  }
+}
+static int dyn_core_graph(fv3_ctx** ctxs, int nctx, double bdt, int n_split) {
+  fv3_ctx* c0 = ctxs[0];
+  bool direct = std::getenv("FV3_HALO_OVERLAP") != nullptr;
+  for (int a = 0; a < nctx; a++) {
+    fv3_ctx* c = ctxs[a];
+    if (c->dyn_calls == 0 || c->timers_on || c->device != c0->device) direct = true;
+    if (fv3_halo_has_remote(c)) direct = true;
+  }
+  if (direct) return dyn_core_direct(ctxs, nctx, bdt, n_split);
+  if (!c0->graphs) c0->graphs = new DynGraphs;
+  std::vector<double*> now;
+  ptr_state(ctxs, nctx, now);
+  DynGraph* G = nullptr;
+  for (auto& g : c0->graphs->g)
+    if (g.bdt == bdt && g.n_split == n_split && g.tp_fp32 == c0->tp_fp32 && (int)g.ctxs.size() == nctx &&
+        std::equal(g.ctxs.begin(), g.ctxs.end(), ctxs) && g.ptr_in == now) { G = &g; break; }
+  cudaSetDevice(c0->device);
+  cudaEvent_t ev;
+  FV3_CUDA(c0, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  if (!G) {
+    DynGraph g;
+    g.ctxs.assign(ctxs, ctxs + nctx); g.bdt = bdt; g.n_split = n_split; g.tp_fp32 = c0->tp_fp32; g.ptr_in = now;
+    std::vector<long long> l0(nctx);
+    for (int a = 0; a < nctx; a++) { l0[a] = ctxs[a]->launches; ctxs[a]->capturing = true; }
+    // fork: the other faces' streams join the capture of the first face's stream
+    cudaError_t e = cudaStreamBeginCapture(c0->stream, cudaStreamCaptureModeRelaxed);
+    int rc = 0;
+    if (e == cudaSuccess) {
+      cudaEventRecord(ev, c0->stream);
+      for (int a = 1; a < nctx; a++) if (ctxs[a]->stream != c0->stream) cudaStreamWaitEvent(ctxs[a]->stream, ev, 0);
+      rc = dyn_core_direct(ctxs, nctx, bdt, n_split);
+      // join
+      for (int a = 1; a < nctx; a++) {
+        if (ctxs[a]->stream == c0->stream) continue;
+        cudaEvent_t ej; cudaEventCreateWithFlags(&ej, cudaEventDisableTiming);
+        cudaEventRecord(ej, ctxs[a]->stream); cudaStreamWaitEvent(c0->stream, ej, 0); cudaEventDestroy(ej);
+      }
+    }
+    cudaGraph_t graph = nullptr;
+    if (e == cudaSuccess) e = cudaStreamEndCapture(c0->stream, &graph);
+    for (int a = 0; a < nctx; a++) ctxs[a]->capturing = false;
+    if (e == cudaSuccess && !rc) e = cudaGraphInstantiate(&g.exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess || rc) {
+      cudaGetLastError();
+      set_ptr_state(ctxs, nctx, now);                       // nothing ran: undo the host-side bookkeeping of the failed capture
+      for (int a = 0; a < nctx; a++) ctxs[a]->launches = l0[a];
+      cudaEventDestroy(ev);
+      if (rc) return rc;
+      return fv3_fail(c0, (int)e, std::string("dyn_core: CUDA graph capture failed: ") + cudaGetErrorString(e));
+    }
+    ptr_state(ctxs, nctx, g.ptr_out);
+    g.launches_ctx.resize(nctx);
+    for (int a = 0; a < nctx; a++) { g.launches_ctx[a] = ctxs[a]->launches - l0[a]; ctxs[a]->launches = l0[a]; }
+    set_ptr_state(ctxs, nctx, now);                         // the capture executed nothing; the replay below does
+    if (c0->graphs->g.size() >= 8) { cudaGraphExecDestroy(c0->graphs->g.front().exec); c0->graphs->g.erase(c0->graphs->g.begin()); }
+    c0->graphs->g.push_back(std::move(g));
+    G = &c0->graphs->g.back();
+  }
+  // replay: after everything already queued on the faces' streams, and before anything queued on them later
+  for (int a = 1; a < nctx; a++) {
+    if (ctxs[a]->stream == c0->stream) continue;
+    cudaEvent_t ej; cudaEventCreateWithFlags(&ej, cudaEventDisableTiming);
+    cudaEventRecord(ej, ctxs[a]->stream); cudaStreamWaitEvent(c0->stream, ej, 0); cudaEventDestroy(ej);
+  }
+  FV3_CUDA(c0, cudaGraphLaunch(G->exec, c0->stream));
+  cudaEventRecord(ev, c0->stream);
+  for (int a = 1; a < nctx; a++) if (ctxs[a]->stream != c0->stream) cudaStreamWaitEvent(ctxs[a]->stream, ev, 0);
+  cudaEventDestroy(ev);
+  set_ptr_state(ctxs, nctx, G->ptr_out);
+  for (int a = 0; a < nctx; a++) ctxs[a]->launches += G->launches_ctx[a];
+  return 0;
+}
+
+static int dyn_core_direct(fv3_ctx** ctxs, int nctx, double bdt, int n_split) {
   for (int a = 0; a < nctx; a++) {
     // the loop below branches on the first context's switches: the linked faces must agree on them
     const fv3_flags_t &f0 = ctxs[0]->f, &fa = ctxs[a]->f;

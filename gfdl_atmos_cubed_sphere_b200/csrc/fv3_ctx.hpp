@@ -138,12 +138,18 @@ struct fv3_ctx {
   double* d_edge_tab;              // edge_profile coefficient tables (nh.cu), built on first use
   double* d_rff = nullptr; int k_rf = 0;   // Rayleigh damping table of the vertical solvers (fast_tau_w_sec > 0), built by the first solver call
   long long launches;
+  bool capturing = false;   // a CUDA-graph capture of fv3_dyn_core is in progress: stages skip their (unchanged) table uploads
+  long long dyn_calls = 0;  // completed fv3_dyn_core calls in which this context took part (the first one does every lazy allocation)
+  struct DynGraphs* graphs = nullptr;   // captured fv3_dyn_core graphs (dyn_core.cu), owned by the first context of the call
   int tp_fp32 = 0;   // fv3_set_transport_fp32: the interior-tile PPM sweeps of d_sw compute in fp32 (fp64 storage and updates)
   bool timers_on;
   std::map<std::string, StageTimer> timers;
   HaloPlan* halo;
   int tile;
 };
+
+bool fv3_halo_has_remote(const fv3_ctx* c);   // halo.cu
+void fv3_free_graphs(fv3_ctx* c);             // dyn_core.cu
 
 // error helpers
 int fv3_fail(fv3_ctx* c, int code, const std::string& msg);

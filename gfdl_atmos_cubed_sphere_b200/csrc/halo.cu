@@ -181,6 +181,16 @@ struct HaloPlan {
   bool xpending;
 };
 
+// a face of another rank takes part in this context's exchanges (dyn_core.cu: such calls are not graph-captured)
+bool fv3_halo_has_remote(const fv3_ctx* c) {
+  if (!c->halo) return false;
+  for (int t = 0; t < 6; t++) {
+    const int r = c->halo->tile_rank[t];
+    if (r >= 0 && r != c->halo->my_rank && !c->halo->peer[t]) return true;
+  }
+  return false;
+}
+
 static NcclApi g_nccl = {nullptr};
 static int p2p_setup(fv3_ctx** ctxs, int nctx, int nranks, int rank);
 static int nccl_load(fv3_ctx* c) {

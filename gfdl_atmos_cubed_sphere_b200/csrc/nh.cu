@@ -722,8 +722,10 @@ int stage_update_dz_d(fv3_ctx* c, double dt) {
   std::vector<int> ki(n1); std::vector<double> kd(n1);
   bool any = false;
   for (int k = 0; k < n1; k++) { ki[k] = c->nord_v[k]; kd[k] = c->damp_vt[k] > 1.E-5 ? c->damp_vt[k] : 0.; any |= kd[k] != 0.; }
-  FV3_CUDA(c, cudaMemcpyAsync(c->d_kint + KI_NORD_V * n1, ki.data(), n1 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  FV3_CUDA(c, cudaMemcpyAsync(c->d_kdbl + KD_DZ * n1, kd.data(), n1 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (!c->capturing) {   // (see stage_d_sw)
+    FV3_CUDA(c, cudaMemcpyAsync(c->d_kint + KI_NORD_V * n1, ki.data(), n1 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    FV3_CUDA(c, cudaMemcpyAsync(c->d_kdbl + KD_DZ * n1, kd.data(), n1 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
   double *crxa = c->scr[0], *xfxa = c->scr[1], *crya = c->scr[2], *yfxa = c->scr[3];
   double *fx = c->scr[5], *fy = c->scr[6];
   double *zn = c->scr[11], *dfx = c->scr[12], *dfy = c->scr[13], *d2 = c->scr[14];

@@ -116,6 +116,74 @@ def set_eta_var_hi(km, ptop=1.0, pint=100.0e2, s_rate=1.03, rdgas=287.05, grav=9
     return ak[1:].copy(), bk[1:].copy(), ks
 
 
+def set_eta_var_gfs(km, ptop=1.0, pint=75.0e2, s_rate=1.028, rdgas=287.05, grav=9.80665):
+    """ak, bk, ks of the reference's generator var_gfs (tools/fv_eta.F90:1002-1164, UKMO-hybrid branch) as set_eta selects it for
+    km = 127, default npz_type (BASELINE config 5: ptop = 1 Pa, pint = 75 hPa, stretch_fac = 1.028; fv_eta.F90:726-744).
+    Differs from var_hi in the tunables (k_inc = 25, s0 = 0.13), the top-layer factors, and in having no sm1_edge pass."""
+    assert km >= 36, "var_gfs needs km - k_inc - 1 >= 9"
+    p00, k_inc, s0, t0 = 1.0e5, 25, 0.13, 270.0
+    pe1 = np.zeros(km + 2); peln = np.zeros(km + 2); ze = np.zeros(km + 2)      # 1-based
+    s_fac = np.zeros(km + 1); dz = np.zeros(km + 1); dlnp = np.zeros(km + 1)
+    pe1[1] = ptop; peln[1] = np.log(pe1[1]); pe1[km + 1] = p00; peln[km + 1] = np.log(pe1[km + 1])
+    ztop = rdgas / grav * t0 * (peln[km + 1] - peln[1])
+    s_inc = (1.0 - s0) / float(k_inc)
+    s_fac[km] = s0
+    for k in range(km - 1, km - k_inc - 1, -1):
+        s_fac[k] = s_fac[k + 1] + s_inc
+    for k in range(km - k_inc - 1, 8, -1):
+        s_fac[k] = s_rate * s_fac[k + 1]
+    s_fac[8] = 0.5 * (1.1 + s_rate) * s_fac[9]
+    s_fac[7] = 1.10 * s_fac[8]; s_fac[6] = 1.15 * s_fac[7]; s_fac[5] = 1.20 * s_fac[6]; s_fac[4] = 1.26 * s_fac[5]
+    s_fac[3] = 1.33 * s_fac[4]; s_fac[2] = 1.41 * s_fac[3]; s_fac[1] = 1.60 * s_fac[2]
+    sum1 = 0.0
+    for k in range(1, km + 1):
+        sum1 = sum1 + s_fac[k]
+    dz0 = ztop / sum1
+    for k in range(1, km + 1):
+        dz[k] = s_fac[k] * dz0
+    ze[km + 1] = 0.0
+    for k in range(km, 0, -1):
+        ze[k] = ze[k + 1] + dz[k]
+    for k in range(1, km + 1):                     # re-scale dz with the stretched ztop
+        dz[k] = dz[k] * (ztop / ze[1])
+    for k in range(km, 0, -1):
+        ze[k] = ze[k + 1] + dz[k]
+    for k in range(1, km + 1):                     # given z --> p
+        dz[k] = ze[k] - ze[k + 1]
+        dlnp[k] = grav * dz[k] / (rdgas * t0)
+    for k in range(2, km + 1):
+        peln[k] = peln[k - 1] + dlnp[k - 1]
+        pe1[k] = np.exp(peln[k])
+    ks = 0
+    for k in range(2, km + 1):
+        if pint < pe1[k]:
+            ks = k - 1
+            break
+    return _ukmo_hybrid(km, pe1, ks)
+
+
+def _ukmo_hybrid(km, pe1, ks):
+    """pe1 -> (ak, bk): pure pressure down to interface ks + 1, UKMO hybrid below (fv_eta.F90:1121-1149 = :1301-1329)"""
+    eta = np.zeros(km + 2)
+    for k in range(1, km + 2):
+        eta[k] = pe1[k] / pe1[km + 1]
+    ep, es = eta[ks + 1], eta[km]
+    alpha = (ep ** 2 - 2.0 * ep * es) / (es - ep) ** 2
+    beta = 2.0 * ep * es ** 2 / (es - ep) ** 2
+    gama = -(ep * es) ** 2 / (es - ep) ** 2
+    ak = np.zeros(km + 2); bk = np.zeros(km + 2)
+    for k in range(1, ks + 2):
+        ak[k] = eta[k] * 1.0e5; bk[k] = 0.0
+    for k in range(ks + 2, km + 1):
+        ak[k] = alpha * eta[k] + beta + gama / eta[k]
+        ak[k] = ak[k] * 1.0e5
+    ak[km + 1] = 0.0
+    for k in range(ks + 2, km + 1):
+        bk[k] = (pe1[k] - ak[k]) / pe1[km + 1]
+    bk[km + 1] = 1.0
+    return ak[1:].copy(), bk[1:].copy(), ks
+
+
 # set_eta, km = 32, default npz_type (fv_eta.F90:410-428: ks = 7, ak = a32, bk = b32); table values from tools/fv_eta.h:114-136
 _A32 = (100.00000, 400.00000, 818.60211, 1378.88653, 2091.79519, 2983.64084, 4121.78960, 5579.22148, 6907.19063, 7735.78639,
         8197.66476, 8377.95525, 8331.69594, 8094.72213, 7690.85756, 7139.01788, 6464.80251, 5712.35727, 4940.05347, 4198.60465,
@@ -127,10 +195,13 @@ _B32 = (0.00000, 0.00000, 0.00000, 0.00000, 0.00000, 0.00000, 0.00000, 0.00000, 
 
 
 def model_levels(npz):
-    """Hybrid levels for a run: the reference's own set_eta result where it is restated -- npz = 79 (var_hi generator) and
+    """Hybrid levels for a run: the reference's own set_eta result where it is restated -- npz = 79 (var_hi generator), npz = 127 (var_gfs generator: BASELINE config 5) and
     npz = 32 (the a32/b32 table: BASELINE config 1b, C48 L32) -- else the generic hybrid_levels."""
     if npz == 79:
         ak, bk, _ = set_eta_var_hi(79)
+        return ak, bk
+    if npz == 127:
+        ak, bk, _ = set_eta_var_gfs(127)
         return ak, bk
     if npz == 32:
         return np.array(_A32, dtype=np.float64), np.array(_B32, dtype=np.float64)

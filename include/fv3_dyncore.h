@@ -283,9 +283,13 @@ int fv3_plane_index(const fv3_ctx *ctx, int i, int j);
 /* dyn_core.F90:313-1286: n_split substeps on device-resident state for the
  * linked contexts of this process (nctx faces), halo exchanges included.
  * bdt is the large (k_split) time step; dt = bdt/n_split (dyn_core.F90:223).
- * flags: must be 0 (no option bits are defined; the call fails with -2 otherwise).
+ * flags: 0, or FV3_DYN_GRAPH: the call is captured once into a CUDA graph (one per context list, bdt, n_split, precision mode
+ * and ping-pong state of the fields) and replayed with a single cudaGraphLaunch afterwards; bit-identical to flags = 0.  Calls
+ * that cannot be captured validly run directly with the same result: the first call of a context (one-time allocations), faces
+ * on other ranks (peer-mapped / NCCL exchange), stage timers on.  Any other bit: -2.
  * Hydrostatic branch: on the last substep pk = pkc on the compute domain (dyn_core.F90:1001-1010), so the
  * pk a caller downloads for the remapping is current. */
+#define FV3_DYN_GRAPH 1
 int fv3_dyn_core(fv3_ctx **ctxs, int nctx, double bdt, int n_split, int flags);
 
 /* fv_tracer2d.F90:49-295 tracer_2d_1L for ONE tracer (nq = 1, trdm = 0, id_divg_mean = 0), all faces of this process in

@@ -356,6 +356,26 @@ def test_dyn_core_baseline_config_sizes(n):
     oc.close(); gc.close()
 
 
+def test_dyn_core_l127_levels():
+    """BASELINE.json configs[4] vertical grid: the 127 hybrid levels of set_eta's default branch (var_gfs, ptop = 1 Pa, ks = 48:
+    init_state.set_eta_var_gfs) -- twice the layers of the other cases and much thinner ones at the top and bottom, which is what
+    the column solvers and the k-chunked transport kernels (8 levels per CTA: 127 = 15 x 8 + 7) see differently.  C48, fp64.
+    Tolerance 1e-9 (w: 1e-8), ten times the L79 one: the top layers are ~0.5 Pa thin under ptop = 1 Pa, so the pressure
+    differences the solvers and the pressure gradient form there cancel one more digit (measured: w 3.0e-9, v 1.5e-10, rest < 1e-13)."""
+    n, npz = 48, 127
+    case = H.Case(n, npz, "A", state="baroclinic")
+    oc = H.OracleCube(case, fast=True)
+    gc = H.CudaCube(case)
+    bdt = 2 * (225.0 / 8) * 384 / n * 0.5
+    oc.dyn_core(bdt, 2)
+    gc.dyn_core(bdt, 2)
+    for t in oc.tiles:
+        res = H.compare(oc.eng[t], gc.eng[t], H.regions_state(case.bounds))
+        _assert({k: v for k, v in res.items() if k != "W"}, 1e-9)
+        _assert({"W": res["W"]}, 1e-8)
+    oc.close(); gc.close()
+
+
 def test_dyn_core_moist_flags():
     """the second flag-set-A run with the non-hydrostatic defaults use_cond = T, moist_kappa = T
     (fv_arrays.F90:1226-1227): condensate-free pressure in the Riemann solvers (nh_utils.F90:412-447, nh_core.F90:120-165),

@@ -114,3 +114,22 @@ def test_set_eta_l79_levels():
     assert abs(p[ks] - 100.0e2) / 100.0e2 < 0.15                                  # pint is snapped to an interface near 100 hPa
     dz = 287.05 / 9.80665 * 270.0 * np.diff(np.log(p))                            # isothermal thickness used by var_hi
     assert 15.0 < dz[-1] < 60.0 and dz[-1] < dz[-2] < dz[-3]                       # thin, stretching layers at the surface
+
+
+def test_set_eta_l127_levels():
+    """tools/fv_eta.F90 set_eta for km = 127, default npz_type (var_gfs, ptop = 1 Pa, stretch 1.028, pint = 75 hPa): structural
+    properties of the restated generator (the levels are computed at run time; the reference holds no table for this branch)."""
+    from gfdl_atmos_cubed_sphere_b200 import init_state as I
+    ak, bk, ks = I.set_eta_var_gfs(127)
+    assert ak.shape == (128,) and bk.shape == (128,)
+    assert ak[0] == 1.0 and bk[0] == 0.0 and ak[-1] == 0.0 and bk[-1] == 1.0
+    assert np.all(bk[:ks + 1] == 0.0) and np.all(np.diff(bk[ks:]) > 0.0)
+    for ps in (1.0e5, 7.0e4, 5.0e4):
+        assert np.all(np.diff(ak + bk * ps) > 0.0)
+    p = ak + bk * 1.0e5
+    assert abs(p[ks] - 75.0e2) / 75.0e2 < 0.15
+    dz = 287.05 / 9.80665 * 270.0 * np.diff(np.log(p))
+    assert 10.0 < dz[-1] < 40.0 and dz[-1] < dz[-2] < dz[-3]
+    assert np.allclose(dz[-26:-1] - dz[-25:], dz[-26] - dz[-25], rtol=1e-3)          # k_inc = 25 layers of linearly growing thickness
+    a2, b2 = I.model_levels(127)
+    assert np.array_equal(a2, ak) and np.array_equal(b2, bk)
