@@ -327,41 +327,53 @@ void halo_destroy(fv3_ctx* c) {
   c->halo = nullptr;
 }
 
-// dst[k][d[e]] = sign[e] * src[k][s[e]]
-__global__ void k_halo_gather(double* __restrict__ dst, const double* __restrict__ src, const int* __restrict__ d, const int* __restrict__ s,
-                              const int* __restrict__ sg, int n, long long plane) {
+// dst[k][d[e]] = sign[e] * src[k][s[e]] for a batch of (destination field, source field, table) jobs in ONE launch: the faces of a
+// process exchange with ~50 small gathers per face and substep, each a few microseconds of work behind a launch -- batched, an
+// exchange of all six faces is 1-2 launches (blockIdx.z = job; jobs shorter than the grid's extent leave their surplus blocks at once).
+struct GatherJob { double* dst; const double* src; const int *d, *s, *sg; int n, nk; };
+constexpr int GATHER_BATCH = 64;   // 64 x 48 B of kernel parameters
+struct GatherJobs { GatherJob j[GATHER_BATCH]; };
+__global__ void k_halo_gather_batch(GatherJobs jobs, long long plane) {
+  const GatherJob& J = jobs.j[blockIdx.z];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
+  if (e >= J.n || (int)blockIdx.y >= J.nk) return;
   const long long ko = (long long)blockIdx.y * plane;
-  dst[ko + d[e]] = (double)sg[e] * __ldg(src + ko + s[e]);
+  J.dst[ko + J.d[e]] = (double)J.sg[e] * __ldg(J.src + ko + J.s[e]);
 }
-// buf[k][e] = src[k][s[e]]   (pack, sign applied by the receiver)
-__global__ void k_halo_pack(double* __restrict__ buf, const double* __restrict__ src, const int* __restrict__ s, int n, long long plane) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  buf[(long long)blockIdx.y * n + e] = __ldg(src + (long long)blockIdx.y * plane + s[e]);
-}
-__global__ void k_halo_unpack(double* __restrict__ dst, const double* __restrict__ buf, const int* __restrict__ d, const int* __restrict__ sg,
-                              int n, long long plane) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  dst[(long long)blockIdx.y * plane + d[e]] = (double)sg[e] * buf[(long long)blockIdx.y * n + e];
-}
-
 // publish / await the sequence number of a peer-mapped message (one thread each).  The wait gives up after ~2e9 polls (a protocol
 // error must not hang the GPU): it raises *err and lets the stream continue.
-__global__ void k_p2p_signal(volatile unsigned long long* flag, unsigned long long seq) {
+// one thread per message of the exchange (<= P2P_MAXMSG per launch)
+constexpr int P2P_MAXMSG = 32;
+struct FlagSet { volatile unsigned long long* f[P2P_MAXMSG]; };
+__global__ void k_p2p_signal(FlagSet flags, unsigned long long seq) {
   __threadfence_system();
-  *flag = seq;
+  *flags.f[threadIdx.x] = seq;
   __threadfence_system();
 }
-__global__ void k_p2p_wait(const volatile unsigned long long* flag, unsigned long long seq, int* err) {
+__global__ void k_p2p_wait(FlagSet flags, unsigned long long seq, int* err) {
   unsigned long long n = 0;
-  while (*flag < seq) {
+  while (*flags.f[threadIdx.x] < seq) {
     if (++n > 2000000000ull) { atomicExch(err, 1); break; }
     __nanosleep(64);
   }
   __threadfence_system();
+}
+// batched pack / unpack: all tables of all messages of an exchange in one launch each (blockIdx.z = job), see k_halo_gather_batch
+struct PackJob { double* buf; const double* src; const int* s; int n, nk; };
+struct UnpackJob { double* dst; const double* buf; const int *d, *sg; int n, nk; };
+struct PackJobs { PackJob j[GATHER_BATCH]; };
+struct UnpackJobs { UnpackJob j[GATHER_BATCH]; };
+__global__ void k_halo_pack_batch(PackJobs jobs, long long plane) {
+  const PackJob& J = jobs.j[blockIdx.z];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= J.n || (int)blockIdx.y >= J.nk) return;
+  J.buf[(long long)blockIdx.y * J.n + e] = __ldg(J.src + (long long)blockIdx.y * plane + J.s[e]);
+}
+__global__ void k_halo_unpack_batch(UnpackJobs jobs, long long plane) {
+  const UnpackJob& J = jobs.j[blockIdx.z];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= J.n || (int)blockIdx.y >= J.nk) return;
+  J.dst[(long long)blockIdx.y * plane + J.d[e]] = (double)J.sg[e] * J.buf[(long long)blockIdx.y * J.n + e];
 }
 
 extern "C" {
@@ -611,8 +623,17 @@ static int halo_exchange_impl(fv3_ctx** ctxs, int nctx, int group, int overlappe
   const unsigned long long seq = p2p ? ++A->seq[group] : 0;
   const int par = (int)(seq & 1);
   if (any_remote) {
+    PackJobs pj; int npj = 0, pn = 0, pk = 0;
+    FlagSet sig; int nsig = 0;
+    auto flush_pack = [&]() {
+      if (!npj) return;
+      k_halo_pack_batch<<<dim3((pn + 127) / 128, pk, npj), 128, 0, st>>>(pj, c0->L.plane);
+      c0->launches++;
+      npj = 0; pn = 0; pk = 0;
+    };
     for (int a = 0; a < nctx; a++) {
       fv3_ctx* c = ctxs[a]; HaloPlan* hp = c->halo; GroupPlan& gp = hp->grp[group];
+      if (c->L.plane != c0->L.plane) return fv3_fail(c, -1, "halo_exchange: the faces of a process must share one plane layout");
       for (int t = 1; t <= 6; t++) {
         const int r = hp->tile_rank[t - 1];
         if (r < 0 || r == my_rank || hp->peer[t - 1]) continue;
@@ -642,7 +663,7 @@ static int halo_exchange_impl(fv3_ctx** ctxs, int nctx, int group, int overlappe
           FV3_CUDA(c, cudaMalloc(&hp->recvbuf[t - 1], cap * sizeof(double)));
           hp->bufcap[t - 1] = cap;
         }
-        // pack
+        // pack: every table of the message is a job of the exchange's one batched launch
         size_t off = 0;
         for (size_t si = 0; si < gp.specs.size(); si++) {
           const FieldSpec& fs = gp.specs[si];
@@ -651,20 +672,21 @@ static int halo_exchange_impl(fv3_ctx** ctxs, int nctx, int group, int overlappe
             for (int sc = 0; sc < ncomp; sc++) {
               const DevTable& tb = gp.send[si][t - 1][ci][sc];
               if (!tb.n) continue;
-              const double* src = c->fld[sc == 0 ? fs.fx : fs.fy];
-              dim3 g((tb.n + 127) / 128, fs.nk);
-              k_halo_pack<<<g, 128, 0, st>>>((p2p ? pack_dst : hp->sendbuf[t - 1]) + off, src, tb.src, tb.n, c->L.plane);
-              c->launches++;
+              pj.j[npj++] = PackJob{(p2p ? pack_dst : hp->sendbuf[t - 1]) + off, c->fld[sc == 0 ? fs.fx : fs.fy], tb.src, tb.n, fs.nk};
+              pn = std::max(pn, tb.n); pk = std::max(pk, fs.nk);
+              if (npj == GATHER_BATCH) flush_pack();
               off += (size_t)tb.n * fs.nk;
             }
         }
-        if (p2p && ns) {   // the message is complete in the receiver's memory: publish its sequence number there
-          k_p2p_signal<<<1, 1, 0, st>>>((volatile unsigned long long*)(A->peer[r] + A->F(r, t - 1, c->tile - 1, group)), seq);
-          c->launches++;
+        if (p2p && ns) {   // once the message is complete in the receiver's memory its sequence number is published there
+          if (nsig == P2P_MAXMSG) return fv3_fail(c, -1, "halo_exchange: more than 32 messages in one exchange");
+          sig.f[nsig++] = (volatile unsigned long long*)(A->peer[r] + A->F(r, t - 1, c->tile - 1, group));
         }
         msgs.push_back({c, t, r, ns, nr});
       }
     }
+    flush_pack();
+    if (nsig) { k_p2p_signal<<<1, nsig, 0, st>>>(sig, seq); c0->launches++; }
     // canonical issue order per peer: (face on the lower rank, face on the higher rank), so the
     // i-th send of rank A to rank B meets the i-th receive B posts for A
     std::sort(msgs.begin(), msgs.end(), [&](const Msg& x, const Msg& y) {
@@ -690,54 +712,83 @@ static int halo_exchange_impl(fv3_ctx** ctxs, int nctx, int group, int overlappe
   }
   // ---- local gathers.  Two-phase so that no face reads a halo another gather is writing:
   // sources are compute-domain points, destinations halo points -> disjoint, one phase suffices.
-  for (int a = 0; a < nctx; a++) {
-    fv3_ctx* c = ctxs[a]; HaloPlan* hp = c->halo; GroupPlan& gp = hp->grp[group];
-    for (size_t si = 0; si < gp.specs.size(); si++) {
-      const FieldSpec& fs = gp.specs[si];
-      const int ncomp = fs.fy >= 0 ? 2 : 1;
-      for (int ci = 0; ci < ncomp; ci++) {
-        double* dst = c->fld[ci == 0 ? fs.fx : fs.fy];
-        for (int t = 1; t <= 6; t++) {
-          fv3_ctx* p = hp->peer[t - 1];
-          if (!p) continue;
-          for (int sc = 0; sc < ncomp; sc++) {
-            const DevTable& tb = gp.tab[si][ci][t - 1][sc];
-            if (!tb.n) continue;
-            const double* src = p->fld[sc == 0 ? fs.fx : fs.fy];
-            dim3 g((tb.n + 127) / 128, fs.nk);
-            k_halo_gather<<<g, 128, 0, st>>>(dst, src, tb.dst, tb.src, tb.sign, tb.n, c->L.plane);
-            c->launches++;
+  {
+    GatherJobs jobs; int nj = 0, nmax = 0, kmax = 0;
+    auto flush = [&]() {
+      if (!nj) return;
+      k_halo_gather_batch<<<dim3((nmax + 127) / 128, kmax, nj), 128, 0, st>>>(jobs, c0->L.plane);
+      c0->launches++;
+      nj = 0; nmax = 0; kmax = 0;
+    };
+    for (int a = 0; a < nctx; a++) {
+      fv3_ctx* c = ctxs[a]; HaloPlan* hp = c->halo; GroupPlan& gp = hp->grp[group];
+      if (c->L.plane != c0->L.plane) return fv3_fail(c, -1, "halo_exchange: the faces of a process must share one plane layout");
+      for (size_t si = 0; si < gp.specs.size(); si++) {
+        const FieldSpec& fs = gp.specs[si];
+        const int ncomp = fs.fy >= 0 ? 2 : 1;
+        for (int ci = 0; ci < ncomp; ci++) {
+          double* dst = c->fld[ci == 0 ? fs.fx : fs.fy];
+          for (int t = 1; t <= 6; t++) {
+            fv3_ctx* p = hp->peer[t - 1];
+            if (!p) continue;
+            for (int sc = 0; sc < ncomp; sc++) {
+              const DevTable& tb = gp.tab[si][ci][t - 1][sc];
+              if (!tb.n) continue;
+              jobs.j[nj++] = GatherJob{dst, p->fld[sc == 0 ? fs.fx : fs.fy], tb.dst, tb.src, tb.sign, tb.n, fs.nk};
+              nmax = std::max(nmax, tb.n); kmax = std::max(kmax, fs.nk);
+              if (nj == GATHER_BATCH) flush();
+            }
           }
         }
       }
     }
+    flush();
   }
-  // ---- unpack remote
-  for (const Msg& m : msgs) {
-    fv3_ctx* c = m.c; HaloPlan* hp = c->halo; GroupPlan& gp = hp->grp[group];
-    size_t off = 0;
-    const double* rbuf = hp->recvbuf[m.tile - 1];
-    if (p2p) {
-      if (!m.nrecv) continue;
-      const long long bo = A->B(A->my_rank, c->tile - 1, m.tile - 1, group, par), fo = A->F(A->my_rank, c->tile - 1, m.tile - 1, group);
-      if (bo < 0 || fo < 0) return fv3_fail(c, -1, "halo_exchange: no arena buffer for an expected message");
-      rbuf = (const double*)(A->base + bo);
-      k_p2p_wait<<<1, 1, 0, st>>>((const volatile unsigned long long*)(A->base + fo), seq, A->d_err);   // holds the stream until the sender's flag arrives
-      c->launches++;
+  // ---- unpack remote: await every message of the exchange (one thread per message), then one batched unpack
+  {
+    UnpackJobs uj; int nuj = 0, un = 0, uk = 0;
+    FlagSet wt; int nwt = 0;
+    std::vector<const double*> rbufs(msgs.size(), nullptr);
+    for (size_t mi = 0; mi < msgs.size(); mi++) {
+      const Msg& m = msgs[mi];
+      fv3_ctx* c = m.c; HaloPlan* hp = c->halo;
+      rbufs[mi] = hp->recvbuf[m.tile - 1];
+      if (p2p) {
+        if (!m.nrecv) continue;
+        const long long bo = A->B(A->my_rank, c->tile - 1, m.tile - 1, group, par), fo = A->F(A->my_rank, c->tile - 1, m.tile - 1, group);
+        if (bo < 0 || fo < 0) return fv3_fail(c, -1, "halo_exchange: no arena buffer for an expected message");
+        rbufs[mi] = (const double*)(A->base + bo);
+        if (nwt == P2P_MAXMSG) return fv3_fail(c, -1, "halo_exchange: more than 32 messages in one exchange");
+        wt.f[nwt++] = (volatile unsigned long long*)(A->base + fo);
+      }
     }
-    for (size_t si = 0; si < gp.specs.size(); si++) {
-      const FieldSpec& fs = gp.specs[si];
-      const int ncomp = fs.fy >= 0 ? 2 : 1;
-      for (int ci = 0; ci < ncomp; ci++)
-        for (int sc = 0; sc < ncomp; sc++) {
-          const DevTable& tb = gp.tab[si][ci][m.tile - 1][sc];
-          if (!tb.n) continue;
-          dim3 g((tb.n + 127) / 128, fs.nk);
-          k_halo_unpack<<<g, 128, 0, st>>>(c->fld[ci == 0 ? fs.fx : fs.fy], rbuf + off, tb.dst, tb.sign, tb.n, c->L.plane);
-          c->launches++;
-          off += (size_t)tb.n * fs.nk;
-        }
+    if (nwt) { k_p2p_wait<<<1, nwt, 0, st>>>(wt, seq, A->d_err); c0->launches++; }   // holds the stream until the senders' flags arrive
+    auto flush_unpack = [&]() {
+      if (!nuj) return;
+      k_halo_unpack_batch<<<dim3((un + 127) / 128, uk, nuj), 128, 0, st>>>(uj, c0->L.plane);
+      c0->launches++;
+      nuj = 0; un = 0; uk = 0;
+    };
+    for (size_t mi = 0; mi < msgs.size(); mi++) {
+      const Msg& m = msgs[mi];
+      if (p2p && !m.nrecv) continue;
+      fv3_ctx* c = m.c; GroupPlan& gp = c->halo->grp[group];
+      size_t off = 0;
+      for (size_t si = 0; si < gp.specs.size(); si++) {
+        const FieldSpec& fs = gp.specs[si];
+        const int ncomp = fs.fy >= 0 ? 2 : 1;
+        for (int ci = 0; ci < ncomp; ci++)
+          for (int sc = 0; sc < ncomp; sc++) {
+            const DevTable& tb = gp.tab[si][ci][m.tile - 1][sc];
+            if (!tb.n) continue;
+            uj.j[nuj++] = UnpackJob{c->fld[ci == 0 ? fs.fx : fs.fy], rbufs[mi] + off, tb.dst, tb.sign, tb.n, fs.nk};
+            un = std::max(un, tb.n); uk = std::max(uk, fs.nk);
+            if (nuj == GATHER_BATCH) flush_unpack();
+            off += (size_t)tb.n * fs.nk;
+          }
+      }
     }
+    flush_unpack();
   }
   if (overlapped) {
     cudaEventRecord(hp0->xdone, st);

@@ -130,7 +130,7 @@ class OracleCube:
     _table_ids = {}
 
     def _table(self, pos_x, pos_y=None, kind="scalar", boundary_only=False):
-        key = (self.case.n, pos_x, pos_y, kind, boundary_only)
+        key = (self.lib[0]._name, self.case.n, pos_x, pos_y, kind, boundary_only)   # the parity and the timing build keep separate registries
         ids = OracleCube._table_ids
         if key not in ids:
             tabs = self.ex.tables(pos_x, pos_y, kind, boundary_only=boundary_only)

@@ -147,9 +147,9 @@ def test_upload_state_dyn_core_download_state():
     fn = lib[0].fv3_dyn_core
     fn.restype = C.c_int
     assert fn(ctxs, 6, C.c_double(600.0), C.c_int(2), C.c_int(0)) == 0, eng[1].last_error()
-    assert fn(ctxs, 6, C.c_double(600.0), C.c_int(2), C.c_int(1)) == -2          # no option bits are defined
+    assert fn(ctxs, 6, C.c_double(600.0), C.c_int(2), C.c_int(2)) == -2          # only bit 0 (FV3_DYN_GRAPH) is defined
     oc.dyn_core(600.0, 2)
-    assert fn(ctxs, 6, C.c_double(600.0), C.c_int(2), C.c_int(0)) == 0
+    assert fn(ctxs, 6, C.c_double(600.0), C.c_int(2), C.c_int(1)) == 0           # second call as a CUDA graph (tests/test_cuda_graph_gpu.py)
     oc.dyn_core(600.0, 2)
     b = case.bounds
     reg = H.regions_state(b)
