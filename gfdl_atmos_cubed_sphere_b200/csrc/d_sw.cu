@@ -775,18 +775,27 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_dsw_vort_uv(Lay L, DevGrid G, tp
   }
 }
 
-// ---- interior tiles, line-per-warp form (tp_line.cuh): delp, [w,] pt transported phase-major by a CTA that is persistent over
-// a chunk of levels.  Same arithmetic as k_dsw_transport (the mass fluxes of delp weight the other fields' fluxes in the outer
-// sweep, the flux divergences are applied in the epilogue); launched when no del-n flux and no q_con is in play.
+// ---- line-per-warp form (tp_line.cuh): delp, [w,] pt transported phase-major by a CTA that is persistent over a chunk of levels.
+// Same arithmetic as k_dsw_transport (the mass fluxes of delp weight the other fields' fluxes in the outer sweep, the flux
+// divergences are applied in the epilogue); launched when no del-n flux and no q_con is in play.
+// NF = 4: the absolute vorticity rides along as a fourth field (area-flux weighted, sw_core.F90:1476-1509) and the epilogue also
+// does the momentum update of k_dsw_vort_uv2 -- all scalar transports of d_sw share the Courant numbers and area fluxes, so the
+// one-field kernel's staging (5 of its 6 input arrays), barriers and per-level bookkeeping are saved.
+struct DswVU { const double *vq, *u, *v, *ke; double *uo, *vo; };
 template <int FAM, int NF, int HORD, bool EDGE, typename R = double>
-__global__ void __launch_bounds__(tp2::NT, 1) k_dsw_transport2(Lay L, DevGrid G, tpt::TileMap M, DswTr a, int nk, int kch) {
-  static_assert(NF == 2 || NF == 3, "fields: delp, [w,] pt");
+__global__ void __launch_bounds__(tp2::NT, 1) k_dsw_transport2(Lay L, DevGrid G, tpt::TileMap M, DswTr a, DswVU vu, int nk, int kch) {
+  static_assert(NF >= 2 && NF <= 4, "fields: delp, [w,] pt [, vorticity]");
+  constexpr int NS = NF == 4 ? 3 : NF;                       // mass-weighted scalars
+  constexpr int NEP = (NF == 4 && EDGE) ? 0 : 2;             // four fields + the cube-edge tables leave no room for the prefetch arrays
+  constexpr int WM = NF == 4 ? tp2::W_MASS_V : tp2::W_MASS;
   const double* src[4 + NF];
   src[0] = a.crx; src[1] = a.cry; src[2] = a.xfx; src[3] = a.yfx; src[4] = a.delp;
-  if (NF == 3) src[5] = a.w;
-  src[3 + NF] = a.pt;
+  if (NS == 3) src[5] = a.w;
+  src[3 + NS] = a.pt;
+  if (NF == 4) src[7] = vu.vq;
   int ord_in[NF], ord_ou[NF];
-  ord_ou[0] = a.hord_dp; if (NF == 3) ord_ou[1] = a.hord_vt; ord_ou[NF - 1] = a.hord_tm;
+  ord_ou[0] = a.hord_dp; if (NS == 3) ord_ou[1] = a.hord_vt; ord_ou[NS - 1] = a.hord_tm;
+  if (NF == 4) ord_ou[3] = a.hord_vt;
 #pragma unroll
   for (int f = 0; f < NF; f++) ord_in[f] = (ord_ou[f] == 10) ? 8 : ord_ou[f];   // tp_core.F90:136-141
   const int n1 = L.npz + 1;
@@ -799,36 +808,44 @@ __global__ void __launch_bounds__(tp2::NT, 1) k_dsw_transport2(Lay L, DevGrid G,
     if (T.wid < tp2::TY && (!EDGE || (i <= L.ied && j <= L.jed))) ra = __ldg(G.rarea + tp2::gidx(T, i, j));
     lastx = T.i0 + tp2::TX > L.ie; lasty = T.j0 + tp2::TY > L.je;
   }
-  tp2::run_tile<FAM, NF, 2, tp2::W_MASS, HORD, 32, EDGE, R>(L, G, M, src, nk, kch, ord_in, ord_ou,
-    [&](tp2::Smem<NF, 2, EDGE, R>& S, const tp2::Geo& T, int k, long long ko, int r) {   // the flux capacitors' old values (read-modify-write, :928-940)
-      const int c = T.lane, i = T.i0 - 3 + c, j = T.j0 - 3 + r;
-      if (c < 3 || c > tp2::TX + 3 || (EDGE && (i > L.ie + 1 || j > L.je + 1))) return;
-      const long long g = ko + tp2::gidx(T, i, j);
-      tpt::cp_async8(&S.ep[0][r * tp2::P + c], a.mfx + g);
-      tpt::cp_async8(&S.ep[1][r * tp2::P + c], a.mfy + g);
+  tp2::run_tile<FAM, NF, NEP, WM, HORD, 32, EDGE, R>(L, G, M, src, nk, kch, ord_in, ord_ou,
+    [&](tp2::Smem<NF, NEP, EDGE, R>& S, const tp2::Geo& T, int k, long long ko, int r) {   // the flux capacitors' old values (read-modify-write, :928-940)
+      if constexpr (NEP == 2) {
+        const int c = T.lane, i = T.i0 - 3 + c, j = T.j0 - 3 + r;
+        if (c < 3 || c > tp2::TX + 3 || (EDGE && (i > L.ie + 1 || j > L.je + 1))) return;
+        const long long g = ko + tp2::gidx(T, i, j);
+        tpt::cp_async8(&S.ep[0][r * tp2::P + c], a.mfx + g);
+        tpt::cp_async8(&S.ep[1][r * tp2::P + c], a.mfy + g);
+      }
     },
-    [&](tp2::Smem<NF, 2, EDGE, R>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
+    [&](tp2::Smem<NF, NEP, EDGE, R>& S, int b, const tp2::Geo& T, int k, long long ko, int r) {
       const int c = T.lane, i = T.i0 - 3 + c, j = T.j0 - 3 + r;
       if (c < 3 || c > tp2::TX + 3 || (EDGE && (i > L.ie + 1 || j > L.je + 1))) return;
       const int o = r * tp2::P + c;
-      const long long g = ko + tp2::gidx(T, i, j);
+      const int gi = tp2::gidx(T, i, j);
+      const long long g = ko + gi;
       const double mx0 = (double)S.qi[0][o], my0 = (double)S.qj[0][o];
       // flux capacitors: the tile's own west / south faces, plus the face's last column / row of faces
       const bool xface = r <= tp2::TY + 2 && (!EDGE || j <= L.je) && (c <= tp2::TX + 2 || (EDGE && lastx));
       const bool yface = c <= tp2::TX + 2 && (!EDGE || i <= L.ie) && (r <= tp2::TY + 2 || (EDGE && lasty));
-      if (xface) a.mfx[g] = S.ep[0][o] + mx0;
-      if (yface) a.mfy[g] = S.ep[1][o] + my0;
+      if (xface) a.mfx[g] = (NEP == 2 ? S.ep[0][NEP == 2 ? o : 0] : a.mfx[g]) + mx0;
+      if (yface) a.mfy[g] = (NEP == 2 ? S.ep[NEP == 2 ? 1 : 0][NEP == 2 ? o : 0] : a.mfy[g]) + my0;
+      if constexpr (NF == 4) {   // momentum update (k_dsw_vort_uv2): v on the west faces, u on the south faces
+        const double kev = (xface || yface) ? __ldg(vu.ke + g) : 0.;
+        if (xface) vu.vo[g] = __ldg(vu.v + g) * __ldg(G.dy + gi) + kev - __ldg(vu.ke + g + T.NI) - (double)S.qi[3][o];
+        if (yface) vu.uo[g] = __ldg(vu.u + g) * __ldg(G.dx + gi) + kev - __ldg(vu.ke + g + 1) + (double)S.qj[3][o];
+      }
       if (r > tp2::TY + 2 || c > tp2::TX + 2 || (EDGE && (i > L.ie || j > L.je))) return;   // not a cell of the tile
       const double mx1 = (double)S.qi[0][o + 1], my1 = (double)S.qj[0][o + tp2::P];
       const double dp = S.q64(b, 0, o);
       const double dpn = dp + (mx0 - mx1 + my0 - my1) * ra;
       const double rdpn = 1. / dpn;   // one division for w and pt (<= 1 ulp from the two divisions of sw_core.F90:986, 1061)
 #pragma unroll
-      for (int f = 1; f < NF; f++) {
+      for (int f = 1; f < NS; f++) {
         const double div = ((double)S.qi[f][o] - (double)S.qi[f][o + 1] + (double)S.qj[f][o] - (double)S.qj[f][o + tp2::P]) * ra;
         const double q = S.q64(b, f, o);
         double v = (q * dp + div) * rdpn;
-        if (NF == 3 && f == 1) {
+        if (NS == 3 && f == 1) {
           if (a.dw && a.kdbl[KD_DAMP4_W * n1 + k] != 0.) v = v + __ldg(a.dw + g);
           a.w_o[g] = v;
         } else a.pt_o[g] = v;
@@ -888,8 +905,19 @@ __global__ void __launch_bounds__(TI* TJ) k_copy_frame(Lay L, FrameGrid FG, Fram
   }
 }
 
+// fuse_vort() : the vorticity transport + momentum update ride in the scalar transport kernel (k_dsw_transport2<.., NF = 4>)
+static int fuse_vort() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FV3_TP_FUSE4"); v = e ? atoi(e) : 1; }
+  return v;
+}
+static bool can_fuse_vort(const fv3_ctx* c, const DswTr& a) {
+  const bool mono = a.hord_dp >= 8 && a.hord_tm >= 8 && a.hord_vt >= 8, none = a.hord_dp < 8 && a.hord_tm < 8 && a.hord_vt < 8;
+  const bool rare = hord_is_rare(a.hord_dp) || hord_is_rare(a.hord_tm) || hord_is_rare(a.hord_vt);
+  return fuse_vort() && use_line_kernels() > 1 && !c->tp_fp32 && a.w && a.pt && !a.qcon && !a.dpx && !a.ptx && !a.qcx && !rare && (mono || none);
+}
 template <int FAM>
-static int launch_transport_t(fv3_ctx* c, const DswTr& a, int nk) {
+static int launch_transport_t(fv3_ctx* c, const DswTr& a, int nk, const DswVU* vu = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
     FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport<FAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DswSmem)));
@@ -909,18 +937,46 @@ static int launch_transport_t(fv3_ctx* c, const DswTr& a, int nk) {
     // the scheme is a compile-time constant of the kernel when every field uses the same common one (hord 10 / 8 / 5 / 6)
     const bool same = a.hord_dp == a.hord_tm && (!a.w || a.hord_dp == a.hord_vt);
     const int hs = same ? a.hord_dp : tp2::ORD_RT;
+    const DswVU vu0{};
+    if (vu) {   // four fields (can_fuse_vort): interior and frame tiles both on the line kernels
+#define TR4_LAUNCH1(H_, E_, MAP_, N_)                                                                                              \
+    do {                                                                                                                           \
+      constexpr int NEP4 = E_ ? 0 : 2;                                                                                             \
+      static_assert(sizeof(tp2::Smem<4, NEP4, E_>) <= 232448, "four-field tile exceeds the 227 KB of shared memory");              \
+      FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport2<F2, 4, H_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<4, NEP4, E_>))); \
+      k_dsw_transport2<F2, 4, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), tp2::NT, sizeof(tp2::Smem<4, NEP4, E_>), c->stream>>>(c->L, c->G, MAP_, a, *vu, nk, E_ ? kch_fr : kch); \
+    } while (0)
+#define TR4_LAUNCH(H_)                                          \
+    do {                                                        \
+      if (n_in) TR4_LAUNCH1(H_, false, Min, n_in);              \
+      if (n_fr) TR4_LAUNCH1(H_, true, Mfr, n_fr);               \
+    } while (0)
+      if constexpr (F2 == 1) {
+        if (hs == 10) TR4_LAUNCH(10);
+        else if (hs == 8) TR4_LAUNCH(8);
+        else TR4_LAUNCH(tp2::ORD_RT);
+      } else {
+        if (hs == 5) TR4_LAUNCH(5);
+        else if (hs == 6) TR4_LAUNCH(6);
+        else TR4_LAUNCH(tp2::ORD_RT);
+      }
+#undef TR4_LAUNCH
+#undef TR4_LAUNCH1
+      c->launches += (n_in ? 1 : 0) + (n_fr ? 1 : 0);
+      return 0;
+    }
 #define TR2_LAUNCH1(NF_, H_, E_, MAP_, N_)                                                                                         \
     do {                                                                                                                           \
       FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport2<F2, NF_, H_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<NF_, 2, E_>))); \
-      k_dsw_transport2<F2, NF_, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), tp2::NT, sizeof(tp2::Smem<NF_, 2, E_>), c->stream>>>(c->L, c->G, MAP_, a, nk, E_ ? kch_fr : kch); \
+      k_dsw_transport2<F2, NF_, H_, E_><<<dim3(N_, E_ ? nch_fr : nch), tp2::NT, sizeof(tp2::Smem<NF_, 2, E_>), c->stream>>>(c->L, c->G, MAP_, a, vu0, nk, E_ ? kch_fr : kch); \
     } while (0)
 #define TR2_LAUNCH32(NF_, H_)                                                                                                      \
     do {                                                                                                                           \
       /* fp32 sweeps (strict float: tp_line.cuh): the interior and the frame instantiation give a shared face the same flux bit for bit */ \
       FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport2<F2, NF_, H_, false, tp2::sf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<NF_, 2, false, tp2::sf>))); \
       FV3_CUDA(c, cudaFuncSetAttribute(k_dsw_transport2<F2, NF_, H_, true, tp2::sf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tp2::Smem<NF_, 2, true, tp2::sf>))); \
-      if (n_in) k_dsw_transport2<F2, NF_, H_, false, tp2::sf><<<dim3(n_in, nch), tp2::NT, sizeof(tp2::Smem<NF_, 2, false, tp2::sf>), c->stream>>>(c->L, c->G, Min, a, nk, kch); \
-      if (n_fr) k_dsw_transport2<F2, NF_, H_, true, tp2::sf><<<dim3(n_fr, nch_fr), tp2::NT, sizeof(tp2::Smem<NF_, 2, true, tp2::sf>), c->stream>>>(c->L, c->G, Mfr, a, nk, kch_fr); \
+      if (n_in) k_dsw_transport2<F2, NF_, H_, false, tp2::sf><<<dim3(n_in, nch), tp2::NT, sizeof(tp2::Smem<NF_, 2, false, tp2::sf>), c->stream>>>(c->L, c->G, Min, a, vu0, nk, kch); \
+      if (n_fr) k_dsw_transport2<F2, NF_, H_, true, tp2::sf><<<dim3(n_fr, nch_fr), tp2::NT, sizeof(tp2::Smem<NF_, 2, true, tp2::sf>), c->stream>>>(c->L, c->G, Mfr, a, vu0, nk, kch_fr); \
     } while (0)
 #define TR2_LAUNCH(NF_, H_)                                                        \
     do {                                                                           \
@@ -947,14 +1003,14 @@ static int launch_transport_t(fv3_ctx* c, const DswTr& a, int nk) {
   c->launches += (n_in ? 1 : 0) + (n_fr ? 1 : 0);
   return 0;
 }
-static int launch_transport(fv3_ctx* c, const DswTr& a, int nk) {
+static int launch_transport(fv3_ctx* c, const DswTr& a, int nk, const DswVU* vu = nullptr) {
   const bool m_dp = a.hord_dp >= 8, m_vt = a.hord_vt >= 8, m_tm = a.hord_tm >= 8;
   const bool vt_used = a.w != nullptr, tm_used = a.pt != nullptr;
   const bool all_mono = m_dp && (m_tm || !tm_used) && (m_vt || !vt_used), none_mono = !m_dp && (!m_tm || !tm_used) && (!m_vt || !vt_used);
   const bool rare = hord_is_rare(a.hord_dp) || (tm_used && hord_is_rare(a.hord_tm)) || (vt_used && hord_is_rare(a.hord_vt));
   if (rare) return launch_transport_t<2>(c, a, nk);   // the general instantiation carries the less common schemes
-  if (all_mono) return launch_transport_t<1>(c, a, nk);
-  if (none_mono) return launch_transport_t<0>(c, a, nk);
+  if (all_mono) return launch_transport_t<1>(c, a, nk, vu);
+  if (none_mono) return launch_transport_t<0>(c, a, nk, vu);
   return launch_transport_t<2>(c, a, nk);
 }
 template <int FM>
@@ -1131,21 +1187,29 @@ int stage_d_sw(fv3_ctx* c, double dt) {
     launch_deln(c, dl);
     tr.ptx = fx; tr.pty = fy;
   }
-  int rc = launch_transport(c, tr, nk); if (rc) return rc;
-  {
+  // the scalar transport, the halo copy-through of its outputs and the ping-pong swap.  With vu (can_fuse_vort) the vorticity
+  // transport and the momentum update ride along: the call then moves behind the kinetic energy / damping kernels that feed it
+  // (nothing in between reads the transported scalars)
+  auto do_transport = [&](const DswVU* vu) -> int {
+    int rc_ = launch_transport(c, tr, nk, vu); if (rc_) return rc_;
     FrameJobs fj{}; int n = 0;
     fj.j[n++] = FrameJob{delp, c->alt_delp, L.ie, L.je};
     fj.j[n++] = FrameJob{pt, c->alt_pt, L.ie, L.je};
     if (nonhydro) fj.j[n++] = FrameJob{w, c->alt_w, L.ie, L.je};
     if (f.use_cond) fj.j[n++] = FrameJob{c->fld[FV3_QCON], c->alt_qcon, L.ie, L.je};
+    if (vu) { fj.j[n++] = FrameJob{u, c->alt_u, L.ie, L.je + 1}; fj.j[n++] = FrameJob{v, c->alt_v, L.ie + 1, L.je}; }
     fj.n = n;
     { const FrameGrid FG = frame_grid(L, L.is, L.ie, L.js, L.je); k_copy_frame<<<dim3(FG.count(), 1, nk), blk, 0, st>>>(L, FG, fj); }
     c->launches++;
-  }
-  std::swap(c->fld[FV3_DELP], c->alt_delp); std::swap(c->fld[FV3_PT], c->alt_pt);
-  if (nonhydro) std::swap(c->fld[FV3_W], c->alt_w);
-  if (f.use_cond) std::swap(c->fld[FV3_QCON], c->alt_qcon);
-  double* delp_new = c->fld[FV3_DELP];
+    std::swap(c->fld[FV3_DELP], c->alt_delp); std::swap(c->fld[FV3_PT], c->alt_pt);
+    if (nonhydro) std::swap(c->fld[FV3_W], c->alt_w);
+    if (f.use_cond) std::swap(c->fld[FV3_QCON], c->alt_qcon);
+    return 0;
+  };
+  const bool fuse4 = nonhydro && can_fuse_vort(c, tr);
+  int rc = 0;
+  if (!fuse4) { rc = do_transport(nullptr); if (rc) return rc; }
+  double* delp_new = fuse4 ? c->alt_delp : c->fld[FV3_DELP];
   // --- KE (:1078-1228); ke lives in fx2's plane from here (tp scratch is rewritten later, so use gx)
   double* ke = gx;      // B-grid (is:ie+1, js:je+1)
   if (hord_wind_is_rare(f.hord_mt)) k_dsw_ke<true><<<grd, blk, 0, st>>>(L, c->G, u, v, uc, vc, uts, vts, ke, dt, f.hord_mt);
@@ -1172,11 +1236,15 @@ int stage_d_sw(fv3_ctx* c, double dt) {
                                   c->d_kint, c->d_kdbl, dt, f.dddmp, f.d4_bg, c->b.stretched_grid);
   c->launches++;
   // --- vorticity transport and momentum update (:1476-1509), fused
+  if (fuse4) {
+    const DswVU vu{vq, u, v, ke, c->alt_u, c->alt_v};
+    rc = do_transport(&vu);
+  } else
   rc = hord_is_rare(f.hord_vt) ? launch_vort_uv_t<2>(c, vq, u, v, ke, c->alt_u, c->alt_v, nk)
        : (f.hord_vt >= 8)      ? launch_vort_uv_t<1>(c, vq, u, v, ke, c->alt_u, c->alt_v, nk)
                                : launch_vort_uv_t<0>(c, vq, u, v, ke, c->alt_u, c->alt_v, nk);
   if (rc) return rc;
-  {
+  if (!fuse4) {
     FrameJobs fj{};
     fj.j[0] = FrameJob{u, c->alt_u, L.ie, L.je + 1};
     fj.j[1] = FrameJob{v, c->alt_v, L.ie + 1, L.je};

@@ -43,7 +43,8 @@ enum { A_CRX = 0, A_CRY = 1, A_XFX = 2, A_YFX = 3, A_Q = 4 };
 //   W_AREA: flux * area flux (xfx / yfx) for every field         (tp_core.F90:193-198 without mfx)
 //   W_MASS: field 0: flux * area flux = the mass flux; field f > 0: flux * mass flux   (sw_core.F90:928-940, tp_core.F90:213-226)
 //   W_RAW : the unweighted Lin-Rood flux 0.5 * (outer + inner)
-enum { W_AREA = 0, W_MASS = 1, W_RAW = 2 };
+//   W_MASS_V: W_MASS for fields 0 .. NF-2, W_AREA for the last one (d_sw: delp, w, pt and the absolute vorticity in one kernel)
+enum { W_AREA = 0, W_MASS = 1, W_RAW = 2, W_MASS_V = 3 };
 
 // T = the type the sweeps compute in.  double: the fp64 product path.  sf ("transport_fp32", BASELINE config 5: fp32 transport on
 // fp64 storage): the level's inputs land as doubles (cp.async cannot convert), each thread converts the elements it fetched itself
@@ -246,7 +247,16 @@ __device__ __forceinline__ void inner_line(const T* __restrict__ cr_, const T* _
   const T cl = cr_[o], cr = cr_[o + sa], xl = xf_[o], xr = xf_[o + sa], ar = area[o];
   const T rra = T(1.) / (ar + xl - xr);
   T q0[NF], g[NF];
-  line_fluxes<FAM, NF, ORD, EDGE, T>(q, o, sa, lane, cl, cr, ord, q0, fin, E);
+  if constexpr (NF > 3 && sizeof(T) == 8) {   // four fp64 fields staged together do not fit 64 registers: three + one
+    const int o3[3] = {ord[0], ord[1], ord[2]}, o1[1] = {ord[3]};
+    T q3[3], f3[3], q1[1], f1[1];
+    line_fluxes<FAM, 3, ORD, EDGE, T>(q, o, sa, lane, cl, cr, o3, q3, f3, E);
+    const EdgeLine E1{E.on, E.base, E.n, E.ef + 3 * EF_FIELD};
+    line_fluxes<FAM, 1, ORD, EDGE, T>(q + 3, o, sa, lane, cl, cr, o1, q1, f1, E1);
+#pragma unroll
+    for (int f = 0; f < 3; f++) { q0[f] = q3[f]; fin[f] = f3[f]; }
+    q0[3] = q1[0]; fin[3] = f1[0];
+  } else line_fluxes<FAM, NF, ORD, EDGE, T>(q, o, sa, lane, cl, cr, ord, q0, fin, E);
 #pragma unroll
   for (int f = 0; f < NF; f++) g[f] = fin[f] * xl;
 #pragma unroll
@@ -265,7 +275,7 @@ __device__ __forceinline__ void outer_line(const T* __restrict__ cr_, const T* _
   T q0[NF], fo[NF];
   // the fields interleaved (one staged evaluation) when their working set fits the 64 registers of a 1024-thread CTA: the
   // branch-free iord = 10 constraint keeps ~12 doubles live per field, so there the fields go one after the other
-  constexpr bool SEQ = (FAM == 1 && ORD != 8 && NF > 1 && sizeof(T) == 8);
+  constexpr bool SEQ = ((FAM == 1 && ORD != 8 && NF > 1) || NF > 3) && sizeof(T) == 8;
   if (SEQ) {
 #pragma unroll
     for (int f = 0; f < NF; f++) {
@@ -283,6 +293,7 @@ __device__ __forceinline__ void outer_line(const T* __restrict__ cr_, const T* _
     T out;
     if (WMODE == W_RAW) out = F;
     else if (WMODE == W_AREA || f == 0) { out = F * xl; m = out; }
+    else if (WMODE == W_MASS_V && f == NF - 1) out = F * xl;
     else out = F * m;
     q[f][o] = out;
   }
