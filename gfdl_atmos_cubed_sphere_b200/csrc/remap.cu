@@ -1,0 +1,450 @@
+// Vertical remapping on device-resident state (the step between the k_split iterations of fv_dynamics).
+//
+// Reference semantics: model/fv_mapz.F90:56-845 (Lagrangian_to_Eulerian) and the column operators of model/fv_operators.F90:
+// map_scalar (:40-134), map1_ppm (:137-229), map1_q2 (:352-443), scalar_profile (:546-916), cs_profile (:919-1300),
+// cs_limiters (:1303-1378).  Built: remap_te = F, moist_kappa = F, consv = 0 (no energy fixer), dry air (the last-step T_v -> T
+// conversion is the identity), abs(kord) in 8..13, kord_wz > 0 (iv = -2), at most one tracer (FV3_WORK_Q, no fillz); anything
+// else is an error (-2), never a silent fall-back.
+//
+// Design: column-parallel like the vertical solvers -- one thread per column, consecutive threads on consecutive i, so every
+// level access is a coalesced row segment of the [k][NJ][NI] arrays.  The reconstruction (a4(1:4), the interface values, the
+// differences and the extremum flags) lives in seven scratch planes of the context instead of per-thread local arrays
+// (km = 79..127 levels x 7 arrays would be 4-7 KB of local memory per thread).  The remap runs once per k_split step against
+// n_split = 8 acoustic substeps, so it is written for clarity: ~30 passes over the column, < 2 % of a step.
+#include "fv3_ctx.hpp"
+#include <cmath>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr double r3 = 1. / 3., r23 = 2. / 3., r12 = 1. / 12.;
+constexpr int CB = 128;
+
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin3(double a, double b, double c) { return dmin(dmin(a, b), c); }
+__device__ __forceinline__ double dmax3(double a, double b, double c) { return dmax(dmax(a, b), c); }
+
+// the scratch of one column: pointers already offset to the column, level k (1-based) at [(k - 1) * plane]
+struct Col {
+  double *a1, *a2, *a3, *a4, *q, *gam;
+  int* fl;   // bit 0 extm, bit 1 ext5, bit 2 ext6
+  long long plane;
+};
+#define LV(p, k) (p)[(long long)((k) - 1) * C.plane]
+#define A1(k) LV(C.a1, k)
+#define A2(k) LV(C.a2, k)
+#define A3(k) LV(C.a3, k)
+#define A4(k) LV(C.a4, k)
+#define QI(k) LV(C.q, k)
+#define GAM(k) LV(C.gam, k)
+#define FL(k) LV(C.fl, k)
+
+// fv_operators.F90:1303-1378 for one layer
+__device__ void cs_limiters(const Col& C, int k, bool extm, int iv) {
+  double a1 = A1(k), a2 = A2(k), a3 = A3(k), a4 = A4(k);
+  if (iv == 0) {
+    if (a1 <= 0.) { a2 = a1; a3 = a1; a4 = 0.; }
+    else if (fabs(a3 - a2) < -a4) {
+      if ((a1 + 0.25 * ((a3 - a2) * (a3 - a2)) / a4 + a4 * r12) < 0.) {
+        if (a1 < a3 && a1 < a2) { a3 = a1; a2 = a1; a4 = 0.; }
+        else if (a3 > a2) { a4 = 3. * (a2 - a1); a3 = a2 - a4; }
+        else { a4 = 3. * (a3 - a1); a2 = a3 - a4; }
+      }
+    }
+  } else {
+    const bool flat = iv == 1 ? ((a1 - a2) * (a1 - a3) >= 0.) : extm;
+    if (flat) { a2 = a1; a3 = a1; a4 = 0.; }
+    else {
+      const double da1 = a3 - a2, da2 = da1 * da1, a6da = a4 * da1;
+      if (a6da < -da2) { a4 = 3. * (a2 - a1); a3 = a2 - a4; }
+      else if (a6da > da2) { a4 = 3. * (a3 - a1); a2 = a3 - a4; }
+    }
+  }
+  A2(k) = a2; A3(k) = a3; A4(k) = a4;
+}
+
+// scalar_profile (scalar: with the q_min tests, :546-916) / cs_profile (:919-1300); A1 holds the layer means, P1(k) the source
+// interface pressures (k = 1..km+1)
+template <class P1>
+__device__ void profile(const Col& C, int km, const P1& pe1, double qs, int iv, int ak, double qmin, bool scalar) {
+  auto delp = [&](int k) { return pe1(k + 1) - pe1(k); };
+  if (iv == -2) {   // lower boundary condition (:570-592 / :941-963)
+    GAM(2) = 0.5;
+    QI(1) = 1.5 * A1(1);
+    for (int k = 2; k <= km - 1; k++) {
+      const double grat = delp(k - 1) / delp(k);
+      const double bet = 2. + grat + grat - GAM(k);
+      QI(k) = (3. * (A1(k - 1) + A1(k)) - QI(k - 1)) / bet;
+      GAM(k + 1) = grat / bet;
+    }
+    const double grat = delp(km - 1) / delp(km);
+    QI(km) = (3. * (A1(km - 1) + A1(km)) - grat * qs - QI(km - 1)) / (2. + grat + grat - GAM(km));
+    QI(km + 1) = qs;
+    for (int k = km - 1; k >= 1; k--) QI(k) = QI(k) - GAM(k + 1) * QI(k + 1);
+  } else {
+    double d4 = 0.;
+    {
+      const double grat = delp(2) / delp(1);
+      const double bet = grat * (grat + 0.5);
+      QI(1) = ((grat + grat) * (grat + 1.) * A1(1) + A1(2)) / bet;
+      GAM(1) = (1. + grat * (grat + 1.5)) / bet;
+    }
+    for (int k = 2; k <= km; k++) {
+      d4 = delp(k - 1) / delp(k);
+      const double bet = 2. + d4 + d4 - GAM(k - 1);
+      QI(k) = (3. * (A1(k - 1) + d4 * A1(k)) - QI(k - 1)) / bet;
+      GAM(k) = d4 / bet;
+    }
+    const double a_bot = 1. + d4 * (d4 + 1.5);
+    QI(km + 1) = (2. * d4 * (d4 + 1.) * A1(km) + A1(km - 1) - a_bot * QI(km)) / (d4 * (d4 + 0.5) - a_bot * GAM(km));
+    for (int k = km; k >= 1; k--) QI(k) = QI(k) - GAM(k) * QI(k + 1);
+  }
+  // large-scale constraints on the interface values (:639-682 / :1034-1073)
+  {
+    double q2 = QI(2);
+    q2 = dmin(q2, dmax(A1(1), A1(2)));
+    q2 = dmax(q2, dmin(A1(1), A1(2)));
+    QI(2) = q2;
+  }
+  for (int k = 2; k <= km; k++) GAM(k) = A1(k) - A1(k - 1);
+  for (int k = 3; k <= km - 1; k++) {
+    const double lo = dmin(A1(k - 1), A1(k)), hi = dmax(A1(k - 1), A1(k));
+    double qk = QI(k);
+    if (GAM(k - 1) * GAM(k + 1) > 0.) { qk = dmin(qk, hi); qk = dmax(qk, lo); }
+    else if (GAM(k - 1) > 0.) qk = dmax(qk, lo);
+    else { qk = dmin(qk, hi); if (iv == 0) qk = dmax(0., qk); }
+    QI(k) = qk;
+  }
+  {
+    double qk = QI(km);
+    qk = dmin(qk, dmax(A1(km - 1), A1(km)));
+    qk = dmax(qk, dmin(A1(km - 1), A1(km)));
+    QI(km) = qk;
+  }
+  for (int k = 1; k <= km; k++) { A2(k) = QI(k); A3(k) = QI(k + 1); }
+  // extremum flags (:695-715 / :1082-1102)
+  for (int k = 1; k <= km; k++) {
+    int f;
+    if (k == 1 || k == km) f = ((A2(k) - A1(k)) * (A3(k) - A1(k)) > 0.) ? 1 : 0;
+    else f = (GAM(k) * GAM(k + 1) < 0.) ? 1 : 0;
+    if (ak > 9) {
+      const double x0 = 2. * A1(k) - (A2(k) + A3(k)), x1 = fabs(A2(k) - A3(k));
+      const double a4 = 3. * x0;
+      A4(k) = a4;
+      if (fabs(x0) > x1) f |= 2;
+      if (fabs(a4) > x1) f |= 4;
+    }
+    FL(k) = f;
+  }
+  // top two layers (:721-754 / :1109-1140)
+  if (iv == 0) A2(1) = dmax(0., A2(1));
+  else if (iv == -1) { if (A2(1) * A1(1) <= 0.) A2(1) = 0.; }
+  else if (iv == 2) { A2(1) = A1(1); A3(1) = A1(1); A4(1) = 0.; }
+  if (iv != 2) {
+    A4(1) = 3. * (2. * A1(1) - (A2(1) + A3(1)));
+    cs_limiters(C, 1, FL(1) & 1, 1);
+  }
+  A4(2) = 3. * (2. * A1(2) - (A2(2) + A3(2)));
+  cs_limiters(C, 2, FL(2) & 1, 2);
+  // Huynh's second constraint in the interior (:759-893 / :1142-1276)
+  auto huynh = [&](int k) {
+    const double a1 = A1(k);
+    const double pmp_1 = a1 - 2. * GAM(k + 1), lac_1 = pmp_1 + 1.5 * GAM(k + 2);
+    A2(k) = dmin(dmax(A2(k), dmin3(a1, pmp_1, lac_1)), dmax3(a1, pmp_1, lac_1));
+    const double pmp_2 = a1 + 2. * GAM(k), lac_2 = pmp_2 - 1.5 * GAM(k - 1);
+    A3(k) = dmin(dmax(A3(k), dmin3(a1, pmp_2, lac_2)), dmax3(a1, pmp_2, lac_2));
+  };
+  auto flat = [&](int k) { const double a1 = A1(k); A2(k) = a1; A3(k) = a1; A4(k) = 0.; };
+  auto a6_a = [&](int k) { return 3. * (2. * A1(k) - (A2(k) + A3(k))); };
+  auto a6_b = [&](int k) { return 6. * A1(k) - 3. * (A2(k) + A3(k)); };
+  for (int k = 3; k <= km - 2; k++) {
+    const int f0 = FL(k), fm = FL(k - 1), fp = FL(k + 1);
+    const bool small = scalar && A1(k) < qmin;
+    switch (ak) {
+      case 8:
+        huynh(k);
+        A4(k) = a6_a(k);
+        break;
+      case 9:
+        if ((f0 & 1) && ((fm & 1) || (fp & 1) || small)) flat(k);
+        else {
+          double a4 = scalar ? a6_a(k) : a6_b(k);
+          if (fabs(a4) > fabs(A2(k) - A3(k))) {
+            huynh(k);
+            a4 = scalar ? a6_a(k) : a6_b(k);
+          }
+          A4(k) = a4;
+        }
+        break;
+      case 10:
+        if (f0 & 1) {
+          if (small || (fm & 1) || (fp & 1)) flat(k);
+          else A4(k) = a6_b(k);
+        } else {
+          double a4 = a6_b(k);
+          if (fabs(a4) > fabs(A2(k) - A3(k))) {
+            huynh(k);
+            a4 = a6_b(k);
+          }
+          A4(k) = a4;
+        }
+        break;
+      case 11:
+        if ((f0 & 2) && ((fm & 2) || (fp & 2) || small)) flat(k);
+        else A4(k) = a6_a(k);
+        break;
+      case 12:
+        if (f0 & 2) {
+          if ((fm & 2) || (fp & 2)) { const double a1 = A1(k); A2(k) = a1; A3(k) = a1; }
+          else if ((fm & 4) || (fp & 4)) huynh(k);
+        } else if (f0 & 4) {
+          if ((fm & 2) || (fp & 2)) huynh(k);
+        }
+        A4(k) = a6_a(k);
+        break;
+      default:   // 13
+        A4(k) = a6_a(k);
+        break;
+    }
+    if (iv == 0) cs_limiters(C, k, f0 & 1, 0);
+  }
+  // bottom two layers (:898-914 / :1281-1298)
+  if (iv == 0) A3(km) = dmax(0., A3(km));
+  else if (iv == -1) { if (A3(km) * A1(km) <= 0.) A3(km) = 0.; }
+  for (int k = km - 1; k <= km; k++) {
+    A4(k) = 3. * (2. * A1(k) - (A2(k) + A3(k)));
+    cs_limiters(C, k, FL(k) & 1, k == km - 1 ? 2 : 1);
+  }
+}
+
+// the conservative mapping loop (fv_operators.F90:88-132 = 183-227 = 399-441): P1 source, P2 target interface pressures;
+// out(k, value) stores layer k.  div_dp2: map1_q2 divides by the tabulated target thickness -- the same difference here.
+template <class P1, class P2, class Out>
+__device__ void map_column(const Col& C, int km, const P1& pe1, const P2& pe2, Out&& out) {
+  int k0 = 1;
+  for (int k = 1; k <= km; k++) {
+    const double t = pe2(k), b = pe2(k + 1);
+    double qsum = 0.;
+    bool done = false;
+    for (int l = k0; l <= km; l++) {
+      const double p0 = pe1(l), p1 = pe1(l + 1);
+      if (t >= p0 && t <= p1) {
+        const double dpl = p1 - p0;
+        const double pl = (t - p0) / dpl;
+        const double a2 = A2(l), a3 = A3(l), a4 = A4(l);
+        if (b <= p1) {
+          const double pr = (b - p0) / dpl;
+          out(k, a2 + 0.5 * (a4 + a3 - a2) * (pr + pl) - a4 * r3 * (pr * (pr + pl) + pl * pl));
+          k0 = l;
+          done = true;
+        } else {
+          qsum = (p1 - t) * (a2 + 0.5 * (a4 + a3 - a2) * (1. + pl) - a4 * (r3 * (1. + pl * (1. + pl))));
+          for (int m = l + 1; m <= km; m++) {
+            const double m0 = pe1(m), m1 = pe1(m + 1);
+            if (b > m1) qsum = qsum + (m1 - m0) * A1(m);
+            else {
+              const double dp = b - m0, esl = dp / (m1 - m0);
+              qsum = qsum + dp * (A2(m) + 0.5 * esl * (A3(m) - A2(m) + A4(m) * (1. - r23 * esl)));
+              k0 = m;
+              break;
+            }
+          }
+        }
+        break;
+      }
+    }
+    if (!done) out(k, qsum / (b - t));
+  }
+}
+
+struct Scr { double *a1, *a2, *a3, *a4, *q, *gam, *fl, *pe4; };
+__device__ __forceinline__ Col col_of(const Scr& S, long long o, long long plane) {
+  return Col{S.a1 + o, S.a2 + o, S.a3 + o, S.a4 + o, S.q + o, S.gam + o, reinterpret_cast<int*>(S.fl) + o, plane};
+}
+
+// map_scalar / map1_ppm / map1_q2 of one column, in place on fld (level k at fld[(k-1)*plane])
+template <class P1, class P2>
+__device__ void remap_field(const Col& C, int km, const P1& pe1, const P2& pe2, double* fld, double qs, int iv, int kord, double qmin,
+                            bool scalar) {
+  for (int k = 1; k <= km; k++) A1(k) = LV(fld, k);
+  profile(C, km, pe1, qs, iv, kord < 0 ? -kord : kord, qmin, scalar);
+  map_column(C, km, pe1, pe2, [&](int k, double v) { LV(fld, k) = v; });
+}
+
+struct L2E {
+  double *pt, *delp, *delz, *w, *u, *v, *pk, *pkz, *omga, *qtr, *pe, *peln;
+  const double *ws, *ak, *bk;   // ak, bk: device tables (km + 1)
+  double akap, k1k, rrg, ptop, t_min;
+  int hydrostatic, last_step, kord_mt, kord_wz, kord_tm, use_tracer, kord_tr;
+};
+
+// steps 0 - 3.3 of fv_mapz.F90 (:188-526) for the cell columns
+__global__ void __launch_bounds__(CB) k_remap_cells(Lay L, L2E a, Scr S) {
+  const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;
+  const int t = blockIdx.x * CB + threadIdx.x;
+  if (t >= nx * ny) return;
+  const int i = L.is + t % nx, j = L.js + t / nx, km = L.npz;
+  const long long o = LIDX(L, i, j);
+  const Col C = col_of(S, o, L.plane);
+  double *pt = a.pt + o, *delp = a.delp + o, *delz = a.delz + o, *pe = a.pe + o, *peln = a.peln + o, *pk = a.pk + o, *pkz = a.pkz + o;
+  double* pe4 = S.pe4 + o;
+  const double ps = LV(pe, km + 1);
+  auto pe1 = [&](int k) { return LV(pe, k); };
+  auto pe2 = [&](int k) { return k == 1 ? a.ptop : k == km + 1 ? ps : a.ak[k - 1] + a.bk[k - 1] * ps; };
+  if (a.kord_tm < 0) {   // theta_v -> T_v (:200-230)
+    if (a.hydrostatic) for (int k = 1; k <= km; k++) LV(pt, k) = LV(pt, k) * (LV(pk, k + 1) - LV(pk, k)) / (a.akap * (LV(peln, k + 1) - LV(peln, k)));
+    else for (int k = 1; k <= km; k++) { const double p = LV(pt, k); LV(pt, k) = p * exp(a.k1k * log(a.rrg * LV(delp, k) / LV(delz, k) * p)); }
+  }
+  if (!a.hydrostatic) for (int k = 1; k <= km; k++) LV(delz, k) = -LV(delz, k) / LV(delp, k);   // :297-303
+  for (int k = 1; k <= km; k++) LV(delp, k) = pe2(k + 1) - pe2(k);                              // :318-331
+  // pn2 = log(pe2) is recomputed where it is needed (the temperature map, then the peln / pk update): no column array is kept
+  auto pn1 = [&](int k) { return LV(peln, k); };
+  auto pn2 = [&](int k) { return (k == 1 || k == km + 1) ? LV(peln, k) : log(pe2(k)); };
+  if (a.kord_tm < 0) remap_field(C, km, pn1, pn2, pt, 0., 1, a.kord_tm, a.t_min, true);          // :373-386
+  else remap_field(C, km, pe1, pe2, pt, 0., 1, a.kord_tm, 0., false);
+  if (a.use_tracer) remap_field(C, km, pe1, pe2, a.qtr + o, 0., 0, a.kord_tr, 0., true);         // :395-408 (map1_q2)
+  if (!a.hydrostatic) {                                                                          // :411-433
+    remap_field(C, km, pe1, pe2, a.w + o, a.ws[o], -2, a.kord_wz, 0., false);
+    remap_field(C, km, pe1, pe2, delz, 0., 1, a.kord_tm, 0., false);
+    for (int k = 1; k <= km; k++) LV(delz, k) = -LV(delz, k) * (pe2(k + 1) - pe2(k));
+  }
+  // 3.1 / 3.2: pk, peln, pkz (:436-506); the old peln (pe0) and omega (pe3) of the last step are parked in the a1 / a2 scratch
+  if (a.last_step) {
+    A2(1) = 0.;
+    for (int k = 2; k <= km + 1; k++) LV(C.a2, k) = LV(a.omga + o, k - 1);
+    for (int k = 1; k <= km + 1; k++) LV(C.a1, k) = LV(peln, k);
+  }
+  for (int k = 2; k <= km; k++) { const double pn = log(pe2(k)); LV(peln, k) = pn; LV(pk, k) = exp(a.akap * pn); }
+  if (a.hydrostatic) for (int k = 1; k <= km; k++) LV(pkz, k) = (LV(pk, k + 1) - LV(pk, k)) / (a.akap * (LV(peln, k + 1) - LV(peln, k)));
+  else {
+    const double ex = a.kord_tm < 0 ? a.akap : a.k1k;
+    for (int k = 1; k <= km; k++) LV(pkz, k) = exp(ex * log(a.rrg * LV(delp, k) / LV(delz, k) * LV(pt, k)));
+  }
+  if (a.kord_tm > 0) for (int k = 1; k <= km; k++) LV(pt, k) = LV(pt, k) * LV(pkz, k);
+  if (a.last_step) {   // 3.3 omega to the new layer centres (:509-526)
+    double* om = a.omga + o;
+    int k_next = 1;
+    for (int n = 1; n <= km; n++) {
+      const double pc = 0.5 * (LV(peln, n) + LV(peln, n + 1));
+      for (int k = k_next; k <= km; k++) {
+        const double l0 = LV(C.a1, k), l1 = LV(C.a1, k + 1);
+        if (pc <= l1 && pc >= l0) {
+          const double e0 = LV(C.a2, k), e1 = LV(C.a2, k + 1);
+          LV(om, n) = e0 + (e1 - e0) * (pc - l0) / (l1 - l0);
+          k_next = k;
+          break;
+        }
+      }
+    }
+  }
+  for (int k = 2; k <= km; k++) LV(pe4, k) = pe2(k);   // :652-668, stored until every wind column has read the old pe
+}
+
+// 4.1 / 4.2 (:535-571): u on the south faces (DIR = 0: i in is..ie, j in js..je+1), v on the west faces (DIR = 1)
+template <int DIR>
+__global__ void __launch_bounds__(CB) k_remap_wind(Lay L, L2E a, Scr S) {
+  const int nx = L.ie - L.is + 1 + DIR, ny = L.je - L.js + 1 + (1 - DIR);
+  const int t = blockIdx.x * CB + threadIdx.x;
+  if (t >= nx * ny) return;
+  const int i = L.is + t % nx, j = L.js + t / nx, km = L.npz;
+  const long long o = LIDX(L, i, j), om = DIR == 0 ? o - L.NI : o - 1;   // the neighbour column the pressures are averaged with
+  const Col C = col_of(S, o, L.plane);
+  const double *pa = a.pe + o, *pb = a.pe + om;
+  const double ps2 = LV(pb, km + 1) + LV(pa, km + 1);
+  auto pe0 = [&](int k) { return k == 1 ? LV(pa, 1) : 0.5 * (LV(pb, k) + LV(pa, k)); };
+  auto pe3 = [&](int k) { return (DIR == 1 && k == 1) ? a.ak[0] : a.ak[k - 1] + 0.5 * a.bk[k - 1] * ps2; };
+  remap_field(C, km, pe0, pe3, (DIR == 0 ? a.u : a.v) + o, 0., -1, a.kord_mt, 0., false);
+}
+
+// the new interface pressures (:661-668) and, between k_split steps, T_v back to theta_v (:833-843)
+__global__ void __launch_bounds__(CB) k_remap_finish(Lay L, L2E a, Scr S) {
+  const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;
+  const int t = blockIdx.x * CB + threadIdx.x;
+  if (t >= nx * ny) return;
+  const int i = L.is + t % nx, j = L.js + t / nx, km = L.npz;
+  const long long o = LIDX(L, i, j);
+  const Col C{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, L.plane};
+  for (int k = 2; k <= km; k++) LV(a.pe + o, k) = LV(S.pe4 + o, k);
+  if (!a.last_step) for (int k = 1; k <= km; k++) LV(a.pt + o, k) = LV(a.pt + o, k) / LV(a.pkz + o, k);
+}
+
+// stand-alone column operator on FV3_WORK_Q (parity of the profiles for every scheme / iv): pe1 = FV3_PE, pe2 = the hybrid levels
+__global__ void __launch_bounds__(CB) k_remap_work_q(Lay L, L2E a, Scr S, int mode, int iv, int kord, double qmin) {
+  const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;
+  const int t = blockIdx.x * CB + threadIdx.x;
+  if (t >= nx * ny) return;
+  const int i = L.is + t % nx, j = L.js + t / nx, km = L.npz;
+  const long long o = LIDX(L, i, j);
+  const Col C = col_of(S, o, L.plane);
+  const double* pe = a.pe + o;
+  const double ps = LV(pe, km + 1);
+  auto pe1 = [&](int k) { return LV(pe, k); };
+  auto pe2 = [&](int k) { return k == 1 ? a.ptop : k == km + 1 ? ps : a.ak[k - 1] + a.bk[k - 1] * ps; };
+  remap_field(C, km, pe1, pe2, a.qtr + o, iv == -2 ? a.ws[o] : 0., iv, kord, qmin, mode != 1);
+}
+
+int check_kord(fv3_ctx* c, int kord, const char* what) {
+  const int ak = kord < 0 ? -kord : kord;
+  if (ak < 8 || ak > 13) return fv3_fail(c, -2, std::string("remap: ") + what + " outside 8..13 (ppm_profile and the strictly monotone schemes are not built)");
+  return 0;
+}
+
+int fill(fv3_ctx* c, L2E& a, Scr& S) {
+  const fv3_flags_t& f = c->f;
+  const int km = c->L.npz;
+  if (!c->d_akbk) {
+    std::vector<double> h(2 * (km + 1));
+    for (int k = 0; k <= km; k++) { h[k] = c->ak[k]; h[km + 1 + k] = c->bk[k]; }
+    FV3_CUDA(c, cudaMalloc(&c->d_akbk, h.size() * sizeof(double)));
+    FV3_CUDA(c, cudaMemcpy(c->d_akbk, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  a.pt = c->fld[FV3_PT]; a.delp = c->fld[FV3_DELP]; a.delz = c->fld[FV3_DELZ]; a.w = c->fld[FV3_W]; a.u = c->fld[FV3_U]; a.v = c->fld[FV3_V];
+  a.pk = c->fld[FV3_PK]; a.pkz = c->fld[FV3_PKZ]; a.omga = c->fld[FV3_OMGA]; a.qtr = c->fld[FV3_WORK_Q]; a.pe = c->fld[FV3_PE];
+  a.peln = c->fld[FV3_PELN]; a.ws = c->fld[FV3_WS]; a.ak = c->d_akbk; a.bk = c->d_akbk + km + 1;
+  const double cv_air = f.cp_air - f.rdgas;
+  a.akap = f.kappa; a.k1k = f.rdgas / cv_air; a.rrg = -f.rdgas / f.grav; a.ptop = f.ptop; a.t_min = 184.;   // fv_mapz.F90:43
+  a.hydrostatic = f.hydrostatic;
+  S = Scr{c->scr[0], c->scr[1], c->scr[2], c->scr[3], c->scr[4], c->scr[5], c->scr[6], c->scr[7]};
+  return 0;
+}
+
+}  // namespace
+
+int stage_remap_work_q(fv3_ctx* c, int mode, int iv, int kord, double qmin) {
+  StageScope ts(c, "REMAP_OP");
+  if (mode < 0 || mode > 2 || iv < -2 || iv > 2) return fv3_fail(c, -1, "remap_work_q: mode in 0..2, iv in -2..2");
+  int rc = check_kord(c, kord, "kord"); if (rc) return rc;
+  L2E a{}; Scr S{};
+  rc = fill(c, a, S); if (rc) return rc;
+  const int n = (c->L.ie - c->L.is + 1) * (c->L.je - c->L.js + 1);
+  k_remap_work_q<<<(n + CB - 1) / CB, CB, 0, c->stream>>>(c->L, a, S, mode, iv, kord, qmin);
+  c->launches++;
+  FV3_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int stage_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr) {
+  StageScope ts(c, "REMAP");
+  const fv3_flags_t& f = c->f;
+  if (f.moist_kappa) return fv3_fail(c, -2, "remap: moist_kappa not supported");
+  if (kord_wz < 0) return fv3_fail(c, -2, "remap: kord_wz < 0 (iv = -3 lower boundary condition) not supported");
+  if (kord_mt < 0) return fv3_fail(c, -2, "remap: kord_mt must be positive");
+  int rc = check_kord(c, kord_mt, "kord_mt"); if (rc) return rc;
+  rc = check_kord(c, kord_tm, "kord_tm"); if (rc) return rc;
+  if (!f.hydrostatic) { rc = check_kord(c, kord_wz, "kord_wz"); if (rc) return rc; }
+  if (use_tracer) { rc = check_kord(c, kord_tr, "kord_tr"); if (rc) return rc; if (kord_tr < 0) return fv3_fail(c, -2, "remap: kord_tr must be positive"); }
+  L2E a{}; Scr S{};
+  rc = fill(c, a, S); if (rc) return rc;
+  a.last_step = last_step; a.kord_mt = kord_mt; a.kord_wz = kord_wz; a.kord_tm = kord_tm; a.use_tracer = use_tracer; a.kord_tr = kord_tr;
+  const Lay& L = c->L;
+  const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;
+  k_remap_cells<<<(nx * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
+  k_remap_wind<0><<<(nx * (ny + 1) + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
+  k_remap_wind<1><<<((nx + 1) * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
+  k_remap_finish<<<(nx * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
+  c->launches += 4;
+  FV3_CUDA(c, cudaGetLastError());
+  return 0;
+}

@@ -202,6 +202,16 @@ int fv3_del2_cubed_cube(fv3_ctx **ctxs, int nctx, int field, double cd, int nmax
 /* Entry conversion of fv_dynamics (fv_dynamics.F90:303-328, 377-398; moist_kappa = F): dp1 = zvir*q_v (q_v in FV3_WORK_Q, result
  * in FV3_DP1), non-hydrostatic pkz = exp(kappa*log(rdg*delp*pt*(1+dp1)/delz)), pt = pt*(1+dp1)[*(1-q_con)]/pkz. */
 int fv3_pt_to_theta(fv3_ctx *ctx, double zvir);
+/* Vertical remapping, the step between the k_split iterations of fv_dynamics (fv_dynamics.F90:578-625 call site).
+ * fv3_lagrangian_to_eulerian: fv_mapz.F90:56-845 on one face after fv3_dyn_core (which leaves pe incl. its one-cell halo, peln,
+ * pk, ws and omga current): delp <- ak/bk hybrid levels, pt (theta_v in; theta_v out, or T_v when last_step), w, delz, u, v,
+ * [the tracer in FV3_WORK_Q], pe, peln, pk, pkz remapped; omga interpolated when last_step.  Built: remap_te = F, moist_kappa = F,
+ * consv = 0 (no energy fixer), dry air (the last-step T_v -> T conversion is the identity), abs(kord_*) in 8..13 (cs_profile /
+ * scalar_profile), kord_wz > 0; everything else returns -2.  kord_tm < 0: T_v is mapped in log p (map_scalar), > 0: theta_v in p.
+ * fv3_remap_work_q: the column operators alone on FV3_WORK_Q, from the layers of FV3_PE to the hybrid levels -- mode 0 map_scalar
+ * (fv_operators.F90:40), 1 map1_ppm (:137; iv = -2 takes its lower boundary value from FV3_WS), 2 map1_q2 (:352). */
+int fv3_lagrangian_to_eulerian(fv3_ctx *ctx, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr);
+int fv3_remap_work_q(fv3_ctx *ctx, int mode, int iv, int kord, double qmin);
 /* dyn_core.F90:1305-1356: filtered heat_source -> pt (levels 1..n_con, limited by delt_max); part of fv3_dyn_core */
 int fv3_dcon_heating(fv3_ctx *ctx, double bdt);
 int fv3_geopk(fv3_ctx *ctx, int cg);

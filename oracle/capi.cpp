@@ -358,6 +358,19 @@ int fv3o_del2_cubed(fv3o_ctx* c, int field, double cd, int nmax) {
   return 0;
 }
 // fv_dynamics.F90:303-328, :377-398: specific humidity in FV3_WORK_Q (read only when zvir != 0 is meaningful; it is multiplied anyway)
+// fv_operators.F90 map_scalar (mode 0) / map1_ppm (1) / map1_q2 (2) of FV3_WORK_Q on the compute domain: from the layers of FV3_PE to
+// the hybrid levels ak + bk * pe(km+1) (remap.cpp)
+int fv3o_remap_work_q(fv3o_ctx* c, int mode, int iv, int kord, double qmin) {
+  Bd bd(c->b);
+  return remap_work_q(F3(c, FV3_WORK_Q), F2(c, FV3_WS), c->fld[FV3_PE].data(), c->ak, c->bk, c->f, bd, mode, iv, kord, qmin);
+}
+// fv_mapz.F90:56-845 Lagrangian_to_Eulerian on one face (remap.cpp states the supported subset)
+int fv3o_lagrangian_to_eulerian(fv3o_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr) {
+  Bd bd(c->b);
+  L2EFields F{F3(c, FV3_PT), F3(c, FV3_DELP), F3(c, FV3_DELZ), F3(c, FV3_W), F3(c, FV3_U), F3(c, FV3_V), F3(c, FV3_PK), F3(c, FV3_PKZ),
+              F3(c, FV3_OMGA), F3(c, FV3_WORK_Q), F2(c, FV3_WS), c->fld[FV3_PE].data(), c->fld[FV3_PELN].data()};
+  return lagrangian_to_eulerian(F, c->ak, c->bk, c->f, bd, last_step, kord_mt, kord_wz, kord_tm, use_tracer, kord_tr);
+}
 int fv3o_pt_to_theta(fv3o_ctx* c, double zvir) {
   if (c->f.moist_kappa) return -2;
   Bd bd(c->b);

@@ -271,4 +271,11 @@ void pk3_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed
 void pe_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed, int npz, double ptop,
              double* pe, V3 delp);
 
+// remap.cpp (fv_mapz.F90 Lagrangian_to_Eulerian, fv_operators.F90 map_scalar / map1_ppm / map1_q2 and their profiles)
+struct L2EFields { V3 pt, delp, delz, w, u, v, pk, pkz, omga, qtr; V2 ws; double *pe, *peln; };
+int remap_work_q(V3 q, V2 ws, double* pe, const std::vector<double>& ak, const std::vector<double>& bk, const fv3_flags_t& f, const Bd& bd,
+                 int mode, int iv, int kord, double qmin);
+int lagrangian_to_eulerian(const L2EFields& F, const std::vector<double>& ak, const std::vector<double>& bk, const fv3_flags_t& f, const Bd& bd,
+                           int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr);
+
 }  // namespace fv3o
