@@ -269,6 +269,39 @@ extern "C" int fv3_del2_cubed_cube(fv3_ctx** ctxs, int nctx, int field, double c
   return 0;
 }
 
+// ---- fv_dynamics: the k_split loop on device-resident state ------------------------------------
+// Reference semantics: model/fv_dynamics.F90:303-398 (entry: pkz, pt -> theta_v), :445-662 (n_map loop: dp1 = delp -> dyn_core ->
+// tracer_2d -> Lagrangian_to_Eulerian -> on the last step the omega filter).  Dry, adiabatic subset: zvir * q_v = 0, no
+// moist_kappa / inline physics / energy fixer (consv_te = 0), at most one tracer (FV3_WORK_Q, advected with hord_tr and remapped
+// with kord_tr when hord_tr != 0).  pt is temperature on entry and on exit.
+extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_out);
+extern "C" int fv3_fv_dynamics(fv3_ctx** ctxs, int nctx, double bdt, int k_split, int n_split, int kord_mt, int kord_wz, int kord_tm,
+                               int kord_tr, int hord_tr, int nf_omega, int flags) {
+  if (!ctxs || nctx < 1 || k_split < 1 || n_split < 1) return -1;
+  if (ctxs[0]->f.sw_test_case) return fv3_fail(ctxs[0], -2, "fv_dynamics: the SW_DYNAMICS build has no k_split loop body beyond dyn_core");
+  if (ctxs[0]->L.npz <= 4) return fv3_fail(ctxs[0], -2, "fv_dynamics: npz <= 4 (no vertical remapping, fv_dynamics.F90:567) not supported");
+  int rc;
+  FORALL(stage_pt_to_theta(c, 0.))                                                        // fv_dynamics.F90:303-398
+  const double mdt = bdt / (double)k_split;                                               // :268
+  for (int n_map = 1; n_map <= k_split; n_map++) {
+    const int last_step = n_map == k_split;
+    FORALL(stage_copy_field(c, FV3_DP1, FV3_DELP))                                        // :473-481 (compute domain + halo)
+    if ((rc = fv3_dyn_core(ctxs, nctx, mdt, n_split, flags))) return rc;                  // :495-502
+    if (hord_tr != 0 && (rc = fv3_tracer_2d(ctxs, nctx, hord_tr, nullptr))) return rc;    // :512-535
+    FORALL(stage_lagrangian_to_eulerian(c, last_step, kord_mt, kord_wz, kord_tm, hord_tr != 0, kord_tr))   // :578-625
+    if (last_step && nf_omega > 0) {                                                      // :658-662
+      const double cd = 0.18 * ctxs[0]->G.da_min;
+      if ((rc = fv3_del2_cubed_cube(ctxs, nctx, FV3_OMGA, cd, nf_omega))) return rc;
+    }
+  }
+  for (int a = 0; a < nctx; a++) {
+    cudaSetDevice(ctxs[a]->device);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fv3_fail(ctxs[a], (int)e, std::string("fv_dynamics: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+
 // ---- whole-state transfer (dyn_core entry/exit) ---------------------------------------------
 extern "C" int fv3_upload_state(fv3_ctx* c, const fv3_state_t* s) {
   if (!c || !s) return -1;

@@ -82,6 +82,17 @@ class CudaCube:
         for t in self.tiles:
             self.eng[t].sync()
 
+    def fv_dynamics(self, bdt, k_split, n_split, kord_mt=9, kord_wz=9, kord_tm=-9, kord_tr=9, hord_tr=0, nf_omega=1, graph=False):
+        """fv3_fv_dynamics: entry conversion, k_split x (dyn_core, tracer_2d, vertical remap), omega filter; pt = T in and out."""
+        fn = self.lib[0].fv3_fv_dynamics
+        fn.restype = C.c_int
+        rc = fn(self.ctxs, len(self.tiles), C.c_double(bdt), C.c_int(k_split), C.c_int(n_split), C.c_int(kord_mt), C.c_int(kord_wz),
+                C.c_int(kord_tm), C.c_int(kord_tr), C.c_int(hord_tr), C.c_int(nf_omega), C.c_int(1 if graph else 0))
+        if rc:
+            raise RuntimeError(f"fv3_fv_dynamics rc={rc}: " + "; ".join(self.eng[t].last_error() for t in self.tiles))
+        for t in self.tiles:
+            self.eng[t].sync()
+
     def set_transport_fp32(self, on=True):
         """fv3_set_transport_fp32 on every face: fp32 PPM sweeps on the interior tiles of d_sw (BASELINE config 5)."""
         fn = self.lib[0].fv3_set_transport_fp32

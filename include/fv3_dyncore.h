@@ -302,6 +302,13 @@ int fv3_plane_index(const fv3_ctx *ctx, int i, int j);
 #define FV3_DYN_GRAPH 1
 int fv3_dyn_core(fv3_ctx **ctxs, int nctx, double bdt, int n_split, int flags);
 
+/* fv_dynamics.F90:303-398 + :445-662: one call of fv_dynamics on device-resident state -- entry conversion
+ * T -> theta_v, then k_split times { dp1 = delp; dyn_core(bdt / k_split, n_split); tracer_2d of FV3_WORK_Q when hord_tr != 0;
+ * Lagrangian_to_Eulerian }, then the omega filter del2_cubed(omga, 0.18 da_min, nf_omega).  Dry adiabatic subset (no q_v, no
+ * moist_kappa, no inline physics, no energy fixer); pt is temperature on entry and on exit.  flags: as fv3_dyn_core. */
+int fv3_fv_dynamics(fv3_ctx **ctxs, int nctx, double bdt, int k_split, int n_split, int kord_mt, int kord_wz, int kord_tm,
+                    int kord_tr, int hord_tr, int nf_omega, int flags);
+
 /* fv_tracer2d.F90:49-295 tracer_2d_1L for ONE tracer (nq = 1, trdm = 0, id_divg_mean = 0), all faces of this process in
  * lockstep, after fv3_dyn_core: the tracer in FV3_WORK_Q (halo included) is advected in place with the accumulated mass
  * fluxes / Courant numbers FV3_MFX, MFY, CX, CY of the acoustic loop and dp1 = FV3_DP1; like the reference the call

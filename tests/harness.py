@@ -301,6 +301,21 @@ class OracleCube:
         self.del2_cubed("HEAT", 0.20 * da_min, min(3, f["nord"] + 1))
         self.all("dcon_heating", float(bdt))
 
+    def fv_dynamics(self, bdt, k_split, n_split, kord_mt, kord_wz, kord_tm, kord_tr, hord_tr, nf_omega):
+        """fv_dynamics.F90:303-398 + :445-662 on the oracle side, the mirror of fv3_fv_dynamics (dry adiabatic subset)."""
+        F = abi.FIELD_ID
+        self.all("pt_to_theta", 0.0)
+        mdt = bdt / k_split
+        for n_map in range(1, k_split + 1):
+            last = int(n_map == k_split)
+            self.all("copy_field", F["DP1"], F["DELP"])
+            self.dyn_core(mdt, n_split)
+            if hord_tr:
+                self.tracer_2d(hord_tr)
+            self.all("lagrangian_to_eulerian", last, kord_mt, kord_wz, kord_tm, int(hord_tr != 0), kord_tr)
+            if last and nf_omega > 0:
+                self.del2_cubed("OMGA", 0.18 * self.case.tiles[0].da_min, nf_omega)
+
     def tracer_2d(self, hord):
         """tracer_2d_1L (model/fv_tracer2d.F90:49-295; nq = 1, trdm = 0, id_divg_mean = 0) on the oracle side: the pointwise
         statements in NumPy with the reference's operation order, the fluxes from the oracle's fv_tp_2d, the q halo updates

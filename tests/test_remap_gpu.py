@@ -117,3 +117,33 @@ def test_k_split_loop_dyn_core_and_remap():
     u = gc.eng[1].get("U")
     assert np.isfinite(u).all() and np.abs(u).max() < 60.0
     oc.close(); gc.close()
+
+
+@pytest.mark.parametrize("hord_tr", [0, 8])
+def test_fv_dynamics_step_matches_the_oracle(hord_tr):
+    """fv3_fv_dynamics (fv_dynamics.F90:303-662, dry adiabatic subset): T -> theta_v, two k_split iterations of {dyn_core with two
+    acoustic substeps, tracer_2d, vertical remap}, omega filter, T out -- one C call against the same sequence of oracle stages."""
+    case = H.Case(N, NPZ, "A", state="baroclinic")
+    oc, gc = H.OracleCube(case), H.CudaCube(case)
+    rng = np.random.default_rng(5)
+    kappa = case.consts["kappa"]
+    for t in oc.tiles:        # the initial state carries theta: make it a temperature, as fv_dynamics expects on entry
+        eo = oc.eng[t]
+        pt, delp = eo.get("PT"), eo.get("DELP")
+        p = case.ak[0] + np.cumsum(delp, axis=0) - 0.5 * delp
+        eo.put("PT", pt * p ** kappa)
+        q = eo.get("WORK_Q"); q[...] = rng.uniform(0.0, 1.0, q.shape); eo.put("WORK_Q", q)
+        for f in ("PT", "WORK_Q"):
+            gc.eng[t].put(f, eo.get(f))
+    oc.fv_dynamics(1800.0, 2, 2, 9, 9, -9, 9, hord_tr, 1)
+    gc.fv_dynamics(1800.0, 2, 2, 9, 9, -9, 9, hord_tr, 1)
+    reg = _regions(case.bounds)
+    if not hord_tr:
+        reg.pop("WORK_Q")
+    for t in oc.tiles:
+        res = H.compare(oc.eng[t], gc.eng[t], reg)
+        _assert({k: v for k, v in res.items() if k not in ("W", "OMGA")}, 1e-9)
+        _assert({k: res[k] for k in ("W", "OMGA")}, 1e-5)      # (see test_k_split_loop_dyn_core_and_remap)
+    T = H.sub(gc.eng[1], "PT", gc.eng[1].get("PT"), 1, N, 1, N)
+    assert 150.0 < T.min() and T.max() < 350.0                  # a temperature again
+    oc.close(); gc.close()
