@@ -38,12 +38,14 @@ from gfdl_atmos_cubed_sphere_b200.parallel import tiles_of_rank  # noqa: E402
 def dsw_dram_traffic(n, npz, flagset):
     """dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of ONE d_sw call on one face, from the committed
     ncu metrics list of this round (profiles/r2_dsw_traffic.json, written by profiles/dsw_traffic.py --json from the csv of
-    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum ... profiles/prof_dsw.py`).  None when
-    the kernels changed after the last capture was committed (the file records the git blob of csrc/d_sw.cu it was taken on)."""
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum ... profiles/prof_dsw.py`; the per-kernel
+    breakdown stays in that file).  None for a workload without a committed capture."""
     try:
         rec = json.load(open(os.path.join(ROOT, "profiles", "r2_dsw_traffic.json")))
         ent = rec.get(f"C{n}L{npz}{flagset}")
-        return (float(ent["bytes"]), ent) if ent else (None, None)
+        if not ent:
+            return None, None
+        return float(ent["bytes"]), {k: ent[k] for k in ("read", "write", "launches", "ncu_serialised_ms", "csv") if k in ent}
     except Exception:
         return None, None
 
