@@ -26,6 +26,42 @@ static double extrap_corner(const double p0[2], const Grid& g, int i1, int j1, i
   return q1 + x1 / (x2 - x1) * (q1 - q2);
 }
 
+// a2b_edge.F90:329-450 a2b_ord2 (replace absent / false): A-grid -> cell corners (is:ie+1, js:je+1), second order
+void a2b_ord2(V2 qin, V2 qout, const Grid& g, const Bd& bd) {
+  const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je, npx = bd.npx, npy = bd.npy;
+  const double r3 = 1. / 3.;
+  if (bd.grid_type < 3 && !bd.bounded_domain) {
+    const int is1 = std::max(1, is - 1), js1 = std::max(1, js - 1), is2 = std::max(2, is), js2 = std::max(2, js);
+    const int ie1 = std::min(npx - 1, ie + 1), je1 = std::min(npy - 1, je + 1);
+    L1 q1(is - 1, ie + 1), q2(js - 1, je + 1);
+    for (int j = js2; j <= je1; j++)
+      for (int i = is2; i <= ie1; i++) qout(i, j) = 0.25 * (qin(i - 1, j - 1) + qin(i, j - 1) + qin(i - 1, j) + qin(i, j));
+    if (bd.sw_corner) qout(1, 1) = r3 * (qin(1, 1) + qin(1, 0) + qin(0, 1));
+    if (bd.se_corner) qout(npx, 1) = r3 * (qin(npx - 1, 1) + qin(npx - 1, 0) + qin(npx, 1));
+    if (bd.ne_corner) qout(npx, npy) = r3 * (qin(npx - 1, npy - 1) + qin(npx, npy - 1) + qin(npx - 1, npy));
+    if (bd.nw_corner) qout(1, npy) = r3 * (qin(1, npy - 1) + qin(0, npy - 1) + qin(1, npy));
+    if (is == 1) {
+      for (int j = js1; j <= je1; j++) q2(j) = 0.5 * (qin(0, j) + qin(1, j));
+      for (int j = js2; j <= je1; j++) qout(1, j) = g.edge_w[j - 1] * q2(j - 1) + (1. - g.edge_w[j - 1]) * q2(j);
+    }
+    if (ie + 1 == npx) {
+      for (int j = js1; j <= je1; j++) q2(j) = 0.5 * (qin(npx - 1, j) + qin(npx, j));
+      for (int j = js2; j <= je1; j++) qout(npx, j) = g.edge_e[j - 1] * q2(j - 1) + (1. - g.edge_e[j - 1]) * q2(j);
+    }
+    if (js == 1) {
+      for (int i = is1; i <= ie1; i++) q1(i) = 0.5 * (qin(i, 0) + qin(i, 1));
+      for (int i = is2; i <= ie1; i++) qout(i, 1) = g.edge_s[i - 1] * q1(i - 1) + (1. - g.edge_s[i - 1]) * q1(i);
+    }
+    if (je + 1 == npy) {
+      for (int i = is1; i <= ie1; i++) q1(i) = 0.5 * (qin(i, npy - 1) + qin(i, npy));
+      for (int i = is2; i <= ie1; i++) qout(i, npy) = g.edge_n[i - 1] * q1(i - 1) + (1. - g.edge_n[i - 1]) * q1(i);
+    }
+  } else {
+    for (int j = js; j <= je + 1; j++)
+      for (int i = is; i <= ie + 1; i++) qout(i, j) = 0.25 * (qin(i - 1, j - 1) + qin(i, j - 1) + qin(i - 1, j) + qin(i, j));
+  }
+}
+
 void a2b_ord4(V2 qin, V2 qout, const Grid& g, const Bd& bd, bool replace) {
   const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je, ng = bd.ng, npx = bd.npx, npy = bd.npy;
   const double c1 = 2. / 3., c2 = -1. / 6.;

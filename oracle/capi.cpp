@@ -25,6 +25,8 @@ struct fv3o_ctx {
   std::vector<double> damp_vt; std::vector<int> nord_v;
   // Rayleigh damping table of nh_utils (SAVEd rff, k_rf, RFw_initialized, nh_utils.F90:53-55)
   std::vector<double> rff; int k_rf = 0; bool rf_init = false;
+  // external-mode damping term divg2(is:ie+1, js:je+1) of the current substep (dyn_core.F90:828-847; empty: d_ext = 0)
+  std::vector<double> divg2;
   explicit fv3o_ctx(const fv3_bounds_t& b_, const fv3_grid_t& g_, const fv3_flags_t& f_) : b(b_), g(g_), f(f_) {}
 };
 
@@ -309,10 +311,39 @@ int fv3o_gz_from_zh(fv3o_ctx* c) {
   return 0;
 }
 // dyn_core.F90:1028 split_p_grad / :1019 grad1_p_update (beta > 0): beta_d = 0 on the first substep of a call (:404-406)
+// d_ext > 0 (external-mode divergence damping, hydrostatic branch): before d_sw the corner values of delp (a2b_ord2, :745-747; kept
+// in ptc as the reference does after d_sw, :791-797 -- d_sw does not read ptc here) ...
+int fv3o_ext_mode_prepare(fv3o_ctx* c) {
+  Bd bd(c->b); Grid g(c->g, bd);
+  V3 delp = F3(c, FV3_DELP), ptc = F3(c, FV3_PTC);
+#pragma omp parallel for schedule(static)
+  for (int k = 1; k <= bd.npz; k++) {
+    L2 wk(bd.isd, bd.ied, bd.jsd, bd.jed);
+    a2b_ord2(delp.k(k), wk, g, bd);
+    for (int j = bd.js; j <= bd.je + 1; j++) for (int i = bd.is; i <= bd.ie + 1; i++) ptc(i, j, k) = wk(i, j);
+  }
+  return 0;
+}
+// ... and after d_sw the mass-weighted vertical mean of the divergence d_sw left in vt (:828-847)
+int fv3o_ext_mode_divg2(fv3o_ctx* c) {
+  Bd bd(c->b);
+  V3 ptc = F3(c, FV3_PTC), vt = F3(c, FV3_VT);
+  const int nd = bd.ie - bd.is + 2;
+  c->divg2.assign((size_t)nd * (bd.je - bd.js + 2), 0.);
+  const double d2_divg = c->f.d_ext * c->g.da_min_c;
+  for (int j = bd.js; j <= bd.je + 1; j++)
+    for (int i = bd.is; i <= bd.ie + 1; i++) {
+      double wk = ptc(i, j, 1), d = wk * vt(i, j, 1);
+      for (int k = 2; k <= bd.npz; k++) { wk = wk + ptc(i, j, k); d = d + ptc(i, j, k) * vt(i, j, k); }
+      c->divg2[(i - bd.is) + (size_t)(j - bd.js) * nd] = d2_divg * d / wk;
+    }
+  return 0;
+}
 int fv3o_split_p_grad(fv3o_ctx* c, double dt, double beta_d) {
   Bd bd(c->b); Grid g(c->g, bd);
+  const double* d2 = (c->f.d_ext > 0. && !c->divg2.empty()) ? c->divg2.data() : nullptr;
   if (c->f.hydrostatic)
-    grad1_p_update(F3(c, FV3_U), F3(c, FV3_V), F3(c, FV3_PKC), F3(c, FV3_GZ), F3(c, FV3_DU), F3(c, FV3_DV), dt, g, bd, bd.npz, c->f.ptop, c->f.kappa, beta_d);
+    grad1_p_update(F3(c, FV3_U), F3(c, FV3_V), F3(c, FV3_PKC), F3(c, FV3_GZ), F3(c, FV3_DU), F3(c, FV3_DV), dt, g, bd, bd.npz, c->f.ptop, c->f.kappa, beta_d, d2);
   else
     split_p_grad(F3(c, FV3_U), F3(c, FV3_V), F3(c, FV3_PKC), F3(c, FV3_GZ), F3(c, FV3_DELP), F3(c, FV3_PK3), F3(c, FV3_DU), F3(c, FV3_DV), beta_d, dt,
                  g, bd, bd.npz, c->f.use_logp != 0, c->f.ptop, c->f.kappa);
@@ -345,8 +376,9 @@ int fv3o_pk_from_pkc(fv3o_ctx* c) {
 // dyn_core.F90:1909 one_grad_p (hydrostatic call :1019-1021, d_ext = 0)
 int fv3o_one_grad_p(fv3o_ctx* c, double dt) {
   Bd bd(c->b); Grid g(c->g, bd);
+  const double* d2 = (c->f.d_ext > 0. && !c->divg2.empty()) ? c->divg2.data() : nullptr;
   one_grad_p(F3(c, FV3_U), F3(c, FV3_V), F3(c, FV3_PKC), F3(c, FV3_GZ), F3(c, FV3_DELP), dt, g, bd, bd.npz, c->f.ptop, c->f.kappa,
-             c->f.hydrostatic != 0);
+             c->f.hydrostatic != 0, d2);
   return 0;
 }
 // dyn_core.F90:2356 del2_cubed on one field (FV3_HEAT: :1303 with cd = 0.20 da_min, nmax = min(3, nord+1); FV3_OMGA:

@@ -198,6 +198,7 @@ void fv_tp_2d(V2 q, V2 crx, V2 cry, int npx, int npy, int hord, V2 fx, V2 fy, V2
 // ---- a2b_edge.F90 ----
 double great_circle_dist(const double q1[2], const double q2[2], double radius);
 void a2b_ord4(V2 qin, V2 qout, const Grid& g, const Bd& bd, bool replace);
+void a2b_ord2(V2 qin, V2 qout, const Grid& g, const Bd& bd);
 void a2b_ord2(V2 qin, V2 qout, const Grid& g, const Bd& bd, bool replace);
 
 // ---- fv_mp_mod.F90 fill_corners ----
@@ -262,9 +263,10 @@ void geopk(double ptop, double* pe, double* peln, V3 delp, V3 pk, V3 gz, V2 hs, 
            double cp_air, bool CG, bool use_cond, const Bd& bd);
 void split_p_grad(V3 u, V3 v, V3 pp, V3 gz, V3 delp, V3 pk, V3 du, V3 dv, double beta, double dt, const Grid& g, const Bd& bd, int npz,
                   bool use_logp, double ptop, double akap);
-void grad1_p_update(V3 u, V3 v, V3 pk, V3 gz, V3 du, V3 dv, double dt, const Grid& g, const Bd& bd, int npz, double ptop, double akap, double beta);
+void grad1_p_update(V3 u, V3 v, V3 pk, V3 gz, V3 du, V3 dv, double dt, const Grid& g, const Bd& bd, int npz, double ptop, double akap, double beta,
+                    const double* divg2 = nullptr);
 void one_grad_p(V3 u, V3 v, V3 pk, V3 gz, V3 delp, double dt, const Grid& g, const Bd& bd, int npz, double ptop, double akap,
-                bool hydrostatic);
+                bool hydrostatic, const double* divg2 = nullptr);
 void pln_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed, int npz, double ptop, V3 pk3, V3 delp);
 void pk3_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed, int npz, double ptop,
               double akap, V3 pk3, V3 delp);

@@ -579,8 +579,12 @@ void split_p_grad(V3 u, V3 v, V3 pp, V3 gz, V3 delp, V3 pk, V3 du, V3 dv, double
 }
 
 // dyn_core.F90:2033-2116 grad1_p_update (beta > 0, hydrostatic), d_ext = 0 (divg2 = 0, dyn_core.F90:745-747)
-void grad1_p_update(V3 u, V3 v, V3 pk, V3 gz, V3 du, V3 dv, double dt, const Grid& g, const Bd& bd, int npz, double ptop, double akap, double beta) {
+void grad1_p_update(V3 u, V3 v, V3 pk, V3 gz, V3 du, V3 dv, double dt, const Grid& g, const Bd& bd, int npz, double ptop, double akap, double beta,
+                    const double* divg2) {
   const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je, isd = bd.isd, ied = bd.ied, jsd = bd.jsd, jed = bd.jed;
+  // divg2(is:ie+1, js:je+1): the external-mode damping term of dyn_core.F90:828-847 (nullptr: d_ext = 0, divg2 = 0)
+  const int nd = ie - is + 2;
+  auto D2 = [&](int i, int j) { return divg2 ? divg2[(i - is) + (size_t)(j - js) * nd] : 0.; };
   const double alpha = 1. - beta, top_value = std::pow(ptop, akap);
   for (int j = js; j <= je + 1; j++) for (int i = is; i <= ie + 1; i++) pk(i, j, 1) = top_value;
 #pragma omp parallel for schedule(static)
@@ -597,7 +601,7 @@ void grad1_p_update(V3 u, V3 v, V3 pk, V3 gz, V3 du, V3 dv, double dt, const Gri
         du(i, j, k) = dt / (wk(i, j) + wk(i + 1, j)) *
                       ((gz(i, j, k + 1) - gz(i + 1, j, k)) * (pk(i + 1, j, k + 1) - pk(i, j, k)) +
                        (gz(i, j, k) - gz(i + 1, j, k + 1)) * (pk(i, j, k + 1) - pk(i + 1, j, k)));
-        u(i, j, k) = (u(i, j, k) + 0. - 0. + alpha * du(i, j, k)) * g.rdx(i, j);
+        u(i, j, k) = (u(i, j, k) + D2(i, j) - D2(i + 1, j) + alpha * du(i, j, k)) * g.rdx(i, j);
       }
     for (int j = js; j <= je; j++)
       for (int i = is; i <= ie + 1; i++) {
@@ -605,15 +609,17 @@ void grad1_p_update(V3 u, V3 v, V3 pk, V3 gz, V3 du, V3 dv, double dt, const Gri
         dv(i, j, k) = dt / (wk(i, j) + wk(i, j + 1)) *
                       ((gz(i, j, k + 1) - gz(i, j + 1, k)) * (pk(i, j + 1, k + 1) - pk(i, j, k)) +
                        (gz(i, j, k) - gz(i, j + 1, k + 1)) * (pk(i, j, k + 1) - pk(i, j + 1, k)));
-        v(i, j, k) = (v(i, j, k) + 0. - 0. + alpha * dv(i, j, k)) * g.rdy(i, j);
+        v(i, j, k) = (v(i, j, k) + D2(i, j) - D2(i, j + 1) + alpha * dv(i, j, k)) * g.rdy(i, j);
       }
   }
 }
 
-// dyn_core.F90:1909-2030 one_grad_p, d_ext = 0 (wk1 = wk2 = 0)
+// dyn_core.F90:1909-2030 one_grad_p; divg2 (nullable: d_ext = 0, wk1 = wk2 = 0) is the external-mode damping term (:1969-1984)
 void one_grad_p(V3 u, V3 v, V3 pk, V3 gz, V3 delp, double dt, const Grid& g, const Bd& bd, int npz, double ptop, double akap,
-                bool hydrostatic) {
+                bool hydrostatic, const double* divg2) {
   const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je, isd = bd.isd, ied = bd.ied, jsd = bd.jsd, jed = bd.jed;
+  const int nd = ie - is + 2;
+  auto D2 = [&](int i, int j) { return divg2 ? divg2[(i - is) + (size_t)(j - js) * nd] : 0.; };
   const double top_value = hydrostatic ? std::pow(ptop, akap) : ptop;
   for (int j = js; j <= je + 1; j++) for (int i = is; i <= ie + 1; i++) pk(i, j, 1) = top_value;
 #pragma omp parallel for schedule(static)
@@ -627,12 +633,12 @@ void one_grad_p(V3 u, V3 v, V3 pk, V3 gz, V3 delp, double dt, const Grid& g, con
     else a2b_ord4(delp.k(k), wk, g, bd, false);
     for (int j = js; j <= je + 1; j++)
       for (int i = is; i <= ie; i++)
-        u(i, j, k) = g.rdx(i, j) * (0. + u(i, j, k) + dt / (wk(i, j) + wk(i + 1, j)) *
+        u(i, j, k) = g.rdx(i, j) * ((D2(i, j) - D2(i + 1, j)) + u(i, j, k) + dt / (wk(i, j) + wk(i + 1, j)) *
                                     ((gz(i, j, k + 1) - gz(i + 1, j, k)) * (pk(i + 1, j, k + 1) - pk(i, j, k)) +
                                      (gz(i, j, k) - gz(i + 1, j, k + 1)) * (pk(i, j, k + 1) - pk(i + 1, j, k))));
     for (int j = js; j <= je; j++)
       for (int i = is; i <= ie + 1; i++)
-        v(i, j, k) = g.rdy(i, j) * (0. + v(i, j, k) + dt / (wk(i, j) + wk(i, j + 1)) *
+        v(i, j, k) = g.rdy(i, j) * ((D2(i, j) - D2(i, j + 1)) + v(i, j, k) + dt / (wk(i, j) + wk(i, j + 1)) *
                                     ((gz(i, j, k + 1) - gz(i, j + 1, k)) * (pk(i, j + 1, k + 1) - pk(i, j, k)) +
                                      (gz(i, j, k) - gz(i, j + 1, k + 1)) * (pk(i, j, k + 1) - pk(i, j + 1, k))));
   }
