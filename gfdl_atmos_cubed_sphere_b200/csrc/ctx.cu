@@ -254,7 +254,7 @@ void fv3_destroy(fv3_ctx* c) {
   for (auto p : alts) cudaFree(p);
   for (int i = 0; i < fv3_ctx::NSCR; i++) cudaFree(c->scr[i]);
   for (auto p : c->metric_alloc) cudaFree(p);
-  cudaFree(c->d_stage); cudaFree(c->d_kint); cudaFree(c->d_kdbl); cudaFree(c->d_dp_ref); cudaFree(c->d_edge_tab); cudaFree(c->d_rff); cudaFree(c->d_akbk);
+  cudaFree(c->d_stage); cudaFree(c->d_kint); cudaFree(c->d_kdbl); cudaFree(c->d_dp_ref); cudaFree(c->d_edge_tab); cudaFree(c->d_rff); cudaFree(c->d_akbk); cudaFree(c->d_divg2);
   for (auto& kv : c->timers) { cudaEventDestroy(kv.second.e0); cudaEventDestroy(kv.second.e1); }
   cudaStreamDestroy(c->stream);
   delete c;
@@ -377,6 +377,8 @@ int fv3_pe_halo(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_pe_halo(c); if (r
 int fv3_gz_from_zh(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_gz_from_zh(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_nh_p_grad(fv3_ctx* c, double dt) { STAGE_PROLOGUE(c) int rc = stage_nh_p_grad(c, dt); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_del2_cubed(fv3_ctx* c, int field, double cd, int nmax) { STAGE_PROLOGUE(c) int rc = stage_del2_cubed(c, field, cd, nmax); if (rc) return rc; STAGE_EPILOGUE(c) }
+int fv3_ext_mode_prepare(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_ext_mode_prepare(c); if (rc) return rc; STAGE_EPILOGUE(c) }
+int fv3_ext_mode_divg2(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_ext_mode_divg2(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_remap_work_q(fv3_ctx* c, int mode, int iv, int kord, double qmin) { STAGE_PROLOGUE(c) int rc = stage_remap_work_q(c, mode, iv, kord, qmin); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr) {
   STAGE_PROLOGUE(c) int rc = stage_lagrangian_to_eulerian(c, last_step, kord_mt, kord_wz, kord_tm, use_tracer, kord_tr); if (rc) return rc; STAGE_EPILOGUE(c)

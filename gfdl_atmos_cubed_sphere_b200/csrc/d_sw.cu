@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_damp(Lay L, DevGrid G, const dou
                                                     const double* __restrict__ dg_even, const double* __restrict__ dg_odd,
                                                     const double* __restrict__ vortb, double* __restrict__ ke,
                                                     double* __restrict__ dterm, const int* kint, const double* kdbl, double dt, double dddmp,
-                                                    double d4_bg, int stretched) {
+                                                    double d4_bg, int stretched, double* __restrict__ delpc_out) {
   PLANE_IJK
   if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
   const int npx = L.npx, npy = L.npy;
@@ -488,8 +488,10 @@ __global__ void __launch_bounds__(TI* TJ) k_dsw_damp(Lay L, DevGrid G, const dou
     dpc = G2(rarea_c, i, j) * dpc;
     const double damp = G.da_min_c * fmax(d2_bg, fmin(0.20, dddmp * fabs(dpc * dt)));
     term = damp * dpc;
+    if (delpc_out) delpc_out[o] = dpc;   // d_sw's delpc output (sw_core.F90:1366), read by the external-mode damping (d_ext > 0)
   } else {
     const double dpc = __ldg(divg_in + o);   // delpc = divg_d saved before the loop (:1376-1381)
+    if (delpc_out) delpc_out[o] = dpc;
     double vo = 0.;
     if (dddmp >= 1.E-5) {
       const double vb = __ldg(vortb + o);
@@ -1233,7 +1235,7 @@ int stage_d_sw(fv3_ctx* c, double dt) {
   }
   k_dsw_damp<<<grd, blk, 0, st>>>(L, c->G, u, v, c->fld[FV3_UA], c->fld[FV3_VA], uc, vc, c->fld[FV3_DIVGD], dg_even, dg_odd, vortb, ke,
                                   (f.d_con > 1.e-5 || f.do_diss_est) ? dterm : nullptr,
-                                  c->d_kint, c->d_kdbl, dt, f.dddmp, f.d4_bg, c->b.stretched_grid);
+                                  c->d_kint, c->d_kdbl, dt, f.dddmp, f.d4_bg, c->b.stretched_grid, f.d_ext > 0. ? c->fld[FV3_VT] : nullptr);
   c->launches++;
   // --- vorticity transport and momentum update (:1476-1509), fused
   if (fuse4) {

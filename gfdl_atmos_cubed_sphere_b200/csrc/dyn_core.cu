@@ -163,10 +163,9 @@ static int dyn_core_direct(fv3_ctx** ctxs, int nctx, double bdt, int n_split) {
     // beta > 0: split_p_grad / grad1_p_update; beta < -0.1 selects one_grad_p in the non-hydrostatic branch (:1029-1030), not built
     if (fa.beta != f0.beta) return fv3_fail(ctxs[a], -1, "dyn_core: the linked contexts disagree on beta");
     if (fa.beta < 0.0) return fv3_fail(ctxs[a], -2, "dyn_core: beta < 0 (one_grad_p in the non-hydrostatic branch) not supported");
-    // d_ext > 0 builds divg2 (dyn_core.F90:745-747, 791-797, 828-845), which only one_grad_p reads (:1021, :1030): with nh_p_grad
-    // (non-hydrostatic, beta = 0) it has no effect on any result and is accepted; the hydrostatic use is not built
-    if (ctxs[a]->f.d_ext > 0.0 && ctxs[a]->f.hydrostatic)
-      return fv3_fail(ctxs[a], -2, "dyn_core: d_ext > 0 with the hydrostatic one_grad_p (external-mode damping) not supported");
+    // d_ext > 0 builds divg2 (dyn_core.F90:745-747, 791-797, 828-845), which only one_grad_p / grad1_p_update read (:1019-1021, :1030):
+    // with nh_p_grad (non-hydrostatic, beta = 0) it has no effect on any result and is skipped; the hydrostatic branch builds it
+    if (fa.d_ext != f0.d_ext) return fv3_fail(ctxs[a], -1, "dyn_core: the linked contexts disagree on d_ext");
   }
   const double dt = bdt / (double)n_split;   // dyn_core.F90:223
   const double dt2 = 0.5 * dt;
@@ -204,7 +203,10 @@ static int dyn_core_direct(fv3_ctx** ctxs, int nctx, double bdt, int n_split) {
       FORALL(stage_geopk(c, 1))
       FORALL(stage_p_grad_c(c, dt2))
       if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DIVGD_UCVC))) return rc;
+      const bool ext_mode = ctxs[0]->f.d_ext > 0.;                                        // external-mode divergence damping
+      if (ext_mode) { FORALL(stage_ext_mode_prepare(c)) }                                 // :745-747
       FORALL(stage_d_sw(c, dt))
+      if (ext_mode) { FORALL(stage_ext_mode_divg2(c)) }                                   // :828-847
       if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;
       FORALL(stage_geopk(c, 0))
       if (last_step) { FORALL(stage_copy_field(c, FV3_PK, FV3_PKC)) }   // :1001-1010: remap_step .and. hydrostatic: pk = pkc

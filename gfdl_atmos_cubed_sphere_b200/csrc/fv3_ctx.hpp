@@ -136,6 +136,7 @@ struct fv3_ctx {
   int* d_kint; double* d_kdbl;     // device copies of per-k coefficient tables
   double* d_dp_ref;                // dp_ref(npz)  dyn_core.F90:242-244
   double* d_edge_tab;              // edge_profile coefficient tables (nh.cu), built on first use
+  double* d_divg2 = nullptr;       // external-mode damping term (d_ext > 0), one plane, built on first use
   double* d_akbk = nullptr;        // ak(0:km), bk(0:km) for the vertical remap (remap.cu), built on first use
   double* d_rff = nullptr; int k_rf = 0;   // Rayleigh damping table of the vertical solvers (fast_tau_w_sec > 0), built by the first solver call
   long long launches;
@@ -168,6 +169,8 @@ struct StageScope {
 };
 
 // stage implementations (each enqueues kernels on c->stream)
+int stage_ext_mode_prepare(fv3_ctx* c);
+int stage_ext_mode_divg2(fv3_ctx* c);
 int stage_remap_work_q(fv3_ctx* c, int mode, int iv, int kord, double qmin);
 int stage_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr);
 int stage_fv_tp_2d(fv3_ctx* c, int nk, int hord, int use_mfx, int use_mass, int nord, double damp_c);

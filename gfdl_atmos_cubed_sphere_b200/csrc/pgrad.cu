@@ -350,12 +350,15 @@ int stage_nh_p_grad(fv3_ctx* c, double dt, double beta_d) {
 template <bool GRAD1>
 __global__ void __launch_bounds__(TI* TJ) k_one_grad_p(Lay L, DevGrid G, const double* __restrict__ pk, const double* __restrict__ gz,
                                                       double* __restrict__ u, double* __restrict__ v, double* __restrict__ du,
-                                                      double* __restrict__ dv, double beta, double dt) {
+                                                      double* __restrict__ dv, double beta, double dt, const double* __restrict__ divg2) {
   PLANE_IJK
   if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
   const long long P = L.plane;
-  const long long o = ko + LIDX(L, i, j);
+  const int o2 = LIDX(L, i, j);
+  const long long o = ko + o2;
   const double alpha = 1. - beta;
+  // external-mode damping (d_ext > 0, dyn_core.F90:1969-1984 / :2102, 2111): differences of the 2-D corner field divg2
+  const double d0 = divg2 ? __ldg(divg2 + o2) : 0.;
   auto WK = [&](long long oo) { return __ldg(pk + oo + P) - __ldg(pk + oo); };
   if (i <= L.ie) {
     const long long e = o + 1;
@@ -365,8 +368,12 @@ __global__ void __launch_bounds__(TI* TJ) k_one_grad_p(Lay L, DevGrid G, const d
     if (GRAD1) {
       const double u1 = u[o] + beta * du[o];
       du[o] = d1;
-      u[o] = (u1 + 0. - 0. + alpha * d1) * G2(rdx, i, j);
-    } else u[o] = G2(rdx, i, j) * (0. + u[o] + d1);
+      const double dE = divg2 ? __ldg(divg2 + o2 + 1) : 0.;
+      u[o] = (u1 + d0 - dE + alpha * d1) * G2(rdx, i, j);
+    } else {
+      const double wk2 = divg2 ? d0 - __ldg(divg2 + o2 + 1) : 0.;
+      u[o] = G2(rdx, i, j) * (wk2 + u[o] + d1);
+    }
   }
   if (j <= L.je) {
     const long long n = o + L.NI;
@@ -376,8 +383,12 @@ __global__ void __launch_bounds__(TI* TJ) k_one_grad_p(Lay L, DevGrid G, const d
     if (GRAD1) {
       const double v1 = v[o] + beta * dv[o];
       dv[o] = d1;
-      v[o] = (v1 + 0. - 0. + alpha * d1) * G2(rdy, i, j);
-    } else v[o] = G2(rdy, i, j) * (0. + v[o] + d1);
+      const double dN = divg2 ? __ldg(divg2 + o2 + L.NI) : 0.;
+      v[o] = (v1 + d0 - dN + alpha * d1) * G2(rdy, i, j);
+    } else {
+      const double wk1 = divg2 ? d0 - __ldg(divg2 + o2 + L.NI) : 0.;
+      v[o] = G2(rdy, i, j) * (wk1 + v[o] + d1);
+    }
   }
 }
 __global__ void __launch_bounds__(TI* TJ) k_set_top(Lay L, double* __restrict__ pkb, double top_value) {
@@ -392,7 +403,11 @@ int stage_one_grad_p(fv3_ctx* c, double dt, double beta_d) {
   const Lay& L = c->L;
   const int km = L.npz;
   if (!c->f.hydrostatic) return fv3_fail(c, -2, "one_grad_p: only the hydrostatic call is supported (non-hydrostatic uses nh_p_grad)");
-  if (c->f.d_ext > 0.0) return fv3_fail(c, -2, "one_grad_p: d_ext > 0 not supported");
+  const double* divg2 = nullptr;
+  if (c->f.d_ext > 0.0) {
+    if (!c->d_divg2) return fv3_fail(c, -1, "one_grad_p: d_ext > 0 needs fv3_ext_mode_prepare / fv3_ext_mode_divg2 around d_sw of this substep");
+    divg2 = c->d_divg2;
+  }
   double *pkb = c->scr[1], *gzb = c->scr[2];
   const long long P = L.plane;
   dim3 blk(TI, TJ);
@@ -405,8 +420,73 @@ int stage_one_grad_p(fv3_ctx* c, double dt, double beta_d) {
     const int nks[2] = {km, km + 1};
     if ((rc = launch_a2b_ord4_batch(c, 2, qin, qout, nks, 4))) return rc;
   }
-  if (beta_d >= 0.) k_one_grad_p<true><<<plane_grid(L, km), blk, 0, c->stream>>>(L, c->G, pkb, gzb, c->fld[FV3_U], c->fld[FV3_V], c->fld[FV3_DU], c->fld[FV3_DV], beta_d, dt);
-  else k_one_grad_p<false><<<plane_grid(L, km), blk, 0, c->stream>>>(L, c->G, pkb, gzb, c->fld[FV3_U], c->fld[FV3_V], nullptr, nullptr, 0., dt);
+  if (beta_d >= 0.) k_one_grad_p<true><<<plane_grid(L, km), blk, 0, c->stream>>>(L, c->G, pkb, gzb, c->fld[FV3_U], c->fld[FV3_V], c->fld[FV3_DU], c->fld[FV3_DV], beta_d, dt, divg2);
+  else k_one_grad_p<false><<<plane_grid(L, km), blk, 0, c->stream>>>(L, c->G, pkb, gzb, c->fld[FV3_U], c->fld[FV3_V], nullptr, nullptr, 0., dt, divg2);
+  c->launches++;
+  return 0;
+}
+
+// ---- external-mode divergence damping (d_ext > 0; hydrostatic branch of dyn_core) -----------------------------------------
+// a2b_edge.F90:329-450 a2b_ord2 (no replace): A-grid -> cell corners (is:ie+1, js:je+1), all levels in one launch
+__global__ void __launch_bounds__(TI* TJ) k_a2b_ord2(Lay L, DevGrid G, const double* __restrict__ qin, double* __restrict__ qout) {
+  PLANE_IJK
+  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
+  const int npx = L.npx, npy = L.npy;
+  const long long o = ko + LIDX(L, i, j);
+  auto Q = [&](int ii, int jj) { return __ldg(qin + ko + LIDX(L, ii, jj)); };
+  const double r3 = 1. / 3.;
+  double out;
+  if (!L.cube) out = 0.25 * (Q(i - 1, j - 1) + Q(i, j - 1) + Q(i - 1, j) + Q(i, j));
+  else if (i == 1 && j == 1) out = r3 * (Q(1, 1) + Q(1, 0) + Q(0, 1));
+  else if (i == npx && j == 1) out = r3 * (Q(npx - 1, 1) + Q(npx - 1, 0) + Q(npx, 1));
+  else if (i == npx && j == npy) out = r3 * (Q(npx - 1, npy - 1) + Q(npx, npy - 1) + Q(npx - 1, npy));
+  else if (i == 1 && j == npy) out = r3 * (Q(1, npy - 1) + Q(0, npy - 1) + Q(1, npy));
+  else if (i == 1 || i == npx) {
+    const int ia = i == 1 ? 0 : npx - 1;
+    const double ew = __ldg((i == 1 ? G.edge_w : G.edge_e) + j - 1);
+    const double qa = 0.5 * (Q(ia, j - 1) + Q(ia + 1, j - 1)), qb = 0.5 * (Q(ia, j) + Q(ia + 1, j));
+    out = ew * qa + (1. - ew) * qb;
+  } else if (j == 1 || j == npy) {
+    const int ja = j == 1 ? 0 : npy - 1;
+    const double es = __ldg((j == 1 ? G.edge_s : G.edge_n) + i - 1);
+    const double qa = 0.5 * (Q(i - 1, ja) + Q(i - 1, ja + 1)), qb = 0.5 * (Q(i, ja) + Q(i, ja + 1));
+    out = es * qa + (1. - es) * qb;
+  } else out = 0.25 * (Q(i - 1, j - 1) + Q(i, j - 1) + Q(i - 1, j) + Q(i, j));
+  qout[o] = out;
+}
+// dyn_core.F90:828-847: divg2 = d_ext * da_min_c * sum_k(dpc * divg) / sum_k(dpc) at the cell corners
+__global__ void __launch_bounds__(TI* TJ) k_ext_divg2(Lay L, const double* __restrict__ dpc, const double* __restrict__ divg, double* __restrict__ divg2,
+                                                      double d2_divg) {
+  const int i = L.isd - FV3_IOFF + blockIdx.x * TI + threadIdx.x;
+  const int j = L.jsd + blockIdx.y * TJ + threadIdx.y;
+  if (i < L.is || i > L.ie + 1 || j < L.js || j > L.je + 1) return;
+  const int o2 = LIDX(L, i, j);
+  double wk = __ldg(dpc + o2), d = wk * __ldg(divg + o2);
+  for (int k = 1; k < L.npz; k++) {
+    const double p = __ldg(dpc + o2 + (long long)k * L.plane);
+    wk = wk + p;
+    d = d + p * __ldg(divg + o2 + (long long)k * L.plane);
+  }
+  divg2[o2] = d2_divg * d / wk;
+}
+// before d_sw (:745-747): delp at the corners -> FV3_PTC (dead between p_grad_c and the next c_sw; the reference parks it there too, :791-797)
+int stage_ext_mode_prepare(fv3_ctx* c) {
+  StageScope ts(c, "EXT_MODE");
+  const Lay& L = c->L;
+  k_a2b_ord2<<<plane_grid(L, L.npz), dim3(TI, TJ), 0, c->stream>>>(L, c->G, c->fld[FV3_DELP], c->fld[FV3_PTC]);
+  c->launches++;
+  return 0;
+}
+// after d_sw, which left its divergence (delpc, sw_core.F90:1366 / :1379) in FV3_VT
+int stage_ext_mode_divg2(fv3_ctx* c) {
+  StageScope ts(c, "EXT_MODE");
+  const Lay& L = c->L;
+  if (!c->d_divg2) {
+    FV3_CUDA(c, cudaMalloc(&c->d_divg2, (size_t)L.plane * sizeof(double)));
+    FV3_CUDA(c, cudaMemsetAsync(c->d_divg2, 0, (size_t)L.plane * sizeof(double), c->stream));   // on the context stream: a legacy-stream memset could land after the kernel below
+  }
+  k_ext_divg2<<<dim3((L.NI + TI - 1) / TI, (L.NJ + TJ - 1) / TJ), dim3(TI, TJ), 0, c->stream>>>(L, c->fld[FV3_PTC], c->fld[FV3_VT], c->d_divg2,
+                                                                                              c->f.d_ext * c->G.da_min_c);
   c->launches++;
   return 0;
 }

@@ -194,7 +194,7 @@ int fv3_gz_from_zh(fv3_ctx *ctx);
 int fv3_nh_p_grad(fv3_ctx *ctx, double dt);
 /* Hydrostatic branch.  dyn_core.F90:2202 geopk: cg != 0 is the C-grid call (dyn_core.F90:478-480: delpc, ptc -> pkc, gz,
  * pe, peln), cg == 0 the D-grid call (:905-907: delp, pt -> pkc, gz, pe, peln, pkz).  dyn_core.F90:1909 one_grad_p
- * (call :1019-1021, d_ext = 0): a2b_ord4 of pkc, gz and the D-grid pressure-gradient update of u, v. */
+ * (call :1019-1021): a2b_ord4 of pkc, gz and the D-grid pressure-gradient update of u, v (+ the d_ext term, see fv3_ext_mode_*). */
 /* del2_cubed (dyn_core.F90:2356-2465) on FV3_HEAT or FV3_OMGA; the halo of the field must be current (fv3_halo_exchange with
  * FV3_HALO_HEAT / FV3_HALO_OMGA, or fv3_del2_cubed_cube which does both).  nmax passes (at most 3). */
 int fv3_del2_cubed(fv3_ctx *ctx, int field, double cd, int nmax);
@@ -210,6 +210,12 @@ int fv3_pt_to_theta(fv3_ctx *ctx, double zvir);
  * scalar_profile), kord_wz > 0; everything else returns -2.  kord_tm < 0: T_v is mapped in log p (map_scalar), > 0: theta_v in p.
  * fv3_remap_work_q: the column operators alone on FV3_WORK_Q, from the layers of FV3_PE to the hybrid levels -- mode 0 map_scalar
  * (fv_operators.F90:40), 1 map1_ppm (:137; iv = -2 takes its lower boundary value from FV3_WS), 2 map1_q2 (:352). */
+/* External-mode divergence damping, flags.d_ext > 0 (0.02 by default in non-SW builds), hydrostatic branch (dyn_core.F90:745-747,
+ * 791-797, 828-847, 1969-1984): fv3_ext_mode_prepare before fv3_d_sw (delp at the cell corners, a2b_ord2), fv3_ext_mode_divg2 after it
+ * (mass-weighted vertical mean of the divergence d_sw leaves in FV3_VT); fv3_one_grad_p / fv3_split_p_grad then add its
+ * differences to u, v.  fv3_dyn_core does this itself; in the non-hydrostatic beta = 0 path divg2 is read by nothing. */
+int fv3_ext_mode_prepare(fv3_ctx *ctx);
+int fv3_ext_mode_divg2(fv3_ctx *ctx);
 int fv3_lagrangian_to_eulerian(fv3_ctx *ctx, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr);
 int fv3_remap_work_q(fv3_ctx *ctx, int mode, int iv, int kord, double qmin);
 /* dyn_core.F90:1305-1356: filtered heat_source -> pt (levels 1..n_con, limited by delt_max); part of fv3_dyn_core */

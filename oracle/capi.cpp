@@ -26,7 +26,7 @@ struct fv3o_ctx {
   // Rayleigh damping table of nh_utils (SAVEd rff, k_rf, RFw_initialized, nh_utils.F90:53-55)
   std::vector<double> rff; int k_rf = 0; bool rf_init = false;
   // external-mode damping term divg2(is:ie+1, js:je+1) of the current substep (dyn_core.F90:828-847; empty: d_ext = 0)
-  std::vector<double> divg2;
+  std::vector<double> divg2, ext_dpc;   // ext_dpc: delp at the cell corners (is:ie+1, js:je+1, npz), taken before d_sw (:745-747)
   explicit fv3o_ctx(const fv3_bounds_t& b_, const fv3_grid_t& g_, const fv3_flags_t& f_) : b(b_), g(g_), f(f_) {}
 };
 
@@ -311,25 +311,30 @@ int fv3o_gz_from_zh(fv3o_ctx* c) {
   return 0;
 }
 // dyn_core.F90:1028 split_p_grad / :1019 grad1_p_update (beta > 0): beta_d = 0 on the first substep of a call (:404-406)
-// d_ext > 0 (external-mode divergence damping, hydrostatic branch): before d_sw the corner values of delp (a2b_ord2, :745-747; kept
-// in ptc as the reference does after d_sw, :791-797 -- d_sw does not read ptc here) ...
+// d_ext > 0 (external-mode divergence damping, hydrostatic branch): before d_sw the corner values of delp (a2b_ord2, :745-747;
+// the reference parks them in ptc after d_sw, :791-797 -- d_sw uses ptc as scratch, so they wait in a private array here) ...
 int fv3o_ext_mode_prepare(fv3o_ctx* c) {
   Bd bd(c->b); Grid g(c->g, bd);
-  V3 delp = F3(c, FV3_DELP), ptc = F3(c, FV3_PTC);
+  V3 delp = F3(c, FV3_DELP);
+  const int nd = bd.ie - bd.is + 2, md = bd.je - bd.js + 2;
+  c->ext_dpc.assign((size_t)nd * md * bd.npz, 0.);
 #pragma omp parallel for schedule(static)
   for (int k = 1; k <= bd.npz; k++) {
     L2 wk(bd.isd, bd.ied, bd.jsd, bd.jed);
     a2b_ord2(delp.k(k), wk, g, bd);
-    for (int j = bd.js; j <= bd.je + 1; j++) for (int i = bd.is; i <= bd.ie + 1; i++) ptc(i, j, k) = wk(i, j);
+    for (int j = bd.js; j <= bd.je + 1; j++)
+      for (int i = bd.is; i <= bd.ie + 1; i++) c->ext_dpc[(i - bd.is) + (size_t)(j - bd.js) * nd + (size_t)(k - 1) * nd * md] = wk(i, j);
   }
   return 0;
 }
 // ... and after d_sw the mass-weighted vertical mean of the divergence d_sw left in vt (:828-847)
 int fv3o_ext_mode_divg2(fv3o_ctx* c) {
   Bd bd(c->b);
-  V3 ptc = F3(c, FV3_PTC), vt = F3(c, FV3_VT);
-  const int nd = bd.ie - bd.is + 2;
-  c->divg2.assign((size_t)nd * (bd.je - bd.js + 2), 0.);
+  V3 vt = F3(c, FV3_VT);
+  const int nd = bd.ie - bd.is + 2, md = bd.je - bd.js + 2;
+  if (c->ext_dpc.size() != (size_t)nd * md * bd.npz) return -1;
+  auto ptc = [&](int i, int j, int k) { return c->ext_dpc[(i - bd.is) + (size_t)(j - bd.js) * nd + (size_t)(k - 1) * nd * md]; };
+  c->divg2.assign((size_t)nd * md, 0.);
   const double d2_divg = c->f.d_ext * c->g.da_min_c;
   for (int j = bd.js; j <= bd.je + 1; j++)
     for (int i = bd.is; i <= bd.ie + 1; i++) {

@@ -237,7 +237,11 @@ class OracleCube:
                 run("GEOPK_C", "geopk", 1)
                 run("PG_C", "p_grad_c", dt2)
                 self.halo("DIVGD_UCVC")
+                if self.case.flags.get("d_ext", 0.0) > 0.0:
+                    self.all("ext_mode_prepare")        # dyn_core.F90:745-747: delp at the cell corners, before d_sw
                 run("D_SW", "d_sw", dt)
+                if self.case.flags.get("d_ext", 0.0) > 0.0:
+                    self.all("ext_mode_divg2")          # :828-847: mass-weighted vertical mean of the divergence
                 self.halo("DELP_PT")
                 run("GEOPK_D", "geopk", 0)
                 if last:

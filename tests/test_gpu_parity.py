@@ -457,6 +457,29 @@ def test_tracer_2d_after_dyn_core(hord):
     oc.close(); gc.close()
 
 
+@pytest.mark.parametrize("beta", [0.0, 0.4])
+def test_hydrostatic_external_mode_damping(beta):
+    """d_ext > 0 (0.02 is the reference's default outside SW_DYNAMICS builds) in the hydrostatic branch: delp at the cell corners
+    (a2b_ord2 incl. its cube-edge and corner formulas) before d_sw, the mass-weighted vertical mean of d_sw's divergence after it
+    (levels 1, 2 take the nord = 0 divergence d_sw recomputes, the others divg_d), its differences added to u, v by one_grad_p /
+    grad1_p_update (dyn_core.F90:745-747, 791-797, 828-847, 1969-1984, 2102-2111).  Four substeps against the oracle, and the
+    option must change the winds."""
+    over = dict(hydrostatic=1, d_ext=0.02, beta=beta)
+    case = H.Case(24, 8, "A", state="baroclinic", flags_override=over)
+    oc, gc = H.OracleCube(case), H.CudaCube(case)
+    oc.dyn_core(1800.0, 4)
+    gc.dyn_core(1800.0, 4)
+    reg = {k: v for k, v in H.regions_state(case.bounds).items() if k in ("DELP", "PT", "U", "V", "MFX", "MFY", "CX", "CY")}
+    for t in oc.tiles:
+        _assert_run(H.compare(oc.eng[t], gc.eng[t], reg))
+    case0 = H.Case(24, 8, "A", state="baroclinic", flags_override=dict(over, d_ext=0.0))
+    g0 = H.CudaCube(case0)
+    g0.dyn_core(1800.0, 4)
+    du = np.abs(gc.eng[1].get("U") - g0.eng[1].get("U")).max()
+    assert 1e-6 < du < 1.0, du
+    oc.close(); gc.close(); g0.close()
+
+
 @pytest.mark.parametrize("hydro", [0, 1])
 def test_dyn_core_beta_split_pressure_gradient(hydro):
     """beta > 0: split_p_grad (non-hydrostatic, dyn_core.F90:1795-1905) / grad1_p_update (hydrostatic, :2033-2116): the
