@@ -33,7 +33,7 @@ _GRID_PTRS = ["area", "rarea", "dxa", "dya", "rdxa", "rdya", "cosa_s", "rsin2", 
               "dy", "rdy", "dxc", "rdxc", "cosa_u", "sina_u", "rsin_u", "divg_v", "del6_v",
               "dx", "rdx", "dyc", "rdyc", "cosa_v", "sina_v", "rsin_v", "divg_u", "del6_u",
               "area_c", "rarea_c", "fC", "cosa", "sina", "rsina",
-              "edge_w", "edge_e", "edge_s", "edge_n", "grid", "agrid"]
+              "edge_w", "edge_e", "edge_s", "edge_n", "grid", "agrid", "ec1", "ec2", "en1", "en2"]
 
 
 class Grid(C.Structure):

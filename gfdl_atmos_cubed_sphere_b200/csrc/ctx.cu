@@ -227,6 +227,19 @@ int fv3_create(const fv3_bounds_t* bd, const fv3_grid_t* grid, const fv3_flags_t
   if ((rc = upload_vec(c, grid->edge_e, bd->npy, &G.edge_e))) { *out = c; return rc; }
   if ((rc = upload_vec(c, grid->edge_s, bd->npx, &G.edge_s))) { *out = c; return rc; }
   if ((rc = upload_vec(c, grid->edge_n, bd->npx, &G.edge_n))) { *out = c; return rc; }
+  {  // unit vectors of the omega diagnostic (nullable): (3, i, j) component first on the host -> three planes on the device
+    auto up3 = [&](const double* h, int ilo, int ni, int jlo, int nj, const double** out_p) -> int {
+      *out_p = nullptr;
+      if (!h) return 0;
+      std::vector<double> t((size_t)3 * ni * nj);
+      for (int n = 0; n < 3; n++)
+        for (size_t e = 0; e < (size_t)ni * nj; e++) t[(size_t)n * ni * nj + e] = h[3 * e + n];
+      return upload_metric(c, t.data(), ilo, ni, jlo, nj, 3, out_p);
+    };
+    const int nic = bd->ie - bd->is + 1, njc = bd->je - bd->js + 1;
+    if ((rc = up3(grid->ec1, isd, nia, jsd, nja, &G.ec1)) || (rc = up3(grid->ec2, isd, nia, jsd, nja, &G.ec2)) ||
+        (rc = up3(grid->en1, bd->is, nic, bd->js, njc + 1, &G.en1)) || (rc = up3(grid->en2, bd->is, nic + 1, bd->js, njc, &G.en2))) { *out = c; return rc; }
+  }
   G.da_min = grid->da_min; G.da_min_c = grid->da_min_c;
   if (L.cube) corner_weights(c, grid);
   // per-k tables
@@ -254,7 +267,7 @@ void fv3_destroy(fv3_ctx* c) {
   for (auto p : alts) cudaFree(p);
   for (int i = 0; i < fv3_ctx::NSCR; i++) cudaFree(c->scr[i]);
   for (auto p : c->metric_alloc) cudaFree(p);
-  cudaFree(c->d_stage); cudaFree(c->d_kint); cudaFree(c->d_kdbl); cudaFree(c->d_dp_ref); cudaFree(c->d_edge_tab); cudaFree(c->d_rff); cudaFree(c->d_akbk); cudaFree(c->d_divg2);
+  cudaFree(c->d_stage); cudaFree(c->d_kint); cudaFree(c->d_kdbl); cudaFree(c->d_dp_ref); cudaFree(c->d_edge_tab); cudaFree(c->d_rff); cudaFree(c->d_akbk); cudaFree(c->d_divg2); cudaFree(c->d_pem);
   for (auto& kv : c->timers) { cudaEventDestroy(kv.second.e0); cudaEventDestroy(kv.second.e1); }
   cudaStreamDestroy(c->stream);
   delete c;
@@ -377,6 +390,8 @@ int fv3_pe_halo(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_pe_halo(c); if (r
 int fv3_gz_from_zh(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_gz_from_zh(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_nh_p_grad(fv3_ctx* c, double dt) { STAGE_PROLOGUE(c) int rc = stage_nh_p_grad(c, dt); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_del2_cubed(fv3_ctx* c, int field, double cd, int nmax) { STAGE_PROLOGUE(c) int rc = stage_del2_cubed(c, field, cd, nmax); if (rc) return rc; STAGE_EPILOGUE(c) }
+int fv3_omega_begin(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_omega_begin(c); if (rc) return rc; STAGE_EPILOGUE(c) }
+int fv3_omega_end(fv3_ctx* c, double dt) { STAGE_PROLOGUE(c) int rc = stage_omega_end(c, dt); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_ext_mode_prepare(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_ext_mode_prepare(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_ext_mode_divg2(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_ext_mode_divg2(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_remap_work_q(fv3_ctx* c, int mode, int iv, int kord, double qmin) { STAGE_PROLOGUE(c) int rc = stage_remap_work_q(c, mode, iv, kord, qmin); if (rc) return rc; STAGE_EPILOGUE(c) }

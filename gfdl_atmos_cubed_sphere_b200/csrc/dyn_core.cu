@@ -30,13 +30,14 @@ extern "C" int fv3_halo_wait(fv3_ctx** ctxs, int nctx);
     if (rc_) return rc_;                               \
   }
 
-static int dyn_core_direct(fv3_ctx** ctxs, int nctx, double bdt, int n_split);
-static int dyn_core_graph(fv3_ctx** ctxs, int nctx, double bdt, int n_split);
+static int dyn_core_direct(fv3_ctx** ctxs, int nctx, double bdt, int n_split, bool end_step);
+static int dyn_core_graph(fv3_ctx** ctxs, int nctx, double bdt, int n_split, bool end_step);
 
 extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, int flags) {
   if (!ctxs || nctx < 1 || n_split < 1) return -1;
-  if (flags & ~FV3_DYN_GRAPH) return fv3_fail(ctxs[0], -2, "dyn_core: unknown flag bit (defined: FV3_DYN_GRAPH = 1)");
-  int rc = (flags & FV3_DYN_GRAPH) ? dyn_core_graph(ctxs, nctx, bdt, n_split) : dyn_core_direct(ctxs, nctx, bdt, n_split);
+  if (flags & ~(FV3_DYN_GRAPH | FV3_DYN_END_STEP)) return fv3_fail(ctxs[0], -2, "dyn_core: unknown flag bit (defined: FV3_DYN_GRAPH = 1, FV3_DYN_END_STEP = 2)");
+  const bool end_step = (flags & FV3_DYN_END_STEP) != 0;
+  int rc = (flags & FV3_DYN_GRAPH) ? dyn_core_graph(ctxs, nctx, bdt, n_split, end_step) : dyn_core_direct(ctxs, nctx, bdt, n_split, end_step);
   if (!rc) for (int a = 0; a < nctx; a++) ctxs[a]->dyn_calls++;
   return rc;
 }
@@ -51,7 +52,7 @@ extern "C" int fv3_dyn_core(fv3_ctx** ctxs, int nctx, double bdt, int n_split, i
 // allocations / one-time tables), remote faces (the peer-mapped exchange passes sequence numbers as kernel arguments, NCCL calls
 // are not captured here), stage timers on, overlapped exchange.
 struct DynGraph {
-  std::vector<fv3_ctx*> ctxs; double bdt; int n_split; int tp_fp32;
+  std::vector<fv3_ctx*> ctxs; double bdt; int n_split; int tp_fp32; bool end_step;
   std::vector<double*> ptr_in, ptr_out;   // fld[] + alt_* of every context at the start / end of the captured call
   long long launches;                     // per context: launches the captured call accounts for (same on every face)
   std::vector<long long> launches_ctx;
@@ -79,7 +80,7 @@ static void set_ptr_state(fv3_ctx** ctxs, int nctx, const std::vector<double*>& 
     c->alt_delp = in[n++]; c->alt_pt = in[n++]; c->alt_w = in[n++]; c->alt_u = in[n++]; c->alt_v = in[n++]; c->alt_qcon = in[n++];
   }
 }
-static int dyn_core_graph(fv3_ctx** ctxs, int nctx, double bdt, int n_split) {
+static int dyn_core_graph(fv3_ctx** ctxs, int nctx, double bdt, int n_split, bool end_step) {
   fv3_ctx* c0 = ctxs[0];
   bool direct = std::getenv("FV3_HALO_OVERLAP") != nullptr;
   for (int a = 0; a < nctx; a++) {
@@ -87,20 +88,21 @@ static int dyn_core_graph(fv3_ctx** ctxs, int nctx, double bdt, int n_split) {
     if (c->dyn_calls == 0 || c->timers_on || c->device != c0->device) direct = true;
     if (fv3_halo_has_remote(c)) direct = true;
   }
-  if (direct) return dyn_core_direct(ctxs, nctx, bdt, n_split);
+  if (end_step) for (int a = 0; a < nctx; a++) if (!ctxs[a]->d_pem) direct = true;   // (its first use allocates)
+  if (direct) return dyn_core_direct(ctxs, nctx, bdt, n_split, end_step);
   if (!c0->graphs) c0->graphs = new DynGraphs;
   std::vector<double*> now;
   ptr_state(ctxs, nctx, now);
   DynGraph* G = nullptr;
   for (auto& g : c0->graphs->g)
-    if (g.bdt == bdt && g.n_split == n_split && g.tp_fp32 == c0->tp_fp32 && (int)g.ctxs.size() == nctx &&
+    if (g.bdt == bdt && g.n_split == n_split && g.tp_fp32 == c0->tp_fp32 && g.end_step == end_step && (int)g.ctxs.size() == nctx &&
         std::equal(g.ctxs.begin(), g.ctxs.end(), ctxs) && g.ptr_in == now) { G = &g; break; }
   cudaSetDevice(c0->device);
   cudaEvent_t ev;
   FV3_CUDA(c0, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   if (!G) {
     DynGraph g;
-    g.ctxs.assign(ctxs, ctxs + nctx); g.bdt = bdt; g.n_split = n_split; g.tp_fp32 = c0->tp_fp32; g.ptr_in = now;
+    g.ctxs.assign(ctxs, ctxs + nctx); g.bdt = bdt; g.n_split = n_split; g.tp_fp32 = c0->tp_fp32; g.end_step = end_step; g.ptr_in = now;
     std::vector<long long> l0(nctx);
     for (int a = 0; a < nctx; a++) { l0[a] = ctxs[a]->launches; ctxs[a]->capturing = true; }
     // fork: the other faces' streams join the capture of the first face's stream
@@ -109,7 +111,7 @@ static int dyn_core_graph(fv3_ctx** ctxs, int nctx, double bdt, int n_split) {
     if (e == cudaSuccess) {
       cudaEventRecord(ev, c0->stream);
       for (int a = 1; a < nctx; a++) if (ctxs[a]->stream != c0->stream) cudaStreamWaitEvent(ctxs[a]->stream, ev, 0);
-      rc = dyn_core_direct(ctxs, nctx, bdt, n_split);
+      rc = dyn_core_direct(ctxs, nctx, bdt, n_split, end_step);
       // join
       for (int a = 1; a < nctx; a++) {
         if (ctxs[a]->stream == c0->stream) continue;
@@ -153,7 +155,7 @@ static int dyn_core_graph(fv3_ctx** ctxs, int nctx, double bdt, int n_split) {
   return 0;
 }
 
-static int dyn_core_direct(fv3_ctx** ctxs, int nctx, double bdt, int n_split) {
+static int dyn_core_direct(fv3_ctx** ctxs, int nctx, double bdt, int n_split, bool end_step) {
   for (int a = 0; a < nctx; a++) {
     // the loop below branches on the first context's switches: the linked faces must agree on them
     const fv3_flags_t &f0 = ctxs[0]->f, &fa = ctxs[a]->f;
@@ -194,11 +196,13 @@ static int dyn_core_direct(fv3_ctx** ctxs, int nctx, double bdt, int n_split) {
       if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;
       continue;
     }
+    const bool omega = last_step && end_step && !sw_advection;   // the omega diagnostic (dyn_core.F90:409-422, 1182-1195)
     if (hydrostatic) {   // geopk replaces the vertical solvers, one_grad_p the pressure gradient (dyn_core.F90:478-480, :905-907, :1017-1021)
       if (linked) {
         if (it == 1 && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;
         if ((rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_UVW))) return rc;
       }
+      if (omega) { FORALL(stage_omega_begin(c)) }
       FORALL(stage_c_sw(c, dt2))
       FORALL(stage_geopk(c, 1))
       FORALL(stage_p_grad_c(c, dt2))
@@ -213,12 +217,14 @@ static int dyn_core_direct(fv3_ctx** ctxs, int nctx, double bdt, int n_split) {
       if (beta > 0.) { FORALL(stage_one_grad_p(c, dt, it == 1 ? 0. : beta)) }   // :1018-1019 grad1_p_update, beta_d (:404-406)
       else { FORALL(stage_one_grad_p(c, dt)) }
       if (last_step && linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_UV_EDGE))) return rc;
+      if (omega) { FORALL(stage_omega_end(c, dt)) }
       continue;
     }
     if (linked) {
       if (it == 1 && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;   // :402 (started in fv_dynamics.F90:467)
       if ((rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_UVW))) return rc;                  // :430-432
     }
+    if (omega) { FORALL(stage_omega_begin(c)) }                                           // :409-422
     if (it == 1) {
       FORALL(stage_gz_init(c))                                                            // :370-385
       if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_GZ))) return rc;         // :387, :488
@@ -244,6 +250,7 @@ static int dyn_core_direct(fv3_ctx** ctxs, int nctx, double bdt, int n_split) {
     if (beta > 0.) { FORALL(stage_nh_p_grad(c, dt, it == 1 ? 0. : beta)) }                // :1027-1028 split_p_grad
     else { FORALL(stage_nh_p_grad(c, dt)) }                                               // :1032
     if (last_step && linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_UV_EDGE))) return rc;   // :1151-1163
+    if (omega) { FORALL(stage_omega_end(c, dt)) }                                         // :1182-1195
   }
   // dyn_core.F90:1300-1356: the dissipative heating accumulated over the substeps is filtered and added to pt
   if (!sw_advection && ctxs[0]->f.d_con > 1.e-5 && fv3_n_con(ctxs[0]->f, ctxs[0]->L.npz) != 0) {
@@ -288,7 +295,7 @@ extern "C" int fv3_fv_dynamics(fv3_ctx** ctxs, int nctx, double bdt, int k_split
   for (int n_map = 1; n_map <= k_split; n_map++) {
     const int last_step = n_map == k_split;
     FORALL(stage_copy_field(c, FV3_DP1, FV3_DELP))                                        // :473-481 (compute domain + halo)
-    if ((rc = fv3_dyn_core(ctxs, nctx, mdt, n_split, flags))) return rc;                  // :495-502
+    if ((rc = fv3_dyn_core(ctxs, nctx, mdt, n_split, (flags & FV3_DYN_GRAPH) | (last_step ? FV3_DYN_END_STEP : 0)))) return rc;   // :495-502
     if (hord_tr != 0 && (rc = fv3_tracer_2d(ctxs, nctx, hord_tr, nullptr))) return rc;    // :512-535
     FORALL(stage_lagrangian_to_eulerian(c, last_step, kord_mt, kord_wz, kord_tm, hord_tr != 0, kord_tr))   // :578-625
     if (last_step && nf_omega > 0) {                                                      // :658-662

@@ -99,6 +99,7 @@ struct DevGrid {
   const double *dx, *rdx, *dyc, *rdyc, *cosa_v, *sina_v, *rsin_v, *divg_u, *del6_u;
   const double *area_c, *rarea_c, *fC, *cosa, *sina, *rsina;
   const double *edge_w, *edge_e, *edge_s, *edge_n;  // 1-based: edge_w[j-1]
+  const double *ec1, *ec2, *en1, *en2;   // omega diagnostic: three planes each (component slowest), nullptr when not given
   double a2b_w[4][3];   // a2b_ord4 corner extrapolation weights x1/(x2-x1) (a2b_edge.F90:106-130,452-462)
   double da_min, da_min_c;
 };
@@ -136,6 +137,7 @@ struct fv3_ctx {
   int* d_kint; double* d_kdbl;     // device copies of per-k coefficient tables
   double* d_dp_ref;                // dp_ref(npz)  dyn_core.F90:242-244
   double* d_edge_tab;              // edge_profile coefficient tables (nh.cu), built on first use
+  double* d_pem = nullptr;         // interface pressures before the last substep (omega diagnostic), npz + 1 planes, built on first use
   double* d_divg2 = nullptr;       // external-mode damping term (d_ext > 0), one plane, built on first use
   double* d_akbk = nullptr;        // ak(0:km), bk(0:km) for the vertical remap (remap.cu), built on first use
   double* d_rff = nullptr; int k_rf = 0;   // Rayleigh damping table of the vertical solvers (fast_tau_w_sec > 0), built by the first solver call
@@ -169,6 +171,8 @@ struct StageScope {
 };
 
 // stage implementations (each enqueues kernels on c->stream)
+int stage_omega_begin(fv3_ctx* c);
+int stage_omega_end(fv3_ctx* c, double dt);
 int stage_ext_mode_prepare(fv3_ctx* c);
 int stage_ext_mode_divg2(fv3_ctx* c);
 int stage_remap_work_q(fv3_ctx* c, int mode, int iv, int kord, double qmin);

@@ -490,3 +490,65 @@ int stage_ext_mode_divg2(fv3_ctx* c) {
   c->launches++;
   return 0;
 }
+
+// ---- omega diagnostic of the last substep of the last dyn_core call (end_step; use_old_omega = T) ------------------------------
+// dyn_core.F90:409-422: pem = ptop + partial sums of delp on (is-1:ie+1, js-1:je+1), one thread per column
+__global__ void __launch_bounds__(TI* TJ) k_pem(Lay L, const double* __restrict__ delp, double* __restrict__ pem, double ptop) {
+  const int i = L.isd - FV3_IOFF + blockIdx.x * TI + threadIdx.x;
+  const int j = L.jsd + blockIdx.y * TJ + threadIdx.y;
+  if (i < L.is - 1 || i > L.ie + 1 || j < L.js - 1 || j > L.je + 1) return;
+  const int o2 = LIDX(L, i, j);
+  double p = ptop;
+  pem[o2] = p;
+  for (int k = 0; k < L.npz; k++) { p = p + __ldg(delp + o2 + (long long)k * L.plane); pem[o2 + (long long)(k + 1) * L.plane] = p; }
+}
+// dyn_core.F90:1182-1195 + adv_pe (:1529-1630): omga = (pe - pem) * rdt + 0.5 * rarea * V3 . grad(pem); pb = a2b_ord2 of the
+// interfaces 2..npz+1 of pem (plane k of pb <-> interface k+2)
+__global__ void __launch_bounds__(TI* TJ) k_omega_old(Lay L, DevGrid G, const double* __restrict__ pe, const double* __restrict__ pem,
+                                                      const double* __restrict__ pb, const double* __restrict__ ua, const double* __restrict__ va,
+                                                      double* __restrict__ omga, double rdt) {
+  PLANE_IJK
+  if (i < L.is || i > L.ie || j < L.js || j > L.je) return;
+  const int o2 = LIDX(L, i, j);
+  const long long o = ko + o2, P = L.plane;
+  double om = (__ldg(pe + o + P) - __ldg(pem + o + P)) * rdt;
+  double up, vp;
+  if (k == L.npz - 1) { up = __ldg(ua + o); vp = __ldg(va + o); }
+  else { up = 0.5 * (__ldg(ua + o) + __ldg(ua + o + P)); vp = 0.5 * (__ldg(va + o) + __ldg(va + o + P)); }
+  const double b00 = __ldg(pb + o), b10 = __ldg(pb + o + 1), b01 = __ldg(pb + o + L.NI), b11 = __ldg(pb + o + L.NI + 1);
+  const double dx0 = G2(dx, i, j), dx1 = G2(dx, i, j + 1), dy0 = G2(dy, i, j), dy1 = G2(dy, i + 1, j);
+  double acc = 0.;
+#pragma unroll
+  for (int n = 0; n < 3; n++) {
+    const long long no = (long long)n * P;
+    const double v3 = up * __ldg(G.ec1 + no + o2) + vp * __ldg(G.ec2 + no + o2);
+    const double pdx0 = (b00 + b10) * dx0 * __ldg(G.en1 + no + o2);
+    const double pdx1 = (b01 + b11) * dx1 * __ldg(G.en1 + no + o2 + L.NI);
+    const double pdy0 = (b00 + b01) * dy0 * __ldg(G.en2 + no + o2);
+    const double pdy1 = (b10 + b11) * dy1 * __ldg(G.en2 + no + o2 + 1);
+    const double grad = pdx1 - pdx0 - pdy0 + pdy1;
+    acc = n == 0 ? v3 * grad : acc + v3 * grad;
+  }
+  omga[o] = om + 0.5 * G2(rarea, i, j) * acc;
+}
+int stage_omega_begin(fv3_ctx* c) {
+  StageScope ts(c, "OMEGA");
+  const Lay& L = c->L;
+  if (!c->d_pem) FV3_CUDA(c, cudaMalloc(&c->d_pem, (size_t)L.plane * (L.npz + 1) * sizeof(double)));
+  k_pem<<<dim3((L.NI + TI - 1) / TI, (L.NJ + TJ - 1) / TJ), dim3(TI, TJ), 0, c->stream>>>(L, c->fld[FV3_DELP], c->d_pem, c->f.ptop);
+  c->launches++;
+  return 0;
+}
+int stage_omega_end(fv3_ctx* c, double dt) {
+  StageScope ts(c, "OMEGA");
+  const Lay& L = c->L;
+  if (!c->f.use_old_omega) return fv3_fail(c, -2, "omega diagnostic: use_old_omega = F not supported");
+  if (!c->d_pem) return fv3_fail(c, -1, "omega_end without omega_begin");
+  if (!c->G.ec1 || !c->G.ec2 || !c->G.en1 || !c->G.en2) return fv3_fail(c, -1, "omega diagnostic: fv3_grid_t.ec1 / ec2 / en1 / en2 were not given to fv3_create");
+  double* pb = c->scr[0];
+  k_a2b_ord2<<<plane_grid(L, L.npz), dim3(TI, TJ), 0, c->stream>>>(L, c->G, c->d_pem + L.plane, pb);
+  k_omega_old<<<plane_grid(L, L.npz), dim3(TI, TJ), 0, c->stream>>>(L, c->G, c->fld[FV3_PE], c->d_pem, pb, c->fld[FV3_UA], c->fld[FV3_VA],
+                                                                  c->fld[FV3_OMGA], 1. / dt);
+  c->launches += 2;
+  return 0;
+}

@@ -72,11 +72,12 @@ class CudaCube:
             if rc:
                 raise RuntimeError(f"fv3_cube_link rc={rc}: {self.eng[self.tiles[0]].last_error()}")
 
-    def dyn_core(self, bdt, n_split, graph=False):
-        """fv3_dyn_core on the faces of this process; graph=True: FV3_DYN_GRAPH (captured once, replayed with one launch)."""
+    def dyn_core(self, bdt, n_split, graph=False, end_step=False):
+        """fv3_dyn_core on the faces of this process; graph=True: FV3_DYN_GRAPH (captured once, replayed with one launch);
+        end_step=True: FV3_DYN_END_STEP (last call of the k_split loop: omega diagnostic on the last substep)."""
         fn = self.lib[0].fv3_dyn_core
         fn.restype = C.c_int
-        rc = fn(self.ctxs, len(self.tiles), C.c_double(bdt), C.c_int(n_split), C.c_int(1 if graph else 0))
+        rc = fn(self.ctxs, len(self.tiles), C.c_double(bdt), C.c_int(n_split), C.c_int((1 if graph else 0) | (2 if end_step else 0)))
         if rc:
             raise RuntimeError(f"fv3_dyn_core rc={rc}: " + "; ".join(self.eng[t].last_error() for t in self.tiles))
         for t in self.tiles:

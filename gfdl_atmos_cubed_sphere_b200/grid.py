@@ -584,6 +584,20 @@ def make_cubed_sphere(n, ng=3, consts=None, alpha=0.0, shift_fac=18.0):
         a["edge_w"] = edge_w; a["edge_e"] = edge_e; a["edge_s"] = edge_s; a["edge_n"] = edge_n
         a["grid"] = np.stack([glon[t], glat[t]], axis=0)
         a["agrid"] = np.stack([alon[t].a, alat[t].a], axis=0)
+        # unit vectors of the omega diagnostic (adv_pe, dyn_core.F90:1529-1630), Fortran-native extents with the component fastest:
+        # ec1, ec2 (3, isd:ied, jsd:jed) from get_center_vect (above; zero in the corner ghost blocks, fv_grid_utils.F90:1757-1760),
+        # en1 (3, is:ie, js:je+1) / en2 (3, is:ie+1, js:je) normal to the cell edges (:629-642)
+        with np.errstate(invalid="ignore"):
+            e1 = np.where(np.isfinite(ec1), ec1, 0.0); e2 = np.where(np.isfinite(ec2), ec2, 0.0)
+        jj, ii = np.meshgrid(np.arange(jsd, jed + 1), np.arange(isd, ied + 1), indexing="ij")
+        ghost = ((ii < 1) | (ii > npx - 1)) & ((jj < 1) | (jj > npy - 1))
+        e1[ghost] = 0.0; e2[ghost] = 0.0
+        a["ec1"] = np.ascontiguousarray(e1); a["ec2"] = np.ascontiguousarray(e2)
+        gc = g3[1 - jsd:npy - jsd + 1, 1 - isd:npx - isd + 1]              # corners (1:npx, 1:npy)
+        n1 = np.cross(gc[:, :-1], gc[:, 1:])                             # (js:je+1, is:ie): grid3(i,j) x grid3(i+1,j)
+        n2 = np.cross(gc[1:, :], gc[:-1, :])                             # (js:je, is:ie+1): grid3(i,j+1) x grid3(i,j)
+        a["en1"] = np.ascontiguousarray(n1 / np.linalg.norm(n1, axis=-1, keepdims=True))
+        a["en2"] = np.ascontiguousarray(n2 / np.linalg.norm(n2, axis=-1, keepdims=True))
         T._divg = (divg_u, divg_v, del6_u, del6_v)
         tiles.append(T)
 
@@ -635,6 +649,9 @@ def make_cartesian(n, ng=3, dx_const=1000.0, deglat=15.0, consts=None):
         a[nm] = np.full(shp, val)
     a["cosa_s"] = np.zeros((nja, nia)); a["rsin2"] = one_a.copy()
     a["sin_sg"] = np.ones((9, nja, nia)); a["cos_sg"] = np.zeros((9, nja, nia))
+    a["ec1"] = np.zeros((nja, nia, 3)); a["ec1"][..., 0] = 1.0             # fv_grid_utils.F90:429-435
+    a["ec2"] = np.zeros((nja, nia, 3)); a["ec2"][..., 1] = 1.0
+    a["en1"] = np.zeros((n + 1, n, 3)); a["en2"] = np.zeros((n, n + 1, 3))   # not set for grid_type >= 3 (:628)
     for nm, shp in (("cosa_u", (nja, nia + 1)), ("cosa_v", (nja + 1, nia)), ("cosa", (nja + 1, nia + 1))):
         a[nm] = np.zeros(shp)
     for nm, shp in (("sina_u", (nja, nia + 1)), ("rsin_u", (nja, nia + 1)), ("sina_v", (nja + 1, nia)),

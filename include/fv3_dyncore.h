@@ -62,6 +62,10 @@ typedef struct fv3_grid_t {
   const double *edge_w, *edge_e, *edge_s, *edge_n;
   /* grid (isd:ied+1, jsd:jed+1, 2) lon,lat of corners; agrid (isd:ied, jsd:jed, 2) */
   const double *grid, *agrid;
+  /* unit vectors of the omega diagnostic (adv_pe, dyn_core.F90:1529-1630), component first as in fv_arrays.F90:1845-1854:
+   * ec1, ec2 (3, isd:ied, jsd:jed); en1 (3, is:ie, js:je+1); en2 (3, is:ie+1, js:je).  May be NULL when fv3_dyn_core is never
+   * called with FV3_DYN_END_STEP. */
+  const double *ec1, *ec2, *en1, *en2;
   double da_min, da_min_c;
 } fv3_grid_t;
 
@@ -214,6 +218,9 @@ int fv3_pt_to_theta(fv3_ctx *ctx, double zvir);
  * 791-797, 828-847, 1969-1984): fv3_ext_mode_prepare before fv3_d_sw (delp at the cell corners, a2b_ord2), fv3_ext_mode_divg2 after it
  * (mass-weighted vertical mean of the divergence d_sw leaves in FV3_VT); fv3_one_grad_p / fv3_split_p_grad then add its
  * differences to u, v.  fv3_dyn_core does this itself; in the non-hydrostatic beta = 0 path divg2 is read by nothing. */
+/* the two halves of the omega diagnostic (FV3_DYN_END_STEP), for stage-by-stage drivers: before / after the last substep */
+int fv3_omega_begin(fv3_ctx *ctx);
+int fv3_omega_end(fv3_ctx *ctx, double dt);
 int fv3_ext_mode_prepare(fv3_ctx *ctx);
 int fv3_ext_mode_divg2(fv3_ctx *ctx);
 int fv3_lagrangian_to_eulerian(fv3_ctx *ctx, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr);
@@ -302,15 +309,20 @@ int fv3_plane_index(const fv3_ctx *ctx, int i, int j);
  * flags: 0, or FV3_DYN_GRAPH: the call is captured once into a CUDA graph (one per context list, bdt, n_split, precision mode
  * and ping-pong state of the fields) and replayed with a single cudaGraphLaunch afterwards; bit-identical to flags = 0.  Calls
  * that cannot be captured validly run directly with the same result: the first call of a context (one-time allocations), faces
- * on other ranks (peer-mapped / NCCL exchange), stage timers on.  Any other bit: -2.
+ * on other ranks (peer-mapped / NCCL exchange), stage timers on.  FV3_DYN_END_STEP: see below.  Any other bit: -2.
  * Hydrostatic branch: on the last substep pk = pkc on the compute domain (dyn_core.F90:1001-1010), so the
  * pk a caller downloads for the remapping is current. */
 #define FV3_DYN_GRAPH 1
+/* FV3_DYN_END_STEP: this is the last dyn_core call of the k_split loop (the reference's end_step argument): on its last substep the
+ * omega diagnostic is formed (dyn_core.F90:409-422, 1182-1195: omga = (pe - pem) / dt + adv_pe(ua, va, pem), use_old_omega = T;
+ * use_old_omega = F is an error).  Without the bit omga is left untouched.  Needs ec1, ec2, en1, en2 in fv3_grid_t. */
+#define FV3_DYN_END_STEP 2
 int fv3_dyn_core(fv3_ctx **ctxs, int nctx, double bdt, int n_split, int flags);
 
 /* fv_dynamics.F90:303-398 + :445-662: one call of fv_dynamics on device-resident state -- entry conversion
  * T -> theta_v, then k_split times { dp1 = delp; dyn_core(bdt / k_split, n_split); tracer_2d of FV3_WORK_Q when hord_tr != 0;
- * Lagrangian_to_Eulerian }, then the omega filter del2_cubed(omga, 0.18 da_min, nf_omega).  Dry adiabatic subset (no q_v, no
+ * Lagrangian_to_Eulerian }, then the omega filter del2_cubed(omga, 0.18 da_min, nf_omega); the last dyn_core call runs with
+ * FV3_DYN_END_STEP (omega diagnostic).  Dry adiabatic subset (no q_v, no
  * moist_kappa, no inline physics, no energy fixer); pt is temperature on entry and on exit.  flags: as fv3_dyn_core. */
 int fv3_fv_dynamics(fv3_ctx **ctxs, int nctx, double bdt, int k_split, int n_split, int kord_mt, int kord_wz, int kord_tm,
                     int kord_tr, int hord_tr, int nf_omega, int flags);

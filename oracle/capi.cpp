@@ -26,6 +26,7 @@ struct fv3o_ctx {
   // Rayleigh damping table of nh_utils (SAVEd rff, k_rf, RFw_initialized, nh_utils.F90:53-55)
   std::vector<double> rff; int k_rf = 0; bool rf_init = false;
   // external-mode damping term divg2(is:ie+1, js:je+1) of the current substep (dyn_core.F90:828-847; empty: d_ext = 0)
+  std::vector<double> pem;   // interface pressures before the last substep (omega diagnostic, dyn_core.F90:409-422)
   std::vector<double> divg2, ext_dpc;   // ext_dpc: delp at the cell corners (is:ie+1, js:je+1, npz), taken before d_sw (:745-747)
   explicit fv3o_ctx(const fv3_bounds_t& b_, const fv3_grid_t& g_, const fv3_flags_t& f_) : b(b_), g(g_), f(f_) {}
 };
@@ -395,6 +396,21 @@ int fv3o_del2_cubed(fv3o_ctx* c, int field, double cd, int nmax) {
   return 0;
 }
 // fv_dynamics.F90:303-328, :377-398: specific humidity in FV3_WORK_Q (read only when zvir != 0 is meaningful; it is multiplied anyway)
+// omega diagnostic of the last substep of the last dyn_core call (end_step): before the substep ...
+int fv3o_omega_begin(fv3o_ctx* c) {
+  Bd bd(c->b);
+  c->pem.assign(c->fld[FV3_PE].size(), 0.);
+  pem_from_delp(c->pem.data(), F3(c, FV3_DELP), c->f.ptop, bd);
+  return 0;
+}
+// ... and after it (use_old_omega = T, dyn_core.F90:1182-1195)
+int fv3o_omega_end(fv3o_ctx* c, double dt) {
+  if (!c->f.use_old_omega) return -2;
+  if (c->pem.size() != c->fld[FV3_PE].size() || !c->g.ec1 || !c->g.ec2 || !c->g.en1 || !c->g.en2) return -1;
+  Bd bd(c->b); Grid g(c->g, bd);
+  omega_old(F3(c, FV3_OMGA), c->fld[FV3_PE].data(), c->pem.data(), F3(c, FV3_UA), F3(c, FV3_VA), 1. / dt, g, bd);
+  return 0;
+}
 // fv_operators.F90 map_scalar (mode 0) / map1_ppm (1) / map1_q2 (2) of FV3_WORK_Q on the compute domain: from the layers of FV3_PE to
 // the hybrid levels ak + bk * pe(km+1) (remap.cpp)
 int fv3o_remap_work_q(fv3o_ctx* c, int mode, int iv, int kord, double qmin) {

@@ -149,6 +149,7 @@ struct Grid {
   const double *sin_sg_p, *cos_sg_p;
   const double *edge_w, *edge_e, *edge_s, *edge_n;  // 1-based: edge_w[j-1]
   const double *grid_p, *agrid_p;
+  const double *ec1_p, *ec2_p, *en1_p, *en2_p;   // (3, ...) component fastest
   double da_min, da_min_c;
   int isd, jsd, nia, nja;
   Grid(const fv3_grid_t& g, const Bd& b) {
@@ -166,6 +167,7 @@ struct Grid {
     sin_sg_p = g.sin_sg; cos_sg_p = g.cos_sg;
     edge_w = g.edge_w; edge_e = g.edge_e; edge_s = g.edge_s; edge_n = g.edge_n;
     grid_p = g.grid; agrid_p = g.agrid; da_min = g.da_min; da_min_c = g.da_min_c;
+    ec1_p = g.ec1; ec2_p = g.ec2; en1_p = g.en1; en2_p = g.en2;
   }
   inline double sin_sg(int i, int j, int n) const {
     return sin_sg_p[(i - isd) + (ptrdiff_t)(j - jsd) * nia + (ptrdiff_t)(n - 1) * nia * nja];
@@ -272,6 +274,10 @@ void pk3_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed
               double akap, V3 pk3, V3 delp);
 void pe_halo(int is, int ie, int js, int je, int isd, int ied, int jsd, int jed, int npz, double ptop,
              double* pe, V3 delp);
+
+// omega diagnostic of the last substep (dyn_core.F90:409-422, 1182-1195, adv_pe :1529-1630), nh.cpp
+void pem_from_delp(double* pem, V3 delp, double ptop, const Bd& bd);
+void omega_old(V3 omga, const double* pe, const double* pem, V3 ua, V3 va, double rdt, const Grid& g, const Bd& bd);
 
 // remap.cpp (fv_mapz.F90 Lagrangian_to_Eulerian, fv_operators.F90 map_scalar / map1_ppm / map1_q2 and their profiles)
 struct L2EFields { V3 pt, delp, delz, w, u, v, pk, pkz, omga, qtr; V2 ws; double *pe, *peln; };

@@ -796,4 +796,58 @@ void pt_to_theta(V3 pt, V3 delp, V3 delz, V3 qv, V3 q_con, V3 dp1, V3 pkz, doubl
       }
 }
 
+// dyn_core.F90:409-422: pem(is-1:ie+1, npz+1, js-1:je+1), the interface pressures before the last substep
+void pem_from_delp(double* pem, V3 delp, double ptop, const Bd& bd) {
+  const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je, km = bd.npz;
+  const size_t nip = ie - is + 3;
+  auto PEM = [&](int i, int k, int j) -> double& { return pem[(i - (is - 1)) + (size_t)(k - 1) * nip + (size_t)(j - (js - 1)) * nip * (km + 1)]; };
+#pragma omp parallel for schedule(static)
+  for (int j = js - 1; j <= je + 1; j++) {
+    for (int i = is - 1; i <= ie + 1; i++) PEM(i, 1, j) = ptop;
+    for (int k = 1; k <= km; k++)
+      for (int i = is - 1; i <= ie + 1; i++) PEM(i, k + 1, j) = PEM(i, k, j) + delp(i, j, k);
+  }
+}
+
+// dyn_core.F90:1182-1195 (use_old_omega = T): omga = (pe - pem) * rdt, then adv_pe (:1529-1630): the advective term
+// 0.5 * rarea * V3 . grad(pe), grad by Green's theorem around the cell from the corner values of pem (a2b_ord2)
+void omega_old(V3 omga, const double* pe, const double* pem, V3 ua, V3 va, double rdt, const Grid& g, const Bd& bd) {
+  const int is = bd.is, ie = bd.ie, js = bd.js, je = bd.je, km = bd.npz, isd = bd.isd, ied = bd.ied, jsd = bd.jsd, jed = bd.jed;
+  const size_t nip = ie - is + 3;
+  auto P = [&](const double* a, int i, int k, int j) { return a[(i - (is - 1)) + (size_t)(k - 1) * nip + (size_t)(j - (js - 1)) * nip * (km + 1)]; };
+  const int nia = ied - isd + 1, nic = ie - is + 1;
+  auto EC = [&](const double* e, int n, int i, int j) { return e[(n - 1) + 3 * ((i - isd) + (size_t)(j - jsd) * nia)]; };
+  auto EN1 = [&](int n, int i, int j) { return g.en1_p[(n - 1) + 3 * ((i - is) + (size_t)(j - js) * nic)]; };          // (3, is:ie, js:je+1)
+  auto EN2 = [&](int n, int i, int j) { return g.en2_p[(n - 1) + 3 * ((i - is) + (size_t)(j - js) * (nic + 1))]; };    // (3, is:ie+1, js:je)
+#pragma omp parallel for schedule(static)
+  for (int k = 1; k <= km; k++)
+    for (int j = js; j <= je; j++)
+      for (int i = is; i <= ie; i++) omga(i, j, k) = (P(pe, i, k + 1, j) - P(pem, i, k + 1, j)) * rdt;
+#pragma omp parallel for schedule(static)
+  for (int k = 1; k <= km; k++) {
+    L2 up(is, ie, js, je), vp(is, ie, js, je), pin(isd, ied, jsd, jed), pb(isd, ied, jsd, jed);
+    for (int j = js; j <= je; j++)
+      for (int i = is; i <= ie; i++) {
+        if (k == km) { up(i, j) = ua(i, j, km); vp(i, j) = va(i, j, km); }
+        else { up(i, j) = 0.5 * (ua(i, j, k) + ua(i, j, k + 1)); vp(i, j) = 0.5 * (va(i, j, k) + va(i, j, k + 1)); }
+      }
+    for (int j = js - 1; j <= je + 1; j++) for (int i = is - 1; i <= ie + 1; i++) pin(i, j) = P(pem, i, k + 1, j);
+    a2b_ord2(pin, pb, g, bd);
+    for (int j = js; j <= je; j++)
+      for (int i = is; i <= ie; i++) {
+        double acc = 0.;
+        for (int n = 1; n <= 3; n++) {
+          const double v3 = up(i, j) * EC(g.ec1_p, n, i, j) + vp(i, j) * EC(g.ec2_p, n, i, j);
+          const double pdx0 = (pb(i, j) + pb(i + 1, j)) * g.dx(i, j) * EN1(n, i, j);
+          const double pdx1 = (pb(i, j + 1) + pb(i + 1, j + 1)) * g.dx(i, j + 1) * EN1(n, i, j + 1);
+          const double pdy0 = (pb(i, j) + pb(i, j + 1)) * g.dy(i, j) * EN2(n, i, j);
+          const double pdy1 = (pb(i + 1, j) + pb(i + 1, j + 1)) * g.dy(i + 1, j) * EN2(n, i + 1, j);
+          const double grad = pdx1 - pdx0 - pdy0 + pdy1;
+          if (n == 1) acc = v3 * grad; else acc = acc + v3 * grad;
+        }
+        omga(i, j, k) = omga(i, j, k) + 0.5 * g.rarea(i, j) * acc;
+      }
+  }
+}
+
 }  // namespace fv3o

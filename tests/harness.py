@@ -204,7 +204,8 @@ class OracleCube:
         for t in self.tiles:
             self.eng[t].call(stage, *args)
 
-    def dyn_core(self, bdt, n_split, timers=None):
+    def dyn_core(self, bdt, n_split, timers=None, end_step=False):
+        """end_step: the reference's argument of that name (last dyn_core call of the k_split loop): omega diagnostic on the last substep"""
         import time
         dt = bdt / n_split
         dt2 = 0.5 * dt
@@ -227,6 +228,9 @@ class OracleCube:
             last = it == n_split
             if it == 1:
                 self.halo("DELP_PT")
+            omega = last and end_step and self.case.flags.get("sw_test_case") != 1
+            if omega:
+                self.all("omega_begin")          # dyn_core.F90:409-422: pem from delp before the last substep
             if self.case.flags.get("sw_test_case") == 1:   # SW_DYNAMICS, test_case 1: d_sw + delp halo only (dyn_core.F90:394, 569, 998)
                 run("D_SW", "d_sw", dt)
                 self.halo("DELP_PT")
@@ -252,6 +256,8 @@ class OracleCube:
                     run("PG_D", "one_grad_p", dt)
                 if last:
                     self.halo("UV_EDGE")
+                if omega:
+                    self.all("omega_end", dt)    # :1182-1195
                 continue
             if it == 1:
                 self.all("gz_init")
@@ -280,6 +286,8 @@ class OracleCube:
                 run("PG_D", "nh_p_grad", dt)
             if last:
                 self.halo("UV_EDGE")
+            if omega:
+                self.all("omega_end", dt)        # :1182-1195
         self.dcon_heating(bdt)
 
     def n_con(self):
@@ -313,7 +321,7 @@ class OracleCube:
         for n_map in range(1, k_split + 1):
             last = int(n_map == k_split)
             self.all("copy_field", F["DP1"], F["DELP"])
-            self.dyn_core(mdt, n_split)
+            self.dyn_core(mdt, n_split, end_step=bool(last))
             if hord_tr:
                 self.tracer_2d(hord_tr)
             self.all("lagrangian_to_eulerian", last, kord_mt, kord_wz, kord_tm, int(hord_tr != 0), kord_tr)

@@ -47,5 +47,5 @@ def test_graph_flag_validation():
     gc = H.CudaCube(case)
     fn = gc.lib[0].fv3_dyn_core
     fn.restype = C.c_int
-    assert fn(gc.ctxs, len(gc.tiles), C.c_double(100.0), C.c_int(1), C.c_int(2)) == -2
+    assert fn(gc.ctxs, len(gc.tiles), C.c_double(100.0), C.c_int(1), C.c_int(4)) == -2
     gc.close()

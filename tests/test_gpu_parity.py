@@ -457,6 +457,35 @@ def test_tracer_2d_after_dyn_core(hord):
     oc.close(); gc.close()
 
 
+@pytest.mark.parametrize("hydro", [0, 1])
+def test_omega_diagnostic_of_the_end_step(hydro):
+    """FV3_DYN_END_STEP: omga = (pe - pem) / dt + adv_pe(ua, va, pem) on the last substep (dyn_core.F90:409-422, 1182-1195, 1529-1630;
+    use_old_omega = T, the reference's default) -- pem from delp before the substep, a2b_ord2 of its interfaces, the gradient by
+    Green's theorem with the en1 / en2 / ec1 / ec2 unit vectors.  Tolerance 1e-8: (pe - pem) is a difference of 1e5 Pa values that
+    differ by ~10 Pa.  Without the flag the hydrostatic branch leaves omga untouched (the non-hydrostatic one uses it as the C-grid w
+    work array of c_sw / Riem_Solver_c, as the reference does, dyn_core.F90:443, 532); a graph replay must give the same bits."""
+    case = H.Case(24, 8, "A", state="baroclinic", flags_override=dict(hydrostatic=hydro))
+    oc, gc = H.OracleCube(case), H.CudaCube(case)
+    b = case.bounds
+    reg = {"OMGA": (b["is_"], b["ie"], b["js"], b["je"])}
+    om0 = gc.eng[1].get("OMGA").copy()
+    oc.dyn_core(900.0, 2); gc.dyn_core(900.0, 2)
+    if hydro:
+        assert np.array_equal(gc.eng[1].get("OMGA"), om0)
+    oc.dyn_core(900.0, 2, end_step=True); gc.dyn_core(900.0, 2, end_step=True)
+    for t in oc.tiles:
+        _assert(H.compare(oc.eng[t], gc.eng[t], reg), 1e-8)
+    om = H.sub(gc.eng[1], "OMGA", gc.eng[1].get("OMGA"), 1, 24, 1, 24)
+    assert 1e-3 < np.abs(om).max() < 5.0                    # Pa/s: a synoptic-scale vertical motion field
+    g2 = H.CudaCube(case)
+    g2.dyn_core(900.0, 2); g2.dyn_core(900.0, 2, end_step=True)                 # call 1: direct; this state: the reference bits
+    g3 = H.CudaCube(case)
+    g3.dyn_core(900.0, 2, graph=True); g3.dyn_core(900.0, 2, graph=True, end_step=True)
+    g3b = g3.eng[2].get("OMGA")
+    assert np.array_equal(g2.eng[2].get("OMGA"), g3b)
+    oc.close(); gc.close(); g2.close(); g3.close()
+
+
 @pytest.mark.parametrize("beta", [0.0, 0.4])
 def test_hydrostatic_external_mode_damping(beta):
     """d_ext > 0 (0.02 is the reference's default outside SW_DYNAMICS builds) in the hydrostatic branch: delp at the cell corners

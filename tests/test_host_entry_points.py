@@ -147,7 +147,7 @@ def test_upload_state_dyn_core_download_state():
     fn = lib[0].fv3_dyn_core
     fn.restype = C.c_int
     assert fn(ctxs, 6, C.c_double(600.0), C.c_int(2), C.c_int(0)) == 0, eng[1].last_error()
-    assert fn(ctxs, 6, C.c_double(600.0), C.c_int(2), C.c_int(2)) == -2          # only bit 0 (FV3_DYN_GRAPH) is defined
+    assert fn(ctxs, 6, C.c_double(600.0), C.c_int(2), C.c_int(4)) == -2          # bits 0 (FV3_DYN_GRAPH) and 1 (FV3_DYN_END_STEP) are defined
     oc.dyn_core(600.0, 2)
     assert fn(ctxs, 6, C.c_double(600.0), C.c_int(2), C.c_int(1)) == 0           # second call as a CUDA graph (tests/test_cuda_graph_gpu.py)
     oc.dyn_core(600.0, 2)
