@@ -12,7 +12,8 @@
 // One call replaces the whole it-loop; all faces owned by this process advance in lockstep
 // (each on its own stream), exchanges are fv3_halo_exchange (device-local gathers and/or NCCL).
 // After the loop (:1300-1356): halo(heat_source) -> del2_cubed -> heating of pt (d_con > 0; csrc/dyn_post.cu).
-// Not included (documented in DESIGN.md): omega diagnostics (:1182-1215), Rayleigh friction, fast physics.
+// FV3_DYN_END_STEP: the omega diagnostic of the last substep (:409-422, :1182-1195, use_old_omega = T).
+// Not included (documented in DESIGN.md): use_old_omega = F, Rayleigh friction, fast physics.
 #include "fv3_ctx.hpp"
 #include <cstdlib>
 #include <algorithm>
