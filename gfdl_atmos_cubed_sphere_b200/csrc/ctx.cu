@@ -390,6 +390,7 @@ int fv3_pe_halo(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_pe_halo(c); if (r
 int fv3_gz_from_zh(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_gz_from_zh(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_nh_p_grad(fv3_ctx* c, double dt) { STAGE_PROLOGUE(c) int rc = stage_nh_p_grad(c, dt); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_del2_cubed(fv3_ctx* c, int field, double cd, int nmax) { STAGE_PROLOGUE(c) int rc = stage_del2_cubed(c, field, cd, nmax); if (rc) return rc; STAGE_EPILOGUE(c) }
+int fv3_omega_new(fv3_ctx* c, int phase, double dt) { STAGE_PROLOGUE(c) int rc = stage_omega_new(c, phase, dt); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_omega_begin(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_omega_begin(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_omega_end(fv3_ctx* c, double dt) { STAGE_PROLOGUE(c) int rc = stage_omega_end(c, dt); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_ext_mode_prepare(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_ext_mode_prepare(c); if (rc) return rc; STAGE_EPILOGUE(c) }

@@ -198,6 +198,7 @@ static int dyn_core_direct(fv3_ctx** ctxs, int nctx, double bdt, int n_split, bo
       continue;
     }
     const bool omega = last_step && end_step && !sw_advection;   // the omega diagnostic (dyn_core.F90:409-422, 1182-1195)
+    const bool omega_new = omega && !ctxs[0]->f.use_old_omega;    // ... in its convergence form (:735-742, 774-781, 1196-1214)
     if (hydrostatic) {   // geopk replaces the vertical solvers, one_grad_p the pressure gradient (dyn_core.F90:478-480, :905-907, :1017-1021)
       if (linked) {
         if (it == 1 && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;
@@ -210,7 +211,9 @@ static int dyn_core_direct(fv3_ctx** ctxs, int nctx, double bdt, int n_split, bo
       if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DIVGD_UCVC))) return rc;
       const bool ext_mode = ctxs[0]->f.d_ext > 0.;                                        // external-mode divergence damping
       if (ext_mode) { FORALL(stage_ext_mode_prepare(c)) }                                 // :745-747
+      if (omega_new) { FORALL(stage_omega_new(c, 0, dt)) }                                // :735-742
       FORALL(stage_d_sw(c, dt))
+      if (omega_new) { FORALL(stage_omega_new(c, 1, dt)) }                                // :774-781
       if (ext_mode) { FORALL(stage_ext_mode_divg2(c)) }                                   // :828-847
       if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT))) return rc;
       FORALL(stage_geopk(c, 0))
@@ -237,7 +240,9 @@ static int dyn_core_direct(fv3_ctx** ctxs, int nctx, double bdt, int n_split, bo
     FORALL(stage_riem_solver_c(c, dt2))                                                   // :531
     FORALL(stage_p_grad_c(c, dt2))                                                        // :562
     if (linked && (rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_DIVGD_UCVC))) return rc;   // :451,:565,:577-578
+    if (omega_new) { FORALL(stage_omega_new(c, 0, dt)) }                                  // :735-742
     FORALL(stage_d_sw(c, dt))                                                             // :666-812
+    if (omega_new) { FORALL(stage_omega_new(c, 1, dt)) }                                  // :774-781
     // delp, pt[, q_con] halos (:823-825 start, :851 complete): update_dz_d and Riem_Solver3 read the compute domain of delp, pt
     // only, so the exchange MAY run on the side stream underneath them (see `overlap` above)
     if (linked && (rc = (overlap ? fv3_halo_start(ctxs, nctx, FV3_HALO_DELP_PT) : fv3_halo_exchange(ctxs, nctx, FV3_HALO_DELP_PT)))) return rc;

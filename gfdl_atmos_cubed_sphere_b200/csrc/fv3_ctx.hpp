@@ -172,6 +172,7 @@ struct StageScope {
 
 // stage implementations (each enqueues kernels on c->stream)
 int stage_omega_begin(fv3_ctx* c);
+int stage_omega_new(fv3_ctx* c, int phase, double dt);
 int stage_omega_end(fv3_ctx* c, double dt);
 int stage_ext_mode_prepare(fv3_ctx* c);
 int stage_ext_mode_divg2(fv3_ctx* c);

@@ -531,9 +531,32 @@ __global__ void __launch_bounds__(TI* TJ) k_omega_old(Lay L, DevGrid G, const do
   }
   omga[o] = om + 0.5 * G2(rarea, i, j) * acc;
 }
+// use_old_omega = F (dyn_core.F90:735-742, 774-781, 1196-1214): phase 0 before d_sw: omga = delp; phase 1 after d_sw: times the
+// convergence of the area fluxes / dt; phase 2 at the end of the substep: running sum over k
+__global__ void __launch_bounds__(TI* TJ) k_omega_new(Lay L, DevGrid G, double* __restrict__ omga, const double* __restrict__ delp,
+                                                      const double* __restrict__ xfx, const double* __restrict__ yfx, int phase, double rdt) {
+  PLANE_IJK
+  if (i < L.is || i > L.ie || j < L.js || j > L.je) return;
+  const long long o = ko + LIDX(L, i, j);
+  if (phase == 0) { omga[o] = __ldg(delp + o); return; }
+  if (phase == 1) { omga[o] = omga[o] * (__ldg(xfx + o) - __ldg(xfx + o + 1) + __ldg(yfx + o) - __ldg(yfx + o + L.NI)) * G2(rarea, i, j) * rdt; return; }
+  if (k != 0) return;   // phase 2: one thread per column
+  double om = omga[o];
+  for (int kk = 1; kk < L.npz; kk++) { om = om + omga[o + (long long)kk * L.plane]; omga[o + (long long)kk * L.plane] = om; }
+}
+int stage_omega_new(fv3_ctx* c, int phase, double dt) {
+  StageScope ts(c, "OMEGA");
+  const Lay& L = c->L;
+  if (phase < 0 || phase > 2) return fv3_fail(c, -1, "omega_new: phase in 0..2");
+  k_omega_new<<<plane_grid(L, phase == 2 ? 1 : L.npz), dim3(TI, TJ), 0, c->stream>>>(L, c->G, c->fld[FV3_OMGA], c->fld[FV3_DELP], c->fld[FV3_XFX],
+                                                                                    c->fld[FV3_YFX], phase, 1. / dt);
+  c->launches++;
+  return 0;
+}
 int stage_omega_begin(fv3_ctx* c) {
   StageScope ts(c, "OMEGA");
   const Lay& L = c->L;
+  if (!c->f.use_old_omega) return 0;
   if (!c->d_pem) FV3_CUDA(c, cudaMalloc(&c->d_pem, (size_t)L.plane * (L.npz + 1) * sizeof(double)));
   k_pem<<<dim3((L.NI + TI - 1) / TI, (L.NJ + TJ - 1) / TJ), dim3(TI, TJ), 0, c->stream>>>(L, c->fld[FV3_DELP], c->d_pem, c->f.ptop);
   c->launches++;
@@ -542,7 +565,7 @@ int stage_omega_begin(fv3_ctx* c) {
 int stage_omega_end(fv3_ctx* c, double dt) {
   StageScope ts(c, "OMEGA");
   const Lay& L = c->L;
-  if (!c->f.use_old_omega) return fv3_fail(c, -2, "omega diagnostic: use_old_omega = F not supported");
+  if (!c->f.use_old_omega) return stage_omega_new(c, 2, dt);
   if (!c->d_pem) return fv3_fail(c, -1, "omega_end without omega_begin");
   if (!c->G.ec1 || !c->G.ec2 || !c->G.en1 || !c->G.en2) return fv3_fail(c, -1, "omega diagnostic: fv3_grid_t.ec1 / ec2 / en1 / en2 were not given to fv3_create");
   double* pb = c->scr[0];

@@ -221,6 +221,9 @@ int fv3_pt_to_theta(fv3_ctx *ctx, double zvir);
 /* the two halves of the omega diagnostic (FV3_DYN_END_STEP), for stage-by-stage drivers: before / after the last substep */
 int fv3_omega_begin(fv3_ctx *ctx);
 int fv3_omega_end(fv3_ctx *ctx, double dt);
+/* use_old_omega = F (dyn_core.F90:735-742, 774-781, 1196-1214): phase 0 before d_sw (omga = delp), 1 after it (times the convergence
+ * of the area fluxes / dt); fv3_omega_end then forms the running sum over k */
+int fv3_omega_new(fv3_ctx *ctx, int phase, double dt);
 int fv3_ext_mode_prepare(fv3_ctx *ctx);
 int fv3_ext_mode_divg2(fv3_ctx *ctx);
 int fv3_lagrangian_to_eulerian(fv3_ctx *ctx, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr);
@@ -315,7 +318,7 @@ int fv3_plane_index(const fv3_ctx *ctx, int i, int j);
 #define FV3_DYN_GRAPH 1
 /* FV3_DYN_END_STEP: this is the last dyn_core call of the k_split loop (the reference's end_step argument): on its last substep the
  * omega diagnostic is formed (dyn_core.F90:409-422, 1182-1195: omga = (pe - pem) / dt + adv_pe(ua, va, pem), use_old_omega = T;
- * use_old_omega = F is an error).  Without the bit omga is left untouched.  Needs ec1, ec2, en1, en2 in fv3_grid_t. */
+ * use_old_omega = F: the convergence form, :735-742, 774-781, 1196-1214).  Without the bit omga is left untouched.  Needs ec1, ec2, en1, en2 in fv3_grid_t. */
 #define FV3_DYN_END_STEP 2
 int fv3_dyn_core(fv3_ctx **ctxs, int nctx, double bdt, int n_split, int flags);
 

@@ -397,7 +397,9 @@ int fv3o_del2_cubed(fv3o_ctx* c, int field, double cd, int nmax) {
 }
 // fv_dynamics.F90:303-328, :377-398: specific humidity in FV3_WORK_Q (read only when zvir != 0 is meaningful; it is multiplied anyway)
 // omega diagnostic of the last substep of the last dyn_core call (end_step): before the substep ...
+int fv3o_omega_new(fv3o_ctx* c, int phase, double dt);
 int fv3o_omega_begin(fv3o_ctx* c) {
+  if (!c->f.use_old_omega) return 0;
   Bd bd(c->b);
   c->pem.assign(c->fld[FV3_PE].size(), 0.);
   pem_from_delp(c->pem.data(), F3(c, FV3_DELP), c->f.ptop, bd);
@@ -405,10 +407,32 @@ int fv3o_omega_begin(fv3o_ctx* c) {
 }
 // ... and after it (use_old_omega = T, dyn_core.F90:1182-1195)
 int fv3o_omega_end(fv3o_ctx* c, double dt) {
-  if (!c->f.use_old_omega) return -2;
+  if (!c->f.use_old_omega) return fv3o_omega_new(c, 2, dt);
   if (c->pem.size() != c->fld[FV3_PE].size() || !c->g.ec1 || !c->g.ec2 || !c->g.en1 || !c->g.en2) return -1;
   Bd bd(c->b); Grid g(c->g, bd);
   omega_old(F3(c, FV3_OMGA), c->fld[FV3_PE].data(), c->pem.data(), F3(c, FV3_UA), F3(c, FV3_VA), 1. / dt, g, bd);
+  return 0;
+}
+// use_old_omega = F (dyn_core.F90:735-742, 774-781, 1196-1214): phase 0 before d_sw: omga = delp; phase 1 after d_sw: times the
+// convergence of the area fluxes / dt; phase 2 at the end of the substep: running sum over k
+int fv3o_omega_new(fv3o_ctx* c, int phase, double dt) {
+  Bd bd(c->b); Grid g(c->g, bd);
+  V3 omga = F3(c, FV3_OMGA), delp = F3(c, FV3_DELP), xfx = F3(c, FV3_XFX), yfx = F3(c, FV3_YFX);
+  const double rdt = 1. / dt;
+  if (phase == 0) {
+    for (int k = 1; k <= bd.npz; k++) for (int j = bd.js; j <= bd.je; j++) for (int i = bd.is; i <= bd.ie; i++) omga(i, j, k) = delp(i, j, k);
+  } else if (phase == 1) {
+    for (int k = 1; k <= bd.npz; k++)
+      for (int j = bd.js; j <= bd.je; j++)
+        for (int i = bd.is; i <= bd.ie; i++)
+          omga(i, j, k) = omga(i, j, k) * (xfx(i, j, k) - xfx(i + 1, j, k) + yfx(i, j, k) - yfx(i, j + 1, k)) * g.rarea(i, j) * rdt;
+  } else {
+    for (int j = bd.js; j <= bd.je; j++)
+      for (int i = bd.is; i <= bd.ie; i++) {
+        double om = omga(i, j, 1);
+        for (int k = 2; k <= bd.npz; k++) { om = om + omga(i, j, k); omga(i, j, k) = om; }
+      }
+  }
   return 0;
 }
 // fv_operators.F90 map_scalar (mode 0) / map1_ppm (1) / map1_q2 (2) of FV3_WORK_Q on the compute domain: from the layers of FV3_PE to

@@ -229,8 +229,9 @@ class OracleCube:
             if it == 1:
                 self.halo("DELP_PT")
             omega = last and end_step and self.case.flags.get("sw_test_case") != 1
+            omega_new = omega and not self.case.flags.get("use_old_omega", 1)
             if omega:
-                self.all("omega_begin")          # dyn_core.F90:409-422: pem from delp before the last substep
+                self.all("omega_begin")          # dyn_core.F90:409-422: pem from delp before the last substep (use_old_omega = T)
             if self.case.flags.get("sw_test_case") == 1:   # SW_DYNAMICS, test_case 1: d_sw + delp halo only (dyn_core.F90:394, 569, 998)
                 run("D_SW", "d_sw", dt)
                 self.halo("DELP_PT")
@@ -243,7 +244,11 @@ class OracleCube:
                 self.halo("DIVGD_UCVC")
                 if self.case.flags.get("d_ext", 0.0) > 0.0:
                     self.all("ext_mode_prepare")        # dyn_core.F90:745-747: delp at the cell corners, before d_sw
+                if omega_new:
+                    self.all("omega_new", 0, dt)     # use_old_omega = F (dyn_core.F90:735-742): omga = delp before d_sw
                 run("D_SW", "d_sw", dt)
+                if omega_new:
+                    self.all("omega_new", 1, dt)     # :774-781: times the convergence of the area fluxes / dt
                 if self.case.flags.get("d_ext", 0.0) > 0.0:
                     self.all("ext_mode_divg2")          # :828-847: mass-weighted vertical mean of the divergence
                 self.halo("DELP_PT")
@@ -271,7 +276,11 @@ class OracleCube:
             run("Riem_Solver_C", "riem_solver_c", dt2)
             run("PG_C", "p_grad_c", dt2)
             self.halo("DIVGD_UCVC")
+            if omega_new:
+                self.all("omega_new", 0, dt)     # use_old_omega = F (dyn_core.F90:735-742): omga = delp before d_sw
             run("D_SW", "d_sw", dt)
+            if omega_new:
+                self.all("omega_new", 1, dt)     # :774-781: times the convergence of the area fluxes / dt
             self.halo("DELP_PT")
             run("UPDATE_DZ", "update_dz_d", dt)
             run("Riem_Solver3", "riem_solver3", dt, 1 if last else 0)

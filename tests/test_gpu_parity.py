@@ -458,6 +458,21 @@ def test_tracer_2d_after_dyn_core(hord):
 
 
 @pytest.mark.parametrize("hydro", [0, 1])
+def test_omega_diagnostic_convergence_form(hydro):
+    """use_old_omega = F (dyn_core.F90:735-742, 774-781, 1196-1214): omga = delp before the last d_sw, times the convergence of its
+    area fluxes / dt after it, summed downward at the end of the substep."""
+    case = H.Case(24, 8, "A", state="baroclinic", flags_override=dict(hydrostatic=hydro, use_old_omega=0))
+    oc, gc = H.OracleCube(case), H.CudaCube(case)
+    b = case.bounds
+    oc.dyn_core(900.0, 2, end_step=True); gc.dyn_core(900.0, 2, end_step=True)
+    for t in oc.tiles:
+        _assert(H.compare(oc.eng[t], gc.eng[t], {"OMGA": (b["is_"], b["ie"], b["js"], b["je"])}), 1e-9)
+    om = H.sub(gc.eng[1], "OMGA", gc.eng[1].get("OMGA"), 1, 24, 1, 24)
+    assert 1e-3 < np.abs(om).max() < 5.0
+    oc.close(); gc.close()
+
+
+@pytest.mark.parametrize("hydro", [0, 1])
 def test_omega_diagnostic_of_the_end_step(hydro):
     """FV3_DYN_END_STEP: omga = (pe - pem) / dt + adv_pe(ua, va, pem) on the last substep (dyn_core.F90:409-422, 1182-1195, 1529-1630;
     use_old_omega = T, the reference's default) -- pem from delp before the substep, a2b_ord2 of its interfaces, the gradient by

@@ -341,3 +341,23 @@ def test_split_p_grad_reduces_to_nh_p_grad_and_keeps_the_jet_steady(built):
         res[beta] = max(np.abs(H.sub(oc.eng[t], "U", oc.eng[t].get("U") - u0[t], 1, 24, 1, 25)).max() for t in oc.tiles)
         oc.close()
     assert res[0.4] < 1.0 and abs(res[0.4] - res[0.0]) < 0.3, res
+
+
+def test_the_two_omega_diagnostics_agree():
+    """dyn_core has two formulations of omega for the physics (dyn_core.F90:1182-1214): use_old_omega = T, the change of the
+    interface pressure over the last substep plus the advective term adv_pe (a2b_ord2, Green's theorem with the en / ec unit
+    vectors), and use_old_omega = F, the downward sum of delp times the convergence of d_sw's area fluxes.  They discretise the
+    same quantity independently, so their agreement pins both restatements (and the exported unit vectors): correlation > 0.999
+    and the same extreme values to 2 % in a hydrostatic baroclinic-wave run."""
+    import numpy as np
+    import harness as H
+    om = {}
+    for old in (1, 0):
+        case = H.Case(24, 8, "A", state="baroclinic", flags_override=dict(hydrostatic=1, use_old_omega=old))
+        oc = H.OracleCube(case)
+        oc.dyn_core(900.0, 2, end_step=True)
+        om[old] = np.stack([H.sub(oc.eng[t], "OMGA", oc.eng[t].get("OMGA"), 1, 24, 1, 24) for t in oc.tiles])
+        oc.close()
+    a, b = om[1].ravel(), om[0].ravel()
+    assert np.corrcoef(a, b)[0, 1] > 0.999
+    assert abs(a.min() - b.min()) < 0.02 * abs(a.min()) and abs(a.max() - b.max()) < 0.02 * abs(a.max())
