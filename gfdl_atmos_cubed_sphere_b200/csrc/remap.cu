@@ -3,7 +3,7 @@
 // Reference semantics: model/fv_mapz.F90:56-845 (Lagrangian_to_Eulerian) and the column operators of model/fv_operators.F90:
 // map_scalar (:40-134), map1_ppm (:137-229), map1_q2 (:352-443), scalar_profile (:546-916), cs_profile (:919-1300),
 // cs_limiters (:1303-1378).  Built: remap_te = F, moist_kappa = F, consv = 0 (no energy fixer), dry air (the last-step T_v -> T
-// conversion is the identity), abs(kord) in 8..13, kord_wz > 0 (iv = -2), at most one tracer (FV3_WORK_Q, no fillz); anything
+// conversion is the identity), abs(kord) in 8..15, kord_wz > 0 (iv = -2), at most one tracer (FV3_WORK_Q, no fillz); anything
 // else is an error (-2), never a silent fall-back.
 //
 // Design: column-parallel like the vertical solvers -- one thread per column, consecutive threads on consecutive i, so every
@@ -114,7 +114,7 @@ __device__ void profile(const Col& C, int km, const P1& pe1, double qs, int iv, 
   for (int k = 3; k <= km - 1; k++) {
     const double lo = dmin(A1(k - 1), A1(k)), hi = dmax(A1(k - 1), A1(k));
     double qk = QI(k);
-    if (GAM(k - 1) * GAM(k + 1) > 0.) { qk = dmin(qk, hi); qk = dmax(qk, lo); }
+    if (ak >= 14 || GAM(k - 1) * GAM(k + 1) > 0.) { qk = dmin(qk, hi); qk = dmax(qk, lo); }
     else if (GAM(k - 1) > 0.) qk = dmax(qk, lo);
     else { qk = dmin(qk, hi); if (iv == 0) qk = dmax(0., qk); }
     QI(k) = qk;
@@ -206,11 +206,17 @@ __device__ void profile(const Col& C, int km, const P1& pe1, double qs, int iv, 
         }
         A4(k) = a6_a(k);
         break;
-      default:   // 13
+      case 13:
         A4(k) = a6_a(k);
         break;
+      case 14:   // strict monotonicity constraint (A4 as the flag loop left it)
+        cs_limiters(C, k, f0 & 1, 2);
+        break;
+      default:   // 15
+        cs_limiters(C, k, f0 & 1, 1);
+        break;
     }
-    if (iv == 0) cs_limiters(C, k, f0 & 1, 0);
+    if (iv == 0 && ak <= 13) cs_limiters(C, k, f0 & 1, 0);
   }
   // bottom two layers (:898-914 / :1281-1298)
   if (iv == 0) A3(km) = dmax(0., A3(km));
@@ -389,7 +395,7 @@ __global__ void __launch_bounds__(CB) k_remap_work_q(Lay L, L2E a, Scr S, int mo
 
 int check_kord(fv3_ctx* c, int kord, const char* what) {
   const int ak = kord < 0 ? -kord : kord;
-  if (ak < 8 || ak > 13) return fv3_fail(c, -2, std::string("remap: ") + what + " outside 8..13 (ppm_profile and the strictly monotone schemes are not built)");
+  if (ak < 8 || ak > 15) return fv3_fail(c, -2, std::string("remap: ") + what + " outside 8..15 (ppm_profile, kord <= 7, is not built)");
   return 0;
 }
 

@@ -210,7 +210,7 @@ int fv3_pt_to_theta(fv3_ctx *ctx, double zvir);
  * fv3_lagrangian_to_eulerian: fv_mapz.F90:56-845 on one face after fv3_dyn_core (which leaves pe incl. its one-cell halo, peln,
  * pk, ws and omga current): delp <- ak/bk hybrid levels, pt (theta_v in; theta_v out, or T_v when last_step), w, delz, u, v,
  * [the tracer in FV3_WORK_Q], pe, peln, pk, pkz remapped; omga interpolated when last_step.  Built: remap_te = F, moist_kappa = F,
- * consv = 0 (no energy fixer), dry air (the last-step T_v -> T conversion is the identity), abs(kord_*) in 8..13 (cs_profile /
+ * consv = 0 (no energy fixer), dry air (the last-step T_v -> T conversion is the identity), abs(kord_*) in 8..15 (cs_profile /
  * scalar_profile), kord_wz > 0; everything else returns -2.  kord_tm < 0: T_v is mapped in log p (map_scalar), > 0: theta_v in p.
  * fv3_remap_work_q: the column operators alone on FV3_WORK_Q, from the layers of FV3_PE to the hybrid levels -- mode 0 map_scalar
  * (fv_operators.F90:40), 1 map1_ppm (:137; iv = -2 takes its lower boundary value from FV3_WS), 2 map1_q2 (:352). */

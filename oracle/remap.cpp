@@ -4,8 +4,8 @@
 // model/fv_operators.F90: map_scalar (:40-134), map1_ppm (:137-229), map1_q2 (:352-443), scalar_profile (:546-916),
 // cs_profile (:919-1300), cs_limiters (:1303-1378).  Scope (everything else is refused with -2 by the C entry point):
 //   remap_te = F, moist_kappa = F, consv = 0 (no energy fixer), no intermediate physics, dry (no specific humidity: the last-step
-//   conversion T_v -> T is the identity, i.e. `adiabatic`), abs(kord) in 8..13 (the cs / scalar profiles; ppm_profile for kord <= 7
-//   and the strictly monotone 14-16 are not restated), kord_wz > 0 (iv = -2; the iv = -3 branch of cs_profile reads an unset
+//   conversion T_v -> T is the identity, i.e. `adiabatic`), abs(kord) in 8..15 (the cs / scalar profiles; ppm_profile for kord <= 7
+//   is not restated), kord_wz > 0 (iv = -2; the iv = -3 branch of cs_profile reads an unset
 //   gam(km), :969-985), at most one tracer (FV3_WORK_Q, iv = 0, no fillz).
 // The Fortran vectorises every loop over i; here one column is processed at a time (same operations on the same operands in the
 // same order for every element).  Parity unpinned: the reference holds no test or golden vector for these routines.
@@ -56,7 +56,7 @@ void cs_limiters(bool extm, A4& a4, int k, int iv) {
 // delp(1:km), a4(1,:) = the layer means on entry.  Returns -2 for a scheme outside the restated set.
 int profile(double qs, A4& a4, const std::vector<double>& delp, int km, int iv, int kord, double qmin, bool scalar) {
   const int ak = std::abs(kord);
-  if (ak < 8 || ak > 13 || iv == -3) return -2;
+  if (ak < 8 || ak > 15 || iv == -3) return -2;
   std::vector<double> gam(km + 3, 0.), q(km + 3, 0.);
   std::vector<char> extm(km + 2, 0), ext5(km + 2, 0), ext6(km + 2, 0);
   if (iv == -2) {   // lower boundary condition q(km+1) = qs (:570-592 / :941-963)
@@ -95,7 +95,7 @@ int profile(double qs, A4& a4, const std::vector<double>& delp, int km, int iv, 
   q[2] = std::max(q[2], std::min(a4(1, 1), a4(1, 2)));
   for (int k = 2; k <= km; k++) gam[k] = a4(1, k) - a4(1, k - 1);
   for (int k = 3; k <= km - 1; k++) {
-    if (gam[k - 1] * gam[k + 1] > 0.) {   // (abs(kord) >= 14 is outside the restated set)
+    if (ak >= 14 || gam[k - 1] * gam[k + 1] > 0.) {   // all interfaces for the strictly monotone schemes, else away from extrema
       q[k] = std::min(q[k], std::max(a4(1, k - 1), a4(1, k)));
       q[k] = std::max(q[k], std::min(a4(1, k - 1), a4(1, k)));
     } else if (gam[k - 1] > 0.) {
@@ -186,8 +186,14 @@ int profile(double qs, A4& a4, const std::vector<double>& delp, int km, int iv, 
       case 13:
         a4(4, k) = a6_a(k);
         break;
+      case 14:   // strict monotonicity constraint (a4(4) as the flag loop left it: 3 * x0)
+        cs_limiters(extm[k], a4, k, 2);
+        break;
+      case 15:
+        cs_limiters(extm[k], a4, k, 1);
+        break;
     }
-    if (iv == 0) cs_limiters(extm[k], a4, k, 0);   // (abs(kord) <= 13)
+    if (iv == 0 && ak <= 13) cs_limiters(extm[k], a4, k, 0);
   }
   // bottom two layers (:898-914 / :1281-1298)
   if (iv == 0) a4(3, km) = std::max(0., a4(3, km));

@@ -15,7 +15,7 @@ import pytest
 
 import harness as H
 
-KORDS = [8, 9, 10, 11, 12, 13]
+KORDS = [8, 9, 10, 11, 12, 13, 14, 15]
 N, NPZ = 12, 16
 
 
@@ -114,7 +114,7 @@ def test_tracer_remap_keeps_a_positive_field_non_negative(kord):
 def test_unsupported_schemes_are_errors():
     case, oc = _cube(substeps=0)
     e = oc.eng[1]
-    for kord in (4, 7, 14, 16):
+    for kord in (4, 7, 16, 17):
         with pytest.raises(RuntimeError):
             e.call("remap_work_q", 0, 1, kord, 0.0)
     with pytest.raises(RuntimeError):
