@@ -147,3 +147,29 @@ def test_fv_dynamics_step_matches_the_oracle(hord_tr):
     T = H.sub(gc.eng[1], "PT", gc.eng[1].get("PT"), 1, N, 1, N)
     assert 150.0 < T.min() and T.max() < 350.0                  # a temperature again
     oc.close(); gc.close()
+
+
+@pytest.mark.parametrize("kord", [8, 10, 11, 13, 14])
+def test_remap_known_answer_linear_profile_on_the_gpu(kord):
+    """KNOWN ANSWER on the device, no oracle involved: a profile linear in pressure must be remapped to the analytic layer means of
+    the new levels by every scheme (exact interface values, exact parabola, limiters inactive on a monotone profile)."""
+    case = H.Case(N, NPZ, "A", state="baroclinic")
+    gc = H.CudaCube(case)
+    gc.dyn_core(900.0, 2)                                   # deforms the Lagrangian surfaces and leaves pe current
+    for t in (1, 4):
+        e = gc.eng[t]
+        pe = np.transpose(H.sub(e, "PE", e.get("PE"), 1, N, 1, N), (1, 0, 2))       # (k, j, i)
+        p2 = case.ak[:, None, None] + case.bk[:, None, None] * pe[-1][None]
+        p2[0] = case.ak[0]; p2[-1] = pe[-1]
+        assert np.abs(np.diff(pe, axis=0) - np.diff(p2, axis=0)).max() > 1e-3
+        mean = lambda p: 2.0 + 3.0e-5 * 0.5 * (p[:-1] + p[1:])
+        full = e.get("WORK_Q")
+        H.sub(e, "WORK_Q", full, 1, N, 1, N)[...] = mean(pe)
+        e.put("WORK_Q", full)
+        for mode, iv in ((0, 1), (1, 1), (2, 0)):
+            q0 = e.get("WORK_Q")
+            e.call("remap_work_q", mode, iv, kord, 0.0)
+            out = H.sub(e, "WORK_Q", e.get("WORK_Q"), 1, N, 1, N)
+            assert np.abs(out - mean(p2)).max() / np.abs(mean(p2)).max() < 1e-12, (t, mode)
+            e.put("WORK_Q", q0)
+    gc.close()

@@ -163,3 +163,52 @@ def test_lagrangian_to_eulerian_invariants(kord_tm, last, hydro):
         u1 = _sec(e, "U", 0, 1)
         assert np.abs(u1 - u0).max() < 0.5 and np.isfinite(u1).all()
     oc.close()
+
+
+def _analytic_case(e, case, coef):
+    """q(p) = c0 + c1 p + c2 p^2 as exact layer means on the deformed levels of engine e; returns (q, expected means on the
+    hybrid target levels)"""
+    pe = _pe(e)
+    p2 = _hybrid(case, pe)
+    c0, c1, c2 = coef
+
+    def mean(p):
+        a, b = p[:-1], p[1:]
+        return c0 + c1 * 0.5 * (a + b) + c2 * (a * a + a * b + b * b) / 3.0
+    return mean(pe), mean(p2)
+
+
+@pytest.mark.parametrize("kord", KORDS)
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_remap_known_answer_linear_profile(kord, mode):
+    """KNOWN ANSWER (independent of any restatement): a profile linear in pressure is reproduced exactly by the 4th-order interface
+    values and the parabolic sub-grid profile, and its monotonicity keeps every limiter of every scheme inactive, so the remapped
+    layer means must equal the analytic means on the new levels -- in the interior; the top / bottom two layers use one-sided
+    closures that are exact for a linear profile as well."""
+    case, oc = _cube(substeps=2)
+    e = oc.eng[5]
+    q, want = _analytic_case(e, case, (2.0, 3.0e-5, 0.0))
+    _set_q(e, q)
+    e.call("remap_work_q", mode, 0 if mode == 2 else 1, kord, 0.0)
+    out = _sec(e, "WORK_Q")
+    assert np.abs(out - want).max() / np.abs(want).max() < 1e-12
+    oc.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_remap_known_answer_quadratic_profile(mode):
+    """KNOWN ANSWER: with the unlimited scheme (kord 13) a profile quadratic in pressure is remapped exactly (the interface solver
+    is exact for cubics, the parabola for quadratics) away from the bottom, whose closure is second order: its error (6e-7 here)
+    decays by ~4 per level through the tridiagonal solve, so the upper levels see the exact answer."""
+    case, oc = _cube(substeps=2)
+    e = oc.eng[2]
+    q, want = _analytic_case(e, case, (1.0, 2.0e-5, 1.5e-10))
+    _set_q(e, q)
+    e.call("remap_work_q", mode, 1, 13, 0.0)
+    out = _sec(e, "WORK_Q")
+    err = np.abs(out - want) / np.abs(want).max()
+    lev = err.max(axis=(1, 2))
+    assert lev[:6].max() < 5e-11, lev
+    assert lev.max() < 1e-5, lev
+    assert all(lev[k] < 0.6 * lev[k + 1] for k in range(9, 13)), lev          # geometric decay away from the bottom closure
+    oc.close()
