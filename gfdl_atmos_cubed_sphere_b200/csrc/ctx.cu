@@ -262,12 +262,16 @@ void fv3_destroy(fv3_ctx* c) {
   cudaStreamSynchronize(c->stream);
   halo_destroy(c);
   fv3_free_graphs(c);
+  if (!c->tracers.empty()) {   // the tracer table owns every tracer array; fld[FV3_WORK_Q] is an alias of one of them
+    for (double* t : c->tracers) cudaFree(t);
+    c->fld[FV3_WORK_Q] = nullptr;
+  }
   for (int i = 0; i < FV3_NUM_FIELDS; i++) cudaFree(c->fld[i]);
   double* alts[6] = {c->alt_delp, c->alt_pt, c->alt_w, c->alt_u, c->alt_v, c->alt_qcon};
   for (auto p : alts) cudaFree(p);
   for (int i = 0; i < fv3_ctx::NSCR; i++) cudaFree(c->scr[i]);
   for (auto p : c->metric_alloc) cudaFree(p);
-  cudaFree(c->d_stage); cudaFree(c->d_kint); cudaFree(c->d_kdbl); cudaFree(c->d_dp_ref); cudaFree(c->d_edge_tab); cudaFree(c->d_rff); cudaFree(c->d_akbk); cudaFree(c->d_divg2); cudaFree(c->d_pem);
+  cudaFree(c->d_stage); cudaFree(c->d_kint); cudaFree(c->d_kdbl); cudaFree(c->d_dp_ref); cudaFree(c->d_edge_tab); cudaFree(c->d_rff); cudaFree(c->d_akbk); cudaFree(c->d_divg2); cudaFree(c->d_pem); cudaFree(c->d_qtr_tab);
   for (auto& kv : c->timers) { cudaEventDestroy(kv.second.e0); cudaEventDestroy(kv.second.e1); }
   cudaStreamDestroy(c->stream);
   delete c;
@@ -390,6 +394,31 @@ int fv3_pe_halo(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_pe_halo(c); if (r
 int fv3_gz_from_zh(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_gz_from_zh(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_nh_p_grad(fv3_ctx* c, double dt) { STAGE_PROLOGUE(c) int rc = stage_nh_p_grad(c, dt); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_del2_cubed(fv3_ctx* c, int field, double cd, int nmax) { STAGE_PROLOGUE(c) int rc = stage_del2_cubed(c, field, cd, nmax); if (rc) return rc; STAGE_EPILOGUE(c) }
+// ---- tracers: nq arrays of the shape of FV3_WORK_Q; the selected one is what FV3_WORK_Q names
+int fv3_set_num_tracers(fv3_ctx* c, int nq) {
+  if (!c || nq < 1 || nq > 64) return -1;
+  FV3_CUDA(c, cudaSetDevice(c->device));
+  if (c->tracers.empty()) c->tracers.push_back(c->fld[FV3_WORK_Q]);
+  const size_t bytes = (size_t)c->L.plane * c->dim[FV3_WORK_Q].nk * sizeof(double);
+  while ((int)c->tracers.size() < nq) {
+    double* d = nullptr;
+    FV3_CUDA(c, cudaMalloc(&d, bytes));
+    FV3_CUDA(c, cudaMemsetAsync(d, 0, bytes, c->stream));
+    c->tracers.push_back(d);
+  }
+  if (c->tracer_sel >= nq) { c->tracer_sel = 0; c->fld[FV3_WORK_Q] = c->tracers[0]; }
+  while ((int)c->tracers.size() > nq) { FV3_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->tracers.back()); c->tracers.pop_back(); }
+  return 0;
+}
+int fv3_num_tracers(const fv3_ctx* c) { return c ? (c->tracers.empty() ? 1 : (int)c->tracers.size()) : -1; }
+int fv3_select_tracer(fv3_ctx* c, int iq) {
+  if (!c) return -1;
+  if (c->tracers.empty()) c->tracers.push_back(c->fld[FV3_WORK_Q]);
+  if (iq < 0 || iq >= (int)c->tracers.size()) return fv3_fail(c, -1, "select_tracer: no such tracer (fv3_set_num_tracers first)");
+  c->tracer_sel = iq;
+  c->fld[FV3_WORK_Q] = c->tracers[iq];
+  return 0;
+}
 int fv3_omega_new(fv3_ctx* c, int phase, double dt) { STAGE_PROLOGUE(c) int rc = stage_omega_new(c, phase, dt); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_omega_begin(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_omega_begin(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_omega_end(fv3_ctx* c, double dt) { STAGE_PROLOGUE(c) int rc = stage_omega_end(c, dt); if (rc) return rc; STAGE_EPILOGUE(c) }

@@ -287,8 +287,8 @@ extern "C" int fv3_del2_cubed_cube(fv3_ctx** ctxs, int nctx, int field, double c
 // ---- fv_dynamics: the k_split loop on device-resident state ------------------------------------
 // Reference semantics: model/fv_dynamics.F90:303-398 (entry: pkz, pt -> theta_v), :445-662 (n_map loop: dp1 = delp -> dyn_core ->
 // tracer_2d -> Lagrangian_to_Eulerian -> on the last step the omega filter).  Dry, adiabatic subset: zvir * q_v = 0, no
-// moist_kappa / inline physics / energy fixer (consv_te = 0), at most one tracer (FV3_WORK_Q, advected with hord_tr and remapped
-// with kord_tr when hord_tr != 0).  pt is temperature on entry and on exit.
+// moist_kappa / inline physics / energy fixer (consv_te = 0), the context's tracers (fv3_set_num_tracers; advected with hord_tr and remapped with kord_tr
+// when hord_tr != 0).  pt is temperature on entry and on exit.
 extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_out);
 extern "C" int fv3_fv_dynamics(fv3_ctx** ctxs, int nctx, double bdt, int k_split, int n_split, int kord_mt, int kord_wz, int kord_tm,
                                int kord_tr, int hord_tr, int nf_omega, int flags) {
@@ -303,7 +303,7 @@ extern "C" int fv3_fv_dynamics(fv3_ctx** ctxs, int nctx, double bdt, int k_split
     FORALL(stage_copy_field(c, FV3_DP1, FV3_DELP))                                        // :473-481 (compute domain + halo)
     if ((rc = fv3_dyn_core(ctxs, nctx, mdt, n_split, (flags & FV3_DYN_GRAPH) | (last_step ? FV3_DYN_END_STEP : 0)))) return rc;   // :495-502
     if (hord_tr != 0 && (rc = fv3_tracer_2d(ctxs, nctx, hord_tr, nullptr))) return rc;    // :512-535
-    FORALL(stage_lagrangian_to_eulerian(c, last_step, kord_mt, kord_wz, kord_tm, hord_tr != 0, kord_tr))   // :578-625
+    FORALL(stage_lagrangian_to_eulerian(c, last_step, kord_mt, kord_wz, kord_tm, hord_tr != 0 ? std::max<int>(1, (int)c->tracers.size()) : 0, kord_tr))   // :578-625
     if (last_step && nf_omega > 0) {                                                      // :658-662
       const double cd = 0.18 * ctxs[0]->G.da_min;
       if ((rc = fv3_del2_cubed_cube(ctxs, nctx, FV3_OMGA, cd, nf_omega))) return rc;

@@ -3,7 +3,7 @@
 // Reference semantics: model/fv_mapz.F90:56-845 (Lagrangian_to_Eulerian) and the column operators of model/fv_operators.F90:
 // map_scalar (:40-134), map1_ppm (:137-229), map1_q2 (:352-443), scalar_profile (:546-916), cs_profile (:919-1300),
 // cs_limiters (:1303-1378).  Built: remap_te = F, moist_kappa = F, consv = 0 (no energy fixer), dry air (the last-step T_v -> T
-// conversion is the identity), abs(kord) in 8..15, kord_wz > 0 (iv = -2), at most one tracer (FV3_WORK_Q, no fillz); anything
+// conversion is the identity), abs(kord) in 8..15, kord_wz > 0 (iv = -2), the tracers of the context's table (no fillz); anything
 // else is an error (-2), never a silent fall-back.
 //
 // Design: column-parallel like the vertical solvers -- one thread per column, consecutive threads on consecutive i, so every
@@ -229,8 +229,9 @@ __device__ void profile(const Col& C, int km, const P1& pe1, double qs, int iv, 
 
 // the conservative mapping loop (fv_operators.F90:88-132 = 183-227 = 399-441): P1 source, P2 target interface pressures;
 // out(k, value) stores layer k.  div_dp2: map1_q2 divides by the tabulated target thickness -- the same difference here.
+// mapn: the operation order of mapn_tracer (:276-336), which fv_mapz uses for nq > 5 tracers
 template <class P1, class P2, class Out>
-__device__ void map_column(const Col& C, int km, const P1& pe1, const P2& pe2, Out&& out) {
+__device__ void map_column(const Col& C, int km, const P1& pe1, const P2& pe2, Out&& out, bool mapn = false) {
   int k0 = 1;
   for (int k = 1; k <= km; k++) {
     const double t = pe2(k), b = pe2(k + 1);
@@ -244,17 +245,28 @@ __device__ void map_column(const Col& C, int km, const P1& pe1, const P2& pe2, O
         const double a2 = A2(l), a3 = A3(l), a4 = A4(l);
         if (b <= p1) {
           const double pr = (b - p0) / dpl;
-          out(k, a2 + 0.5 * (a4 + a3 - a2) * (pr + pl) - a4 * r3 * (pr * (pr + pl) + pl * pl));
+          if (mapn) {
+            double fac1 = pr + pl;
+            const double fac2 = r3 * (pr * fac1 + pl * pl);
+            fac1 = 0.5 * fac1;
+            out(k, a2 + (a4 + a3 - a2) * fac1 - a4 * fac2);
+          } else out(k, a2 + 0.5 * (a4 + a3 - a2) * (pr + pl) - a4 * r3 * (pr * (pr + pl) + pl * pl));
           k0 = l;
           done = true;
         } else {
-          qsum = (p1 - t) * (a2 + 0.5 * (a4 + a3 - a2) * (1. + pl) - a4 * (r3 * (1. + pl * (1. + pl))));
+          if (mapn) {
+            double fac1 = 1. + pl;
+            const double fac2 = r3 * (1. + pl * fac1);
+            fac1 = 0.5 * fac1;
+            qsum = (p1 - t) * (a2 + (a4 + a3 - a2) * fac1 - a4 * fac2);
+          } else qsum = (p1 - t) * (a2 + 0.5 * (a4 + a3 - a2) * (1. + pl) - a4 * (r3 * (1. + pl * (1. + pl))));
           for (int m = l + 1; m <= km; m++) {
             const double m0 = pe1(m), m1 = pe1(m + 1);
             if (b > m1) qsum = qsum + (m1 - m0) * A1(m);
             else {
               const double dp = b - m0, esl = dp / (m1 - m0);
-              qsum = qsum + dp * (A2(m) + 0.5 * esl * (A3(m) - A2(m) + A4(m) * (1. - r23 * esl)));
+              if (mapn) { const double fac1 = 0.5 * esl, fac2 = 1. - r23 * esl; qsum = qsum + dp * (A2(m) + fac1 * (A3(m) - A2(m) + A4(m) * fac2)); }
+              else qsum = qsum + dp * (A2(m) + 0.5 * esl * (A3(m) - A2(m) + A4(m) * (1. - r23 * esl)));
               k0 = m;
               break;
             }
@@ -275,14 +287,15 @@ __device__ __forceinline__ Col col_of(const Scr& S, long long o, long long plane
 // map_scalar / map1_ppm / map1_q2 of one column, in place on fld (level k at fld[(k-1)*plane])
 template <class P1, class P2>
 __device__ void remap_field(const Col& C, int km, const P1& pe1, const P2& pe2, double* fld, double qs, int iv, int kord, double qmin,
-                            bool scalar) {
+                            bool scalar, bool mapn = false) {
   for (int k = 1; k <= km; k++) A1(k) = LV(fld, k);
   profile(C, km, pe1, qs, iv, kord < 0 ? -kord : kord, qmin, scalar);
-  map_column(C, km, pe1, pe2, [&](int k, double v) { LV(fld, k) = v; });
+  map_column(C, km, pe1, pe2, [&](int k, double v) { LV(fld, k) = v; }, mapn);
 }
 
 struct L2E {
   double *pt, *delp, *delz, *w, *u, *v, *pk, *pkz, *omga, *qtr, *pe, *peln;
+  double* const* qtrs;   // device table of the tracer arrays (use_tracer entries)
   const double *ws, *ak, *bk;   // ak, bk: device tables (km + 1)
   double akap, k1k, rrg, ptop, t_min;
   int hydrostatic, last_step, kord_mt, kord_wz, kord_tm, use_tracer, kord_tr;
@@ -312,7 +325,7 @@ __global__ void __launch_bounds__(CB) k_remap_cells(Lay L, L2E a, Scr S) {
   auto pn2 = [&](int k) { return (k == 1 || k == km + 1) ? LV(peln, k) : log(pe2(k)); };
   if (a.kord_tm < 0) remap_field(C, km, pn1, pn2, pt, 0., 1, a.kord_tm, a.t_min, true);          // :373-386
   else remap_field(C, km, pe1, pe2, pt, 0., 1, a.kord_tm, 0., false);
-  if (a.use_tracer) remap_field(C, km, pe1, pe2, a.qtr + o, 0., 0, a.kord_tr, 0., true);         // :395-408 (map1_q2)
+  for (int iq = 0; iq < a.use_tracer; iq++) remap_field(C, km, pe1, pe2, a.qtrs[iq] + o, 0., 0, a.kord_tr, 0., true, a.use_tracer > 5);   // :390-408 (map1_q2; mapn_tracer for nq > 5)
   if (!a.hydrostatic) {                                                                          // :411-433
     remap_field(C, km, pe1, pe2, a.w + o, a.ws[o], -2, a.kord_wz, 0., false);
     remap_field(C, km, pe1, pe2, delz, 0., 1, a.kord_tm, 0., false);
@@ -442,9 +455,17 @@ int stage_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kor
   int rc = check_kord(c, kord_mt, "kord_mt"); if (rc) return rc;
   rc = check_kord(c, kord_tm, "kord_tm"); if (rc) return rc;
   if (!f.hydrostatic) { rc = check_kord(c, kord_wz, "kord_wz"); if (rc) return rc; }
+  if (use_tracer < 0 || use_tracer > 64) return fv3_fail(c, -1, "remap: use_tracer (the number of tracers to remap) in 0..64");
   if (use_tracer) { rc = check_kord(c, kord_tr, "kord_tr"); if (rc) return rc; if (kord_tr < 0) return fv3_fail(c, -2, "remap: kord_tr must be positive"); }
   L2E a{}; Scr S{};
   rc = fill(c, a, S); if (rc) return rc;
+  if (use_tracer) {   // the first use_tracer tracers of the context's table (fv3_set_num_tracers; one tracer: FV3_WORK_Q's own array)
+    if (c->tracers.empty()) c->tracers.push_back(c->fld[FV3_WORK_Q]);
+    if (use_tracer > (int)c->tracers.size()) return fv3_fail(c, -1, "remap: use_tracer exceeds the number of tracers of the context");
+    if (!c->d_qtr_tab) FV3_CUDA(c, cudaMalloc(&c->d_qtr_tab, 64 * sizeof(double*)));
+    FV3_CUDA(c, cudaMemcpyAsync(c->d_qtr_tab, c->tracers.data(), use_tracer * sizeof(double*), cudaMemcpyHostToDevice, c->stream));
+    a.qtrs = c->d_qtr_tab;
+  }
   a.last_step = last_step; a.kord_mt = kord_mt; a.kord_wz = kord_wz; a.kord_tm = kord_tm; a.use_tracer = use_tracer; a.kord_tr = kord_tr;
   const Lay& L = c->L;
   const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tr_step(Lay L, DevGrid G, tpt::T
                                                       double* __restrict__ dp1, const double* __restrict__ cx, const double* __restrict__ cy,
                                                       const double* __restrict__ xfx, const double* __restrict__ yfx,
                                                       const double* __restrict__ mfx, const double* __restrict__ mfy,
-                                                      const int* __restrict__ nsplt, int it, int ord_in, int ord_ou) {
+                                                      const int* __restrict__ nsplt, int it, int ord_in, int ord_ou, int update_dp1) {
   using namespace tpt;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(tpt::NT, 2) k_tr_step(Lay L, DevGrid G, tpt::T
     const double dp2 = d1 + (mx0 - mx1 + my0 - my1) * ra;
     const double qn = (S.q[r + 3][c + 3] * d1 + (FX(S, r, c) * mx0 - FX(S, r, c + 1) * mx1 + FY(S, r, c) * my0 - FY(S, r + 1, c) * my1) * ra) / dp2;
     qo[o] = qn;
-    if (it < ns) dp1[o] = dp2;   // not the last sub-cycle (:268-274)
+    if (update_dp1 && it < ns) dp1[o] = dp2;   // after the LAST tracer of a sub-cycle that is not the last one (:268-274)
   }
 }
 
@@ -126,20 +126,48 @@ extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_ou
   const bool linked = c0->halo != nullptr;
   std::vector<double> cmax(npz, 0.), tmp(npz);
   std::vector<unsigned long long*> d_cmax(nctx, nullptr);
-  std::vector<double*> q_home(nctx);
-  for (int a = 0; a < nctx; a++) q_home[a] = ctxs[a]->fld[FV3_WORK_Q];
-  // whatever path leaves this function: the tracer pointer of every context is its own allocation again (the sub-cycles
-  // ping-pong fld[WORK_Q] with a scratch plane because the halo exchange reads fld[WORK_Q]) and the per-call tables are freed
+  // All nq tracers of the contexts are advected (fv_tracer2d.F90:206-275: per sub-cycle every tracer is updated with the same
+  // dp1 -> dp2, then dp1 = dp2).  cur[a][iq]: where tracer iq of context a lives right now; spare[a]: the buffer the next kernel
+  // writes -- it starts as the scratch plane scr[0] and rotates through the tracer buffers (the halo exchange reads
+  // fld[FV3_WORK_Q], which is pointed at the tracer being exchanged).
+  for (int a = 0; a < nctx; a++) if (ctxs[a]->tracers.empty()) ctxs[a]->tracers.push_back(ctxs[a]->fld[FV3_WORK_Q]);
+  const int nq = (int)c0->tracers.size();
+  for (int a = 0; a < nctx; a++)
+    if ((int)ctxs[a]->tracers.size() != nq) return fv3_fail(ctxs[a], -1, "tracer_2d: the linked contexts disagree on the number of tracers");
+  std::vector<std::vector<double*>> cur(nctx);
+  std::vector<double*> spare(nctx), scr0(nctx);
+  for (int a = 0; a < nctx; a++) { cur[a] = ctxs[a]->tracers; spare[a] = scr0[a] = ctxs[a]->scr[0]; }
+  // whatever path leaves this function: the tracer table of every context holds nq distinct tracer-sized buffers or better, scr[0]
+  // is the scratch plane again, fld[WORK_Q] aliases the selected tracer, the per-call tables are freed.  finish(copy): when the
+  // scratch plane ended up holding a tracer, that tracer moves (copy = true: with its data) into the spare buffer.
   struct Cleanup {
-    fv3_ctx** ctxs; int n; std::vector<double*>& home; std::vector<unsigned long long*>& tab;
-    ~Cleanup() {
+    fv3_ctx** ctxs; int n; std::vector<std::vector<double*>>& cur; std::vector<double*>& spare; std::vector<double*>& scr0;
+    std::vector<unsigned long long*>& tab; bool done = false;
+    int finish(bool copy) {
+      int rc = 0;
       for (int a = 0; a < n; a++) {
-        cudaSetDevice(ctxs[a]->device);
-        ctxs[a]->fld[FV3_WORK_Q] = home[a];
-        if (tab[a]) { cudaStreamSynchronize(ctxs[a]->stream); cudaFree(tab[a]); }
+        fv3_ctx* c = ctxs[a];
+        cudaSetDevice(c->device);
+        if (spare[a] != scr0[a]) {
+          for (double*& p : cur[a])
+            if (p == scr0[a]) {
+              if (copy && cudaMemcpyAsync(spare[a], p, (size_t)c->L.plane * c->L.npz * sizeof(double), cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) rc = 1;
+              p = spare[a];
+            }
+          spare[a] = scr0[a];
+        }
+        c->tracers = cur[a];
+        c->fld[FV3_WORK_Q] = c->tracers[c->tracer_sel];
       }
+      done = true;
+      return rc;
     }
-  } cleanup{ctxs, nctx, q_home, d_cmax};
+    ~Cleanup() {
+      if (!done) finish(false);
+      for (int a = 0; a < n; a++)
+        if (tab[a]) { cudaSetDevice(ctxs[a]->device); cudaStreamSynchronize(ctxs[a]->stream); cudaFree(tab[a]); }
+    }
+  } cleanup{ctxs, nctx, cur, spare, scr0, d_cmax};
   // ---- xfx, yfx, cmax
   for (int a = 0; a < nctx; a++) {
     fv3_ctx* c = ctxs[a];
@@ -177,7 +205,6 @@ extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_ou
     nmax = std::max(nmax, nsplt[k]);
   }
   const int ord_in = (hord == 10) ? 8 : hord;
-  std::vector<double*> alt(nctx);
   for (int a = 0; a < nctx; a++) {
     fv3_ctx* c = ctxs[a];
     cudaSetDevice(c->device);
@@ -188,7 +215,6 @@ extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_ou
     k_tr_scale<<<plane_grid(c->L, npz), dim3(TI, TJ), 0, c->stream>>>(c->L, c->fld[FV3_CX], c->fld[FV3_XFX], c->fld[FV3_CY], c->fld[FV3_YFX],
                                                                         c->fld[FV3_MFX], c->fld[FV3_MFY], d_frac);
     c->launches++;
-    alt[a] = c->scr[0];               // ping-pong partner (a scratch plane: npz+1 levels >= npz)
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -202,33 +228,34 @@ extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_ou
   }
   // ---- sub-cycles
   for (int it = 1; it <= nmax; it++) {
-    if (linked) { int rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_TRACER); if (rc) return rc; }   // q_pack (:188) / qn2 (:282)
-    for (int a = 0; a < nctx; a++) {
-      fv3_ctx* c = ctxs[a];
-      cudaSetDevice(c->device);
-      const Lay& L = c->L;
-      int* d_ns = (int*)((double*)d_cmax[a] + 2 * npz);
-      tpt::TileMap Min, Mfr; int n_in, n_fr;
-      tpt::tile_maps(L, Min, Mfr, n_in, n_fr);
+    for (int iq = 0; iq < nq; iq++) {
+      for (int a = 0; a < nctx; a++) ctxs[a]->fld[FV3_WORK_Q] = cur[a][iq];
+      if (linked) { int rc = fv3_halo_exchange(ctxs, nctx, FV3_HALO_TRACER); if (rc) return rc; }   // q_pack (:188) / qn2 (:282)
+      const int upd = iq == nq - 1 ? 1 : 0;
+      for (int a = 0; a < nctx; a++) {
+        fv3_ctx* c = ctxs[a];
+        cudaSetDevice(c->device);
+        const Lay& L = c->L;
+        int* d_ns = (int*)((double*)d_cmax[a] + 2 * npz);
+        tpt::TileMap Min, Mfr; int n_in, n_fr;
+        tpt::tile_maps(L, Min, Mfr, n_in, n_fr);
 #define TR_LAUNCH(FAM, EDGE, MAP, N)                                                                                              \
   k_tr_step<FAM, EDGE><<<dim3(N, 1, npz), tpt::NT, sizeof(tpt::Smem), c->stream>>>(                                               \
-      L, c->G, MAP, c->fld[FV3_WORK_Q], alt[a], c->fld[FV3_DP1], c->fld[FV3_CX], c->fld[FV3_CY], c->fld[FV3_XFX], c->fld[FV3_YFX], \
-      c->fld[FV3_MFX], c->fld[FV3_MFY], d_ns, it, ord_in, hord)
-      if (hord_is_rare(hord)) { if (n_in) TR_LAUNCH(2, false, Min, n_in); if (n_fr) TR_LAUNCH(2, true, Mfr, n_fr); }
-      else if (hord >= 8) { if (n_in) TR_LAUNCH(1, false, Min, n_in); if (n_fr) TR_LAUNCH(1, true, Mfr, n_fr); }
-      else { if (n_in) TR_LAUNCH(0, false, Min, n_in); if (n_fr) TR_LAUNCH(0, true, Mfr, n_fr); }
+      L, c->G, MAP, cur[a][iq], spare[a], c->fld[FV3_DP1], c->fld[FV3_CX], c->fld[FV3_CY], c->fld[FV3_XFX], c->fld[FV3_YFX],      \
+      c->fld[FV3_MFX], c->fld[FV3_MFY], d_ns, it, ord_in, hord, upd)
+        if (hord_is_rare(hord)) { if (n_in) TR_LAUNCH(2, false, Min, n_in); if (n_fr) TR_LAUNCH(2, true, Mfr, n_fr); }
+        else if (hord >= 8) { if (n_in) TR_LAUNCH(1, false, Min, n_in); if (n_fr) TR_LAUNCH(1, true, Mfr, n_fr); }
+        else { if (n_in) TR_LAUNCH(0, false, Min, n_in); if (n_fr) TR_LAUNCH(0, true, Mfr, n_fr); }
 #undef TR_LAUNCH
-      c->launches += (n_in ? 1 : 0) + (n_fr ? 1 : 0);
-      std::swap(c->fld[FV3_WORK_Q], alt[a]);   // the halo exchange of the next sub-cycle reads fld[WORK_Q]
+        c->launches += (n_in ? 1 : 0) + (n_fr ? 1 : 0);
+        std::swap(cur[a][iq], spare[a]);   // the tracer now lives in what was the spare buffer
+      }
     }
   }
+  if (cleanup.finish(true)) return fv3_fail(c0, 1, "tracer_2d: device copy failed");
   for (int a = 0; a < nctx; a++) {
     fv3_ctx* c = ctxs[a];
     cudaSetDevice(c->device);
-    if (c->fld[FV3_WORK_Q] != q_home[a]) {   // odd number of sub-cycles: result sits in the scratch plane
-      FV3_CUDA(c, cudaMemcpyAsync(q_home[a], c->fld[FV3_WORK_Q], (size_t)c->L.plane * npz * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-      c->fld[FV3_WORK_Q] = q_home[a];
-    }
     FV3_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fv3_fail(c, (int)e, std::string("tracer_2d: ") + cudaGetErrorString(e));

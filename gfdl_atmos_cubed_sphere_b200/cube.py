@@ -94,6 +94,15 @@ class CudaCube:
         for t in self.tiles:
             self.eng[t].sync()
 
+    def set_num_tracers(self, nq):
+        """fv3_set_num_tracers on every face: nq tracer arrays; FV3_WORK_Q names the one chosen with select_tracer."""
+        for t in self.tiles:
+            self.eng[t].call("set_num_tracers", int(nq))
+
+    def select_tracer(self, iq):
+        for t in self.tiles:
+            self.eng[t].call("select_tracer", int(iq))
+
     def set_transport_fp32(self, on=True):
         """fv3_set_transport_fp32 on every face: fp32 PPM sweeps on the interior tiles of d_sw (BASELINE config 5)."""
         fn = self.lib[0].fv3_set_transport_fp32

@@ -209,7 +209,7 @@ int fv3_pt_to_theta(fv3_ctx *ctx, double zvir);
 /* Vertical remapping, the step between the k_split iterations of fv_dynamics (fv_dynamics.F90:578-625 call site).
  * fv3_lagrangian_to_eulerian: fv_mapz.F90:56-845 on one face after fv3_dyn_core (which leaves pe incl. its one-cell halo, peln,
  * pk, ws and omga current): delp <- ak/bk hybrid levels, pt (theta_v in; theta_v out, or T_v when last_step), w, delz, u, v,
- * [the tracer in FV3_WORK_Q], pe, peln, pk, pkz remapped; omga interpolated when last_step.  Built: remap_te = F, moist_kappa = F,
+ * [the first use_tracer tracers of the context], pe, peln, pk, pkz remapped; omga interpolated when last_step.  Built: remap_te = F, moist_kappa = F,
  * consv = 0 (no energy fixer), dry air (the last-step T_v -> T conversion is the identity), abs(kord_*) in 8..15 (cs_profile /
  * scalar_profile), kord_wz > 0; everything else returns -2.  kord_tm < 0: T_v is mapped in log p (map_scalar), > 0: theta_v in p.
  * fv3_remap_work_q: the column operators alone on FV3_WORK_Q, from the layers of FV3_PE to the hybrid levels -- mode 0 map_scalar
@@ -329,6 +329,14 @@ int fv3_dyn_core(fv3_ctx **ctxs, int nctx, double bdt, int n_split, int flags);
  * moist_kappa, no inline physics, no energy fixer); pt is temperature on entry and on exit.  flags: as fv3_dyn_core. */
 int fv3_fv_dynamics(fv3_ctx **ctxs, int nctx, double bdt, int k_split, int n_split, int kord_mt, int kord_wz, int kord_tm,
                     int kord_tr, int hord_tr, int nf_omega, int flags);
+
+/* Tracers: fv3_set_num_tracers(ctx, nq) gives the context nq tracer arrays (isd:ied, jsd:jed, npz); FV3_WORK_Q names the one chosen
+ * with fv3_select_tracer (0 by default), so fv3_put_field / fv3_get_field(FV3_WORK_Q) move the selected tracer.  fv3_tracer_2d
+ * advects ALL nq tracers (one CFL / sub-cycle count, dp1 advanced once per sub-cycle: fv_tracer2d.F90:206-275), the vertical
+ * remap maps the first `use_tracer` of them. */
+int fv3_set_num_tracers(fv3_ctx *ctx, int nq);
+int fv3_num_tracers(const fv3_ctx *ctx);
+int fv3_select_tracer(fv3_ctx *ctx, int iq);
 
 /* fv_tracer2d.F90:49-295 tracer_2d_1L for ONE tracer (nq = 1, trdm = 0, id_divg_mean = 0), all faces of this process in
  * lockstep, after fv3_dyn_core: the tracer in FV3_WORK_Q (halo included) is advected in place with the accumulated mass

@@ -26,6 +26,8 @@ struct fv3o_ctx {
   // Rayleigh damping table of nh_utils (SAVEd rff, k_rf, RFw_initialized, nh_utils.F90:53-55)
   std::vector<double> rff; int k_rf = 0; bool rf_init = false;
   // external-mode damping term divg2(is:ie+1, js:je+1) of the current substep (dyn_core.F90:828-847; empty: d_ext = 0)
+  // tracers: store[i] holds tracer i except for i == tracer_sel, which lives in fld[FV3_WORK_Q] (fv3o_select_tracer swaps)
+  std::vector<std::vector<double>> store; int tracer_sel = 0;
   std::vector<double> pem;   // interface pressures before the last substep (omega diagnostic, dyn_core.F90:409-422)
   std::vector<double> divg2, ext_dpc;   // ext_dpc: delp at the cell corners (is:ie+1, js:je+1, npz), taken before d_sw (:745-747)
   explicit fv3o_ctx(const fv3_bounds_t& b_, const fv3_grid_t& g_, const fv3_flags_t& f_) : b(b_), g(g_), f(f_) {}
@@ -442,10 +444,35 @@ int fv3o_remap_work_q(fv3o_ctx* c, int mode, int iv, int kord, double qmin) {
   return remap_work_q(F3(c, FV3_WORK_Q), F2(c, FV3_WS), c->fld[FV3_PE].data(), c->ak, c->bk, c->f, bd, mode, iv, kord, qmin);
 }
 // fv_mapz.F90:56-845 Lagrangian_to_Eulerian on one face (remap.cpp states the supported subset)
+int fv3o_set_num_tracers(fv3o_ctx* c, int nq) {
+  if (nq < 1 || nq > 64) return -1;
+  if (c->store.empty()) c->store.resize(1);
+  if (c->tracer_sel >= nq) return -1;
+  c->store.resize(nq);
+  for (int i = 0; i < nq; i++) if (i != c->tracer_sel && c->store[i].size() != c->fld[FV3_WORK_Q].size()) c->store[i].assign(c->fld[FV3_WORK_Q].size(), 0.);
+  return 0;
+}
+int fv3o_num_tracers(const fv3o_ctx* c) { return c->store.empty() ? 1 : (int)c->store.size(); }
+int fv3o_select_tracer(fv3o_ctx* c, int iq) {
+  if (c->store.empty()) c->store.resize(1);
+  if (iq < 0 || iq >= (int)c->store.size()) return -1;
+  if (iq == c->tracer_sel) return 0;
+  c->store[c->tracer_sel].swap(c->fld[FV3_WORK_Q]);   // park the selected tracer
+  c->fld[FV3_WORK_Q].swap(c->store[iq]);
+  c->tracer_sel = iq;
+  return 0;
+}
+// use_tracer: the number of tracers to remap (the first use_tracer of the context's table)
 int fv3o_lagrangian_to_eulerian(fv3o_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr) {
   Bd bd(c->b);
+  if (use_tracer < 0 || use_tracer > fv3o_num_tracers(c)) return -1;
   L2EFields F{F3(c, FV3_PT), F3(c, FV3_DELP), F3(c, FV3_DELZ), F3(c, FV3_W), F3(c, FV3_U), F3(c, FV3_V), F3(c, FV3_PK), F3(c, FV3_PKZ),
-              F3(c, FV3_OMGA), F3(c, FV3_WORK_Q), F2(c, FV3_WS), c->fld[FV3_PE].data(), c->fld[FV3_PELN].data()};
+              F3(c, FV3_OMGA), {}, F2(c, FV3_WS), c->fld[FV3_PE].data(), c->fld[FV3_PELN].data()};
+  const FieldDim& d = c->dim[FV3_WORK_Q];
+  for (int iq = 0; iq < use_tracer; iq++) {
+    std::vector<double>& buf = (iq == c->tracer_sel || c->store.empty()) ? c->fld[FV3_WORK_Q] : c->store[iq];
+    F.qtr.push_back(V3(buf.data(), d.ilo, d.ilo + d.ni - 1, d.jlo, d.jlo + d.nj - 1));
+  }
   return lagrangian_to_eulerian(F, c->ak, c->bk, c->f, bd, last_step, kord_mt, kord_wz, kord_tm, use_tracer, kord_tr);
 }
 int fv3o_pt_to_theta(fv3o_ctx* c, double zvir) {

@@ -280,7 +280,7 @@ void pem_from_delp(double* pem, V3 delp, double ptop, const Bd& bd);
 void omega_old(V3 omga, const double* pe, const double* pem, V3 ua, V3 va, double rdt, const Grid& g, const Bd& bd);
 
 // remap.cpp (fv_mapz.F90 Lagrangian_to_Eulerian, fv_operators.F90 map_scalar / map1_ppm / map1_q2 and their profiles)
-struct L2EFields { V3 pt, delp, delz, w, u, v, pk, pkz, omga, qtr; V2 ws; double *pe, *peln; };
+struct L2EFields { V3 pt, delp, delz, w, u, v, pk, pkz, omga; std::vector<V3> qtr; V2 ws; double *pe, *peln; };
 int remap_work_q(V3 q, V2 ws, double* pe, const std::vector<double>& ak, const std::vector<double>& bk, const fv3_flags_t& f, const Bd& bd,
                  int mode, int iv, int kord, double qmin);
 int lagrangian_to_eulerian(const L2EFields& F, const std::vector<double>& ak, const std::vector<double>& bk, const fv3_flags_t& f, const Bd& bd,

@@ -6,7 +6,7 @@
 //   remap_te = F, moist_kappa = F, consv = 0 (no energy fixer), no intermediate physics, dry (no specific humidity: the last-step
 //   conversion T_v -> T is the identity, i.e. `adiabatic`), abs(kord) in 8..15 (the cs / scalar profiles; ppm_profile for kord <= 7
 //   is not restated), kord_wz > 0 (iv = -2; the iv = -3 branch of cs_profile reads an unset
-//   gam(km), :969-985), at most one tracer (FV3_WORK_Q, iv = 0, no fillz).
+//   gam(km), :969-985), tracers with map1_q2 or, for nq > 5, with the operation order of mapn_tracer (iv = 0, no fillz).
 // The Fortran vectorises every loop over i; here one column is processed at a time (same operations on the same operands in the
 // same order for every element).  Parity unpinned: the reference holds no test or golden vector for these routines.
 #include "fv3_oracle.hpp"
@@ -208,8 +208,9 @@ int profile(double qs, A4& a4, const std::vector<double>& delp, int km, int iv, 
 
 // the conservative mapping loop shared by map_scalar / map1_ppm / map1_q2 (fv_operators.F90:88-132, 183-227, 399-441) for one
 // column: pe1(1:km+1) -> pe2(1:kn+1).  dp2 != nullptr: divide by dp2(k) (map1_q2) instead of pe2(k+1) - pe2(k).
+// mapn: the operation order of mapn_tracer (:276-336: the geometric factors fac1, fac2 are formed first), which fv_mapz uses for nq > 5
 void map_column(int km, const std::vector<double>& pe1, A4& q4, const std::vector<double>& dp1, int kn, const std::vector<double>& pe2,
-                std::vector<double>& q2, const double* dp2) {
+                std::vector<double>& q2, const double* dp2, bool mapn = false) {
   int k0 = 1;
   for (int k = 1; k <= kn; k++) {
     double qsum = 0.;
@@ -219,15 +220,30 @@ void map_column(int km, const std::vector<double>& pe1, A4& q4, const std::vecto
         const double pl = (pe2[k] - pe1[l]) / dp1[l];
         if (pe2[k + 1] <= pe1[l + 1]) {   // the new layer lies within one old layer
           const double pr = (pe2[k + 1] - pe1[l]) / dp1[l];
+          if (mapn) {
+            double fac1 = pr + pl;
+            const double fac2 = r3 * (pr * fac1 + pl * pl);
+            fac1 = 0.5 * fac1;
+            q2[k] = q4(2, l) + (q4(4, l) + q4(3, l) - q4(2, l)) * fac1 - q4(4, l) * fac2;
+          } else
           q2[k] = q4(2, l) + 0.5 * (q4(4, l) + q4(3, l) - q4(2, l)) * (pr + pl) - q4(4, l) * r3 * (pr * (pr + pl) + pl * pl);
           k0 = l;
           done = true;
         } else {                          // fractional area of layer l, whole layers, fraction of the last one
+          if (mapn) {
+            const double dp = pe1[l + 1] - pe2[k];
+            double fac1 = 1. + pl;
+            const double fac2 = r3 * (1. + pl * fac1);
+            fac1 = 0.5 * fac1;
+            qsum = dp * (q4(2, l) + (q4(4, l) + q4(3, l) - q4(2, l)) * fac1 - q4(4, l) * fac2);
+          } else
           qsum = (pe1[l + 1] - pe2[k]) * (q4(2, l) + 0.5 * (q4(4, l) + q4(3, l) - q4(2, l)) * (1. + pl) - q4(4, l) * (r3 * (1. + pl * (1. + pl))));
           for (int m = l + 1; m <= km; m++) {
             if (pe2[k + 1] > pe1[m + 1]) qsum = qsum + dp1[m] * q4(1, m);
             else {
               const double dp = pe2[k + 1] - pe1[m], esl = dp / dp1[m];
+              if (mapn) { const double fac1 = 0.5 * esl, fac2 = 1. - r23 * esl; qsum = qsum + dp * (q4(2, m) + fac1 * (q4(3, m) - q4(2, m) + q4(4, m) * fac2)); }
+              else
               qsum = qsum + dp * (q4(2, m) + 0.5 * esl * (q4(3, m) - q4(2, m) + q4(4, m) * (1. - r23 * esl)));
               k0 = m;
               break;
@@ -243,13 +259,13 @@ void map_column(int km, const std::vector<double>& pe1, A4& q4, const std::vecto
 
 // map_scalar (scalar = true) / map1_ppm (false) / map1_q2 (scalar = true, dp2 given) of one column, in place on q(1:km)
 int remap_field(int km, const std::vector<double>& pe1, const std::vector<double>& pe2, std::vector<double>& q, double qs, int iv, int kord,
-                double qmin, bool scalar, const double* dp2 = nullptr) {
+                double qmin, bool scalar, const double* dp2 = nullptr, bool mapn = false) {
   A4 q4(km);
   std::vector<double> dp1(km + 2, 0.);
   for (int k = 1; k <= km; k++) { dp1[k] = pe1[k + 1] - pe1[k]; q4(1, k) = q[k]; }
   const int rc = profile(qs, q4, dp1, km, iv, kord, qmin, scalar);
   if (rc) return rc;
-  map_column(km, pe1, q4, dp1, km, pe2, q, dp2);
+  map_column(km, pe1, q4, dp1, km, pe2, q, dp2, mapn);
   return 0;
 }
 
@@ -277,7 +293,7 @@ int remap_work_q(V3 q, V2 ws, double* pe, const std::vector<double>& ak, const s
   return bad ? -2 : 0;
 }
 
-// fv_mapz.F90:56-845 on one face; use_tracer: the one tracer in FV3_WORK_Q is remapped with kord_tr.
+// fv_mapz.F90:56-845 on one face; use_tracer: the number of tracers (F.qtr) remapped with kord_tr (map1_q2 for nq <= 5, :398-408; mapn_tracer for nq > 5, :390-393).
 int lagrangian_to_eulerian(const L2EFields& F, const std::vector<double>& ak, const std::vector<double>& bk, const fv3_flags_t& f, const Bd& bd,
                            int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr) {
   if (f.moist_kappa || kord_wz < 0) return -2;
@@ -289,7 +305,8 @@ int lagrangian_to_eulerian(const L2EFields& F, const std::vector<double>& ak, co
   double *pe = F.pe, *peln = F.peln;
   auto PE = [&](int i, int k, int j) -> double& { return pe[(i - (is - 1)) + (size_t)(k - 1) * nip + (size_t)(j - (js - 1)) * nip * (km + 1)]; };
   auto PELN = [&](int i, int k, int j) -> double& { return peln[(i - is) + (size_t)(k - 1) * nie + (size_t)(j - js) * nie * (km + 1)]; };
-  V3 pt = F.pt, delp = F.delp, delz = F.delz, w = F.w, u = F.u, v = F.v, pk = F.pk, pkz = F.pkz, omga = F.omga, qtr = F.qtr;
+  V3 pt = F.pt, delp = F.delp, delz = F.delz, w = F.w, u = F.u, v = F.v, pk = F.pk, pkz = F.pkz, omga = F.omga;
+  if ((int)F.qtr.size() < use_tracer) return -1;
   V2 ws = F.ws;
   std::vector<double> pe4((size_t)nie * (je - js + 1) * (km + 1), 0.);   // the new interface pressures, stored until every row has used the old ones
   auto PE4 = [&](int i, int j, int k) -> double& { return pe4[(i - is) + (size_t)(j - js) * nie + (size_t)(k - 1) * nie * (je - js + 1)]; };
@@ -320,9 +337,10 @@ int lagrangian_to_eulerian(const L2EFields& F, const std::vector<double>& ak, co
         if (rc) bad = 1;
         for (int k = 1; k <= km; k++) pt(i, j, k) = col[k];
         // 2) the tracer (:395-408, map1_q2, no fillz)
-        if (use_tracer) {
+        for (int iq = 0; iq < use_tracer; iq++) {
+          V3 qtr = F.qtr[iq];
           for (int k = 1; k <= km; k++) col[k] = qtr(i, j, k);
-          rc = remap_field(km, pe1, pe2, col, 0., 0, kord_tr, 0., true, dp2.data());
+          rc = remap_field(km, pe1, pe2, col, 0., 0, kord_tr, 0., true, dp2.data(), use_tracer > 5);   // nq > 5: mapn_tracer (:390-393)
           if (rc) bad = 1;
           for (int k = 1; k <= km; k++) qtr(i, j, k) = col[k];
         }

@@ -333,12 +333,19 @@ class OracleCube:
             self.dyn_core(mdt, n_split, end_step=bool(last))
             if hord_tr:
                 self.tracer_2d(hord_tr)
-            self.all("lagrangian_to_eulerian", last, kord_mt, kord_wz, kord_tm, int(hord_tr != 0), kord_tr)
+            self.all("lagrangian_to_eulerian", last, kord_mt, kord_wz, kord_tm, getattr(self, "nq", 1) if hord_tr else 0, kord_tr)
             if last and nf_omega > 0:
                 self.del2_cubed("OMGA", 0.18 * self.case.tiles[0].da_min, nf_omega)
 
+    def set_num_tracers(self, nq):
+        self.nq = nq
+        self.all("set_num_tracers", nq)
+
+    def select_tracer(self, iq):
+        self.all("select_tracer", iq)
+
     def tracer_2d(self, hord):
-        """tracer_2d_1L (model/fv_tracer2d.F90:49-295; nq = 1, trdm = 0, id_divg_mean = 0) on the oracle side: the pointwise
+        """tracer_2d_1L (model/fv_tracer2d.F90:49-295; all tracers of the engines, trdm = 0, id_divg_mean = 0) on the oracle side: the pointwise
         statements in NumPy with the reference's operation order, the fluxes from the oracle's fv_tp_2d, the q halo updates
         from the NumPy exchange, the CFL maximum over the six faces.  Operates on WORK_Q, DP1, CX, CY, MFX, MFY (XFX, YFX
         are overwritten) exactly like fv3_tracer_2d; returns cmax(npz)."""
@@ -380,20 +387,27 @@ class OracleCube:
                           ("MFX", "mfx"), ("MFY", "mfy"), ("CX", "cx"), ("CY", "cy")):
                 e.put(f, s[nm])
         sl = (slice(None), slice(js - jsd, je - jsd + 1), slice(is_ - isd, ie - isd + 1))
+        nq = getattr(self, "nq", 1)
         for it in range(1, int(nsplt.max()) + 1):
-            self._exchange_scalar("WORK_Q")                                                      # q_pack :188 / qn2 :282
-            for t in self.tiles:
-                e, s = self.eng[t], st[t]
-                e.call("fv_tp_2d", npz, hord, 1, 0, 0, 0.0)
-                fx, fy = e.get("WORK_FX"), e.get("WORK_FY")
-                q = e.get("WORK_Q")
-                qi, d1 = q[sl], s["dp1"][sl]
-                dp2 = d1 + (s["mfx"][:, :, :-1] - s["mfx"][:, :, 1:] + s["mfy"][:, :-1, :] - s["mfy"][:, 1:, :]) * s["rarea"][None]   # :212
-                qn = (qi * d1 + (fx[:, :, :-1] - fx[:, :, 1:] + fy[:, :-1, :] - fy[:, 1:, :]) * s["rarea"][None]) / dp2          # :232,239,250
-                act = (it <= nsplt)[:, None, None]
-                q[sl] = np.where(act, qn, qi)
-                s["dp1"][sl] = np.where((it < nsplt)[:, None, None], dp2, d1)                    # :268-274
-                e.put("WORK_Q", q)
+            for iq in range(nq):                                                                 # every tracer sees the same dp1 -> dp2 (:206-266)
+                if nq > 1:
+                    self.select_tracer(iq)
+                self._exchange_scalar("WORK_Q")                                                  # q_pack :188 / qn2 :282
+                for t in self.tiles:
+                    e, s = self.eng[t], st[t]
+                    e.call("fv_tp_2d", npz, hord, 1, 0, 0, 0.0)
+                    fx, fy = e.get("WORK_FX"), e.get("WORK_FY")
+                    q = e.get("WORK_Q")
+                    qi, d1 = q[sl], s["dp1"][sl]
+                    dp2 = d1 + (s["mfx"][:, :, :-1] - s["mfx"][:, :, 1:] + s["mfy"][:, :-1, :] - s["mfy"][:, 1:, :]) * s["rarea"][None]   # :212
+                    qn = (qi * d1 + (fx[:, :, :-1] - fx[:, :, 1:] + fy[:, :-1, :] - fy[:, 1:, :]) * s["rarea"][None]) / dp2          # :232,239,250
+                    act = (it <= nsplt)[:, None, None]
+                    q[sl] = np.where(act, qn, qi)
+                    if iq == nq - 1:
+                        s["dp1"][sl] = np.where((it < nsplt)[:, None, None], dp2, d1)            # :268-274, after the last tracer
+                    e.put("WORK_Q", q)
+        if nq > 1:
+            self.select_tracer(0)
         for t in self.tiles:
             self.eng[t].put("DP1", st[t]["dp1"])
         return cmax

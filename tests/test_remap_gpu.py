@@ -173,3 +173,43 @@ def test_remap_known_answer_linear_profile_on_the_gpu(kord):
             assert np.abs(out - mean(p2)).max() / np.abs(mean(p2)).max() < 1e-12, (t, mode)
             e.put("WORK_Q", q0)
     gc.close()
+
+
+@pytest.mark.parametrize("nq", [3, 6])
+def test_fv_dynamics_with_several_tracers(nq):
+    """nq tracers through fv3_fv_dynamics: tracer_2d advects all of them with one CFL / sub-cycle count and one dp1 -> dp2 per
+    sub-cycle (fv_tracer2d.F90:206-275), the remap maps them with map1_q2 (nq <= 5) or in the operation order of mapn_tracer
+    (nq > 5: fv_mapz.F90:390-408).  Against the oracle; a tracer that is constant must stay constant, and the tracer buffers must
+    come back in their slots (the sub-cycles rotate them through a spare buffer)."""
+    case = H.Case(N, NPZ, "A", state="baroclinic")
+    oc, gc = H.OracleCube(case), H.CudaCube(case)
+    oc.set_num_tracers(nq); gc.set_num_tracers(nq)
+    rng = np.random.default_rng(3)
+    kappa = case.consts["kappa"]
+    for t in oc.tiles:
+        eo, eg = oc.eng[t], gc.eng[t]
+        pt, delp = eo.get("PT"), eo.get("DELP")
+        p = case.ak[0] + np.cumsum(delp, axis=0) - 0.5 * delp
+        eo.put("PT", pt * p ** kappa); eg.put("PT", eo.get("PT"))
+        for iq in range(nq):
+            q = np.full(eo.shape("WORK_Q"), 0.25 * (iq + 1)) if iq == 1 else rng.uniform(0.0, 1.0, eo.shape("WORK_Q")) * (iq + 1)
+            for e in (eo, eg):
+                e.call("select_tracer", iq); e.put("WORK_Q", q)
+        for e in (eo, eg):
+            e.call("select_tracer", 0)
+    oc.fv_dynamics(1800.0, 2, 2, 9, 9, -9, 9, 8, 1)
+    gc.fv_dynamics(1800.0, 2, 2, 9, 9, -9, 9, 8, 1)
+    b = case.bounds
+    reg = {"WORK_Q": (b["is_"], b["ie"], b["js"], b["je"])}
+    for iq in range(nq):
+        oc.select_tracer(iq); gc.select_tracer(iq)
+        for t in oc.tiles:
+            _assert(H.compare(oc.eng[t], gc.eng[t], reg), 1e-9)
+        if iq == 1:
+            q = H.sub(gc.eng[2], "WORK_Q", gc.eng[2].get("WORK_Q"), 1, N, 1, N)
+            assert np.abs(q - 0.5).max() < 1e-12
+    reg2 = _regions(case.bounds); reg2.pop("WORK_Q")
+    for t in oc.tiles:
+        res = H.compare(oc.eng[t], gc.eng[t], reg2)
+        _assert({k: v for k, v in res.items() if k not in ("W", "OMGA")}, 1e-9)
+    oc.close(); gc.close()
