@@ -428,6 +428,9 @@ int fv3_remap_work_q(fv3_ctx* c, int mode, int iv, int kord, double qmin) { STAG
 int fv3_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr) {
   STAGE_PROLOGUE(c) int rc = stage_lagrangian_to_eulerian(c, last_step, kord_mt, kord_wz, kord_tm, use_tracer, kord_tr); if (rc) return rc; STAGE_EPILOGUE(c)
 }
+int fv3_lagrangian_to_eulerian_qv(fv3_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr, int sphum, double r_vir) {
+  STAGE_PROLOGUE(c) int rc = stage_lagrangian_to_eulerian(c, last_step, kord_mt, kord_wz, kord_tm, use_tracer, kord_tr, sphum, r_vir); if (rc) return rc; STAGE_EPILOGUE(c)
+}
 int fv3_pt_to_theta(fv3_ctx* c, double zvir) { STAGE_PROLOGUE(c) int rc = stage_pt_to_theta(c, zvir); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_dcon_heating(fv3_ctx* c, double bdt) { STAGE_PROLOGUE(c) int rc = stage_dcon_heating(c, bdt); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_geopk(fv3_ctx* c, int cg) { STAGE_PROLOGUE(c) int rc = stage_geopk(c, cg); if (rc) return rc; STAGE_EPILOGUE(c) }

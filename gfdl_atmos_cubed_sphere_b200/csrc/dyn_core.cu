@@ -290,20 +290,42 @@ extern "C" int fv3_del2_cubed_cube(fv3_ctx** ctxs, int nctx, int field, double c
 // moist_kappa / inline physics / energy fixer (consv_te = 0), the context's tracers (fv3_set_num_tracers; advected with hord_tr and remapped with kord_tr
 // when hord_tr != 0).  pt is temperature on entry and on exit.
 extern "C" int fv3_tracer_2d(fv3_ctx** ctxs, int nctx, int hord, double* cmax_out);
+extern "C" int fv3_select_tracer(fv3_ctx* c, int iq);
+// sphum >= 0: that tracer is the specific humidity q_v (no condensates): theta_v and T_v carry the factor 1 + zvir q_v
+// (fv_dynamics.F90:303-398 on entry, fv_mapz.F90:792-822 on exit); sphum = -1: dry
+extern "C" int fv3_fv_dynamics_qv(fv3_ctx** ctxs, int nctx, double bdt, int k_split, int n_split, int kord_mt, int kord_wz, int kord_tm,
+                                  int kord_tr, int hord_tr, int nf_omega, int flags, int sphum, double zvir);
 extern "C" int fv3_fv_dynamics(fv3_ctx** ctxs, int nctx, double bdt, int k_split, int n_split, int kord_mt, int kord_wz, int kord_tm,
                                int kord_tr, int hord_tr, int nf_omega, int flags) {
+  return fv3_fv_dynamics_qv(ctxs, nctx, bdt, k_split, n_split, kord_mt, kord_wz, kord_tm, kord_tr, hord_tr, nf_omega, flags, -1, 0.);
+}
+extern "C" int fv3_fv_dynamics_qv(fv3_ctx** ctxs, int nctx, double bdt, int k_split, int n_split, int kord_mt, int kord_wz, int kord_tm,
+                                  int kord_tr, int hord_tr, int nf_omega, int flags, int sphum, double zvir) {
   if (!ctxs || nctx < 1 || k_split < 1 || n_split < 1) return -1;
+  if (sphum >= 0 && hord_tr == 0) return fv3_fail(ctxs[0], -1, "fv_dynamics: a specific-humidity tracer needs tracer transport (hord_tr != 0)");
   if (ctxs[0]->f.sw_test_case) return fv3_fail(ctxs[0], -2, "fv_dynamics: the SW_DYNAMICS build has no k_split loop body beyond dyn_core");
   if (ctxs[0]->L.npz <= 4) return fv3_fail(ctxs[0], -2, "fv_dynamics: npz <= 4 (no vertical remapping, fv_dynamics.F90:567) not supported");
   int rc;
-  FORALL(stage_pt_to_theta(c, 0.))                                                        // fv_dynamics.F90:303-398
+  if (sphum >= 0) {   // the entry conversion reads q_v through FV3_WORK_Q
+    for (int a = 0; a < nctx; a++) {
+      const int sel = ctxs[a]->tracer_sel;
+      if ((rc = fv3_select_tracer(ctxs[a], sphum))) return rc;
+      cudaSetDevice(ctxs[a]->device);
+      rc = stage_pt_to_theta(ctxs[a], zvir);
+      fv3_select_tracer(ctxs[a], sel);
+      if (rc) return rc;
+    }
+  } else {
+    FORALL(stage_pt_to_theta(c, 0.))                                                      // fv_dynamics.F90:303-398
+  }
   const double mdt = bdt / (double)k_split;                                               // :268
   for (int n_map = 1; n_map <= k_split; n_map++) {
     const int last_step = n_map == k_split;
     FORALL(stage_copy_field(c, FV3_DP1, FV3_DELP))                                        // :473-481 (compute domain + halo)
     if ((rc = fv3_dyn_core(ctxs, nctx, mdt, n_split, (flags & FV3_DYN_GRAPH) | (last_step ? FV3_DYN_END_STEP : 0)))) return rc;   // :495-502
     if (hord_tr != 0 && (rc = fv3_tracer_2d(ctxs, nctx, hord_tr, nullptr))) return rc;    // :512-535
-    FORALL(stage_lagrangian_to_eulerian(c, last_step, kord_mt, kord_wz, kord_tm, hord_tr != 0 ? std::max<int>(1, (int)c->tracers.size()) : 0, kord_tr))   // :578-625
+    FORALL(stage_lagrangian_to_eulerian(c, last_step, kord_mt, kord_wz, kord_tm, hord_tr != 0 ? std::max<int>(1, (int)c->tracers.size()) : 0, kord_tr,
+                                        sphum, zvir))                                     // :578-625
     if (last_step && nf_omega > 0) {                                                      // :658-662
       const double cd = 0.18 * ctxs[0]->G.da_min;
       if ((rc = fv3_del2_cubed_cube(ctxs, nctx, FV3_OMGA, cd, nf_omega))) return rc;

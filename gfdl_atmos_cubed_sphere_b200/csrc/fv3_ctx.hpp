@@ -181,7 +181,8 @@ int stage_omega_end(fv3_ctx* c, double dt);
 int stage_ext_mode_prepare(fv3_ctx* c);
 int stage_ext_mode_divg2(fv3_ctx* c);
 int stage_remap_work_q(fv3_ctx* c, int mode, int iv, int kord, double qmin);
-int stage_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr);
+int stage_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr, int sphum = -1,
+                                 double r_vir = 0.);
 int stage_fv_tp_2d(fv3_ctx* c, int nk, int hord, int use_mfx, int use_mass, int nord, double damp_c);
 int stage_c_sw(fv3_ctx* c, double dt2);
 int stage_d_sw(fv3_ctx* c, double dt);

@@ -297,7 +297,8 @@ struct L2E {
   double *pt, *delp, *delz, *w, *u, *v, *pk, *pkz, *omga, *qtr, *pe, *peln;
   double* const* qtrs;   // device table of the tracer arrays (use_tracer entries)
   const double *ws, *ak, *bk;   // ak, bk: device tables (km + 1)
-  double akap, k1k, rrg, ptop, t_min;
+  double akap, k1k, rrg, ptop, t_min, r_vir;
+  int sphum;             // index of the specific-humidity tracer in qtrs, or -1
   int hydrostatic, last_step, kord_mt, kord_wz, kord_tm, use_tracer, kord_tr;
 };
 
@@ -389,6 +390,10 @@ __global__ void __launch_bounds__(CB) k_remap_finish(Lay L, L2E a, Scr S) {
   const Col C{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, L.plane};
   for (int k = 2; k <= km; k++) LV(a.pe + o, k) = LV(S.pe4 + o, k);
   if (!a.last_step) for (int k = 1; k <= km; k++) LV(a.pt + o, k) = LV(a.pt + o, k) / LV(a.pkz + o, k);
+  else if (a.sphum >= 0) {   // T_v -> T (:792-822 with dtmp = 0, no condensates)
+    const double* qv = a.qtrs[a.sphum] + o;
+    for (int k = 1; k <= km; k++) LV(a.pt + o, k) = (LV(a.pt + o, k) + 0. * LV(a.pkz + o, k)) / (1. + a.r_vir * LV(qv, k));
+  }
 }
 
 // stand-alone column operator on FV3_WORK_Q (parity of the profiles for every scheme / iv): pe1 = FV3_PE, pe2 = the hybrid levels
@@ -446,7 +451,7 @@ int stage_remap_work_q(fv3_ctx* c, int mode, int iv, int kord, double qmin) {
   return 0;
 }
 
-int stage_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr) {
+int stage_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr, int sphum, double r_vir) {
   StageScope ts(c, "REMAP");
   const fv3_flags_t& f = c->f;
   if (f.moist_kappa) return fv3_fail(c, -2, "remap: moist_kappa not supported");
@@ -466,6 +471,9 @@ int stage_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kor
     FV3_CUDA(c, cudaMemcpyAsync(c->d_qtr_tab, c->tracers.data(), use_tracer * sizeof(double*), cudaMemcpyHostToDevice, c->stream));
     a.qtrs = c->d_qtr_tab;
   }
+  if (sphum >= use_tracer) return fv3_fail(c, -1, "remap: sphum must be one of the remapped tracers (or -1)");
+  if (sphum >= 0 && c->f.use_cond) return fv3_fail(c, -2, "remap: specific humidity with use_cond (condensates, moist_cv) not supported");
+  a.sphum = sphum < 0 ? -1 : sphum; a.r_vir = r_vir;
   a.last_step = last_step; a.kord_mt = kord_mt; a.kord_wz = kord_wz; a.kord_tm = kord_tm; a.use_tracer = use_tracer; a.kord_tr = kord_tr;
   const Lay& L = c->L;
   const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;

@@ -83,12 +83,15 @@ class CudaCube:
         for t in self.tiles:
             self.eng[t].sync()
 
-    def fv_dynamics(self, bdt, k_split, n_split, kord_mt=9, kord_wz=9, kord_tm=-9, kord_tr=9, hord_tr=0, nf_omega=1, graph=False):
-        """fv3_fv_dynamics: entry conversion, k_split x (dyn_core, tracer_2d, vertical remap), omega filter; pt = T in and out."""
-        fn = self.lib[0].fv3_fv_dynamics
+    def fv_dynamics(self, bdt, k_split, n_split, kord_mt=9, kord_wz=9, kord_tm=-9, kord_tr=9, hord_tr=0, nf_omega=1, graph=False,
+                    sphum=-1, zvir=0.0):
+        """fv3_fv_dynamics[_qv]: entry conversion, k_split x (dyn_core, tracer_2d, vertical remap), omega filter; pt = T in and out;
+        sphum >= 0: that tracer is the specific humidity (zvir = rvgas / rdgas - 1)."""
+        fn = self.lib[0].fv3_fv_dynamics_qv
         fn.restype = C.c_int
         rc = fn(self.ctxs, len(self.tiles), C.c_double(bdt), C.c_int(k_split), C.c_int(n_split), C.c_int(kord_mt), C.c_int(kord_wz),
-                C.c_int(kord_tm), C.c_int(kord_tr), C.c_int(hord_tr), C.c_int(nf_omega), C.c_int(1 if graph else 0))
+                C.c_int(kord_tm), C.c_int(kord_tr), C.c_int(hord_tr), C.c_int(nf_omega), C.c_int(1 if graph else 0), C.c_int(sphum),
+                C.c_double(zvir))
         if rc:
             raise RuntimeError(f"fv3_fv_dynamics rc={rc}: " + "; ".join(self.eng[t].last_error() for t in self.tiles))
         for t in self.tiles:

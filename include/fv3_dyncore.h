@@ -227,6 +227,10 @@ int fv3_omega_new(fv3_ctx *ctx, int phase, double dt);
 int fv3_ext_mode_prepare(fv3_ctx *ctx);
 int fv3_ext_mode_divg2(fv3_ctx *ctx);
 int fv3_lagrangian_to_eulerian(fv3_ctx *ctx, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr);
+/* the same with water vapour: tracer `sphum` (< use_tracer; -1: none) is the specific humidity, so the last-step conversion T_v -> T
+ * divides by 1 + r_vir q_v (fv_mapz.F90:792-822, dtmp = 0; use_cond / condensates are not supported); r_vir = rvgas / rdgas - 1 */
+int fv3_lagrangian_to_eulerian_qv(fv3_ctx *ctx, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr, int sphum,
+                                  double r_vir);
 int fv3_remap_work_q(fv3_ctx *ctx, int mode, int iv, int kord, double qmin);
 /* dyn_core.F90:1305-1356: filtered heat_source -> pt (levels 1..n_con, limited by delt_max); part of fv3_dyn_core */
 int fv3_dcon_heating(fv3_ctx *ctx, double bdt);
@@ -329,6 +333,10 @@ int fv3_dyn_core(fv3_ctx **ctxs, int nctx, double bdt, int n_split, int flags);
  * moist_kappa, no inline physics, no energy fixer); pt is temperature on entry and on exit.  flags: as fv3_dyn_core. */
 int fv3_fv_dynamics(fv3_ctx **ctxs, int nctx, double bdt, int k_split, int n_split, int kord_mt, int kord_wz, int kord_tm,
                     int kord_tr, int hord_tr, int nf_omega, int flags);
+/* the same with water vapour (no condensates): tracer `sphum` is q_v, zvir = rvgas / rdgas - 1: the entry conversion forms
+ * theta_v = T (1 + zvir q_v) / pkz and the last remap returns T = T_v / (1 + zvir q_v) */
+int fv3_fv_dynamics_qv(fv3_ctx **ctxs, int nctx, double bdt, int k_split, int n_split, int kord_mt, int kord_wz, int kord_tm,
+                       int kord_tr, int hord_tr, int nf_omega, int flags, int sphum, double zvir);
 
 /* Tracers: fv3_set_num_tracers(ctx, nq) gives the context nq tracer arrays (isd:ied, jsd:jed, npz); FV3_WORK_Q names the one chosen
  * with fv3_select_tracer (0 by default), so fv3_put_field / fv3_get_field(FV3_WORK_Q) move the selected tracer.  fv3_tracer_2d

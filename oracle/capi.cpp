@@ -463,7 +463,12 @@ int fv3o_select_tracer(fv3o_ctx* c, int iq) {
   return 0;
 }
 // use_tracer: the number of tracers to remap (the first use_tracer of the context's table)
+int fv3o_lagrangian_to_eulerian_qv(fv3o_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr, int sphum, double r_vir);
 int fv3o_lagrangian_to_eulerian(fv3o_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr) {
+  return fv3o_lagrangian_to_eulerian_qv(c, last_step, kord_mt, kord_wz, kord_tm, use_tracer, kord_tr, -1, 0.);
+}
+// sphum: index of the specific-humidity tracer (< use_tracer) or -1; r_vir = rvgas / rdgas - 1
+int fv3o_lagrangian_to_eulerian_qv(fv3o_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr, int sphum, double r_vir) {
   Bd bd(c->b);
   if (use_tracer < 0 || use_tracer > fv3o_num_tracers(c)) return -1;
   L2EFields F{F3(c, FV3_PT), F3(c, FV3_DELP), F3(c, FV3_DELZ), F3(c, FV3_W), F3(c, FV3_U), F3(c, FV3_V), F3(c, FV3_PK), F3(c, FV3_PKZ),
@@ -473,7 +478,7 @@ int fv3o_lagrangian_to_eulerian(fv3o_ctx* c, int last_step, int kord_mt, int kor
     std::vector<double>& buf = (iq == c->tracer_sel || c->store.empty()) ? c->fld[FV3_WORK_Q] : c->store[iq];
     F.qtr.push_back(V3(buf.data(), d.ilo, d.ilo + d.ni - 1, d.jlo, d.jlo + d.nj - 1));
   }
-  return lagrangian_to_eulerian(F, c->ak, c->bk, c->f, bd, last_step, kord_mt, kord_wz, kord_tm, use_tracer, kord_tr);
+  return lagrangian_to_eulerian(F, c->ak, c->bk, c->f, bd, last_step, kord_mt, kord_wz, kord_tm, use_tracer, kord_tr, sphum, r_vir);
 }
 int fv3o_pt_to_theta(fv3o_ctx* c, double zvir) {
   if (c->f.moist_kappa) return -2;

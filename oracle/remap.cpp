@@ -3,8 +3,8 @@
 // Vertical remapping: restatement of model/fv_mapz.F90:56-845 (Lagrangian_to_Eulerian) and of the column operators it calls in
 // model/fv_operators.F90: map_scalar (:40-134), map1_ppm (:137-229), map1_q2 (:352-443), scalar_profile (:546-916),
 // cs_profile (:919-1300), cs_limiters (:1303-1378).  Scope (everything else is refused with -2 by the C entry point):
-//   remap_te = F, moist_kappa = F, consv = 0 (no energy fixer), no intermediate physics, dry (no specific humidity: the last-step
-//   conversion T_v -> T is the identity, i.e. `adiabatic`), abs(kord) in 8..15 (the cs / scalar profiles; ppm_profile for kord <= 7
+//   remap_te = F, moist_kappa = F, use_cond = F, consv = 0 (no energy fixer), no intermediate physics; the last-step conversion
+//   T_v -> T divides by 1 + r_vir q_v when a specific-humidity tracer is named, else it is the identity (`adiabatic`), abs(kord) in 8..15 (the cs / scalar profiles; ppm_profile for kord <= 7
 //   is not restated), kord_wz > 0 (iv = -2; the iv = -3 branch of cs_profile reads an unset
 //   gam(km), :969-985), tracers with map1_q2 or, for nq > 5, with the operation order of mapn_tracer (iv = 0, no fillz).
 // The Fortran vectorises every loop over i; here one column is processed at a time (same operations on the same operands in the
@@ -295,8 +295,9 @@ int remap_work_q(V3 q, V2 ws, double* pe, const std::vector<double>& ak, const s
 
 // fv_mapz.F90:56-845 on one face; use_tracer: the number of tracers (F.qtr) remapped with kord_tr (map1_q2 for nq <= 5, :398-408; mapn_tracer for nq > 5, :390-393).
 int lagrangian_to_eulerian(const L2EFields& F, const std::vector<double>& ak, const std::vector<double>& bk, const fv3_flags_t& f, const Bd& bd,
-                           int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr) {
+                           int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr, int sphum, double r_vir) {
   if (f.moist_kappa || kord_wz < 0) return -2;
+  if (sphum >= use_tracer) return -1;
   const int km = bd.npz, is = bd.is, ie = bd.ie, js = bd.js, je = bd.je;
   const bool hydrostatic = f.hydrostatic != 0;
   const double akap = f.kappa, cv_air = f.cp_air - f.rdgas, k1k = f.rdgas / cv_air, rrg = -f.rdgas / f.grav, ptop = f.ptop;
@@ -411,7 +412,14 @@ int lagrangian_to_eulerian(const L2EFields& F, const std::vector<double>& ak, co
   for (int k = 2; k <= km; k++)
     for (int j = js; j <= je; j++)
       for (int i = is; i <= ie; i++) PE(i, k, j) = PE4(i, j, k - 1);
-  // 9) last step: T_v -> T is the identity for dry air (:792-822); otherwise back to theta_v for dyn_core (:833-843)
+  // 9) last step: T_v -> T (:792-822, dtmp = 0; no condensates: `.not. use_cond`, `.not. adiabatic` when a specific humidity is
+  //    named, the identity otherwise); not the last step: back to theta_v for dyn_core (:833-843)
+  if (last_step && sphum >= 0) {
+    V3 qv = F.qtr[sphum];
+    for (int k = 1; k <= km; k++)
+      for (int j = js; j <= je; j++)
+        for (int i = is; i <= ie; i++) pt(i, j, k) = (pt(i, j, k) + 0. / (hydrostatic ? f.cp_air : cv_air) * pkz(i, j, k)) / (1. + r_vir * qv(i, j, k));
+  }
   if (!last_step)
     for (int k = 1; k <= km; k++)
       for (int j = js; j <= je; j++)

@@ -322,10 +322,15 @@ class OracleCube:
         self.del2_cubed("HEAT", 0.20 * da_min, min(3, f["nord"] + 1))
         self.all("dcon_heating", float(bdt))
 
-    def fv_dynamics(self, bdt, k_split, n_split, kord_mt, kord_wz, kord_tm, kord_tr, hord_tr, nf_omega):
-        """fv_dynamics.F90:303-398 + :445-662 on the oracle side, the mirror of fv3_fv_dynamics (dry adiabatic subset)."""
+    def fv_dynamics(self, bdt, k_split, n_split, kord_mt, kord_wz, kord_tm, kord_tr, hord_tr, nf_omega, sphum=-1, zvir=0.0):
+        """fv_dynamics.F90:303-398 + :445-662 on the oracle side, the mirror of fv3_fv_dynamics[_qv] (no condensates)."""
         F = abi.FIELD_ID
-        self.all("pt_to_theta", 0.0)
+        if sphum >= 0:
+            self.select_tracer(sphum)
+            self.all("pt_to_theta", float(zvir))
+            self.select_tracer(0)
+        else:
+            self.all("pt_to_theta", 0.0)
         mdt = bdt / k_split
         for n_map in range(1, k_split + 1):
             last = int(n_map == k_split)
@@ -333,7 +338,8 @@ class OracleCube:
             self.dyn_core(mdt, n_split, end_step=bool(last))
             if hord_tr:
                 self.tracer_2d(hord_tr)
-            self.all("lagrangian_to_eulerian", last, kord_mt, kord_wz, kord_tm, getattr(self, "nq", 1) if hord_tr else 0, kord_tr)
+            self.all("lagrangian_to_eulerian_qv", last, kord_mt, kord_wz, kord_tm, getattr(self, "nq", 1) if hord_tr else 0, kord_tr,
+                     int(sphum), float(zvir))
             if last and nf_omega > 0:
                 self.del2_cubed("OMGA", 0.18 * self.case.tiles[0].da_min, nf_omega)
 

@@ -213,3 +213,39 @@ def test_fv_dynamics_with_several_tracers(nq):
         res = H.compare(oc.eng[t], gc.eng[t], reg2)
         _assert({k: v for k, v in res.items() if k not in ("W", "OMGA")}, 1e-9)
     oc.close(); gc.close()
+
+
+def test_fv_dynamics_with_water_vapour():
+    """fv3_fv_dynamics_qv: tracer 0 is the specific humidity (no condensates): theta_v = T (1 + zvir q_v) / pkz on entry
+    (fv_dynamics.F90:303-398), T = T_v / (1 + zvir q_v) after the last remap (fv_mapz.F90:792-822).  Against the oracle, and the
+    moisture must matter (a moist run differs from the dry one)."""
+    zvir = 461.5 / 287.05 - 1.0
+    case = H.Case(N, NPZ, "A", state="baroclinic")
+    oc, gc, gd = H.OracleCube(case), H.CudaCube(case), H.CudaCube(case)
+    for cube in (oc, gc, gd):
+        cube.set_num_tracers(2)
+    rng = np.random.default_rng(9)
+    kappa = case.consts["kappa"]
+    for t in oc.tiles:
+        eo = oc.eng[t]
+        pt, delp = eo.get("PT"), eo.get("DELP")
+        p = case.ak[0] + np.cumsum(delp, axis=0) - 0.5 * delp
+        T0 = pt * p ** kappa
+        qv = 0.015 * (p / 1.0e5) ** 3 * rng.uniform(0.5, 1.0, pt.shape)          # a few g/kg near the surface
+        q1 = rng.uniform(0.0, 1.0, pt.shape)
+        for e in (eo, gc.eng[t], gd.eng[t]):
+            e.put("PT", T0)
+            e.call("select_tracer", 0); e.put("WORK_Q", qv)
+            e.call("select_tracer", 1); e.put("WORK_Q", q1)
+            e.call("select_tracer", 0)
+    oc.fv_dynamics(1800.0, 2, 2, 9, 9, -9, 9, 8, 1, sphum=0, zvir=zvir)
+    gc.fv_dynamics(1800.0, 2, 2, 9, 9, -9, 9, 8, 1, sphum=0, zvir=zvir)
+    gd.fv_dynamics(1800.0, 2, 2, 9, 9, -9, 9, 8, 1)
+    reg = _regions(case.bounds)
+    for t in oc.tiles:
+        res = H.compare(oc.eng[t], gc.eng[t], reg)
+        _assert({k: v for k, v in res.items() if k not in ("W", "OMGA")}, 1e-9)
+    Tm = H.sub(gc.eng[1], "PT", gc.eng[1].get("PT"), 1, N, 1, N); Td = H.sub(gd.eng[1], "PT", gd.eng[1].get("PT"), 1, N, 1, N)
+    assert 150.0 < Tm.min() and Tm.max() < 350.0
+    assert np.abs(Tm - Td).max() > 1e-3
+    oc.close(); gc.close(); gd.close()
