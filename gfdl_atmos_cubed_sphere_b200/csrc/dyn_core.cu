@@ -324,8 +324,14 @@ extern "C" int fv3_fv_dynamics_qv(fv3_ctx** ctxs, int nctx, double bdt, int k_sp
     FORALL(stage_copy_field(c, FV3_DP1, FV3_DELP))                                        // :473-481 (compute domain + halo)
     if ((rc = fv3_dyn_core(ctxs, nctx, mdt, n_split, (flags & FV3_DYN_GRAPH) | (last_step ? FV3_DYN_END_STEP : 0)))) return rc;   // :495-502
     if (hord_tr != 0 && (rc = fv3_tracer_2d(ctxs, nctx, hord_tr, nullptr))) return rc;    // :512-535
-    FORALL(stage_lagrangian_to_eulerian(c, last_step, kord_mt, kord_wz, kord_tm, hord_tr != 0 ? std::max<int>(1, (int)c->tracers.size()) : 0, kord_tr,
-                                        sphum, zvir))                                     // :578-625
+    static const bool remap_serial = std::getenv("FV3_REMAP_SERIAL") != nullptr;          // experiment: one face at a time
+    for (int a_ = 0; a_ < nctx; a_++) {                                                   // :578-625
+      fv3_ctx* c = ctxs[a_];
+      cudaSetDevice(c->device);
+      if ((rc = stage_lagrangian_to_eulerian(c, last_step, kord_mt, kord_wz, kord_tm, hord_tr != 0 ? std::max<int>(1, (int)c->tracers.size()) : 0, kord_tr,
+                                             sphum, zvir))) return rc;
+      if (remap_serial) cudaStreamSynchronize(c->stream);
+    }
     if (last_step && nf_omega > 0) {                                                      // :658-662
       const double cd = 0.18 * ctxs[0]->G.da_min;
       if ((rc = fv3_del2_cubed_cube(ctxs, nctx, FV3_OMGA, cd, nf_omega))) return rc;
