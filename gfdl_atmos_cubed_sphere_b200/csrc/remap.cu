@@ -9,10 +9,13 @@
 // Design: column-parallel like the vertical solvers -- one thread per column, consecutive threads on consecutive i, so every
 // level access is a coalesced row segment of the [k][NJ][NI] arrays.  The reconstruction (a4(1:4), the interface values, the
 // differences and the extremum flags) lives in seven scratch planes of the context instead of per-thread local arrays
-// (km = 79..127 levels x 7 arrays would be 4-7 KB of local memory per thread).  The remap runs once per k_split step against
-// n_split = 8 acoustic substeps and is written for clarity, not yet for speed: ~30 passes over the column per field through the
-// scratch planes; measured 7.7 ms per C384L79 face for six fields (pt, tracer, w, delz, u, v) = 13 % on top of the 58 ms of the
-// eight acoustic substeps it follows.  The obvious next step is to fuse the passes (sliding register windows as in nh.cu).
+// (km = 79..127 levels x 7 arrays would be 4-7 KB of local memory per thread); each sweep keeps its loop-carried and neighbouring
+// values in registers.  Measured inside an fv_dynamics step at C384L79 (profiles/prof_fv_dynamics.py, ncu launch list
+// profiles/r2/r2_remap_launches.csv): 21 ms per face for six fields (pt, tracer, w, delz, u, v) against 58 ms for the eight
+// acoustic substeps it follows.  The kernels are bound by occupancy x memory-level parallelism, not by bytes (1.5 TB/s): every
+// sweep is a chain of L2 / DRAM round trips with one or two loads in flight per thread, so the launch bounds trade registers for
+// resident warps (64 -> 40 and 124 -> 64 registers bought 17 %); the next step is to batch the loads of several levels per
+// thread (software pipelining) and to split k_remap_cells per field.
 #include "fv3_ctx.hpp"
 #include <cmath>
 #include <string>
@@ -43,9 +46,8 @@ struct Col {
 #define GAM(k) LV(C.gam, k)
 #define FL(k) LV(C.fl, k)
 
-// fv_operators.F90:1303-1378 for one layer
-__device__ void cs_limiters(const Col& C, int k, bool extm, int iv) {
-  double a1 = A1(k), a2 = A2(k), a3 = A3(k), a4 = A4(k);
+// fv_operators.F90:1303-1378 for one layer, on registers
+__device__ __forceinline__ void cs_limiters(double a1, double& a2, double& a3, double& a4, bool extm, int iv) {
   if (iv == 0) {
     if (a1 <= 0.) { a2 = a1; a3 = a1; a4 = 0.; }
     else if (fabs(a3 - a2) < -a4) {
@@ -64,166 +66,224 @@ __device__ void cs_limiters(const Col& C, int k, bool extm, int iv) {
       else if (a6da > da2) { a4 = 3. * (a3 - a1); a2 = a3 - a4; }
     }
   }
-  A2(k) = a2; A3(k) = a3; A4(k) = a4;
 }
 
 // scalar_profile (scalar: with the q_min tests, :546-916) / cs_profile (:919-1300); A1 holds the layer means, P1(k) the source
-// interface pressures (k = 1..km+1)
+// interface pressures (k = 1..km+1).  Every level access is an L2 round trip (the columns of a block do not fit L1), so each sweep
+// keeps its loop-carried and neighbouring values in registers and touches a scratch element once; the operations and their
+// order are those of the Fortran.
 template <class P1>
 __device__ void profile(const Col& C, int km, const P1& pe1, double qs, int iv, int ak, double qmin, bool scalar) {
-  auto delp = [&](int k) { return pe1(k + 1) - pe1(k); };
-  if (iv == -2) {   // lower boundary condition (:570-592 / :941-963)
-    GAM(2) = 0.5;
-    QI(1) = 1.5 * A1(1);
-    for (int k = 2; k <= km - 1; k++) {
-      const double grat = delp(k - 1) / delp(k);
-      const double bet = 2. + grat + grat - GAM(k);
-      QI(k) = (3. * (A1(k - 1) + A1(k)) - QI(k - 1)) / bet;
-      GAM(k + 1) = grat / bet;
+  // ---- interface values: tridiagonal solve (:570-622 / :941-1013)
+  {
+    double plast = pe1(3);
+    double dpm, dpk;                       // delp(k - 1), delp(k)
+    { const double p1 = pe1(1), p2 = pe1(2); dpm = p2 - p1; dpk = plast - p2; }
+    double a_prev = A1(1), a_cur = A1(2);  // A1(k - 1), A1(k)
+    if (iv == -2) {   // lower boundary condition q(km+1) = qs
+      double g_cur = 0.5, q_prev = 1.5 * a_prev;
+      GAM(2) = g_cur;
+      QI(1) = q_prev;
+      for (int k = 2; k <= km - 1; k++) {
+        const double grat = dpm / dpk;
+        const double bet = 2. + grat + grat - g_cur;
+        const double qk = (3. * (a_prev + a_cur) - q_prev) / bet;
+        QI(k) = qk;
+        g_cur = grat / bet;
+        GAM(k + 1) = g_cur;
+        q_prev = qk;
+        dpm = dpk; { const double pn = pe1(k + 2); dpk = pn - plast; plast = pn; }
+        a_prev = a_cur; a_cur = A1(k + 1);
+      }
+      const double grat = dpm / dpk;       // delp(km - 1) / delp(km)
+      double q_next = (3. * (a_prev + a_cur) - grat * qs - q_prev) / (2. + grat + grat - g_cur);
+      QI(km) = q_next;
+      QI(km + 1) = qs;
+      for (int k = km - 1; k >= 1; k--) { q_next = QI(k) - GAM(k + 1) * q_next; QI(k) = q_next; }
+    } else {
+      double d4, g_prev, q_prev;
+      {
+        const double grat = dpk / dpm;     // delp(2) / delp(1)
+        const double bet = grat * (grat + 0.5);
+        q_prev = ((grat + grat) * (grat + 1.) * a_prev + a_cur) / bet;
+        g_prev = (1. + grat * (grat + 1.5)) / bet;
+        QI(1) = q_prev; GAM(1) = g_prev;
+      }
+      for (int k = 2;; k++) {
+        d4 = dpm / dpk;
+        const double bet = 2. + d4 + d4 - g_prev;
+        q_prev = (3. * (a_prev + d4 * a_cur) - q_prev) / bet;
+        g_prev = d4 / bet;
+        QI(k) = q_prev; GAM(k) = g_prev;
+        if (k == km) break;
+        dpm = dpk; { const double pn = pe1(k + 2); dpk = pn - plast; plast = pn; }
+        a_prev = a_cur; a_cur = A1(k + 1);
+      }
+      const double a_bot = 1. + d4 * (d4 + 1.5);
+      double q_next = (2. * d4 * (d4 + 1.) * a_cur + a_prev - a_bot * q_prev) / (d4 * (d4 + 0.5) - a_bot * g_prev);
+      QI(km + 1) = q_next;
+      for (int k = km; k >= 1; k--) { q_next = QI(k) - GAM(k) * q_next; QI(k) = q_next; }
     }
-    const double grat = delp(km - 1) / delp(km);
-    QI(km) = (3. * (A1(km - 1) + A1(km)) - grat * qs - QI(km - 1)) / (2. + grat + grat - GAM(km));
-    QI(km + 1) = qs;
-    for (int k = km - 1; k >= 1; k--) QI(k) = QI(k) - GAM(k + 1) * QI(k + 1);
-  } else {
-    double d4 = 0.;
+  }
+  // ---- differences gam(k) = a1(k) - a1(k-1), large-scale constraints on the interface values (:639-682 / :1034-1073) and the
+  //      continuous first-guess edge values a2(k) = q(k), a3(k) = q(k+1): one sweep, q(k-1) is finished when gam(k) is known
+  {
+    double am2 = A1(1), am1 = A1(2);       // a1(k - 2), a1(k - 1)
+    A2(1) = QI(1);
     {
-      const double grat = delp(2) / delp(1);
-      const double bet = grat * (grat + 0.5);
-      QI(1) = ((grat + grat) * (grat + 1.) * A1(1) + A1(2)) / bet;
-      GAM(1) = (1. + grat * (grat + 1.5)) / bet;
+      double q2 = QI(2);
+      q2 = dmin(q2, dmax(am2, am1));
+      q2 = dmax(q2, dmin(am2, am1));
+      A2(2) = q2; A3(1) = q2;
     }
-    for (int k = 2; k <= km; k++) {
-      d4 = delp(k - 1) / delp(k);
-      const double bet = 2. + d4 + d4 - GAM(k - 1);
-      QI(k) = (3. * (A1(k - 1) + d4 * A1(k)) - QI(k - 1)) / bet;
-      GAM(k) = d4 / bet;
+    double g_pp = 0., g_prev = am1 - am2;  // gam(k - 2), gam(k - 1)
+    GAM(2) = g_prev;
+    for (int k = 3; k <= km; k++) {
+      const double a_k = A1(k), g_k = a_k - am1;
+      GAM(k) = g_k;
+      if (k >= 4) {                        // interface k - 1 (3 .. km - 1): gam(k - 2), gam(k), a1(k - 2), a1(k - 1)
+        const double lo = dmin(am2, am1), hi = dmax(am2, am1);
+        double qk = QI(k - 1);
+        if (ak >= 14 || g_pp * g_k > 0.) { qk = dmin(qk, hi); qk = dmax(qk, lo); }
+        else if (g_pp > 0.) qk = dmax(qk, lo);
+        else { qk = dmin(qk, hi); if (iv == 0) qk = dmax(0., qk); }
+        A2(k - 1) = qk; A3(k - 2) = qk;
+      }
+      g_pp = g_prev; g_prev = g_k; am2 = am1; am1 = a_k;
     }
-    const double a_bot = 1. + d4 * (d4 + 1.5);
-    QI(km + 1) = (2. * d4 * (d4 + 1.) * A1(km) + A1(km - 1) - a_bot * QI(km)) / (d4 * (d4 + 0.5) - a_bot * GAM(km));
-    for (int k = km; k >= 1; k--) QI(k) = QI(k) - GAM(k) * QI(k + 1);
+    {                                      // interface km (am2 = a1(km - 1), am1 = a1(km))
+      double qk = QI(km);
+      qk = dmin(qk, dmax(am2, am1));
+      qk = dmax(qk, dmin(am2, am1));
+      A2(km) = qk; A3(km - 1) = qk;
+    }
+    A3(km) = QI(km + 1);
   }
-  // large-scale constraints on the interface values (:639-682 / :1034-1073)
+  // ---- extremum flags (:695-715 / :1082-1102)
   {
-    double q2 = QI(2);
-    q2 = dmin(q2, dmax(A1(1), A1(2)));
-    q2 = dmax(q2, dmin(A1(1), A1(2)));
-    QI(2) = q2;
+    double a2 = A2(1), g_k = 0.;
+    for (int k = 1; k <= km; k++) {
+      const double a1 = A1(k), a3 = A3(k);
+      const double g_k1 = k < km ? GAM(k + 1) : 0.;
+      int f;
+      if (k == 1 || k == km) f = ((a2 - a1) * (a3 - a1) > 0.) ? 1 : 0;
+      else f = (g_k * g_k1 < 0.) ? 1 : 0;
+      if (ak > 9) {
+        const double x0 = 2. * a1 - (a2 + a3), x1 = fabs(a2 - a3);
+        const double a4 = 3. * x0;
+        A4(k) = a4;
+        if (fabs(x0) > x1) f |= 2;
+        if (fabs(a4) > x1) f |= 4;
+      }
+      FL(k) = f;
+      a2 = a3;                             // the first-guess profile is continuous: a2(k + 1) = a3(k)
+      g_k = g_k1;
+    }
   }
-  for (int k = 2; k <= km; k++) GAM(k) = A1(k) - A1(k - 1);
-  for (int k = 3; k <= km - 1; k++) {
-    const double lo = dmin(A1(k - 1), A1(k)), hi = dmax(A1(k - 1), A1(k));
-    double qk = QI(k);
-    if (ak >= 14 || GAM(k - 1) * GAM(k + 1) > 0.) { qk = dmin(qk, hi); qk = dmax(qk, lo); }
-    else if (GAM(k - 1) > 0.) qk = dmax(qk, lo);
-    else { qk = dmin(qk, hi); if (iv == 0) qk = dmax(0., qk); }
-    QI(k) = qk;
+  // ---- top two layers (:721-754 / :1109-1140)
+  {
+    const double a1 = A1(1);
+    double a2 = A2(1), a3 = A3(1), a4 = 0.;
+    if (iv == 0) a2 = dmax(0., a2);
+    else if (iv == -1) { if (a2 * a1 <= 0.) a2 = 0.; }
+    else if (iv == 2) { a2 = a1; a3 = a1; a4 = 0.; }
+    if (iv != 2) {
+      a4 = 3. * (2. * a1 - (a2 + a3));
+      cs_limiters(a1, a2, a3, a4, FL(1) & 1, 1);
+    }
+    A2(1) = a2; A3(1) = a3; A4(1) = a4;
   }
   {
-    double qk = QI(km);
-    qk = dmin(qk, dmax(A1(km - 1), A1(km)));
-    qk = dmax(qk, dmin(A1(km - 1), A1(km)));
-    QI(km) = qk;
+    const double a1 = A1(2);
+    double a2 = A2(2), a3 = A3(2), a4 = 3. * (2. * a1 - (a2 + a3));
+    cs_limiters(a1, a2, a3, a4, FL(2) & 1, 2);
+    A2(2) = a2; A3(2) = a3; A4(2) = a4;
   }
-  for (int k = 1; k <= km; k++) { A2(k) = QI(k); A3(k) = QI(k + 1); }
-  // extremum flags (:695-715 / :1082-1102)
-  for (int k = 1; k <= km; k++) {
-    int f;
-    if (k == 1 || k == km) f = ((A2(k) - A1(k)) * (A3(k) - A1(k)) > 0.) ? 1 : 0;
-    else f = (GAM(k) * GAM(k + 1) < 0.) ? 1 : 0;
-    if (ak > 9) {
-      const double x0 = 2. * A1(k) - (A2(k) + A3(k)), x1 = fabs(A2(k) - A3(k));
-      const double a4 = 3. * x0;
-      A4(k) = a4;
-      if (fabs(x0) > x1) f |= 2;
-      if (fabs(a4) > x1) f |= 4;
-    }
-    FL(k) = f;
-  }
-  // top two layers (:721-754 / :1109-1140)
-  if (iv == 0) A2(1) = dmax(0., A2(1));
-  else if (iv == -1) { if (A2(1) * A1(1) <= 0.) A2(1) = 0.; }
-  else if (iv == 2) { A2(1) = A1(1); A3(1) = A1(1); A4(1) = 0.; }
-  if (iv != 2) {
-    A4(1) = 3. * (2. * A1(1) - (A2(1) + A3(1)));
-    cs_limiters(C, 1, FL(1) & 1, 1);
-  }
-  A4(2) = 3. * (2. * A1(2) - (A2(2) + A3(2)));
-  cs_limiters(C, 2, FL(2) & 1, 2);
-  // Huynh's second constraint in the interior (:759-893 / :1142-1276)
-  auto huynh = [&](int k) {
-    const double a1 = A1(k);
-    const double pmp_1 = a1 - 2. * GAM(k + 1), lac_1 = pmp_1 + 1.5 * GAM(k + 2);
-    A2(k) = dmin(dmax(A2(k), dmin3(a1, pmp_1, lac_1)), dmax3(a1, pmp_1, lac_1));
-    const double pmp_2 = a1 + 2. * GAM(k), lac_2 = pmp_2 - 1.5 * GAM(k - 1);
-    A3(k) = dmin(dmax(A3(k), dmin3(a1, pmp_2, lac_2)), dmax3(a1, pmp_2, lac_2));
-  };
-  auto flat = [&](int k) { const double a1 = A1(k); A2(k) = a1; A3(k) = a1; A4(k) = 0.; };
-  auto a6_a = [&](int k) { return 3. * (2. * A1(k) - (A2(k) + A3(k))); };
-  auto a6_b = [&](int k) { return 6. * A1(k) - 3. * (A2(k) + A3(k)); };
-  for (int k = 3; k <= km - 2; k++) {
-    const int f0 = FL(k), fm = FL(k - 1), fp = FL(k + 1);
-    const bool small = scalar && A1(k) < qmin;
-    switch (ak) {
-      case 8:
-        huynh(k);
-        A4(k) = a6_a(k);
-        break;
-      case 9:
-        if ((f0 & 1) && ((fm & 1) || (fp & 1) || small)) flat(k);
-        else {
-          double a4 = scalar ? a6_a(k) : a6_b(k);
-          if (fabs(a4) > fabs(A2(k) - A3(k))) {
-            huynh(k);
-            a4 = scalar ? a6_a(k) : a6_b(k);
+  // ---- Huynh's second constraint in the interior (:759-893 / :1142-1276)
+  if (km >= 5) {
+    int fm = FL(2), f0 = FL(3);
+    double gm = GAM(2), g0 = GAM(3), g1 = GAM(4);      // gam(k - 1), gam(k), gam(k + 1)
+    for (int k = 3; k <= km - 2; k++) {
+      const int fp = FL(k + 1);
+      const double g2 = GAM(k + 2);
+      const double a1 = A1(k);
+      double a2 = A2(k), a3 = A3(k), a4 = ak >= 14 ? A4(k) : 0.;
+      const bool small = scalar && a1 < qmin;
+      auto huynh = [&]() {
+        const double pmp_1 = a1 - 2. * g1, lac_1 = pmp_1 + 1.5 * g2;
+        a2 = dmin(dmax(a2, dmin3(a1, pmp_1, lac_1)), dmax3(a1, pmp_1, lac_1));
+        const double pmp_2 = a1 + 2. * g0, lac_2 = pmp_2 - 1.5 * gm;
+        a3 = dmin(dmax(a3, dmin3(a1, pmp_2, lac_2)), dmax3(a1, pmp_2, lac_2));
+      };
+      auto flat = [&]() { a2 = a1; a3 = a1; a4 = 0.; };
+      auto a6_a = [&]() { return 3. * (2. * a1 - (a2 + a3)); };
+      auto a6_b = [&]() { return 6. * a1 - 3. * (a2 + a3); };
+      switch (ak) {
+        case 8:
+          huynh();
+          a4 = a6_a();
+          break;
+        case 9:
+          if ((f0 & 1) && ((fm & 1) || (fp & 1) || small)) flat();
+          else {
+            a4 = scalar ? a6_a() : a6_b();
+            if (fabs(a4) > fabs(a2 - a3)) {
+              huynh();
+              a4 = scalar ? a6_a() : a6_b();
+            }
           }
-          A4(k) = a4;
-        }
-        break;
-      case 10:
-        if (f0 & 1) {
-          if (small || (fm & 1) || (fp & 1)) flat(k);
-          else A4(k) = a6_b(k);
-        } else {
-          double a4 = a6_b(k);
-          if (fabs(a4) > fabs(A2(k) - A3(k))) {
-            huynh(k);
-            a4 = a6_b(k);
+          break;
+        case 10:
+          if (f0 & 1) {
+            if (small || (fm & 1) || (fp & 1)) flat();
+            else a4 = a6_b();
+          } else {
+            a4 = a6_b();
+            if (fabs(a4) > fabs(a2 - a3)) {
+              huynh();
+              a4 = a6_b();
+            }
           }
-          A4(k) = a4;
-        }
-        break;
-      case 11:
-        if ((f0 & 2) && ((fm & 2) || (fp & 2) || small)) flat(k);
-        else A4(k) = a6_a(k);
-        break;
-      case 12:
-        if (f0 & 2) {
-          if ((fm & 2) || (fp & 2)) { const double a1 = A1(k); A2(k) = a1; A3(k) = a1; }
-          else if ((fm & 4) || (fp & 4)) huynh(k);
-        } else if (f0 & 4) {
-          if ((fm & 2) || (fp & 2)) huynh(k);
-        }
-        A4(k) = a6_a(k);
-        break;
-      case 13:
-        A4(k) = a6_a(k);
-        break;
-      case 14:   // strict monotonicity constraint (A4 as the flag loop left it)
-        cs_limiters(C, k, f0 & 1, 2);
-        break;
-      default:   // 15
-        cs_limiters(C, k, f0 & 1, 1);
-        break;
+          break;
+        case 11:
+          if ((f0 & 2) && ((fm & 2) || (fp & 2) || small)) flat();
+          else a4 = a6_a();
+          break;
+        case 12:
+          if (f0 & 2) {
+            if ((fm & 2) || (fp & 2)) { a2 = a1; a3 = a1; }
+            else if ((fm & 4) || (fp & 4)) huynh();
+          } else if (f0 & 4) {
+            if ((fm & 2) || (fp & 2)) huynh();
+          }
+          a4 = a6_a();
+          break;
+        case 13:
+          a4 = a6_a();
+          break;
+        case 14:   // strict monotonicity constraint (a4 as the flag sweep left it)
+          cs_limiters(a1, a2, a3, a4, f0 & 1, 2);
+          break;
+        default:   // 15
+          cs_limiters(a1, a2, a3, a4, f0 & 1, 1);
+          break;
+      }
+      if (iv == 0 && ak <= 13) cs_limiters(a1, a2, a3, a4, f0 & 1, 0);
+      A2(k) = a2; A3(k) = a3; A4(k) = a4;
+      fm = f0; f0 = fp; gm = g0; g0 = g1; g1 = g2;
     }
-    if (iv == 0 && ak <= 13) cs_limiters(C, k, f0 & 1, 0);
   }
-  // bottom two layers (:898-914 / :1281-1298)
-  if (iv == 0) A3(km) = dmax(0., A3(km));
-  else if (iv == -1) { if (A3(km) * A1(km) <= 0.) A3(km) = 0.; }
+  // ---- bottom two layers (:898-914 / :1281-1298)
   for (int k = km - 1; k <= km; k++) {
-    A4(k) = 3. * (2. * A1(k) - (A2(k) + A3(k)));
-    cs_limiters(C, k, FL(k) & 1, k == km - 1 ? 2 : 1);
+    const double a1 = A1(k);
+    double a2 = A2(k), a3 = A3(k);
+    if (k == km) {
+      if (iv == 0) a3 = dmax(0., a3);
+      else if (iv == -1) { if (a3 * a1 <= 0.) a3 = 0.; }
+    }
+    double a4 = 3. * (2. * a1 - (a2 + a3));
+    cs_limiters(a1, a2, a3, a4, FL(k) & 1, k == km - 1 ? 2 : 1);
+    A2(k) = a2; A3(k) = a3; A4(k) = a4;
   }
 }
 
@@ -303,7 +363,7 @@ struct L2E {
 };
 
 // steps 0 - 3.3 of fv_mapz.F90 (:188-526) for the cell columns
-__global__ void __launch_bounds__(CB) k_remap_cells(Lay L, L2E a, Scr S) {
+__global__ void __launch_bounds__(CB, 8) k_remap_cells(Lay L, L2E a, Scr S) {
   const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;
   const int t = blockIdx.x * CB + threadIdx.x;
   if (t >= nx * ny) return;
@@ -366,7 +426,7 @@ __global__ void __launch_bounds__(CB) k_remap_cells(Lay L, L2E a, Scr S) {
 
 // 4.1 / 4.2 (:535-571): u on the south faces (DIR = 0: i in is..ie, j in js..je+1), v on the west faces (DIR = 1)
 template <int DIR>
-__global__ void __launch_bounds__(CB) k_remap_wind(Lay L, L2E a, Scr S) {
+__global__ void __launch_bounds__(CB, 12) k_remap_wind(Lay L, L2E a, Scr S) {
   const int nx = L.ie - L.is + 1 + DIR, ny = L.je - L.js + 1 + (1 - DIR);
   const int t = blockIdx.x * CB + threadIdx.x;
   if (t >= nx * ny) return;
