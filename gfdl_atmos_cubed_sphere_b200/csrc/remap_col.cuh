@@ -1,0 +1,341 @@
+// Column operators of the vertical remap (fv_operators.F90: scalar_profile / cs_profile :546-1300, cs_limiters :1303-1378, the
+// mapping loop of map_scalar / map1_ppm / map1_q2 / mapn_tracer :88-132, 183-227, 276-336, 399-441) for ONE column whose
+// reconstruction arrays are strided (level stride = plane).  __host__ __device__: remap.cu runs them one thread per column; the
+// CPU suite runs the same source on the host against the oracle (tests/host_remap_test.cu, tests/test_host_remap.py).
+#pragma once
+#include <cmath>
+
+#ifdef __CUDACC__
+#define RMP_HD __host__ __device__
+#else
+#define RMP_HD
+#endif
+
+namespace rmp {
+
+constexpr double r3 = 1. / 3., r23 = 2. / 3., r12 = 1. / 12.;
+
+RMP_HD inline double dmin(double a, double b) { return a < b ? a : b; }
+RMP_HD inline double dmax(double a, double b) { return a > b ? a : b; }
+RMP_HD inline double dmin3(double a, double b, double c) { return dmin(dmin(a, b), c); }
+RMP_HD inline double dmax3(double a, double b, double c) { return dmax(dmax(a, b), c); }
+
+// the scratch of one column: pointers already offset to the column, level k (1-based) at [(k - 1) * plane]
+struct Col {
+  double *a1, *a2, *a3, *a4, *q, *gam;
+  int* fl;   // bit 0 extm, bit 1 ext5, bit 2 ext6
+  long long plane;
+};
+#define LV(p, k) (p)[(long long)((k) - 1) * C.plane]
+#define A1(k) LV(C.a1, k)
+#define A2(k) LV(C.a2, k)
+#define A3(k) LV(C.a3, k)
+#define A4(k) LV(C.a4, k)
+#define QI(k) LV(C.q, k)
+#define GAM(k) LV(C.gam, k)
+#define FL(k) LV(C.fl, k)
+
+// fv_operators.F90:1303-1378 for one layer, on registers
+RMP_HD inline void cs_limiters(double a1, double& a2, double& a3, double& a4, bool extm, int iv) {
+  if (iv == 0) {
+    if (a1 <= 0.) { a2 = a1; a3 = a1; a4 = 0.; }
+    else if (fabs(a3 - a2) < -a4) {
+      if ((a1 + 0.25 * ((a3 - a2) * (a3 - a2)) / a4 + a4 * r12) < 0.) {
+        if (a1 < a3 && a1 < a2) { a3 = a1; a2 = a1; a4 = 0.; }
+        else if (a3 > a2) { a4 = 3. * (a2 - a1); a3 = a2 - a4; }
+        else { a4 = 3. * (a3 - a1); a2 = a3 - a4; }
+      }
+    }
+  } else {
+    const bool flat = iv == 1 ? ((a1 - a2) * (a1 - a3) >= 0.) : extm;
+    if (flat) { a2 = a1; a3 = a1; a4 = 0.; }
+    else {
+      const double da1 = a3 - a2, da2 = da1 * da1, a6da = a4 * da1;
+      if (a6da < -da2) { a4 = 3. * (a2 - a1); a3 = a2 - a4; }
+      else if (a6da > da2) { a4 = 3. * (a3 - a1); a2 = a3 - a4; }
+    }
+  }
+}
+
+// scalar_profile (scalar: with the q_min tests, :546-916) / cs_profile (:919-1300); A1 holds the layer means, P1(k) the source
+// interface pressures (k = 1..km+1).  Every level access is an L2 round trip (the columns of a block do not fit L1), so each sweep
+// keeps its loop-carried and neighbouring values in registers and touches a scratch element once; the operations and their
+// order are those of the Fortran.
+template <class P1>
+RMP_HD inline void profile(const Col& C, int km, const P1& pe1, double qs, int iv, int ak, double qmin, bool scalar) {
+  // ---- interface values: tridiagonal solve (:570-622 / :941-1013)
+  {
+    double plast = pe1(3);
+    double dpm, dpk;                       // delp(k - 1), delp(k)
+    { const double p1 = pe1(1), p2 = pe1(2); dpm = p2 - p1; dpk = plast - p2; }
+    double a_prev = A1(1), a_cur = A1(2);  // A1(k - 1), A1(k)
+    if (iv == -2) {   // lower boundary condition q(km+1) = qs
+      double g_cur = 0.5, q_prev = 1.5 * a_prev;
+      GAM(2) = g_cur;
+      QI(1) = q_prev;
+      for (int k = 2; k <= km - 1; k++) {
+        const double grat = dpm / dpk;
+        const double bet = 2. + grat + grat - g_cur;
+        const double qk = (3. * (a_prev + a_cur) - q_prev) / bet;
+        QI(k) = qk;
+        g_cur = grat / bet;
+        GAM(k + 1) = g_cur;
+        q_prev = qk;
+        dpm = dpk; { const double pn = pe1(k + 2); dpk = pn - plast; plast = pn; }
+        a_prev = a_cur; a_cur = A1(k + 1);
+      }
+      const double grat = dpm / dpk;       // delp(km - 1) / delp(km)
+      double q_next = (3. * (a_prev + a_cur) - grat * qs - q_prev) / (2. + grat + grat - g_cur);
+      QI(km) = q_next;
+      QI(km + 1) = qs;
+      for (int k = km - 1; k >= 1; k--) { q_next = QI(k) - GAM(k + 1) * q_next; QI(k) = q_next; }
+    } else {
+      double d4, g_prev, q_prev;
+      {
+        const double grat = dpk / dpm;     // delp(2) / delp(1)
+        const double bet = grat * (grat + 0.5);
+        q_prev = ((grat + grat) * (grat + 1.) * a_prev + a_cur) / bet;
+        g_prev = (1. + grat * (grat + 1.5)) / bet;
+        QI(1) = q_prev; GAM(1) = g_prev;
+      }
+      for (int k = 2;; k++) {
+        d4 = dpm / dpk;
+        const double bet = 2. + d4 + d4 - g_prev;
+        q_prev = (3. * (a_prev + d4 * a_cur) - q_prev) / bet;
+        g_prev = d4 / bet;
+        QI(k) = q_prev; GAM(k) = g_prev;
+        if (k == km) break;
+        dpm = dpk; { const double pn = pe1(k + 2); dpk = pn - plast; plast = pn; }
+        a_prev = a_cur; a_cur = A1(k + 1);
+      }
+      const double a_bot = 1. + d4 * (d4 + 1.5);
+      double q_next = (2. * d4 * (d4 + 1.) * a_cur + a_prev - a_bot * q_prev) / (d4 * (d4 + 0.5) - a_bot * g_prev);
+      QI(km + 1) = q_next;
+      for (int k = km; k >= 1; k--) { q_next = QI(k) - GAM(k) * q_next; QI(k) = q_next; }
+    }
+  }
+  // ---- differences gam(k) = a1(k) - a1(k-1), large-scale constraints on the interface values (:639-682 / :1034-1073) and the
+  //      continuous first-guess edge values a2(k) = q(k), a3(k) = q(k+1): one sweep, q(k-1) is finished when gam(k) is known
+  {
+    double am2 = A1(1), am1 = A1(2);       // a1(k - 2), a1(k - 1)
+    A2(1) = QI(1);
+    {
+      double q2 = QI(2);
+      q2 = dmin(q2, dmax(am2, am1));
+      q2 = dmax(q2, dmin(am2, am1));
+      A2(2) = q2; A3(1) = q2;
+    }
+    double g_pp = 0., g_prev = am1 - am2;  // gam(k - 2), gam(k - 1)
+    GAM(2) = g_prev;
+    for (int k = 3; k <= km; k++) {
+      const double a_k = A1(k), g_k = a_k - am1;
+      GAM(k) = g_k;
+      if (k >= 4) {                        // interface k - 1 (3 .. km - 1): gam(k - 2), gam(k), a1(k - 2), a1(k - 1)
+        const double lo = dmin(am2, am1), hi = dmax(am2, am1);
+        double qk = QI(k - 1);
+        if (ak >= 14 || g_pp * g_k > 0.) { qk = dmin(qk, hi); qk = dmax(qk, lo); }
+        else if (g_pp > 0.) qk = dmax(qk, lo);
+        else { qk = dmin(qk, hi); if (iv == 0) qk = dmax(0., qk); }
+        A2(k - 1) = qk; A3(k - 2) = qk;
+      }
+      g_pp = g_prev; g_prev = g_k; am2 = am1; am1 = a_k;
+    }
+    {                                      // interface km (am2 = a1(km - 1), am1 = a1(km))
+      double qk = QI(km);
+      qk = dmin(qk, dmax(am2, am1));
+      qk = dmax(qk, dmin(am2, am1));
+      A2(km) = qk; A3(km - 1) = qk;
+    }
+    A3(km) = QI(km + 1);
+  }
+  // ---- extremum flags (:695-715 / :1082-1102)
+  {
+    double a2 = A2(1), g_k = 0.;
+    for (int k = 1; k <= km; k++) {
+      const double a1 = A1(k), a3 = A3(k);
+      const double g_k1 = k < km ? GAM(k + 1) : 0.;
+      int f;
+      if (k == 1 || k == km) f = ((a2 - a1) * (a3 - a1) > 0.) ? 1 : 0;
+      else f = (g_k * g_k1 < 0.) ? 1 : 0;
+      if (ak > 9) {
+        const double x0 = 2. * a1 - (a2 + a3), x1 = fabs(a2 - a3);
+        const double a4 = 3. * x0;
+        A4(k) = a4;
+        if (fabs(x0) > x1) f |= 2;
+        if (fabs(a4) > x1) f |= 4;
+      }
+      FL(k) = f;
+      a2 = a3;                             // the first-guess profile is continuous: a2(k + 1) = a3(k)
+      g_k = g_k1;
+    }
+  }
+  // ---- top two layers (:721-754 / :1109-1140)
+  {
+    const double a1 = A1(1);
+    double a2 = A2(1), a3 = A3(1), a4 = 0.;
+    if (iv == 0) a2 = dmax(0., a2);
+    else if (iv == -1) { if (a2 * a1 <= 0.) a2 = 0.; }
+    else if (iv == 2) { a2 = a1; a3 = a1; a4 = 0.; }
+    if (iv != 2) {
+      a4 = 3. * (2. * a1 - (a2 + a3));
+      cs_limiters(a1, a2, a3, a4, FL(1) & 1, 1);
+    }
+    A2(1) = a2; A3(1) = a3; A4(1) = a4;
+  }
+  {
+    const double a1 = A1(2);
+    double a2 = A2(2), a3 = A3(2), a4 = 3. * (2. * a1 - (a2 + a3));
+    cs_limiters(a1, a2, a3, a4, FL(2) & 1, 2);
+    A2(2) = a2; A3(2) = a3; A4(2) = a4;
+  }
+  // ---- Huynh's second constraint in the interior (:759-893 / :1142-1276)
+  if (km >= 5) {
+    int fm = FL(2), f0 = FL(3);
+    double gm = GAM(2), g0 = GAM(3), g1 = GAM(4);      // gam(k - 1), gam(k), gam(k + 1)
+    for (int k = 3; k <= km - 2; k++) {
+      const int fp = FL(k + 1);
+      const double g2 = GAM(k + 2);
+      const double a1 = A1(k);
+      double a2 = A2(k), a3 = A3(k), a4 = ak >= 14 ? A4(k) : 0.;
+      const bool small = scalar && a1 < qmin;
+      auto huynh = [&]() {
+        const double pmp_1 = a1 - 2. * g1, lac_1 = pmp_1 + 1.5 * g2;
+        a2 = dmin(dmax(a2, dmin3(a1, pmp_1, lac_1)), dmax3(a1, pmp_1, lac_1));
+        const double pmp_2 = a1 + 2. * g0, lac_2 = pmp_2 - 1.5 * gm;
+        a3 = dmin(dmax(a3, dmin3(a1, pmp_2, lac_2)), dmax3(a1, pmp_2, lac_2));
+      };
+      auto flat = [&]() { a2 = a1; a3 = a1; a4 = 0.; };
+      auto a6_a = [&]() { return 3. * (2. * a1 - (a2 + a3)); };
+      auto a6_b = [&]() { return 6. * a1 - 3. * (a2 + a3); };
+      switch (ak) {
+        case 8:
+          huynh();
+          a4 = a6_a();
+          break;
+        case 9:
+          if ((f0 & 1) && ((fm & 1) || (fp & 1) || small)) flat();
+          else {
+            a4 = scalar ? a6_a() : a6_b();
+            if (fabs(a4) > fabs(a2 - a3)) {
+              huynh();
+              a4 = scalar ? a6_a() : a6_b();
+            }
+          }
+          break;
+        case 10:
+          if (f0 & 1) {
+            if (small || (fm & 1) || (fp & 1)) flat();
+            else a4 = a6_b();
+          } else {
+            a4 = a6_b();
+            if (fabs(a4) > fabs(a2 - a3)) {
+              huynh();
+              a4 = a6_b();
+            }
+          }
+          break;
+        case 11:
+          if ((f0 & 2) && ((fm & 2) || (fp & 2) || small)) flat();
+          else a4 = a6_a();
+          break;
+        case 12:
+          if (f0 & 2) {
+            if ((fm & 2) || (fp & 2)) { a2 = a1; a3 = a1; }
+            else if ((fm & 4) || (fp & 4)) huynh();
+          } else if (f0 & 4) {
+            if ((fm & 2) || (fp & 2)) huynh();
+          }
+          a4 = a6_a();
+          break;
+        case 13:
+          a4 = a6_a();
+          break;
+        case 14:   // strict monotonicity constraint (a4 as the flag sweep left it)
+          cs_limiters(a1, a2, a3, a4, f0 & 1, 2);
+          break;
+        default:   // 15
+          cs_limiters(a1, a2, a3, a4, f0 & 1, 1);
+          break;
+      }
+      if (iv == 0 && ak <= 13) cs_limiters(a1, a2, a3, a4, f0 & 1, 0);
+      A2(k) = a2; A3(k) = a3; A4(k) = a4;
+      fm = f0; f0 = fp; gm = g0; g0 = g1; g1 = g2;
+    }
+  }
+  // ---- bottom two layers (:898-914 / :1281-1298)
+  for (int k = km - 1; k <= km; k++) {
+    const double a1 = A1(k);
+    double a2 = A2(k), a3 = A3(k);
+    if (k == km) {
+      if (iv == 0) a3 = dmax(0., a3);
+      else if (iv == -1) { if (a3 * a1 <= 0.) a3 = 0.; }
+    }
+    double a4 = 3. * (2. * a1 - (a2 + a3));
+    cs_limiters(a1, a2, a3, a4, FL(k) & 1, k == km - 1 ? 2 : 1);
+    A2(k) = a2; A3(k) = a3; A4(k) = a4;
+  }
+}
+
+// the conservative mapping loop (fv_operators.F90:88-132 = 183-227 = 399-441): P1 source, P2 target interface pressures;
+// out(k, value) stores layer k.  div_dp2: map1_q2 divides by the tabulated target thickness -- the same difference here.
+// mapn: the operation order of mapn_tracer (:276-336), which fv_mapz uses for nq > 5 tracers
+template <class P1, class P2, class Out>
+RMP_HD inline void map_column(const Col& C, int km, const P1& pe1, const P2& pe2, Out&& out, bool mapn = false) {
+  int k0 = 1;
+  for (int k = 1; k <= km; k++) {
+    const double t = pe2(k), b = pe2(k + 1);
+    double qsum = 0.;
+    bool done = false;
+    for (int l = k0; l <= km; l++) {
+      const double p0 = pe1(l), p1 = pe1(l + 1);
+      if (t >= p0 && t <= p1) {
+        const double dpl = p1 - p0;
+        const double pl = (t - p0) / dpl;
+        const double a2 = A2(l), a3 = A3(l), a4 = A4(l);
+        if (b <= p1) {
+          const double pr = (b - p0) / dpl;
+          if (mapn) {
+            double fac1 = pr + pl;
+            const double fac2 = r3 * (pr * fac1 + pl * pl);
+            fac1 = 0.5 * fac1;
+            out(k, a2 + (a4 + a3 - a2) * fac1 - a4 * fac2);
+          } else out(k, a2 + 0.5 * (a4 + a3 - a2) * (pr + pl) - a4 * r3 * (pr * (pr + pl) + pl * pl));
+          k0 = l;
+          done = true;
+        } else {
+          if (mapn) {
+            double fac1 = 1. + pl;
+            const double fac2 = r3 * (1. + pl * fac1);
+            fac1 = 0.5 * fac1;
+            qsum = (p1 - t) * (a2 + (a4 + a3 - a2) * fac1 - a4 * fac2);
+          } else qsum = (p1 - t) * (a2 + 0.5 * (a4 + a3 - a2) * (1. + pl) - a4 * (r3 * (1. + pl * (1. + pl))));
+          for (int m = l + 1; m <= km; m++) {
+            const double m0 = pe1(m), m1 = pe1(m + 1);
+            if (b > m1) qsum = qsum + (m1 - m0) * A1(m);
+            else {
+              const double dp = b - m0, esl = dp / (m1 - m0);
+              if (mapn) { const double fac1 = 0.5 * esl, fac2 = 1. - r23 * esl; qsum = qsum + dp * (A2(m) + fac1 * (A3(m) - A2(m) + A4(m) * fac2)); }
+              else qsum = qsum + dp * (A2(m) + 0.5 * esl * (A3(m) - A2(m) + A4(m) * (1. - r23 * esl)));
+              k0 = m;
+              break;
+            }
+          }
+        }
+        break;
+      }
+    }
+    if (!done) out(k, qsum / (b - t));
+  }
+}
+
+// map_scalar / map1_ppm / map1_q2 (mapn: in the operation order of mapn_tracer) of one column, in place on fld (level k at
+// fld[(k-1)*plane]); scalar: scalar_profile (with the q_min tests), else cs_profile
+template <class P1, class P2>
+RMP_HD inline void remap_field(const Col& C, int km, const P1& pe1, const P2& pe2, double* fld, double qs, int iv, int kord, double qmin,
+                               bool scalar, bool mapn = false) {
+  for (int k = 1; k <= km; k++) A1(k) = LV(fld, k);
+  profile(C, km, pe1, qs, iv, kord < 0 ? -kord : kord, qmin, scalar);
+  map_column(C, km, pe1, pe2, [&](int k, double v) { LV(fld, k) = v; }, mapn);
+}
+
+}  // namespace rmp
