@@ -271,7 +271,7 @@ void fv3_destroy(fv3_ctx* c) {
   for (auto p : alts) cudaFree(p);
   for (int i = 0; i < fv3_ctx::NSCR; i++) cudaFree(c->scr[i]);
   for (auto p : c->metric_alloc) cudaFree(p);
-  cudaFree(c->d_stage); cudaFree(c->d_kint); cudaFree(c->d_kdbl); cudaFree(c->d_dp_ref); cudaFree(c->d_edge_tab); cudaFree(c->d_rff); cudaFree(c->d_akbk); cudaFree(c->d_divg2); cudaFree(c->d_pem); cudaFree(c->d_qtr_tab);
+  cudaFree(c->d_stage); cudaFree(c->d_kint); cudaFree(c->d_kdbl); cudaFree(c->d_dp_ref); cudaFree(c->d_edge_tab); cudaFree(c->d_rff); cudaFree(c->d_akbk); cudaFree(c->d_divg2); cudaFree(c->d_pem);
   for (auto& kv : c->timers) { cudaEventDestroy(kv.second.e0); cudaEventDestroy(kv.second.e1); }
   cudaStreamDestroy(c->stream);
   delete c;

@@ -140,7 +140,6 @@ struct fv3_ctx {
   // tracers (fv3_set_num_tracers): every tracer array incl. the one FV3_WORK_Q was created with; fld[FV3_WORK_Q] always aliases
   // tracers[tracer_sel] (fv3_select_tracer), so every single-tracer entry point works on the selected one
   std::vector<double*> tracers; int tracer_sel = 0;
-  double** d_qtr_tab = nullptr;    // device copy of the tracer table for the remap kernel
   double* d_pem = nullptr;         // interface pressures before the last substep (omega diagnostic), npz + 1 planes, built on first use
   double* d_divg2 = nullptr;       // external-mode damping term (d_ext > 0), one plane, built on first use
   double* d_akbk = nullptr;        // ak(0:km), bk(0:km) for the vertical remap (remap.cu), built on first use

@@ -11,11 +11,10 @@
 // differences and the extremum flags) lives in seven scratch planes of the context instead of per-thread local arrays
 // (km = 79..127 levels x 7 arrays would be 4-7 KB of local memory per thread); each sweep keeps its loop-carried and neighbouring
 // values in registers.  Measured inside an fv_dynamics step at C384L79 (profiles/prof_fv_dynamics.py, ncu launch list
-// profiles/r2/r2_remap_launches.csv): 21 ms per face for six fields (pt, tracer, w, delz, u, v) against 58 ms for the eight
-// acoustic substeps it follows.  The kernels are bound by occupancy x memory-level parallelism, not by bytes (1.5 TB/s): every
-// sweep is a chain of L2 / DRAM round trips with one or two loads in flight per thread, so the launch bounds trade registers for
-// resident warps (64 -> 40 and 124 -> 64 registers bought 17 %); the next step is to batch the loads of several levels per
-// thread (software pipelining) and to split k_remap_cells per field.
+// profiles/r2/r2_remap_launches.csv): 20 ms per face for six fields (pt, tracer, w, delz, u, v) against 58 ms for the eight
+// acoustic substeps it follows (26 ms before the register carries, the four-level load batches of remap_col.cuh, the per-field
+// launches and the launch bounds below; one fv_dynamics step 506 -> 476 ms).  The kernels are bound by occupancy x memory-level
+// parallelism, not by bytes (1.5 TB/s): every sweep is a chain of L2 / DRAM round trips.
 #include "fv3_ctx.hpp"
 #include <cmath>
 #include <string>
@@ -35,14 +34,17 @@ __device__ __forceinline__ Col col_of(const Scr& S, long long o, long long plane
 
 struct L2E {
   double *pt, *delp, *delz, *w, *u, *v, *pk, *pkz, *omga, *qtr, *pe, *peln;
-  double* const* qtrs;   // device table of the tracer arrays (use_tracer entries)
+  const double* qv;      // the specific-humidity tracer (last-step conversion), or nullptr
   const double *ws, *ak, *bk;   // ak, bk: device tables (km + 1)
   double akap, k1k, rrg, ptop, t_min, r_vir;
-  int sphum;             // index of the specific-humidity tracer in qtrs, or -1
   int hydrostatic, last_step, kord_mt, kord_wz, kord_tm, use_tracer, kord_tr;
 };
 
-// steps 0 - 3.3 of fv_mapz.F90 (:188-526) for the cell columns
+// steps 0 - 3.3 of fv_mapz.F90 (:188-526) for the cell columns, in four launches (PART 0: temperature, 1: tracers, 2: w and delz,
+// 3: pressure variables, pkz, omega) -- the columns are independent, so the launch boundaries change nothing, and each part
+// keeps the register allocation of its batched sweeps (remap_col.cuh) to itself: one kernel for everything needed 128 registers
+// and still spilled
+template <int PART>
 __global__ void __launch_bounds__(CB, 8) k_remap_cells(Lay L, L2E a, Scr S) {
   const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;
   const int t = blockIdx.x * CB + threadIdx.x;
@@ -55,6 +57,7 @@ __global__ void __launch_bounds__(CB, 8) k_remap_cells(Lay L, L2E a, Scr S) {
   const double ps = LV(pe, km + 1);
   auto pe1 = [&](int k) { return LV(pe, k); };
   auto pe2 = [&](int k) { return k == 1 ? a.ptop : k == km + 1 ? ps : a.ak[k - 1] + a.bk[k - 1] * ps; };
+  if constexpr (PART == 0) {
   if (a.kord_tm < 0) {   // theta_v -> T_v (:200-230)
     if (a.hydrostatic) for (int k = 1; k <= km; k++) LV(pt, k) = LV(pt, k) * (LV(pk, k + 1) - LV(pk, k)) / (a.akap * (LV(peln, k + 1) - LV(peln, k)));
     else for (int k = 1; k <= km; k++) { const double p = LV(pt, k); LV(pt, k) = p * exp(a.k1k * log(a.rrg * LV(delp, k) / LV(delz, k) * p)); }
@@ -66,12 +69,16 @@ __global__ void __launch_bounds__(CB, 8) k_remap_cells(Lay L, L2E a, Scr S) {
   auto pn2 = [&](int k) { return (k == 1 || k == km + 1) ? LV(peln, k) : log(pe2(k)); };
   if (a.kord_tm < 0) remap_field(C, km, pn1, pn2, pt, 0., 1, a.kord_tm, a.t_min, true);          // :373-386
   else remap_field(C, km, pe1, pe2, pt, 0., 1, a.kord_tm, 0., false);
-  for (int iq = 0; iq < a.use_tracer; iq++) remap_field(C, km, pe1, pe2, a.qtrs[iq] + o, 0., 0, a.kord_tr, 0., true, a.use_tracer > 5);   // :390-408 (map1_q2; mapn_tracer for nq > 5)
+  }
+  if constexpr (PART == 1)   // one launch per tracer (a.qtr): a loop over the tracers around the inlined sweeps made the compiler spill 480 bytes
+    remap_field(C, km, pe1, pe2, a.qtr + o, 0., 0, a.kord_tr, 0., true, a.use_tracer > 5);   // :390-408 (map1_q2; mapn_tracer order for nq > 5)
+  if constexpr (PART == 2)
   if (!a.hydrostatic) {                                                                          // :411-433
     remap_field(C, km, pe1, pe2, a.w + o, a.ws[o], -2, a.kord_wz, 0., false);
     remap_field(C, km, pe1, pe2, delz, 0., 1, a.kord_tm, 0., false);
     for (int k = 1; k <= km; k++) LV(delz, k) = -LV(delz, k) * (pe2(k + 1) - pe2(k));
   }
+  if constexpr (PART == 3) {
   // 3.1 / 3.2: pk, peln, pkz (:436-506); the old peln (pe0) and omega (pe3) of the last step are parked in the a1 / a2 scratch
   if (a.last_step) {
     A2(1) = 0.;
@@ -102,11 +109,12 @@ __global__ void __launch_bounds__(CB, 8) k_remap_cells(Lay L, L2E a, Scr S) {
     }
   }
   for (int k = 2; k <= km; k++) LV(pe4, k) = pe2(k);   // :652-668, stored until every wind column has read the old pe
+  }
 }
 
 // 4.1 / 4.2 (:535-571): u on the south faces (DIR = 0: i in is..ie, j in js..je+1), v on the west faces (DIR = 1)
 template <int DIR>
-__global__ void __launch_bounds__(CB, 12) k_remap_wind(Lay L, L2E a, Scr S) {
+__global__ void __launch_bounds__(CB, 8) k_remap_wind(Lay L, L2E a, Scr S) {
   const int nx = L.ie - L.is + 1 + DIR, ny = L.je - L.js + 1 + (1 - DIR);
   const int t = blockIdx.x * CB + threadIdx.x;
   if (t >= nx * ny) return;
@@ -130,8 +138,8 @@ __global__ void __launch_bounds__(CB) k_remap_finish(Lay L, L2E a, Scr S) {
   const Col C{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, L.plane};
   for (int k = 2; k <= km; k++) LV(a.pe + o, k) = LV(S.pe4 + o, k);
   if (!a.last_step) for (int k = 1; k <= km; k++) LV(a.pt + o, k) = LV(a.pt + o, k) / LV(a.pkz + o, k);
-  else if (a.sphum >= 0) {   // T_v -> T (:792-822 with dtmp = 0, no condensates)
-    const double* qv = a.qtrs[a.sphum] + o;
+  else if (a.qv) {   // T_v -> T (:792-822 with dtmp = 0, no condensates)
+    const double* qv = a.qv + o;
     for (int k = 1; k <= km; k++) LV(a.pt + o, k) = (LV(a.pt + o, k) + 0. * LV(a.pkz + o, k)) / (1. + a.r_vir * LV(qv, k));
   }
 }
@@ -207,17 +215,22 @@ int stage_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kor
   if (use_tracer) {   // the first use_tracer tracers of the context's table (fv3_set_num_tracers; one tracer: FV3_WORK_Q's own array)
     if (c->tracers.empty()) c->tracers.push_back(c->fld[FV3_WORK_Q]);
     if (use_tracer > (int)c->tracers.size()) return fv3_fail(c, -1, "remap: use_tracer exceeds the number of tracers of the context");
-    if (!c->d_qtr_tab) FV3_CUDA(c, cudaMalloc(&c->d_qtr_tab, 64 * sizeof(double*)));
-    FV3_CUDA(c, cudaMemcpyAsync(c->d_qtr_tab, c->tracers.data(), use_tracer * sizeof(double*), cudaMemcpyHostToDevice, c->stream));
-    a.qtrs = c->d_qtr_tab;
   }
   if (sphum >= use_tracer) return fv3_fail(c, -1, "remap: sphum must be one of the remapped tracers (or -1)");
   if (sphum >= 0 && c->f.use_cond) return fv3_fail(c, -2, "remap: specific humidity with use_cond (condensates, moist_cv) not supported");
-  a.sphum = sphum < 0 ? -1 : sphum; a.r_vir = r_vir;
+  a.qv = sphum < 0 ? nullptr : c->tracers[sphum]; a.r_vir = r_vir;
   a.last_step = last_step; a.kord_mt = kord_mt; a.kord_wz = kord_wz; a.kord_tm = kord_tm; a.use_tracer = use_tracer; a.kord_tr = kord_tr;
   const Lay& L = c->L;
   const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;
-  k_remap_cells<<<(nx * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
+  k_remap_cells<0><<<(nx * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
+  for (int iq = 0; iq < use_tracer; iq++) {
+    a.qtr = c->tracers[iq];
+    k_remap_cells<1><<<(nx * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
+    c->launches++;
+  }
+  if (!f.hydrostatic) { k_remap_cells<2><<<(nx * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S); c->launches++; }
+  k_remap_cells<3><<<(nx * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
+  c->launches++;
   k_remap_wind<0><<<(nx * (ny + 1) + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
   k_remap_wind<1><<<((nx + 1) * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
   k_remap_finish<<<(nx * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);

@@ -61,9 +61,16 @@ RMP_HD inline void cs_limiters(double a1, double& a2, double& a3, double& a4, bo
 // interface pressures (k = 1..km+1).  Every level access is an L2 round trip (the columns of a block do not fit L1), so each sweep
 // keeps its loop-carried and neighbouring values in registers and touches a scratch element once; the operations and their
 // order are those of the Fortran.
+// RB levels are handled per batch: every sweep first issues the loads of RB levels (independent of the values the sweep carries from
+// level to level), then does the arithmetic and the stores.  A thread otherwise has one or two loads in flight per level -- the
+// sweeps are chains of L2 / DRAM round trips, bound by occupancy x memory-level parallelism (remap.cu header) -- and the compiler
+// cannot hoist the loads itself (it cannot prove that the strided stores do not alias them).  No load of a batch reads an element
+// an earlier iteration of the same batch stores (checked sweep by sweep below).
+constexpr int RB = 4;
+
 template <class P1>
 RMP_HD inline void profile(const Col& C, int km, const P1& pe1, double qs, int iv, int ak, double qmin, bool scalar) {
-  // ---- interface values: tridiagonal solve (:570-622 / :941-1013)
+  // ---- interface values: tridiagonal solve (:570-622 / :941-1013).  Loads: pe1, A1, then QI / GAM at other levels than stored.
   {
     double plast = pe1(3);
     double dpm, dpk;                       // delp(k - 1), delp(k)
@@ -73,24 +80,40 @@ RMP_HD inline void profile(const Col& C, int km, const P1& pe1, double qs, int i
       double g_cur = 0.5, q_prev = 1.5 * a_prev;
       GAM(2) = g_cur;
       QI(1) = q_prev;
-      for (int k = 2; k <= km - 1; k++) {
-        const double grat = dpm / dpk;
-        const double bet = 2. + grat + grat - g_cur;
-        const double qk = (3. * (a_prev + a_cur) - q_prev) / bet;
-        QI(k) = qk;
-        g_cur = grat / bet;
-        GAM(k + 1) = g_cur;
-        q_prev = qk;
-        dpm = dpk; { const double pn = pe1(k + 2); dpk = pn - plast; plast = pn; }
-        a_prev = a_cur; a_cur = A1(k + 1);
+      for (int k = 2; k <= km - 1;) {
+        const int nb = km - k < RB ? km - k : RB;   // levels k .. k + nb - 1 <= km - 1
+        double pn[RB], an[RB];
+#pragma unroll
+        for (int j = 0; j < RB; j++) if (j < nb) { pn[j] = pe1(k + j + 2); an[j] = A1(k + j + 1); }
+#pragma unroll
+        for (int j = 0; j < RB; j++) if (j < nb) {
+          const double grat = dpm / dpk;
+          const double bet = 2. + grat + grat - g_cur;
+          const double qk = (3. * (a_prev + a_cur) - q_prev) / bet;
+          QI(k + j) = qk;
+          g_cur = grat / bet;
+          GAM(k + j + 1) = g_cur;
+          q_prev = qk;
+          dpm = dpk; dpk = pn[j] - plast; plast = pn[j];
+          a_prev = a_cur; a_cur = an[j];
+        }
+        k += nb;
       }
       const double grat = dpm / dpk;       // delp(km - 1) / delp(km)
       double q_next = (3. * (a_prev + a_cur) - grat * qs - q_prev) / (2. + grat + grat - g_cur);
       QI(km) = q_next;
       QI(km + 1) = qs;
-      for (int k = km - 1; k >= 1; k--) { q_next = QI(k) - GAM(k + 1) * q_next; QI(k) = q_next; }
+      for (int k = km - 1; k >= 1;) {
+        const int nb = k < RB ? k : RB;
+        double qv[RB], gv[RB];
+#pragma unroll
+        for (int j = 0; j < RB; j++) if (j < nb) { qv[j] = QI(k - j); gv[j] = GAM(k - j + 1); }
+#pragma unroll
+        for (int j = 0; j < RB; j++) if (j < nb) { q_next = qv[j] - gv[j] * q_next; QI(k - j) = q_next; }
+        k -= nb;
+      }
     } else {
-      double d4, g_prev, q_prev;
+      double d4 = 0., g_prev, q_prev;
       {
         const double grat = dpk / dpm;     // delp(2) / delp(1)
         const double bet = grat * (grat + 0.5);
@@ -98,24 +121,39 @@ RMP_HD inline void profile(const Col& C, int km, const P1& pe1, double qs, int i
         g_prev = (1. + grat * (grat + 1.5)) / bet;
         QI(1) = q_prev; GAM(1) = g_prev;
       }
-      for (int k = 2;; k++) {
-        d4 = dpm / dpk;
-        const double bet = 2. + d4 + d4 - g_prev;
-        q_prev = (3. * (a_prev + d4 * a_cur) - q_prev) / bet;
-        g_prev = d4 / bet;
-        QI(k) = q_prev; GAM(k) = g_prev;
-        if (k == km) break;
-        dpm = dpk; { const double pn = pe1(k + 2); dpk = pn - plast; plast = pn; }
-        a_prev = a_cur; a_cur = A1(k + 1);
+      for (int k = 2; k <= km;) {
+        const int nb = km - k + 1 < RB ? km - k + 1 : RB;   // levels k .. k + nb - 1 <= km
+        double pn[RB], an[RB];
+#pragma unroll
+        for (int j = 0; j < RB; j++) if (j < nb && k + j < km) { pn[j] = pe1(k + j + 2); an[j] = A1(k + j + 1); }
+#pragma unroll
+        for (int j = 0; j < RB; j++) if (j < nb) {
+          d4 = dpm / dpk;
+          const double bet = 2. + d4 + d4 - g_prev;
+          q_prev = (3. * (a_prev + d4 * a_cur) - q_prev) / bet;
+          g_prev = d4 / bet;
+          QI(k + j) = q_prev; GAM(k + j) = g_prev;
+          if (k + j < km) { dpm = dpk; dpk = pn[j] - plast; plast = pn[j]; a_prev = a_cur; a_cur = an[j]; }
+        }
+        k += nb;
       }
       const double a_bot = 1. + d4 * (d4 + 1.5);
       double q_next = (2. * d4 * (d4 + 1.) * a_cur + a_prev - a_bot * q_prev) / (d4 * (d4 + 0.5) - a_bot * g_prev);
       QI(km + 1) = q_next;
-      for (int k = km; k >= 1; k--) { q_next = QI(k) - GAM(k) * q_next; QI(k) = q_next; }
+      for (int k = km; k >= 1;) {
+        const int nb = k < RB ? k : RB;
+        double qv[RB], gv[RB];
+#pragma unroll
+        for (int j = 0; j < RB; j++) if (j < nb) { qv[j] = QI(k - j); gv[j] = GAM(k - j); }
+#pragma unroll
+        for (int j = 0; j < RB; j++) if (j < nb) { q_next = qv[j] - gv[j] * q_next; QI(k - j) = q_next; }
+        k -= nb;
+      }
     }
   }
   // ---- differences gam(k) = a1(k) - a1(k-1), large-scale constraints on the interface values (:639-682 / :1034-1073) and the
-  //      continuous first-guess edge values a2(k) = q(k), a3(k) = q(k+1): one sweep, q(k-1) is finished when gam(k) is known
+  //      continuous first-guess edge values a2(k) = q(k), a3(k) = q(k+1): one sweep, q(k-1) is finished when gam(k) is known.
+  //      Loads: A1, QI; stores: GAM, A2, A3.
   {
     double am2 = A1(1), am1 = A1(2);       // a1(k - 2), a1(k - 1)
     A2(1) = QI(1);
@@ -127,18 +165,26 @@ RMP_HD inline void profile(const Col& C, int km, const P1& pe1, double qs, int i
     }
     double g_pp = 0., g_prev = am1 - am2;  // gam(k - 2), gam(k - 1)
     GAM(2) = g_prev;
-    for (int k = 3; k <= km; k++) {
-      const double a_k = A1(k), g_k = a_k - am1;
-      GAM(k) = g_k;
-      if (k >= 4) {                        // interface k - 1 (3 .. km - 1): gam(k - 2), gam(k), a1(k - 2), a1(k - 1)
-        const double lo = dmin(am2, am1), hi = dmax(am2, am1);
-        double qk = QI(k - 1);
-        if (ak >= 14 || g_pp * g_k > 0.) { qk = dmin(qk, hi); qk = dmax(qk, lo); }
-        else if (g_pp > 0.) qk = dmax(qk, lo);
-        else { qk = dmin(qk, hi); if (iv == 0) qk = dmax(0., qk); }
-        A2(k - 1) = qk; A3(k - 2) = qk;
+    for (int k = 3; k <= km;) {
+      const int nb = km - k + 1 < RB ? km - k + 1 : RB;
+      double av[RB], qv[RB];
+#pragma unroll
+      for (int j = 0; j < RB; j++) if (j < nb) { av[j] = A1(k + j); qv[j] = k + j >= 4 ? QI(k + j - 1) : 0.; }
+#pragma unroll
+      for (int j = 0; j < RB; j++) if (j < nb) {
+        const double a_k = av[j], g_k = a_k - am1;
+        GAM(k + j) = g_k;
+        if (k + j >= 4) {                  // interface k + j - 1 (3 .. km - 1): gam(k - 2), gam(k), a1(k - 2), a1(k - 1)
+          const double lo = dmin(am2, am1), hi = dmax(am2, am1);
+          double qk = qv[j];
+          if (ak >= 14 || g_pp * g_k > 0.) { qk = dmin(qk, hi); qk = dmax(qk, lo); }
+          else if (g_pp > 0.) qk = dmax(qk, lo);
+          else { qk = dmin(qk, hi); if (iv == 0) qk = dmax(0., qk); }
+          A2(k + j - 1) = qk; A3(k + j - 2) = qk;
+        }
+        g_pp = g_prev; g_prev = g_k; am2 = am1; am1 = a_k;
       }
-      g_pp = g_prev; g_prev = g_k; am2 = am1; am1 = a_k;
+      k += nb;
     }
     {                                      // interface km (am2 = a1(km - 1), am1 = a1(km))
       double qk = QI(km);
@@ -148,25 +194,33 @@ RMP_HD inline void profile(const Col& C, int km, const P1& pe1, double qs, int i
     }
     A3(km) = QI(km + 1);
   }
-  // ---- extremum flags (:695-715 / :1082-1102)
+  // ---- extremum flags (:695-715 / :1082-1102).  Loads: A1, A3, GAM; stores: A4, FL.
   {
     double a2 = A2(1), g_k = 0.;
-    for (int k = 1; k <= km; k++) {
-      const double a1 = A1(k), a3 = A3(k);
-      const double g_k1 = k < km ? GAM(k + 1) : 0.;
-      int f;
-      if (k == 1 || k == km) f = ((a2 - a1) * (a3 - a1) > 0.) ? 1 : 0;
-      else f = (g_k * g_k1 < 0.) ? 1 : 0;
-      if (ak > 9) {
-        const double x0 = 2. * a1 - (a2 + a3), x1 = fabs(a2 - a3);
-        const double a4 = 3. * x0;
-        A4(k) = a4;
-        if (fabs(x0) > x1) f |= 2;
-        if (fabs(a4) > x1) f |= 4;
+    for (int k = 1; k <= km;) {
+      const int nb = km - k + 1 < RB ? km - k + 1 : RB;
+      double av[RB], a3v[RB], gv[RB];
+#pragma unroll
+      for (int j = 0; j < RB; j++) if (j < nb) { av[j] = A1(k + j); a3v[j] = A3(k + j); gv[j] = k + j < km ? GAM(k + j + 1) : 0.; }
+#pragma unroll
+      for (int j = 0; j < RB; j++) if (j < nb) {
+        const int kk = k + j;
+        const double a1 = av[j], a3 = a3v[j], g_k1 = gv[j];
+        int f;
+        if (kk == 1 || kk == km) f = ((a2 - a1) * (a3 - a1) > 0.) ? 1 : 0;
+        else f = (g_k * g_k1 < 0.) ? 1 : 0;
+        if (ak > 9) {
+          const double x0 = 2. * a1 - (a2 + a3), x1 = fabs(a2 - a3);
+          const double a4 = 3. * x0;
+          A4(kk) = a4;
+          if (fabs(x0) > x1) f |= 2;
+          if (fabs(a4) > x1) f |= 4;
+        }
+        FL(kk) = f;
+        a2 = a3;                           // the first-guess profile is continuous: a2(k + 1) = a3(k)
+        g_k = g_k1;
       }
-      FL(k) = f;
-      a2 = a3;                             // the first-guess profile is continuous: a2(k + 1) = a3(k)
-      g_k = g_k1;
+      k += nb;
     }
   }
   // ---- top two layers (:721-754 / :1109-1140)
@@ -188,15 +242,13 @@ RMP_HD inline void profile(const Col& C, int km, const P1& pe1, double qs, int i
     cs_limiters(a1, a2, a3, a4, FL(2) & 1, 2);
     A2(2) = a2; A3(2) = a3; A4(2) = a4;
   }
-  // ---- Huynh's second constraint in the interior (:759-893 / :1142-1276)
+  // ---- Huynh's second constraint in the interior (:759-893 / :1142-1276).  Loads: FL, GAM, A1 .. A4 at the batch's own levels
+  //      (the stores of an iteration go to its own level only).
   if (km >= 5) {
     int fm = FL(2), f0 = FL(3);
     double gm = GAM(2), g0 = GAM(3), g1 = GAM(4);      // gam(k - 1), gam(k), gam(k + 1)
-    for (int k = 3; k <= km - 2; k++) {
-      const int fp = FL(k + 1);
-      const double g2 = GAM(k + 2);
-      const double a1 = A1(k);
-      double a2 = A2(k), a3 = A3(k), a4 = ak >= 14 ? A4(k) : 0.;
+    // one level on registers; called with compile-time batch slots so that the batch arrays below stay in registers
+    auto level = [&](int k, int fp, double g2, double a1, double a2, double a3, double a4) {
       const bool small = scalar && a1 < qmin;
       auto huynh = [&]() {
         const double pmp_1 = a1 - 2. * g1, lac_1 = pmp_1 + 1.5 * g2;
@@ -260,6 +312,22 @@ RMP_HD inline void profile(const Col& C, int km, const P1& pe1, double qs, int i
       if (iv == 0 && ak <= 13) cs_limiters(a1, a2, a3, a4, f0 & 1, 0);
       A2(k) = a2; A3(k) = a3; A4(k) = a4;
       fm = f0; f0 = fp; gm = g0; g0 = g1; g1 = g2;
+    };
+    static_assert(RB == 4, "the batch slots below are written out for RB = 4");
+    for (int kb = 3; kb <= km - 2;) {
+      const int nb = km - 2 - kb + 1 < RB ? km - 2 - kb + 1 : RB;
+      int fpv[RB];
+      double g2v[RB], a1v[RB], a2v[RB], a3v[RB], a4v[RB];
+#pragma unroll
+      for (int j = 0; j < RB; j++) if (j < nb) {
+        fpv[j] = FL(kb + j + 1); g2v[j] = GAM(kb + j + 2); a1v[j] = A1(kb + j); a2v[j] = A2(kb + j); a3v[j] = A3(kb + j);
+        a4v[j] = ak >= 14 ? A4(kb + j) : 0.;
+      }
+      level(kb, fpv[0], g2v[0], a1v[0], a2v[0], a3v[0], a4v[0]);
+      if (nb > 1) level(kb + 1, fpv[1], g2v[1], a1v[1], a2v[1], a3v[1], a4v[1]);
+      if (nb > 2) level(kb + 2, fpv[2], g2v[2], a1v[2], a2v[2], a3v[2], a4v[2]);
+      if (nb > 3) level(kb + 3, fpv[3], g2v[3], a1v[3], a2v[3], a3v[3], a4v[3]);
+      kb += nb;
     }
   }
   // ---- bottom two layers (:898-914 / :1281-1298)
@@ -333,7 +401,15 @@ RMP_HD inline void map_column(const Col& C, int km, const P1& pe1, const P2& pe2
 template <class P1, class P2>
 RMP_HD inline void remap_field(const Col& C, int km, const P1& pe1, const P2& pe2, double* fld, double qs, int iv, int kord, double qmin,
                                bool scalar, bool mapn = false) {
-  for (int k = 1; k <= km; k++) A1(k) = LV(fld, k);
+  for (int k = 1; k <= km;) {   // batched like the sweeps of profile()
+    const int nb = km - k + 1 < RB ? km - k + 1 : RB;
+    double v[RB];
+#pragma unroll
+    for (int j = 0; j < RB; j++) if (j < nb) v[j] = LV(fld, k + j);
+#pragma unroll
+    for (int j = 0; j < RB; j++) if (j < nb) A1(k + j) = v[j];
+    k += nb;
+  }
   profile(C, km, pe1, qs, iv, kord < 0 ? -kord : kord, qmin, scalar);
   map_column(C, km, pe1, pe2, [&](int k, double v) { LV(fld, k) = v; }, mapn);
 }
