@@ -133,3 +133,29 @@ def test_set_eta_l127_levels():
     assert np.allclose(dz[-26:-1] - dz[-25:], dz[-26] - dz[-25], rtol=1e-3)          # k_inc = 25 layers of linearly growing thickness
     a2, b2 = I.model_levels(127)
     assert np.array_equal(a2, ak) and np.array_equal(b2, bk)
+
+
+def test_omega_unit_vectors():
+    """ec1, ec2 (get_center_vect, fv_grid_utils.F90:1738-1779) and en1, en2 (:629-642), the unit vectors of the omega diagnostic
+    adv_pe: unit length, tangent to the sphere at the cell centre / normal to the great circle through the edge's end points,
+    ec1 . ec2 = cos_sg(5) (:355-356), zero in the corner ghost blocks (:1757-1760)."""
+    from gfdl_atmos_cubed_sphere_b200 import grid as G
+    n = 10
+    tiles = G.make_cubed_sphere(n)[0]
+    for t in (0, 3):
+        a = tiles[t].arr
+        e1, e2, n1, n2 = a["ec1"], a["ec2"], a["en1"], a["en2"]
+        assert e1.shape == (n + 6, n + 6, 3) and n1.shape == (n + 1, n, 3) and n2.shape == (n, n + 1, 3)
+        inner = (slice(3, -3), slice(3, -3))
+        for e in (e1, e2):
+            assert np.allclose(np.linalg.norm(e[inner], axis=-1), 1.0, atol=1e-14)
+        assert np.abs(e1[0, 0]).max() == 0.0 and np.abs(e2[-1, -1]).max() == 0.0
+        assert np.allclose((e1 * e2).sum(-1)[inner], a["cos_sg"][4][inner], atol=1e-14)
+        lon, lat = a["agrid"][0][inner], a["agrid"][1][inner]
+        pc = np.stack([np.cos(lat) * np.cos(lon), np.cos(lat) * np.sin(lon), np.sin(lat)], axis=-1)
+        assert np.abs((e1[inner] * pc).sum(-1)).max() < 1e-2 and np.abs((e2[inner] * pc).sum(-1)).max() < 1e-2   # tangent (to grid accuracy)
+        glon, glat = a["grid"][0][3:-3, 3:-3], a["grid"][1][3:-3, 3:-3]                  # corners (1:npx, 1:npy)
+        g3 = np.stack([np.cos(glat) * np.cos(glon), np.cos(glat) * np.sin(glon), np.sin(glat)], axis=-1)
+        assert np.allclose(np.linalg.norm(n1, axis=-1), 1.0, atol=1e-14) and np.allclose(np.linalg.norm(n2, axis=-1), 1.0, atol=1e-14)
+        assert np.abs((n1 * g3[:, :-1]).sum(-1)).max() < 1e-14 and np.abs((n1 * g3[:, 1:]).sum(-1)).max() < 1e-14   # normal to both end points
+        assert np.abs((n2 * g3[:-1, :]).sum(-1)).max() < 1e-14 and np.abs((n2 * g3[1:, :]).sum(-1)).max() < 1e-14
