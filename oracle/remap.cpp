@@ -2,10 +2,10 @@
 //
 // Vertical remapping: restatement of model/fv_mapz.F90:56-845 (Lagrangian_to_Eulerian) and of the column operators it calls in
 // model/fv_operators.F90: map_scalar (:40-134), map1_ppm (:137-229), map1_q2 (:352-443), scalar_profile (:546-916),
-// cs_profile (:919-1300), cs_limiters (:1303-1378).  Scope (everything else is refused with -2 by the C entry point):
+// cs_profile (:919-1300), cs_limiters (:1303-1378), ppm_profile (:1382-1639), ppm_limiters (:1642-1723).  Scope (everything else is refused with -2 by the C entry point):
 //   remap_te = F, moist_kappa = F, use_cond = F, consv = 0 (no energy fixer), no intermediate physics; the last-step conversion
-//   T_v -> T divides by 1 + r_vir q_v when a specific-humidity tracer is named, else it is the identity (`adiabatic`), abs(kord) in 8..15 (the cs / scalar profiles; ppm_profile for kord <= 7
-//   is not restated), kord_wz > 0 (iv = -2; the iv = -3 branch of cs_profile reads an unset
+//   T_v -> T divides by 1 + r_vir q_v when a specific-humidity tracer is named, else it is the identity (`adiabatic`), abs(kord) in 8..15 (the cs / scalar profiles)
+//   or 1..7 (ppm_profile :1382-1639, ppm_limiters :1642-1723), kord_wz > 0 (iv = -2; the iv = -3 branch of cs_profile reads an unset
 //   gam(km), :969-985), tracers with map1_q2 or, for nq > 5, with the operation order of mapn_tracer (iv = 0, no fillz).
 // The Fortran vectorises every loop over i; here one column is processed at a time (same operations on the same operands in the
 // same order for every element).  Parity unpinned: the reference holds no test or golden vector for these routines.
@@ -206,6 +206,119 @@ int profile(double qs, A4& a4, const std::vector<double>& delp, int km, int iv, 
   return 0;
 }
 
+// fv_operators.F90:1642-1723, one element (dm = the limited slope dc(k))
+void ppm_limiters(double dm, A4& a4, int k, int lmt) {
+  if (lmt == 3) return;
+  if (lmt == 0) {          // standard PPM constraint
+    if (dm == 0.) { a4(2, k) = a4(1, k); a4(3, k) = a4(1, k); a4(4, k) = 0.; }
+    else {
+      const double da1 = a4(3, k) - a4(2, k), da2 = da1 * da1, a6da = a4(4, k) * da1;
+      if (a6da < -da2) { a4(4, k) = 3. * (a4(2, k) - a4(1, k)); a4(3, k) = a4(2, k) - a4(4, k); }
+      else if (a6da > da2) { a4(4, k) = 3. * (a4(3, k) - a4(1, k)); a4(2, k) = a4(3, k) - a4(4, k); }
+    }
+  } else if (lmt == 1) {   // improved full monotonicity constraint (no first guess of a4(4) needed)
+    const double qmp = 2. * dm;
+    a4(2, k) = a4(1, k) - fsign(std::min(std::fabs(qmp), std::fabs(a4(2, k) - a4(1, k))), qmp);
+    a4(3, k) = a4(1, k) + fsign(std::min(std::fabs(qmp), std::fabs(a4(3, k) - a4(1, k))), qmp);
+    a4(4, k) = 3. * (2. * a4(1, k) - (a4(2, k) + a4(3, k)));
+  } else if (lmt == 2) {   // positive definite constraint
+    if (std::fabs(a4(3, k) - a4(2, k)) < -a4(4, k)) {
+      const double fmin = a4(1, k) + 0.25 * ((a4(3, k) - a4(2, k)) * (a4(3, k) - a4(2, k))) / a4(4, k) + a4(4, k) * r12;
+      if (fmin < 0.) {
+        if (a4(1, k) < a4(3, k) && a4(1, k) < a4(2, k)) { a4(3, k) = a4(1, k); a4(2, k) = a4(1, k); a4(4, k) = 0.; }
+        else if (a4(3, k) > a4(2, k)) { a4(4, k) = 3. * (a4(2, k) - a4(1, k)); a4(3, k) = a4(2, k) - a4(4, k); }
+        else { a4(4, k) = 3. * (a4(3, k) - a4(1, k)); a4(2, k) = a4(3, k) - a4(4, k); }
+      }
+    }
+  }
+}
+
+// ppm_profile (fv_operators.F90:1382-1639; BOT_MONO not defined; steepz is commented out in the reference) of one column, the
+// piecewise parabolic reconstruction map_scalar / map1_ppm / map1_q2 use for kord <= 7.  kord in 1..7, km >= 5.
+int ppm_profile(A4& a4, const std::vector<double>& delp, int km, int iv, int kord) {
+  if (kord < 1 || kord > 7 || km < 5 || iv == -3) return -2;
+  const int km1 = km - 1;
+  std::vector<double> dc(km + 2, 0.), h2(km + 2, 0.), delq(km + 2, 0.), df2(km + 2, 0.), d4(km + 2, 0.);
+  for (int k = 2; k <= km; k++) { delq[k - 1] = a4(1, k) - a4(1, k - 1); d4[k] = delp[k - 1] + delp[k]; }
+  for (int k = 2; k <= km1; k++) {
+    const double c1 = (delp[k - 1] + 0.5 * delp[k]) / d4[k + 1];
+    const double c2 = (delp[k + 1] + 0.5 * delp[k]) / d4[k];
+    df2[k] = delp[k] * (c1 * delq[k] + c2 * delq[k - 1]) / (d4[k] + delp[k + 1]);
+    dc[k] = fsign(std::min(std::min(std::fabs(df2[k]), max3(a4(1, k - 1), a4(1, k), a4(1, k + 1)) - a4(1, k)),
+                           a4(1, k) - min3(a4(1, k - 1), a4(1, k), a4(1, k + 1))), df2[k]);
+  }
+  // 4th order interpolation of the provisional cell edge value (:1445-1454)
+  for (int k = 3; k <= km1; k++) {
+    const double c1 = delq[k - 1] * delp[k - 1] / d4[k];
+    const double a1 = d4[k - 1] / (d4[k] + delp[k - 1]);
+    const double a2 = d4[k + 1] / (d4[k] + delp[k]);
+    a4(2, k) = a4(1, k - 1) + c1 + 2. / (d4[k - 1] + d4[k + 1]) * (delp[k] * (c1 * (a1 - a2) + a2 * dc[k - 1]) - delp[k - 1] * a1 * dc[k]);
+  }
+  {   // top: area preserving cubic with zero second derivative at the boundary (:1460-1478)
+    const double d1 = delp[1], d2 = delp[2];
+    const double qm = (d2 * a4(1, 1) + d1 * a4(1, 2)) / (d1 + d2);
+    const double dq = 2. * (a4(1, 2) - a4(1, 1)) / (d1 + d2);
+    const double c1 = 4. * (a4(2, 3) - qm - d2 * dq) / (d2 * (2. * d2 * d2 + d1 * (d2 + 3. * d1)));
+    const double c3 = dq - 0.5 * c1 * (d2 * (5. * d1 + d2) - 3. * d1 * d1);
+    a4(2, 2) = qm - 0.25 * c1 * d1 * d2 * (d2 + 3. * d1);
+    a4(2, 1) = d1 * (2. * c1 * (d1 * d1) - c3) + a4(2, 2);
+    a4(2, 2) = std::max(a4(2, 2), std::min(a4(1, 1), a4(1, 2)));
+    a4(2, 2) = std::min(a4(2, 2), std::max(a4(1, 1), a4(1, 2)));
+    dc[1] = 0.5 * (a4(2, 2) - a4(1, 1));
+  }
+  if (iv == 0) { a4(2, 1) = std::max(0., a4(2, 1)); a4(2, 2) = std::max(0., a4(2, 2)); }   // :1482-1496
+  else if (iv == -1) { if (a4(2, 1) * a4(1, 1) <= 0.) a4(2, 1) = 0.; }
+  else if (std::abs(iv) == 2) { a4(2, 1) = a4(1, 1); a4(3, 1) = a4(1, 1); }
+  {   // bottom (:1500-1518)
+    const double d1 = delp[km], d2 = delp[km1];
+    const double qm = (d2 * a4(1, km) + d1 * a4(1, km1)) / (d1 + d2);
+    const double dq = 2. * (a4(1, km1) - a4(1, km)) / (d1 + d2);
+    const double c1 = (a4(2, km1) - qm - d2 * dq) / (d2 * (2. * d2 * d2 + d1 * (d2 + 3. * d1)));
+    const double c3 = dq - 2.0 * c1 * (d2 * (5. * d1 + d2) - 3. * d1 * d1);
+    a4(2, km) = qm - c1 * d1 * d2 * (d2 + 3. * d1);
+    a4(3, km) = d1 * (8. * c1 * (d1 * d1) - c3) + a4(2, km);
+    a4(2, km) = std::max(a4(2, km), std::min(a4(1, km), a4(1, km1)));
+    a4(2, km) = std::min(a4(2, km), std::max(a4(1, km), a4(1, km1)));
+    dc[km] = 0.5 * (a4(1, km) - a4(2, km));
+  }
+  if (iv == 0) { a4(2, km) = std::max(0., a4(2, km)); a4(3, km) = std::max(0., a4(3, km)); }   // :1539-1548
+  else if (iv < 0) { if (a4(1, km) * a4(3, km) <= 0.) a4(3, km) = 0.; }
+  for (int k = 1; k <= km1; k++) a4(3, k) = a4(2, k + 1);
+  // top 2 and bottom 2 layers always use the monotonic mapping
+  for (int k = 1; k <= 2; k++) {
+    a4(4, k) = 3. * (2. * a4(1, k) - (a4(2, k) + a4(3, k)));
+    ppm_limiters(dc[k], a4, k, 0);
+  }
+  if (kord >= 7) {   // Huynh's 2nd constraint (:1568-1614)
+    for (int k = 2; k <= km1; k++)
+      h2[k] = 2. * (dc[k + 1] / delp[k + 1] - dc[k - 1] / delp[k - 1]) / (delp[k] + 0.5 * (delp[k - 1] + delp[k + 1])) * (delp[k] * delp[k]);
+    const double fac = 1.5;
+    for (int k = 3; k <= km - 2; k++) {
+      const double pmp = 2. * dc[k];
+      double qmp = a4(1, k) + pmp;
+      double lac = a4(1, k) + fac * h2[k - 1] + dc[k];
+      a4(3, k) = std::min(std::max(a4(3, k), min3(a4(1, k), qmp, lac)), max3(a4(1, k), qmp, lac));
+      qmp = a4(1, k) - pmp;
+      lac = a4(1, k) + fac * h2[k + 1] - dc[k];
+      a4(2, k) = std::min(std::max(a4(2, k), min3(a4(1, k), qmp, lac)), max3(a4(1, k), qmp, lac));
+      a4(4, k) = 3. * (2. * a4(1, k) - (a4(2, k) + a4(3, k)));
+      if (iv == 0 && kord >= 6) ppm_limiters(dc[k], a4, k, 2);
+    }
+  } else {           // (:1616-1630)
+    int lmt = std::max(0, kord - 3);
+    if (iv == 0) lmt = std::min(2, lmt);
+    for (int k = 3; k <= km - 2; k++) {
+      if (kord != 4) a4(4, k) = 3. * (2. * a4(1, k) - (a4(2, k) + a4(3, k)));
+      if (kord != 6) ppm_limiters(dc[k], a4, k, lmt);
+    }
+  }
+  for (int k = km1; k <= km; k++) {
+    a4(4, k) = 3. * (2. * a4(1, k) - (a4(2, k) + a4(3, k)));
+    ppm_limiters(dc[k], a4, k, 0);
+  }
+  return 0;
+}
+
 // the conservative mapping loop shared by map_scalar / map1_ppm / map1_q2 (fv_operators.F90:88-132, 183-227, 399-441) for one
 // column: pe1(1:km+1) -> pe2(1:kn+1).  dp2 != nullptr: divide by dp2(k) (map1_q2) instead of pe2(k+1) - pe2(k).
 // mapn: the operation order of mapn_tracer (:276-336: the geometric factors fac1, fac2 are formed first), which fv_mapz uses for nq > 5
@@ -263,7 +376,11 @@ int remap_field(int km, const std::vector<double>& pe1, const std::vector<double
   A4 q4(km);
   std::vector<double> dp1(km + 2, 0.);
   for (int k = 1; k <= km; k++) { dp1[k] = pe1[k + 1] - pe1[k]; q4(1, k) = q[k]; }
-  const int rc = profile(qs, q4, dp1, km, iv, kord, qmin, scalar);
+  // kord > 7: scalar_profile / cs_profile, else ppm_profile (:86-90, 181-185, 394-398)
+  // (the callers pass abs(kord); mapn_tracer has no ppm_profile branch, :262-273)
+  const int ak = std::abs(kord);
+  if (mapn && ak <= 7) return -2;
+  const int rc = ak > 7 ? profile(qs, q4, dp1, km, iv, ak, qmin, scalar) : ppm_profile(q4, dp1, km, iv, ak);
   if (rc) return rc;
   map_column(km, pe1, q4, dp1, km, pe2, q, dp2, mapn);
   return 0;

@@ -2,7 +2,7 @@
 operators).  The reference has no test or golden vector for these routines ("parity unpinned"), so the restatement is held to
 the properties the algorithm defines:
   * a remap onto the SAME levels returns the layer means (every new layer lies within one old layer: the parabola integrates
-    to its mean), for every scheme 8..13 and every boundary mode;
+    to its mean), for every scheme 3..15 and every boundary mode;
   * the mapping is conservative: sum_k q dp is unchanged for map1_ppm / map_scalar / map1_q2;
   * a constant stays constant, a positive tracer stays non-negative (iv = 0);
   * Lagrangian_to_Eulerian leaves the surface pressure, the column height and the column integral of w unchanged, puts delp on
@@ -15,7 +15,7 @@ import pytest
 
 import harness as H
 
-KORDS = [8, 9, 10, 11, 12, 13, 14, 15]
+KORDS = [3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15]   # <= 7: ppm_profile (1, 2 = 3: the same limiter), > 7: cs / scalar_profile
 N, NPZ = 12, 16
 
 
@@ -97,7 +97,7 @@ def test_remap_is_conservative_and_keeps_a_constant(kord, mode, iv):
     oc.close()
 
 
-@pytest.mark.parametrize("kord", KORDS)
+@pytest.mark.parametrize("kord", [k for k in KORDS if k != 6])   # (6 is the unlimited parabola of ppm_profile: no positivity promise)
 def test_tracer_remap_keeps_a_positive_field_non_negative(kord):
     case, oc = _cube(substeps=2)
     e = oc.eng[2]
@@ -114,7 +114,7 @@ def test_tracer_remap_keeps_a_positive_field_non_negative(kord):
 def test_unsupported_schemes_are_errors():
     case, oc = _cube(substeps=0)
     e = oc.eng[1]
-    for kord in (4, 7, 16, 17):
+    for kord in (0, 16, 17):
         with pytest.raises(RuntimeError):
             e.call("remap_work_q", 0, 1, kord, 0.0)
     with pytest.raises(RuntimeError):
@@ -122,7 +122,8 @@ def test_unsupported_schemes_are_errors():
     oc.close()
 
 
-@pytest.mark.parametrize("kord_tm,last,hydro", [(-9, 0, 0), (-10, 1, 0), (9, 0, 0), (-9, 0, 1), (-8, 1, 1)])
+@pytest.mark.parametrize("kord_tm,last,hydro", [(-9, 0, 0), (-10, 1, 0), (9, 0, 0), (-9, 0, 1), (-8, 1, 1), (-7, 0, 0), (4, 1, 0),
+                                                  (-6, 1, 1)])
 def test_lagrangian_to_eulerian_invariants(kord_tm, last, hydro):
     case, oc = _cube(substeps=2, hydrostatic=hydro)
     f = case.flags
@@ -134,7 +135,8 @@ def test_lagrangian_to_eulerian_invariants(kord_tm, last, hydro):
         pt0 = _sec(e, "PT")
         om0 = _sec(e, "OMGA")
         u0 = _sec(e, "U", 0, 1)
-        e.call("lagrangian_to_eulerian", last, 9, 9, kord_tm, 0, 9)
+        ko = 9 if abs(kord_tm) > 7 else abs(kord_tm)          # (the ppm_profile cases remap the winds and w with it as well)
+        e.call("lagrangian_to_eulerian", last, ko, ko, kord_tm, 0, 9)
         p2 = _hybrid(case, pe)
         dp1 = _sec(e, "DELP")
         assert np.abs(dp1 - np.diff(p2, axis=0)).max() / dp1.max() < 1e-14          # delp on the hybrid levels
@@ -211,4 +213,23 @@ def test_remap_known_answer_quadratic_profile(mode):
     assert lev[:6].max() < 5e-11, lev
     assert lev.max() < 1e-5, lev
     assert all(lev[k] < 0.6 * lev[k + 1] for k in range(9, 13)), lev          # geometric decay away from the bottom closure
+    oc.close()
+
+
+@pytest.mark.parametrize("kord", [3, 4, 6, 7])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_ppm_profile_known_answer_quadratic_profile(kord, mode):
+    """KNOWN ANSWER for ppm_profile (kord <= 7): its interface values come from an explicit local 4th-order formula, so -- unlike the
+    tridiagonal solve of the cs profiles -- the one-sided closures of the top / bottom layers do not leak into the interior: a
+    profile quadratic and monotone in pressure (no limiter active) is remapped to rounding error away from the three boundary
+    layers on each side."""
+    case, oc = _cube(substeps=2)
+    e = oc.eng[2]
+    q, want = _analytic_case(e, case, (1.0, 2.0e-5, 1.5e-10))
+    _set_q(e, q)
+    e.call("remap_work_q", mode, 1, kord, 0.0)
+    out = _sec(e, "WORK_Q")
+    lev = (np.abs(out - want) / np.abs(want).max()).max(axis=(1, 2))
+    assert lev[3:NPZ - 3].max() < 2e-15, lev
+    assert lev.max() < 1e-5, lev
     oc.close()
