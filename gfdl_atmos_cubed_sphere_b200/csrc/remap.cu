@@ -2,9 +2,10 @@
 //
 // Reference semantics: model/fv_mapz.F90:56-845 (Lagrangian_to_Eulerian) and the column operators of model/fv_operators.F90:
 // map_scalar (:40-134), map1_ppm (:137-229), map1_q2 (:352-443), scalar_profile (:546-916), cs_profile (:919-1300),
-// cs_limiters (:1303-1378).  Built: remap_te = F, moist_kappa = F, consv = 0 (no energy fixer), dry air (the last-step T_v -> T
-// conversion is the identity), abs(kord) in 8..15, kord_wz > 0 (iv = -2), the tracers of the context's table (no fillz); anything
-// else is an error (-2), never a silent fall-back.
+// cs_limiters (:1303-1378), ppm_profile / ppm_limiters (:1382-1723).  Built: remap_te = F, moist_kappa = F, consv = 0 (no energy
+// fixer), dry air or water vapour without condensates, abs(kord) in 8..15 (cs / scalar profiles) and 1..7 (ppm_profile: separate
+// instantiations of the kernels, so the kernels of the default schemes do not carry it), kord_wz > 0 (iv = -2), the tracers of the
+// context's table (no fillz); anything else is an error (-2), never a silent fall-back.
 //
 // Design: column-parallel like the vertical solvers -- one thread per column, consecutive threads on consecutive i, so every
 // level access is a coalesced row segment of the [k][NJ][NI] arrays.  The reconstruction (a4(1:4), the interface values, the
@@ -18,6 +19,7 @@
 #include "fv3_ctx.hpp"
 #include <cmath>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "remap_col.cuh"
@@ -44,7 +46,7 @@ struct L2E {
 // 3: pressure variables, pkz, omega) -- the columns are independent, so the launch boundaries change nothing, and each part
 // keeps the register allocation of its batched sweeps (remap_col.cuh) to itself: one kernel for everything needed 128 registers
 // and still spilled
-template <int PART>
+template <int PART, bool PPM>
 __global__ void __launch_bounds__(CB, 8) k_remap_cells(Lay L, L2E a, Scr S) {
   const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;
   const int t = blockIdx.x * CB + threadIdx.x;
@@ -67,15 +69,15 @@ __global__ void __launch_bounds__(CB, 8) k_remap_cells(Lay L, L2E a, Scr S) {
   // pn2 = log(pe2) is recomputed where it is needed (the temperature map, then the peln / pk update): no column array is kept
   auto pn1 = [&](int k) { return LV(peln, k); };
   auto pn2 = [&](int k) { return (k == 1 || k == km + 1) ? LV(peln, k) : log(pe2(k)); };
-  if (a.kord_tm < 0) remap_field(C, km, pn1, pn2, pt, 0., 1, a.kord_tm, a.t_min, true);          // :373-386
-  else remap_field(C, km, pe1, pe2, pt, 0., 1, a.kord_tm, 0., false);
+  if (a.kord_tm < 0) remap_field<PPM>(C, km, pn1, pn2, pt, 0., 1, a.kord_tm, a.t_min, true);          // :373-386
+  else remap_field<PPM>(C, km, pe1, pe2, pt, 0., 1, a.kord_tm, 0., false);
   }
   if constexpr (PART == 1)   // one launch per tracer (a.qtr): a loop over the tracers around the inlined sweeps made the compiler spill 480 bytes
-    remap_field(C, km, pe1, pe2, a.qtr + o, 0., 0, a.kord_tr, 0., true, a.use_tracer > 5);   // :390-408 (map1_q2; mapn_tracer order for nq > 5)
+    remap_field<PPM>(C, km, pe1, pe2, a.qtr + o, 0., 0, a.kord_tr, 0., true, a.use_tracer > 5);   // :390-408 (map1_q2; mapn_tracer order for nq > 5)
   if constexpr (PART == 2)
   if (!a.hydrostatic) {                                                                          // :411-433
-    remap_field(C, km, pe1, pe2, a.w + o, a.ws[o], -2, a.kord_wz, 0., false);
-    remap_field(C, km, pe1, pe2, delz, 0., 1, a.kord_tm, 0., false);
+    remap_field<PPM>(C, km, pe1, pe2, a.w + o, a.ws[o], -2, a.kord_wz, 0., false);
+    remap_field<PPM>(C, km, pe1, pe2, delz, 0., 1, a.kord_tm, 0., false);
     for (int k = 1; k <= km; k++) LV(delz, k) = -LV(delz, k) * (pe2(k + 1) - pe2(k));
   }
   if constexpr (PART == 3) {
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(CB, 8) k_remap_cells(Lay L, L2E a, Scr S) {
 }
 
 // 4.1 / 4.2 (:535-571): u on the south faces (DIR = 0: i in is..ie, j in js..je+1), v on the west faces (DIR = 1)
-template <int DIR>
+template <int DIR, bool PPM>
 __global__ void __launch_bounds__(CB, 8) k_remap_wind(Lay L, L2E a, Scr S) {
   const int nx = L.ie - L.is + 1 + DIR, ny = L.je - L.js + 1 + (1 - DIR);
   const int t = blockIdx.x * CB + threadIdx.x;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(CB, 8) k_remap_wind(Lay L, L2E a, Scr S) {
   const double ps2 = LV(pb, km + 1) + LV(pa, km + 1);
   auto pe0 = [&](int k) { return k == 1 ? LV(pa, 1) : 0.5 * (LV(pb, k) + LV(pa, k)); };
   auto pe3 = [&](int k) { return (DIR == 1 && k == 1) ? a.ak[0] : a.ak[k - 1] + 0.5 * a.bk[k - 1] * ps2; };
-  remap_field(C, km, pe0, pe3, (DIR == 0 ? a.u : a.v) + o, 0., -1, a.kord_mt, 0., false);
+  remap_field<PPM>(C, km, pe0, pe3, (DIR == 0 ? a.u : a.v) + o, 0., -1, a.kord_mt, 0., false);
 }
 
 // the new interface pressures (:661-668) and, between k_split steps, T_v back to theta_v (:833-843)
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(CB) k_remap_finish(Lay L, L2E a, Scr S) {
 }
 
 // stand-alone column operator on FV3_WORK_Q (parity of the profiles for every scheme / iv): pe1 = FV3_PE, pe2 = the hybrid levels
+template <bool PPM>
 __global__ void __launch_bounds__(CB) k_remap_work_q(Lay L, L2E a, Scr S, int mode, int iv, int kord, double qmin) {
   const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;
   const int t = blockIdx.x * CB + threadIdx.x;
@@ -156,12 +159,14 @@ __global__ void __launch_bounds__(CB) k_remap_work_q(Lay L, L2E a, Scr S, int mo
   const double ps = LV(pe, km + 1);
   auto pe1 = [&](int k) { return LV(pe, k); };
   auto pe2 = [&](int k) { return k == 1 ? a.ptop : k == km + 1 ? ps : a.ak[k - 1] + a.bk[k - 1] * ps; };
-  remap_field(C, km, pe1, pe2, a.qtr + o, iv == -2 ? a.ws[o] : 0., iv, kord, qmin, mode != 1);
+  remap_field<PPM>(C, km, pe1, pe2, a.qtr + o, iv == -2 ? a.ws[o] : 0., iv, kord, qmin, mode != 1);
 }
 
-int check_kord(fv3_ctx* c, int kord, const char* what) {
+// abs(kord) in 8..15: cs_profile / scalar_profile; 1..7: ppm_profile (the PPM instantiations of the kernels)
+int check_kord(fv3_ctx* c, int kord, const char* what, bool* ppm) {
   const int ak = kord < 0 ? -kord : kord;
-  if (ak < 8 || ak > 15) return fv3_fail(c, -2, std::string("remap: ") + what + " outside 8..15 (ppm_profile, kord <= 7, is not built)");
+  if (ak < 1 || ak > 15) return fv3_fail(c, -2, std::string("remap: ") + what + " outside 1..15");
+  if (ak <= 7) *ppm = true;
   return 0;
 }
 
@@ -189,11 +194,14 @@ int fill(fv3_ctx* c, L2E& a, Scr& S) {
 int stage_remap_work_q(fv3_ctx* c, int mode, int iv, int kord, double qmin) {
   StageScope ts(c, "REMAP_OP");
   if (mode < 0 || mode > 2 || iv < -2 || iv > 2) return fv3_fail(c, -1, "remap_work_q: mode in 0..2, iv in -2..2");
-  int rc = check_kord(c, kord, "kord"); if (rc) return rc;
+  bool ppm = false;
+  int rc = check_kord(c, kord, "kord", &ppm); if (rc) return rc;
+  if (ppm && c->L.npz < 5) return fv3_fail(c, -2, "remap: ppm_profile (kord <= 7) needs npz >= 5");
   L2E a{}; Scr S{};
   rc = fill(c, a, S); if (rc) return rc;
   const int n = (c->L.ie - c->L.is + 1) * (c->L.je - c->L.js + 1);
-  k_remap_work_q<<<(n + CB - 1) / CB, CB, 0, c->stream>>>(c->L, a, S, mode, iv, kord, qmin);
+  if (ppm) k_remap_work_q<true><<<(n + CB - 1) / CB, CB, 0, c->stream>>>(c->L, a, S, mode, iv, kord, qmin);
+  else k_remap_work_q<false><<<(n + CB - 1) / CB, CB, 0, c->stream>>>(c->L, a, S, mode, iv, kord, qmin);
   c->launches++;
   FV3_CUDA(c, cudaGetLastError());
   return 0;
@@ -205,11 +213,17 @@ int stage_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kor
   if (f.moist_kappa) return fv3_fail(c, -2, "remap: moist_kappa not supported");
   if (kord_wz < 0) return fv3_fail(c, -2, "remap: kord_wz < 0 (iv = -3 lower boundary condition) not supported");
   if (kord_mt < 0) return fv3_fail(c, -2, "remap: kord_mt must be positive");
-  int rc = check_kord(c, kord_mt, "kord_mt"); if (rc) return rc;
-  rc = check_kord(c, kord_tm, "kord_tm"); if (rc) return rc;
-  if (!f.hydrostatic) { rc = check_kord(c, kord_wz, "kord_wz"); if (rc) return rc; }
+  bool ppm = false;   // any field with abs(kord) <= 7: the launches below use the instantiations that hold ppm_profile
+  int rc = check_kord(c, kord_mt, "kord_mt", &ppm); if (rc) return rc;
+  rc = check_kord(c, kord_tm, "kord_tm", &ppm); if (rc) return rc;
+  if (!f.hydrostatic) { rc = check_kord(c, kord_wz, "kord_wz", &ppm); if (rc) return rc; }
   if (use_tracer < 0 || use_tracer > 64) return fv3_fail(c, -1, "remap: use_tracer (the number of tracers to remap) in 0..64");
-  if (use_tracer) { rc = check_kord(c, kord_tr, "kord_tr"); if (rc) return rc; if (kord_tr < 0) return fv3_fail(c, -2, "remap: kord_tr must be positive"); }
+  if (use_tracer) {
+    rc = check_kord(c, kord_tr, "kord_tr", &ppm); if (rc) return rc;
+    if (kord_tr < 0) return fv3_fail(c, -2, "remap: kord_tr must be positive");
+    if (kord_tr <= 7 && use_tracer > 5) return fv3_fail(c, -2, "remap: kord_tr <= 7 with more than 5 tracers (mapn_tracer has no ppm_profile branch)");
+  }
+  if (ppm && c->L.npz < 5) return fv3_fail(c, -2, "remap: ppm_profile (kord <= 7) needs npz >= 5");
   L2E a{}; Scr S{};
   rc = fill(c, a, S); if (rc) return rc;
   if (use_tracer) {   // the first use_tracer tracers of the context's table (fv3_set_num_tracers; one tracer: FV3_WORK_Q's own array)
@@ -222,17 +236,22 @@ int stage_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kor
   a.last_step = last_step; a.kord_mt = kord_mt; a.kord_wz = kord_wz; a.kord_tm = kord_tm; a.use_tracer = use_tracer; a.kord_tr = kord_tr;
   const Lay& L = c->L;
   const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;
-  k_remap_cells<0><<<(nx * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
-  for (int iq = 0; iq < use_tracer; iq++) {
-    a.qtr = c->tracers[iq];
-    k_remap_cells<1><<<(nx * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
+  const int gc = (nx * ny + CB - 1) / CB;
+  auto launch = [&](auto P) {   // P: std::bool_constant, the PPM instantiation or not
+    constexpr bool PPM = decltype(P)::value;
+    k_remap_cells<0, PPM><<<gc, CB, 0, c->stream>>>(L, a, S);
+    for (int iq = 0; iq < use_tracer; iq++) {
+      a.qtr = c->tracers[iq];
+      k_remap_cells<1, PPM><<<gc, CB, 0, c->stream>>>(L, a, S);
+      c->launches++;
+    }
+    if (!f.hydrostatic) { k_remap_cells<2, PPM><<<gc, CB, 0, c->stream>>>(L, a, S); c->launches++; }
+    k_remap_cells<3, false><<<gc, CB, 0, c->stream>>>(L, a, S);   // (pressure variables only: no profile)
     c->launches++;
-  }
-  if (!f.hydrostatic) { k_remap_cells<2><<<(nx * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S); c->launches++; }
-  k_remap_cells<3><<<(nx * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
-  c->launches++;
-  k_remap_wind<0><<<(nx * (ny + 1) + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
-  k_remap_wind<1><<<((nx + 1) * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
+    k_remap_wind<0, PPM><<<(nx * (ny + 1) + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
+    k_remap_wind<1, PPM><<<((nx + 1) * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
+  };
+  if (ppm) launch(std::true_type{}); else launch(std::false_type{});
   k_remap_finish<<<(nx * ny + CB - 1) / CB, CB, 0, c->stream>>>(L, a, S);
   c->launches += 4;
   FV3_CUDA(c, cudaGetLastError());

@@ -1,4 +1,5 @@
-// Column operators of the vertical remap (fv_operators.F90: scalar_profile / cs_profile :546-1300, cs_limiters :1303-1378, the
+// Column operators of the vertical remap (fv_operators.F90: scalar_profile / cs_profile :546-1300, cs_limiters :1303-1378,
+// ppm_profile / ppm_limiters :1382-1723, the
 // mapping loop of map_scalar / map1_ppm / map1_q2 / mapn_tracer :88-132, 183-227, 276-336, 399-441) for ONE column whose
 // reconstruction arrays are strided (level stride = plane).  __host__ __device__: remap.cu runs them one thread per column; the
 // CPU suite runs the same source on the host against the oracle (tests/host_remap_test.cu, tests/test_host_remap.py).
@@ -344,6 +345,152 @@ RMP_HD inline void profile(const Col& C, int km, const P1& pe1, double qs, int i
   }
 }
 
+// ---- ppm_profile (fv_operators.F90:1382-1639) and ppm_limiters (:1642-1723): the piecewise parabolic reconstruction of the
+// schemes kord <= 7.  Scratch use: A1 layer means, A2 / A3 / A4 the parabola, GAM the limited slopes dc, QI Huynh's h2.  The layer
+// thicknesses are differences of the source interface pressures, as the callers form dp1 (:80-84).
+RMP_HD inline double dsign(double a, double b) { return copysign(fabs(a), b); }   // Fortran sign(a, b)
+
+RMP_HD inline void ppm_limiters(double dm, double a1, double& a2, double& a3, double& a4, int lmt) {
+  if (lmt == 0) {          // standard PPM constraint
+    if (dm == 0.) { a2 = a1; a3 = a1; a4 = 0.; }
+    else {
+      const double da1 = a3 - a2, da2 = da1 * da1, a6da = a4 * da1;
+      if (a6da < -da2) { a4 = 3. * (a2 - a1); a3 = a2 - a4; }
+      else if (a6da > da2) { a4 = 3. * (a3 - a1); a2 = a3 - a4; }
+    }
+  } else if (lmt == 1) {   // improved full monotonicity constraint
+    const double qmp = 2. * dm;
+    const double n2 = a1 - dsign(dmin(fabs(qmp), fabs(a2 - a1)), qmp);
+    const double n3 = a1 + dsign(dmin(fabs(qmp), fabs(a3 - a1)), qmp);
+    a2 = n2; a3 = n3;
+    a4 = 3. * (2. * a1 - (a2 + a3));
+  } else if (lmt == 2) {   // positive definite constraint
+    if (fabs(a3 - a2) < -a4) {
+      const double fmin = a1 + 0.25 * ((a3 - a2) * (a3 - a2)) / a4 + a4 * r12;
+      if (fmin < 0.) {
+        if (a1 < a3 && a1 < a2) { a3 = a1; a2 = a1; a4 = 0.; }
+        else if (a3 > a2) { a4 = 3. * (a2 - a1); a3 = a2 - a4; }
+        else { a4 = 3. * (a3 - a1); a2 = a3 - a4; }
+      }
+    }
+  }                        // lmt == 3: nothing
+}
+
+template <class P1>
+RMP_HD inline void ppm_profile(const Col& C, int km, const P1& pe1, int iv, int kord) {
+  const int km1 = km - 1;
+  // ---- limited slopes dc(2 .. km-1) (:1429-1439) and the 4th-order provisional edge values a2(3 .. km-1) (:1445-1454): one sweep,
+  //      thicknesses and means of the neighbouring layers carried in registers
+  {
+    double plast = pe1(4);
+    double dm2 = 0., dm1, d0, dp1;         // delp(k - 2), delp(k - 1), delp(k), delp(k + 1)
+    { const double p1 = pe1(1), p2 = pe1(2), p3 = pe1(3); dm1 = p2 - p1; d0 = p3 - p2; dp1 = plast - p3; }
+    double am1 = A1(1), a0 = A1(2), ap1 = A1(3);
+    double dcm = 0.;                       // dc(k - 1)
+    for (int k = 2; k <= km1; k++) {
+      const double delq_k = ap1 - a0, delq_m = a0 - am1;
+      const double d4_k = dm1 + d0, d4_p = d0 + dp1;
+      const double c1 = (dm1 + 0.5 * d0) / d4_p;
+      const double c2 = (dp1 + 0.5 * d0) / d4_k;
+      const double df2 = d0 * (c1 * delq_k + c2 * delq_m) / (d4_k + dp1);
+      const double dc = dsign(dmin(dmin(fabs(df2), dmax3(am1, a0, ap1) - a0), a0 - dmin3(am1, a0, ap1)), df2);
+      GAM(k) = dc;
+      if (k >= 3) {
+        const double d4_m = dm2 + dm1;
+        const double e1 = delq_m * dm1 / d4_k;
+        const double b1 = d4_m / (d4_k + dm1);
+        const double b2 = d4_p / (d4_k + d0);
+        A2(k) = am1 + e1 + 2. / (d4_m + d4_p) * (d0 * (e1 * (b1 - b2) + b2 * dcm) - dm1 * b1 * dc);
+      }
+      if (k < km1) {
+        const double pn = pe1(k + 3);
+        dm2 = dm1; dm1 = d0; d0 = dp1; dp1 = pn - plast; plast = pn;
+        am1 = a0; a0 = ap1; ap1 = A1(k + 2);
+        dcm = dc;
+      }
+    }
+  }
+  // ---- top: area preserving cubic with zero second derivative at the boundary (:1460-1496)
+  {
+    const double p1 = pe1(1), p2 = pe1(2), p3 = pe1(3);
+    const double d1 = p2 - p1, d2 = p3 - p2;
+    const double a11 = A1(1), a12 = A1(2);
+    const double qm = (d2 * a11 + d1 * a12) / (d1 + d2);
+    const double dq = 2. * (a12 - a11) / (d1 + d2);
+    const double c1 = 4. * (A2(3) - qm - d2 * dq) / (d2 * (2. * d2 * d2 + d1 * (d2 + 3. * d1)));
+    const double c3 = dq - 0.5 * c1 * (d2 * (5. * d1 + d2) - 3. * d1 * d1);
+    double a22 = qm - 0.25 * c1 * d1 * d2 * (d2 + 3. * d1);
+    double a21 = d1 * (2. * c1 * (d1 * d1) - c3) + a22;
+    a22 = dmax(a22, dmin(a11, a12));
+    a22 = dmin(a22, dmax(a11, a12));
+    GAM(1) = 0.5 * (a22 - a11);
+    if (iv == 0) { a21 = dmax(0., a21); a22 = dmax(0., a22); }
+    else if (iv == -1) { if (a21 * a11 <= 0.) a21 = 0.; }
+    else if (iv == 2 || iv == -2) a21 = a11;   // (a3(1) = a1(1) of :1494 is overwritten by a3(1) = a2(2) below)
+    A2(1) = a21; A2(2) = a22;
+  }
+  // ---- bottom (:1500-1548)
+  {
+    const double p1 = pe1(km1), p2 = pe1(km), p3 = pe1(km + 1);
+    const double d1 = p3 - p2, d2 = p2 - p1;
+    const double a1m = A1(km), a1n = A1(km1);
+    const double qm = (d2 * a1m + d1 * a1n) / (d1 + d2);
+    const double dq = 2. * (a1n - a1m) / (d1 + d2);
+    const double c1 = (A2(km1) - qm - d2 * dq) / (d2 * (2. * d2 * d2 + d1 * (d2 + 3. * d1)));
+    const double c3 = dq - 2.0 * c1 * (d2 * (5. * d1 + d2) - 3. * d1 * d1);
+    double a2m = qm - c1 * d1 * d2 * (d2 + 3. * d1);
+    double a3m = d1 * (8. * c1 * (d1 * d1) - c3) + a2m;
+    a2m = dmax(a2m, dmin(a1m, a1n));
+    a2m = dmin(a2m, dmax(a1m, a1n));
+    GAM(km) = 0.5 * (a1m - a2m);
+    if (iv == 0) { a2m = dmax(0., a2m); a3m = dmax(0., a3m); }
+    else if (iv < 0) { if (a1m * a3m <= 0.) a3m = 0.; }
+    A2(km) = a2m; A3(km) = a3m;
+  }
+  // ---- Huynh's h2(2 .. km-1) (:1572-1583), only for kord >= 7
+  if (kord >= 7) {
+    double plast = pe1(3);
+    double dm1, d0;
+    { const double p1 = pe1(1), p2 = pe1(2); dm1 = p2 - p1; d0 = plast - p2; }
+    double dcm = GAM(1), dc0 = GAM(2);
+    for (int k = 2; k <= km1; k++) {
+      const double pn = pe1(k + 2);
+      const double dp1 = pn - plast, dcp = GAM(k + 1);
+      QI(k) = 2. * (dcp / dp1 - dcm / dm1) / (d0 + 0.5 * (dm1 + dp1)) * (d0 * d0);
+      dm1 = d0; d0 = dp1; plast = pn; dcm = dc0; dc0 = dcp;
+    }
+  }
+  // ---- the parabolas, top to bottom (:1551-1637).  a3(k) = a2(k + 1) (:1551-1555) is read from the first-guess a2 of the next
+  //      layer, which no earlier layer has modified; the top two and bottom two layers always use the standard constraint
+  int lmt = kord - 3;
+  lmt = lmt > 0 ? lmt : 0;
+  if (iv == 0) lmt = lmt < 2 ? lmt : 2;
+  double a2n = A2(1);                      // first-guess a2 of the layer at hand
+  for (int k = 1; k <= km; k++) {
+    const double a1 = A1(k), dc = GAM(k);
+    double a2 = a2n, a3, a4 = 0.;
+    if (k < km) { a2n = A2(k + 1); a3 = a2n; } else a3 = A3(km);
+    if (k <= 2 || k >= km1) {
+      a4 = 3. * (2. * a1 - (a2 + a3));
+      ppm_limiters(dc, a1, a2, a3, a4, 0);
+    } else if (kord >= 7) {
+      const double pmp = 2. * dc;
+      double qmp = a1 + pmp;
+      double lac = a1 + 1.5 * QI(k - 1) + dc;
+      a3 = dmin(dmax(a3, dmin3(a1, qmp, lac)), dmax3(a1, qmp, lac));
+      qmp = a1 - pmp;
+      lac = a1 + 1.5 * QI(k + 1) - dc;
+      a2 = dmin(dmax(a2, dmin3(a1, qmp, lac)), dmax3(a1, qmp, lac));
+      a4 = 3. * (2. * a1 - (a2 + a3));
+      if (iv == 0) ppm_limiters(dc, a1, a2, a3, a4, 2);
+    } else {
+      if (kord != 4) a4 = 3. * (2. * a1 - (a2 + a3));
+      if (kord != 6) ppm_limiters(dc, a1, a2, a3, a4, lmt);
+    }
+    A2(k) = a2; A3(k) = a3; A4(k) = a4;
+  }
+}
+
 // the conservative mapping loop (fv_operators.F90:88-132 = 183-227 = 399-441): P1 source, P2 target interface pressures;
 // out(k, value) stores layer k.  div_dp2: map1_q2 divides by the tabulated target thickness -- the same difference here.
 // mapn: the operation order of mapn_tracer (:276-336), which fv_mapz uses for nq > 5 tracers
@@ -397,8 +544,9 @@ RMP_HD inline void map_column(const Col& C, int km, const P1& pe1, const P2& pe2
 }
 
 // map_scalar / map1_ppm / map1_q2 (mapn: in the operation order of mapn_tracer) of one column, in place on fld (level k at
-// fld[(k-1)*plane]); scalar: scalar_profile (with the q_min tests), else cs_profile
-template <class P1, class P2>
+// fld[(k-1)*plane]); scalar: scalar_profile (with the q_min tests), else cs_profile.  PPM: the instantiation that also holds
+// ppm_profile for abs(kord) <= 7 (:86-90, 181-185, 394-398); the kernels of the schemes 8..15 are compiled without it
+template <bool PPM, class P1, class P2>
 RMP_HD inline void remap_field(const Col& C, int km, const P1& pe1, const P2& pe2, double* fld, double qs, int iv, int kord, double qmin,
                                bool scalar, bool mapn = false) {
   for (int k = 1; k <= km;) {   // batched like the sweeps of profile()
@@ -410,6 +558,11 @@ RMP_HD inline void remap_field(const Col& C, int km, const P1& pe1, const P2& pe
     for (int j = 0; j < RB; j++) if (j < nb) A1(k + j) = v[j];
     k += nb;
   }
+  if constexpr (PPM) {
+    const int ak = kord < 0 ? -kord : kord;
+    if (ak <= 7) ppm_profile(C, km, pe1, iv, ak);
+    else profile(C, km, pe1, qs, iv, ak, qmin, scalar);
+  } else
   profile(C, km, pe1, qs, iv, kord < 0 ? -kord : kord, qmin, scalar);
   map_column(C, km, pe1, pe2, [&](int k, double v) { LV(fld, k) = v; }, mapn);
 }

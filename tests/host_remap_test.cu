@@ -22,7 +22,7 @@ int main() {
     const double *p1 = pe1.data() + c, *p2 = pe2.data() + c;
     auto P1 = [&](int k) { return p1[(size_t)(k - 1) * ncol]; };
     auto P2 = [&](int k) { return p2[(size_t)(k - 1) * ncol]; };
-    rmp::remap_field(C, km, P1, P2, q.data() + c, qs[c], iv, kord, qmin, scalar != 0, mapn != 0);
+    rmp::remap_field<true>(C, km, P1, P2, q.data() + c, qs[c], iv, kord, qmin, scalar != 0, mapn != 0);
   }
   fwrite(q.data(), sizeof(double), q.size(), stdout);
   return 0;

@@ -1,5 +1,5 @@
 """CPU: the vertical-remap column operators the CUDA kernels execute (csrc/remap_col.cuh, compiled __host__ __device__) run on the
-HOST and compared with the oracle (oracle/remap.cpp) for every scheme 8..15 and every boundary mode -- BIT FOR BIT: remap.cu is
+HOST and compared with the oracle (oracle/remap.cpp) for every scheme 3..15 (ppm_profile for <= 7, the cs / scalar profiles above) and every boundary mode -- BIT FOR BIT: remap.cu is
 built without FMA contraction precisely so that its decisions at the tie-prone switches of schemes 11 / 12 are the oracle's
 (tests/test_remap_gpu.py), and the host build has no FMA either.  GPU time is scarce; this keeps the kernels' column arithmetic
 pinned on every CPU run and lets the sweeps be restructured (register carries, batching) without a device."""

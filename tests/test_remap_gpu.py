@@ -88,7 +88,7 @@ def test_unsupported_remap_options_are_errors():
     case = H.Case(12, 8, "A", state="baroclinic")
     gc = H.CudaCube(case)
     e = gc.eng[1]
-    for args in [(0, 7, 9, -9, 0, 9), (0, 9, -9, -9, 0, 9), (0, 9, 9, -16, 0, 9), (0, 9, 9, -9, 1, 16)]:
+    for args in [(0, 0, 9, -9, 0, 9), (0, 9, -9, -9, 0, 9), (0, 9, 9, -16, 0, 9), (0, 9, 9, -9, 1, 16)]:
         with pytest.raises(RuntimeError, match="remap"):
             e.call("lagrangian_to_eulerian", *args)
     gc.close()
