@@ -1,21 +1,20 @@
 """-m gpu: the vertical remap with ppm_profile (abs(kord) <= 7, fv_operators.F90:1382-1723) against the oracle through the C ABI.
 
-FIRST DEVICE RUN PENDING.  The PPM instantiations of the remap kernels (csrc/remap.cu: k_remap_cells<., true>, k_remap_wind<., true>,
-k_remap_work_q<true>) were written after this round's GPU budget was spent.  What pins them without a device:
+The PPM instantiations of the remap kernels (csrc/remap.cu: k_remap_cells<., true>, k_remap_wind<., true>, k_remap_work_q<true>) were
+written late in round 2, pinned without a device first --
   * their column code (csrc/remap_col.cuh: ppm_profile / ppm_limiters, __host__ __device__) runs on the host and equals the oracle
-    BIT FOR BIT for every scheme 3..7 in every mode (tests/test_host_remap.py) -- the method that predicted the device results of
-    the schemes 8..15 exactly (remap.cu is built without FMA contraction);
+    BIT FOR BIT for every scheme 3..7 in every mode (tests/test_host_remap.py);
   * the oracle side is held to an oracle-independent known answer (tests/test_remap_oracle.py: a quadratic profile is remapped to
     rounding error in the interior);
-  * the instruction streams of the kernels of the schemes 8..15 are unchanged (the PPM code lives in separate instantiations).
-The tests below therefore carry the same xfail(strict=False) guard the round-1 pending tests carried for their first B200 run
-(tests/test_zz_pending_gpu.py): a pass is reported as XPASS, a failure cannot stop the `-x` run of the validated suite."""
+  * the instruction streams of the kernels of the schemes 8..15 are unchanged (the PPM code lives in separate instantiations)
+-- and then run on a B200 with the last seconds of the round's GPU budget: 9 passed (profiles/r2/r2g_ppm_remap_pytest.txt), so
+they are plain tests (no xfail guard)."""
 import pytest
 
 import harness as H
 from test_remap_gpu import TOL, _assert, _pair, _regions
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first B200 run of the ppm_profile instantiations pending")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("kord", [3, 4, 5, 6, 7])
