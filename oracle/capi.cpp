@@ -28,6 +28,7 @@ struct fv3o_ctx {
   // external-mode damping term divg2(is:ie+1, js:je+1) of the current substep (dyn_core.F90:828-847; empty: d_ext = 0)
   // tracers: store[i] holds tracer i except for i == tracer_sel, which lives in fld[FV3_WORK_Q] (fv3o_select_tracer swaps)
   std::vector<std::vector<double>> store; int tracer_sel = 0;
+  int tracer_fill = 0;   // flagstruct%fill: fillz after each remapped tracer (fv3o_set_tracer_fill)
   std::vector<double> pem;   // interface pressures before the last substep (omega diagnostic, dyn_core.F90:409-422)
   std::vector<double> divg2, ext_dpc;   // ext_dpc: delp at the cell corners (is:ie+1, js:je+1, npz), taken before d_sw (:745-747)
   explicit fv3o_ctx(const fv3_bounds_t& b_, const fv3_grid_t& g_, const fv3_flags_t& f_) : b(b_), g(g_), f(f_) {}
@@ -478,8 +479,11 @@ int fv3o_lagrangian_to_eulerian_qv(fv3o_ctx* c, int last_step, int kord_mt, int 
     std::vector<double>& buf = (iq == c->tracer_sel || c->store.empty()) ? c->fld[FV3_WORK_Q] : c->store[iq];
     F.qtr.push_back(V3(buf.data(), d.ilo, d.ilo + d.ni - 1, d.jlo, d.jlo + d.nj - 1));
   }
-  return lagrangian_to_eulerian(F, c->ak, c->bk, c->f, bd, last_step, kord_mt, kord_wz, kord_tm, use_tracer, kord_tr, sphum, r_vir);
+  return lagrangian_to_eulerian(F, c->ak, c->bk, c->f, bd, last_step, kord_mt, kord_wz, kord_tm, use_tracer, kord_tr, sphum, r_vir, c->tracer_fill);
 }
+// flagstruct%fill; fillz (fv_fill.F90:34) of FV3_WORK_Q with the thicknesses FV3_DELP on the compute domain
+int fv3o_set_tracer_fill(fv3o_ctx* c, int on) { c->tracer_fill = on != 0; return 0; }
+int fv3o_fillz(fv3o_ctx* c) { Bd bd(c->b); fillz(F3(c, FV3_WORK_Q), F3(c, FV3_DELP), bd); return 0; }
 int fv3o_pt_to_theta(fv3o_ctx* c, double zvir) {
   if (c->f.moist_kappa) return -2;
   Bd bd(c->b);

@@ -284,6 +284,7 @@ struct L2EFields { V3 pt, delp, delz, w, u, v, pk, pkz, omga; std::vector<V3> qt
 int remap_work_q(V3 q, V2 ws, double* pe, const std::vector<double>& ak, const std::vector<double>& bk, const fv3_flags_t& f, const Bd& bd,
                  int mode, int iv, int kord, double qmin);
 int lagrangian_to_eulerian(const L2EFields& F, const std::vector<double>& ak, const std::vector<double>& bk, const fv3_flags_t& f, const Bd& bd,
-                           int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr, int sphum = -1, double r_vir = 0.);
+                           int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr, int sphum = -1, double r_vir = 0., int fill = 0);
+void fillz(V3 q, V3 dp, const Bd& bd);
 
 }  // namespace fv3o

@@ -6,7 +6,8 @@
 //   remap_te = F, moist_kappa = F, use_cond = F, consv = 0 (no energy fixer), no intermediate physics; the last-step conversion
 //   T_v -> T divides by 1 + r_vir q_v when a specific-humidity tracer is named, else it is the identity (`adiabatic`), abs(kord) in 8..15 (the cs / scalar profiles)
 //   or 1..7 (ppm_profile :1382-1639, ppm_limiters :1642-1723), kord_wz > 0 (iv = -2; the iv = -3 branch of cs_profile reads an unset
-//   gam(km), :969-985), tracers with map1_q2 or, for nq > 5, with the operation order of mapn_tracer (iv = 0, no fillz).
+//   gam(km), :969-985), tracers with map1_q2 or, for nq > 5, with the operation order of mapn_tracer (iv = 0).
+// flagstruct%fill: fillz (fv_fill.F90:34-139, default branch) after each tracer.
 // The Fortran vectorises every loop over i; here one column is processed at a time (same operations on the same operands in the
 // same order for every element).  Parity unpinned: the reference holds no test or golden vector for these routines.
 #include "fv3_oracle.hpp"
@@ -388,6 +389,47 @@ int remap_field(int km, const std::vector<double>& pe1, const std::vector<double
 
 }  // namespace
 
+// fillz (fv_fill.F90:34-139; the default branch, DEV_GFS_PHYS not defined) for one column of one tracer: negative mixing ratios
+// borrow mass from the layer above, then below; columns that needed it get the non-local rescaling of :113-135.  q, dp: 1..km
+void fillz_column(int km, std::vector<double>& q, const std::vector<double>& dp) {
+  auto pos = [](double x) { return x > 0. ? x : 0.; };   // max(0., x)
+  if (q[1] < 0.) { q[2] = q[2] + q[1] * dp[1] / dp[2]; q[1] = 0.; }
+  bool zfix = false;
+  for (int k = 2; k <= km - 1; k++) {
+    if (q[k] < 0.) {
+      zfix = true;
+      if (q[k - 1] > 0.) {   // borrow from above
+        const double dq = std::min(q[k - 1] * dp[k - 1], -q[k] * dp[k]);
+        q[k - 1] = q[k - 1] - dq / dp[k - 1];
+        q[k] = q[k] + dq / dp[k];
+      }
+      if (q[k] < 0. && q[k + 1] > 0.) {   // borrow from below
+        const double dq = std::min(q[k + 1] * dp[k + 1], -q[k] * dp[k]);
+        q[k + 1] = q[k + 1] - dq / dp[k + 1];
+        q[k] = q[k] + dq / dp[k];
+      }
+    }
+  }
+  if (q[km] < 0. && q[km - 1] > 0.) {
+    zfix = true;
+    const double qup = q[km - 1] * dp[km - 1], qly = -q[km] * dp[km];
+    const double dup = std::min(qly, qup);
+    q[km - 1] = q[km - 1] - dup / dp[km - 1];
+    q[km] = q[km] + dup / dp[km];
+  }
+  if (zfix) {
+    std::vector<double> dm(km + 1, 0.);
+    double sum0 = 0.;
+    for (int k = 2; k <= km; k++) { dm[k] = q[k] * dp[k]; sum0 = sum0 + dm[k]; }
+    if (sum0 > 0.) {
+      double sum1 = 0.;
+      for (int k = 2; k <= km; k++) sum1 = sum1 + pos(dm[k]);
+      const double fac = sum0 / sum1;
+      for (int k = 2; k <= km; k++) q[k] = pos(fac * dm[k] / dp[k]);
+    }
+  }
+}
+
 // stand-alone column operator on FV3_WORK_Q (compute domain): pe1 = FV3_PE of the context, pe2 = ak + bk * pe1(km+1)
 // mode 0: map_scalar (iv, kord, qmin), 1: map1_ppm (iv, kord; qs = FV3_WS when iv = -2), 2: map1_q2 (iv = 0, kord)
 int remap_work_q(V3 q, V2 ws, double* pe, const std::vector<double>& ak, const std::vector<double>& bk, const fv3_flags_t& f, const Bd& bd,
@@ -410,9 +452,22 @@ int remap_work_q(V3 q, V2 ws, double* pe, const std::vector<double>& ak, const s
   return bad ? -2 : 0;
 }
 
-// fv_mapz.F90:56-845 on one face; use_tracer: the number of tracers (F.qtr) remapped with kord_tr (map1_q2 for nq <= 5, :398-408; mapn_tracer for nq > 5, :390-393).
+// fillz of q with the thicknesses dp on the compute domain (fv3o_fillz)
+void fillz(V3 q, V3 dp, const Bd& bd) {
+  const int km = bd.npz;
+#pragma omp parallel for schedule(static)
+  for (int j = bd.js; j <= bd.je; j++)
+    for (int i = bd.is; i <= bd.ie; i++) {
+      std::vector<double> col(km + 2), d(km + 2);
+      for (int k = 1; k <= km; k++) { col[k] = q(i, j, k); d[k] = dp(i, j, k); }
+      fillz_column(km, col, d);
+      for (int k = 1; k <= km; k++) q(i, j, k) = col[k];
+    }
+}
+
+// fv_mapz.F90:56-845 on one face; fill: flagstruct%fill (fillz after each tracer, :391 / fv_operators.F90:337); use_tracer: the number of tracers (F.qtr) remapped with kord_tr (map1_q2 for nq <= 5, :398-408; mapn_tracer for nq > 5, :390-393).
 int lagrangian_to_eulerian(const L2EFields& F, const std::vector<double>& ak, const std::vector<double>& bk, const fv3_flags_t& f, const Bd& bd,
-                           int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr, int sphum, double r_vir) {
+                           int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr, int sphum, double r_vir, int fill) {
   if (f.moist_kappa || kord_wz < 0) return -2;
   if (sphum >= use_tracer) return -1;
   const int km = bd.npz, is = bd.is, ie = bd.ie, js = bd.js, je = bd.je;
@@ -460,6 +515,7 @@ int lagrangian_to_eulerian(const L2EFields& F, const std::vector<double>& ak, co
           for (int k = 1; k <= km; k++) col[k] = qtr(i, j, k);
           rc = remap_field(km, pe1, pe2, col, 0., 0, kord_tr, 0., true, dp2.data(), use_tracer > 5);   // nq > 5: mapn_tracer (:390-393)
           if (rc) bad = 1;
+          if (fill && !rc) fillz_column(km, col, dp2);
           for (int k = 1; k <= km; k++) qtr(i, j, k) = col[k];
         }
         // 3) w with the lower boundary condition ws, then delz (:411-433)

@@ -233,3 +233,59 @@ def test_ppm_profile_known_answer_quadratic_profile(kord, mode):
     assert lev[3:NPZ - 3].max() < 2e-15, lev
     assert lev.max() < 1e-5, lev
     oc.close()
+
+
+def test_fillz_properties_and_known_answer():
+    """fillz (fv_fill.F90:34-139): a non-negative tracer is left untouched bit for bit; negative layers borrow from their vertical
+    neighbours, so the column integral sum_k q dp is kept and -- wherever the column total is positive -- the result is
+    non-negative; a hand-computed column as the known answer."""
+    case, oc = _cube(substeps=0)
+    e = oc.eng[3]
+    dp = _sec(e, "DELP")
+    rng = np.random.default_rng(5)
+    q = rng.uniform(0.0, 1.0, (NPZ, N, N))
+    _set_q(e, q)
+    e.call("fillz")
+    assert np.array_equal(_sec(e, "WORK_Q"), q)
+    q = rng.uniform(-0.3, 1.0, (NPZ, N, N)) * rng.integers(0, 2, (NPZ, N, N))          # negative layers next to empty and full ones
+    q[:, 0, 0] = -np.abs(q[:, 0, 0])                                                    # one column without any mass to borrow
+    _set_q(e, q)
+    e.call("fillz")
+    out = _sec(e, "WORK_Q")
+    s0, s1 = (q * dp).sum(0), (out * dp).sum(0)
+    assert np.abs(s1 - s0).max() / np.abs(s0).max() < 1e-14
+    fixable = (q[1:] * dp[1:]).sum(0) > 0.0                                             # (the non-local fix works on layers 2..km)
+    assert fixable.sum() > 100 and not fixable[0, 0]
+    assert out[1:][:, fixable].min() >= 0.0
+    assert out[0].min() > -1e-16            # (layer 1 lends to layer 2 after its own test: q1 - (q1 dp1) / dp1 may round to -1 ulp)
+    assert np.array_equal(out[:, 0, 0], np.concatenate([[0.0], q[1:, 0, 0]]) + np.concatenate([[0.0, q[0, 0, 0] * dp[0, 0, 0] / dp[1, 0, 0]], np.zeros(NPZ - 2)]))
+    # known answer on layers of equal thickness: layer 3 borrows 0.5 from layer 2 (above) and the rest from layer 4 (below)
+    full = e.get("DELP"); full[...] = 100.0; e.put("DELP", full)
+    col = np.array([1.0, 0.5, -1.0, 2.0] + [0.25] * (NPZ - 4))
+    _set_q(e, np.broadcast_to(col[:, None, None], (NPZ, N, N)).copy())
+    e.call("fillz")
+    want = np.array([1.0, 0.0, 0.0, 1.5] + [0.25] * (NPZ - 4))
+    assert np.abs(_sec(e, "WORK_Q") - want[:, None, None]).max() < 1e-15
+    oc.close()
+
+
+def test_lagrangian_to_eulerian_with_fill_keeps_the_tracer_mass_and_removes_negatives():
+    case, oc = _cube(substeps=2)
+    e = oc.eng[2]
+    q = np.zeros((NPZ, N, N)); q[4:7] = 1.0; q[10] = 1e-3
+    dp0 = _sec(e, "DELP")
+    outs = {}
+    for fill in (0, 1):
+        oc2_case, oc2 = _cube(substeps=2)
+        e2 = oc2.eng[2]
+        _set_q(e2, q)
+        e2.call("set_tracer_fill", fill)
+        e2.call("lagrangian_to_eulerian", 0, 9, 9, -9, 1, 6)       # kord_tr = 6: the unlimited parabola undershoots
+        outs[fill] = (_sec(e2, "WORK_Q"), _sec(e2, "DELP"))
+        oc2.close()
+    (a, dpa), (b, dpb) = outs[0], outs[1]
+    assert a.min() < -1e-6, "the test needs undershoots to fill"
+    assert b.min() > -1e-16
+    assert np.abs((a * dpa).sum(0) - (b * dpb).sum(0)).max() / (a * dpa).sum(0).max() < 1e-13
+    assert np.abs((b * dpb).sum(0) - (q * dp0).sum(0)).max() / (q * dp0).sum(0).max() < 1e-13
+    oc.close()
