@@ -419,6 +419,8 @@ int fv3_select_tracer(fv3_ctx* c, int iq) {
   c->fld[FV3_WORK_Q] = c->tracers[iq];
   return 0;
 }
+int fv3_set_tracer_fill(fv3_ctx* c, int on) { if (!c) return -1; c->tracer_fill = on != 0; return 0; }
+int fv3_fillz(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_fillz(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_omega_new(fv3_ctx* c, int phase, double dt) { STAGE_PROLOGUE(c) int rc = stage_omega_new(c, phase, dt); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_omega_begin(fv3_ctx* c) { STAGE_PROLOGUE(c) int rc = stage_omega_begin(c); if (rc) return rc; STAGE_EPILOGUE(c) }
 int fv3_omega_end(fv3_ctx* c, double dt) { STAGE_PROLOGUE(c) int rc = stage_omega_end(c, dt); if (rc) return rc; STAGE_EPILOGUE(c) }

@@ -140,6 +140,7 @@ struct fv3_ctx {
   // tracers (fv3_set_num_tracers): every tracer array incl. the one FV3_WORK_Q was created with; fld[FV3_WORK_Q] always aliases
   // tracers[tracer_sel] (fv3_select_tracer), so every single-tracer entry point works on the selected one
   std::vector<double*> tracers; int tracer_sel = 0;
+  int tracer_fill = 0;             // flagstruct%fill: fillz after each remapped tracer (fv3_set_tracer_fill)
   double* d_pem = nullptr;         // interface pressures before the last substep (omega diagnostic), npz + 1 planes, built on first use
   double* d_divg2 = nullptr;       // external-mode damping term (d_ext > 0), one plane, built on first use
   double* d_akbk = nullptr;        // ak(0:km), bk(0:km) for the vertical remap (remap.cu), built on first use
@@ -180,6 +181,7 @@ int stage_omega_end(fv3_ctx* c, double dt);
 int stage_ext_mode_prepare(fv3_ctx* c);
 int stage_ext_mode_divg2(fv3_ctx* c);
 int stage_remap_work_q(fv3_ctx* c, int mode, int iv, int kord, double qmin);
+int stage_fillz(fv3_ctx* c);
 int stage_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr, int sphum = -1,
                                  double r_vir = 0.);
 int stage_fv_tp_2d(fv3_ctx* c, int nk, int hord, int use_mfx, int use_mass, int nord, double damp_c);

@@ -5,7 +5,7 @@
 // cs_limiters (:1303-1378), ppm_profile / ppm_limiters (:1382-1723).  Built: remap_te = F, moist_kappa = F, consv = 0 (no energy
 // fixer), dry air or water vapour without condensates, abs(kord) in 8..15 (cs / scalar profiles) and 1..7 (ppm_profile: separate
 // instantiations of the kernels, so the kernels of the default schemes do not carry it), kord_wz > 0 (iv = -2), the tracers of the
-// context's table (no fillz); anything else is an error (-2), never a silent fall-back.
+// context's table, fillz after each of them when fv3_set_tracer_fill is on (flagstruct%fill); anything else is an error (-2), never a silent fall-back.
 //
 // Design: column-parallel like the vertical solvers -- one thread per column, consecutive threads on consecutive i, so every
 // level access is a coalesced row segment of the [k][NJ][NI] arrays.  The reconstruction (a4(1:4), the interface values, the
@@ -162,6 +162,15 @@ __global__ void __launch_bounds__(CB) k_remap_work_q(Lay L, L2E a, Scr S, int mo
   remap_field<PPM>(C, km, pe1, pe2, a.qtr + o, iv == -2 ? a.ws[o] : 0., iv, kord, qmin, mode != 1);
 }
 
+// fillz (flagstruct%fill: fv_mapz.F90:391, fv_operators.F90:337) of one tracer with the layer thicknesses dp, one thread per column
+__global__ void __launch_bounds__(CB) k_fillz(Lay L, double* q, const double* dp) {
+  const int nx = L.ie - L.is + 1, ny = L.je - L.js + 1;
+  const int t = blockIdx.x * CB + threadIdx.x;
+  if (t >= nx * ny) return;
+  const long long o = LIDX(L, L.is + t % nx, L.js + t / nx);
+  fillz_column(L.npz, q + o, dp + o, L.plane);
+}
+
 // abs(kord) in 8..15: cs_profile / scalar_profile; 1..7: ppm_profile (the PPM instantiations of the kernels)
 int check_kord(fv3_ctx* c, int kord, const char* what, bool* ppm) {
   const int ak = kord < 0 ? -kord : kord;
@@ -190,6 +199,17 @@ int fill(fv3_ctx* c, L2E& a, Scr& S) {
 }
 
 }  // namespace
+
+// fillz of FV3_WORK_Q with the thicknesses FV3_DELP (compute domain)
+int stage_fillz(fv3_ctx* c) {
+  StageScope ts(c, "REMAP_OP");
+  if (c->L.npz < 3) return fv3_fail(c, -2, "fillz: npz >= 3");
+  const int n = (c->L.ie - c->L.is + 1) * (c->L.je - c->L.js + 1);
+  k_fillz<<<(n + CB - 1) / CB, CB, 0, c->stream>>>(c->L, c->fld[FV3_WORK_Q], c->fld[FV3_DELP]);
+  c->launches++;
+  FV3_CUDA(c, cudaGetLastError());
+  return 0;
+}
 
 int stage_remap_work_q(fv3_ctx* c, int mode, int iv, int kord, double qmin) {
   StageScope ts(c, "REMAP_OP");
@@ -244,6 +264,7 @@ int stage_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kor
       a.qtr = c->tracers[iq];
       k_remap_cells<1, PPM><<<gc, CB, 0, c->stream>>>(L, a, S);
       c->launches++;
+      if (c->tracer_fill) { k_fillz<<<gc, CB, 0, c->stream>>>(L, a.qtr, a.delp); c->launches++; }   // delp holds dp2 since PART 0
     }
     if (!f.hydrostatic) { k_remap_cells<2, PPM><<<gc, CB, 0, c->stream>>>(L, a, S); c->launches++; }
     k_remap_cells<3, false><<<gc, CB, 0, c->stream>>>(L, a, S);   // (pressure variables only: no profile)

@@ -1,5 +1,5 @@
 // Column operators of the vertical remap (fv_operators.F90: scalar_profile / cs_profile :546-1300, cs_limiters :1303-1378,
-// ppm_profile / ppm_limiters :1382-1723, the
+// ppm_profile / ppm_limiters :1382-1723; fv_fill.F90: fillz :34-139; the
 // mapping loop of map_scalar / map1_ppm / map1_q2 / mapn_tracer :88-132, 183-227, 276-336, 399-441) for ONE column whose
 // reconstruction arrays are strided (level stride = plane).  __host__ __device__: remap.cu runs them one thread per column; the
 // CPU suite runs the same source on the host against the oracle (tests/host_remap_test.cu, tests/test_host_remap.py).
@@ -565,6 +565,57 @@ RMP_HD inline void remap_field(const Col& C, int km, const P1& pe1, const P2& pe
   } else
   profile(C, km, pe1, qs, iv, kord < 0 ? -kord : kord, qmin, scalar);
   map_column(C, km, pe1, pe2, [&](int k, double v) { LV(fld, k) = v; }, mapn);
+}
+
+// fillz (fv_fill.F90:34-139; the default branch, DEV_GFS_PHYS not defined) for one column of one tracer, in place on q with the
+// layer thicknesses dp (level k at [(k-1)*plane]): negative mixing ratios borrow mass from the layer above, then below; columns
+// that needed it get the non-local rescaling of :113-135 (dm(k) = q(k) dp(k) is formed again in each of its three passes instead of
+// being kept in a column array: the same product).  The three layers a step works on are carried in registers.
+RMP_HD inline void fillz_column(int km, double* q, const double* dp, long long plane) {
+  auto Q = [&](int k) -> double& { return q[(long long)(k - 1) * plane]; };
+  auto DP = [&](int k) { return dp[(long long)(k - 1) * plane]; };
+  auto pos = [](double x) { return x > 0. ? x : 0.; };   // max(0., x)
+  double dpm = DP(1), dp0 = DP(2);         // dp(k - 1), dp(k)
+  double qm = Q(1), q0 = Q(2);             // q(k - 1), q(k)
+  if (qm < 0.) { q0 = q0 + qm * dpm / dp0; qm = 0.; }
+  bool zfix = false;
+  for (int k = 2; k <= km - 1; k++) {
+    const double dpp = DP(k + 1);
+    double qp = Q(k + 1);
+    if (q0 < 0.) {
+      zfix = true;
+      if (qm > 0.) {                       // borrow from above
+        const double dq = dmin(qm * dpm, -q0 * dp0);
+        qm = qm - dq / dpm;
+        q0 = q0 + dq / dp0;
+      }
+      if (q0 < 0. && qp > 0.) {            // borrow from below
+        const double dq = dmin(qp * dpp, -q0 * dp0);
+        qp = qp - dq / dpp;
+        q0 = q0 + dq / dp0;
+      }
+    }
+    Q(k - 1) = qm;
+    qm = q0; q0 = qp; dpm = dp0; dp0 = dpp;
+  }
+  if (q0 < 0. && qm > 0.) {                // bottom layer (qm = q(km - 1), q0 = q(km))
+    zfix = true;
+    const double qup = qm * dpm, qly = -q0 * dp0;
+    const double dup = dmin(qly, qup);
+    qm = qm - dup / dpm;
+    q0 = q0 + dup / dp0;
+  }
+  Q(km - 1) = qm; Q(km) = q0;
+  if (zfix) {
+    double sum0 = 0.;
+    for (int k = 2; k <= km; k++) sum0 = sum0 + Q(k) * DP(k);
+    if (sum0 > 0.) {
+      double sum1 = 0.;
+      for (int k = 2; k <= km; k++) sum1 = sum1 + pos(Q(k) * DP(k));
+      const double fac = sum0 / sum1;
+      for (int k = 2; k <= km; k++) { const double d = DP(k); Q(k) = pos(fac * (Q(k) * d) / d); }
+    }
+  }
 }
 
 }  // namespace rmp

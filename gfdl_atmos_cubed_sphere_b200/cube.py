@@ -102,6 +102,11 @@ class CudaCube:
         for t in self.tiles:
             self.eng[t].call("set_num_tracers", int(nq))
 
+    def set_tracer_fill(self, on):
+        """flagstruct%fill: fillz after each remapped tracer (fv3_set_tracer_fill on every face)"""
+        for t in self.tiles:
+            self.eng[t].call("set_tracer_fill", int(bool(on)))
+
     def select_tracer(self, iq):
         for t in self.tiles:
             self.eng[t].call("select_tracer", int(iq))

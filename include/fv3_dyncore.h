@@ -233,6 +233,11 @@ int fv3_lagrangian_to_eulerian(fv3_ctx *ctx, int last_step, int kord_mt, int kor
 int fv3_lagrangian_to_eulerian_qv(fv3_ctx *ctx, int last_step, int kord_mt, int kord_wz, int kord_tm, int use_tracer, int kord_tr, int sphum,
                                   double r_vir);
 int fv3_remap_work_q(fv3_ctx *ctx, int mode, int iv, int kord, double qmin);
+/* flagstruct%fill (fv_arrays.F90 `fill`): when on, fv3_lagrangian_to_eulerian / fv3_fv_dynamics apply fillz (fv_fill.F90:34-139, the
+ * default branch -- DEV_GFS_PHYS not defined) to each tracer after its remap (fv_mapz.F90:391, fv_operators.F90:337).  Off by
+ * default.  fv3_fillz: the operator alone on FV3_WORK_Q with the layer thicknesses FV3_DELP, compute domain. */
+int fv3_set_tracer_fill(fv3_ctx *ctx, int on);
+int fv3_fillz(fv3_ctx *ctx);
 /* dyn_core.F90:1305-1356: filtered heat_source -> pt (levels 1..n_con, limited by delt_max); part of fv3_dyn_core */
 int fv3_dcon_heating(fv3_ctx *ctx, double bdt);
 int fv3_geopk(fv3_ctx *ctx, int cg);

@@ -350,6 +350,9 @@ class OracleCube:
     def select_tracer(self, iq):
         self.all("select_tracer", iq)
 
+    def set_tracer_fill(self, on):
+        self.all("set_tracer_fill", int(bool(on)))
+
     def tracer_2d(self, hord):
         """tracer_2d_1L (model/fv_tracer2d.F90:49-295; all tracers of the engines, trdm = 0, id_divg_mean = 0) on the oracle side: the pointwise
         statements in NumPy with the reference's operation order, the fluxes from the oracle's fv_tp_2d, the q halo updates

@@ -2,6 +2,7 @@
 // Driven by tests/test_host_remap.py, which compares the result with the oracle (oracle/remap.cpp).  No GPU involved.
 //   stdin : int km, ncol, iv, kord, scalar, mapn; double qmin; then doubles pe1[km+1][ncol], pe2[km+1][ncol], q[km][ncol], qs[ncol]
 //           (level-major like the device planes: level stride = ncol);  stdout: double q[km][ncol] remapped in place
+//   iv = 99: fillz instead (fillz_column), with the layer thicknesses in the first km levels of the pe2 block
 #include <cstdio>
 #include <vector>
 #include "../gfdl_atmos_cubed_sphere_b200/csrc/remap_col.cuh"
@@ -22,6 +23,7 @@ int main() {
     const double *p1 = pe1.data() + c, *p2 = pe2.data() + c;
     auto P1 = [&](int k) { return p1[(size_t)(k - 1) * ncol]; };
     auto P2 = [&](int k) { return p2[(size_t)(k - 1) * ncol]; };
+    if (iv == 99) { rmp::fillz_column(km, q.data() + c, p2, (long long)ncol); continue; }
     rmp::remap_field<true>(C, km, P1, P2, q.data() + c, qs[c], iv, kord, qmin, scalar != 0, mapn != 0);
   }
   fwrite(q.data(), sizeof(double), q.size(), stdout);

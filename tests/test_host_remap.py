@@ -60,3 +60,31 @@ def test_host_execution_of_the_cuda_remap_matches_the_oracle_bit_for_bit(exe, st
     assert r.returncode == 0, r.stderr
     got = np.frombuffer(r.stdout, dtype=np.float64).reshape(km, n, n)
     assert np.array_equal(got, want), float(np.abs(got - want).max())
+
+
+def test_host_execution_of_the_cuda_fillz_matches_the_oracle_bit_for_bit(exe, state):
+    """fillz_column (csrc/remap_col.cuh, what k_fillz runs per column) on the host against oracle/remap.cpp::fillz_column: columns
+    with negative layers next to empty and full ones, a column with nothing to borrow, non-uniform thicknesses"""
+    case, oc = state
+    e = oc.eng[6]
+    n, km = T.N, T.NPZ
+    rng = np.random.default_rng(77)
+    q0 = e.get("WORK_Q")
+    dp = T._sec(e, "DELP")
+    q = rng.uniform(-0.4, 1.0, (km, n, n)) * rng.integers(0, 2, (km, n, n))
+    q[:, 0, 0] = -np.abs(q[:, 0, 0])
+    q[:, 1, :] = np.abs(q[:, 1, :])                  # a row that needs nothing
+    q[-1, 2, :] = -0.2; q[-2, 2, :] = 0.5            # the bottom-layer branch
+    T._set_q(e, q)
+    e.call("fillz")
+    want = T._sec(e, "WORK_Q")
+    e.put("WORK_Q", q0)
+    assert (want != q).any()
+    blob = struct.pack("6i", km, n * n, 99, 0, 0, 0) + struct.pack("d", 0.0) + np.zeros((km + 1, n * n)).tobytes() + \
+        np.concatenate([dp.reshape(km, -1), np.zeros((1, n * n))]).tobytes() + np.ascontiguousarray(q).reshape(km, -1).tobytes() + \
+        np.zeros(n * n).tobytes()
+    r = subprocess.run([exe], input=blob, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    got = np.frombuffer(r.stdout, dtype=np.float64).reshape(km, n, n)
+    assert np.array_equal(got, want), float(np.abs(got - want).max())
+    assert np.array_equal(np.signbit(got), np.signbit(want))
