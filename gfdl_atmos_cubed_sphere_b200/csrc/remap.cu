@@ -239,9 +239,11 @@ int stage_lagrangian_to_eulerian(fv3_ctx* c, int last_step, int kord_mt, int kor
   if (!f.hydrostatic) { rc = check_kord(c, kord_wz, "kord_wz", &ppm); if (rc) return rc; }
   if (use_tracer < 0 || use_tracer > 64) return fv3_fail(c, -1, "remap: use_tracer (the number of tracers to remap) in 0..64");
   if (use_tracer) {
-    rc = check_kord(c, kord_tr, "kord_tr", &ppm); if (rc) return rc;
     if (kord_tr < 0) return fv3_fail(c, -2, "remap: kord_tr must be positive");
-    if (kord_tr <= 7 && use_tracer > 5) return fv3_fail(c, -2, "remap: kord_tr <= 7 with more than 5 tracers (mapn_tracer has no ppm_profile branch)");
+    // more than 5 tracers: mapn_tracer (fv_operators.F90:262-273) has no ppm_profile branch -- it calls scalar_profile whatever
+    // kord is, and scalar_profile treats abs(kord) 0..8 alike (`case (0:8)`, :756; abs(kord) > 9 / >= 14 false, <= 13 true)
+    if (use_tracer > 5 && kord_tr >= 1 && kord_tr <= 7) kord_tr = 8;
+    rc = check_kord(c, kord_tr, "kord_tr", &ppm); if (rc) return rc;
   }
   if (ppm && c->L.npz < 5) return fv3_fail(c, -2, "remap: ppm_profile (kord <= 7) needs npz >= 5");
   L2E a{}; Scr S{};

@@ -211,7 +211,8 @@ int fv3_pt_to_theta(fv3_ctx *ctx, double zvir);
  * pk, ws and omga current): delp <- ak/bk hybrid levels, pt (theta_v in; theta_v out, or T_v when last_step), w, delz, u, v,
  * [the first use_tracer tracers of the context], pe, peln, pk, pkz remapped; omga interpolated when last_step.  Built: remap_te = F, moist_kappa = F,
  * consv = 0 (no energy fixer), dry air (the last-step T_v -> T conversion is the identity), abs(kord_*) in 8..15 (cs_profile /
- * scalar_profile) or 1..7 (ppm_profile, fv_operators.F90:1382-1723; npz >= 5, at most 5 tracers: mapn_tracer has no such branch),
+ * scalar_profile) or 1..7 (ppm_profile, fv_operators.F90:1382-1723; npz >= 5; with more than 5 tracers kord_tr 1..7 acts as 8, as
+ * in mapn_tracer, which calls scalar_profile whatever kord is),
  * kord_wz > 0; everything else returns -2.  kord_tm < 0: T_v is mapped in log p (map_scalar), > 0: theta_v in p.
  * fv3_remap_work_q: the column operators alone on FV3_WORK_Q, from the layers of FV3_PE to the hybrid levels -- mode 0 map_scalar
  * (fv_operators.F90:40), 1 map1_ppm (:137; iv = -2 takes its lower boundary value from FV3_WS), 2 map1_q2 (:352). */

@@ -378,9 +378,10 @@ int remap_field(int km, const std::vector<double>& pe1, const std::vector<double
   std::vector<double> dp1(km + 2, 0.);
   for (int k = 1; k <= km; k++) { dp1[k] = pe1[k + 1] - pe1[k]; q4(1, k) = q[k]; }
   // kord > 7: scalar_profile / cs_profile, else ppm_profile (:86-90, 181-185, 394-398)
-  // (the callers pass abs(kord); mapn_tracer has no ppm_profile branch, :262-273)
-  const int ak = std::abs(kord);
-  if (mapn && ak <= 7) return -2;
+  // (the callers pass abs(kord); mapn_tracer has no ppm_profile branch, :262-273: it calls scalar_profile whatever kord is, whose
+  //  interior `select case (abs(kord))` treats 0..8 alike, :756, as do the tests abs(kord) > 9 / >= 14 / <= 13)
+  int ak = std::abs(kord);
+  if (mapn && ak <= 7) ak = 8;
   const int rc = ak > 7 ? profile(qs, q4, dp1, km, iv, ak, qmin, scalar) : ppm_profile(q4, dp1, km, iv, ak);
   if (rc) return rc;
   map_column(km, pe1, q4, dp1, km, pe2, q, dp2, mapn);

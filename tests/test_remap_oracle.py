@@ -289,3 +289,21 @@ def test_lagrangian_to_eulerian_with_fill_keeps_the_tracer_mass_and_removes_nega
     assert np.abs((a * dpa).sum(0) - (b * dpb).sum(0)).max() / (a * dpa).sum(0).max() < 1e-13
     assert np.abs((b * dpb).sum(0) - (q * dp0).sum(0)).max() / (q * dp0).sum(0).max() < 1e-13
     oc.close()
+
+
+def test_more_than_five_tracers_with_kord_tr_below_8_follow_mapn_tracer():
+    """nq > 5: fv_mapz calls mapn_tracer, which has no ppm_profile branch -- scalar_profile runs whatever kord_tr is and treats
+    abs(kord) 0..8 alike (fv_operators.F90:262-273, 756): kord_tr = 5 must give what kord_tr = 8 gives, and not what the
+    ppm_profile of map1_q2 (nq <= 5) gives."""
+    q = np.zeros((NPZ, N, N)); q[4:7] = 1.0; q[10] = 1e-3
+    res = {}
+    for nq, kord_tr in [(6, 5), (6, 8), (1, 5)]:
+        case, oc = _cube(substeps=2)
+        e = oc.eng[2]
+        e.call("set_num_tracers", nq)
+        _set_q(e, q)
+        e.call("lagrangian_to_eulerian", 0, 9, 9, -9, nq, kord_tr)
+        res[(nq, kord_tr)] = _sec(e, "WORK_Q")
+        oc.close()
+    assert np.array_equal(res[(6, 5)], res[(6, 8)])
+    assert np.abs(res[(6, 5)] - res[(1, 5)]).max() > 1e-6

@@ -78,3 +78,29 @@ def test_fv_dynamics_with_fill():
             _assert(H.compare(oc.eng[t], gc.eng[t], reg), 1e-9)
             assert H.sub(gc.eng[t], "WORK_Q", gc.eng[t].get("WORK_Q"), 1, N, 1, N).min() > -1e-16
     oc.close(); gc.close()
+
+
+def test_six_tracers_with_kord_tr_below_8_follow_mapn_tracer():
+    """nq > 5 and kord_tr = 5: mapn_tracer runs scalar_profile whatever kord is (fv_operators.F90:262-273; 0..8 alike, :756) -- a
+    host-side choice of the kernels of scheme 8; against the oracle, with fill on."""
+    case, oc, gc = _pair()
+    b = case.bounds
+    reg = {"WORK_Q": (b["is_"], b["ie"], b["js"], b["je"])}
+    rng = np.random.default_rng(8)
+    for cube in (oc, gc):
+        cube.set_num_tracers(6)
+        cube.set_tracer_fill(1)
+    for t in oc.tiles:
+        eo, eg = oc.eng[t], gc.eng[t]
+        for iq in range(6):
+            q = rng.uniform(0.0, 1.0, eo.shape("WORK_Q")) ** 4 * (iq + 1)
+            for e in (eo, eg):
+                e.call("select_tracer", iq); e.put("WORK_Q", q)
+        for e in (eo, eg):
+            e.call("select_tracer", 0)
+            e.call("lagrangian_to_eulerian", 0, 9, 9, -9, 6, 5)
+    for iq in range(6):
+        oc.select_tracer(iq); gc.select_tracer(iq)
+        for t in oc.tiles:
+            _assert(H.compare(oc.eng[t], gc.eng[t], reg), TOL)
+    oc.close(); gc.close()
