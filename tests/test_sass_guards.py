@@ -43,3 +43,22 @@ def test_general_instantiation_exists_and_is_separate():
     """FAM = 2 carries the less common schemes out of line (calls with by-reference results => it does use the stack)."""
     ins = _sass("_Z15k_dsw_transportILi2ELb0EEv3Lay7DevGridN3tpt7TileMapE5DswTr")
     assert any(re.match(r"(LDL|STL)\b", i) for i in ins)
+
+
+def test_remap_kernels_keep_their_occupancy_budget():
+    """The remap kernels are bound by occupancy x memory-level parallelism (csrc/remap.cu header): the in-step kernels are held to 64
+    registers (launch bounds: 8 CTAs of 128 threads per SM) and a stack of at most 128 bytes -- a tracer loop inside the kernel once
+    cost 480 bytes of stack and 20 % of the remap time (profiles/r2_dsw_summary.md).  Both sets of instantiations (cs / scalar
+    profiles; with ppm_profile) and k_fillz are checked."""
+    if not (os.path.exists(LIB) and os.path.exists(CUOBJDUMP)):
+        pytest.skip("library or cuobjdump not available")
+    out = subprocess.run([CUOBJDUMP, "--dump-resource-usage", LIB], capture_output=True, text=True).stdout
+    usage = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
+        usage[m.group(1)] = (int(m.group(2)), int(m.group(3)))
+    step = {k: v for k, v in usage.items() if re.search(r"k_remap_(cells|wind)", k)}
+    assert len(step) == 11, sorted(step)      # cells<0..2> x {cs, ppm} + cells<3> + wind<0, 1> x {cs, ppm}
+    for k, (reg, stack) in step.items():
+        assert reg <= 64 and stack <= 128, (k, reg, stack)
+    fz = [v for k, v in usage.items() if "k_fillz" in k]
+    assert len(fz) == 1 and fz[0][0] <= 64 and fz[0][1] == 0, fz
